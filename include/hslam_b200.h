@@ -1,0 +1,309 @@
+/*
+ * hslam_b200.h — C ABI of the B200-native photometric Gauss-Newton hot path.
+ *
+ * This is the drop-in boundary for the DSO-style hot path of AUBVRL/H-SLAM
+ * (namespace FSLAM in the reference).  The reference has no FFI of its own
+ * (SURVEY.md §8b): the path is reached through C++ member functions.  Every
+ * entry point below therefore cites the reference member function (file:line,
+ * relative to the reference root) whose work it replaces; the C++ host shim in
+ * h-slam_b200/host/ keeps those member-function names and forwards here.
+ *
+ * Conventions
+ *  - POD only, no C++/torch types.  Every function returns 0 on success and a
+ *    negative hslam_status on failure; hslam_last_error() (thread-local) holds
+ *    the message.  Nothing throws across this boundary.
+ *  - There is NO CPU fallback: if no CUDA device is usable every compute entry
+ *    point returns HSLAM_ERR_CUDA.
+ *  - A handle is single-threaded; different handles may be used concurrently
+ *    from different host threads (the reference runs two CoarseTracker
+ *    instances on two threads, Src/System.cpp:127-133).
+ *  - Matrices crossing the boundary are COLUMN-MAJOR (Eigen default), except
+ *    rigid transforms which are 12 doubles: R row-major (9) then t (3).
+ *  - "host pointer" / "device pointer" is stated per argument.
+ */
+#ifndef HSLAM_B200_H
+#define HSLAM_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define HSLAM_ABI_VERSION 1
+#define HSLAM_MAX_PYR_LEVELS 10   /* CoarseTracker::PYR_LEVELS, Include/CoarseTracker.h:32 */
+#define HSLAM_PATTERN_NUM 8       /* ChosenPattern 8, Include/GlobalTypes.h:33,181 */
+#define HSLAM_CPARS 4             /* Include/GlobalTypes.h:223 */
+#define HSLAM_MAX_FRAMES 16       /* window size cap of this build (reference default 7, Src/Settings.cpp:58) */
+#define HSLAM_PRECALC_STRIDE 28   /* floats per (host,target) record, see hslam_window.precalc */
+#define HSLAM_J_FLOATS 74         /* sizeof(RawResidualJacobian)/4, Include/OptimizationClasses.h:48-77 */
+
+typedef enum {
+  HSLAM_OK = 0,
+  HSLAM_ERR_ARG = -1,      /* bad argument (null, size, level out of range) */
+  HSLAM_ERR_CUDA = -2,     /* CUDA runtime error or no device */
+  HSLAM_ERR_STATE = -3,    /* call order violated (e.g. accumulate before set_window) */
+  HSLAM_ERR_NOMEM = -4,
+  HSLAM_ERR_NCCL = -5
+} hslam_status;
+
+/* ResState, Include/GlobalTypes.h (enum ResState {IN=0, OOB, OUT}) */
+#define HSLAM_RES_IN 0
+#define HSLAM_RES_OOB 1
+#define HSLAM_RES_OUT 2
+
+/* Settings consumed by the hot path (Src/Settings.cpp; SURVEY.md §5 "Config"). */
+typedef struct hslam_params {
+  float huberTH;                 /* setting_huberTH = 9                 (Settings.cpp:68)  */
+  float coarseCutoffTH;          /* setting_coarseCutoffTH = 20         (Settings.cpp:77)  */
+  float outlierTHSumComponent;   /* setting_outlierTHSumComponent=2500  (Settings.cpp:64)  */
+  float affineOptModeA;          /* 1e12  (Settings.cpp:109); <0 fixes a */
+  float affineOptModeB;          /* 1e8   (Settings.cpp:110); <0 fixes b */
+  float scale_xi_rot;            /* SCALE_XI_ROT   = 1    (GlobalTypes.h:35) */
+  float scale_xi_trans;          /* SCALE_XI_TRANS = 0.5  (GlobalTypes.h:36) */
+  float scale_a;                 /* SCALE_A = 10          (GlobalTypes.h:40) */
+  float scale_b;                 /* SCALE_B = 1000        (GlobalTypes.h:41) */
+  float scale_f;                 /* SCALE_F = 50          (GlobalTypes.h:37) */
+  float scale_c;                 /* SCALE_C = 50          (GlobalTypes.h:38) */
+  float scale_idepth;            /* SCALE_IDEPTH = 1      (GlobalTypes.h:34) */
+  int   max_tracker_iterations[5]; /* {10,20,50,50,50}    (CoarseTracker.cpp:518) */
+} hslam_params;
+
+typedef struct hslam_ctx hslam_ctx;
+typedef struct hslam_frame hslam_frame;
+typedef struct hslam_tracker hslam_tracker;
+typedef struct hslam_ba hslam_ba;
+
+const char* hslam_last_error(void);
+int  hslam_abi_version(void);
+void hslam_params_default(hslam_params* p);
+
+/* One context = one CUDA device + one stream.  Replaces the three
+ * IndexThreadReduce pools of System (Src/System.cpp:33-34,51). */
+int hslam_create(const hslam_params* params /*nullable => defaults*/, int device, hslam_ctx** out);
+int hslam_destroy(hslam_ctx* ctx);
+int hslam_synchronize(hslam_ctx* ctx);
+/* cudaStream_t of the context, for callers that time or interoperate. */
+int hslam_get_stream(hslam_ctx* ctx, void** cuda_stream_out);
+/* Number of kernels this context has launched so far (bench.py's gpu_launches). */
+int64_t hslam_launch_count(hslam_ctx* ctx);
+
+/* ---------------------------------------------------------------- frames ---
+ * Replaces Frame::CreateDirPyrs (Src/Frame.cpp:104-181): level 0 copies the
+ * intensities, level l>0 is the 2x2 box mean of level l-1, dx/dy are central
+ * differences over flat indices w <= i < w*(h-1) (row ends wrap exactly as in
+ * the reference), absSquaredGrad = dx^2+dy^2 (x gammaBGrad[I]^2 if given).
+ * Rows 0 and h-1, which the reference leaves uninitialised, hold dx=dy=0.
+ * Device layout: one float4 {I, dx, dy, absSquaredGrad} per pixel per level.
+ * img: w*h float32 intensities in [0,255] (photometrically corrected). */
+int hslam_frame_create(hslam_ctx* ctx, const float* img_host, int w, int h, int levels,
+                       const float* gammaBGrad256_host /*nullable*/, hslam_frame** out);
+/* Same, input already resident in HBM (device pointer). */
+int hslam_frame_create_from_device(hslam_ctx* ctx, const float* img_dev, int w, int h, int levels,
+                                   const float* gammaBGrad256_host /*nullable*/, hslam_frame** out);
+/* Re-use an existing frame's buffers for a new image of the same size. */
+int hslam_frame_update(hslam_frame* f, const float* img, int img_is_device);
+/* For host code that still reads DirPyr / absSquaredGrad: AoS Vec3f (12 B
+ * stride) and float planes exactly as the reference stores them. */
+int hslam_frame_download(hslam_frame* f, int lvl, float* dI_xyz_host /*w*h*3, nullable*/,
+                         float* absSqGrad_host /*w*h, nullable*/);
+int hslam_frame_level_size(hslam_frame* f, int lvl, int* w, int* h);
+int hslam_frame_destroy(hslam_frame* f);
+
+/* --------------------------------------------------------------- tracker ---
+ * One per CoarseTracker instance (Include/CoarseTracker.h:14-95). */
+int hslam_tracker_create(hslam_ctx* ctx, int w, int h, hslam_tracker** out);
+int hslam_tracker_destroy(hslam_tracker* trk);
+/* CoarseTracker::makeK (Src/CoarseTracker.cpp:72-101).  The caller passes the
+ * level-0 intrinsics (HCalib->fxl() ...); levels 1.. are derived by the
+ * reference rule.  Ki = K^-1 is derived with Eigen's 3x3 cofactor formula. */
+int hslam_tracker_make_K(hslam_tracker* trk, int levels, int w0, int h0,
+                         float fx0, float fy0, float cx0, float cy0);
+/* Read back the per-level intrinsics (fx,fy,cx,cy,w,h,Ki row-major 9). */
+int hslam_tracker_get_K(hslam_tracker* trk, int lvl, float out_fxfycxcy[4], int out_wh[2], float out_Ki[9]);
+/* Upload the reference point cloud pc_u/pc_v/pc_idepth/pc_color of one level
+ * (output of makeCoarseDepthL0, Src/CoarseTracker.cpp:216-261). Host pointers. */
+int hslam_tracker_set_ref(hslam_tracker* trk, int lvl, const float* u, const float* v,
+                          const float* idepth, const float* color, int n);
+/* lastRef->ab_exposure and lastRef_aff_g2l (Src/CoarseTracker.cpp:496-500). */
+int hslam_tracker_set_ref_aff(hslam_tracker* trk, float ref_exposure, double ref_aff_a, double ref_aff_b);
+
+/* CoarseTracker::calcRes (Src/CoarseTracker.cpp:329-485).
+ * out6 = {E, numTermsInE, sumSqShiftT/(n+0.1), 0, sumSqShiftRT/(n+0.1), numSaturated/numTermsInE}.
+ * The warped buffers are not materialised: the same launch also reduces the
+ * normal equations (see calc_gs). n_warped_out (nullable) receives buf_warped_n
+ * BEFORE padding to a multiple of 4. */
+int hslam_tracker_calc_res(hslam_tracker* trk, int lvl, const hslam_frame* newFrame,
+                           const double refToNew[12], double aff_a, double aff_b,
+                           float new_exposure, float cutoffTH, double out6[6], int* n_warped_out);
+/* CoarseTracker::calcGSSSE (Src/CoarseTracker.cpp:267-324) evaluated on the
+ * inliers of calcRes at the same (pose, aff, cutoffTH): H (8x8 col-major) and
+ * b (8) with the 1/n_padded normalisation and SCALE_* scaling applied. */
+int hslam_tracker_calc_gs(hslam_tracker* trk, int lvl, const hslam_frame* newFrame,
+                          const double refToNew[12], double aff_a, double aff_b,
+                          float new_exposure, float cutoffTH, double H[64], double b[8]);
+/* CoarseTracker::trackNewestCoarse (Src/CoarseTracker.cpp:506-683): the whole
+ * coarse-to-fine LM loop in ONE cooperative launch (8x8 LDLT, SE3 exp and the
+ * accept/reject logic run on the device).  refToNew_io / aff_io are
+ * lastToNew_out / aff_g2l_out.  lastResiduals[5] is NaN-initialised,
+ * lastFlow[3] = lastFlowIndicators.  *ok receives the bool return value.
+ * iterations_out (nullable, 5 ints) receives the LM iterations per level. */
+int hslam_tracker_track(hslam_tracker* trk, const hslam_frame* newFrame, float new_exposure,
+                        double refToNew_io[12], double aff_io[2], int coarsestLvl,
+                        const double minResForAbort[5], double lastResiduals[5],
+                        double lastFlow[3], int* ok, int* iterations_out);
+/* Asynchronous pair of the above for batched/pipelined callers: enqueue does
+ * the (pinned) H2D of the 14 state doubles and the launch; finish waits and
+ * fills the outputs. */
+int hslam_tracker_track_enqueue(hslam_tracker* trk, const hslam_frame* newFrame, float new_exposure,
+                                const double refToNew[12], const double aff[2], int coarsestLvl,
+                                const double minResForAbort[5]);
+int hslam_tracker_track_finish(hslam_tracker* trk, double refToNew_out[12], double aff_out[2],
+                               double lastResiduals[5], double lastFlow[3], int* ok,
+                               int* iterations_out);
+
+/* -------------------------------------------------------------- window BA ---
+ * Device-resident mirror of EnergyFunctional + its points/residuals
+ * (Include/EnergyFunctional.h:30-121).  Re-pack only when the reference
+ * invalidates EFIndicesValid / EFAdjointsValid / EFDeltaValid
+ * (Src/EnergyFunctional.cpp:17-19). */
+
+/* Per-window state; all pointers are HOST pointers, copied on the call.
+ * Pair index convention everywhere: idx = host + target*n_frames
+ * (Src/EnergyFunctional.cpp:60, AccumulatedTopHessian.cpp:53). */
+typedef struct hslam_window {
+  int n_frames;
+  int w, h;                      /* HCalib->Width/Height */
+  float fx, fy, cx, cy;          /* HCalib->fxl(),fyl(),cxl(),cyl()   (Include/CalibData.h:93-96) */
+  float fxi, fyi;                /* HCalib->fxli(),fyli()             (Include/CalibData.h:97-98) */
+  const hslam_frame* const* frames;  /* n_frames, index = Frame::idx */
+  const float* frameEnergyTH;    /* n_frames, Frame::frameEnergyTH */
+  /* FrameFramePrecalc (Src/OptimizationClasses.cpp:13-39), HSLAM_PRECALC_STRIDE
+   * floats per pair: [0..8] PRE_KRKiTll row-major, [9..11] PRE_KtTll,
+   * [12..20] PRE_RTll_0 row-major, [21..23] PRE_tTll_0, [24..25] PRE_aff_mode,
+   * [26] PRE_b0_mode, [27] unused. */
+  const float* precalc;          /* n*n*28 */
+  const double* adHost;          /* n*n*64 col-major, EnergyFunctional::adHost   (EnergyFunctional.cpp:60) */
+  const double* adTarget;        /* n*n*64 col-major, EnergyFunctional::adTarget (EnergyFunctional.cpp:61) */
+  const float* adHTdeltaF;       /* n*n*8,  EnergyFunctional::adHTdeltaF         (EnergyFunctional.cpp:136) */
+  float  cDeltaF[4];             /* EnergyFunctional::cDeltaF (EnergyFunctional.cpp:140) */
+  double cPrior[4];              /* EnergyFunctional::cPrior  (EnergyFunctional.cpp:63)  */
+  const double* framePrior;      /* n*8, FrameOptimizationData::prior       (Include/Frame.h:265) */
+  const double* frameDeltaPrior; /* n*8, FrameOptimizationData::delta_prior (Include/Frame.h:266) */
+} hslam_window;
+
+/* MapPoint + MapPointOptimizationData flattened (Include/MapPoint.h:16-162).
+ * HOST pointers.  res_begin/res_index give each point's `residuals` vector in
+ * the point's own order (the order the reference iterates, it fixes the float
+ * summation order of Hdd/bd/Hcd, AccumulatedTopHessian.cpp:35-120). */
+typedef struct hslam_point_soa {
+  int n_points;
+  const float* u;            /* P */
+  const float* v;            /* P */
+  const float* idepth;       /* P   MapPoint::idepth */
+  const float* idepth_zero;  /* P   efPoint->idepth_zero */
+  const float* color;        /* P*8 MapPoint::color,   point-major */
+  const float* weights;      /* P*8 MapPoint::weights, point-major */
+  const float* priorF;       /* P   efPoint->priorF */
+  const float* deltaF;       /* P   efPoint->deltaF (EnergyFunctional.cpp:148) */
+  const int32_t* host_idx;   /* P   host->frame->idx */
+  const int32_t* res_begin;  /* P+1 CSR offsets into res_index */
+  const int32_t* res_index;  /* residual ids (index into hslam_residual_soa) */
+} hslam_point_soa;
+
+/* PointFrameResidual flattened (Include/OptimizationClasses.h:79-163). HOST pointers. */
+typedef struct hslam_residual_soa {
+  int n_residuals;
+  const int32_t* point_idx;    /* R */
+  const int32_t* target_idx;   /* R  targetIDX (hostIDX comes from the point) */
+  const int8_t*  state_state;  /* R  HSLAM_RES_* */
+  const uint8_t* is_linearized;/* R  PointFrameResidual::isLinearized */
+  const uint8_t* is_active;    /* R  isActiveAndIsGoodNEW */
+  const double*  state_energy; /* R  nullable (zeros) */
+} hslam_residual_soa;
+
+int hslam_ba_create(hslam_ctx* ctx, hslam_ba** out);
+int hslam_ba_destroy(hslam_ba* ba);
+/* setAdjointsF/setDeltaF/setPrecalcValues results (EnergyFunctional.cpp:22-82,
+ * 128-152; System.cpp:321-331).  Cheap: O(n^2) floats. */
+int hslam_ba_set_window(hslam_ba* ba, const hslam_window* win);
+/* Topology: call after makeIDX / insertResidual / dropResidual / removePoint
+ * (EnergyFunctional.cpp:819-840,371-380,428-454).  Residuals are re-ordered on
+ * the device by (host,target) pair; all per-residual outputs are returned in
+ * the caller's order. */
+int hslam_ba_set_topology(hslam_ba* ba, const hslam_point_soa* pts, const hslam_residual_soa* res);
+/* Per-iteration point state only (idepth, deltaF change in doStepFromBackup /
+ * setDeltaF; FullSystemOptimize.cpp:171-264). Host pointers, P floats each. */
+int hslam_ba_update_points(hslam_ba* ba, const float* idepth, const float* deltaF,
+                           const float* idepth_zero /*nullable: unchanged*/);
+
+/* System::linearizeAll_Reductor -> PointFrameResidual::linearize
+ * (FullSystemOptimize.cpp:19-52,114; OptimizationClasses.cpp:43-233) over every
+ * residual that is not linearised.  If fixLinearization != 0 applyRes(true) is
+ * done in the same pass (FullSystemOptimize.cpp:26-28).  Outputs (host, caller
+ * order, each nullable): energy_sum = stats[0]; newState/newEnergy/
+ * newEnergyWithOutlier = state_NewState/state_NewEnergy/state_NewEnergyWithOutlier;
+ * centerProjectedTo R*3; projectedTo R*16. */
+int hslam_ba_linearize(hslam_ba* ba, int fixLinearization, double* energy_sum,
+                       int8_t* newState, float* newEnergy, float* newEnergyWithOutlier,
+                       float* centerProjectedTo, float* projectedTo);
+/* System::applyRes_Reductor -> PointFrameResidual::applyRes(true) + takeData
+ * (FullSystemOptimize.cpp:55-59; OptimizationClasses.cpp:235-256, .h:155-161). */
+int hslam_ba_apply_res(hslam_ba* ba);
+/* PointFrameResidual::fixLinearizationF (OptimizationClasses.cpp:258-284) on
+ * the listed residual ids (host pointer): res_toZeroF = resF - J*delta,
+ * isLinearized = true. */
+int hslam_ba_fix_linearization(hslam_ba* ba, const int32_t* residual_ids, int count);
+
+#define HSLAM_ACC_A   0   /* EnergyFunctional::accumulateAF_MT  (EnergyFunctional.cpp:155-175) */
+#define HSLAM_ACC_L   1   /* EnergyFunctional::accumulateLF_MT  (EnergyFunctional.cpp:178-197) */
+#define HSLAM_ACC_SC  2   /* EnergyFunctional::accumulateSCF_MT (EnergyFunctional.cpp:203-220) */
+/* addPoint<mode> + stitchDoubleMT for the chosen system.  H is (8n+4)^2
+ * col-major, b is (8n+4); host pointers.  nres (nullable) = resInA / resInL.
+ * SC requires A and L to have been accumulated for the current state (it reads
+ * Hdd/bd/Hcd_acc{A,L}F exactly like AccumulatedSCHessian.cpp:23-31). */
+int hslam_ba_accumulate(hslam_ba* ba, int which, double* H, double* b, int* nres);
+/* The three systems in one pass (what solveSystemF needs,
+ * EnergyFunctional.cpp:717-724): Hb_out = [H_A|b_A|H_L|b_L|H_SC|b_SC], each H
+ * (8n+4)^2 col-major followed by its b. nres2 (nullable) = {resInA,resInL}. */
+int hslam_ba_accumulate_all(hslam_ba* ba, double* Hb_out_host, int* nres2);
+/* Device-resident variants: results stay in HBM (device pointer to
+ * 3*((8n+4)^2+(8n+4)) doubles owned by the handle) for an all-reduce. */
+int hslam_ba_accumulate_all_device(hslam_ba* ba, double** Hb_dev_out, int* count_out);
+/* One fused GN-iteration pass: linearize(fixLinearization=0) + applyRes +
+ * accumulate_all, enqueued back-to-back with no host round trip. */
+int hslam_ba_iteration_device(hslam_ba* ba, double** Hb_dev_out, int* count_out);
+/* Copy the device Hb block to the host (after an external all-reduce). */
+int hslam_ba_download_Hb(hslam_ba* ba, double* Hb_out_host);
+/* Sum the stitched [H|b] block across ranks with ONE ncclAllReduce(sum, fp64)
+ * on the context stream.  nccl_comm is a ncclComm_t; libnccl is resolved at
+ * run time from the process (dlsym), there is no link-time dependency.
+ * prior_rank: priors were added by every rank; this call removes the
+ * duplicates so that the sum holds them once (AccumulatedTopHessian.cpp:268). */
+int hslam_ba_allreduce(hslam_ba* ba, void* nccl_comm);
+/* In a sharded window only one rank may add the priors (cPrior, frame priors):
+ * 1 (default) = add, 0 = skip. */
+int hslam_ba_set_add_priors(hslam_ba* ba, int add_priors);
+
+/* Side effects of addPoint on the points (AccumulatedTopHessian.cpp:122-139,
+ * AccumulatedSCHessian.cpp:16-33), needed by resubstituteFPt / flagPointsForRemoval
+ * / makeCoarseDepthL0.  Host pointers, caller order, each nullable. */
+int hslam_ba_point_results(hslam_ba* ba, float* HdiF, float* bdSumF, float* idepth_hessian,
+                           float* Hdd_accAF, float* bd_accAF, float* Hcd_accAF /*P*4*/,
+                           float* Hdd_accLF, float* bd_accLF, float* Hcd_accLF /*P*4*/);
+/* Per-residual state after applyRes: state_state, isActive, JpJdF (R*8),
+ * and the raw Jacobian (R*74 in RawResidualJacobian member order: resF[8],
+ * Jpdxi[2][6], Jpdc[2][4], Jpdd[2], JIdx[2][8], JabF[2][8], JIdx2[4], JabJIdx[4],
+ * Jab2[4]; 2x2 blocks col-major). Each nullable. */
+int hslam_ba_residual_results(hslam_ba* ba, int8_t* state_state, uint8_t* is_active,
+                              float* JpJdF, float* J74, float* res_toZeroF /*R*8*/);
+
+/* EnergyFunctional::resubstituteF_MT / resubstituteFPt
+ * (EnergyFunctional.cpp:222-274): x is the (8n+4) solution; step_out[P] =
+ * efPoint->step.   */
+int hslam_ba_resubstitute(hslam_ba* ba, const double* x_host, float* step_out_host);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* HSLAM_B200_H */

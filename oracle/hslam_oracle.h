@@ -1,0 +1,171 @@
+/*
+ * hslam_oracle.h — C interface of the CPU ORACLE.  TEST INFRASTRUCTURE ONLY.
+ *
+ * A CPU restatement of the reference's (AUBVRL/H-SLAM, namespace FSLAM)
+ * photometric Gauss-Newton hot path.  Only tests/, __graft_entry__.smoke() and
+ * bench.py's cpu_baseline / --impl reference legs may load this library; the
+ * product (h-slam_b200/) never does.
+ *
+ * PARITY UNPINNED: the reference ships no tests, golden vectors or fixtures for
+ * this path and cannot be compiled in this environment
+ * (Eigen/Boost/OpenCV absent), so the oracle is pinned only by (a) analytic
+ * known answers (finite-difference Jacobians, Schur identity vs a dense
+ * elimination, zero-motion tracking, Sophus group identities) and (b) agreement
+ * between its two independent precisions, see tests/test_oracle_*.py.
+ *
+ * Two restatements of every function:
+ *   *_f : float-faithful — fp32 arithmetic in the operation order written in
+ *         the reference source (Eigen fixed-size 3-vector reductions evaluated
+ *         as a0+(a1+a2), the order of Eigen 3.3's redux_novec_unroller), the
+ *         4-lane SSE layout and the 1/1k/1M shiftUp tiers of MatrixAccumulators;
+ *         compiled with -ffp-contract=off.
+ *   *_d : the same mathematics in fp64 on the same fp32 inputs.
+ */
+#ifndef HSLAM_ORACLE_H
+#define HSLAM_ORACLE_H
+#include <stdint.h>
+#include "../include/hslam_b200.h" /* data-format structs only (hslam_params, *_soa) */
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+/* ---- SE3 (Thirdparty/Sophus/sophus/se3.hpp:131-139,407-427; so3.hpp:343-369) ---- */
+void orc_se3_exp(const double xi[6] /*upsilon,omega*/, double T[12] /*R row-major, t*/);
+void orc_se3_log(const double T[12], double xi[6]);
+void orc_se3_mul(const double A[12], const double B[12], double C[12]);
+void orc_se3_inv(const double A[12], double Ainv[12]);
+void orc_se3_adj(const double T[12], double Adj[36] /*row-major 6x6*/);
+/* AffLight::fromToVecExposure (Include/GlobalTypes.h:334-346) */
+void orc_aff_from_to(float expF, float expT, double aF, double bF, double aT, double bT, double out2[2]);
+/* Pivoted LDLT solve of an n x n (n<=16) symmetric system, col-major; stands in
+ * for Eigen's ldlt().solve() (Src/CoarseTracker.cpp:563). */
+void orc_ldlt_solve(const double* A, const double* rhs, int n, double* x);
+
+/* ---- pyramid: Frame::CreateDirPyrs (Src/Frame.cpp:104-181) ----
+ * dI_out: concatenated levels, Vec3f AoS (3 floats/px); absgrad_out likewise 1
+ * float/px.  Rows 0 and h-1 (uninitialised in the reference) are written 0. */
+int orc_pyramid(const float* img, int w, int h, int levels, const float* gammaBGrad256,
+                float* dI_out, float* absgrad_out);
+int64_t orc_pyramid_offset(int w, int h, int lvl); /* pixel offset of level lvl */
+
+/* ---- tracker ---- */
+typedef struct orc_trk_level {
+  int w, h;
+  float fx, fy, cx, cy;
+  float K[9];   /* row-major */
+  float Ki[9];  /* row-major */
+  int n;
+  const float* pc_u;
+  const float* pc_v;
+  const float* pc_idepth;
+  const float* pc_color;
+} orc_trk_level;
+
+/* CoarseTracker::makeK (Src/CoarseTracker.cpp:72-101) */
+void orc_make_K(int levels, int w0, int h0, float fx0, float fy0, float cx0, float cy0,
+                orc_trk_level* out_levels);
+/* CoarseTracker::makeCoarseDepthL0 (Src/CoarseTracker.cpp:105-263).  Input =
+ * the (u,v,new_idepth,weight) splats of the IN residuals; dI_ref = reference
+ * frame pyramid (orc_pyramid layout).  Output arrays per level are caller
+ * allocated with w_l*h_l floats each; pc_n[l] receives the count. */
+int orc_make_coarse_depth(int levels, int w0, int h0, int n_splat, const int* su, const int* sv,
+                          const float* sidepth, const float* sweight, const float* dI_ref,
+                          float* const* pc_u, float* const* pc_v, float* const* pc_idepth,
+                          float* const* pc_color, int* pc_n);
+
+typedef struct orc_trk_frame_pair {
+  float ref_exposure, new_exposure;
+  double ref_aff_a, ref_aff_b;
+} orc_trk_frame_pair;
+
+/* CoarseTracker::calcRes (Src/CoarseTracker.cpp:329-485). warped (nullable):
+ * 8 arrays {idepth,u,v,dx,dy,residual,weight,refColor}, each >= n+4 floats
+ * (doubles for _d); *n_warped = count BEFORE padding; mask (nullable, n bytes):
+ * 0 = gated out, 1 = inlier, 2 = saturated. */
+int orc_trk_calc_res_f(const orc_trk_level* L, int lvl, const float* dI_new, const orc_trk_frame_pair* fp,
+                       const hslam_params* prm, const double refToNew[12], double aff_a, double aff_b,
+                       float cutoffTH, double out6[6], float* const* warped, int* n_warped, uint8_t* mask);
+int orc_trk_calc_res_d(const orc_trk_level* L, int lvl, const float* dI_new, const orc_trk_frame_pair* fp,
+                       const hslam_params* prm, const double refToNew[12], double aff_a, double aff_b,
+                       float cutoffTH, double out6[6], double* const* warped, int* n_warped, uint8_t* mask);
+/* CoarseTracker::calcGSSSE (Src/CoarseTracker.cpp:267-324) + Accumulator9
+ * (Include/MatrixAccumulators.h:982-1345) on the warped buffers of calc_res. */
+int orc_trk_calc_gs_f(const orc_trk_level* L, const orc_trk_frame_pair* fp, const hslam_params* prm,
+                      double aff_a, double aff_b, const float* const* warped, int n_warped_unpadded,
+                      double H[64], double b[8]);
+int orc_trk_calc_gs_d(const orc_trk_level* L, const orc_trk_frame_pair* fp, const hslam_params* prm,
+                      double aff_a, double aff_b, const double* const* warped, int n_warped_unpadded,
+                      double H[64], double b[8]);
+/* CoarseTracker::trackNewestCoarse (Src/CoarseTracker.cpp:506-683).
+ * dI_new = whole pyramid (orc_pyramid layout).  trace (nullable): per LM
+ * evaluation 4 doubles {lvl, E/N, accepted, lambda} up to trace_cap rows,
+ * *trace_n = rows written. */
+int orc_trk_track_f(const orc_trk_level* levels, int n_levels, const float* dI_new, const orc_trk_frame_pair* fp,
+                    const hslam_params* prm, double refToNew_io[12], double aff_io[2], int coarsestLvl,
+                    const double minResForAbort[5], double lastResiduals[5], double lastFlow[3],
+                    int* ok, int* iterations, double* trace, int trace_cap, int* trace_n);
+int orc_trk_track_d(const orc_trk_level* levels, int n_levels, const float* dI_new, const orc_trk_frame_pair* fp,
+                    const hslam_params* prm, double refToNew_io[12], double aff_io[2], int coarsestLvl,
+                    const double minResForAbort[5], double lastResiduals[5], double lastFlow[3],
+                    int* ok, int* iterations, double* trace, int trace_cap, int* trace_n);
+
+/* ---- window BA ---- */
+/* Host-side state preparation restated from FrameOptimizationData::setState
+ * (Include/Frame.h:184-197), FrameFramePrecalc::set (Src/OptimizationClasses.cpp:13-39),
+ * EnergyFunctional::setAdjointsF / setDeltaF (Src/EnergyFunctional.cpp:22-82,128-152).
+ * Inputs per frame: worldToCam_evalPT (12 doubles), state[10], state_zero[10],
+ * ab_exposure.  Outputs: precalc n*n*28 float, adHost/adTarget n*n*64 double
+ * col-major, adHTdeltaF n*n*8 float, all indexed host + target*n. */
+int orc_ba_prepare_window(int n, const double* w2c_evalPT, const double* state, const double* state_zero,
+                          const float* ab_exposure, float fx, float fy, float cx, float cy,
+                          const hslam_params* prm, float* precalc, double* adHost, double* adTarget,
+                          float* adHTdeltaF);
+
+typedef struct orc_window {
+  int n_frames;
+  int w, h;
+  float fx, fy, cx, cy, fxi, fyi;
+  const float* const* dI;       /* n_frames pointers to level-0 Vec3f AoS images */
+  const float* frameEnergyTH;
+  const float* precalc;
+  const double* adHost;
+  const double* adTarget;
+  const float* adHTdeltaF;
+  float cDeltaF[4];
+  double cPrior[4];
+  const double* framePrior;
+  const double* frameDeltaPrior;
+} orc_window;
+
+typedef struct orc_ba orc_ba;  /* holds J, states, accumulators; scalar chosen at creation */
+orc_ba* orc_ba_create(int use_double, const hslam_params* prm);
+void orc_ba_destroy(orc_ba* ba);
+int orc_ba_set_window(orc_ba* ba, const orc_window* w);
+int orc_ba_set_topology(orc_ba* ba, const hslam_point_soa* pts, const hslam_residual_soa* res);
+int orc_ba_update_points(orc_ba* ba, const float* idepth, const float* deltaF, const float* idepth_zero);
+/* threads<=1: the reference's non-MT branch; threads>1: IndexThreadReduce
+ * semantics (Include/IndexThreadReduce.h:70-207) on a std::thread pool. */
+int orc_ba_set_threads(orc_ba* ba, int threads);
+int orc_ba_linearize(orc_ba* ba, int fixLinearization, double* energy_sum, int8_t* newState,
+                     float* newEnergy, float* newEnergyWithOutlier, float* centerProjectedTo,
+                     float* projectedTo);
+int orc_ba_apply_res(orc_ba* ba);
+int orc_ba_fix_linearization(orc_ba* ba, const int32_t* ids, int count);
+int orc_ba_accumulate(orc_ba* ba, int which, double* H, double* b, int* nres);
+int orc_ba_point_results(orc_ba* ba, double* HdiF, double* bdSumF, double* idepth_hessian,
+                         double* Hdd_accAF, double* bd_accAF, double* Hcd_accAF,
+                         double* Hdd_accLF, double* bd_accLF, double* Hcd_accLF);
+int orc_ba_residual_results(orc_ba* ba, int8_t* state_state, uint8_t* is_active, double* JpJdF,
+                            double* J74, double* res_toZeroF);
+/* Raw relative accumulators before stitching, for fine-grained parity:
+ * top: n*n blocks of 13*13 doubles (col-major) for mode `which` (0/1);
+ * sc : accD n*n*n*64, accE n*n*32, accEB n*n*8, accHcc 16, accbc 4. */
+int orc_ba_raw_top(orc_ba* ba, int which, double* acc1313);
+int orc_ba_raw_sc(orc_ba* ba, double* accD, double* accE, double* accEB, double* accHcc, double* accbc);
+int orc_ba_resubstitute(orc_ba* ba, const double* x, float* step_out);
+
+#ifdef __cplusplus
+}
+#endif
+#endif
