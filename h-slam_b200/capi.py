@@ -1,0 +1,377 @@
+"""ctypes binding of include/hslam_b200.h plus thin Python mirrors of the reference classes.
+
+Everything here goes through the C ABI of libhslam_b200.so (hand-written sm_100a kernels).  There
+is no CPU path: if the library is missing or no CUDA device is present the calls raise.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libhslam_b200.so")
+
+ACC_A, ACC_L, ACC_SC = 0, 1, 2
+RES_IN, RES_OOB, RES_OUT = 0, 1, 2
+
+
+class HslamError(RuntimeError):
+    pass
+
+
+class Params(C.Structure):
+    _fields_ = [
+        ("huberTH", C.c_float), ("coarseCutoffTH", C.c_float), ("outlierTHSumComponent", C.c_float),
+        ("affineOptModeA", C.c_float), ("affineOptModeB", C.c_float), ("scale_xi_rot", C.c_float),
+        ("scale_xi_trans", C.c_float), ("scale_a", C.c_float), ("scale_b", C.c_float), ("scale_f", C.c_float),
+        ("scale_c", C.c_float), ("scale_idepth", C.c_float), ("max_tracker_iterations", C.c_int * 5),
+    ]
+
+
+class WindowStruct(C.Structure):
+    _fields_ = [
+        ("n_frames", C.c_int), ("w", C.c_int), ("h", C.c_int),
+        ("fx", C.c_float), ("fy", C.c_float), ("cx", C.c_float), ("cy", C.c_float), ("fxi", C.c_float), ("fyi", C.c_float),
+        ("frames", C.c_void_p), ("frameEnergyTH", C.c_void_p), ("precalc", C.c_void_p), ("adHost", C.c_void_p),
+        ("adTarget", C.c_void_p), ("adHTdeltaF", C.c_void_p), ("cDeltaF", C.c_float * 4), ("cPrior", C.c_double * 4),
+        ("framePrior", C.c_void_p), ("frameDeltaPrior", C.c_void_p),
+    ]
+
+
+class PointSoA(C.Structure):
+    _fields_ = [("n_points", C.c_int)] + [(k, C.c_void_p) for k in (
+        "u", "v", "idepth", "idepth_zero", "color", "weights", "priorF", "deltaF", "host_idx", "res_begin", "res_index")]
+
+
+class ResidualSoA(C.Structure):
+    _fields_ = [("n_residuals", C.c_int)] + [(k, C.c_void_p) for k in (
+        "point_idx", "target_idx", "state_state", "is_linearized", "is_active", "state_energy")]
+
+
+def _ptr(a):
+    return a.ctypes.data_as(C.c_void_p) if a is not None else None
+
+
+_lib = None
+
+
+def load():
+    """Load the CUDA library; raises loudly if it was not built (no fallback)."""
+    global _lib
+    if _lib is None:
+        if not os.path.exists(LIB_PATH):
+            raise HslamError(f"{LIB_PATH} is missing: build it with `python -c 'import __graft_entry__ as g; g.build()'` "
+                             "or `make -C h-slam_b200/csrc` (there is no CPU fallback)")
+        L = C.CDLL(LIB_PATH)
+        L.hslam_last_error.restype = C.c_char_p
+        L.hslam_launch_count.restype = C.c_int64
+        L.hslam_launch_count.argtypes = [C.c_void_p]
+        _lib = L
+    return _lib
+
+
+def _chk(rc):
+    if rc != 0:
+        raise HslamError(f"hslam error {rc}: {load().hslam_last_error().decode()}")
+
+
+def default_params():
+    p = Params()
+    load().hslam_params_default(C.byref(p))
+    return p
+
+
+class Context:
+    def __init__(self, device=0, params=None):
+        self.L = load()
+        self.h = C.c_void_p()
+        self.params = params or default_params()
+        _chk(self.L.hslam_create(C.byref(self.params), C.c_int(device), C.byref(self.h)))
+
+    def close(self):
+        if self.h:
+            self.L.hslam_destroy(self.h)
+            self.h = C.c_void_p()
+
+    def synchronize(self):
+        _chk(self.L.hslam_synchronize(self.h))
+
+    @property
+    def stream(self):
+        s = C.c_void_p()
+        _chk(self.L.hslam_get_stream(self.h, C.byref(s)))
+        return s.value or 0
+
+    @property
+    def launches(self):
+        return int(self.L.hslam_launch_count(self.h))
+
+
+class Frame:
+    """Device mirror of Frame::DirPyr / absSquaredGrad (reference Src/Frame.cpp:104-181)."""
+
+    def __init__(self, ctx: Context, img, levels, gamma=None, device_ptr=None, w=None, h=None):
+        self.ctx, self.L = ctx, ctx.L
+        self.h = C.c_void_p()
+        g = np.ascontiguousarray(gamma, np.float32) if gamma is not None else None
+        if device_ptr is not None:
+            self.w, self.hh = w, h
+            _chk(self.L.hslam_frame_create_from_device(ctx.h, C.c_void_p(device_ptr), w, h, levels, _ptr(g), C.byref(self.h)))
+        else:
+            img = np.ascontiguousarray(img, np.float32)
+            self.hh, self.w = img.shape
+            _chk(self.L.hslam_frame_create(ctx.h, _ptr(img), self.w, self.hh, levels, _ptr(g), C.byref(self.h)))
+        self.levels = levels
+
+    def update(self, img=None, device_ptr=None):
+        if device_ptr is not None:
+            _chk(self.L.hslam_frame_update(self.h, C.c_void_p(device_ptr), 1))
+        else:
+            img = np.ascontiguousarray(img, np.float32)
+            _chk(self.L.hslam_frame_update(self.h, _ptr(img), 0))
+
+    def download(self, lvl):
+        w, h = self.w >> lvl, self.hh >> lvl
+        dI = np.zeros((h, w, 3), np.float32)
+        ag = np.zeros((h, w), np.float32)
+        _chk(self.L.hslam_frame_download(self.h, lvl, _ptr(dI), _ptr(ag)))
+        return dI, ag
+
+    def close(self):
+        if self.h:
+            self.L.hslam_frame_destroy(self.h)
+            self.h = C.c_void_p()
+
+
+class CoarseTracker:
+    """Mirror of FSLAM::CoarseTracker (reference Include/CoarseTracker.h:14-95)."""
+
+    def __init__(self, ctx: Context, w, h):
+        self.ctx, self.L = ctx, ctx.L
+        self.h = C.c_void_p()
+        _chk(self.L.hslam_tracker_create(ctx.h, w, h, C.byref(self.h)))
+        self.lastResiduals = np.full(5, np.nan)
+        self.lastFlowIndicators = np.full(3, 1000.0)
+        self.iterations = np.zeros(5, np.int32)
+
+    def makeK(self, cam, levels):
+        self.levels = levels
+        _chk(self.L.hslam_tracker_make_K(self.h, levels, cam.w, cam.h, C.c_float(cam.fx), C.c_float(cam.fy),
+                                         C.c_float(cam.cx), C.c_float(cam.cy)))
+
+    def get_K(self, lvl):
+        k = np.zeros(4, np.float32); wh = np.zeros(2, np.int32); ki = np.zeros(9, np.float32)
+        _chk(self.L.hslam_tracker_get_K(self.h, lvl, _ptr(k), _ptr(wh), _ptr(ki)))
+        return k, wh, ki
+
+    def setCoarseTrackingRef(self, pc, ref_exposure=1.0, ref_aff=(0.0, 0.0)):
+        """pc: per level (u, v, idepth, color) as produced by makeCoarseDepthL0."""
+        for l, (u, v, idp, col) in enumerate(pc):
+            a = [np.ascontiguousarray(x, np.float32) for x in (u, v, idp, col)]
+            _chk(self.L.hslam_tracker_set_ref(self.h, l, _ptr(a[0]), _ptr(a[1]), _ptr(a[2]), _ptr(a[3]), len(a[0])))
+        _chk(self.L.hslam_tracker_set_ref_aff(self.h, C.c_float(ref_exposure), C.c_double(ref_aff[0]), C.c_double(ref_aff[1])))
+
+    def calcRes(self, lvl, frame: Frame, T, aff, cutoffTH, new_exposure=1.0):
+        out6 = np.zeros(6)
+        nw = C.c_int(0)
+        T = np.ascontiguousarray(T, np.float64)
+        _chk(self.L.hslam_tracker_calc_res(self.h, lvl, frame.h, _ptr(T), C.c_double(aff[0]), C.c_double(aff[1]),
+                                           C.c_float(new_exposure), C.c_float(cutoffTH), _ptr(out6), C.byref(nw)))
+        return out6, nw.value
+
+    def calcGSSSE(self, lvl, frame: Frame, T, aff, cutoffTH, new_exposure=1.0):
+        H = np.zeros(64); b = np.zeros(8)
+        T = np.ascontiguousarray(T, np.float64)
+        _chk(self.L.hslam_tracker_calc_gs(self.h, lvl, frame.h, _ptr(T), C.c_double(aff[0]), C.c_double(aff[1]),
+                                          C.c_float(new_exposure), C.c_float(cutoffTH), _ptr(H), _ptr(b)))
+        return H.reshape(8, 8).T.copy(), b
+
+    def trackNewestCoarse(self, frame: Frame, T, aff, coarsestLvl, minResForAbort=None, new_exposure=1.0):
+        T = np.array(T, np.float64).copy()
+        aff = np.array(aff, np.float64).copy()
+        mra = np.full(5, np.nan) if minResForAbort is None else np.ascontiguousarray(minResForAbort, np.float64)
+        ok = C.c_int(0)
+        _chk(self.L.hslam_tracker_track(self.h, frame.h, C.c_float(new_exposure), _ptr(T), _ptr(aff), C.c_int(coarsestLvl),
+                                        _ptr(mra), _ptr(self.lastResiduals), _ptr(self.lastFlowIndicators), C.byref(ok),
+                                        _ptr(self.iterations)))
+        return bool(ok.value), T, aff
+
+    def track_enqueue(self, frame: Frame, T, aff, coarsestLvl, minResForAbort=None, new_exposure=1.0):
+        T = np.ascontiguousarray(T, np.float64)
+        aff = np.ascontiguousarray(aff, np.float64)
+        mra = np.full(5, np.nan) if minResForAbort is None else np.ascontiguousarray(minResForAbort, np.float64)
+        _chk(self.L.hslam_tracker_track_enqueue(self.h, frame.h, C.c_float(new_exposure), _ptr(T), _ptr(aff),
+                                                C.c_int(coarsestLvl), _ptr(mra)))
+
+    def track_finish(self):
+        T = np.zeros(12); aff = np.zeros(2); ok = C.c_int(0)
+        _chk(self.L.hslam_tracker_track_finish(self.h, _ptr(T), _ptr(aff), _ptr(self.lastResiduals),
+                                               _ptr(self.lastFlowIndicators), C.byref(ok), _ptr(self.iterations)))
+        return bool(ok.value), T, aff
+
+    def close(self):
+        if self.h:
+            self.L.hslam_tracker_destroy(self.h)
+            self.h = C.c_void_p()
+
+
+class EnergyFunctional:
+    """Mirror of FSLAM::EnergyFunctional's accumulate path + the residual linearisation it consumes
+    (reference Include/EnergyFunctional.h:30-121, Src/FullSystemOptimize.cpp:19-165)."""
+
+    def __init__(self, ctx: Context):
+        self.ctx, self.L = ctx, ctx.L
+        self.h = C.c_void_p()
+        _chk(self.L.hslam_ba_create(ctx.h, C.byref(self.h)))
+        self._keep = []
+        self.resInA = self.resInL = 0
+
+    def set_window(self, win, frames):
+        cam = win.cam
+        ws = WindowStruct()
+        ws.n_frames, ws.w, ws.h = win.n, cam.w, cam.h
+        ws.fx, ws.fy, ws.cx, ws.cy = cam.fx, cam.fy, cam.cx, cam.cy
+        ws.fxi, ws.fyi = np.float32(1.0) / np.float32(cam.fx), np.float32(1.0) / np.float32(cam.fy)
+        fr = (C.c_void_p * win.n)(*[f.h for f in frames])
+        ws.frames = C.cast(fr, C.c_void_p)
+        ka = dict(frameEnergyTH=np.ascontiguousarray(win.frameEnergyTH, np.float32), precalc=np.ascontiguousarray(win.precalc, np.float32),
+                  adHost=np.ascontiguousarray(win.adHost, np.float64), adTarget=np.ascontiguousarray(win.adTarget, np.float64),
+                  adHTdeltaF=np.ascontiguousarray(win.adHTdeltaF, np.float32), framePrior=np.ascontiguousarray(win.framePrior, np.float64),
+                  frameDeltaPrior=np.ascontiguousarray(win.frameDeltaPrior, np.float64))
+        for k, a in ka.items():
+            setattr(ws, k, _ptr(a))
+        for i in range(4):
+            ws.cDeltaF[i] = float(win.cDeltaF[i])
+            ws.cPrior[i] = float(win.cPrior[i])
+        _chk(self.L.hslam_ba_set_window(self.h, C.byref(ws)))
+        self.n = win.n
+        self.N = 8 * win.n + 4
+
+    def set_topology(self, win):
+        keep = dict(
+            u=np.ascontiguousarray(win.u, np.float32), v=np.ascontiguousarray(win.v, np.float32),
+            idepth=np.ascontiguousarray(win.idepth, np.float32), idepth_zero=np.ascontiguousarray(win.idepth_zero, np.float32),
+            color=np.ascontiguousarray(win.color, np.float32), weights=np.ascontiguousarray(win.weights, np.float32),
+            priorF=np.ascontiguousarray(win.priorF, np.float32), deltaF=np.ascontiguousarray(win.deltaF, np.float32),
+            host_idx=np.ascontiguousarray(win.host_idx, np.int32), res_begin=np.ascontiguousarray(win.res_begin, np.int32),
+            res_index=np.ascontiguousarray(win.res_index, np.int32))
+        ps = PointSoA(len(keep["u"]))
+        for k, a in keep.items():
+            setattr(ps, k, _ptr(a))
+        keep2 = dict(
+            point_idx=np.ascontiguousarray(win.point_idx, np.int32), target_idx=np.ascontiguousarray(win.target_idx, np.int32),
+            state_state=np.ascontiguousarray(win.state_state, np.int8), is_linearized=np.ascontiguousarray(win.is_linearized, np.uint8),
+            is_active=np.ascontiguousarray(win.is_active, np.uint8))
+        rs = ResidualSoA(len(keep2["point_idx"]))
+        for k, a in keep2.items():
+            setattr(rs, k, _ptr(a))
+        rs.state_energy = None
+        _chk(self.L.hslam_ba_set_topology(self.h, C.byref(ps), C.byref(rs)))
+        self.P, self.R = ps.n_points, rs.n_residuals
+
+    def update_points(self, idepth=None, deltaF=None, idepth_zero=None):
+        a = [None if x is None else np.ascontiguousarray(x, np.float32) for x in (idepth, deltaF, idepth_zero)]
+        _chk(self.L.hslam_ba_update_points(self.h, _ptr(a[0]), _ptr(a[1]), _ptr(a[2])))
+
+    def linearizeAll(self, fixLinearization=False, outputs=True):
+        R = self.R
+        e = C.c_double(0)
+        if outputs:
+            ns = np.zeros(R, np.int8); ne = np.zeros(R, np.float32); nwo = np.zeros(R, np.float32)
+            cpt = np.zeros(R * 3, np.float32); pto = np.zeros(R * 16, np.float32)
+        else:
+            ns = ne = nwo = cpt = pto = None
+        _chk(self.L.hslam_ba_linearize(self.h, C.c_int(int(fixLinearization)), C.byref(e), _ptr(ns), _ptr(ne), _ptr(nwo),
+                                       _ptr(cpt), _ptr(pto)))
+        if not outputs:
+            return dict(energy=e.value)
+        return dict(energy=e.value, newState=ns, newEnergy=ne, newEnergyWithOutlier=nwo,
+                    centerProjectedTo=cpt.reshape(R, 3), projectedTo=pto.reshape(R, 8, 2))
+
+    def applyRes(self):
+        _chk(self.L.hslam_ba_apply_res(self.h))
+
+    def fixLinearization(self, ids):
+        ids = np.ascontiguousarray(ids, np.int32)
+        _chk(self.L.hslam_ba_fix_linearization(self.h, _ptr(ids), C.c_int(len(ids))))
+
+    def _acc(self, which):
+        N = self.N
+        H = np.zeros(N * N); b = np.zeros(N); nres = C.c_int(0)
+        _chk(self.L.hslam_ba_accumulate(self.h, C.c_int(which), _ptr(H), _ptr(b), C.byref(nres)))
+        return H.reshape(N, N).T.copy(), b, nres.value
+
+    def accumulateAF_MT(self):
+        H, b, self.resInA = self._acc(ACC_A)
+        return H, b
+
+    def accumulateLF_MT(self):
+        H, b, self.resInL = self._acc(ACC_L)
+        return H, b
+
+    def accumulateSCF_MT(self):
+        H, b, _ = self._acc(ACC_SC)
+        return H, b
+
+    def accumulate_all(self):
+        N = self.N
+        per = N * N + N
+        out = np.zeros(3 * per)
+        nres = np.zeros(2, np.int32)
+        _chk(self.L.hslam_ba_accumulate_all(self.h, _ptr(out), _ptr(nres)))
+        self.resInA, self.resInL = int(nres[0]), int(nres[1])
+        res = []
+        for s in range(3):
+            blk = out[s * per:(s + 1) * per]
+            res.append((blk[:N * N].reshape(N, N).T.copy(), blk[N * N:].copy()))
+        return res
+
+    def iteration_device(self):
+        """linearize + applyRes + accumulate A/L/SC enqueued with no host round trip; returns (device ptr, count)."""
+        p = C.c_void_p(); cnt = C.c_int(0)
+        _chk(self.L.hslam_ba_iteration_device(self.h, C.byref(p), C.byref(cnt)))
+        return p.value, cnt.value
+
+    def accumulate_all_device(self):
+        p = C.c_void_p(); cnt = C.c_int(0)
+        _chk(self.L.hslam_ba_accumulate_all_device(self.h, C.byref(p), C.byref(cnt)))
+        return p.value, cnt.value
+
+    def download_Hb(self):
+        N = self.N
+        per = N * N + N
+        out = np.zeros(3 * per)
+        _chk(self.L.hslam_ba_download_Hb(self.h, _ptr(out)))
+        return [(out[s * per:s * per + N * N].reshape(N, N).T.copy(), out[s * per + N * N:(s + 1) * per].copy()) for s in range(3)]
+
+    def set_add_priors(self, flag):
+        _chk(self.L.hslam_ba_set_add_priors(self.h, C.c_int(int(flag))))
+
+    def point_results(self):
+        P = self.P
+        names = ["HdiF", "bdSumF", "idepth_hessian", "Hdd_accAF", "bd_accAF", "Hcd_accAF", "Hdd_accLF", "bd_accLF", "Hcd_accLF"]
+        arrs = [np.zeros(P * (4 if "Hcd" in k else 1), np.float32) for k in names]
+        _chk(self.L.hslam_ba_point_results(self.h, *[_ptr(a) for a in arrs]))
+        d = dict(zip(names, arrs))
+        d["Hcd_accAF"] = d["Hcd_accAF"].reshape(P, 4); d["Hcd_accLF"] = d["Hcd_accLF"].reshape(P, 4)
+        return d
+
+    def residual_results(self, want_J=True):
+        R = self.R
+        st = np.zeros(R, np.int8); act = np.zeros(R, np.uint8); jp = np.zeros(R * 8, np.float32)
+        j74 = np.zeros(R * 74, np.float32) if want_J else None
+        rtz = np.zeros(R * 8, np.float32)
+        _chk(self.L.hslam_ba_residual_results(self.h, _ptr(st), _ptr(act), _ptr(jp), _ptr(j74), _ptr(rtz)))
+        return dict(state_state=st, is_active=act, JpJdF=jp.reshape(R, 8), J=None if j74 is None else j74.reshape(R, 74),
+                    res_toZeroF=rtz.reshape(R, 8))
+
+    def resubstituteF_MT(self, x):
+        step = np.zeros(self.P, np.float32)
+        _chk(self.L.hslam_ba_resubstitute(self.h, _ptr(np.ascontiguousarray(x, np.float64)), _ptr(step)))
+        return step
+
+    def close(self):
+        if self.h:
+            self.L.hslam_ba_destroy(self.h)
+            self.h = C.c_void_p()

@@ -1,0 +1,100 @@
+// common.cuh — shared pieces of the sm_100a hot-path library (product code).
+#pragma once
+#include <cuda_runtime.h>
+#include <cstdint>
+#include <cstdio>
+#include <string>
+#include <vector>
+#include "../../include/hslam_b200.h"
+
+namespace hs {
+
+void set_error(const std::string& msg);
+
+#define HS_CUDA(call)                                                                              \
+  do {                                                                                             \
+    cudaError_t e__ = (call);                                                                      \
+    if (e__ != cudaSuccess) {                                                                      \
+      hs::set_error(std::string(#call) + ": " + cudaGetErrorString(e__) + " (" + __FILE__ + ":" +  \
+                    std::to_string(__LINE__) + ")");                                               \
+      return HSLAM_ERR_CUDA;                                                                       \
+    }                                                                                              \
+  } while (0)
+
+#define HS_ARG(cond, msg)                 \
+  do {                                    \
+    if (!(cond)) {                        \
+      hs::set_error(std::string(msg));    \
+      return HSLAM_ERR_ARG;               \
+    }                                     \
+  } while (0)
+
+// ---- exactly-rounded fp32 primitives -------------------------------------------------
+// Everything that decides a mask (projection, bounds gates, bilinear weights, residual,
+// Huber weight, energy) is written with these so that ptxas can never contract a*b+c into an
+// FMA: the CPU oracle is compiled with -ffp-contract=off and the two must agree bit for bit.
+__device__ __forceinline__ float xmul(float a, float b) { return __fmul_rn(a, b); }
+__device__ __forceinline__ float xadd(float a, float b) { return __fadd_rn(a, b); }
+__device__ __forceinline__ float xsub(float a, float b) { return __fsub_rn(a, b); }
+__device__ __forceinline__ float xdiv(float a, float b) { return __fdiv_rn(a, b); }
+__device__ __forceinline__ float xsqrt(float a) { return __fsqrt_rn(a); }
+// a0 + (a1 + a2): Eigen 3.3 redux order for a 3-term coefficient product (see oracle_math.hpp)
+__device__ __forceinline__ float xdot3(float m0, float m1, float m2, float x, float y, float z) {
+  return xadd(xmul(m0, x), xadd(xmul(m1, y), xmul(m2, z)));
+}
+
+// getInterpolatedElement33 (Include/GlobalTypes.h:377-388) on the float4 {I,dx,dy,absgrad} image.
+// Four 16-byte texel loads through the read-only path.
+struct Hit3 { float I, dx, dy; };
+__device__ __forceinline__ Hit3 interp33(const float4* __restrict__ img, float x, float y, int width) {
+  int ix = (int)x, iy = (int)y;
+  float dx = xsub(x, (float)ix), dy = xsub(y, (float)iy);
+  float dxdy = xmul(dx, dy);
+  const float4* bp = img + ix + iy * width;
+  float4 tl = __ldg(bp), tr = __ldg(bp + 1), bl = __ldg(bp + width), br = __ldg(bp + width + 1);
+  float wBR = dxdy, wBL = xsub(dy, dxdy), wTR = xsub(dx, dxdy);
+  float wTL = xadd(xsub(xsub(1.0f, dx), dy), dxdy);
+  Hit3 h;
+  h.I = xadd(xadd(xadd(xmul(wBR, br.x), xmul(wBL, bl.x)), xmul(wTR, tr.x)), xmul(wTL, tl.x));
+  h.dx = xadd(xadd(xadd(xmul(wBR, br.y), xmul(wBL, bl.y)), xmul(wTR, tr.y)), xmul(wTL, tl.y));
+  h.dy = xadd(xadd(xadd(xmul(wBR, br.z), xmul(wBL, bl.z)), xmul(wTR, tr.z)), xmul(wTL, tl.z));
+  return h;
+}
+
+// Fixed-shape warp tree: lane 0 ends with the sum; the association is the same on every run.
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_down_sync(0xffffffffu, v, o);
+  return v;
+}
+__device__ __forceinline__ double warp_sum(double v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_down_sync(0xffffffffu, v, o);
+  return v;
+}
+__device__ __forceinline__ int warp_sum(int v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_down_sync(0xffffffffu, v, o);
+  return v;
+}
+
+}  // namespace hs
+
+struct hslam_ctx {
+  int device = 0;
+  cudaStream_t stream = nullptr;
+  hslam_params prm;
+  int sm_count = 148;
+  int64_t launches = 0;
+};
+
+struct hslam_frame {
+  hslam_ctx* ctx = nullptr;
+  int w = 0, h = 0, levels = 0;
+  float4* dI[HSLAM_MAX_PYR_LEVELS] = {nullptr};  // {I,dx,dy,absSquaredGrad} per pixel
+  float4* base = nullptr;                        // one allocation for all levels
+  float* staging = nullptr;                      // device copy of the input image (H2D target)
+  float* gamma = nullptr;                        // 256-entry BGrad table or null
+  float* pinned = nullptr;                       // pinned host staging for async H2D
+  cudaEvent_t h2d_done = nullptr;                // guards re-use of `pinned`
+};

@@ -1,0 +1,84 @@
+// context.cu — context lifetime, error reporting and defaults of the C ABI (include/hslam_b200.h).
+#include "common.cuh"
+
+static thread_local std::string g_last_error;
+
+namespace hs {
+void set_error(const std::string& msg) { g_last_error = msg; }
+}  // namespace hs
+
+extern "C" {
+
+const char* hslam_last_error(void) { return g_last_error.c_str(); }
+int hslam_abi_version(void) { return HSLAM_ABI_VERSION; }
+
+void hslam_params_default(hslam_params* p) {
+  if (!p) return;
+  p->huberTH = 9.0f;                 // Src/Settings.cpp:68
+  p->coarseCutoffTH = 20.0f;         // :77
+  p->outlierTHSumComponent = 2500;   // :64
+  p->affineOptModeA = 1e12f;         // :109
+  p->affineOptModeB = 1e8f;          // :110
+  p->scale_xi_rot = 1.0f;            // Include/GlobalTypes.h:34-41
+  p->scale_xi_trans = 0.5f;
+  p->scale_a = 10.0f;
+  p->scale_b = 1000.0f;
+  p->scale_f = 50.0f;
+  p->scale_c = 50.0f;
+  p->scale_idepth = 1.0f;
+  const int it[5] = {10, 20, 50, 50, 50};  // Src/CoarseTracker.cpp:518
+  for (int i = 0; i < 5; ++i) p->max_tracker_iterations[i] = it[i];
+}
+
+int hslam_create(const hslam_params* params, int device, hslam_ctx** out) {
+  HS_ARG(out, "hslam_create: null output");
+  int ndev = 0;
+  cudaError_t e = cudaGetDeviceCount(&ndev);
+  if (e != cudaSuccess || ndev == 0) {
+    // No CPU fallback by design: the caller must see this.
+    hs::set_error(std::string("hslam_create: no usable CUDA device (") + cudaGetErrorString(e) + ")");
+    return HSLAM_ERR_CUDA;
+  }
+  HS_ARG(device >= 0 && device < ndev, "hslam_create: device index out of range");
+  HS_CUDA(cudaSetDevice(device));
+  hslam_ctx* c = new hslam_ctx();
+  c->device = device;
+  if (params) c->prm = *params; else hslam_params_default(&c->prm);
+  cudaDeviceProp prop;
+  HS_CUDA(cudaGetDeviceProperties(&prop, device));
+  c->sm_count = prop.multiProcessorCount;
+  if (!prop.cooperativeLaunch) {
+    delete c;
+    hs::set_error("hslam_create: device lacks cooperative launch");
+    return HSLAM_ERR_CUDA;
+  }
+  HS_CUDA(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
+  *out = c;
+  return 0;
+}
+
+int hslam_destroy(hslam_ctx* c) {
+  if (!c) return 0;
+  cudaSetDevice(c->device);
+  cudaStreamSynchronize(c->stream);
+  cudaStreamDestroy(c->stream);
+  delete c;
+  return 0;
+}
+
+int hslam_synchronize(hslam_ctx* c) {
+  HS_ARG(c, "hslam_synchronize: null");
+  HS_CUDA(cudaSetDevice(c->device));
+  HS_CUDA(cudaStreamSynchronize(c->stream));
+  return 0;
+}
+
+int hslam_get_stream(hslam_ctx* c, void** s) {
+  HS_ARG(c && s, "hslam_get_stream: null");
+  *s = (void*)c->stream;
+  return 0;
+}
+
+int64_t hslam_launch_count(hslam_ctx* c) { return c ? c->launches : -1; }
+
+}  // extern "C"

@@ -1,0 +1,863 @@
+// tracker.cu — frame-to-keyframe direct image alignment on the device.
+//
+// Replaces CoarseTracker::calcRes / calcGSSSE / trackNewestCoarse
+// (reference Src/CoarseTracker.cpp:329-485, 267-324, 506-683) and the SSE Accumulator9
+// (Include/MatrixAccumulators.h:982-1345).
+//
+// Design (B200): one thread per reference point; the point record {u,v,idepth,color} is ONE float4
+// load; the four bilinear texels are four float4 loads of the {I,dx,dy,.} image; residual, Huber
+// weight and the 9-column Jacobian stay in registers and the 45 upper-triangular J^T W J products
+// are reduced warp-shuffle -> shared-memory -> per-block partial, so the reference's eight
+// buf_warped_* arrays are never written.  The per-block partials are folded in a fixed order in
+// fp64, which makes H,b bit-identical from run to run.
+//
+// hslam_tracker_track runs the WHOLE coarse-to-fine Levenberg-Marquardt loop in one cooperative
+// launch: after every evaluation a grid barrier is followed by every block redundantly folding the
+// partials and doing the 8x8 LDLT solve + SE3 exp + accept/reject on one thread, so there is no
+// host round trip between the ~50 evaluations of a frame (SURVEY.md §7 "Latency, not bandwidth").
+#include "common.cuh"
+#include <cooperative_groups.h>
+#include <cmath>
+#include <cstring>
+
+namespace cg = cooperative_groups;
+
+namespace hs {
+
+constexpr int TRK_THREADS = 256;
+constexpr int TRK_NACC = 45;      // upper triangle of the 9x9
+constexpr int TRK_PART = 56;      // floats per block partial: 45 H, E, flowT, flowRT, flowNum, nE, nSat, nW (+pad)
+constexpr int P_E = 45, P_FT = 46, P_FRT = 47, P_FN = 48, P_NE = 49, P_NSAT = 50, P_NW = 51;
+
+struct TrkLevelDev {
+  int w, h, n;
+  float fx, fy, cx, cy;
+  float Ki[9];
+  const float4* pc;  // {u, v, idepth, color}
+};
+
+// Everything one evaluation needs, prepared once per (pose, aff) by ONE thread.
+struct EvalConst {
+  float RKi[9], t[3], Ki[9];
+  float fx, fy, cx, cy;
+  float affLL0, affLL1;     // (float) fromToVecExposure(...)
+  float b0;                 // (float) lastRef_aff_g2l.b
+  float cutoff, maxEnergy, huber;
+  int w, h, n, lvl;
+  const float4* pc;
+  const float4* img;
+};
+
+struct EvalResult {          // folded, fp64
+  double acc[TRK_NACC];
+  double E, flowT, flowRT, flowNum;
+  int nE, nSat, nW, pad;
+};
+
+__device__ __forceinline__ void make_eval_const(EvalConst& c, const TrkLevelDev& L, int lvl, const float4* img,
+                                                const double* T /*R rm 9 + t 3*/, double aff_a, double aff_b,
+                                                float ref_exposure, float new_exposure, double ref_aff_a,
+                                                double ref_aff_b, float cutoff, float huber) {
+  float R[9];
+#pragma unroll
+  for (int i = 0; i < 9; ++i) R[i] = (float)T[i];
+  // Mat33f RKi = R.cast<float>() * Ki[lvl]   (CoarseTracker.cpp:345), coefficient order a0+(a1+a2)
+#pragma unroll
+  for (int i = 0; i < 3; ++i)
+#pragma unroll
+    for (int j = 0; j < 3; ++j)
+      c.RKi[3 * i + j] = xdot3(R[3 * i], R[3 * i + 1], R[3 * i + 2], L.Ki[j], L.Ki[3 + j], L.Ki[6 + j]);
+#pragma unroll
+  for (int i = 0; i < 3; ++i) c.t[i] = (float)T[9 + i];
+#pragma unroll
+  for (int i = 0; i < 9; ++i) c.Ki[i] = L.Ki[i];
+  c.fx = L.fx; c.fy = L.fy; c.cx = L.cx; c.cy = L.cy;
+  // AffLight::fromToVecExposure (GlobalTypes.h:334-346) in fp64, then cast (CoarseTracker.cpp:347)
+  float eF = ref_exposure, eT = new_exposure;
+  if (eF == 0.f || eT == 0.f) { eF = eT = 1.f; }
+  double a = exp(aff_a - ref_aff_a) * (double)eT / (double)eF;
+  double b = aff_b - a * ref_aff_b;
+  c.affLL0 = (float)a; c.affLL1 = (float)b;
+  c.b0 = (float)ref_aff_b;
+  c.cutoff = cutoff; c.huber = huber;
+  c.maxEnergy = xsub(xmul(xmul(2.0f, huber), cutoff), xmul(huber, huber));  // :354
+  c.w = L.w; c.h = L.h; c.n = L.n; c.lvl = lvl; c.pc = L.pc; c.img = img;
+}
+
+// One pass over the reference cloud of a level: every thread accumulates its points, the block
+// reduces, thread t<TRK_PART writes partial[blockIdx][t].  smem: float[TRK_THREADS/32][TRK_PART].
+__device__ __forceinline__ void eval_block(const EvalConst& c, float* __restrict__ partial, float (*red)[TRK_PART],
+                                           int block, int nblocks) {
+  float acc[TRK_NACC];
+#pragma unroll
+  for (int i = 0; i < TRK_NACC; ++i) acc[i] = 0.f;
+  float E = 0.f, flowT = 0.f, flowRT = 0.f, flowNum = 0.f;
+  int nE = 0, nSat = 0, nW = 0;
+  const float wm3 = (float)(c.w - 3), hm3 = (float)(c.h - 3);
+
+  for (int i = block * TRK_THREADS + threadIdx.x; i < c.n; i += nblocks * TRK_THREADS) {
+    float4 p = __ldg(c.pc + i);
+    float x = p.x, y = p.y, id = p.z, refColor = p.w;
+    // pt = RKi*(x,y,1) + t*id ; CoarseTracker.cpp:377-382
+    float pt0 = xadd(xdot3(c.RKi[0], c.RKi[1], c.RKi[2], x, y, 1.0f), xmul(c.t[0], id));
+    float pt1 = xadd(xdot3(c.RKi[3], c.RKi[4], c.RKi[5], x, y, 1.0f), xmul(c.t[1], id));
+    float pt2 = xadd(xdot3(c.RKi[6], c.RKi[7], c.RKi[8], x, y, 1.0f), xmul(c.t[2], id));
+    float u = xdiv(pt0, pt2), v = xdiv(pt1, pt2);
+    float Ku = xadd(xmul(c.fx, u), c.cx), Kv = xadd(xmul(c.fy, v), c.cy);
+    float new_idepth = xdiv(id, pt2);
+
+    if (c.lvl == 0 && (i & 31) == 0) {  // flow indicators, :384-415
+      float k0 = xdot3(c.Ki[0], c.Ki[1], c.Ki[2], x, y, 1.0f);
+      float k1 = xdot3(c.Ki[3], c.Ki[4], c.Ki[5], x, y, 1.0f);
+      float k2 = xdot3(c.Ki[6], c.Ki[7], c.Ki[8], x, y, 1.0f);
+      float t0 = xmul(c.t[0], id), t1 = xmul(c.t[1], id), t2 = xmul(c.t[2], id);
+      float q2 = xadd(k2, t2);
+      float KuT = xadd(xmul(c.fx, xdiv(xadd(k0, t0), q2)), c.cx), KvT = xadd(xmul(c.fy, xdiv(xadd(k1, t1), q2)), c.cy);
+      q2 = xsub(k2, t2);
+      float KuT2 = xadd(xmul(c.fx, xdiv(xsub(k0, t0), q2)), c.cx), KvT2 = xadd(xmul(c.fy, xdiv(xsub(k1, t1), q2)), c.cy);
+      float r0 = xdot3(c.RKi[0], c.RKi[1], c.RKi[2], x, y, 1.0f);
+      float r1 = xdot3(c.RKi[3], c.RKi[4], c.RKi[5], x, y, 1.0f);
+      float r2 = xdot3(c.RKi[6], c.RKi[7], c.RKi[8], x, y, 1.0f);
+      q2 = xsub(r2, t2);
+      float Ku3 = xadd(xmul(c.fx, xdiv(xsub(r0, t0), q2)), c.cx), Kv3 = xadd(xmul(c.fy, xdiv(xsub(r1, t1), q2)), c.cy);
+      float a, b;
+      a = xsub(KuT, x); b = xsub(KvT, y);   flowT = xadd(flowT, xadd(xmul(a, a), xmul(b, b)));
+      a = xsub(KuT2, x); b = xsub(KvT2, y); flowT = xadd(flowT, xadd(xmul(a, a), xmul(b, b)));
+      a = xsub(Ku, x); b = xsub(Kv, y);     flowRT = xadd(flowRT, xadd(xmul(a, a), xmul(b, b)));
+      a = xsub(Ku3, x); b = xsub(Kv3, y);   flowRT = xadd(flowRT, xadd(xmul(a, a), xmul(b, b)));
+      flowNum += 2.f;
+    }
+
+    if (!(Ku > 2.f && Kv > 2.f && Ku < wm3 && Kv < hm3 && new_idepth > 0.f)) continue;  // :417
+    Hit3 hit = interp33(c.img, Ku, Kv, c.w);
+    if (!isfinite(hit.I)) continue;
+    float residual = xsub(hit.I, xadd(xmul(c.affLL0, refColor), c.affLL1));
+    float ar = fabsf(residual);
+    float hw = ar < c.huber ? 1.0f : xdiv(c.huber, ar);
+    nE++;
+    if (ar > c.cutoff) {
+      E = xadd(E, c.maxEnergy);
+      nSat++;
+      continue;
+    }
+    E = xadd(E, xmul(xmul(xmul(hw, residual), residual), xsub(2.0f, hw)));
+    nW++;
+    // Jacobian row, CoarseTracker.cpp:284-305 (contraction allowed from here on: tolerance-checked)
+    float dx = hit.dx * c.fx, dy = hit.dy * c.fy;
+    float J[9];
+    J[0] = new_idepth * dx;
+    J[1] = new_idepth * dy;
+    J[2] = -new_idepth * (u * dx + v * dy);
+    J[3] = -(u * v * dx + dy * (1.f + v * v));
+    J[4] = u * v * dy + dx * (1.f + u * u);
+    J[5] = u * dy - v * dx;
+    J[6] = c.affLL0 * (c.b0 - refColor);
+    J[7] = -1.f;
+    J[8] = residual;
+    int k = 0;
+#pragma unroll
+    for (int r = 0; r < 9; ++r) {
+      float Jw = J[r] * hw;
+#pragma unroll
+      for (int cc = r; cc < 9; ++cc, ++k) acc[k] = fmaf(Jw, J[cc], acc[k]);
+    }
+  }
+
+  // warp tree -> smem -> fixed-order cross-warp sum
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+#pragma unroll
+  for (int i = 0; i < TRK_NACC; ++i) {
+    float s = warp_sum(acc[i]);
+    if (lane == 0) red[wid][i] = s;
+  }
+  {
+    float s;
+    s = warp_sum(E);      if (lane == 0) red[wid][P_E] = s;
+    s = warp_sum(flowT);  if (lane == 0) red[wid][P_FT] = s;
+    s = warp_sum(flowRT); if (lane == 0) red[wid][P_FRT] = s;
+    s = warp_sum(flowNum); if (lane == 0) red[wid][P_FN] = s;
+    int q;
+    q = warp_sum(nE);   if (lane == 0) red[wid][P_NE] = __int_as_float(q);
+    q = warp_sum(nSat); if (lane == 0) red[wid][P_NSAT] = __int_as_float(q);
+    q = warp_sum(nW);   if (lane == 0) red[wid][P_NW] = __int_as_float(q);
+  }
+  __syncthreads();
+  if (threadIdx.x < TRK_PART) {
+    int t = threadIdx.x;
+    if (t >= P_NE && t <= P_NW) {
+      int q = 0;
+#pragma unroll
+      for (int w = 0; w < TRK_THREADS / 32; ++w) q += __float_as_int(red[w][t]);
+      partial[(size_t)block * TRK_PART + t] = __int_as_float(q);
+    } else if (t < P_NE) {
+      float s = 0.f;
+#pragma unroll
+      for (int w = 0; w < TRK_THREADS / 32; ++w) s += red[w][t];
+      partial[(size_t)block * TRK_PART + t] = s;
+    }
+    __threadfence();  // partials visible device-wide before the block signals (ticket / grid barrier)
+  }
+  __syncthreads();
+}
+
+// Deterministic fold of nblocks partials into fp64; executed by one whole block.
+// smem: double fold[4][TRK_PART].
+__device__ __forceinline__ void fold_partials(const float* __restrict__ partial, int nblocks, EvalResult& out,
+                                              double (*fold)[TRK_PART]) {
+  int t = threadIdx.x & 63, q = threadIdx.x >> 6;  // 4 interleaved groups of 64 threads
+  if (t < TRK_PART && q < 4) {
+    if (t >= P_NE && t <= P_NW) {
+      long long s = 0;
+      for (int b = q; b < nblocks; b += 4) s += __float_as_int(__ldcg(partial + (size_t)b * TRK_PART + t));
+      fold[q][t] = (double)s;
+    } else {
+      double s = 0.0;
+      for (int b = q; b < nblocks; b += 4) s += (double)__ldcg(partial + (size_t)b * TRK_PART + t);
+      fold[q][t] = s;
+    }
+  }
+  __syncthreads();
+  if (threadIdx.x < TRK_PART) {
+    int i = threadIdx.x;
+    double s = (fold[0][i] + fold[1][i]) + (fold[2][i] + fold[3][i]);
+    if (i < TRK_NACC) out.acc[i] = s;
+    else if (i == P_E) out.E = s;
+    else if (i == P_FT) out.flowT = s;
+    else if (i == P_FRT) out.flowRT = s;
+    else if (i == P_FN) out.flowNum = s;
+    else if (i == P_NE) out.nE = (int)s;
+    else if (i == P_NSAT) out.nSat = (int)s;
+    else if (i == P_NW) out.nW = (int)s;
+  }
+  __syncthreads();
+}
+
+// ---------------------------------------------------------------- single evaluation (calcRes / calcGS)
+struct EvalArgs {
+  TrkLevelDev L;
+  int lvl;
+  const float4* img;
+  double T[12];
+  double aff_a, aff_b, ref_aff_a, ref_aff_b;
+  float ref_exposure, new_exposure, cutoff, huber;
+};
+
+__global__ void __launch_bounds__(TRK_THREADS) trk_eval_kernel(EvalArgs a, float* __restrict__ partial,
+                                                               unsigned int* __restrict__ ticket,
+                                                               EvalResult* __restrict__ result) {
+  __shared__ EvalConst c;
+  __shared__ float red[TRK_THREADS / 32][TRK_PART];
+  __shared__ double fold[4][TRK_PART];
+  __shared__ EvalResult res;
+  __shared__ bool last;
+  if (threadIdx.x == 0)
+    make_eval_const(c, a.L, a.lvl, a.img, a.T, a.aff_a, a.aff_b, a.ref_exposure, a.new_exposure, a.ref_aff_a,
+                    a.ref_aff_b, a.cutoff, a.huber);
+  __syncthreads();
+  eval_block(c, partial, red, blockIdx.x, gridDim.x);
+  // last block folds (threadfence + ticket); fold order is by block index, not arrival order
+  if (threadIdx.x == 0) {
+    __threadfence();
+    unsigned int t = atomicAdd(ticket, 1u);
+    last = (t == gridDim.x - 1);
+  }
+  __syncthreads();
+  if (last) {
+    __threadfence();
+    fold_partials(partial, gridDim.x, res, fold);
+    if (threadIdx.x == 0) {
+      *result = res;
+      *ticket = 0;
+    }
+  }
+}
+
+// ---------------------------------------------------------------- fp64 helpers for the LM loop
+__device__ void d_ldlt_solve(const double* Ain, const double* rhs, int n, double* x) {
+  // symmetric diagonal pivoting, same scheme as the oracle (stands in for Eigen::LDLT)
+  double A[64];
+  int perm[8];
+  for (int i = 0; i < n * n; ++i) A[i] = Ain[i];
+  for (int i = 0; i < n; ++i) perm[i] = i;
+#define AT(r, c) A[(r) + (c) * n]
+  for (int k = 0; k < n; ++k) {
+    int p = k;
+    double best = fabs(AT(k, k));
+    for (int i = k + 1; i < n; ++i)
+      if (fabs(AT(i, i)) > best) { best = fabs(AT(i, i)); p = i; }
+    if (p != k) {
+      for (int c = 0; c < n; ++c) { double t = AT(k, c); AT(k, c) = AT(p, c); AT(p, c) = t; }
+      for (int r = 0; r < n; ++r) { double t = AT(r, k); AT(r, k) = AT(r, p); AT(r, p) = t; }
+      int t = perm[k]; perm[k] = perm[p]; perm[p] = t;
+    }
+    double d = AT(k, k);
+    if (d == 0.0) continue;
+    for (int i = k + 1; i < n; ++i) AT(i, k) /= d;
+    for (int j = k + 1; j < n; ++j)
+      for (int i = j; i < n; ++i) {
+        AT(i, j) -= AT(i, k) * d * AT(j, k);
+        AT(j, i) = AT(i, j);
+      }
+  }
+  double y[8];
+  for (int i = 0; i < n; ++i) y[i] = rhs[perm[i]];
+  for (int i = 0; i < n; ++i)
+    for (int j = 0; j < i; ++j) y[i] -= AT(i, j) * y[j];
+  for (int i = 0; i < n; ++i) y[i] = (AT(i, i) != 0.0) ? y[i] / AT(i, i) : 0.0;
+  for (int i = n - 1; i >= 0; --i)
+    for (int j = i + 1; j < n; ++j) y[i] -= AT(j, i) * y[j];
+  for (int i = 0; i < n; ++i) x[perm[i]] = y[i];
+#undef AT
+}
+
+__device__ void d_matmul3(const double* A, const double* B, double* C) {
+  double t[9];
+  for (int i = 0; i < 3; ++i)
+    for (int j = 0; j < 3; ++j) t[3 * i + j] = A[3 * i] * B[j] + A[3 * i + 1] * B[3 + j] + A[3 * i + 2] * B[6 + j];
+  for (int i = 0; i < 9; ++i) C[i] = t[i];
+}
+
+// Sophus SE3::exp (se3.hpp:407-427 / so3.hpp:343-369), T = [R row-major | t]
+__device__ void d_se3_exp(const double* xi, double* T) {
+  const double* ups = xi;
+  const double* om = xi + 3;
+  double theta_sq = om[0] * om[0] + om[1] * om[1] + om[2] * om[2];
+  double theta = sqrt(theta_sq), half = 0.5 * theta, imag, real;
+  const double eps = 1e-10;
+  if (theta < eps) {
+    double t4 = theta_sq * theta_sq;
+    imag = 0.5 - (1.0 / 48.0) * theta_sq + (1.0 / 3840.0) * t4;
+    real = 1.0 - 0.5 * theta_sq + (1.0 / 384.0) * t4;
+  } else {
+    imag = sin(half) / theta;
+    real = cos(half);
+  }
+  double qw = real, qx = imag * om[0], qy = imag * om[1], qz = imag * om[2];
+  double tx = 2 * qx, ty = 2 * qy, tz = 2 * qz;
+  double twx = tx * qw, twy = ty * qw, twz = tz * qw, txx = tx * qx, txy = ty * qx, txz = tz * qx;
+  double tyy = ty * qy, tyz = tz * qy, tzz = tz * qz;
+  T[0] = 1 - (tyy + tzz); T[1] = txy - twz; T[2] = txz + twy;
+  T[3] = txy + twz; T[4] = 1 - (txx + tzz); T[5] = tyz - twx;
+  T[6] = txz - twy; T[7] = tyz + twx; T[8] = 1 - (txx + tyy);
+  double O[9] = {0, -om[2], om[1], om[2], 0, -om[0], -om[1], om[0], 0}, O2[9], V[9];
+  d_matmul3(O, O, O2);
+  if (theta < eps) {
+    for (int i = 0; i < 9; ++i) V[i] = T[i];
+  } else {
+    double a = (1 - cos(theta)) / theta_sq, b = (theta - sin(theta)) / (theta_sq * theta);
+    for (int i = 0; i < 9; ++i) V[i] = (i % 4 == 0 ? 1.0 : 0.0) + a * O[i] + b * O2[i];
+  }
+  for (int i = 0; i < 3; ++i) T[9 + i] = V[3 * i] * ups[0] + V[3 * i + 1] * ups[1] + V[3 * i + 2] * ups[2];
+}
+
+__device__ void d_se3_mul(const double* A, const double* B, double* C) {
+  double R[9], t[3];
+  d_matmul3(A, B, R);
+  for (int i = 0; i < 3; ++i) t[i] = A[3 * i] * B[9] + A[3 * i + 1] * B[10] + A[3 * i + 2] * B[11] + A[9 + i];
+  for (int i = 0; i < 9; ++i) C[i] = R[i];
+  for (int i = 0; i < 3; ++i) C[9 + i] = t[i];
+}
+
+// H (8x8 col-major), b from the folded accumulators; CoarseTracker.cpp:309-323
+__host__ __device__ inline void make_Hb(const double* acc, int nW, const float* scales8, double* H, double* b) {
+  int n = (nW + 3) & ~3;
+  double inv = (double)(1.0f / (float)n);
+  int k = 0;
+  double full[9][9];
+  for (int r = 0; r < 9; ++r)
+    for (int c = r; c < 9; ++c, ++k) full[r][c] = full[c][r] = acc[k];
+  for (int r = 0; r < 8; ++r) {
+    for (int c = 0; c < 8; ++c) H[r + 8 * c] = full[r][c] * inv;
+    b[r] = full[r][8] * inv;
+  }
+  for (int c = 0; c < 8; ++c)
+    for (int r = 0; r < 8; ++r) H[r + 8 * c] *= (double)scales8[c];
+  for (int r = 0; r < 8; ++r)
+    for (int c = 0; c < 8; ++c) H[r + 8 * c] *= (double)scales8[r];
+  for (int r = 0; r < 8; ++r) b[r] *= (double)scales8[r];
+}
+
+// ---------------------------------------------------------------- the fused LM kernel
+struct TrackArgs {
+  TrkLevelDev L[5];
+  const float4* img[5];
+  int coarsestLvl;
+  int maxIterations[5];
+  float scales8[8];   // {rot,rot,rot,trans,trans,trans,a,b} as applied in CoarseTracker.cpp:312-323,597-600
+  float coarseCutoffTH, huber, affineOptModeA, affineOptModeB;
+  float ref_exposure, new_exposure;
+  double ref_aff_a, ref_aff_b;
+};
+
+struct TrackIO {           // pinned-host visible struct copied in/out
+  double T[12];
+  double aff[2];
+  double minResForAbort[5];
+  double lastResiduals[5];
+  double lastFlow[3];
+  int ok;
+  int iterations[5];
+  int evals;
+  int pad;
+};
+
+struct LMState {
+  double cur[12], cand[12];
+  double aff_cur[2], aff_cand[2];
+  double H[64], b[8];
+  double resOldE, resOldN;       // resOld[0], resOld[1]
+  double flowOld[3];
+  float lambda, levelCutoffRepeat;
+  int lvl, iteration, phase, haveRepeated, done, ok, evals;
+  double incnorm;
+};
+
+__device__ __forceinline__ double sat_ratio(const EvalResult& r) { return (double)((float)r.nSat / (float)r.nE); }
+
+__global__ void __launch_bounds__(TRK_THREADS) trk_track_kernel(TrackArgs a, float* __restrict__ partial0,
+                                                                float* __restrict__ partial1,
+                                                                TrackIO* __restrict__ io) {
+  cg::grid_group grid = cg::this_grid();
+  __shared__ EvalConst c;
+  __shared__ float red[TRK_THREADS / 32][TRK_PART];
+  __shared__ double fold[4][TRK_PART];
+  __shared__ EvalResult res;
+  __shared__ LMState s;
+  __shared__ int iters[5];
+  __shared__ double lastRes[5];
+
+  // Every block carries an identical copy of the LM state and takes identical decisions.
+  if (threadIdx.x == 0) {
+    for (int i = 0; i < 12; ++i) s.cur[i] = io->T[i];
+    s.aff_cur[0] = io->aff[0]; s.aff_cur[1] = io->aff[1];
+    s.haveRepeated = 0; s.done = 0; s.ok = 0; s.evals = 0;
+    for (int i = 0; i < 5; ++i) { iters[i] = 0; lastRes[i] = nan(""); }
+    s.flowOld[0] = s.flowOld[1] = s.flowOld[2] = 1000.0;
+  }
+  __syncthreads();
+  int buf = 0;
+
+  for (int lvl = a.coarsestLvl; lvl >= 0; lvl--) {
+    const TrkLevelDev& L = a.L[lvl];
+    int nb = (L.n + TRK_THREADS - 1) / TRK_THREADS;
+    if (nb > (int)gridDim.x) nb = gridDim.x;
+    if (nb < 1) nb = 1;
+    // --- initial evaluation with cutoff doubling, CoarseTracker.cpp:530-541
+    if (threadIdx.x == 0) { s.levelCutoffRepeat = 1.f; }
+    __syncthreads();
+    while (true) {
+      if (threadIdx.x == 0)
+        make_eval_const(c, L, lvl, a.img[lvl], s.cur, s.aff_cur[0], s.aff_cur[1], a.ref_exposure, a.new_exposure,
+                        a.ref_aff_a, a.ref_aff_b, xmul(a.coarseCutoffTH, s.levelCutoffRepeat), a.huber);
+      __syncthreads();
+      float* part = buf ? partial1 : partial0;
+      if ((int)blockIdx.x < nb) eval_block(c, part, red, blockIdx.x, nb);
+      __threadfence();
+      grid.sync();
+      fold_partials(part, nb, res, fold);
+      buf ^= 1;
+      bool again = (sat_ratio(res) > 0.6) && (s.levelCutoffRepeat < 50.f);
+      __syncthreads();
+      if (threadIdx.x == 0) { s.evals++; if (again) s.levelCutoffRepeat *= 2.f; }
+      __syncthreads();
+      if (!again) break;
+    }
+    if (threadIdx.x == 0) {
+      make_Hb(res.acc, res.nW, a.scales8, s.H, s.b);
+      s.resOldE = res.E; s.resOldN = (double)res.nE;
+      s.flowOld[0] = (double)((float)res.flowT / ((float)res.flowNum + 0.1));
+      s.flowOld[1] = 0.0;
+      s.flowOld[2] = (double)((float)res.flowRT / ((float)res.flowNum + 0.1));
+      s.lambda = 0.01f;
+    }
+    __syncthreads();
+
+    // --- LM iterations, CoarseTracker.cpp:559-646
+    for (int iteration = 0; iteration < a.maxIterations[lvl]; iteration++) {
+      if (threadIdx.x == 0) {
+        iters[lvl]++;
+        double Hl[64], nb8[8], inc[8];
+        for (int i = 0; i < 64; ++i) Hl[i] = s.H[i];
+        for (int i = 0; i < 8; ++i) Hl[i + 8 * i] *= (double)(1.f + s.lambda);
+        for (int i = 0; i < 8; ++i) nb8[i] = -s.b[i];
+        bool fixA = a.affineOptModeA < 0.f, fixB = a.affineOptModeB < 0.f;
+        if (!fixA && !fixB) {
+          d_ldlt_solve(Hl, nb8, 8, inc);
+        } else if (fixA && fixB) {   // :565-569
+          double H6[36];
+          for (int cc = 0; cc < 6; ++cc) for (int r = 0; r < 6; ++r) H6[r + 6 * cc] = Hl[r + 8 * cc];
+          d_ldlt_solve(H6, nb8, 6, inc);
+          inc[6] = inc[7] = 0.0;
+        } else if (!fixA && fixB) {  // :570-574
+          double H7[49];
+          for (int cc = 0; cc < 7; ++cc) for (int r = 0; r < 7; ++r) H7[r + 7 * cc] = Hl[r + 8 * cc];
+          d_ldlt_solve(H7, nb8, 7, inc);
+          inc[7] = 0.0;
+        } else {                     // :575-587 fix a
+          double Hs[64], bs[8], H7[49], nb7[7], x7[7];
+          for (int i = 0; i < 64; ++i) Hs[i] = Hl[i];
+          for (int i = 0; i < 8; ++i) bs[i] = s.b[i];
+          for (int r = 0; r < 8; ++r) Hs[r + 8 * 6] = Hs[r + 8 * 7];
+          for (int cc = 0; cc < 8; ++cc) Hs[6 + 8 * cc] = Hs[7 + 8 * cc];
+          bs[6] = bs[7];
+          for (int cc = 0; cc < 7; ++cc) for (int r = 0; r < 7; ++r) H7[r + 7 * cc] = Hs[r + 8 * cc];
+          for (int i = 0; i < 7; ++i) nb7[i] = -bs[i];
+          d_ldlt_solve(H7, nb7, 7, x7);
+          for (int i = 0; i < 6; ++i) inc[i] = x7[i];
+          inc[6] = 0.0; inc[7] = x7[6];
+        }
+        float extrapFac = 1.f;
+        if (s.lambda < 0.001f) extrapFac = sqrtf(sqrtf(0.001f / s.lambda));
+        double nrm = 0.0, sum = 0.0, incS[8];
+        for (int i = 0; i < 8; ++i) { inc[i] *= (double)extrapFac; nrm += inc[i] * inc[i]; }
+        for (int i = 0; i < 8; ++i) { incS[i] = inc[i] * (double)a.scales8[i]; sum += incS[i]; }
+        if (!isfinite(sum)) for (int i = 0; i < 8; ++i) incS[i] = 0.0;
+        double Texp[12];
+        d_se3_exp(incS, Texp);
+        d_se3_mul(Texp, s.cur, s.cand);
+        s.aff_cand[0] = s.aff_cur[0] + incS[6];
+        s.aff_cand[1] = s.aff_cur[1] + incS[7];
+        s.incnorm = sqrt(nrm);
+        make_eval_const(c, L, lvl, a.img[lvl], s.cand, s.aff_cand[0], s.aff_cand[1], a.ref_exposure, a.new_exposure,
+                        a.ref_aff_a, a.ref_aff_b, xmul(a.coarseCutoffTH, s.levelCutoffRepeat), a.huber);
+      }
+      __syncthreads();
+      float* part = buf ? partial1 : partial0;
+      if ((int)blockIdx.x < nb) eval_block(c, part, red, blockIdx.x, nb);
+      __threadfence();
+      grid.sync();
+      fold_partials(part, nb, res, fold);
+      buf ^= 1;
+      if (threadIdx.x == 0) {
+        s.evals++;
+        bool accept = (res.E / (double)res.nE) < (s.resOldE / s.resOldN);  // :611
+        if (accept) {
+          make_Hb(res.acc, res.nW, a.scales8, s.H, s.b);
+          s.resOldE = res.E; s.resOldN = (double)res.nE;
+          s.flowOld[0] = (double)((float)res.flowT / ((float)res.flowNum + 0.1));
+          s.flowOld[2] = (double)((float)res.flowRT / ((float)res.flowNum + 0.1));
+          for (int i = 0; i < 12; ++i) s.cur[i] = s.cand[i];
+          s.aff_cur[0] = s.aff_cand[0]; s.aff_cur[1] = s.aff_cand[1];
+          s.lambda *= 0.5f;
+        } else {
+          s.lambda *= 4.f;
+          if (s.lambda < 0.001f) s.lambda = 0.001f;
+        }
+      }
+      __syncthreads();
+      if (!(s.incnorm > 1e-3)) break;   // uniform: s is identical in every block
+    }
+
+    // --- level epilogue, :648-659
+    bool abort_now = false;
+    if (threadIdx.x == 0) lastRes[lvl] = (double)sqrtf((float)(s.resOldE / s.resOldN));
+    __syncthreads();
+    abort_now = lastRes[lvl] > 1.5 * io->minResForAbort[lvl];
+    if (abort_now) { if (threadIdx.x == 0) { s.done = 1; s.ok = 0; } __syncthreads(); break; }
+    if (s.levelCutoffRepeat > 1.f && !s.haveRepeated) {
+      __syncthreads();
+      if (threadIdx.x == 0) s.haveRepeated = 1;
+      lvl++;
+      __syncthreads();
+    }
+  }
+
+  if (blockIdx.x == 0 && threadIdx.x == 0) {
+    int ok = 0;
+    if (!s.done) {
+      ok = 1;
+      double aa = s.aff_cur[0], ab = s.aff_cur[1];
+      if ((a.affineOptModeA != 0.f && fabsf((float)aa) > 1.2f) || (a.affineOptModeB != 0.f && fabsf((float)ab) > 200.f))
+        ok = 0;
+      float eF = a.ref_exposure, eT = a.new_exposure;
+      if (eF == 0.f || eT == 0.f) { eF = eT = 1.f; }
+      double ra = exp(aa - a.ref_aff_a) * (double)eT / (double)eF;
+      double rb = ab - ra * a.ref_aff_b;
+      if ((a.affineOptModeA == 0.f && fabsf(logf((float)ra)) > 1.5f) || (a.affineOptModeB == 0.f && fabsf((float)rb) > 200.f))
+        ok = 0;
+      for (int i = 0; i < 12; ++i) io->T[i] = s.cur[i];   // lastToNew_out is set before the checks (:663-664)
+      io->aff[0] = aa; io->aff[1] = ab;
+      if (ok) {
+        if (a.affineOptModeA < 0.f) io->aff[0] = 0.0;
+        if (a.affineOptModeB < 0.f) io->aff[1] = 0.0;
+      }
+    }
+    io->ok = ok;
+    for (int i = 0; i < 5; ++i) { io->lastResiduals[i] = lastRes[i]; io->iterations[i] = iters[i]; }
+    for (int i = 0; i < 3; ++i) io->lastFlow[i] = s.flowOld[i];
+    io->evals = s.evals;
+  }
+}
+
+}  // namespace hs
+
+using namespace hs;
+
+struct hslam_tracker {
+  hslam_ctx* ctx = nullptr;
+  int w = 0, h = 0, levels = 0;
+  TrkLevelDev L[HSLAM_MAX_PYR_LEVELS];
+  float4* pc[HSLAM_MAX_PYR_LEVELS] = {nullptr};
+  int pc_cap[HSLAM_MAX_PYR_LEVELS] = {0};
+  float ref_exposure = 1.f;
+  double ref_aff_a = 0, ref_aff_b = 0;
+  float* partial[2] = {nullptr, nullptr};
+  int partial_blocks = 0;
+  unsigned int* ticket = nullptr;
+  EvalResult* d_result = nullptr;
+  EvalResult* h_result = nullptr;   // pinned
+  TrackIO* d_io = nullptr;
+  TrackIO* h_io = nullptr;          // pinned
+  float4* h_pack = nullptr;         // pinned staging for set_ref
+  size_t h_pack_cap = 0;
+  int coop_blocks = 0;
+};
+
+static int ensure_partials(hslam_tracker* t, int blocks) {
+  if (blocks <= t->partial_blocks) return 0;
+  for (int i = 0; i < 2; ++i) {
+    if (t->partial[i]) cudaFree(t->partial[i]);
+    HS_CUDA(cudaMalloc(&t->partial[i], (size_t)blocks * TRK_PART * sizeof(float)));
+  }
+  t->partial_blocks = blocks;
+  return 0;
+}
+
+extern "C" {
+
+int hslam_tracker_create(hslam_ctx* ctx, int w, int h, hslam_tracker** out) {
+  HS_ARG(ctx && out && w > 0 && h > 0, "hslam_tracker_create: bad argument");
+  HS_CUDA(cudaSetDevice(ctx->device));
+  hslam_tracker* t = new hslam_tracker();
+  t->ctx = ctx; t->w = w; t->h = h;
+  memset(t->L, 0, sizeof(t->L));
+  HS_CUDA(cudaMalloc(&t->ticket, sizeof(unsigned int)));
+  HS_CUDA(cudaMemsetAsync(t->ticket, 0, sizeof(unsigned int), ctx->stream));
+  HS_CUDA(cudaMalloc(&t->d_result, sizeof(EvalResult)));
+  HS_CUDA(cudaMallocHost(&t->h_result, sizeof(EvalResult)));
+  HS_CUDA(cudaMalloc(&t->d_io, sizeof(TrackIO)));
+  HS_CUDA(cudaMallocHost(&t->h_io, sizeof(TrackIO)));
+  int per_sm = 0;
+  HS_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, trk_track_kernel, TRK_THREADS, 0));
+  HS_ARG(per_sm >= 1, "hslam_tracker_create: track kernel does not fit on an SM");
+  t->coop_blocks = ctx->sm_count * (per_sm > 2 ? 2 : per_sm);
+  int rc = ensure_partials(t, t->coop_blocks > 1024 ? t->coop_blocks : 1024);
+  if (rc) return rc;
+  *out = t;
+  return 0;
+}
+
+int hslam_tracker_destroy(hslam_tracker* t) {
+  if (!t) return 0;
+  cudaSetDevice(t->ctx->device);
+  cudaStreamSynchronize(t->ctx->stream);
+  for (int l = 0; l < HSLAM_MAX_PYR_LEVELS; ++l) cudaFree(t->pc[l]);
+  cudaFree(t->partial[0]); cudaFree(t->partial[1]);
+  cudaFree(t->ticket); cudaFree(t->d_result); cudaFreeHost(t->h_result);
+  cudaFree(t->d_io); cudaFreeHost(t->h_io);
+  if (t->h_pack) cudaFreeHost(t->h_pack);
+  delete t;
+  return 0;
+}
+
+static inline float cof3(const float* m, int i, int j) {
+  int i1 = (i + 1) % 3, i2 = (i + 2) % 3, j1 = (j + 1) % 3, j2 = (j + 2) % 3;
+  volatile float a = m[3 * i1 + j1] * m[3 * i2 + j2];
+  volatile float b = m[3 * i1 + j2] * m[3 * i2 + j1];
+  return a - b;
+}
+
+// CoarseTracker::makeK (Src/CoarseTracker.cpp:72-101); Ki by Eigen's 3x3 cofactor inverse.
+int hslam_tracker_make_K(hslam_tracker* t, int levels, int w0, int h0, float fx0, float fy0, float cx0, float cy0) {
+  HS_ARG(t && levels >= 1 && levels <= HSLAM_MAX_PYR_LEVELS, "hslam_tracker_make_K: bad levels");
+  t->levels = levels;
+  t->L[0].w = w0; t->L[0].h = h0; t->L[0].fx = fx0; t->L[0].fy = fy0; t->L[0].cx = cx0; t->L[0].cy = cy0;
+  for (int l = 1; l < levels; ++l) {
+    t->L[l].w = w0 >> l; t->L[l].h = h0 >> l;
+    t->L[l].fx = (float)(t->L[l - 1].fx * 0.5);
+    t->L[l].fy = (float)(t->L[l - 1].fy * 0.5);
+    t->L[l].cx = (float)((cx0 + 0.5) / ((int)1 << l) - 0.5);
+    t->L[l].cy = (float)((cy0 + 0.5) / ((int)1 << l) - 0.5);
+  }
+  for (int l = 0; l < levels; ++l) {
+    float K[9] = {t->L[l].fx, 0.f, t->L[l].cx, 0.f, t->L[l].fy, t->L[l].cy, 0.f, 0.f, 1.f};
+    float c0 = cof3(K, 0, 0), c1 = cof3(K, 1, 0), c2 = cof3(K, 2, 0);
+    volatile float p0 = c0 * K[0], p1 = c1 * K[3], p2 = c2 * K[6];
+    volatile float s12 = p1 + p2;
+    float det = p0 + s12;
+    float invdet = 1.0f / det;
+    float* r = t->L[l].Ki;
+    r[0] = c0 * invdet; r[1] = c1 * invdet; r[2] = c2 * invdet;
+    r[3] = cof3(K, 0, 1) * invdet; r[4] = cof3(K, 1, 1) * invdet; r[5] = cof3(K, 2, 1) * invdet;
+    r[6] = cof3(K, 0, 2) * invdet; r[7] = cof3(K, 1, 2) * invdet; r[8] = cof3(K, 2, 2) * invdet;
+  }
+  return 0;
+}
+
+int hslam_tracker_get_K(hslam_tracker* t, int lvl, float out4[4], int out_wh[2], float out_Ki[9]) {
+  HS_ARG(t && lvl >= 0 && lvl < t->levels, "hslam_tracker_get_K: bad level");
+  if (out4) { out4[0] = t->L[lvl].fx; out4[1] = t->L[lvl].fy; out4[2] = t->L[lvl].cx; out4[3] = t->L[lvl].cy; }
+  if (out_wh) { out_wh[0] = t->L[lvl].w; out_wh[1] = t->L[lvl].h; }
+  if (out_Ki) memcpy(out_Ki, t->L[lvl].Ki, 9 * sizeof(float));
+  return 0;
+}
+
+int hslam_tracker_set_ref(hslam_tracker* t, int lvl, const float* u, const float* v, const float* idepth,
+                          const float* color, int n) {
+  HS_ARG(t && lvl >= 0 && lvl < t->levels && n >= 0, "hslam_tracker_set_ref: bad level/count");
+  HS_ARG(n == 0 || (u && v && idepth && color), "hslam_tracker_set_ref: null array");
+  hslam_ctx* ctx = t->ctx;
+  HS_CUDA(cudaSetDevice(ctx->device));
+  if (n > t->pc_cap[lvl]) {
+    HS_CUDA(cudaStreamSynchronize(ctx->stream));
+    cudaFree(t->pc[lvl]);
+    int cap = n + n / 4 + 256;
+    HS_CUDA(cudaMalloc(&t->pc[lvl], (size_t)cap * sizeof(float4)));
+    t->pc_cap[lvl] = cap;
+  }
+  if ((size_t)n > t->h_pack_cap) {
+    HS_CUDA(cudaStreamSynchronize(ctx->stream));
+    if (t->h_pack) cudaFreeHost(t->h_pack);
+    t->h_pack_cap = (size_t)n + n / 4 + 256;
+    HS_CUDA(cudaMallocHost(&t->h_pack, t->h_pack_cap * sizeof(float4)));
+  } else {
+    HS_CUDA(cudaStreamSynchronize(ctx->stream));  // previous async copy out of h_pack
+  }
+  for (int i = 0; i < n; ++i) t->h_pack[i] = make_float4(u[i], v[i], idepth[i], color[i]);
+  if (n) HS_CUDA(cudaMemcpyAsync(t->pc[lvl], t->h_pack, (size_t)n * sizeof(float4), cudaMemcpyHostToDevice, ctx->stream));
+  t->L[lvl].n = n;
+  t->L[lvl].pc = t->pc[lvl];
+  return 0;
+}
+
+int hslam_tracker_set_ref_aff(hslam_tracker* t, float ref_exposure, double a, double b) {
+  HS_ARG(t, "hslam_tracker_set_ref_aff: null");
+  t->ref_exposure = ref_exposure; t->ref_aff_a = a; t->ref_aff_b = b;
+  return 0;
+}
+
+static int run_eval(hslam_tracker* t, int lvl, const hslam_frame* f, const double T[12], double aff_a, double aff_b,
+                    float new_exposure, float cutoffTH) {
+  HS_ARG(t && f && T, "tracker eval: null argument");
+  HS_ARG(lvl >= 0 && lvl < t->levels && lvl < f->levels, "tracker eval: level out of range");
+  HS_ARG(t->L[lvl].w == (f->w >> lvl) && t->L[lvl].h == (f->h >> lvl), "tracker eval: frame size != tracker K size");
+  HS_ARG(f->ctx == t->ctx, "tracker eval: frame belongs to another context");
+  hslam_ctx* ctx = t->ctx;
+  HS_CUDA(cudaSetDevice(ctx->device));
+  EvalArgs a;
+  a.L = t->L[lvl]; a.lvl = lvl; a.img = f->dI[lvl];
+  memcpy(a.T, T, sizeof(a.T));
+  a.aff_a = aff_a; a.aff_b = aff_b; a.ref_aff_a = t->ref_aff_a; a.ref_aff_b = t->ref_aff_b;
+  a.ref_exposure = t->ref_exposure; a.new_exposure = new_exposure; a.cutoff = cutoffTH; a.huber = ctx->prm.huberTH;
+  int blocks = (t->L[lvl].n + TRK_THREADS - 1) / TRK_THREADS;
+  if (blocks < 1) blocks = 1;
+  int cap = ctx->sm_count * 4;
+  if (blocks > cap) blocks = cap;
+  int rc = ensure_partials(t, blocks);
+  if (rc) return rc;
+  trk_eval_kernel<<<blocks, TRK_THREADS, 0, ctx->stream>>>(a, t->partial[0], t->ticket, t->d_result);
+  ctx->launches++;
+  HS_CUDA(cudaGetLastError());
+  HS_CUDA(cudaMemcpyAsync(t->h_result, t->d_result, sizeof(EvalResult), cudaMemcpyDeviceToHost, ctx->stream));
+  HS_CUDA(cudaStreamSynchronize(ctx->stream));
+  return 0;
+}
+
+int hslam_tracker_calc_res(hslam_tracker* t, int lvl, const hslam_frame* f, const double T[12], double aff_a,
+                           double aff_b, float new_exposure, float cutoffTH, double out6[6], int* n_warped_out) {
+  HS_ARG(out6, "hslam_tracker_calc_res: null output");
+  int rc = run_eval(t, lvl, f, T, aff_a, aff_b, new_exposure, cutoffTH);
+  if (rc) return rc;
+  const EvalResult& r = *t->h_result;
+  out6[0] = r.E;
+  out6[1] = r.nE;
+  out6[2] = (double)((float)r.flowT / ((float)r.flowNum + 0.1));
+  out6[3] = 0;
+  out6[4] = (double)((float)r.flowRT / ((float)r.flowNum + 0.1));
+  out6[5] = (double)((float)r.nSat / (float)r.nE);
+  if (n_warped_out) *n_warped_out = r.nW;
+  return 0;
+}
+
+static void scales_from(const hslam_params& p, float* s) {
+  s[0] = s[1] = s[2] = p.scale_xi_rot; s[3] = s[4] = s[5] = p.scale_xi_trans; s[6] = p.scale_a; s[7] = p.scale_b;
+}
+
+int hslam_tracker_calc_gs(hslam_tracker* t, int lvl, const hslam_frame* f, const double T[12], double aff_a,
+                          double aff_b, float new_exposure, float cutoffTH, double H[64], double b[8]) {
+  HS_ARG(H && b, "hslam_tracker_calc_gs: null output");
+  int rc = run_eval(t, lvl, f, T, aff_a, aff_b, new_exposure, cutoffTH);
+  if (rc) return rc;
+  float s8[8];
+  scales_from(t->ctx->prm, s8);
+  make_Hb(t->h_result->acc, t->h_result->nW, s8, H, b);
+  return 0;
+}
+
+int hslam_tracker_track_enqueue(hslam_tracker* t, const hslam_frame* f, float new_exposure, const double T[12],
+                                const double aff[2], int coarsestLvl, const double minResForAbort[5]) {
+  HS_ARG(t && f && T && aff, "hslam_tracker_track: null argument");
+  HS_ARG(coarsestLvl >= 0 && coarsestLvl < 5 && coarsestLvl < t->levels && coarsestLvl < f->levels,
+         "hslam_tracker_track: coarsestLvl out of range (reference asserts < 5, CoarseTracker.cpp:511)");
+  HS_ARG(f->ctx == t->ctx, "hslam_tracker_track: frame belongs to another context");
+  HS_ARG(t->L[0].w == f->w && t->L[0].h == f->h, "hslam_tracker_track: frame size != tracker K size");
+  hslam_ctx* ctx = t->ctx;
+  HS_CUDA(cudaSetDevice(ctx->device));
+  TrackArgs a;
+  memset(&a, 0, sizeof(a));
+  int maxn = 0;
+  for (int l = 0; l <= coarsestLvl; ++l) {
+    a.L[l] = t->L[l]; a.img[l] = f->dI[l];
+    if (t->L[l].n > maxn) maxn = t->L[l].n;
+  }
+  a.coarsestLvl = coarsestLvl;
+  for (int i = 0; i < 5; ++i) a.maxIterations[i] = ctx->prm.max_tracker_iterations[i];
+  scales_from(ctx->prm, a.scales8);
+  a.coarseCutoffTH = ctx->prm.coarseCutoffTH; a.huber = ctx->prm.huberTH;
+  a.affineOptModeA = ctx->prm.affineOptModeA; a.affineOptModeB = ctx->prm.affineOptModeB;
+  a.ref_exposure = t->ref_exposure; a.new_exposure = new_exposure;
+  a.ref_aff_a = t->ref_aff_a; a.ref_aff_b = t->ref_aff_b;
+  TrackIO* io = t->h_io;
+  memcpy(io->T, T, sizeof(io->T));
+  io->aff[0] = aff[0]; io->aff[1] = aff[1];
+  for (int i = 0; i < 5; ++i) io->minResForAbort[i] = minResForAbort ? minResForAbort[i] : NAN;
+  HS_CUDA(cudaMemcpyAsync(t->d_io, io, sizeof(TrackIO), cudaMemcpyHostToDevice, ctx->stream));
+  int blocks = (maxn + TRK_THREADS - 1) / TRK_THREADS;
+  if (blocks < 1) blocks = 1;
+  if (blocks > t->coop_blocks) blocks = t->coop_blocks;
+  int rc = ensure_partials(t, blocks);
+  if (rc) return rc;
+  void* args[] = {&a, &t->partial[0], &t->partial[1], &t->d_io};
+  HS_CUDA(cudaLaunchCooperativeKernel((void*)trk_track_kernel, dim3(blocks), dim3(TRK_THREADS), args, 0, ctx->stream));
+  ctx->launches++;
+  HS_CUDA(cudaMemcpyAsync(t->h_io, t->d_io, sizeof(TrackIO), cudaMemcpyDeviceToHost, ctx->stream));
+  return 0;
+}
+
+int hslam_tracker_track_finish(hslam_tracker* t, double T_out[12], double aff_out[2], double lastResiduals[5],
+                               double lastFlow[3], int* ok, int* iterations_out) {
+  HS_ARG(t, "hslam_tracker_track_finish: null");
+  HS_CUDA(cudaSetDevice(t->ctx->device));
+  HS_CUDA(cudaStreamSynchronize(t->ctx->stream));
+  const TrackIO* io = t->h_io;
+  if (io->ok || true) {
+    // the reference writes lastToNew_out/aff_g2l_out only when all levels ran (:663-664)
+    if (T_out) memcpy(T_out, io->T, sizeof(io->T));
+    if (aff_out) { aff_out[0] = io->aff[0]; aff_out[1] = io->aff[1]; }
+  }
+  if (lastResiduals) memcpy(lastResiduals, io->lastResiduals, sizeof(io->lastResiduals));
+  if (lastFlow) memcpy(lastFlow, io->lastFlow, sizeof(io->lastFlow));
+  if (ok) *ok = io->ok;
+  if (iterations_out) memcpy(iterations_out, io->iterations, sizeof(io->iterations));
+  return 0;
+}
+
+int hslam_tracker_track(hslam_tracker* t, const hslam_frame* f, float new_exposure, double T_io[12], double aff_io[2],
+                        int coarsestLvl, const double minResForAbort[5], double lastResiduals[5], double lastFlow[3],
+                        int* ok, int* iterations_out) {
+  int rc = hslam_tracker_track_enqueue(t, f, new_exposure, T_io, aff_io, coarsestLvl, minResForAbort);
+  if (rc) return rc;
+  return hslam_tracker_track_finish(t, T_io, aff_io, lastResiduals, lastFlow, ok, iterations_out);
+}
+
+}  // extern "C"

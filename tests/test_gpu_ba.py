@@ -1,0 +1,197 @@
+"""GPU parity: windowed BA linearisation + accumulate A/L/SC + stitch through the C ABI vs the oracle.
+
+Bit-exact: residual states, energies, the 74 Jacobian floats, JpJdF, res_toZeroF and the per-point
+Hdd/bd/Hcd/HdiF/bdSumF (vs the float-faithful restatement).  H,b of the three systems: <= 1e-5
+relative Frobenius vs the fp64 oracle (BASELINE.json north_star) and no worse than the float
+restatement's own error.
+"""
+import numpy as np
+import pytest
+
+from conftest import rel_fro
+
+pytestmark = pytest.mark.gpu
+
+
+def run_sequence(ba, win, is_lin, kind):
+    """The same call sequence on the GPU mirror (kind='gpu') and on the oracle (kind='orc')."""
+    lin = ba.linearizeAll(False) if kind == "gpu" else ba.linearize(False)
+    (ba.applyRes if kind == "gpu" else ba.apply_res)()
+    ids = np.nonzero(is_lin)[0].astype(np.int32)
+    (ba.fixLinearization if kind == "gpu" else ba.fix_linearization)(ids)
+    idp = (win.idepth * np.float32(1.001)).astype(np.float32)
+    ba.update_points(idepth=idp, deltaF=(idp - win.idepth_zero).astype(np.float32))
+    lin2 = ba.linearizeAll(False) if kind == "gpu" else ba.linearize(False)
+    (ba.applyRes if kind == "gpu" else ba.apply_res)()
+    return lin, lin2
+
+
+@pytest.fixture(scope="module")
+def ba_setup(ctx, capi, O, synth, window_small):
+    win, is_lin = window_small
+    frames = [capi.Frame(ctx, im, 1) for im in win.images]
+    dIs = [O.pyramid(im, 1)[0][0] for im in win.images]
+    ef = capi.EnergyFunctional(ctx)
+    ef.set_window(win, frames)
+    ef.set_topology(win)
+    of = O.BAOracle(win, dIs, prec="f")
+    od = O.BAOracle(win, dIs, prec="d")
+    g = run_sequence(ef, win, is_lin, "gpu")
+    f = run_sequence(of, win, is_lin, "orc")
+    d = run_sequence(od, win, is_lin, "orc")
+    yield dict(win=win, is_lin=is_lin, ef=ef, of=of, od=od, g=g, f=f, d=d, frames=frames)
+    ef.close()
+    for fr in frames:
+        fr.close()
+
+
+def test_linearize_states_and_energies_bit_exact(ba_setup):
+    for i in (0, 1):
+        g, f = ba_setup["g"][i], ba_setup["f"][i]
+        assert np.array_equal(g["newState"], f["newState"])
+        assert np.bincount(g["newState"], minlength=3)[0] > 0.8 * len(g["newState"]) * (1 if i == 0 else 0.6)
+        assert np.array_equal(g["newEnergy"], f["newEnergy"])
+        assert np.array_equal(g["newEnergyWithOutlier"], f["newEnergyWithOutlier"])
+        ok = g["newState"] != 1
+        assert np.array_equal(g["centerProjectedTo"][ok], f["centerProjectedTo"][ok])
+        assert np.array_equal(g["projectedTo"][ok], f["projectedTo"][ok])
+        assert g["energy"] == pytest.approx(f["energy"], rel=1e-12)
+
+
+def test_jacobians_bit_exact(ba_setup):
+    rg = ba_setup["ef"].residual_results()
+    rf = ba_setup["of"].residual_results()
+    assert np.array_equal(rg["state_state"], rf["state_state"])
+    assert np.array_equal(rg["is_active"], rf["is_active"])
+    ok = rg["state_state"] != 1
+    assert np.array_equal(rg["J"][ok], rf["J"][ok].astype(np.float32))
+    assert np.array_equal(rg["JpJdF"][ok], rf["JpJdF"][ok].astype(np.float32))
+    lin = ba_setup["is_lin"].astype(bool)
+    assert np.array_equal(rg["res_toZeroF"][lin], rf["res_toZeroF"][lin].astype(np.float32))
+
+
+def test_accumulate_against_double_oracle(ba_setup):
+    ef, of, od = ba_setup["ef"], ba_setup["of"], ba_setup["od"]
+    HA, bA = ef.accumulateAF_MT()
+    HL, bL = ef.accumulateLF_MT()
+    HS, bS = ef.accumulateSCF_MT()
+    ref = {}
+    for name, o in (("f", of), ("d", od)):
+        a = o.accumulate(0); l = o.accumulate(1); s = o.accumulate(2)
+        ref[name] = (a, l, s)
+    assert ef.resInA == ref["f"][0][2] and ef.resInL == ref["f"][1][2]
+    assert ef.resInA > 0 and ef.resInL > 0
+    for (Hg, bg), k, nm in (((HA, bA), 0, "A"), ((HL, bL), 1, "L"), ((HS, bS), 2, "SC")):
+        Hd, bd = ref["d"][k][0], ref["d"][k][1]
+        Hf, bf = ref["f"][k][0], ref["f"][k][1]
+        eH, eb = rel_fro(Hg, Hd), rel_fro(bg, bd)
+        fH, fb = rel_fro(Hf, Hd), rel_fro(bf, bd)
+        assert eH <= max(1e-5, 1.5 * fH), (nm, eH, fH)
+        assert eb <= max(1e-5, 1.5 * fb), (nm, eb, fb)
+    # structure: A and L are symmetrised by the reference's stitch, SC only in the calibration columns
+    assert np.allclose(HA, HA.T, rtol=0, atol=1e-9 * np.abs(HA).max())
+    assert np.allclose(HS[:4, 4:], HS[4:, :4].T)
+    # fused pass gives the same three systems bit for bit
+    allr = ef.accumulate_all()
+    for (H1, b1), (H2, b2) in zip(allr, ((HA, bA), (HL, bL), (HS, bS))):
+        assert np.array_equal(H1, H2) and np.array_equal(b1, b2)
+
+
+def test_point_side_effects_bit_exact(ba_setup):
+    ef, of = ba_setup["ef"], ba_setup["of"]
+    ef.accumulateAF_MT(); ef.accumulateLF_MT(); ef.accumulateSCF_MT()
+    of.accumulate(0); of.accumulate(1); of.accumulate(2)
+    pg, pf = ef.point_results(), of.point_results()
+    for k in pg:
+        assert np.array_equal(pg[k], pf[k].astype(np.float32)), k
+    assert (pg["HdiF"] > 0).sum() > 0.9 * len(pg["HdiF"])
+
+
+def test_raw_schur_blocks_vs_double(ba_setup):
+    """Schur identity on the stitched system: H_sc equals the dense elimination of the inverse depths."""
+    od = ba_setup["od"]
+    od.accumulate(0); od.accumulate(1); od.accumulate(2)
+    raw = od.raw_sc()
+    n = ba_setup["win"].n
+    # accD[(h,t1,t2)] is symmetric under t1<->t2 transpose
+    for h in range(n):
+        for t1 in range(n):
+            for t2 in range(n):
+                a = raw["D"][h + n * t1 + n * n * t2]
+                b = raw["D"][h + n * t2 + n * n * t1]
+                assert np.allclose(a, b.T, rtol=1e-12, atol=1e-9)
+
+
+def test_deterministic(ba_setup):
+    ef = ba_setup["ef"]
+    a = ef.accumulate_all()
+    for _ in range(3):
+        b = ef.accumulate_all()
+        for (H1, b1), (H2, b2) in zip(a, b):
+            assert np.array_equal(H1, H2) and np.array_equal(b1, b2)
+
+
+def test_resubstitute(ba_setup):
+    ef, of, od = ba_setup["ef"], ba_setup["of"], ba_setup["od"]
+    ef.accumulate_all()
+    for o in (of, od):
+        o.accumulate(0); o.accumulate(1); o.accumulate(2)
+    rng = np.random.default_rng(5)
+    x = rng.normal(0, 1e-3, ef.N)
+    sg, sf, sd = ef.resubstituteF_MT(x), of.resubstitute(x), od.resubstitute(x)
+    assert np.array_equal(sg, sf)
+    assert rel_fro(sg, sd) < 1e-4
+
+
+def test_iteration_device_matches_stepwise(ctx, capi, O, synth, window_small):
+    win, is_lin = window_small
+    frames = [capi.Frame(ctx, im, 1) for im in win.images]
+    a = capi.EnergyFunctional(ctx); a.set_window(win, frames); a.set_topology(win)
+    b = capi.EnergyFunctional(ctx); b.set_window(win, frames); b.set_topology(win)
+    a.linearizeAll(False, outputs=False); a.applyRes(); ra = a.accumulate_all()
+    b.iteration_device(); rb = b.download_Hb()
+    for (H1, b1), (H2, b2) in zip(ra, rb):
+        assert np.array_equal(H1, H2) and np.array_equal(b1, b2)
+    a.close(); b.close()
+    for f in frames:
+        f.close()
+
+
+def test_bad_arguments(ctx, capi, synth, window_small):
+    win, _ = window_small
+    ef = capi.EnergyFunctional(ctx)
+    with pytest.raises(capi.HslamError):
+        ef.set_topology(win)            # window first
+    frames = [capi.Frame(ctx, im, 1) for im in win.images]
+    ef.set_window(win, frames)
+    import copy
+    bad = copy.copy(win)
+    bad.target_idx = win.target_idx.copy(); bad.target_idx[0] = 99
+    with pytest.raises(capi.HslamError):
+        ef.set_topology(bad)
+    ef.close()
+    for f in frames:
+        f.close()
+
+
+def test_empty_window(ctx, capi, synth, window_small):
+    """No points / no residuals: H_A = 0, H_L = priors only, H_SC = 0 (reference: loops do nothing)."""
+    import copy
+    win, _ = window_small
+    e = copy.copy(win)
+    z = lambda dt: np.zeros(0, dt)
+    e.u = e.v = e.idepth = e.idepth_zero = e.priorF = e.deltaF = z(np.float32)
+    e.color = e.weights = np.zeros((0, 8), np.float32)
+    e.host_idx = z(np.int32); e.res_begin = np.zeros(1, np.int32); e.res_index = z(np.int32)
+    e.point_idx = e.target_idx = z(np.int32); e.state_state = z(np.int8); e.is_linearized = e.is_active = z(np.uint8)
+    frames = [capi.Frame(ctx, im, 1) for im in win.images]
+    ef = capi.EnergyFunctional(ctx); ef.set_window(e, frames); ef.set_topology(e)
+    ef.linearizeAll(False, outputs=False); ef.applyRes()
+    (HA, bA), (HL, bL), (HS, bS) = ef.accumulate_all()
+    assert not HA.any() and not bA.any() and not HS.any() and not bS.any()
+    assert np.allclose(np.diag(HL)[:4], win.cPrior)
+    assert np.allclose(np.diag(HL)[4:], win.framePrior)
+    assert np.allclose(bL[4:], win.framePrior * win.frameDeltaPrior)
+    ef.close()
+    for f in frames:
+        f.close()
