@@ -1,0 +1,363 @@
+#!/usr/bin/env python
+"""bench.py — hot-path benchmark (driver contract; see DESIGN.md "Measurement").
+
+Workload (BASELINE.json configs[1]): windowed photometric BA linearisation, 7 keyframes x 2000 points
+per keyframe x 8-px pattern (P=14000 points, R=84000 residuals, 672k pattern pixels per window).
+A *step* = ONE Gauss-Newton iteration's hot path (linearizeAll + applyRes + accumulateAF/LF/SCF with
+the per-point Schur fold + fp64 stitch) over a batch of `--windows` independent windows per GPU, each
+with its own frames/points/Jacobians in HBM (the batch working set is >> the 126 MB L2, so no
+flush is needed between iterations).  Metric: pattern-pixel residuals linearised and reduced into H,b
+per second (Mres/s), whole job.
+
+    python bench.py --gpus N --steps K --warmup W           # ours (CUDA through the C ABI)
+    python bench.py --impl reference ...                    # the reference's CPU algorithm (oracle port, all host cores)
+
+Multi-GPU: one process per GPU (torchrun), windows are independent => weak scaling, no data-path
+collective; `--mode sharded` instead shards ONE oversized window's points across ranks and sums the
+stitched fp64 H,b with one NCCL all-reduce.
+"""
+from __future__ import annotations
+
+import argparse
+import importlib
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+N_FRAMES = 7
+PTS_PER_FRAME = 2000
+METRIC = "photometric residual+Hessian throughput (BA linearise+accumulate+Schur, 7KFx2000pts)"
+UNIT = "Mres/s"
+
+# algorithmic bytes per residual of each kernel class (DESIGN.md "Kernels and rooflines")
+ALGO_BYTES_PER_RES = {
+    "ba_linearize": 384 + 13.3 + 12 + 296 + 64,   # 8 px x 4 texels x 12 B, point record/6, indices; J + projectedTo written
+    "ba_top": 148 + 2 + 24,                       # 37 Jacobian floats + flags read; 6 per-residual point terms written
+    "ba_schur": 32 + 2,                           # JpJdF read per residual
+}
+
+
+def _clock_sampler(stop, out, gpu_index):
+    q = "clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown," \
+        "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
+    while not stop.is_set():
+        try:
+            r = subprocess.run(["nvidia-smi", f"--query-gpu={q}", "--format=csv,noheader,nounits", "-i", str(gpu_index)],
+                               capture_output=True, text=True, timeout=5)
+            parts = [p.strip() for p in r.stdout.strip().split(",")]
+            if len(parts) >= 6:
+                out.append(parts)
+        except Exception:
+            pass
+        stop.wait(0.2)
+
+
+def _clock_summary(samples):
+    if not samples:
+        return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["unavailable"]}
+    sm = sorted(int(s[0]) for s in samples if s[0].isdigit())
+    names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+    reasons = [n for i, n in enumerate(names) if any(s[2 + i].lower().startswith("active") for s in samples)]
+    return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": int(samples[0][1]) if samples[0][1].isdigit() else None,
+            "reasons": reasons}
+
+
+def build_windows(synth, n_windows, seed0, n_scenes=2):
+    kfs = [synth.render_keyframes(640, 480, N_FRAMES, seed=4321 + 17 * s) for s in range(min(n_scenes, n_windows))]
+    wins = []
+    for i in range(n_windows):
+        w, _ = synth.make_window(points_per_frame=PTS_PER_FRAME, seed=seed0 + i, keyframes=kfs[i % len(kfs)])
+        wins.append(w)
+    return wins
+
+
+def reference_arm(args, rank):
+    """The reference's own CPU algorithm for the path (oracle port, -O3 -march=native, IndexThreadReduce
+    semantics on all host cores).  One window per step (bounded sample of the batched workload)."""
+    if rank != 0:
+        return
+    synth = importlib.import_module("h-slam_b200.synth")
+    from oracle import oraclelib as O
+    cores = os.cpu_count() or 1
+    win, _ = synth.make_window(points_per_frame=PTS_PER_FRAME, seed=1000)
+    dIs = [O.pyramid(im, 1)[0][0] for im in win.images]
+    ba = O.BAOracle(win, dIs, prec="f", threads=cores, fast=True)
+
+    def step():
+        ba.linearize(False); ba.apply_res()
+        ba.accumulate(0); ba.accumulate(1); ba.accumulate(2)
+
+    for _ in range(args.warmup):
+        step()
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        step()
+    dt = time.perf_counter() - t0
+    px = win.R * 8 * args.steps
+    val = px / dt / 1e6
+    line = {
+        "impl": "reference", "metric": METRIC, "value": val, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": 1e3 * dt / args.steps, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": "cfg2: BA window 7KF x 2000pts/KF x 8px, 1 GN iteration hot path; CPU arm: 1 window per step",
+                   "windows_per_step": 1, "points": int(win.P), "residuals": int(win.R)},
+        "cpu_baseline": {"value": val, "unit": UNIT, "cores": cores, "kind": "port",
+                         "sample": f"{args.steps} GN iterations of one 84k-residual window"},
+        "e2e": {"value": val, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line), flush=True)
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--windows", type=int, default=8, help="independent windows per GPU per step")
+    ap.add_argument("--mode", default="batched", choices=["batched", "sharded"])
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
+
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+
+    if args.impl == "reference":
+        reference_arm(args, rank)
+        return
+
+    import torch
+    import torch.distributed as dist
+
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device; the hot path has no CPU fallback (use --impl reference for the CPU arm)")
+    torch.cuda.set_device(local_rank)
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+
+    capi = importlib.import_module("h-slam_b200.capi")
+    synth = importlib.import_module("h-slam_b200.synth")
+    if args.mode == "sharded":
+        from bench_sharded import run_sharded
+        run_sharded(args, rank, local_rank, world, capi, synth)
+        return
+
+    ctx = capi.Context(local_rank)
+    stream = torch.cuda.ExternalStream(ctx.stream, device=torch.device("cuda", local_rank))
+    wins = build_windows(synth, args.windows, seed0=100 + 1000 * rank)
+    efs, frames_all, host_imgs = [], [], []
+    for w in wins:
+        # `value` leg: inputs resident in HBM before the timed region (images uploaded via torch, pyramid built on device)
+        fr = []
+        for im in w.images:
+            t = torch.from_numpy(np.ascontiguousarray(im)).cuda(non_blocking=False)
+            host_imgs.append(t)
+            fr.append(capi.Frame(ctx, None, 1, device_ptr=t.data_ptr(), w=w.cam.w, h=w.cam.h))
+        ef = capi.EnergyFunctional(ctx)
+        ef.set_window(w, fr)
+        ef.set_topology(w)
+        efs.append(ef); frames_all.append(fr)
+    ctx.synchronize()
+    px_per_step = sum(w.R for w in wins) * 8
+    res_per_step = sum(w.R for w in wins)
+
+    def step_device():
+        for ef in efs:
+            ef.iteration_device()
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    for _ in range(args.warmup):
+        step_device()
+    barrier()
+    samples, stop = [], threading.Event()
+    th = threading.Thread(target=_clock_sampler, args=(stop, samples, local_rank), daemon=True)
+    th.start()
+    l0 = ctx.launches
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record(stream)
+    for _ in range(args.steps):
+        step_device()
+    e1.record(stream)
+    barrier()
+    ms = e0.elapsed_time(e1)
+    launches = ctx.launches - l0
+    stop.set(); th.join(timeout=2)
+    t_max = ms
+    if world > 1:
+        tt = torch.tensor([ms], device="cuda")
+        dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+        t_max = float(tt.item())
+    value = world * px_per_step * args.steps / (t_max * 1e-3) / 1e6
+
+    # ---- per-kernel device timing (CUDA events on the launching stream) for the roofline
+    ctx.profile_enable(True)
+    for _ in range(args.steps):
+        step_device()
+    prof = ctx.profile_read()
+    ctx.profile_enable(False)
+    peaks = {}
+    try:
+        peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+    except Exception:
+        pass
+    peak = float(peaks.get("hbm_gbs", 6650.0))
+    peak_kind = "measured (MEASURED_PEAKS.json hbm_gbs)" if "hbm_gbs" in peaks else "fallback 6650 GB/s (B200_PROFILING.md)"
+    dom = max(prof.items(), key=lambda kv: kv[1][0])[0]
+    dom_ms, dom_cnt = prof[dom]
+    per_launch_res = res_per_step / len(efs)
+    if dom == "ba_top":
+        dom_cnt_eff = dom_cnt / 2   # two modes per window iteration share the bytes
+    else:
+        dom_cnt_eff = dom_cnt
+    algo_bytes = ALGO_BYTES_PER_RES.get(dom, 0.0) * per_launch_res
+    avg_s = dom_ms * 1e-3 / max(dom_cnt, 1)
+    achieved = algo_bytes / avg_s / 1e9 if avg_s > 0 else 0.0
+    traffic = None
+    try:
+        traffic = json.load(open(os.path.join(ROOT, "profiles", "traffic.json"))).get(dom)
+    except Exception:
+        pass
+    roofline = {"bound": "hbm", "kernel": dom, "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                "traffic": traffic, "peak_source": peak_kind, "avg_launch_us": avg_s * 1e6,
+                "algorithmic_bytes_per_launch": algo_bytes,
+                "kernel_share_of_step": {k: v[0] / sum(x[0] for x in prof.values()) for k, v in prof.items()}}
+
+    # ---- e2e: the same GN iteration through the C ABI with HOST buffers, copies inside the timed region
+    N = 8 * N_FRAMES + 4
+    xs = [np.random.default_rng(i).normal(0, 1e-4, N) for i in range(len(wins))]
+
+    def step_e2e():
+        for ef, w, fr, x in zip(efs, wins, frames_all, xs):
+            ef.set_window(w, fr)                                   # H2D: precalc, adjoints, deltas, priors
+            ef.update_points(idepth=w.idepth, deltaF=w.deltaF)     # H2D: per-point state
+            ef.linearizeAll(False, outputs="states")               # D2H: energy, newState, newEnergy, newEnergyWithOutlier
+            ef.applyRes()
+            ef.accumulate_all()                                    # D2H: 3 x (H,b), resInA/L
+            ef.resubstituteF_MT(x)                                 # H2D: x ; D2H: point steps
+
+    n2 = N_FRAMES * N_FRAMES
+    h2d = sum(n2 * 28 * 4 + n2 * 8 * 4 + 2 * n2 * 64 * 8 + 2 * N_FRAMES * 64 + w.P * 16 + w.P * 4 + 16 + n2 * 8 * 4 for w in wins)
+    d2h = sum(8 + w.R * 9 + 3 * (N * N + N) * 8 + 8 + w.P * 4 for w in wins)
+    for _ in range(2):
+        step_e2e()
+    barrier()
+    k_e2e = max(3, args.steps // 2)
+    e0.record(stream)
+    t0 = time.perf_counter()
+    for _ in range(k_e2e):
+        step_e2e()
+    e1.record(stream)
+    barrier()
+    wall = time.perf_counter() - t0
+    ms_e2e = max(e0.elapsed_time(e1), 1e3 * wall)
+    if world > 1:
+        tt = torch.tensor([ms_e2e], device="cuda")
+        dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+        ms_e2e = float(tt.item())
+    e2e_val = world * px_per_step * k_e2e / (ms_e2e * 1e-3) / 1e6
+
+    line = {
+        "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+        "ms_per_step": t_max / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "f32", "data": "synthetic",
+        "config": {"workload": f"cfg2: BA window 7KF x 2000pts/KF x 8px (P=14000, R=84000), 1 GN iteration hot path, "
+                               f"{args.windows} independent windows per GPU per step",
+                   "windows_per_gpu": args.windows, "l2_policy": "inputs larger than L2 (no flush): batch working set "
+                   f"~{args.windows * 62} MB vs 126 MB L2", "jacobians": "materialised (SoA in HBM)"},
+        "e2e": {"value": e2e_val, "unit": UNIT, "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
+                "ms_per_step": ms_e2e / k_e2e, "steps": k_e2e},
+        "gpu_launches": int(launches),
+        "clocks": _clock_summary(samples),
+        "roofline": roofline,
+    }
+
+    if rank == 0:
+        line["extra"] = extras(ctx, capi, synth, torch, stream, efs[0], wins[0])
+        if not args.no_cpu_baseline:
+            line["cpu_baseline"] = cpu_baseline(synth, wins[0])
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+def extras(ctx, capi, synth, torch, stream, ef0, win0):
+    """Latency figures of the other two headline quantities: BA ms/window and tracking ms/frame."""
+    out = {}
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    # BA: one window, one GN iteration, device time
+    for _ in range(3):
+        ef0.iteration_device()
+    ctx.synchronize()
+    reps = 20
+    e0.record(stream)
+    for _ in range(reps):
+        ef0.iteration_device()
+    e1.record(stream)
+    torch.cuda.synchronize()
+    out["ba_ms_per_window_device"] = e0.elapsed_time(e1) / reps
+    # tracking: config 1 (640x480, 5 levels, ~28k level-0 points)
+    tp = synth.make_tracking_pair()
+    trk = capi.CoarseTracker(ctx, tp.cam.w, tp.cam.h)
+    trk.makeK(tp.cam, tp.levels)
+    trk.setCoarseTrackingRef(tp.pc)
+    frame = capi.Frame(ctx, tp.img_new, tp.levels)
+    T0 = np.concatenate([np.eye(3).reshape(9), np.zeros(3)])
+    for _ in range(3):
+        trk.trackNewestCoarse(frame, T0, (0.0, 0.0), tp.levels - 1)
+    e0.record(stream)
+    for _ in range(reps):
+        trk.track_enqueue(frame, T0, (0.0, 0.0), tp.levels - 1)
+    e1.record(stream)
+    torch.cuda.synchronize()
+    trk.track_finish()
+    out["tracking_ms_per_frame_device"] = e0.elapsed_time(e1) / reps
+    t0 = time.perf_counter()
+    for _ in range(reps):
+        frame.update(tp.img_new)                                   # H2D 1.2 MB + 5-level pyramid
+        trk.trackNewestCoarse(frame, T0, (0.0, 0.0), tp.levels - 1)  # LM on device + D2H of the result
+    out["tracking_ms_per_frame_e2e"] = 1e3 * (time.perf_counter() - t0) / reps
+    out["tracking_iterations"] = [int(i) for i in trk.iterations]
+    out["tracking_points_per_level"] = [int(len(p[0])) for p in tp.pc]
+    trk.close(); frame.close()
+    return out
+
+
+def cpu_baseline(synth, win):
+    from oracle import oraclelib as O
+    cores = os.cpu_count() or 1
+    dIs = [O.pyramid(im, 1)[0][0] for im in win.images]
+    ba = O.BAOracle(win, dIs, prec="f", threads=cores, fast=True)
+
+    def step():
+        ba.linearize(False); ba.apply_res()
+        ba.accumulate(0); ba.accumulate(1); ba.accumulate(2)
+
+    step()
+    reps, t0 = 0, time.perf_counter()
+    while reps < 200 and (time.perf_counter() - t0 < 10.0 or reps < 5):
+        step(); reps += 1
+    dt = time.perf_counter() - t0
+    return {"value": win.R * 8 * reps / dt / 1e6, "unit": UNIT, "cores": cores, "kind": "port",
+            "ms_per_window": 1e3 * dt / reps,
+            "sample": f"{reps} GN iterations of one cfg2 window (84k residuals) on {cores} threads, oracle port -O3 -march=native"}
+
+
+if __name__ == "__main__":
+    main()

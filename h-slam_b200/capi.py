@@ -107,6 +107,17 @@ class Context:
     def launches(self):
         return int(self.L.hslam_launch_count(self.h))
 
+    def profile_enable(self, on=True):
+        _chk(self.L.hslam_profile_enable(self.h, C.c_int(int(on))))
+
+    def profile_read(self):
+        """{kernel class: (summed ms, launches)} measured with CUDA events on the context stream."""
+        K = 14
+        ms = np.zeros(K, np.float32); cnt = np.zeros(K, np.int32)
+        _chk(self.L.hslam_profile_read(self.h, _ptr(ms), _ptr(cnt)))
+        self.L.hslam_kernel_name.restype = C.c_char_p
+        return {self.L.hslam_kernel_name(k).decode(): (float(ms[k]), int(cnt[k])) for k in range(K) if cnt[k] > 0}
+
 
 class Frame:
     """Device mirror of Frame::DirPyr / absSquaredGrad (reference Src/Frame.cpp:104-181)."""
@@ -277,15 +288,17 @@ class EnergyFunctional:
     def linearizeAll(self, fixLinearization=False, outputs=True):
         R = self.R
         e = C.c_double(0)
+        ns = ne = nwo = cpt = pto = None
         if outputs:
             ns = np.zeros(R, np.int8); ne = np.zeros(R, np.float32); nwo = np.zeros(R, np.float32)
+        if outputs is True:
             cpt = np.zeros(R * 3, np.float32); pto = np.zeros(R * 16, np.float32)
-        else:
-            ns = ne = nwo = cpt = pto = None
         _chk(self.L.hslam_ba_linearize(self.h, C.c_int(int(fixLinearization)), C.byref(e), _ptr(ns), _ptr(ne), _ptr(nwo),
                                        _ptr(cpt), _ptr(pto)))
         if not outputs:
             return dict(energy=e.value)
+        if outputs is not True:   # "states": what setNewFrameEnergyTH / the accept test need
+            return dict(energy=e.value, newState=ns, newEnergy=ne, newEnergyWithOutlier=nwo)
         return dict(energy=e.value, newState=ns, newEnergy=ne, newEnergyWithOutlier=nwo,
                     centerProjectedTo=cpt.reshape(R, 3), projectedTo=pto.reshape(R, 8, 2))
 

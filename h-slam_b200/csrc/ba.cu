@@ -1217,10 +1217,11 @@ static int launch_linearize(hslam_ba* ba, bool apply) {
   int blocks = (ba->R + 127) / 128;
   if (blocks < 1) blocks = 1;
   if (apply)
-    ba_linearize_kernel<true><<<blocks, 128, 0, ctx->stream>>>(ba->win, ba->res, ba->pts, ba->d_epart.p, ba->d_ticket.p, ba->d_energy.p);
+    HS_LAUNCH(ctx, HSLAM_K_BA_LINEARIZE, (ba_linearize_kernel<true><<<blocks, 128, 0, ctx->stream>>>(
+                                             ba->win, ba->res, ba->pts, ba->d_epart.p, ba->d_ticket.p, ba->d_energy.p)));
   else
-    ba_linearize_kernel<false><<<blocks, 128, 0, ctx->stream>>>(ba->win, ba->res, ba->pts, ba->d_epart.p, ba->d_ticket.p, ba->d_energy.p);
-  ctx->launches++;
+    HS_LAUNCH(ctx, HSLAM_K_BA_LINEARIZE, (ba_linearize_kernel<false><<<blocks, 128, 0, ctx->stream>>>(
+                                             ba->win, ba->res, ba->pts, ba->d_epart.p, ba->d_ticket.p, ba->d_energy.p)));
   HS_CUDA(cudaGetLastError());
   return 0;
 }
@@ -1264,8 +1265,7 @@ int hslam_ba_apply_res(hslam_ba* ba) {
   HS_CUDA(cudaSetDevice(ba->ctx->device));
   int blocks = (ba->R + 255) / 256;
   if (blocks < 1) blocks = 1;
-  ba_apply_kernel<<<blocks, 256, 0, ba->ctx->stream>>>(ba->res);
-  ba->ctx->launches++;
+  HS_LAUNCH(ba->ctx, HSLAM_K_BA_APPLY, (ba_apply_kernel<<<blocks, 256, 0, ba->ctx->stream>>>(ba->res)));
   HS_CUDA(cudaGetLastError());
   return 0;
 }
@@ -1281,8 +1281,8 @@ int hslam_ba_fix_linearization(hslam_ba* ba, const int32_t* ids, int count) {
   }
   TRY(ba->d_ids.ensure(count));
   TRY(upload(ba, ba->d_ids.p, sorted.data(), count));
-  ba_fixlin_kernel<<<(count + 127) / 128, 128, 0, ba->ctx->stream>>>(ba->win, ba->res, ba->pts, ba->d_ids.p, count);
-  ba->ctx->launches++;
+  HS_LAUNCH(ba->ctx, HSLAM_K_BA_FIXLIN, (ba_fixlin_kernel<<<(count + 127) / 128, 128, 0, ba->ctx->stream>>>(
+                                            ba->win, ba->res, ba->pts, ba->d_ids.p, count)));
   HS_CUDA(cudaGetLastError());
   ba->n_linearized = -1;  // unknown without a count: run both modes
   return 0;
@@ -1294,19 +1294,19 @@ static int launch_top(hslam_ba* ba, int mode) {
   if (ba->n_topchunks > 0) {
     float* part = ba->d_toppartial.p;
     if (mode == 0)
-      ba_top_kernel<0><<<ba->n_topchunks, TOP_THREADS, 0, ctx->stream>>>(ba->win, ba->res, ba->pts, ba->d_topchunks.p, part);
+      HS_LAUNCH(ctx, HSLAM_K_BA_TOP, (ba_top_kernel<0><<<ba->n_topchunks, TOP_THREADS, 0, ctx->stream>>>(
+                                         ba->win, ba->res, ba->pts, ba->d_topchunks.p, part)));
     else
-      ba_top_kernel<1><<<ba->n_topchunks, TOP_THREADS, 0, ctx->stream>>>(ba->win, ba->res, ba->pts, ba->d_topchunks.p, part);
-    ctx->launches++;
+      HS_LAUNCH(ctx, HSLAM_K_BA_TOP, (ba_top_kernel<1><<<ba->n_topchunks, TOP_THREADS, 0, ctx->stream>>>(
+                                         ba->win, ba->res, ba->pts, ba->d_topchunks.p, part)));
   }
-  ba_fold_top_kernel<<<ba->n * ba->n, 96, 0, ctx->stream>>>(ba->d_toppartial.p, ba->d_pair_chunk_begin.p, ba->n * ba->n,
-                                                            ba->d_accTop[mode].p, ba->d_nres.p + mode);
-  ctx->launches++;
+  HS_LAUNCH(ctx, HSLAM_K_BA_FOLD_TOP, (ba_fold_top_kernel<<<ba->n * ba->n, 96, 0, ctx->stream>>>(
+                                          ba->d_toppartial.p, ba->d_pair_chunk_begin.p, ba->n * ba->n,
+                                          ba->d_accTop[mode].p, ba->d_nres.p + mode)));
   int pblocks = (ba->P + 127) / 128;
-  if (pblocks > 0) {
-    ba_point_sum_kernel<<<pblocks, 128, 0, ctx->stream>>>(ba->res, ba->pts, mode == 0, mode == 1);
-    ctx->launches++;
-  }
+  if (pblocks > 0)
+    HS_LAUNCH(ctx, HSLAM_K_BA_POINT_SUM,
+              (ba_point_sum_kernel<<<pblocks, 128, 0, ctx->stream>>>(ba->res, ba->pts, mode == 0, mode == 1)));
   HS_CUDA(cudaGetLastError());
   return 0;
 }
@@ -1318,13 +1318,12 @@ static int launch_schur(hslam_ba* ba) {
   if (smem > 48 * 1024)
     HS_CUDA(cudaFuncSetAttribute(ba_schur_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   if (ba->n_ptchunks > 0) {
-    ba_schur_kernel<<<ba->n_ptchunks, SC_THREADS, smem, ctx->stream>>>(ba->win, ba->res, ba->pts, ba->d_ptchunks.p, LD,
-                                                                      ba->d_scpartial.p);
-    ctx->launches++;
+    HS_LAUNCH(ctx, HSLAM_K_BA_SCHUR, (ba_schur_kernel<<<ba->n_ptchunks, SC_THREADS, smem, ctx->stream>>>(
+                                         ba->win, ba->res, ba->pts, ba->d_ptchunks.p, LD, ba->d_scpartial.p)));
   }
   dim3 g((LD * LD + 255) / 256, ba->n);
-  ba_fold_sc_kernel<<<g, 256, 0, ctx->stream>>>(ba->d_scpartial.p, ba->d_host_chunk_begin.p, LD, ba->d_G.p);
-  ctx->launches++;
+  HS_LAUNCH(ctx, HSLAM_K_BA_FOLD_SC, (ba_fold_sc_kernel<<<g, 256, 0, ctx->stream>>>(
+                                         ba->d_scpartial.p, ba->d_host_chunk_begin.p, LD, ba->d_G.p)));
   HS_CUDA(cudaGetLastError());
   return 0;
 }
@@ -1344,8 +1343,7 @@ static int launch_stitch(hslam_ba* ba, int sys_begin, int sys_end) {
   // zero first: the lower blocks (a>b) of the top systems are written by their mirror block
   HS_CUDA(cudaMemsetAsync(ba->d_Hb.p + per * sys_begin, 0, per * (sys_end - sys_begin) * sizeof(double), ctx->stream));
   dim3 grid(ba->n + 1, ba->n + 1, 3);
-  ba_stitch_kernel<<<grid, 64, 0, ctx->stream>>>(S);
-  ctx->launches++;
+  HS_LAUNCH(ctx, HSLAM_K_BA_STITCH, (ba_stitch_kernel<<<grid, 64, 0, ctx->stream>>>(S)));
   HS_CUDA(cudaGetLastError());
   return 0;
 }
@@ -1498,8 +1496,8 @@ int hslam_ba_resubstitute(hslam_ba* ba, const double* x, float* step_out) {
   TRY(upload(ba, ba->d_xc.p, xF.data(), 4)); TRY(upload(ba, ba->d_xAd.p, xAd.data(), xAd.size()));
   int blocks = (ba->P + 127) / 128;
   if (blocks > 0) {
-    ba_resub_kernel<<<blocks, 128, 0, ba->ctx->stream>>>(ba->win, ba->res, ba->pts, ba->d_xc.p, ba->d_xAd.p);
-    ba->ctx->launches++;
+    HS_LAUNCH(ba->ctx, HSLAM_K_BA_RESUB, (ba_resub_kernel<<<blocks, 128, 0, ba->ctx->stream>>>(
+                                             ba->win, ba->res, ba->pts, ba->d_xc.p, ba->d_xAd.p)));
     HS_CUDA(cudaGetLastError());
   }
   TRY(download_pts(ba, ba->d_step.p, 1, step_out));

@@ -86,7 +86,31 @@ struct hslam_ctx {
   hslam_params prm;
   int sm_count = 148;
   int64_t launches = 0;
+  // optional per-kernel event timing (hslam_profile_*)
+  bool profile = false;
+  struct ProfRec { int k; cudaEvent_t a, b; };
+  std::vector<ProfRec> prof_recs;
+  std::vector<cudaEvent_t> prof_pool;
 };
+
+namespace hs {
+struct ProfScope {   // brackets one launch with events when profiling is on; always counts the launch
+  hslam_ctx* c; int k; cudaEvent_t a = nullptr, b = nullptr;
+  ProfScope(hslam_ctx* ctx, int kid) : c(ctx), k(kid) {
+    c->launches++;
+    if (!c->profile) return;
+    auto get = [&]() { cudaEvent_t e; if (!c->prof_pool.empty()) { e = c->prof_pool.back(); c->prof_pool.pop_back(); } else cudaEventCreate(&e); return e; };
+    a = get(); b = get();
+    cudaEventRecord(a, c->stream);
+  }
+  ~ProfScope() {
+    if (!a) return;
+    cudaEventRecord(b, c->stream);
+    c->prof_recs.push_back({k, a, b});
+  }
+};
+}  // namespace hs
+#define HS_LAUNCH(ctx, kid, ...) do { hs::ProfScope ps__(ctx, kid); __VA_ARGS__; } while (0)
 
 struct hslam_frame {
   hslam_ctx* ctx = nullptr;

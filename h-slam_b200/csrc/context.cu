@@ -61,6 +61,8 @@ int hslam_destroy(hslam_ctx* c) {
   if (!c) return 0;
   cudaSetDevice(c->device);
   cudaStreamSynchronize(c->stream);
+  for (auto& r : c->prof_recs) { cudaEventDestroy(r.a); cudaEventDestroy(r.b); }
+  for (auto e : c->prof_pool) cudaEventDestroy(e);
   cudaStreamDestroy(c->stream);
   delete c;
   return 0;
@@ -80,5 +82,31 @@ int hslam_get_stream(hslam_ctx* c, void** s) {
 }
 
 int64_t hslam_launch_count(hslam_ctx* c) { return c ? c->launches : -1; }
+
+static const char* k_names[HSLAM_K_COUNT] = {"pyramid_level", "trk_eval", "trk_track", "ba_linearize", "ba_apply",
+                                             "ba_top", "ba_fold_top", "ba_point_sum", "ba_schur", "ba_fold_sc",
+                                             "ba_stitch", "ba_resub", "ba_fixlin", "unpack_level"};
+const char* hslam_kernel_name(int k) { return (k >= 0 && k < HSLAM_K_COUNT) ? k_names[k] : ""; }
+
+int hslam_profile_enable(hslam_ctx* c, int enable) {
+  HS_ARG(c, "hslam_profile_enable: null");
+  c->profile = enable != 0;
+  return 0;
+}
+
+int hslam_profile_read(hslam_ctx* c, float ms_out[HSLAM_K_COUNT], int count_out[HSLAM_K_COUNT]) {
+  HS_ARG(c && ms_out && count_out, "hslam_profile_read: null");
+  HS_CUDA(cudaSetDevice(c->device));
+  HS_CUDA(cudaStreamSynchronize(c->stream));
+  for (int k = 0; k < HSLAM_K_COUNT; ++k) { ms_out[k] = 0.f; count_out[k] = 0; }
+  for (auto& r : c->prof_recs) {
+    float ms = 0.f;
+    cudaEventElapsedTime(&ms, r.a, r.b);
+    ms_out[r.k] += ms; count_out[r.k]++;
+    c->prof_pool.push_back(r.a); c->prof_pool.push_back(r.b);
+  }
+  c->prof_recs.clear();
+  return 0;
+}
 
 }  // extern "C"

@@ -60,11 +60,11 @@ int build_pyramid(hslam_frame* f, const float* img_dev) {
     int cap = ctx->sm_count * 8;
     if (blocks > cap) blocks = cap;
     if (l == 0)
-      pyramid_level_kernel<true><<<blocks, 256, 0, ctx->stream>>>(img_dev, nullptr, f->dI[0], wl, hl, 0, f->gamma);
+      HS_LAUNCH(ctx, HSLAM_K_PYRAMID, (pyramid_level_kernel<true><<<blocks, 256, 0, ctx->stream>>>(
+                                          img_dev, nullptr, f->dI[0], wl, hl, 0, f->gamma)));
     else
-      pyramid_level_kernel<false><<<blocks, 256, 0, ctx->stream>>>(nullptr, f->dI[l - 1], f->dI[l], wl, hl,
-                                                                  f->w >> (l - 1), f->gamma);
-    ctx->launches++;
+      HS_LAUNCH(ctx, HSLAM_K_PYRAMID, (pyramid_level_kernel<false><<<blocks, 256, 0, ctx->stream>>>(
+                                          nullptr, f->dI[l - 1], f->dI[l], wl, hl, f->w >> (l - 1), f->gamma)));
   }
   HS_CUDA(cudaGetLastError());
   return 0;
@@ -156,8 +156,7 @@ int hslam_frame_download(hslam_frame* f, int lvl, float* dI_xyz_host, float* abs
   float *d3 = nullptr, *da = nullptr;
   if (dI_xyz_host) HS_CUDA(cudaMalloc(&d3, (size_t)n * 3 * sizeof(float)));
   if (absSqGrad_host) HS_CUDA(cudaMalloc(&da, (size_t)n * sizeof(float)));
-  unpack_level_kernel<<<(n + 255) / 256, 256, 0, ctx->stream>>>(f->dI[lvl], d3, da, n);
-  ctx->launches++;
+  HS_LAUNCH(ctx, HSLAM_K_UNPACK, (unpack_level_kernel<<<(n + 255) / 256, 256, 0, ctx->stream>>>(f->dI[lvl], d3, da, n)));
   if (d3) HS_CUDA(cudaMemcpyAsync(dI_xyz_host, d3, (size_t)n * 3 * sizeof(float), cudaMemcpyDeviceToHost, ctx->stream));
   if (da) HS_CUDA(cudaMemcpyAsync(absSqGrad_host, da, (size_t)n * sizeof(float), cudaMemcpyDeviceToHost, ctx->stream));
   HS_CUDA(cudaStreamSynchronize(ctx->stream));

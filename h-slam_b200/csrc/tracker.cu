@@ -755,8 +755,8 @@ static int run_eval(hslam_tracker* t, int lvl, const hslam_frame* f, const doubl
   if (blocks > cap) blocks = cap;
   int rc = ensure_partials(t, blocks);
   if (rc) return rc;
-  trk_eval_kernel<<<blocks, TRK_THREADS, 0, ctx->stream>>>(a, t->partial[0], t->ticket, t->d_result);
-  ctx->launches++;
+  HS_LAUNCH(ctx, HSLAM_K_TRK_EVAL,
+            (trk_eval_kernel<<<blocks, TRK_THREADS, 0, ctx->stream>>>(a, t->partial[0], t->ticket, t->d_result)));
   HS_CUDA(cudaGetLastError());
   HS_CUDA(cudaMemcpyAsync(t->h_result, t->d_result, sizeof(EvalResult), cudaMemcpyDeviceToHost, ctx->stream));
   HS_CUDA(cudaStreamSynchronize(ctx->stream));
@@ -828,8 +828,10 @@ int hslam_tracker_track_enqueue(hslam_tracker* t, const hslam_frame* f, float ne
   int rc = ensure_partials(t, blocks);
   if (rc) return rc;
   void* args[] = {&a, &t->partial[0], &t->partial[1], &t->d_io};
-  HS_CUDA(cudaLaunchCooperativeKernel((void*)trk_track_kernel, dim3(blocks), dim3(TRK_THREADS), args, 0, ctx->stream));
-  ctx->launches++;
+  cudaError_t lerr = cudaSuccess;
+  HS_LAUNCH(ctx, HSLAM_K_TRK_TRACK, (lerr = cudaLaunchCooperativeKernel((void*)trk_track_kernel, dim3(blocks),
+                                                                       dim3(TRK_THREADS), args, 0, ctx->stream)));
+  HS_CUDA(lerr);
   HS_CUDA(cudaMemcpyAsync(t->h_io, t->d_io, sizeof(TrackIO), cudaMemcpyDeviceToHost, ctx->stream));
   return 0;
 }

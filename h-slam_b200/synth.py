@@ -419,16 +419,21 @@ def _frame_priors(n):
     return p.reshape(-1)
 
 
-def make_window(w=640, h=480, n_frames=7, points_per_frame=2000, seed=4321, frac_linearized=0.0,
-                pose_noise=4e-4, state_noise=3e-4, idepth_noise=0.003):
-    """Config 2 (SURVEY.md §8d): n keyframes on a smooth trajectory, points_per_frame points per host KF,
-    residuals to every other KF, idepth_zero = idepth*(1+N(0,0.01)), state-state_zero ~ N(0,state_noise)."""
-    rng = np.random.default_rng(seed)
+@dataclasses.dataclass
+class Keyframes:
+    cam: Camera
+    images: list
+    depths: list
+    T_true: list
+    aff_true: list
+
+
+def render_keyframes(w=640, h=480, n_frames=7, seed=4321):
+    """n keyframes of the synthetic room on a smooth trajectory (5-10 cm steps), exact poses and depth."""
     cam = Camera.tum_like(w, h)
     scene = Scene(seed)
     n = n_frames
-    T_true, T_eval, images, depths = [], [], [], []
-    aff_true = []
+    kf = Keyframes(cam, [], [], [], [])
     for f in range(n):
         s = f - (n - 1) / 2
         xi = np.array([0.07 * s, 0.01 * np.sin(0.9 * f), 0.035 * s, 0.004 * s, -0.012 * s, 0.003 * np.cos(f)])
@@ -436,12 +441,26 @@ def make_window(w=640, h=480, n_frames=7, points_per_frame=2000, seed=4321, frac
         Tt = T12(R, t)
         a_f, b_f = 0.01 * f, 0.8 * f
         img, dep = scene.render(cam, Tt, aff=(a_f, b_f))
+        kf.images.append(img); kf.depths.append(dep); kf.T_true.append(Tt); kf.aff_true.append((a_f, b_f))
+    return kf
+
+
+def make_window(w=640, h=480, n_frames=7, points_per_frame=2000, seed=4321, frac_linearized=0.0,
+                pose_noise=4e-4, state_noise=3e-4, idepth_noise=0.003, keyframes=None):
+    """Config 2 (SURVEY.md §8d): n keyframes on a smooth trajectory, points_per_frame points per host KF,
+    residuals to every other KF, idepth_zero = idepth*(1+N(0,0.01)), state-state_zero ~ N(0,state_noise).
+    `keyframes` re-uses rendered images (render_keyframes) so that many windows with different points,
+    noise and states can be drawn from one rendering."""
+    rng = np.random.default_rng(seed)
+    kf = keyframes if keyframes is not None else render_keyframes(w, h, n_frames, seed)
+    cam = kf.cam
+    w, h = cam.w, cam.h
+    n = len(kf.images)
+    images, depths, aff_true = kf.images, kf.depths, kf.aff_true
+    T_eval = []
+    for f in range(n):
         Rn, tn = se3_exp(rng.normal(0, pose_noise, 6))
-        T_true.append(Tt)
-        T_eval.append(se3_mul(T12(Rn, tn), Tt))
-        images.append(img)
-        depths.append(dep)
-        aff_true.append((a_f, b_f))
+        T_eval.append(se3_mul(T12(Rn, tn), kf.T_true[f]))
     state_zero = np.zeros((n, 10))
     state = np.zeros((n, 10))
     for f in range(n):
@@ -480,15 +499,13 @@ def make_window(w=640, h=480, n_frames=7, points_per_frame=2000, seed=4321, frac
     color = np.concatenate(col); weights = np.concatenate(wts); host_idx = np.concatenate(hosts)
     P = len(u)
     # residual topology: each point -> every other frame, stored in a shuffled per-point order
-    point_idx, target_idx, res_begin, res_index = [], [], [0], []
-    r = 0
-    for p in range(P):
-        tg = [t for t in range(n) if t != host_idx[p]]
-        rng.shuffle(tg)
-        for t in tg:
-            point_idx.append(p); target_idx.append(t); res_index.append(r); r += 1
-        res_begin.append(r)
-    R_ = r
+    others = np.arange(n - 1)[None, :] + (np.arange(n - 1)[None, :] >= host_idx[:, None])   # P x (n-1), skips the host
+    others = rng.permuted(others, axis=1)
+    R_ = P * (n - 1)
+    point_idx = np.repeat(np.arange(P, dtype=np.int32), n - 1)
+    target_idx = others.reshape(-1).astype(np.int32)
+    res_begin = np.arange(P + 1, dtype=np.int32) * (n - 1)
+    res_index = np.arange(R_, dtype=np.int32)
     is_lin = (rng.random(R_) < frac_linearized).astype(np.uint8)
     priorF = np.where(rng.random(P) < 0.1, np.float32(50.0 * 50.0), np.float32(0)).astype(np.float32)
     return Window(

@@ -87,6 +87,28 @@ int hslam_synchronize(hslam_ctx* ctx);
 int hslam_get_stream(hslam_ctx* ctx, void** cuda_stream_out);
 /* Number of kernels this context has launched so far (bench.py's gpu_launches). */
 int64_t hslam_launch_count(hslam_ctx* ctx);
+/* Per-kernel device timing with CUDA events on the context stream (measurement only).
+ * enable=1 starts bracketing every launch with a pair of events; hslam_profile_read
+ * synchronises, returns for each kernel class its summed duration (ms) and launch count
+ * since the last read and clears the counters.  Classes: see HSLAM_K_* below. */
+#define HSLAM_K_PYRAMID 0
+#define HSLAM_K_TRK_EVAL 1
+#define HSLAM_K_TRK_TRACK 2
+#define HSLAM_K_BA_LINEARIZE 3
+#define HSLAM_K_BA_APPLY 4
+#define HSLAM_K_BA_TOP 5
+#define HSLAM_K_BA_FOLD_TOP 6
+#define HSLAM_K_BA_POINT_SUM 7
+#define HSLAM_K_BA_SCHUR 8
+#define HSLAM_K_BA_FOLD_SC 9
+#define HSLAM_K_BA_STITCH 10
+#define HSLAM_K_BA_RESUB 11
+#define HSLAM_K_BA_FIXLIN 12
+#define HSLAM_K_UNPACK 13
+#define HSLAM_K_COUNT 14
+int hslam_profile_enable(hslam_ctx* ctx, int enable);
+int hslam_profile_read(hslam_ctx* ctx, float ms_out[HSLAM_K_COUNT], int count_out[HSLAM_K_COUNT]);
+const char* hslam_kernel_name(int k);
 
 /* ---------------------------------------------------------------- frames ---
  * Replaces Frame::CreateDirPyrs (Src/Frame.cpp:104-181): level 0 copies the
