@@ -237,6 +237,28 @@ class EnergyFunctional:
         _chk(self.L.hslam_ba_create(ctx.h, C.byref(self.h)))
         self._keep = []
         self.resInA = self.resInL = 0
+        self._async = False
+        self._alive = []      # output buffers the C side fills at wait()
+        self._pendings = []
+
+    class Pending:
+        """Result of a call made between begin_async() and wait(); .get() after wait()."""
+
+        def __init__(self, fn):
+            self.fn, self.value, self.done = fn, None, False
+
+        def get(self):
+            if not self.done:
+                raise HslamError("result requested before wait()")
+            return self.value
+
+    def _result(self, keep, fn):
+        if not self._async:
+            return fn()
+        self._alive.append(keep)
+        p = EnergyFunctional.Pending(fn)
+        self._pendings.append(p)
+        return p
 
     def set_window(self, win, frames):
         cam = win.cam
@@ -295,12 +317,15 @@ class EnergyFunctional:
             cpt = np.zeros(R * 3, np.float32); pto = np.zeros(R * 16, np.float32)
         _chk(self.L.hslam_ba_linearize(self.h, C.c_int(int(fixLinearization)), C.byref(e), _ptr(ns), _ptr(ne), _ptr(nwo),
                                        _ptr(cpt), _ptr(pto)))
-        if not outputs:
-            return dict(energy=e.value)
-        if outputs is not True:   # "states": what setNewFrameEnergyTH / the accept test need
-            return dict(energy=e.value, newState=ns, newEnergy=ne, newEnergyWithOutlier=nwo)
-        return dict(energy=e.value, newState=ns, newEnergy=ne, newEnergyWithOutlier=nwo,
-                    centerProjectedTo=cpt.reshape(R, 3), projectedTo=pto.reshape(R, 8, 2))
+
+        def fin():
+            if not outputs:
+                return dict(energy=e.value)
+            if outputs is not True:   # "states": what setNewFrameEnergyTH / the accept test need
+                return dict(energy=e.value, newState=ns, newEnergy=ne, newEnergyWithOutlier=nwo)
+            return dict(energy=e.value, newState=ns, newEnergy=ne, newEnergyWithOutlier=nwo,
+                        centerProjectedTo=cpt.reshape(R, 3), projectedTo=pto.reshape(R, 8, 2))
+        return self._result((e, ns, ne, nwo, cpt, pto), fin)
 
     def applyRes(self):
         _chk(self.L.hslam_ba_apply_res(self.h))
@@ -313,19 +338,23 @@ class EnergyFunctional:
         N = self.N
         H = np.zeros(N * N); b = np.zeros(N); nres = C.c_int(0)
         _chk(self.L.hslam_ba_accumulate(self.h, C.c_int(which), _ptr(H), _ptr(b), C.byref(nres)))
-        return H.reshape(N, N).T.copy(), b, nres.value
+
+        def fin():
+            if which == ACC_A:
+                self.resInA = nres.value
+            elif which == ACC_L:
+                self.resInL = nres.value
+            return H.reshape(N, N).T.copy(), b
+        return self._result((H, b, nres), fin)
 
     def accumulateAF_MT(self):
-        H, b, self.resInA = self._acc(ACC_A)
-        return H, b
+        return self._acc(ACC_A)
 
     def accumulateLF_MT(self):
-        H, b, self.resInL = self._acc(ACC_L)
-        return H, b
+        return self._acc(ACC_L)
 
     def accumulateSCF_MT(self):
-        H, b, _ = self._acc(ACC_SC)
-        return H, b
+        return self._acc(ACC_SC)
 
     def accumulate_all(self):
         N = self.N
@@ -333,12 +362,15 @@ class EnergyFunctional:
         out = np.zeros(3 * per)
         nres = np.zeros(2, np.int32)
         _chk(self.L.hslam_ba_accumulate_all(self.h, _ptr(out), _ptr(nres)))
-        self.resInA, self.resInL = int(nres[0]), int(nres[1])
-        res = []
-        for s in range(3):
-            blk = out[s * per:(s + 1) * per]
-            res.append((blk[:N * N].reshape(N, N).T.copy(), blk[N * N:].copy()))
-        return res
+
+        def fin():
+            self.resInA, self.resInL = int(nres[0]), int(nres[1])
+            res = []
+            for s in range(3):
+                blk = out[s * per:(s + 1) * per]
+                res.append((blk[:N * N].reshape(N, N).T.copy(), blk[N * N:].copy()))
+            return res
+        return self._result((out, nres), fin)
 
     def iteration_device(self):
         """linearize + applyRes + accumulate A/L/SC enqueued with no host round trip; returns (device ptr, count)."""
@@ -356,7 +388,19 @@ class EnergyFunctional:
         per = N * N + N
         out = np.zeros(3 * per)
         _chk(self.L.hslam_ba_download_Hb(self.h, _ptr(out)))
-        return [(out[s * per:s * per + N * N].reshape(N, N).T.copy(), out[s * per + N * N:(s + 1) * per].copy()) for s in range(3)]
+        return self._result((out,), lambda: [(out[s * per:s * per + N * N].reshape(N, N).T.copy(),
+                                              out[s * per + N * N:(s + 1) * per].copy()) for s in range(3)])
+
+    def begin_async(self):
+        _chk(self.L.hslam_ba_begin_async(self.h))
+        self._async = True
+
+    def wait(self):
+        _chk(self.L.hslam_ba_wait(self.h))
+        self._async = False
+        for p in self._pendings:
+            p.value, p.done = p.fn(), True
+        self._pendings, self._alive = [], []
 
     def set_add_priors(self, flag):
         _chk(self.L.hslam_ba_set_add_priors(self.h, C.c_int(int(flag))))
@@ -366,9 +410,12 @@ class EnergyFunctional:
         names = ["HdiF", "bdSumF", "idepth_hessian", "Hdd_accAF", "bd_accAF", "Hcd_accAF", "Hdd_accLF", "bd_accLF", "Hcd_accLF"]
         arrs = [np.zeros(P * (4 if "Hcd" in k else 1), np.float32) for k in names]
         _chk(self.L.hslam_ba_point_results(self.h, *[_ptr(a) for a in arrs]))
-        d = dict(zip(names, arrs))
-        d["Hcd_accAF"] = d["Hcd_accAF"].reshape(P, 4); d["Hcd_accLF"] = d["Hcd_accLF"].reshape(P, 4)
-        return d
+
+        def fin():
+            d = dict(zip(names, arrs))
+            d["Hcd_accAF"] = d["Hcd_accAF"].reshape(P, 4); d["Hcd_accLF"] = d["Hcd_accLF"].reshape(P, 4)
+            return d
+        return self._result(arrs, fin)
 
     def residual_results(self, want_J=True):
         R = self.R
@@ -376,15 +423,35 @@ class EnergyFunctional:
         j74 = np.zeros(R * 74, np.float32) if want_J else None
         rtz = np.zeros(R * 8, np.float32)
         _chk(self.L.hslam_ba_residual_results(self.h, _ptr(st), _ptr(act), _ptr(jp), _ptr(j74), _ptr(rtz)))
-        return dict(state_state=st, is_active=act, JpJdF=jp.reshape(R, 8), J=None if j74 is None else j74.reshape(R, 74),
-                    res_toZeroF=rtz.reshape(R, 8))
+        return self._result((st, act, jp, j74, rtz), lambda: dict(
+            state_state=st, is_active=act, JpJdF=jp.reshape(R, 8), J=None if j74 is None else j74.reshape(R, 74),
+            res_toZeroF=rtz.reshape(R, 8)))
 
     def resubstituteF_MT(self, x):
         step = np.zeros(self.P, np.float32)
         _chk(self.L.hslam_ba_resubstitute(self.h, _ptr(np.ascontiguousarray(x, np.float64)), _ptr(step)))
-        return step
+        return self._result((step,), lambda: step)
 
     def close(self):
         if self.h:
             self.L.hslam_ba_destroy(self.h)
+            self.h = C.c_void_p()
+
+
+class EnergyFunctionalBatch:
+    """A batch of independent windows stepped together: 4 launches per GN iteration for all of them."""
+
+    def __init__(self, ctx: Context, efs):
+        self.ctx, self.L = ctx, ctx.L
+        self.h = C.c_void_p()
+        self.efs = list(efs)
+        arr = (C.c_void_p * len(self.efs))(*[e.h for e in self.efs])
+        _chk(self.L.hslam_ba_batch_create(ctx.h, arr, C.c_int(len(self.efs)), C.byref(self.h)))
+
+    def iteration(self):
+        _chk(self.L.hslam_ba_batch_iteration(self.h))
+
+    def close(self):
+        if self.h:
+            self.L.hslam_ba_batch_destroy(self.h)
             self.h = C.c_void_p()

@@ -1,0 +1,986 @@
+// ba_kernels.cuh — device code of the windowed-BA hot path (included by ba.cu only).
+//
+// One Gauss-Newton iteration of one window — or of a whole BATCH of independent windows — is FOUR
+// launches: linearise(+applyRes) -> top Hessian A and L (+ per-pair fold) -> Schur fold (+ per-point
+// sums, + per-host fold) -> fp64 stitch.  Every kernel takes an array of per-window descriptors plus
+// a block-prefix table, so a batch fills the 148 SMs with one grid per stage instead of W small ones.
+//
+// Replaces (reference file:line)
+//   PointFrameResidual::linearize / applyRes / takeData / fixLinearizationF
+//       Src/OptimizationClasses.cpp:43-284, Include/OptimizationClasses.h:155-161
+//   AccumulatedTopHessianSSE::addPoint<mode> + AccumulatorApprox      Src/AccumulatedTopHessian.cpp:21-141
+//   AccumulatedSCHessianSSE::addPoint + AccumulatorXX/X (Schur fold)  Src/AccumulatedSCHessian.cpp:10-53
+//   stitchDoubleInternal / stitchDoubleMT (top and SC)                AccumulatedTopHessian.cpp:218-280, .h:69-117,
+//                                                                     AccumulatedSCHessian.cpp:54-133, .h:70-111
+//   EnergyFunctional::resubstituteFPt                                  Src/EnergyFunctional.cpp:249-274
+//
+// Determinism: no floating-point atomics.  Fixed-shape warp trees, fixed-order cross-warp sums,
+// per-chunk partials folded BY CHUNK INDEX (the last-arriving block of a pair/host does the fold, the
+// order of the sum does not depend on which block that is), gather-style stitch.
+#pragma once
+#include "common.cuh"
+
+namespace hs {
+
+constexpr int JS = 80;                 // floats per residual row: 74 of RawResidualJacobian + JI_r(2) Jab_r(2) rr(1) + pad
+constexpr int J_RESF = 0, J_XI0 = 8, J_XI1 = 14, J_C0 = 20, J_C1 = 24, J_DD = 28, J_IDX0 = 30, J_IDX1 = 38,
+              J_AB0 = 46, J_AB1 = 54, J_IDX2 = 62, J_ABIDX = 66, J_AB2 = 70, J_JIR = 74, J_JABR = 76, J_RR = 78;
+constexpr int LIN_THREADS = 128;
+constexpr int TOP_THREADS = 128;
+constexpr int TOP_PART = 96;           // 91 accumulators + nres + pad
+constexpr int SC_THREADS = 256;
+constexpr int SC_PTS = 64;             // points staged in shared memory per sub-tile
+constexpr int ST_WARPS = 16;           // warps per stitch block
+constexpr int ST_THREADS = ST_WARPS * 32;
+
+__constant__ int c_pat[8][2] = {{0, -2}, {-1, -1}, {1, -1}, {-2, 0}, {0, 0}, {2, 0}, {-1, 1}, {0, 2}};
+
+struct BAWin {
+  int n, w, h;
+  float fx, fy, cx, cy, fxi, fyi;
+  float huber, outlierTH, scale_idepth, scale_f, scale_c, affA, affB;
+  float cDeltaF[4];
+  const float4* img[HSLAM_MAX_FRAMES];
+  float frameEnergyTH[HSLAM_MAX_FRAMES];
+  const float* precalc;      // n*n*28
+  const float* adHTdeltaF;   // n*n*8
+};
+
+struct BARes {               // per-residual SoA, sorted by (host,target) pair, stride = rs
+  int R, rs;
+  const int* point;          // sorted point index
+  const int* pair;           // host + target*n
+  int8_t* state_state;
+  int8_t* newState;
+  uint8_t* isLin;
+  uint8_t* isActive;
+  float* state_energy;
+  float* newEnergy;
+  float* newEnergyWO;
+  float* J;                  // [JS][rs]
+  float* JpJdF;              // [8][rs]
+  float* rtz;                // [8][rs] res_toZeroF
+  float* cpt;                // [3][rs] centerProjectedTo
+  float* pto;                // [16][rs] projectedTo
+  float* ptc[2];             // [6][rs] per-residual contribution to (bd,Hdd,Hcd[4]) for mode A / L
+};
+
+struct BAPts {               // per-point SoA, sorted by host
+  int P;
+  const float4* uvid;        // {u, v, idepth, idepth_zero}
+  const float4* color;       // [P][2] float4
+  const float4* weights;     // [P][2] float4
+  const float* priorF;
+  const float* deltaF;
+  const int* host;
+  const int* res_begin;      // CSR over sorted residual positions, in the point's own order
+  const int* res_index;
+  float* HdiF; float* bdSumF; float* idepth_hessian;
+  float* Hdd[2]; float* bd[2]; float4* Hcd[2];
+  float* step;
+};
+
+struct TopChunk { int pair, start, count, mode; };
+struct PtChunk { int host, start, count, pad; };
+
+struct StitchArgs {
+  int n, LD;
+  const double* adHost;      // n*n*64 col-major
+  const double* adTarget;
+  const double* accTop;      // [2][n*n][TOP_PART] fp64 (A, L)
+  const double* G;           // [host][LD*LD]
+  double* Hb;                // 3 x (N*N + N)
+  int* nres;                 // [2]
+  double cPrior[4];
+  float cDeltaF[4];
+  const double* framePrior;  // n*8
+  const double* frameDeltaPrior;
+  int add_priors;
+  int has_L;                 // 0: no linearised residual exists, the L accumulators are all zero
+};
+
+// Everything the four kernels need about ONE window.
+struct BADesc {
+  BAWin W;
+  BARes r;
+  BAPts p;
+  // linearise
+  double* epart; unsigned int* ticket; double* energy;
+  // top
+  const TopChunk* topchunks; float* toppartial; unsigned int* pair_ticket; const int* pair_chunk_begin; double* accTop;
+  // schur
+  const PtChunk* ptchunks; float* scpartial; unsigned int* host_ticket; const int* host_chunk_begin; double* G; int LD;
+  // stitch
+  StitchArgs S;
+};
+
+__device__ __forceinline__ int find_window(const int* __restrict__ prefix, int nwin, int b, int& local) {
+  if (nwin == 1) { local = b; return 0; }
+  int lo = 0, hi = nwin;   // prefix[lo] <= b < prefix[hi]
+  while (hi - lo > 1) {
+    int m = (lo + hi) >> 1;
+    if (prefix[m] <= b) lo = m; else hi = m;
+  }
+  local = b - prefix[lo];
+  return lo;
+}
+
+// ------------------------------------------------------------------------------------------------
+// K4: PointFrameResidual::linearize (+ applyRes/takeData when APPLY) — one thread per residual.
+// Exactly-rounded primitives in the operation order of the source: states, energies and all 74
+// Jacobian floats are bit-identical to the float-faithful oracle.  The eight pattern projections are
+// computed first, then all 32 texel loads are issued together (memory-level parallelism), then the
+// per-pixel arithmetic runs in pattern order.
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ void take_data(const BARes& r, int k) {  // OptimizationClasses.h:155-161
+  const float* J = r.J + k;
+  const int s = r.rs;
+  float d0 = J[J_DD * s], d1 = J[(J_DD + 1) * s];
+  float JJ0 = xadd(xmul(J[(J_IDX2 + 0) * s], d0), xmul(J[(J_IDX2 + 2) * s], d1));
+  float JJ1 = xadd(xmul(J[(J_IDX2 + 1) * s], d0), xmul(J[(J_IDX2 + 3) * s], d1));
+#pragma unroll
+  for (int i = 0; i < 6; ++i)
+    r.JpJdF[i * s + k] = xadd(xmul(J[(J_XI0 + i) * s], JJ0), xmul(J[(J_XI1 + i) * s], JJ1));
+  r.JpJdF[6 * s + k] = xadd(xmul(J[(J_ABIDX + 0) * s], d0), xmul(J[(J_ABIDX + 2) * s], d1));
+  r.JpJdF[7 * s + k] = xadd(xmul(J[(J_ABIDX + 1) * s], d0), xmul(J[(J_ABIDX + 3) * s], d1));
+}
+
+__device__ __forceinline__ void apply_one(const BARes& r, int k) {  // OptimizationClasses.cpp:235-256
+  if (r.state_state[k] == HSLAM_RES_OOB) return;
+  int8_t ns = r.newState[k];
+  if (ns == HSLAM_RES_IN) { r.isActive[k] = 1; take_data(r, k); } else { r.isActive[k] = 0; }
+  r.state_state[k] = ns;
+  r.state_energy[k] = r.newEnergy[k];
+}
+
+template <bool APPLY>
+__global__ void __launch_bounds__(LIN_THREADS) ba_linearize_kernel(const BADesc* __restrict__ descs,
+                                                                   const int* __restrict__ prefix, int nwin) {
+  int lb;
+  const int win = find_window(prefix, nwin, blockIdx.x, lb);
+  const BADesc& D = descs[win];
+  const BAWin& W = D.W;
+  const BARes& r = D.r;
+  const int nblocks = (nwin == 1) ? gridDim.x : (prefix[win + 1] - prefix[win]);
+  const int k = lb * LIN_THREADS + threadIdx.x;
+  const int s = r.rs;
+  double energy_ret = 0.0;
+  if (k < r.R && !r.isLin[k]) {
+    float* J = r.J + k;
+    r.newEnergyWO[k] = -1.f;
+    bool oob = (r.state_state[k] == HSLAM_RES_OOB);
+    const float old_energy = r.state_energy[k];
+    const int p = r.point[k], pair = r.pair[k];
+    const int hostI = pair % W.n, tgtI = pair / W.n;
+    float energyLeft = 0.f, wJI2 = 0.f;
+    if (!oob) {
+      const float4* pc = reinterpret_cast<const float4*>(W.precalc + (size_t)HSLAM_PRECALC_STRIDE * pair);
+      const float4 q0 = __ldg(pc), q1 = __ldg(pc + 1), q2 = __ldg(pc + 2), q3 = __ldg(pc + 3), q4 = __ldg(pc + 4),
+                   q5 = __ldg(pc + 5), q6 = __ldg(pc + 6);
+      // [0..8] KRKi, [9..11] Kt, [12..20] R0, [21..23] t0, [24] a, [25] b, [26] b0
+      const float KRKi[9] = {q0.x, q0.y, q0.z, q0.w, q1.x, q1.y, q1.z, q1.w, q2.x};
+      const float Kt[3] = {q2.y, q2.z, q2.w};
+      const float R0[9] = {q3.x, q3.y, q3.z, q3.w, q4.x, q4.y, q4.z, q4.w, q5.x};
+      const float t0[3] = {q5.y, q5.z, q5.w};
+      const float affLL0 = q6.x, affLL1 = q6.y, b0 = q6.z;
+      const float4 pu = __ldg(D.p.uvid + p);
+      const float u_pt = pu.x, v_pt = pu.y, idp = pu.z, idz = pu.w;
+      const float wm3 = (float)(W.w - 3), hm3 = (float)(W.h - 3);
+      // ---- centre projection at the FEJ point, DirectProjection.h:20-38
+      const float Kl0 = xmul(xsub(xadd(u_pt, 0.f), W.cx), W.fxi), Kl1 = xmul(xsub(xadd(v_pt, 0.f), W.cy), W.fyi);
+      const float p0 = xadd(xdot3(R0[0], R0[1], R0[2], Kl0, Kl1, 1.f), xmul(t0[0], idz));
+      const float p1 = xadd(xdot3(R0[3], R0[4], R0[5], Kl0, Kl1, 1.f), xmul(t0[1], idz));
+      const float p2 = xadd(xdot3(R0[6], R0[7], R0[8], Kl0, Kl1, 1.f), xmul(t0[2], idz));
+      const float drescale = xdiv(1.0f, p2);
+      const float new_idepth = xmul(idz, drescale);
+      if (!(drescale > 0.f)) oob = true;
+      const float u = xmul(p0, drescale), v = xmul(p1, drescale);
+      const float Ku = xadd(xmul(u, W.fx), W.cx), Kv = xadd(xmul(v, W.fy), W.cy);
+      if (!oob && !(Ku > 1.1f && Kv > 1.1f && Ku < wm3 && Kv < hm3)) oob = true;
+      if (!oob) {
+        r.cpt[k] = Ku; r.cpt[s + k] = Kv; r.cpt[2 * s + k] = new_idepth;
+        // OptimizationClasses.cpp:85-121
+        float ddx = xmul(xmul(xmul(drescale, xsub(t0[0], xmul(t0[2], u))), W.scale_idepth), W.fx);
+        float ddy = xmul(xmul(xmul(drescale, xsub(t0[1], xmul(t0[2], v))), W.scale_idepth), W.fy);
+        float cx2 = xmul(drescale, xsub(xmul(R0[6], u), R0[0]));
+        float cx3 = xmul(xmul(xmul(W.fx, drescale), xsub(xmul(R0[7], u), R0[1])), W.fyi);
+        float cx0 = xmul(Kl0, cx2), cx1 = xmul(Kl1, cx3);
+        float cy2 = xmul(xmul(xmul(W.fy, drescale), xsub(xmul(R0[6], v), R0[3])), W.fxi);
+        float cy3 = xmul(drescale, xsub(xmul(R0[7], v), R0[4]));
+        float cy0 = xmul(Kl0, cy2), cy1 = xmul(Kl1, cy3);
+        cx0 = xmul(xadd(cx0, u), W.scale_f); cx1 = xmul(cx1, W.scale_f);
+        cx2 = xmul(xadd(cx2, 1.f), W.scale_c); cx3 = xmul(cx3, W.scale_c);
+        cy0 = xmul(cy0, W.scale_f); cy1 = xmul(xadd(cy1, v), W.scale_f);
+        cy2 = xmul(cy2, W.scale_c); cy3 = xmul(xadd(cy3, 1.f), W.scale_c);
+        J[(J_XI0 + 0) * s] = xmul(new_idepth, W.fx);
+        J[(J_XI0 + 1) * s] = 0.f;
+        J[(J_XI0 + 2) * s] = xmul(xmul(-new_idepth, u), W.fx);
+        J[(J_XI0 + 3) * s] = xmul(xmul(-u, v), W.fx);
+        J[(J_XI0 + 4) * s] = xmul(xadd(1.f, xmul(u, u)), W.fx);
+        J[(J_XI0 + 5) * s] = xmul(-v, W.fx);
+        J[(J_XI1 + 0) * s] = 0.f;
+        J[(J_XI1 + 1) * s] = xmul(new_idepth, W.fy);
+        J[(J_XI1 + 2) * s] = xmul(xmul(-new_idepth, v), W.fy);
+        J[(J_XI1 + 3) * s] = xmul(-xadd(1.f, xmul(v, v)), W.fy);
+        J[(J_XI1 + 4) * s] = xmul(xmul(u, v), W.fy);
+        J[(J_XI1 + 5) * s] = xmul(u, W.fy);
+        J[(J_C0 + 0) * s] = cx0; J[(J_C0 + 1) * s] = cx1; J[(J_C0 + 2) * s] = cx2; J[(J_C0 + 3) * s] = cx3;
+        J[(J_C1 + 0) * s] = cy0; J[(J_C1 + 1) * s] = cy1; J[(J_C1 + 2) * s] = cy2; J[(J_C1 + 3) * s] = cy3;
+        J[J_DD * s] = ddx; J[(J_DD + 1) * s] = ddy;
+        // ---- 8-pixel pattern at the current state, :141-204.  Pass 1: projections + bounds.
+        float Kup[8], Kvp[8];
+        int n_ok = 8;   // number of leading pattern pixels that are in bounds (the source returns at the first OOB)
+#pragma unroll
+        for (int idx = 0; idx < 8; ++idx) {
+          float px = xadd(u_pt, (float)c_pat[idx][0]), py = xadd(v_pt, (float)c_pat[idx][1]);
+          float a0 = xadd(xdot3(KRKi[0], KRKi[1], KRKi[2], px, py, 1.f), xmul(Kt[0], idp));
+          float a1 = xadd(xdot3(KRKi[3], KRKi[4], KRKi[5], px, py, 1.f), xmul(Kt[1], idp));
+          float a2 = xadd(xdot3(KRKi[6], KRKi[7], KRKi[8], px, py, 1.f), xmul(Kt[2], idp));
+          Kup[idx] = xdiv(a0, a2); Kvp[idx] = xdiv(a1, a2);
+          bool in = (Kup[idx] > 1.1f && Kvp[idx] > 1.1f && Kup[idx] < wm3 && Kvp[idx] < hm3);
+          if (!in && n_ok == 8) n_ok = idx;
+        }
+        // the source stores projectedTo before it tests the next pixel: pixels [0, n_ok) are written
+#pragma unroll
+        for (int idx = 0; idx < 8; ++idx)
+          if (idx < n_ok) { r.pto[(2 * idx) * s + k] = Kup[idx]; r.pto[(2 * idx + 1) * s + k] = Kvp[idx]; }
+        if (n_ok < 8) {
+          oob = true;
+          // Jacobian entries of the pixels before the first OOB one are written by the source as well;
+          // they are never read for an OOB residual, so they are left untouched here.
+        } else {
+          // Pass 2: all 32 texel loads in flight at once.
+          const float4* img = W.img[tgtI];
+          Hit3 hit[8];
+#pragma unroll
+          for (int idx = 0; idx < 8; ++idx) hit[idx] = interp33(img, Kup[idx], Kvp[idx], W.w);
+          const float4 c0 = __ldg(D.p.color + 2 * p), c1 = __ldg(D.p.color + 2 * p + 1);
+          const float4 w0 = __ldg(D.p.weights + 2 * p), w1 = __ldg(D.p.weights + 2 * p + 1);
+          const float color[8] = {c0.x, c0.y, c0.z, c0.w, c1.x, c1.y, c1.z, c1.w};
+          const float wgt[8] = {w0.x, w0.y, w0.z, w0.w, w1.x, w1.y, w1.z, w1.w};
+          float II00 = 0.f, II11 = 0.f, II10 = 0.f, AI00 = 0.f, AI01 = 0.f, AI10 = 0.f, AI11 = 0.f;
+          float AA00 = 0.f, AA01 = 0.f, AA11 = 0.f;
+          float JIr0 = 0.f, JIr1 = 0.f, Jabr0 = 0.f, Jabr1 = 0.f, rr = 0.f;
+          bool nonfinite = false;
+#pragma unroll
+          for (int idx = 0; idx < 8; ++idx) {
+            if (nonfinite) continue;
+            const float hI = hit[idx].I, hdx = hit[idx].dx, hdy = hit[idx].dy;
+            if (!isfinite(hI)) { nonfinite = true; continue; }   // :157-161
+            float residual = xsub(hI, xadd(xmul(affLL0, color[idx]), affLL1));
+            float drdA = xsub(color[idx], b0);
+            float w = xsqrt(xdiv(W.outlierTH, xadd(W.outlierTH, xadd(xmul(hdx, hdx), xmul(hdy, hdy)))));
+            w = xmul(0.5f, xadd(w, wgt[idx]));
+            float ar = fabsf(residual);
+            float hw = ar < W.huber ? 1.f : xdiv(W.huber, ar);
+            energyLeft = xadd(energyLeft, xmul(xmul(xmul(xmul(xmul(w, w), hw), residual), residual), xsub(2.f, hw)));
+            if (hw < 1.f) hw = xsqrt(hw);
+            hw = xmul(hw, w);
+            float h1 = xmul(hdx, hw), h2 = xmul(hdy, hw);
+            float rF = xmul(residual, hw), ja = xmul(drdA, hw);
+            J[(J_RESF + idx) * s] = rF;
+            J[(J_IDX0 + idx) * s] = h1;
+            J[(J_IDX1 + idx) * s] = h2;
+            float jab0 = W.affA < 0.f ? 0.f : ja, jab1 = W.affB < 0.f ? 0.f : hw;
+            J[(J_AB0 + idx) * s] = jab0;
+            J[(J_AB1 + idx) * s] = jab1;
+            II00 = xadd(II00, xmul(h1, h1)); II11 = xadd(II11, xmul(h2, h2)); II10 = xadd(II10, xmul(h1, h2));
+            AI00 = xadd(AI00, xmul(ja, h1)); AI01 = xadd(AI01, xmul(ja, h2));
+            AI10 = xadd(AI10, xmul(hw, h1)); AI11 = xadd(AI11, xmul(hw, h2));
+            AA00 = xadd(AA00, xmul(xmul(xmul(drdA, drdA), hw), hw));
+            AA01 = xadd(AA01, xmul(xmul(drdA, hw), hw));
+            AA11 = xadd(AA11, xmul(hw, hw));
+            // wJI2_sum uses hitColor AFTER the *= hw (OptimizationClasses.cpp:174-175 precede :197)
+            wJI2 = xadd(wJI2, xmul(xmul(hw, hw), xadd(xmul(h1, h1), xmul(h2, h2))));
+            // sums addPoint<0> forms from resF (AccumulatedTopHessian.cpp:84-94), same order
+            JIr0 = xadd(JIr0, xmul(rF, h1)); JIr1 = xadd(JIr1, xmul(rF, h2));
+            Jabr0 = xadd(Jabr0, xmul(rF, jab0)); Jabr1 = xadd(Jabr1, xmul(rF, jab1));
+            rr = xadd(rr, xmul(rF, rF));
+          }
+          if (nonfinite) {
+            oob = true;
+          } else {
+            J[(J_IDX2 + 0) * s] = II00; J[(J_IDX2 + 1) * s] = II10; J[(J_IDX2 + 2) * s] = II10; J[(J_IDX2 + 3) * s] = II11;
+            J[(J_ABIDX + 0) * s] = AI00; J[(J_ABIDX + 1) * s] = AI10; J[(J_ABIDX + 2) * s] = AI01; J[(J_ABIDX + 3) * s] = AI11;
+            J[(J_AB2 + 0) * s] = AA00; J[(J_AB2 + 1) * s] = AA01; J[(J_AB2 + 2) * s] = AA01; J[(J_AB2 + 3) * s] = AA11;
+            J[(J_JIR + 0) * s] = JIr0; J[(J_JIR + 1) * s] = JIr1; J[(J_JABR + 0) * s] = Jabr0; J[(J_JABR + 1) * s] = Jabr1;
+            J[J_RR * s] = rr;
+          }
+        }
+      }
+    }
+    if (oob) {
+      r.newState[k] = HSLAM_RES_OOB;
+      energy_ret = (double)old_energy;
+    } else {
+      r.newEnergyWO[k] = energyLeft;
+      float th = fmaxf(W.frameEnergyTH[hostI], W.frameEnergyTH[tgtI]);
+      if (energyLeft > th || wJI2 < 2.f) { energyLeft = th; r.newState[k] = HSLAM_RES_OUT; }
+      else r.newState[k] = HSLAM_RES_IN;
+      r.newEnergy[k] = energyLeft;
+      energy_ret = (double)energyLeft;
+    }
+    if (APPLY) apply_one(r, k);
+  }
+  // ---- energy: block tree in fp64, per-block partial, last block of the window folds in block order
+  __shared__ double wsumd[LIN_THREADS / 32];
+  __shared__ bool last;
+  double e = warp_sum(energy_ret);
+  if ((threadIdx.x & 31) == 0) wsumd[threadIdx.x >> 5] = e;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    D.epart[lb] = (wsumd[0] + wsumd[1]) + (wsumd[2] + wsumd[3]);
+    __threadfence();
+    last = (atomicAdd(D.ticket, 1u) == (unsigned)nblocks - 1);
+  }
+  __syncthreads();
+  if (last && threadIdx.x < 32) {
+    __threadfence();
+    double acc = 0.0;
+    for (int b = threadIdx.x; b < nblocks; b += 32) acc += __ldcg(D.epart + b);
+    acc = warp_sum(acc);
+    if (threadIdx.x == 0) { *D.energy = acc; *D.ticket = 0; }
+  }
+}
+
+__global__ void ba_apply_kernel(BARes r) {
+  int k = blockIdx.x * blockDim.x + threadIdx.x;
+  if (k < r.R && !r.isLin[k]) apply_one(r, k);
+}
+
+// PointFrameResidual::fixLinearizationF, OptimizationClasses.cpp:258-284 (ids = sorted positions)
+__global__ void ba_fixlin_kernel(BAWin W, BARes r, BAPts pts, const int* __restrict__ ids, int count) {
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= count) return;
+  int k = ids[i];
+  const int s = r.rs;
+  const float* J = r.J + k;
+  const float* dp = W.adHTdeltaF + 8 * r.pair[k];
+  float dx = 0.f, dy = 0.f, cxs = 0.f, cys = 0.f;
+#pragma unroll
+  for (int j = 0; j < 6; ++j) { dx = xadd(dx, xmul(J[(J_XI0 + j) * s], dp[j])); dy = xadd(dy, xmul(J[(J_XI1 + j) * s], dp[j])); }
+#pragma unroll
+  for (int j = 0; j < 4; ++j) { cxs = xadd(cxs, xmul(J[(J_C0 + j) * s], W.cDeltaF[j])); cys = xadd(cys, xmul(J[(J_C1 + j) * s], W.cDeltaF[j])); }
+  float dd = pts.deltaF[r.point[k]];
+  float Jpx = xadd(xadd(dx, cxs), xmul(J[J_DD * s], dd));
+  float Jpy = xadd(xadd(dy, cys), xmul(J[(J_DD + 1) * s], dd));
+  float da = dp[6], db = dp[7];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) {
+    float rtz = J[(J_RESF + j) * s];
+    rtz = xsub(rtz, xmul(J[(J_IDX0 + j) * s], Jpx));
+    rtz = xsub(rtz, xmul(J[(J_IDX1 + j) * s], Jpy));
+    rtz = xsub(rtz, xmul(J[(J_AB0 + j) * s], da));
+    rtz = xsub(rtz, xmul(J[(J_AB1 + j) * s], db));
+    r.rtz[j * s + k] = rtz;
+  }
+  r.isLin[k] = 1;
+}
+
+// ------------------------------------------------------------------------------------------------
+// K5: AccumulatedTopHessianSSE::addPoint<mode> — per-pair 13x13 relative accumulators, modes A and L
+// in ONE launch.  A block owns a chunk of ONE (mode,pair) residual segment; each thread accumulates
+// its residuals into 91 registers ([C(4);xi(6)]^2 upper = 55, [C;xi] x [a,b,r] = 30, [a,b,r]^2 upper
+// = 6), then warp shuffles -> shared memory -> fixed-order cross-warp sum -> per-chunk partial.  The
+// last block of a (mode,pair) to finish folds that pair's chunks in chunk order into fp64.
+// ------------------------------------------------------------------------------------------------
+template <int MODE>
+__device__ __forceinline__ void top_accumulate(const BADesc& D, const TopChunk& ch, float (&acc)[91], int& nres) {
+  const BAWin& W = D.W;
+  const BARes& r = D.r;
+  const int s = r.rs;
+  float dp[8];
+  if (MODE == 1) {
+#pragma unroll
+    for (int j = 0; j < 8; ++j) dp[j] = __ldg(W.adHTdeltaF + 8 * ch.pair + j);
+  }
+  for (int k = ch.start + threadIdx.x; k < ch.start + ch.count; k += TOP_THREADS) {
+    bool lin = r.isLin[k] != 0, act = r.isActive[k] != 0;
+    if (MODE == 0 ? (lin || !act) : (!lin || !act)) continue;
+    const float* J = r.J + k;
+    float x[10], y[10];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) { x[j] = J[(J_C0 + j) * s]; y[j] = J[(J_C1 + j) * s]; }
+#pragma unroll
+    for (int j = 0; j < 6; ++j) { x[4 + j] = J[(J_XI0 + j) * s]; y[4 + j] = J[(J_XI1 + j) * s]; }
+    const float d0 = J[J_DD * s], d1 = J[(J_DD + 1) * s];
+    const float a = J[(J_IDX2 + 0) * s], b = J[(J_IDX2 + 2) * s], c = J[(J_IDX2 + 3) * s];
+    const float AI00 = J[(J_ABIDX + 0) * s], AI10 = J[(J_ABIDX + 1) * s], AI01 = J[(J_ABIDX + 2) * s],
+                AI11 = J[(J_ABIDX + 3) * s];
+    const float AA00 = J[(J_AB2 + 0) * s], AA01 = J[(J_AB2 + 2) * s], AA11 = J[(J_AB2 + 3) * s];
+    float JIr0, JIr1, Jabr0, Jabr1, rr;
+    if (MODE == 0) {
+      JIr0 = J[(J_JIR + 0) * s]; JIr1 = J[(J_JIR + 1) * s];
+      Jabr0 = J[(J_JABR + 0) * s]; Jabr1 = J[(J_JABR + 1) * s]; rr = J[J_RR * s];
+    } else {
+      // resApprox = res_toZeroF + J*delta, AccumulatedTopHessian.cpp:63-81 (sequential sums)
+      float dx = 0.f, dy = 0.f, cxs = 0.f, cys = 0.f;
+#pragma unroll
+      for (int j = 0; j < 6; ++j) { dx = xadd(dx, xmul(x[4 + j], dp[j])); dy = xadd(dy, xmul(y[4 + j], dp[j])); }
+#pragma unroll
+      for (int j = 0; j < 4; ++j) { cxs = xadd(cxs, xmul(x[j], W.cDeltaF[j])); cys = xadd(cys, xmul(y[j], W.cDeltaF[j])); }
+      float dd = D.p.deltaF[r.point[k]];
+      float Jpx = xadd(xadd(dx, cxs), xmul(d0, dd)), Jpy = xadd(xadd(dy, cys), xmul(d1, dd));
+      JIr0 = JIr1 = Jabr0 = Jabr1 = rr = 0.f;
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        float i0 = J[(J_IDX0 + j) * s], i1 = J[(J_IDX1 + j) * s], a0 = J[(J_AB0 + j) * s], a1 = J[(J_AB1 + j) * s];
+        float rz = r.rtz[j * s + k];
+        rz = xadd(rz, xmul(i0, Jpx)); rz = xadd(rz, xmul(i1, Jpy));
+        rz = xadd(rz, xmul(a0, dp[6])); rz = xadd(rz, xmul(a1, dp[7]));
+        JIr0 = xadd(JIr0, xmul(rz, i0)); JIr1 = xadd(JIr1, xmul(rz, i1));
+        Jabr0 = xadd(Jabr0, xmul(rz, a0)); Jabr1 = xadd(Jabr1, xmul(rz, a1));
+        rr = xadd(rr, xmul(rz, rz));
+      }
+    }
+    // 10x10 upper triangle: [x y] [[a b],[b c]] [x y]^T
+    int idx = 0;
+#pragma unroll
+    for (int rI = 0; rI < 10; ++rI) {
+      float px = fmaf(a, x[rI], b * y[rI]), py = fmaf(b, x[rI], c * y[rI]);
+#pragma unroll
+      for (int cI = rI; cI < 10; ++cI, ++idx) acc[idx] += fmaf(x[cI], px, y[cI] * py);
+    }
+    // 10x3 top-right: columns a, b, r  (MatrixAccumulators.h:859-901)
+#pragma unroll
+    for (int rI = 0; rI < 10; ++rI) {
+      acc[55 + 3 * rI + 0] += fmaf(x[rI], AI00, y[rI] * AI01);
+      acc[55 + 3 * rI + 1] += fmaf(x[rI], AI10, y[rI] * AI11);
+      acc[55 + 3 * rI + 2] += fmaf(x[rI], JIr0, y[rI] * JIr1);
+    }
+    acc[85] += AA00; acc[86] += AA01; acc[87] += Jabr0; acc[88] += AA11; acc[89] += Jabr1; acc[90] += rr;
+    nres++;
+    // per-residual contribution to the point sums (:114-117), exact ops: they are summed per point in
+    // the point's own order by the Schur kernel, which keeps Hdd/bd/Hcd bit-identical to the oracle.
+    float Ji0 = xadd(xmul(a, d0), xmul(b, d1)), Ji1 = xadd(xmul(b, d0), xmul(c, d1));
+    float* o = r.ptc[MODE] + k;
+    o[0] = xadd(xmul(JIr0, d0), xmul(JIr1, d1));
+    o[s] = xadd(xmul(Ji0, d0), xmul(Ji1, d1));
+#pragma unroll
+    for (int j = 0; j < 4; ++j) o[(2 + j) * s] = xadd(xmul(x[j], Ji0), xmul(y[j], Ji1));
+  }
+}
+
+__global__ void __launch_bounds__(TOP_THREADS) ba_top_kernel(const BADesc* __restrict__ descs,
+                                                             const int* __restrict__ prefix, int nwin,
+                                                             int lb_offset) {
+  int lb;
+  const int win = find_window(prefix, nwin, blockIdx.x, lb);
+  lb += lb_offset;   // single-window launches of mode L only start at the first mode-1 chunk
+  const BADesc& D = descs[win];
+  const TopChunk ch = D.topchunks[lb];
+  float acc[91];
+#pragma unroll
+  for (int i = 0; i < 91; ++i) acc[i] = 0.f;
+  int nres = 0;
+  if (ch.mode == 0) top_accumulate<0>(D, ch, acc, nres);
+  else top_accumulate<1>(D, ch, acc, nres);
+
+  __shared__ float red[TOP_THREADS / 32][TOP_PART];
+  __shared__ bool last;
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+#pragma unroll
+  for (int i = 0; i < 91; ++i) {
+    float v = warp_sum(acc[i]);
+    if (lane == 0) red[wid][i] = v;
+  }
+  int q = warp_sum(nres);
+  if (lane == 0) red[wid][91] = __int_as_float(q);
+  __syncthreads();
+  float* out = D.toppartial + (size_t)lb * TOP_PART;
+  if (threadIdx.x < 92) {
+    int t = threadIdx.x;
+    if (t == 91) {
+      int n = 0;
+#pragma unroll
+      for (int w = 0; w < TOP_THREADS / 32; ++w) n += __float_as_int(red[w][91]);
+      out[91] = __int_as_float(n);
+    } else {
+      float v = 0.f;
+#pragma unroll
+      for (int w = 0; w < TOP_THREADS / 32; ++w) v += red[w][t];
+      out[t] = v;
+    }
+    __threadfence();
+  }
+  __syncthreads();
+  // ---- per-(mode,pair) fold by the last block of that pair, chunks visited in index order
+  const int nn = D.W.n * D.W.n;
+  const int slot = ch.mode * nn + ch.pair;
+  const int cb = D.pair_chunk_begin[slot], ce = D.pair_chunk_begin[slot + 1];
+  if (threadIdx.x == 0) last = (atomicAdd(D.pair_ticket + slot, 1u) == (unsigned)(ce - cb) - 1);
+  __syncthreads();
+  if (last) {
+    __threadfence();
+    if (threadIdx.x < 92) {
+      int t = threadIdx.x;
+      double* dst = D.accTop + (size_t)slot * TOP_PART;
+      if (t == 91) {
+        int n = 0;
+        for (int c = cb; c < ce; ++c) n += __float_as_int(__ldcg(D.toppartial + (size_t)c * TOP_PART + 91));
+        dst[91] = (double)n;
+      } else {
+        double sum = 0.0;
+        for (int c = cb; c < ce; ++c) sum += (double)__ldcg(D.toppartial + (size_t)c * TOP_PART + t);
+        dst[t] = sum;
+      }
+    }
+    if (threadIdx.x == 0) D.pair_ticket[slot] = 0;
+  }
+}
+
+// Per-point sums of Hdd/bd/Hcd over the point's residuals in the point's own order (the tail of
+// addPoint<mode>, AccumulatedTopHessian.cpp:122-139).  Only used by the stand-alone accumulate(A|L)
+// entry points; the fused path does this inside the Schur kernel.
+__global__ void ba_point_sum_kernel(BARes r, BAPts pts, int do_A, int do_L) {
+  int p = blockIdx.x * blockDim.x + threadIdx.x;
+  if (p >= pts.P) return;
+  const int s = r.rs;
+  float bdv[2] = {0.f, 0.f}, Hddv[2] = {0.f, 0.f}, Hcdv[2][4] = {{0.f, 0.f, 0.f, 0.f}, {0.f, 0.f, 0.f, 0.f}};
+  for (int i = pts.res_begin[p]; i < pts.res_begin[p + 1]; ++i) {
+    int k = pts.res_index[i];
+    if (!r.isActive[k]) continue;
+    int m = r.isLin[k] ? 1 : 0;
+    if ((m == 0 && !do_A) || (m == 1 && !do_L)) continue;
+    const float* o = r.ptc[m] + k;
+    bdv[m] = xadd(bdv[m], o[0]);
+    Hddv[m] = xadd(Hddv[m], o[s]);
+#pragma unroll
+    for (int j = 0; j < 4; ++j) Hcdv[m][j] = xadd(Hcdv[m][j], o[(2 + j) * s]);
+  }
+  if (do_A) { pts.Hdd[0][p] = Hddv[0]; pts.bd[0][p] = bdv[0]; pts.Hcd[0][p] = make_float4(Hcdv[0][0], Hcdv[0][1], Hcdv[0][2], Hcdv[0][3]); }
+  if (do_L) { pts.Hdd[1][p] = Hddv[1]; pts.bd[1][p] = bdv[1]; pts.Hcd[1][p] = make_float4(Hcdv[1][0], Hcdv[1][1], Hcdv[1][2], Hcdv[1][3]); }
+}
+
+// ------------------------------------------------------------------------------------------------
+// K6: AccumulatedSCHessianSSE::addPoint — the per-point Schur fold (+ the tail of addPoint<mode>:
+// per-point sums of Hdd/bd/Hcd over the point's residuals in the point's own order).
+// For the points of one host the reference's accD[(h,t1,t2)], accE[(h,t1)], accEB[(h,t1)], accHcc,
+// accbc are all blocks of ONE weighted Gram matrix  G_h = sum_p HdiF_p * a_p a_p^T  of the vector
+// a_p = [JpJdF(p->t) for t = 0..n-1 (zero where there is no active residual) ; Hcd(4) ; bdSumF].
+// A block stages SC_PTS such vectors in shared memory and every thread owns 4x4 register tiles of
+// the upper triangle of G; points are visited sequentially, so the sum order is fixed.  fp32 SIMT:
+// the matrix is only (8n+5) wide — tensor cores are deliberately not used (north_star).
+// ------------------------------------------------------------------------------------------------
+constexpr int SC_MAXT = 3;   // upper-triangular tiles per thread: NT(NT+1)/2 <= 3*256 (n <= 16: NT=34 -> 595)
+
+__device__ __forceinline__ void tri_decode(int t, int NT, int& ti, int& tj) {
+  // t-th tile of the upper triangle enumerated row by row: row ti has NT-ti tiles
+  int row = 0, rem = t;
+  while (rem >= NT - row) { rem -= NT - row; row++; }
+  ti = row; tj = row + rem;
+}
+
+__global__ void __launch_bounds__(SC_THREADS) ba_schur_kernel(const BADesc* __restrict__ descs,
+                                                              const int* __restrict__ prefix, int nwin) {
+  extern __shared__ __align__(16) float smem[];
+  int lb;
+  const int win = find_window(prefix, nwin, blockIdx.x, lb);
+  const BADesc& D = descs[win];
+  const BARes& r = D.r;
+  const BAPts& pts = D.p;
+  const int LD = D.LD;
+  float* A = smem;                       // [SC_PTS][LD]
+  float* wv = smem + SC_PTS * LD;        // [SC_PTS] HdiF
+  __shared__ bool last;
+  const PtChunk ch = D.ptchunks[lb];
+  const int s = r.rs, n = D.W.n;
+  const int NT = LD / 4, ntiles = NT * (NT + 1) / 2;
+  int tI[SC_MAXT], tJ[SC_MAXT];
+  float acc[SC_MAXT][16];
+#pragma unroll
+  for (int j = 0; j < SC_MAXT; ++j) {
+    int tile = threadIdx.x + j * SC_THREADS;
+    tI[j] = tJ[j] = -1;
+    if (tile < ntiles) tri_decode(tile, NT, tI[j], tJ[j]);
+#pragma unroll
+    for (int i = 0; i < 16; ++i) acc[j][i] = 0.f;
+  }
+
+  for (int base = 0; base < ch.count; base += SC_PTS) {
+    const int cnt = min(SC_PTS, ch.count - base);
+    for (int i = threadIdx.x; i < SC_PTS * LD; i += SC_THREADS) A[i] = 0.f;
+    __syncthreads();
+    // phase 1: 4 lanes per point.  Lane 0 forms the point's Hdd/bd/Hcd sums sequentially (the order of
+    // addPoint<mode>), all 4 lanes copy the JpJdF rows of the point's active residuals.
+    {
+      const int lp = threadIdx.x >> 2, q = threadIdx.x & 3;
+      int ngood = 0;
+      const int p = ch.start + base + lp;
+      float bdv[2] = {0.f, 0.f}, Hddv[2] = {0.f, 0.f};
+      float Hcdv[2][4] = {{0.f, 0.f, 0.f, 0.f}, {0.f, 0.f, 0.f, 0.f}};
+      if (lp < cnt) {
+        const int rb = pts.res_begin[p], re = pts.res_begin[p + 1];
+        for (int i = rb + q; i < re; i += 4) {
+          int k = pts.res_index[i];
+          if (!r.isActive[k]) continue;
+          ngood++;
+          int t = r.pair[k] / n;
+          float* dst = A + lp * LD + 8 * t;
+#pragma unroll
+          for (int j = 0; j < 8; ++j) dst[j] = r.JpJdF[j * s + k];
+        }
+        if (q == 0) {
+          for (int i = rb; i < re; ++i) {   // AccumulatedTopHessian.cpp:35-120, residual order of the point
+            int k = pts.res_index[i];
+            if (!r.isActive[k]) continue;
+            int m = r.isLin[k] ? 1 : 0;
+            const float* o = r.ptc[m] + k;
+            bdv[m] = xadd(bdv[m], o[0]);
+            Hddv[m] = xadd(Hddv[m], o[s]);
+#pragma unroll
+            for (int j = 0; j < 4; ++j) Hcdv[m][j] = xadd(Hcdv[m][j], o[(2 + j) * s]);
+          }
+        }
+      }
+      ngood += __shfl_xor_sync(0xffffffffu, ngood, 1);   // all 32 lanes take part
+      ngood += __shfl_xor_sync(0xffffffffu, ngood, 2);
+      if (lp < cnt) {
+        if (q == 0) {
+          for (int m = 0; m < 2; ++m) {   // :122-139
+            pts.Hdd[m][p] = Hddv[m]; pts.bd[m][p] = bdv[m];
+            pts.Hcd[m][p] = make_float4(Hcdv[m][0], Hcdv[m][1], Hcdv[m][2], Hcdv[m][3]);
+          }
+          // AccumulatedSCHessian.cpp:12-33
+          float hdi = 0.f, bds = 0.f, idh = 0.f;
+          float4 hcd = make_float4(0.f, 0.f, 0.f, 0.f);
+          if (ngood > 0) {
+            float H = xadd(xadd(Hddv[0], Hddv[1]), pts.priorF[p]);
+            if (H < 1e-10f) H = 1e-10f;
+            idh = H;
+            hdi = xdiv(1.0f, H);
+            bds = xadd(bdv[0], bdv[1]);
+            bds = xadd(bds, xmul(pts.priorF[p], pts.deltaF[p]));  // shiftPriorToZero = true (EnergyFunctional.cpp:209)
+            hcd = make_float4(xadd(Hcdv[0][0], Hcdv[1][0]), xadd(Hcdv[0][1], Hcdv[1][1]), xadd(Hcdv[0][2], Hcdv[1][2]),
+                              xadd(Hcdv[0][3], Hcdv[1][3]));
+          }
+          pts.HdiF[p] = hdi; pts.bdSumF[p] = bds; pts.idepth_hessian[p] = idh;
+          float* dst = A + lp * LD + 8 * n;
+          dst[0] = hcd.x; dst[1] = hcd.y; dst[2] = hcd.z; dst[3] = hcd.w; dst[4] = bds;
+          wv[lp] = hdi;
+        }
+      } else if (lp < SC_PTS && q == 0) {
+        wv[lp] = 0.f;
+      }
+    }
+    __syncthreads();
+    // phase 2: G += sum_p (w_p a_p) a_p^T, 4x4 register tiles of the upper triangle, points in order
+#pragma unroll
+    for (int j = 0; j < SC_MAXT; ++j) {
+      if (tI[j] >= 0) {
+        const float* ap = A + 4 * tI[j];
+        const float* bp = A + 4 * tJ[j];
+        for (int lp = 0; lp < cnt; ++lp) {
+          float w = wv[lp];
+          float4 av = *reinterpret_cast<const float4*>(ap + lp * LD);
+          float4 bv = *reinterpret_cast<const float4*>(bp + lp * LD);
+          float a4[4] = {w * av.x, w * av.y, w * av.z, w * av.w};
+          float b4[4] = {bv.x, bv.y, bv.z, bv.w};
+#pragma unroll
+          for (int ii = 0; ii < 4; ++ii)
+#pragma unroll
+            for (int jj = 0; jj < 4; ++jj) acc[j][4 * ii + jj] = fmaf(a4[ii], b4[jj], acc[j][4 * ii + jj]);
+        }
+      }
+    }
+    __syncthreads();
+  }
+  float* out = D.scpartial + (size_t)lb * LD * LD;
+#pragma unroll
+  for (int j = 0; j < SC_MAXT; ++j) {
+    if (tI[j] >= 0) {
+#pragma unroll
+      for (int ii = 0; ii < 4; ++ii)
+        *reinterpret_cast<float4*>(out + (size_t)(4 * tI[j] + ii) * LD + 4 * tJ[j]) =
+            make_float4(acc[j][4 * ii], acc[j][4 * ii + 1], acc[j][4 * ii + 2], acc[j][4 * ii + 3]);
+    }
+  }
+  __threadfence();
+  __syncthreads();
+  // ---- per-host fold by the last block of that host, chunks in index order
+  const int cb = D.host_chunk_begin[ch.host], ce = D.host_chunk_begin[ch.host + 1];
+  if (threadIdx.x == 0) last = (atomicAdd(D.host_ticket + ch.host, 1u) == (unsigned)(ce - cb) - 1);
+  __syncthreads();
+  if (last) {
+    __threadfence();
+    double* G = D.G + (size_t)ch.host * LD * LD;
+    for (int i = threadIdx.x; i < LD * LD; i += SC_THREADS) {
+      int row = i / LD, col = i % LD;
+      if ((col >> 2) < (row >> 2)) continue;   // lower tiles are not produced
+      double sum = 0.0;
+      for (int c = cb; c < ce; ++c) sum += (double)__ldcg(D.scpartial + (size_t)c * LD * LD + i);
+      G[i] = sum;
+    }
+    if (threadIdx.x == 0) D.host_ticket[ch.host] = 0;
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// K7: stitch — relative accumulators -> (8n+4)^2 system in fp64, gather form.
+// One block per output 8x8 block (a,b) of one system; index n is the calibration block.  The
+// Ad * M * Ad^T "sandwiches" that land in a block are dealt round-robin to the block's 16 warps (each
+// warp computes one 8x8 sandwich with two elements per lane through a private shared-memory stage),
+// then the warps' partial blocks are summed in warp order.
+// ------------------------------------------------------------------------------------------------
+// element (r,c) of the 13x13 relative accumulator from its packed 91-value form
+__device__ __forceinline__ double acc13(const double* a, int r, int c) {
+  if (r > c) { int t = r; r = c; c = t; }
+  if (c < 10) return a[r * 10 - (r * (r - 1)) / 2 + (c - r)];   // row-major upper triangle of 10x10
+  if (r < 10) return a[55 + 3 * r + (c - 10)];
+  const int br[3][3] = {{85, 86, 87}, {86, 88, 89}, {87, 89, 90}};
+  return a[br[r - 10][c - 10]];
+}
+__device__ __forceinline__ double Gsym(const double* G, int LD, int i, int j) {
+  return ((j >> 2) >= (i >> 2)) ? G[(size_t)i * LD + j] : G[(size_t)j * LD + i];
+}
+
+// out(r, c0) and out(r, c1) of A1 * M * A2^T for one warp: lane -> r = lane&7, c0 = lane>>3, c1 = c0+4
+template <class MF>
+__device__ __forceinline__ void sandwich_warp(const double* __restrict__ A1, const double* __restrict__ A2, MF M,
+                                              double (*tmp)[9], int lane, double& o0, double& o1) {
+  const int r = lane & 7, c0 = lane >> 3, c1 = c0 + 4;
+  double t0 = 0.0, t1 = 0.0;
+#pragma unroll
+  for (int y = 0; y < 8; ++y) {
+    double m = M(r, y);
+    t0 += m * A2[c0 + 8 * y];
+    t1 += m * A2[c1 + 8 * y];
+  }
+  __syncwarp();
+  tmp[r][c0] = t0; tmp[r][c1] = t1;
+  __syncwarp();
+#pragma unroll
+  for (int x = 0; x < 8; ++x) {
+    double a = A1[r + 8 * x];
+    o0 += a * tmp[x][c0];
+    o1 += a * tmp[x][c1];
+  }
+}
+
+__global__ void __launch_bounds__(ST_THREADS) ba_stitch_kernel(const BADesc* __restrict__ descs,
+                                                               const int* __restrict__ prefix, int nwin,
+                                                               int sys_begin, int sys_end) {
+  int lb;
+  const int win = find_window(prefix, nwin, blockIdx.x, lb);
+  const StitchArgs& S = descs[win].S;
+  const int n = S.n, N = 8 * n + 4, LD = S.LD;
+  const int nb1 = n + 1;
+  const int sys = lb / (nb1 * nb1), ab = lb % (nb1 * nb1);
+  const int a = ab % nb1, b = ab / nb1;
+  if (sys < sys_begin || sys >= sys_end) return;   // systems (0=A, 1=L, 2=SC) this launch produces
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  __shared__ double tmp[ST_WARPS][8][9];
+  __shared__ double part[ST_WARPS][64];
+  double* H = S.Hb + (size_t)sys * ((size_t)N * N + N);
+  double* bv = H + (size_t)N * N;
+  const int nn = n * n;
+  auto AdH = [&](int h, int t) { return S.adHost + 64 * (size_t)(h + t * n); };
+  auto AdT = [&](int h, int t) { return S.adTarget + 64 * (size_t)(h + t * n); };
+  double o0 = 0.0, o1 = 0.0;
+  int ci = 0;   // contribution counter, identical in every warp
+#define CONTRIB(A1, A2, MF)                                                                 \
+  do {                                                                                      \
+    if ((ci % ST_WARPS) == warp) sandwich_warp((A1), (A2), (MF), tmp[warp], lane, o0, o1);   \
+    ci++;                                                                                   \
+  } while (0)
+
+  if (sys < 2) {
+    const double* acc = S.accTop + (size_t)sys * nn * TOP_PART;
+    auto ACC = [&](int h, int t) { return acc + (size_t)(h + t * n) * TOP_PART; };
+    const bool usePrior = (sys == 1) && S.add_priors;
+    const bool live = (sys == 0) || S.has_L;   // without linearised residuals the L accumulators are zero
+    if (a < n && b < n) {
+      if (a > b) return;                        // written by the mirror block (AccumulatedTopHessian.h:105-116)
+      if (live) {
+        if (a == b) {
+          // S[a,a] = sum_t AdH[a,t] M[a,t] AdH[a,t]^T + sum_h AdT[h,a] M[h,a] AdT[h,a]^T + AdH[a,a] M[a,a] AdT[a,a]^T
+          for (int t = 0; t < n; ++t) {
+            const double* m = ACC(a, t);
+            if (m[91] == 0.0) continue;   // acc.num == 0 (AccumulatedTopHessian.cpp:243)
+            CONTRIB(AdH(a, t), AdH(a, t), [&](int x, int y) { return acc13(m, 4 + x, 4 + y); });
+          }
+          for (int h = 0; h < n; ++h) {
+            const double* m = ACC(h, a);
+            if (m[91] == 0.0) continue;
+            CONTRIB(AdT(h, a), AdT(h, a), [&](int x, int y) { return acc13(m, 4 + x, 4 + y); });
+          }
+          const double* m = ACC(a, a);
+          if (m[91] != 0.0) CONTRIB(AdH(a, a), AdT(a, a), [&](int x, int y) { return acc13(m, 4 + x, 4 + y); });
+        } else {
+          // H[a,b] = S[a,b] + S[b,a]^T
+          const double* m1 = ACC(a, b);
+          if (m1[91] != 0.0) CONTRIB(AdH(a, b), AdT(a, b), [&](int x, int y) { return acc13(m1, 4 + x, 4 + y); });
+          const double* m2 = ACC(b, a);
+          if (m2[91] != 0.0) CONTRIB(AdT(b, a), AdH(b, a), [&](int x, int y) { return acc13(m2, 4 + y, 4 + x); });
+        }
+      }
+      const int r = lane & 7, c0 = lane >> 3;
+      part[warp][r + 8 * c0] = o0; part[warp][r + 8 * (c0 + 4)] = o1;
+      __syncthreads();
+      if (threadIdx.x < 64) {
+        const int rr = threadIdx.x & 7, cc = threadIdx.x >> 3;
+        double o = 0.0;
+#pragma unroll
+        for (int w = 0; w < ST_WARPS; ++w) o += part[w][threadIdx.x];
+        if (a == b) {
+          if (usePrior && rr == cc) o += S.framePrior[8 * a + rr];
+          H[(size_t)(4 + 8 * a + rr) + (size_t)N * (4 + 8 * a + cc)] = o;
+        } else {
+          H[(size_t)(4 + 8 * a + rr) + (size_t)N * (4 + 8 * b + cc)] = o;
+          H[(size_t)(4 + 8 * b + cc) + (size_t)N * (4 + 8 * a + rr)] = o;
+        }
+      }
+    } else if (a < n && b == n) {
+      // H[a, 0:4] (8x4), its transpose, and b[a]: mat-vec products, one thread per output element
+      if (threadIdx.x < 40) {
+        const int r = threadIdx.x & 7, c = threadIdx.x >> 3;
+        double o = 0.0;
+        if (live) {
+          for (int t = 0; t < n; ++t) {
+            const double* m = ACC(a, t);
+            if (m[91] == 0.0) continue;
+            const double* A1 = AdH(a, t);
+#pragma unroll
+            for (int x = 0; x < 8; ++x) o += A1[r + 8 * x] * (c < 4 ? acc13(m, 4 + x, c) : acc13(m, 4 + x, 12));
+          }
+          for (int h = 0; h < n; ++h) {
+            const double* m = ACC(h, a);
+            if (m[91] == 0.0) continue;
+            const double* A1 = AdT(h, a);
+#pragma unroll
+            for (int x = 0; x < 8; ++x) o += A1[r + 8 * x] * (c < 4 ? acc13(m, 4 + x, c) : acc13(m, 4 + x, 12));
+          }
+        }
+        if (c < 4) {
+          H[(size_t)(4 + 8 * a + r) + (size_t)N * c] = o;
+          H[(size_t)c + (size_t)N * (4 + 8 * a + r)] = o;
+        } else {
+          if (usePrior) o += S.framePrior[8 * a + r] * S.frameDeltaPrior[8 * a + r];
+          bv[4 + 8 * a + r] = o;
+        }
+      }
+    } else if (a == n && b == n) {
+      if (threadIdx.x < 20) {
+        const int r = threadIdx.x & 3, c = threadIdx.x >> 2;
+        double o = 0.0;
+        if (live)
+          for (int k = 0; k < nn; ++k) {
+            const double* m = acc + (size_t)k * TOP_PART;
+            if (m[91] == 0.0) continue;
+            o += (c < 4) ? acc13(m, r, c) : acc13(m, r, 12);
+          }
+        if (c < 4) {
+          if (usePrior && r == c) o += S.cPrior[r];
+          H[(size_t)r + (size_t)N * c] = o;
+        } else {
+          if (usePrior) o += S.cPrior[r] * (double)S.cDeltaF[r];
+          bv[r] = o;
+        }
+      } else if (threadIdx.x == 32) {
+        int tot = 0;
+        if (live)
+          for (int k = 0; k < nn; ++k) tot += (int)acc[(size_t)k * TOP_PART + 91];
+        S.nres[sys] = tot;   // resInA / resInL (EnergyFunctional.cpp:163,186)
+      }
+    }
+    return;
+  }
+
+  // ---- Schur complement system: H_sc = sum_i T_i G_i T_i^T with T_i[a,j] = d(a,i) AdH[i,j] + d(a,j) AdT[i,j]
+  auto Gh = [&](int i) { return S.G + (size_t)i * LD * LD; };
+  if (a < n && b < n) {
+    if (a == b) {   // sum_{j,k} AdH[a,j] D_a[j,k] AdH[a,k]^T   (AccumulatedSCHessian.cpp:108)
+      const double* G = Gh(a);
+      for (int j = 0; j < n; ++j)
+        for (int k = 0; k < n; ++k)
+          CONTRIB(AdH(a, j), AdH(a, k), [&](int x, int y) { return Gsym(G, LD, 8 * j + x, 8 * k + y); });
+    }
+    {   // :111  H[i,k] += AdH[ij] D AdT[ik]^T with i=a, k=b
+      const double* G = Gh(a);
+      for (int j = 0; j < n; ++j)
+        CONTRIB(AdH(a, j), AdT(a, b), [&](int x, int y) { return Gsym(G, LD, 8 * j + x, 8 * b + y); });
+    }
+    {   // :110  H[j,i] += AdT[ij] D AdH[ik]^T with j=a, i=b
+      const double* G = Gh(b);
+      for (int k = 0; k < n; ++k)
+        CONTRIB(AdT(b, a), AdH(b, k), [&](int x, int y) { return Gsym(G, LD, 8 * a + x, 8 * k + y); });
+    }
+    for (int i = 0; i < n; ++i) {   // :109  H[j,k] += AdT[ij] D AdT[ik]^T with j=a, k=b
+      const double* G = Gh(i);
+      CONTRIB(AdT(i, a), AdT(i, b), [&](int x, int y) { return Gsym(G, LD, 8 * a + x, 8 * b + y); });
+    }
+    const int r = lane & 7, c0 = lane >> 3;
+    part[warp][r + 8 * c0] = o0; part[warp][r + 8 * (c0 + 4)] = o1;
+    __syncthreads();
+    if (threadIdx.x < 64) {
+      const int rr = threadIdx.x & 7, cc = threadIdx.x >> 3;
+      double o = 0.0;
+#pragma unroll
+      for (int w = 0; w < ST_WARPS; ++w) o += part[w][threadIdx.x];
+      H[(size_t)(4 + 8 * a + rr) + (size_t)N * (4 + 8 * b + cc)] = o;
+    }
+  } else if (a < n && b == n) {
+    if (threadIdx.x < 40) {   // :86-89: H[i,0:4] += AdH[ij] E[ij], H[j,0:4] += AdT[ij] E[ij]; b likewise with EB
+      const int r = threadIdx.x & 7, c = threadIdx.x >> 3;
+      double o = 0.0;
+      const int col = 8 * n + c;   // Hcd columns 8n..8n+3, bdSum column 8n+4
+      {
+        const double* G = Gh(a);
+        for (int j = 0; j < n; ++j) {
+          const double* A1 = AdH(a, j);
+#pragma unroll
+          for (int x = 0; x < 8; ++x) o += A1[r + 8 * x] * Gsym(G, LD, 8 * j + x, col);
+        }
+      }
+      for (int i = 0; i < n; ++i) {
+        const double* G = Gh(i);
+        const double* A1 = AdT(i, a);
+#pragma unroll
+        for (int x = 0; x < 8; ++x) o += A1[r + 8 * x] * Gsym(G, LD, 8 * a + x, col);
+      }
+      if (c < 4) {
+        H[(size_t)(4 + 8 * a + r) + (size_t)N * c] = o;
+        H[(size_t)c + (size_t)N * (4 + 8 * a + r)] = o;   // .h:106-110
+      } else {
+        bv[4 + 8 * a + r] = o;
+      }
+    }
+  } else if (a == n && b == n) {
+    if (threadIdx.x < 20) {
+      const int r = threadIdx.x & 3, c = threadIdx.x >> 2;
+      double o = 0.0;
+      for (int i = 0; i < n; ++i) o += Gsym(Gh(i), LD, 8 * n + r, 8 * n + c);
+      if (c < 4) H[(size_t)r + (size_t)N * c] = o; else bv[r] = o;
+    }
+  }
+#undef CONTRIB
+}
+
+// EnergyFunctional::resubstituteFPt (EnergyFunctional.cpp:249-274); xAd[n*h+t] uploaded by the host
+__global__ void ba_resub_kernel(BAWin W, BARes r, BAPts pts, const float* __restrict__ xc, const float* __restrict__ xAd) {
+  int p = blockIdx.x * blockDim.x + threadIdx.x;
+  if (p >= pts.P) return;
+  const int s = r.rs, n = W.n;
+  int ngood = 0;
+  for (int i = pts.res_begin[p]; i < pts.res_begin[p + 1]; ++i) if (r.isActive[pts.res_index[i]]) ngood++;
+  if (ngood == 0) { pts.step[p] = 0.f; return; }
+  float b = pts.bdSumF[p];
+  float4 ha = pts.Hcd[0][p], hl = pts.Hcd[1][p];
+  float dot = 0.f;
+  dot = xadd(dot, xmul(xc[0], xadd(ha.x, hl.x))); dot = xadd(dot, xmul(xc[1], xadd(ha.y, hl.y)));
+  dot = xadd(dot, xmul(xc[2], xadd(ha.z, hl.z))); dot = xadd(dot, xmul(xc[3], xadd(ha.w, hl.w)));
+  b = xsub(b, dot);
+  for (int i = pts.res_begin[p]; i < pts.res_begin[p + 1]; ++i) {
+    int k = pts.res_index[i];
+    if (!r.isActive[k]) continue;
+    int pair = r.pair[k], h = pair % n, t = pair / n;
+    const float* xa = xAd + 8 * (n * h + t);
+    float d = 0.f;
+#pragma unroll
+    for (int j = 0; j < 8; ++j) d = xadd(d, xmul(xa[j], r.JpJdF[j * s + k]));
+    b = xsub(b, d);
+  }
+  pts.step[p] = xmul(-b, pts.HdiF[p]);
+}
+
+}  // namespace hs

@@ -310,6 +310,37 @@ __device__ void d_ldlt_solve(const double* Ain, const double* rhs, int n, double
 #undef AT
 }
 
+// Unpivoted LDL^T of the damped (SPD) system in shared memory; lanes 0..n-1 each own a row.
+// A is overwritten by L (strict lower) and D (diagonal); y holds rhs on entry and x on exit.
+__device__ __forceinline__ void warp_ldlt_solve(double (*A)[9], double* y, int n, int lane) {
+  for (int k = 0; k < n; ++k) {
+    double d = A[k][k];
+    double lik = 0.0;
+    const bool mine = lane > k && lane < n;
+    if (mine) lik = A[lane][k] / d;
+    __syncwarp();
+    if (mine) A[lane][k] = lik;
+    __syncwarp();
+    if (mine)
+      for (int j = k + 1; j <= lane; ++j) A[lane][j] -= lik * d * A[j][k];
+    __syncwarp();
+  }
+  for (int i = 0; i < n; ++i) {          // L z = rhs
+    double zi = y[i];
+    __syncwarp();
+    if (lane > i && lane < n) y[lane] -= A[lane][i] * zi;
+    __syncwarp();
+  }
+  if (lane < n) y[lane] = y[lane] / A[lane][lane];   // D
+  __syncwarp();
+  for (int i = n - 1; i >= 0; --i) {     // L^T x = z
+    double xi = y[i];
+    __syncwarp();
+    if (lane < i) y[lane] -= A[i][lane] * xi;
+    __syncwarp();
+  }
+}
+
 __device__ void d_matmul3(const double* A, const double* B, double* C) {
   double t[9];
   for (int i = 0; i < 3; ++i)
@@ -425,6 +456,8 @@ __global__ void __launch_bounds__(TRK_THREADS) trk_track_kernel(TrackArgs a, flo
   __shared__ LMState s;
   __shared__ int iters[5];
   __shared__ double lastRes[5];
+  __shared__ double sA[8][9];
+  __shared__ double sy[8];
 
   // Every block carries an identical copy of the LM state and takes identical decisions.
   if (threadIdx.x == 0) {
@@ -474,38 +507,36 @@ __global__ void __launch_bounds__(TRK_THREADS) trk_track_kernel(TrackArgs a, flo
 
     // --- LM iterations, CoarseTracker.cpp:559-646
     for (int iteration = 0; iteration < a.maxIterations[lvl]; iteration++) {
+      // 8x8 damped solve by the first warp: lanes 0..7 own one row each of a shared-memory LDLT
+      // (the serial thread-0 version spent ~10 us per iteration in local-memory traffic).
+      if (threadIdx.x < 32) {
+        const int lane = threadIdx.x;
+        const bool fixA = a.affineOptModeA < 0.f, fixB = a.affineOptModeB < 0.f;
+        int nsolve = 8;
+        if (fixA && fixB) nsolve = 6; else if (fixA != fixB) nsolve = 7;
+        if (lane < 8) {
+          const double damp = (double)(1.f + s.lambda);
+          for (int cc = 0; cc < 8; ++cc) {
+            int sr = lane, sc = cc;
+            if (fixA && !fixB) { if (sr == 6) sr = 7; if (sc == 6) sc = 7; }   // :575-587: row/col 6 := row/col 7
+            double v = s.H[sr + 8 * sc];
+            if (sr == sc) v *= damp;
+            sA[lane][cc] = v;
+          }
+          int sb = (fixA && !fixB && lane == 6) ? 7 : lane;
+          sy[lane] = -s.b[sb];
+        }
+        __syncwarp();
+        warp_ldlt_solve(sA, sy, nsolve, lane);
+      }
       if (threadIdx.x == 0) {
         iters[lvl]++;
-        double Hl[64], nb8[8], inc[8];
-        for (int i = 0; i < 64; ++i) Hl[i] = s.H[i];
-        for (int i = 0; i < 8; ++i) Hl[i + 8 * i] *= (double)(1.f + s.lambda);
-        for (int i = 0; i < 8; ++i) nb8[i] = -s.b[i];
-        bool fixA = a.affineOptModeA < 0.f, fixB = a.affineOptModeB < 0.f;
-        if (!fixA && !fixB) {
-          d_ldlt_solve(Hl, nb8, 8, inc);
-        } else if (fixA && fixB) {   // :565-569
-          double H6[36];
-          for (int cc = 0; cc < 6; ++cc) for (int r = 0; r < 6; ++r) H6[r + 6 * cc] = Hl[r + 8 * cc];
-          d_ldlt_solve(H6, nb8, 6, inc);
-          inc[6] = inc[7] = 0.0;
-        } else if (!fixA && fixB) {  // :570-574
-          double H7[49];
-          for (int cc = 0; cc < 7; ++cc) for (int r = 0; r < 7; ++r) H7[r + 7 * cc] = Hl[r + 8 * cc];
-          d_ldlt_solve(H7, nb8, 7, inc);
-          inc[7] = 0.0;
-        } else {                     // :575-587 fix a
-          double Hs[64], bs[8], H7[49], nb7[7], x7[7];
-          for (int i = 0; i < 64; ++i) Hs[i] = Hl[i];
-          for (int i = 0; i < 8; ++i) bs[i] = s.b[i];
-          for (int r = 0; r < 8; ++r) Hs[r + 8 * 6] = Hs[r + 8 * 7];
-          for (int cc = 0; cc < 8; ++cc) Hs[6 + 8 * cc] = Hs[7 + 8 * cc];
-          bs[6] = bs[7];
-          for (int cc = 0; cc < 7; ++cc) for (int r = 0; r < 7; ++r) H7[r + 7 * cc] = Hs[r + 8 * cc];
-          for (int i = 0; i < 7; ++i) nb7[i] = -bs[i];
-          d_ldlt_solve(H7, nb7, 7, x7);
-          for (int i = 0; i < 6; ++i) inc[i] = x7[i];
-          inc[6] = 0.0; inc[7] = x7[6];
-        }
+        double inc[8];
+        const bool fixA = a.affineOptModeA < 0.f, fixB = a.affineOptModeB < 0.f;
+        for (int i = 0; i < 8; ++i) inc[i] = sy[i];
+        if (fixA && fixB) { inc[6] = inc[7] = 0.0; }          // :565-569
+        else if (!fixA && fixB) { inc[7] = 0.0; }             // :570-574
+        else if (fixA && !fixB) { inc[7] = inc[6]; inc[6] = 0.0; }   // :583-586
         float extrapFac = 1.f;
         if (s.lambda < 0.001f) extrapFac = sqrtf(sqrtf(0.001f / s.lambda));
         double nrm = 0.0, sum = 0.0, incS[8];

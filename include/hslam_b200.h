@@ -295,6 +295,19 @@ int hslam_ba_accumulate_all_device(hslam_ba* ba, double** Hb_dev_out, int* count
 /* One fused GN-iteration pass: linearize(fixLinearization=0) + applyRes +
  * accumulate_all, enqueued back-to-back with no host round trip. */
 int hslam_ba_iteration_device(hslam_ba* ba, double** Hb_dev_out, int* count_out);
+/* Asynchronous use of a handle: between begin_async and wait every call only ENQUEUES its copies
+ * and kernels (host output buffers are filled, and must stay valid, until hslam_ba_wait returns).
+ * Without begin_async each call that returns data synchronises once before returning. */
+int hslam_ba_begin_async(hslam_ba* ba);
+int hslam_ba_wait(hslam_ba* ba);
+/* A batch of independent windows of one context (BASELINE.json configs[4]: "batched 64 independent
+ * synthetic windows"): one GN iteration (linearizeAll + applyRes + accumulateAF/LF/SCF) of EVERY
+ * window in FOUR launches; results stay in each window's device buffers (hslam_ba_download_Hb,
+ * hslam_ba_point_results ...).  Replaces running System::optimize's inner loop window by window. */
+typedef struct hslam_ba_batch hslam_ba_batch;
+int hslam_ba_batch_create(hslam_ctx* ctx, hslam_ba* const* windows, int count, hslam_ba_batch** out);
+int hslam_ba_batch_iteration(hslam_ba_batch* batch);
+int hslam_ba_batch_destroy(hslam_ba_batch* batch);
 /* Copy the device Hb block to the host (after an external all-reduce). */
 int hslam_ba_download_Hb(hslam_ba* ba, double* Hb_out_host);
 /* Sum the stitched [H|b] block across ranks with ONE ncclAllReduce(sum, fp64)
