@@ -10,7 +10,7 @@ import os
 import numpy as np
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libhslam_b200.so")
+LIB_PATH = os.environ.get("HSLAM_B200_LIB", os.path.join(_HERE, "libhslam_b200.so"))
 
 ACC_A, ACC_L, ACC_SC = 0, 1, 2
 RES_IN, RES_OOB, RES_OUT = 0, 1, 2

@@ -67,6 +67,7 @@ struct hslam_ba {
   DevBuf<float> d_scpartial;
   DevBuf<unsigned int> d_host_ticket;
   int n_ptchunks = 0;
+  int maxres = 1;
   DevBuf<double> d_accTop, d_G, d_Hb, d_epart, d_energy;
   DevBuf<int> d_nres;          // [2]
   DevBuf<unsigned int> d_ticket;
@@ -173,7 +174,7 @@ static void fill_desc(hslam_ba* ba) {
   D.topchunks = ba->d_topchunks.p; D.toppartial = ba->d_toppartial.p; D.pair_ticket = ba->d_pair_ticket.p;
   D.pair_chunk_begin = ba->d_pair_chunk_begin.p; D.accTop = ba->d_accTop.p;
   D.ptchunks = ba->d_ptchunks.p; D.scpartial = ba->d_scpartial.p; D.host_ticket = ba->d_host_ticket.p;
-  D.host_chunk_begin = ba->d_host_chunk_begin.p; D.G = ba->d_G.p; D.LD = ba->LD;
+  D.host_chunk_begin = ba->d_host_chunk_begin.p; D.G = ba->d_G.p; D.LD = ba->LD; D.maxres = ba->maxres;
   StitchArgs& S = D.S;
   S.n = ba->n; S.LD = ba->LD;
   S.adHost = ba->d_adH.p; S.adTarget = ba->d_adT.p; S.accTop = ba->d_accTop.p; S.G = ba->d_G.p; S.Hb = ba->d_Hb.p;
@@ -312,6 +313,9 @@ int hslam_ba_set_topology(hslam_ba* ba, const hslam_point_soa* pt, const hslam_r
   hslam_ctx* ctx = ba->ctx;
   HS_CUDA(cudaSetDevice(ctx->device));
   HS_ARG(P == 0 || pt->res_begin[P] == R, "hslam_ba_set_topology: CSR does not cover every residual exactly once");
+  ba->maxres = 1;
+  for (int p = 0; p < P; ++p) ba->maxres = std::max(ba->maxres, pt->res_begin[p + 1] - pt->res_begin[p]);
+  HS_ARG(ba->maxres <= HSLAM_MAX_FRAMES, "hslam_ba_set_topology: a point has more residuals than HSLAM_MAX_FRAMES");
   TRY(ba_flush(ba));
   // ---- points sorted by host (stable counting sort)
   std::vector<int> hostCount(n + 1, 0);
@@ -467,7 +471,7 @@ int hslam_ba_set_topology(hslam_ba* ba, const hslam_point_soa* pt, const hslam_r
     TRY(upload(ba, ba->d_ptchunks.p, ch.data(), ch.size())); TRY(upload(ba, ba->d_host_chunk_begin.p, hcb.data(), hcb.size()));
     HS_CUDA(cudaMemsetAsync(ba->d_G.p, 0, (size_t)n * ba->LD * ba->LD * sizeof(double), ctx->stream));
   }
-  TRY(ba->d_epart.ensure((size_t)(ba->rs / LIN_THREADS + 2)));
+  TRY(ba->d_epart.ensure((size_t)(ba->rs / 32 + 2 * LIN_THREADS / 32)));   // one energy partial per warp
   ba->have_topology = true;
   fill_desc(ba);
   TRY(ba_flush(ba));
@@ -519,12 +523,12 @@ static int launch_top(hslam_ba* ba, int modes) {
   int first = (modes & 1) ? 0 : ba->n_topchunks[0];
   int count = ((modes & 1) ? ba->n_topchunks[0] : 0) + ((modes & 2) ? ba->n_topchunks[1] : 0);
   if (count > 0)
-    HS_LAUNCH(ctx, HSLAM_K_BA_TOP, (ba_top_kernel<<<count, TOP_THREADS, 0, ctx->stream>>>(ba->d_desc.p, nullptr, 1, first)));
+    HS_LAUNCH(ctx, HSLAM_K_BA_TOP, (ba_top_kernel<<<count, 2 * TOP_THREADS, 0, ctx->stream>>>(ba->d_desc.p, nullptr, 1, first)));
   HS_CUDA(cudaGetLastError());
   return 0;
 }
 
-static size_t schur_smem(int LD) { return (size_t)(SC_PTS * LD + SC_PTS) * sizeof(float); }
+static size_t schur_smem(int LD, int maxres) { return (size_t)(SC_PTS * LD + SC_PTS + SC_PTS * maxres * 8) * sizeof(float); }
 static int schur_attr(size_t smem) {
   static size_t configured = 48 * 1024;
   if (smem > configured) {
@@ -537,10 +541,11 @@ static int schur_attr(size_t smem) {
 static int launch_schur(hslam_ba* ba) {
   hslam_ctx* ctx = ba->ctx;
   TRY(sync_desc(ba));
-  size_t smem = schur_smem(ba->LD);
+  size_t smem = schur_smem(ba->LD, ba->maxres);
   TRY(schur_attr(smem));
   if (ba->n_ptchunks > 0)
     HS_LAUNCH(ctx, HSLAM_K_BA_SCHUR, (ba_schur_kernel<<<ba->n_ptchunks, SC_THREADS, smem, ctx->stream>>>(ba->d_desc.p, nullptr, 1)));
+  HS_LAUNCH(ctx, HSLAM_K_BA_FOLD_SC, (ba_fold_sc_kernel<<<ba->n * ((ba->LD * ba->LD + 255) / 256), 256, 0, ctx->stream>>>(ba->d_desc.p, nullptr, 1)));
   HS_CUDA(cudaGetLastError());
   return 0;
 }
@@ -767,11 +772,11 @@ struct hslam_ba_batch {
   std::vector<hslam_ba*> items;
   std::vector<uint64_t> versions;
   DevBuf<BADesc> d_descs;
-  DevBuf<int> d_prefix;          // 4 tables of (count+1): linearize, top, schur, stitch
+  DevBuf<int> d_prefix;          // 5 tables of (count+1): linearize, top, schur, stitch, schur fold
   BADesc* h_descs = nullptr;     // pinned
   int* h_prefix = nullptr;       // pinned
   cudaEvent_t copied = nullptr;
-  int blocks[4] = {0, 0, 0, 0};
+  int blocks[5] = {0, 0, 0, 0, 0};
   size_t smem = 0;
 };
 
@@ -785,8 +790,8 @@ static int batch_refresh(hslam_ba_batch* B) {
   }
   if (!dirty) return 0;
   HS_CUDA(cudaEventSynchronize(B->copied));
-  int* pf[4];
-  for (int k = 0; k < 4; ++k) { pf[k] = B->h_prefix + k * (n + 1); pf[k][0] = 0; }
+  int* pf[5];
+  for (int k = 0; k < 5; ++k) { pf[k] = B->h_prefix + k * (n + 1); pf[k][0] = 0; }
   B->smem = 0;
   for (int i = 0; i < n; ++i) {
     hslam_ba* ba = B->items[i];
@@ -798,11 +803,12 @@ static int batch_refresh(hslam_ba_batch* B) {
     pf[1][i + 1] = pf[1][i] + top;
     pf[2][i + 1] = pf[2][i] + ba->n_ptchunks;
     pf[3][i + 1] = pf[3][i] + 3 * (ba->n + 1) * (ba->n + 1);
-    B->smem = std::max(B->smem, schur_smem(ba->LD));
+    pf[4][i + 1] = pf[4][i] + ba->n * ((ba->LD * ba->LD + 255) / 256);
+    B->smem = std::max(B->smem, schur_smem(ba->LD, ba->maxres));
   }
-  for (int k = 0; k < 4; ++k) B->blocks[k] = pf[k][n];
+  for (int k = 0; k < 5; ++k) B->blocks[k] = pf[k][n];
   HS_CUDA(cudaMemcpyAsync(B->d_descs.p, B->h_descs, n * sizeof(BADesc), cudaMemcpyHostToDevice, B->ctx->stream));
-  HS_CUDA(cudaMemcpyAsync(B->d_prefix.p, B->h_prefix, 4 * (n + 1) * sizeof(int), cudaMemcpyHostToDevice, B->ctx->stream));
+  HS_CUDA(cudaMemcpyAsync(B->d_prefix.p, B->h_prefix, 5 * (n + 1) * sizeof(int), cudaMemcpyHostToDevice, B->ctx->stream));
   HS_CUDA(cudaEventRecord(B->copied, B->ctx->stream));
   return 0;
 }
@@ -820,9 +826,9 @@ int hslam_ba_batch_create(hslam_ctx* ctx, hslam_ba* const* items, int count, hsl
   }
   B->versions.assign(count, 0);
   TRY(B->d_descs.ensure(count));
-  TRY(B->d_prefix.ensure(4 * (size_t)(count + 1)));
+  TRY(B->d_prefix.ensure(5 * (size_t)(count + 1)));
   HS_CUDA(cudaMallocHost((void**)&B->h_descs, count * sizeof(BADesc)));
-  HS_CUDA(cudaMallocHost((void**)&B->h_prefix, 4 * (size_t)(count + 1) * sizeof(int)));
+  HS_CUDA(cudaMallocHost((void**)&B->h_prefix, 5 * (size_t)(count + 1) * sizeof(int)));
   HS_CUDA(cudaEventCreateWithFlags(&B->copied, cudaEventDisableTiming));
   *out = B;
   return 0;
@@ -850,9 +856,10 @@ int hslam_ba_batch_iteration(hslam_ba_batch* B) {
   TRY(schur_attr(B->smem));
   HS_LAUNCH(ctx, HSLAM_K_BA_LINEARIZE, (ba_linearize_kernel<true><<<B->blocks[0], LIN_THREADS, 0, ctx->stream>>>(B->d_descs.p, pf, n)));
   if (B->blocks[1] > 0)
-    HS_LAUNCH(ctx, HSLAM_K_BA_TOP, (ba_top_kernel<<<B->blocks[1], TOP_THREADS, 0, ctx->stream>>>(B->d_descs.p, pf + (n + 1), n, 0)));
+    HS_LAUNCH(ctx, HSLAM_K_BA_TOP, (ba_top_kernel<<<B->blocks[1], 2 * TOP_THREADS, 0, ctx->stream>>>(B->d_descs.p, pf + (n + 1), n, 0)));
   if (B->blocks[2] > 0)
     HS_LAUNCH(ctx, HSLAM_K_BA_SCHUR, (ba_schur_kernel<<<B->blocks[2], SC_THREADS, B->smem, ctx->stream>>>(B->d_descs.p, pf + 2 * (n + 1), n)));
+  HS_LAUNCH(ctx, HSLAM_K_BA_FOLD_SC, (ba_fold_sc_kernel<<<B->blocks[4], 256, 0, ctx->stream>>>(B->d_descs.p, pf + 4 * (n + 1), n)));
   HS_LAUNCH(ctx, HSLAM_K_BA_STITCH, (ba_stitch_kernel<<<B->blocks[3], ST_THREADS, 0, ctx->stream>>>(B->d_descs.p, pf + 3 * (n + 1), n, 0, 3)));
   HS_CUDA(cudaGetLastError());
   return 0;

@@ -25,6 +25,9 @@ namespace hs {
 constexpr int JS = 80;                 // floats per residual row: 74 of RawResidualJacobian + JI_r(2) Jab_r(2) rr(1) + pad
 constexpr int J_RESF = 0, J_XI0 = 8, J_XI1 = 14, J_C0 = 20, J_C1 = 24, J_DD = 28, J_IDX0 = 30, J_IDX1 = 38,
               J_AB0 = 46, J_AB1 = 54, J_IDX2 = 62, J_ABIDX = 66, J_AB2 = 70, J_JIR = 74, J_JABR = 76, J_RR = 78;
+#ifndef LIN_MINB
+#define LIN_MINB 6   /* measured on B200: 3 -> 209 us, 4 -> 185, 5 -> 176, 6 -> 170, 8 -> 189 per 672k residuals */
+#endif
 constexpr int LIN_THREADS = 128;
 constexpr int TOP_THREADS = 128;
 constexpr int TOP_PART = 96;           // 91 accumulators + nres + pad
@@ -110,6 +113,7 @@ struct BADesc {
   const TopChunk* topchunks; float* toppartial; unsigned int* pair_ticket; const int* pair_chunk_begin; double* accTop;
   // schur
   const PtChunk* ptchunks; float* scpartial; unsigned int* host_ticket; const int* host_chunk_begin; double* G; int LD;
+  int maxres;                // longest residual list of a point (<= HSLAM_MAX_FRAMES)
   // stitch
   StitchArgs S;
 };
@@ -154,7 +158,7 @@ __device__ __forceinline__ void apply_one(const BARes& r, int k) {  // Optimizat
 }
 
 template <bool APPLY>
-__global__ void __launch_bounds__(LIN_THREADS) ba_linearize_kernel(const BADesc* __restrict__ descs,
+__global__ void __launch_bounds__(LIN_THREADS, LIN_MINB) ba_linearize_kernel(const BADesc* __restrict__ descs,
                                                                    const int* __restrict__ prefix, int nwin) {
   int lb;
   const int win = find_window(prefix, nwin, blockIdx.x, lb);
@@ -184,6 +188,10 @@ __global__ void __launch_bounds__(LIN_THREADS) ba_linearize_kernel(const BADesc*
       const float t0[3] = {q5.y, q5.z, q5.w};
       const float affLL0 = q6.x, affLL1 = q6.y, b0 = q6.z;
       const float4 pu = __ldg(D.p.uvid + p);
+      // host colours / weights are needed only after the gather, but their addresses are known now:
+      // issue them with the point record so their latency overlaps the projections
+      const float4 c0 = __ldg(D.p.color + 2 * p), c1 = __ldg(D.p.color + 2 * p + 1);
+      const float4 w0 = __ldg(D.p.weights + 2 * p), w1 = __ldg(D.p.weights + 2 * p + 1);
       const float u_pt = pu.x, v_pt = pu.y, idp = pu.z, idz = pu.w;
       const float wm3 = (float)(W.w - 3), hm3 = (float)(W.h - 3);
       // ---- centre projection at the FEJ point, DirectProjection.h:20-38
@@ -254,8 +262,6 @@ __global__ void __launch_bounds__(LIN_THREADS) ba_linearize_kernel(const BADesc*
           Hit3 hit[8];
 #pragma unroll
           for (int idx = 0; idx < 8; ++idx) hit[idx] = interp33(img, Kup[idx], Kvp[idx], W.w);
-          const float4 c0 = __ldg(D.p.color + 2 * p), c1 = __ldg(D.p.color + 2 * p + 1);
-          const float4 w0 = __ldg(D.p.weights + 2 * p), w1 = __ldg(D.p.weights + 2 * p + 1);
           const float color[8] = {c0.x, c0.y, c0.z, c0.w, c1.x, c1.y, c1.z, c1.w};
           const float wgt[8] = {w0.x, w0.y, w0.z, w0.w, w1.x, w1.y, w1.z, w1.w};
           float II00 = 0.f, II11 = 0.f, II10 = 0.f, AI00 = 0.f, AI01 = 0.f, AI10 = 0.f, AI11 = 0.f;
@@ -322,24 +328,26 @@ __global__ void __launch_bounds__(LIN_THREADS) ba_linearize_kernel(const BADesc*
     }
     if (APPLY) apply_one(r, k);
   }
-  // ---- energy: block tree in fp64, per-block partial, last block of the window folds in block order
-  __shared__ double wsumd[LIN_THREADS / 32];
-  __shared__ bool last;
+  // ---- energy: warp tree in fp64, one partial per WARP (no block barrier: a warp retires as soon as
+  // its residuals are done), the last warp of the window folds the partials in index order.
+  constexpr int WPB = LIN_THREADS / 32;
+  const int lane = threadIdx.x & 31;
+  const int nwarps = nblocks * WPB;
   double e = warp_sum(energy_ret);
-  if ((threadIdx.x & 31) == 0) wsumd[threadIdx.x >> 5] = e;
-  __syncthreads();
-  if (threadIdx.x == 0) {
-    D.epart[lb] = (wsumd[0] + wsumd[1]) + (wsumd[2] + wsumd[3]);
+  unsigned int tk = 0;
+  if (lane == 0) {
+    D.epart[lb * WPB + (threadIdx.x >> 5)] = e;
     __threadfence();
-    last = (atomicAdd(D.ticket, 1u) == (unsigned)nblocks - 1);
+    tk = atomicAdd(D.ticket, 1u);
   }
-  __syncthreads();
-  if (last && threadIdx.x < 32) {
+  tk = __shfl_sync(0xffffffffu, tk, 0);
+  if (tk == (unsigned)nwarps - 1) {
     __threadfence();
     double acc = 0.0;
-    for (int b = threadIdx.x; b < nblocks; b += 32) acc += __ldcg(D.epart + b);
+#pragma unroll 8
+    for (int b = lane; b < nwarps; b += 32) acc += __ldcg(D.epart + b);
     acc = warp_sum(acc);
-    if (threadIdx.x == 0) { *D.energy = acc; *D.ticket = 0; }
+    if (lane == 0) { *D.energy = acc; *D.ticket = 0; }
   }
 }
 
@@ -384,8 +392,11 @@ __global__ void ba_fixlin_kernel(BAWin W, BARes r, BAPts pts, const int* __restr
 // = 6), then warp shuffles -> shared memory -> fixed-order cross-warp sum -> per-chunk partial.  The
 // last block of a (mode,pair) to finish folds that pair's chunks in chunk order into fp64.
 // ------------------------------------------------------------------------------------------------
-template <int MODE>
-__device__ __forceinline__ void top_accumulate(const BADesc& D, const TopChunk& ch, float (&acc)[91], int& nres) {
+// PART 0 threads own the 55 entries of the 10x10 block, PART 1 threads the other 36 (+ nres and the
+// per-residual point terms): half the accumulator registers per thread, twice the warps in flight.
+// Loads that only feed the other part's entries are dead code in each instantiation.
+template <int MODE, int PART>
+__device__ __forceinline__ void top_accumulate(const BADesc& D, const TopChunk& ch, float (&acc)[55], int& nres) {
   const BAWin& W = D.W;
   const BARes& r = D.r;
   const int s = r.rs;
@@ -394,7 +405,7 @@ __device__ __forceinline__ void top_accumulate(const BADesc& D, const TopChunk& 
 #pragma unroll
     for (int j = 0; j < 8; ++j) dp[j] = __ldg(W.adHTdeltaF + 8 * ch.pair + j);
   }
-  for (int k = ch.start + threadIdx.x; k < ch.start + ch.count; k += TOP_THREADS) {
+  for (int k = ch.start + (threadIdx.x & (TOP_THREADS - 1)); k < ch.start + ch.count; k += TOP_THREADS) {
     bool lin = r.isLin[k] != 0, act = r.isActive[k] != 0;
     if (MODE == 0 ? (lin || !act) : (!lin || !act)) continue;
     const float* J = r.J + k;
@@ -433,59 +444,71 @@ __device__ __forceinline__ void top_accumulate(const BADesc& D, const TopChunk& 
         rr = xadd(rr, xmul(rz, rz));
       }
     }
-    // 10x10 upper triangle: [x y] [[a b],[b c]] [x y]^T
-    int idx = 0;
+    if (PART == 0) {
+      // 10x10 upper triangle: [x y] [[a b],[b c]] [x y]^T
+      int idx = 0;
 #pragma unroll
-    for (int rI = 0; rI < 10; ++rI) {
-      float px = fmaf(a, x[rI], b * y[rI]), py = fmaf(b, x[rI], c * y[rI]);
+      for (int rI = 0; rI < 10; ++rI) {
+        float px = fmaf(a, x[rI], b * y[rI]), py = fmaf(b, x[rI], c * y[rI]);
 #pragma unroll
-      for (int cI = rI; cI < 10; ++cI, ++idx) acc[idx] += fmaf(x[cI], px, y[cI] * py);
+        for (int cI = rI; cI < 10; ++cI, ++idx) acc[idx] += fmaf(x[cI], px, y[cI] * py);
+      }
+    } else {
+      // 10x3 top-right: columns a, b, r  (MatrixAccumulators.h:859-901); entries 55..84 -> acc[0..29]
+#pragma unroll
+      for (int rI = 0; rI < 10; ++rI) {
+        acc[3 * rI + 0] += fmaf(x[rI], AI00, y[rI] * AI01);
+        acc[3 * rI + 1] += fmaf(x[rI], AI10, y[rI] * AI11);
+        acc[3 * rI + 2] += fmaf(x[rI], JIr0, y[rI] * JIr1);
+      }
+      acc[30] += AA00; acc[31] += AA01; acc[32] += Jabr0; acc[33] += AA11; acc[34] += Jabr1; acc[35] += rr;
+      nres++;
+      // per-residual contribution to the point sums (:114-117), exact ops: they are summed per point in
+      // the point's own order by the Schur kernel, which keeps Hdd/bd/Hcd bit-identical to the oracle.
+      float Ji0 = xadd(xmul(a, d0), xmul(b, d1)), Ji1 = xadd(xmul(b, d0), xmul(c, d1));
+      float* o = r.ptc[MODE] + k;
+      o[0] = xadd(xmul(JIr0, d0), xmul(JIr1, d1));
+      o[s] = xadd(xmul(Ji0, d0), xmul(Ji1, d1));
+#pragma unroll
+      for (int j = 0; j < 4; ++j) o[(2 + j) * s] = xadd(xmul(x[j], Ji0), xmul(y[j], Ji1));
     }
-    // 10x3 top-right: columns a, b, r  (MatrixAccumulators.h:859-901)
-#pragma unroll
-    for (int rI = 0; rI < 10; ++rI) {
-      acc[55 + 3 * rI + 0] += fmaf(x[rI], AI00, y[rI] * AI01);
-      acc[55 + 3 * rI + 1] += fmaf(x[rI], AI10, y[rI] * AI11);
-      acc[55 + 3 * rI + 2] += fmaf(x[rI], JIr0, y[rI] * JIr1);
-    }
-    acc[85] += AA00; acc[86] += AA01; acc[87] += Jabr0; acc[88] += AA11; acc[89] += Jabr1; acc[90] += rr;
-    nres++;
-    // per-residual contribution to the point sums (:114-117), exact ops: they are summed per point in
-    // the point's own order by the Schur kernel, which keeps Hdd/bd/Hcd bit-identical to the oracle.
-    float Ji0 = xadd(xmul(a, d0), xmul(b, d1)), Ji1 = xadd(xmul(b, d0), xmul(c, d1));
-    float* o = r.ptc[MODE] + k;
-    o[0] = xadd(xmul(JIr0, d0), xmul(JIr1, d1));
-    o[s] = xadd(xmul(Ji0, d0), xmul(Ji1, d1));
-#pragma unroll
-    for (int j = 0; j < 4; ++j) o[(2 + j) * s] = xadd(xmul(x[j], Ji0), xmul(y[j], Ji1));
   }
 }
 
-__global__ void __launch_bounds__(TOP_THREADS) ba_top_kernel(const BADesc* __restrict__ descs,
-                                                             const int* __restrict__ prefix, int nwin,
-                                                             int lb_offset) {
+__global__ void __launch_bounds__(2 * TOP_THREADS, 2) ba_top_kernel(const BADesc* __restrict__ descs,
+                                                                    const int* __restrict__ prefix, int nwin,
+                                                                    int lb_offset) {
   int lb;
   const int win = find_window(prefix, nwin, blockIdx.x, lb);
   lb += lb_offset;   // single-window launches of mode L only start at the first mode-1 chunk
   const BADesc& D = descs[win];
   const TopChunk ch = D.topchunks[lb];
-  float acc[91];
+  const int part = threadIdx.x / TOP_THREADS;   // warp-uniform
+  float acc[55];
 #pragma unroll
-  for (int i = 0; i < 91; ++i) acc[i] = 0.f;
+  for (int i = 0; i < 55; ++i) acc[i] = 0.f;
   int nres = 0;
-  if (ch.mode == 0) top_accumulate<0>(D, ch, acc, nres);
-  else top_accumulate<1>(D, ch, acc, nres);
+  if (ch.mode == 0) { if (part == 0) top_accumulate<0, 0>(D, ch, acc, nres); else top_accumulate<0, 1>(D, ch, acc, nres); }
+  else              { if (part == 0) top_accumulate<1, 0>(D, ch, acc, nres); else top_accumulate<1, 1>(D, ch, acc, nres); }
 
   __shared__ float red[TOP_THREADS / 32][TOP_PART];
   __shared__ bool last;
-  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31, wid = (threadIdx.x >> 5) & (TOP_THREADS / 32 - 1);
+  if (part == 0) {
 #pragma unroll
-  for (int i = 0; i < 91; ++i) {
-    float v = warp_sum(acc[i]);
-    if (lane == 0) red[wid][i] = v;
+    for (int i = 0; i < 55; ++i) {
+      float v = warp_sum(acc[i]);
+      if (lane == 0) red[wid][i] = v;
+    }
+  } else {
+#pragma unroll
+    for (int i = 0; i < 36; ++i) {
+      float v = warp_sum(acc[i]);
+      if (lane == 0) red[wid][55 + i] = v;
+    }
+    int q = warp_sum(nres);
+    if (lane == 0) red[wid][91] = __int_as_float(q);
   }
-  int q = warp_sum(nres);
-  if (lane == 0) red[wid][91] = __int_as_float(q);
   __syncthreads();
   float* out = D.toppartial + (size_t)lb * TOP_PART;
   if (threadIdx.x < 92) {
@@ -582,7 +605,9 @@ __global__ void __launch_bounds__(SC_THREADS) ba_schur_kernel(const BADesc* __re
   const int LD = D.LD;
   float* A = smem;                       // [SC_PTS][LD]
   float* wv = smem + SC_PTS * LD;        // [SC_PTS] HdiF
-  __shared__ bool last;
+  float* stg = wv + SC_PTS;              // [SC_PTS][maxres][8]: 6 point terms + mode flag per residual slot
+  const int maxres = D.maxres;
+  __shared__ int cntS[SC_PTS];
   const PtChunk ch = D.ptchunks[lb];
   const int s = r.rs, n = D.W.n;
   const int NT = LD / 4, ntiles = NT * (NT + 1) / 2;
@@ -601,65 +626,76 @@ __global__ void __launch_bounds__(SC_THREADS) ba_schur_kernel(const BADesc* __re
     const int cnt = min(SC_PTS, ch.count - base);
     for (int i = threadIdx.x; i < SC_PTS * LD; i += SC_THREADS) A[i] = 0.f;
     __syncthreads();
-    // phase 1: 4 lanes per point.  Lane 0 forms the point's Hdd/bd/Hcd sums sequentially (the order of
-    // addPoint<mode>), all 4 lanes copy the JpJdF rows of the point's active residuals.
-    {
-      const int lp = threadIdx.x >> 2, q = threadIdx.x & 3;
-      int ngood = 0;
-      const int p = ch.start + base + lp;
-      float bdv[2] = {0.f, 0.f}, Hddv[2] = {0.f, 0.f};
-      float Hcdv[2][4] = {{0.f, 0.f, 0.f, 0.f}, {0.f, 0.f, 0.f, 0.f}};
+    // phase 1a: one thread per (point, residual slot): every load of the staging step is independent
+    // of the others, so the whole sub-tile costs a few memory round trips instead of one per residual.
+    for (int it = threadIdx.x; it < SC_PTS * maxres; it += SC_THREADS) {
+      const int lp = it / maxres, slot = it - lp * maxres;
+      float* st = stg + (size_t)it * 8;
+      float flag = 0.f;
       if (lp < cnt) {
+        const int p = ch.start + base + lp;
         const int rb = pts.res_begin[p], re = pts.res_begin[p + 1];
-        for (int i = rb + q; i < re; i += 4) {
-          int k = pts.res_index[i];
-          if (!r.isActive[k]) continue;
-          ngood++;
-          int t = r.pair[k] / n;
-          float* dst = A + lp * LD + 8 * t;
+        if (slot == 0) cntS[lp] = re - rb;
+        if (rb + slot < re) {
+          const int k = pts.res_index[rb + slot];
+          if (r.isActive[k]) {
+            const int m = r.isLin[k] ? 1 : 0;
+            const int t = r.pair[k] / n;
+            float* dst = A + lp * LD + 8 * t;
 #pragma unroll
-          for (int j = 0; j < 8; ++j) dst[j] = r.JpJdF[j * s + k];
-        }
-        if (q == 0) {
-          for (int i = rb; i < re; ++i) {   // AccumulatedTopHessian.cpp:35-120, residual order of the point
-            int k = pts.res_index[i];
-            if (!r.isActive[k]) continue;
-            int m = r.isLin[k] ? 1 : 0;
+            for (int j = 0; j < 8; ++j) dst[j] = r.JpJdF[j * s + k];
             const float* o = r.ptc[m] + k;
-            bdv[m] = xadd(bdv[m], o[0]);
-            Hddv[m] = xadd(Hddv[m], o[s]);
 #pragma unroll
-            for (int j = 0; j < 4; ++j) Hcdv[m][j] = xadd(Hcdv[m][j], o[(2 + j) * s]);
+            for (int j = 0; j < 6; ++j) st[j] = o[j * s];
+            flag = (float)(m + 1);
           }
         }
       }
-      ngood += __shfl_xor_sync(0xffffffffu, ngood, 1);   // all 32 lanes take part
-      ngood += __shfl_xor_sync(0xffffffffu, ngood, 2);
+      st[6] = flag;
+    }
+    __syncthreads();
+    // phase 1b: one thread per point forms Hdd/bd/Hcd sequentially in the point's residual order
+    // (AccumulatedTopHessian.cpp:35-139), then the Schur scalars (AccumulatedSCHessian.cpp:12-33).
+    if (threadIdx.x < SC_PTS) {
+      const int lp = threadIdx.x;
       if (lp < cnt) {
-        if (q == 0) {
-          for (int m = 0; m < 2; ++m) {   // :122-139
-            pts.Hdd[m][p] = Hddv[m]; pts.bd[m][p] = bdv[m];
-            pts.Hcd[m][p] = make_float4(Hcdv[m][0], Hcdv[m][1], Hcdv[m][2], Hcdv[m][3]);
-          }
-          // AccumulatedSCHessian.cpp:12-33
-          float hdi = 0.f, bds = 0.f, idh = 0.f;
-          float4 hcd = make_float4(0.f, 0.f, 0.f, 0.f);
-          if (ngood > 0) {
-            float H = xadd(xadd(Hddv[0], Hddv[1]), pts.priorF[p]);
-            if (H < 1e-10f) H = 1e-10f;
-            idh = H;
-            hdi = xdiv(1.0f, H);
-            bds = xadd(bdv[0], bdv[1]);
-            bds = xadd(bds, xmul(pts.priorF[p], pts.deltaF[p]));  // shiftPriorToZero = true (EnergyFunctional.cpp:209)
-            hcd = make_float4(xadd(Hcdv[0][0], Hcdv[1][0]), xadd(Hcdv[0][1], Hcdv[1][1]), xadd(Hcdv[0][2], Hcdv[1][2]),
-                              xadd(Hcdv[0][3], Hcdv[1][3]));
-          }
-          pts.HdiF[p] = hdi; pts.bdSumF[p] = bds; pts.idepth_hessian[p] = idh;
-          float* dst = A + lp * LD + 8 * n;
-          dst[0] = hcd.x; dst[1] = hcd.y; dst[2] = hcd.z; dst[3] = hcd.w; dst[4] = bds;
-          wv[lp] = hdi;
+        const int p = ch.start + base + lp;
+        float bdv[2] = {0.f, 0.f}, Hddv[2] = {0.f, 0.f};
+        float Hcdv[2][4] = {{0.f, 0.f, 0.f, 0.f}, {0.f, 0.f, 0.f, 0.f}};
+        int ngood = 0;
+        const int nr = min(cntS[lp], maxres);
+        for (int slot = 0; slot < nr; ++slot) {
+          const float* st = stg + ((size_t)lp * maxres + slot) * 8;
+          const int f = (int)st[6];
+          if (f == 0) continue;
+          const int m = f - 1;
+          ngood++;
+          bdv[m] = xadd(bdv[m], st[0]);
+          Hddv[m] = xadd(Hddv[m], st[1]);
+#pragma unroll
+          for (int j = 0; j < 4; ++j) Hcdv[m][j] = xadd(Hcdv[m][j], st[2 + j]);
         }
-      } else if (lp < SC_PTS && q == 0) {
+        for (int m = 0; m < 2; ++m) {
+          pts.Hdd[m][p] = Hddv[m]; pts.bd[m][p] = bdv[m];
+          pts.Hcd[m][p] = make_float4(Hcdv[m][0], Hcdv[m][1], Hcdv[m][2], Hcdv[m][3]);
+        }
+        float hdi = 0.f, bds = 0.f, idh = 0.f;
+        float4 hcd = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (ngood > 0) {
+          float H = xadd(xadd(Hddv[0], Hddv[1]), pts.priorF[p]);
+          if (H < 1e-10f) H = 1e-10f;
+          idh = H;
+          hdi = xdiv(1.0f, H);
+          bds = xadd(bdv[0], bdv[1]);
+          bds = xadd(bds, xmul(pts.priorF[p], pts.deltaF[p]));  // shiftPriorToZero = true (EnergyFunctional.cpp:209)
+          hcd = make_float4(xadd(Hcdv[0][0], Hcdv[1][0]), xadd(Hcdv[0][1], Hcdv[1][1]), xadd(Hcdv[0][2], Hcdv[1][2]),
+                            xadd(Hcdv[0][3], Hcdv[1][3]));
+        }
+        pts.HdiF[p] = hdi; pts.bdSumF[p] = bds; pts.idepth_hessian[p] = idh;
+        float* dst = A + lp * LD + 8 * n;
+        dst[0] = hcd.x; dst[1] = hcd.y; dst[2] = hcd.z; dst[3] = hcd.w; dst[4] = bds;
+        wv[lp] = hdi;
+      } else {
         wv[lp] = 0.f;
       }
     }
@@ -695,24 +731,38 @@ __global__ void __launch_bounds__(SC_THREADS) ba_schur_kernel(const BADesc* __re
             make_float4(acc[j][4 * ii], acc[j][4 * ii + 1], acc[j][4 * ii + 2], acc[j][4 * ii + 3]);
     }
   }
-  __threadfence();
-  __syncthreads();
-  // ---- per-host fold by the last block of that host, chunks in index order
-  const int cb = D.host_chunk_begin[ch.host], ce = D.host_chunk_begin[ch.host + 1];
-  if (threadIdx.x == 0) last = (atomicAdd(D.host_ticket + ch.host, 1u) == (unsigned)(ce - cb) - 1);
-  __syncthreads();
-  if (last) {
-    __threadfence();
-    double* G = D.G + (size_t)ch.host * LD * LD;
-    for (int i = threadIdx.x; i < LD * LD; i += SC_THREADS) {
-      int row = i / LD, col = i % LD;
-      if ((col >> 2) < (row >> 2)) continue;   // lower tiles are not produced
-      double sum = 0.0;
-      for (int c = cb; c < ce; ++c) sum += (double)__ldcg(D.scpartial + (size_t)c * LD * LD + i);
-      G[i] = sum;
-    }
-    if (threadIdx.x == 0) D.host_ticket[ch.host] = 0;
+}
+
+// Fold of the Schur chunk partials into fp64 G[host], chunks in index order.  A separate, wide launch:
+// folding inside the Schur kernel by "the last block of a host" put ~0.5 MB of dependent reads per host
+// on ONE block at the very end of the kernel (measured: 165 us of a 190 us launch for 8 windows).
+// grid: per window n * ceil(LD*LD / 256) blocks.
+__global__ void __launch_bounds__(256) ba_fold_sc_kernel(const BADesc* __restrict__ descs,
+                                                         const int* __restrict__ prefix, int nwin) {
+  int lb;
+  const int win = find_window(prefix, nwin, blockIdx.x, lb);
+  const BADesc& D = descs[win];
+  const int LD = D.LD, per = (LD * LD + 255) / 256;
+  const int host = lb / per;
+  const int i = (lb % per) * 256 + threadIdx.x;
+  if (i >= LD * LD) return;
+  const int row = i / LD, col = i % LD;
+  if ((col >> 2) < (row >> 2)) return;   // lower tiles are not produced
+  const int cb = D.host_chunk_begin[host], ce = D.host_chunk_begin[host + 1];
+  const float* src = D.scpartial + (size_t)cb * LD * LD + i;
+  const size_t stride = (size_t)LD * LD;
+  double sum = 0.0;
+  int c = cb;
+  for (; c + 8 <= ce; c += 8) {   // 8 independent loads in flight, summed in chunk order
+    float v[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) v[j] = __ldcg(src + (size_t)j * stride);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) sum += (double)v[j];
+    src += 8 * stride;
   }
+  for (; c < ce; ++c) { sum += (double)__ldcg(src); src += stride; }
+  D.G[(size_t)host * LD * LD + i] = sum;
 }
 
 // ------------------------------------------------------------------------------------------------
