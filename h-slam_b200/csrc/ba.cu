@@ -171,6 +171,7 @@ static void fill_desc(hslam_ba* ba) {
   p.step = ba->d_step.p;
   D.W.precalc = ba->d_precalc.p; D.W.adHTdeltaF = ba->d_adHTd.p;
   D.epart = ba->d_epart.p; D.ticket = ba->d_ticket.p; D.energy = ba->d_energy.p;
+  D.lin_warps = std::max(1, (ba->R + LIN_THREADS - 1) / LIN_THREADS) * (LIN_THREADS / 32);
   D.topchunks = ba->d_topchunks.p; D.toppartial = ba->d_toppartial.p; D.pair_ticket = ba->d_pair_ticket.p;
   D.pair_chunk_begin = ba->d_pair_chunk_begin.p; D.accTop = ba->d_accTop.p;
   D.ptchunks = ba->d_ptchunks.p; D.scpartial = ba->d_scpartial.p; D.host_ticket = ba->d_host_ticket.p;
@@ -550,11 +551,11 @@ static int launch_schur(hslam_ba* ba) {
   return 0;
 }
 
-static int launch_stitch(hslam_ba* ba, int sys_begin, int sys_end) {
+static int launch_stitch(hslam_ba* ba, int sys_begin, int sys_end, int with_energy = 0) {
   hslam_ctx* ctx = ba->ctx;
   TRY(sync_desc(ba));
   int blocks = 3 * (ba->n + 1) * (ba->n + 1);
-  HS_LAUNCH(ctx, HSLAM_K_BA_STITCH, (ba_stitch_kernel<<<blocks, ST_THREADS, 0, ctx->stream>>>(ba->d_desc.p, nullptr, 1, sys_begin, sys_end)));
+  HS_LAUNCH(ctx, HSLAM_K_BA_STITCH, (ba_stitch_kernel<<<blocks, ST_THREADS, 0, ctx->stream>>>(ba->d_desc.p, nullptr, 1, sys_begin, sys_end, with_energy)));
   HS_CUDA(cudaGetLastError());
   return 0;
 }
@@ -579,11 +580,11 @@ static int queue_Hb(hslam_ba* ba, int sys, double* H, double* b) {
   });
 }
 
-static int enqueue_accumulate_all(hslam_ba* ba) {
+static int enqueue_accumulate_all(hslam_ba* ba, int with_energy = 0) {
   const int modes = 1 | (ba->n_linearized != 0 ? 2 : 0);
   TRY(launch_top(ba, modes));
   TRY(launch_schur(ba));
-  TRY(launch_stitch(ba, 0, 3));
+  TRY(launch_stitch(ba, 0, 3, with_energy));
   return 0;
 }
 
@@ -594,6 +595,10 @@ int hslam_ba_linearize(hslam_ba* ba, int fixLinearization, double* energy_sum, i
   HS_ARG(ba && ba->have_topology && ba->have_window, "hslam_ba_linearize: window/topology not set");
   HS_CUDA(cudaSetDevice(ba->ctx->device));
   TRY(launch_linearize(ba, fixLinearization != 0));
+  if (energy_sum) {
+    HS_LAUNCH(ba->ctx, HSLAM_K_BA_ENERGY, (ba_energy_kernel<<<1, 256, 0, ba->ctx->stream>>>(ba->d_desc.p)));
+    HS_CUDA(cudaGetLastError());
+  }
   TRY(download(ba, energy_sum, ba->d_energy.p, 1));
   TRY(download_res(ba, ba->d_newState.p, 1, newState));
   TRY(download_res(ba, ba->d_newEnergy.p, 1, newEnergy));
@@ -665,7 +670,10 @@ int hslam_ba_iteration_device(hslam_ba* ba, double** Hb_dev_out, int* count_out)
   HS_ARG(ba && ba->have_topology && ba->have_window, "hslam_ba_iteration: window/topology not set");
   HS_CUDA(cudaSetDevice(ba->ctx->device));
   TRY(launch_linearize(ba, true));
-  return hslam_ba_accumulate_all_device(ba, Hb_dev_out, count_out);
+  TRY(enqueue_accumulate_all(ba, 1));   // the stitch also sums the energy partials of the linearise pass
+  if (Hb_dev_out) *Hb_dev_out = ba->d_Hb.p;
+  if (count_out) *count_out = 3 * (ba->N * ba->N + ba->N);
+  return 0;
 }
 
 int hslam_ba_download_Hb(hslam_ba* ba, double* out) {
@@ -860,7 +868,7 @@ int hslam_ba_batch_iteration(hslam_ba_batch* B) {
   if (B->blocks[2] > 0)
     HS_LAUNCH(ctx, HSLAM_K_BA_SCHUR, (ba_schur_kernel<<<B->blocks[2], SC_THREADS, B->smem, ctx->stream>>>(B->d_descs.p, pf + 2 * (n + 1), n)));
   HS_LAUNCH(ctx, HSLAM_K_BA_FOLD_SC, (ba_fold_sc_kernel<<<B->blocks[4], 256, 0, ctx->stream>>>(B->d_descs.p, pf + 4 * (n + 1), n)));
-  HS_LAUNCH(ctx, HSLAM_K_BA_STITCH, (ba_stitch_kernel<<<B->blocks[3], ST_THREADS, 0, ctx->stream>>>(B->d_descs.p, pf + 3 * (n + 1), n, 0, 3)));
+  HS_LAUNCH(ctx, HSLAM_K_BA_STITCH, (ba_stitch_kernel<<<B->blocks[3], ST_THREADS, 0, ctx->stream>>>(B->d_descs.p, pf + 3 * (n + 1), n, 0, 3, 1)));
   HS_CUDA(cudaGetLastError());
   return 0;
 }

@@ -108,7 +108,7 @@ struct BADesc {
   BARes r;
   BAPts p;
   // linearise
-  double* epart; unsigned int* ticket; double* energy;
+  double* epart; unsigned int* ticket; double* energy; int lin_warps;   // lin_warps = 4 * linearise blocks
   // top
   const TopChunk* topchunks; float* toppartial; unsigned int* pair_ticket; const int* pair_chunk_begin; double* accTop;
   // schur
@@ -165,7 +165,6 @@ __global__ void __launch_bounds__(LIN_THREADS, LIN_MINB) ba_linearize_kernel(con
   const BADesc& D = descs[win];
   const BAWin& W = D.W;
   const BARes& r = D.r;
-  const int nblocks = (nwin == 1) ? gridDim.x : (prefix[win + 1] - prefix[win]);
   const int k = lb * LIN_THREADS + threadIdx.x;
   const int s = r.rs;
   double energy_ret = 0.0;
@@ -328,27 +327,34 @@ __global__ void __launch_bounds__(LIN_THREADS, LIN_MINB) ba_linearize_kernel(con
     }
     if (APPLY) apply_one(r, k);
   }
-  // ---- energy: warp tree in fp64, one partial per WARP (no block barrier: a warp retires as soon as
-  // its residuals are done), the last warp of the window folds the partials in index order.
-  constexpr int WPB = LIN_THREADS / 32;
-  const int lane = threadIdx.x & 31;
-  const int nwarps = nblocks * WPB;
-  double e = warp_sum(energy_ret);
-  unsigned int tk = 0;
-  if (lane == 0) {
-    D.epart[lb * WPB + (threadIdx.x >> 5)] = e;
-    __threadfence();
-    tk = atomicAdd(D.ticket, 1u);
+  // ---- energy: warp tree in fp64, one partial per WARP, no fence and no block barrier: a warp retires
+  // as soon as its residuals are done (a __threadfence here made every warp wait for its ~100 Jacobian
+  // stores to drain: ~20 % of the kernel).  The partials are summed in index order by the next kernel
+  // of the stream (ba_energy_kernel, or the stitch kernel in the fused/batched path).
+  const double e = warp_sum(energy_ret);
+  if ((threadIdx.x & 31) == 0) D.epart[lb * (LIN_THREADS / 32) + (threadIdx.x >> 5)] = e;
+}
+
+// Fixed-order sum of the per-warp energy partials of ONE window by one block (any block size that is a
+// multiple of 32, <= 512).  `red` is shared scratch of 16 doubles.
+__device__ __forceinline__ void energy_sum_block(const BADesc& D, double* red) {
+  const int nparts = D.lin_warps;
+  double acc = 0.0;
+#pragma unroll 4
+  for (int b = threadIdx.x; b < nparts; b += blockDim.x) acc += __ldcg(D.epart + b);
+  acc = warp_sum(acc);
+  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = acc;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    double t = 0.0;
+    for (int w = 0; w < (int)(blockDim.x >> 5); ++w) t += red[w];
+    *D.energy = t;
   }
-  tk = __shfl_sync(0xffffffffu, tk, 0);
-  if (tk == (unsigned)nwarps - 1) {
-    __threadfence();
-    double acc = 0.0;
-#pragma unroll 8
-    for (int b = lane; b < nwarps; b += 32) acc += __ldcg(D.epart + b);
-    acc = warp_sum(acc);
-    if (lane == 0) { *D.energy = acc; *D.ticket = 0; }
-  }
+}
+
+__global__ void __launch_bounds__(256) ba_energy_kernel(const BADesc* __restrict__ descs) {
+  __shared__ double red[16];
+  energy_sum_block(descs[blockIdx.x], red);
 }
 
 __global__ void ba_apply_kernel(BARes r) {
@@ -809,7 +815,7 @@ __device__ __forceinline__ void sandwich_warp(const double* __restrict__ A1, con
 
 __global__ void __launch_bounds__(ST_THREADS) ba_stitch_kernel(const BADesc* __restrict__ descs,
                                                                const int* __restrict__ prefix, int nwin,
-                                                               int sys_begin, int sys_end) {
+                                                               int sys_begin, int sys_end, int with_energy) {
   int lb;
   const int win = find_window(prefix, nwin, blockIdx.x, lb);
   const StitchArgs& S = descs[win].S;
@@ -932,6 +938,7 @@ __global__ void __launch_bounds__(ST_THREADS) ba_stitch_kernel(const BADesc* __r
           for (int k = 0; k < nn; ++k) tot += (int)acc[(size_t)k * TOP_PART + 91];
         S.nres[sys] = tot;   // resInA / resInL (EnergyFunctional.cpp:163,186)
       }
+      if (sys == 0 && with_energy) energy_sum_block(descs[win], &part[0][0]);   // uniform per block
     }
     return;
   }
