@@ -112,7 +112,7 @@ class Context:
 
     def profile_read(self):
         """{kernel class: (summed ms, launches)} measured with CUDA events on the context stream."""
-        K = 15
+        K = 16
         ms = np.zeros(K, np.float32); cnt = np.zeros(K, np.int32)
         _chk(self.L.hslam_profile_read(self.h, _ptr(ms), _ptr(cnt)))
         self.L.hslam_kernel_name.restype = C.c_char_p

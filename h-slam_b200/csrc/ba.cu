@@ -55,6 +55,9 @@ struct hslam_ba {
   DevBuf<uint8_t> d_isLin, d_isActive;
   DevBuf<float> d_senergy, d_newEnergy, d_newEnergyWO, d_J, d_JpJdF, d_rtz, d_cpt, d_pto, d_ptc[2];
   std::vector<int> r_sorted2orig, r_orig2sorted;
+  DevBuf<int> d_r_s2o, d_p_s2o;          // device copies of the sorted->caller permutations
+  DevBuf<char> d_scratch;                // staging for layout conversion kernels
+  size_t scratch_used = 0;
   int n_linearized = 0;
   // chunks / partials
   DevBuf<TopChunk> d_topchunks;
@@ -92,6 +95,7 @@ static int ba_flush(hslam_ba* ba) {
   for (auto& f : ba->pending) f();
   ba->pending.clear();
   ba->arena_used = 0;
+  ba->scratch_used = 0;
   return 0;
 }
 static int arena_alloc(hslam_ba* ba, size_t bytes, void** out) {
@@ -133,23 +137,42 @@ template <class T> static int download(hslam_ba* ba, T* dst_host, const T* src_d
   if (!dst_host) return 0;
   return download_then<T>(ba, src_dev, n, [dst_host, n](const T* s) { memcpy(dst_host, s, n * sizeof(T)); });
 }
-// per-residual SoA block [comps][rs] -> caller order [R][comps]
+// device scratch for layout conversions; lives until the next flush (bump allocation)
+static int scratch_alloc(hslam_ba* ba, size_t bytes, void** out) {
+  bytes = (bytes + 255) & ~(size_t)255;
+  if (ba->scratch_used + bytes > ba->d_scratch.cap) {
+    TRY(ba_flush(ba));
+    if (bytes > ba->d_scratch.cap) TRY(ba->d_scratch.ensure(std::max(bytes * 2, (size_t)16 << 20)));
+  }
+  *out = ba->d_scratch.p + ba->scratch_used;
+  ba->scratch_used += bytes;
+  return 0;
+}
+// per-residual SoA block [comps][rs] -> caller order [R][comps]: permuted on the device, then ONE
+// contiguous D2H and a plain memcpy on the host (the host-side scatter cost ~0.3 ms per 84k residuals)
 template <class T> static int download_res(hslam_ba* ba, const T* dev, int comps, T* out) {
-  if (!out) return 0;
-  const size_t rs = ba->rs;
-  return download_then<T>(ba, dev, comps * rs, [ba, comps, out, rs](const T* src) {
-    for (int k = 0; k < ba->R; ++k) {
-      size_t r = ba->r_sorted2orig[k];
-      for (int c = 0; c < comps; ++c) out[r * comps + c] = src[c * rs + k];
-    }
-  });
+  if (!out || ba->R == 0) return 0;
+  void* tmp;
+  TRY(scratch_alloc(ba, (size_t)ba->R * comps * sizeof(T), &tmp));
+  HS_LAUNCH(ba->ctx, HSLAM_K_BA_EXPORT, (ba_export_kernel<T><<<(ba->R + 255) / 256, 256, 0, ba->ctx->stream>>>(
+                                            dev, comps, ba->rs, ba->R, ba->d_r_s2o.p, (T*)tmp)));
+  return download(ba, out, (const T*)tmp, (size_t)ba->R * comps);
 }
 template <class T> static int download_pts(hslam_ba* ba, const T* dev, int comps, T* out) {
-  if (!out) return 0;
-  return download_then<T>(ba, dev, (size_t)ba->P * comps, [ba, comps, out](const T* src) {
-    for (int sp = 0; sp < ba->P; ++sp)
-      for (int c = 0; c < comps; ++c) out[(size_t)ba->p_sorted2orig[sp] * comps + c] = src[(size_t)sp * comps + c];
-  });
+  if (!out || ba->P == 0) return 0;
+  void* tmp;
+  TRY(scratch_alloc(ba, (size_t)ba->P * comps * sizeof(T), &tmp));
+  // point arrays are [P] or [P][4] point-major: treat as comps interleaved -> stride 1 per component is
+  // not SoA, so export component by component with stride = comps
+  if (comps == 1) {
+    HS_LAUNCH(ba->ctx, HSLAM_K_BA_EXPORT, (ba_export_kernel<T><<<(ba->P + 255) / 256, 256, 0, ba->ctx->stream>>>(
+                                              dev, 1, ba->P, ba->P, ba->d_p_s2o.p, (T*)tmp)));
+  } else {
+    // [P][comps] AoS: export as `comps`-wide records
+    HS_LAUNCH(ba->ctx, HSLAM_K_BA_EXPORT, (ba_export_aos_kernel<T><<<(ba->P + 255) / 256, 256, 0, ba->ctx->stream>>>(
+                                              dev, comps, ba->P, ba->d_p_s2o.p, (T*)tmp)));
+  }
+  return download(ba, out, (const T*)tmp, (size_t)ba->P * comps);
 }
 
 // ---------------------------------------------------------------- descriptor
@@ -229,6 +252,7 @@ int hslam_ba_destroy(hslam_ba* ba) {
   ba->d_ptchunks.release(); ba->d_host_chunk_begin.release(); ba->d_scpartial.release(); ba->d_G.release();
   ba->d_Hb.release(); ba->d_epart.release(); ba->d_energy.release(); ba->d_nres.release(); ba->d_ticket.release();
   ba->d_xc.release(); ba->d_xAd.release(); ba->d_ids.release(); ba->d_desc.release();
+  ba->d_r_s2o.release(); ba->d_p_s2o.release(); ba->d_scratch.release();
   if (ba->arena) cudaFreeHost(ba->arena);
   delete ba;
   return 0;
@@ -359,6 +383,8 @@ int hslam_ba_set_topology(hslam_ba* ba, const hslam_point_soa* pt, const hslam_r
   ba->P = P; ba->R = R; ba->rs = (R + 31) & ~31;
   if (ba->rs == 0) ba->rs = 32;
   const size_t rsz = ba->rs;
+  TRY(ba->d_r_s2o.ensure(R + 1)); TRY(ba->d_p_s2o.ensure(P + 1));
+  TRY(upload(ba, ba->d_r_s2o.p, ba->r_sorted2orig.data(), R)); TRY(upload(ba, ba->d_p_s2o.p, ba->p_sorted2orig.data(), P));
   // ---- allocate
   TRY(ba->d_uvid.ensure(P + 1)); TRY(ba->d_color.ensure(2 * (size_t)P + 2)); TRY(ba->d_weights.ensure(2 * (size_t)P + 2));
   TRY(ba->d_priorF.ensure(P + 1)); TRY(ba->d_deltaF.ensure(P + 1)); TRY(ba->d_phost.ensure(P + 1));
@@ -481,23 +507,25 @@ int hslam_ba_set_topology(hslam_ba* ba, const hslam_point_soa* pt, const hslam_r
 
 int hslam_ba_update_points(hslam_ba* ba, const float* idepth, const float* deltaF, const float* idepth_zero) {
   HS_ARG(ba && ba->have_topology, "hslam_ba_update_points: no topology");
-  HS_CUDA(cudaSetDevice(ba->ctx->device));
+  hslam_ctx* ctx = ba->ctx;
+  HS_CUDA(cudaSetDevice(ctx->device));
   const int P = ba->P;
-  if (idepth || idepth_zero) {
-    for (int sp = 0; sp < P; ++sp) {
-      int p = ba->p_sorted2orig[sp];
-      if (idepth) ba->h_uvid[sp].z = idepth[p];
-      if (idepth_zero) ba->h_uvid[sp].w = idepth_zero[p];
-    }
-    TRY(upload(ba, ba->d_uvid.p, ba->h_uvid.data(), P));
+  if (P == 0) return 0;
+  // caller-order arrays go up as they are; a tiny kernel scatters them into the sorted point records
+  const float* srcs[3] = {idepth, idepth_zero, deltaF};
+  for (int i = 0; i < 3; ++i) {
+    if (!srcs[i]) continue;
+    void* tmp;
+    TRY(scratch_alloc(ba, (size_t)P * sizeof(float), &tmp));
+    TRY(upload(ba, (float*)tmp, srcs[i], P));
+    if (i < 2)
+      HS_LAUNCH(ctx, HSLAM_K_BA_EXPORT, (ba_import_kernel<float><<<(P + 255) / 256, 256, 0, ctx->stream>>>(
+                                            (const float*)tmp, P, ba->d_p_s2o.p, (float*)ba->d_uvid.p, 4, i == 0 ? 2 : 3)));
+    else
+      HS_LAUNCH(ctx, HSLAM_K_BA_EXPORT, (ba_import_kernel<float><<<(P + 255) / 256, 256, 0, ctx->stream>>>(
+                                            (const float*)tmp, P, ba->d_p_s2o.p, ba->d_deltaF.p, 1, 0)));
   }
-  if (deltaF && P) {
-    void* s;
-    TRY(arena_alloc(ba, (size_t)P * sizeof(float), &s));
-    float* d = (float*)s;
-    for (int sp = 0; sp < P; ++sp) d[sp] = deltaF[ba->p_sorted2orig[sp]];
-    HS_CUDA(cudaMemcpyAsync(ba->d_deltaF.p, d, (size_t)P * sizeof(float), cudaMemcpyHostToDevice, ba->ctx->stream));
-  }
+  HS_CUDA(cudaGetLastError());
   return 0;
 }
 

@@ -1013,6 +1013,33 @@ __global__ void __launch_bounds__(ST_THREADS) ba_stitch_kernel(const BADesc* __r
 #undef CONTRIB
 }
 
+// Layout conversion for the host API: component-major sorted SoA [comps][stride] -> caller order
+// [count][comps] (idx = sorted2orig), so the D2H copy is contiguous and the host only memcpy's.
+template <class T>
+__global__ void ba_export_kernel(const T* __restrict__ src, int comps, int stride, int count,
+                                 const int* __restrict__ sorted2orig, T* __restrict__ dst) {
+  int k = blockIdx.x * blockDim.x + threadIdx.x;
+  if (k >= count) return;
+  size_t o = (size_t)sorted2orig[k] * comps;
+  for (int c = 0; c < comps; ++c) dst[o + c] = src[(size_t)c * stride + k];
+}
+template <class T>
+__global__ void ba_export_aos_kernel(const T* __restrict__ src, int comps, int count,
+                                     const int* __restrict__ sorted2orig, T* __restrict__ dst) {
+  int k = blockIdx.x * blockDim.x + threadIdx.x;
+  if (k >= count) return;
+  size_t o = (size_t)sorted2orig[k] * comps;
+  for (int c = 0; c < comps; ++c) dst[o + c] = src[(size_t)k * comps + c];
+}
+// and the other way for per-point uploads: caller order [count] -> sorted order
+template <class T>
+__global__ void ba_import_kernel(const T* __restrict__ src, int count, const int* __restrict__ sorted2orig,
+                                 T* __restrict__ dst, int dst_stride_elems, int dst_offset) {
+  int k = blockIdx.x * blockDim.x + threadIdx.x;
+  if (k >= count) return;
+  dst[(size_t)k * dst_stride_elems + dst_offset] = src[sorted2orig[k]];
+}
+
 // EnergyFunctional::resubstituteFPt (EnergyFunctional.cpp:249-274); xAd[n*h+t] uploaded by the host
 __global__ void ba_resub_kernel(BAWin W, BARes r, BAPts pts, const float* __restrict__ xc, const float* __restrict__ xAd) {
   int p = blockIdx.x * blockDim.x + threadIdx.x;

@@ -106,7 +106,8 @@ int64_t hslam_launch_count(hslam_ctx* ctx);
 #define HSLAM_K_BA_FIXLIN 12
 #define HSLAM_K_UNPACK 13
 #define HSLAM_K_BA_ENERGY 14
-#define HSLAM_K_COUNT 15
+#define HSLAM_K_BA_EXPORT 15
+#define HSLAM_K_COUNT 16
 int hslam_profile_enable(hslam_ctx* ctx, int enable);
 int hslam_profile_read(hslam_ctx* ctx, float ms_out[HSLAM_K_COUNT], int count_out[HSLAM_K_COUNT]);
 const char* hslam_kernel_name(int k);
