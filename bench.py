@@ -233,32 +233,24 @@ def main():
     roofline = {"bound": "hbm", "kernel": dom, "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                 "traffic": traffic, "peak_source": peak_kind, "avg_launch_us": avg_s * 1e6,
                 "algorithmic_bytes_per_launch": algo_bytes,
-                "kernel_share_of_step": {k: v[0] / sum(x[0] for x in prof.values()) for k, v in prof.items()}}
+                "kernel_share_of_step": {k: v[0] / sum(x[0] for x in prof.values()) for k, v in prof.items()},
+                "kernel_avg_us": {k: 1e3 * v[0] / max(v[1], 1) for k, v in prof.items()}}
 
     # ---- e2e: the same GN iteration through the C ABI with HOST buffers, copies inside the timed region
     N = 8 * N_FRAMES + 4
     xs = [np.random.default_rng(i).normal(0, 1e-4, N) for i in range(len(wins))]
 
+    io = batch.make_io(wins, frames_all, pinned=True)     # caller-side buffers (page-locked via hslam_host_alloc)
+
     def step_e2e():
-        # phase 1 (all windows enqueued, then ONE wait each): host tables up, linearise, accumulate, systems down
-        for ef, w, fr in zip(efs, wins, frames_all):
-            ef.begin_async()
-            ef.set_window(w, fr)                                   # H2D: precalc, adjoints, deltas, priors
-            ef.update_points(idepth=w.idepth, deltaF=w.deltaF)     # H2D: per-point state
-            ef.linearizeAll(False, outputs="states")               # D2H: energy, newState, newEnergy, newEnergyWithOutlier
-            ef.applyRes()
-            ef.accumulate_all()                                    # D2H: 3 x (H,b), resInA/L
-        for ef in efs:
-            ef.wait()
-        # (the host solves the 60x60 system here in the real pipeline) phase 2: back-substitution
-        for ef, x in zip(efs, xs):
-            ef.begin_async()
-            ef.resubstituteF_MT(x)                                 # H2D: x ; D2H: point steps
-        for ef in efs:
-            ef.wait()
+        # phase 1: ONE C-ABI call for the batch — host tables + per-point state up (one H2D block), linearizeAll +
+        # applyRes + accumulateAF/LF/SCF, energies + residual states + 3 x (H,b) down, returns when they are valid
+        batch.step_host(io)
+        # (the host solves the 60x60 systems here in the real pipeline) phase 2: back-substitution, x up, steps down
+        batch.resubstitute_host(io, xs)
 
     n2 = N_FRAMES * N_FRAMES
-    h2d = sum(n2 * 28 * 4 + n2 * 8 * 4 + 2 * n2 * 64 * 8 + 2 * N_FRAMES * 64 + w.P * 16 + w.P * 4 + 16 + n2 * 8 * 4 for w in wins)
+    h2d = sum(n2 * 28 * 4 + n2 * 8 * 4 + 2 * n2 * 64 * 8 + 2 * N_FRAMES * 64 + 2 * w.P * 4 + N * 8 + 2 * 136 for w in wins)
     d2h = sum(8 + w.R * 9 + 3 * (N * N + N) * 8 + 8 + w.P * 4 for w in wins)
     for _ in range(2):
         step_e2e()
@@ -285,7 +277,8 @@ def main():
         "config": {"workload": f"cfg2: BA window 7KF x 2000pts/KF x 8px (P=14000, R=84000), 1 GN iteration hot path, "
                                f"{args.windows} independent windows per GPU per step",
                    "windows_per_gpu": args.windows, "l2_policy": "inputs larger than L2 (no flush): batch working set "
-                   f"~{args.windows * 62} MB vs 126 MB L2", "jacobians": "materialised (SoA in HBM)"},
+                   f"~{args.windows * 62} MB vs 126 MB L2", "jacobians": "materialised (SoA in HBM)",
+                   "e2e_api": "hslam_ba_batch_step_host + hslam_ba_batch_resubstitute_host (host buffers, 2 waits per step)"},
         "e2e": {"value": e2e_val, "unit": UNIT, "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
                 "ms_per_step": ms_e2e / k_e2e, "steps": k_e2e},
         "gpu_launches": int(launches),

@@ -49,6 +49,11 @@ class ResidualSoA(C.Structure):
         "point_idx", "target_idx", "state_state", "is_linearized", "is_active", "state_energy")]
 
 
+class StepIO(C.Structure):
+    _fields_ = [(k, C.c_void_p) for k in ("window", "idepth", "deltaF", "idepth_zero", "energy", "newState", "newEnergy",
+                                          "newEnergyWithOutlier", "Hb", "nres2")]
+
+
 def _ptr(a):
     return a.ctypes.data_as(C.c_void_p) if a is not None else None
 
@@ -106,6 +111,15 @@ class Context:
     @property
     def launches(self):
         return int(self.L.hslam_launch_count(self.h))
+
+    def host_empty(self, shape, dtype):
+        """numpy array in page-locked memory owned by the context (hslam_host_alloc): copies are direct DMA."""
+        dt = np.dtype(dtype)
+        n = int(np.prod(shape)) if np.ndim(shape) else int(shape)
+        p = C.c_void_p()
+        _chk(self.L.hslam_host_alloc(self.h, C.c_size_t(max(n * dt.itemsize, 1)), C.byref(p)))
+        buf = (C.c_char * (n * dt.itemsize)).from_address(p.value)
+        return np.frombuffer(buf, dtype=dt, count=n).reshape(shape)
 
     def profile_enable(self, on=True):
         _chk(self.L.hslam_profile_enable(self.h, C.c_int(int(on))))
@@ -260,7 +274,9 @@ class EnergyFunctional:
         self._pendings.append(p)
         return p
 
-    def set_window(self, win, frames):
+    @staticmethod
+    def window_struct(win, frames):
+        """(hslam_window, keep-alive list) for `win`; the arrays are referenced, not copied."""
         cam = win.cam
         ws = WindowStruct()
         ws.n_frames, ws.w, ws.h = win.n, cam.w, cam.h
@@ -277,6 +293,10 @@ class EnergyFunctional:
         for i in range(4):
             ws.cDeltaF[i] = float(win.cDeltaF[i])
             ws.cPrior[i] = float(win.cPrior[i])
+        return ws, [fr, ka]
+
+    def set_window(self, win, frames):
+        ws, _keep = EnergyFunctional.window_struct(win, frames)
         _chk(self.L.hslam_ba_set_window(self.h, C.byref(ws)))
         self.n = win.n
         self.N = 8 * win.n + 4
@@ -450,6 +470,41 @@ class EnergyFunctionalBatch:
 
     def iteration(self):
         _chk(self.L.hslam_ba_batch_iteration(self.h))
+
+    def make_io(self, wins, frames_per_window, pinned=True):
+        """Persistent host-side I/O block for step_host(): per window the hslam_window struct, the per-point
+        inputs and the output arrays (page-locked when `pinned`)."""
+        n = len(self.efs)
+        arr = (StepIO * n)()
+        keep, outs = [], []
+        for i, (ef, w, fr) in enumerate(zip(self.efs, wins, frames_per_window)):
+            ws, ka = EnergyFunctional.window_struct(w, fr)
+            N = 8 * w.n + 4
+            mk = (lambda shape, dt: self.ctx.host_empty(shape, dt)) if pinned else (lambda shape, dt: np.zeros(shape, dt))
+            o = dict(energy=mk(1, np.float64), newState=mk(ef.R, np.int8), newEnergy=mk(ef.R, np.float32),
+                     newEnergyWithOutlier=mk(ef.R, np.float32), Hb=mk(3 * (N * N + N), np.float64), nres2=mk(2, np.int32),
+                     step=mk(ef.P, np.float32))
+            inp = dict(idepth=np.ascontiguousarray(w.idepth, np.float32), deltaF=np.ascontiguousarray(w.deltaF, np.float32))
+            arr[i].window = C.cast(C.pointer(ws), C.c_void_p)
+            arr[i].idepth, arr[i].deltaF, arr[i].idepth_zero = _ptr(inp["idepth"]), _ptr(inp["deltaF"]), None
+            for k in ("energy", "newState", "newEnergy", "newEnergyWithOutlier", "Hb", "nres2"):
+                setattr(arr[i], k, _ptr(o[k]))
+            keep.append((ws, ka, inp))
+            outs.append(o)
+        return dict(arr=arr, keep=keep, out=outs)
+
+    def step_host(self, io):
+        """One GN iteration of every window with host buffers (one H2D block, one D2H block, one wait)."""
+        _chk(self.L.hslam_ba_batch_step_host(self.h, io["arr"]))
+        return io["out"]
+
+    def resubstitute_host(self, io, xs):
+        n = len(self.efs)
+        xa = [np.ascontiguousarray(x, np.float64) for x in xs]
+        xp = (C.c_void_p * n)(*[a.ctypes.data for a in xa])
+        sp = (C.c_void_p * n)(*[o["step"].ctypes.data for o in io["out"]])
+        _chk(self.L.hslam_ba_batch_resubstitute_host(self.h, xp, sp))
+        return [o["step"] for o in io["out"]]
 
     def close(self):
         if self.h:

@@ -42,7 +42,6 @@ struct hslam_ba {
   // window tables
   DevBuf<float> d_precalc, d_adHTd;
   DevBuf<double> d_adH, d_adT, d_fprior, d_fdprior;
-  std::vector<double> h_adH, h_adT;
   // points
   DevBuf<float4> d_uvid, d_color, d_weights, d_Hcd[2];
   DevBuf<float> d_priorF, d_deltaF, d_HdiF, d_bdSumF, d_idh, d_Hdd[2], d_bd[2], d_step;
@@ -75,6 +74,7 @@ struct hslam_ba {
   DevBuf<int> d_nres;          // [2]
   DevBuf<unsigned int> d_ticket;
   DevBuf<float> d_xc, d_xAd;
+  DevBuf<double> d_x;
   DevBuf<int> d_ids;
   // descriptor
   BADesc hdesc;
@@ -205,6 +205,8 @@ static void fill_desc(hslam_ba* ba) {
   S.nres = ba->d_nres.p; S.framePrior = ba->d_fprior.p; S.frameDeltaPrior = ba->d_fdprior.p;
   S.add_priors = ba->add_priors; S.has_L = ba->n_linearized != 0;
   for (int i = 0; i < 4; ++i) S.cDeltaF[i] = D.W.cDeltaF[i];
+  D.r_s2o = ba->d_r_s2o.p; D.p_s2o = ba->d_p_s2o.p;
+  D.x = ba->d_x.p; D.xc = ba->d_xc.p; D.xAd = ba->d_xAd.p;
   ba->desc_version++;
 }
 static int sync_desc(hslam_ba* ba) {
@@ -251,7 +253,7 @@ int hslam_ba_destroy(hslam_ba* ba) {
   ba->d_pair_ticket.release(); ba->d_host_ticket.release();
   ba->d_ptchunks.release(); ba->d_host_chunk_begin.release(); ba->d_scpartial.release(); ba->d_G.release();
   ba->d_Hb.release(); ba->d_epart.release(); ba->d_energy.release(); ba->d_nres.release(); ba->d_ticket.release();
-  ba->d_xc.release(); ba->d_xAd.release(); ba->d_ids.release(); ba->d_desc.release();
+  ba->d_xc.release(); ba->d_xAd.release(); ba->d_x.release(); ba->d_ids.release(); ba->d_desc.release();
   ba->d_r_s2o.release(); ba->d_p_s2o.release(); ba->d_scratch.release();
   if (ba->arena) cudaFreeHost(ba->arena);
   delete ba;
@@ -310,8 +312,7 @@ int hslam_ba_set_window(hslam_ba* ba, const hslam_window* w) {
   TRY(upload(ba, ba->d_fdprior.p, w->frameDeltaPrior, (size_t)n * 8));
   TRY(upload(ba, ba->d_precalc.p, w->precalc, nn * HSLAM_PRECALC_STRIDE));
   TRY(upload(ba, ba->d_adHTd.p, w->adHTdeltaF, nn * 8));
-  ba->h_adH.assign(w->adHost, w->adHost + nn * 64);
-  ba->h_adT.assign(w->adTarget, w->adTarget + nn * 64);
+  TRY(ba->d_x.ensure(ba->N)); TRY(ba->d_xc.ensure(4)); TRY(ba->d_xAd.ensure(nn * 8));
   TRY(ba->d_Hb.ensure(3 * ((size_t)ba->N * ba->N + ba->N)));
   if (ba->d_accTop.cap < 2 * nn * TOP_PART) {
     TRY(ba->d_accTop.ensure(2 * nn * TOP_PART));
@@ -767,35 +768,14 @@ int hslam_ba_residual_results(hslam_ba* ba, int8_t* state_state, uint8_t* is_act
 int hslam_ba_resubstitute(hslam_ba* ba, const double* x, float* step_out) {
   HS_ARG(ba && x && ba->have_topology && ba->have_window, "hslam_ba_resubstitute: bad argument");
   HS_CUDA(cudaSetDevice(ba->ctx->device));
-  const int n = ba->n, N = ba->N;
-  void* s;
-  TRY(arena_alloc(ba, ((size_t)n * n * 8 + 4) * sizeof(float), &s));
-  float* xc = (float*)s;
-  float* xAd = xc + 4;
-  std::vector<float> xF(N);
-  for (int i = 0; i < N; ++i) xF[i] = (float)x[i];
-  for (int i = 0; i < 4; ++i) xc[i] = xF[i];
-  // EnergyFunctional.cpp:236-238 (float row-vector times float 8x8, index order)
-  for (int h = 0; h < n; ++h)
-    for (int t = 0; t < n; ++t)
-      for (int c = 0; c < 8; ++c) {
-        volatile float a = 0.f, b = 0.f;
-        for (int r = 0; r < 8; ++r) {
-          volatile float pa = xF[4 + 8 * h + r] * (float)ba->h_adH[64 * (size_t)(h + n * t) + r + 8 * c];
-          volatile float pb = xF[4 + 8 * t + r] * (float)ba->h_adT[64 * (size_t)(h + n * t) + r + 8 * c];
-          a = a + pa; b = b + pb;
-        }
-        xAd[8 * (size_t)(n * h + t) + c] = a + b;
-      }
-  TRY(ba->d_xc.ensure(4)); TRY(ba->d_xAd.ensure((size_t)n * n * 8));
-  HS_CUDA(cudaMemcpyAsync(ba->d_xc.p, xc, 4 * sizeof(float), cudaMemcpyHostToDevice, ba->ctx->stream));
-  HS_CUDA(cudaMemcpyAsync(ba->d_xAd.p, xAd, (size_t)n * n * 8 * sizeof(float), cudaMemcpyHostToDevice, ba->ctx->stream));
+  TRY(sync_desc(ba));
+  TRY(upload(ba, ba->d_x.p, x, (size_t)ba->N));
+  // xAd = x_h^T adHostF + x_t^T adTargetF (EnergyFunctional.cpp:228-238) is formed on the device
+  HS_LAUNCH(ba->ctx, HSLAM_K_BA_RESUB, (ba_xad_kernel<<<1, 256, 0, ba->ctx->stream>>>(ba->d_desc.p)));
   int blocks = (ba->P + 127) / 128;
-  if (blocks > 0) {
-    HS_LAUNCH(ba->ctx, HSLAM_K_BA_RESUB, (ba_resub_kernel<<<blocks, 128, 0, ba->ctx->stream>>>(
-                                             ba->hdesc.W, ba->hdesc.r, ba->hdesc.p, ba->d_xc.p, ba->d_xAd.p)));
-    HS_CUDA(cudaGetLastError());
-  }
+  if (blocks > 0)
+    HS_LAUNCH(ba->ctx, HSLAM_K_BA_RESUB, (ba_resub_kernel<<<blocks, 128, 0, ba->ctx->stream>>>(ba->d_desc.p, nullptr, 1, nullptr, nullptr)));
+  HS_CUDA(cudaGetLastError());
   TRY(download_pts(ba, ba->d_step.p, 1, step_out));
   return end_call(ba);
 }
@@ -808,13 +788,20 @@ struct hslam_ba_batch {
   std::vector<hslam_ba*> items;
   std::vector<uint64_t> versions;
   DevBuf<BADesc> d_descs;
-  DevBuf<int> d_prefix;          // 5 tables of (count+1): linearize, top, schur, stitch, schur fold
+  DevBuf<int> d_prefix;          // NPF tables of (count+1): linearize, top, schur, stitch, schur fold, resubstitute
   BADesc* h_descs = nullptr;     // pinned
   int* h_prefix = nullptr;       // pinned
   cudaEvent_t copied = nullptr;
-  int blocks[5] = {0, 0, 0, 0, 0};
+  int blocks[6] = {0, 0, 0, 0, 0, 0};
   size_t smem = 0;
+  // host API staging: one pinned block up, one down, their device twins, and the per-window offset table
+  char* h_up = nullptr; char* h_dn = nullptr;
+  size_t h_up_cap = 0, h_dn_cap = 0;
+  DevBuf<char> d_up, d_dn;
+  DevBuf<BAIO> d_io;
+  std::vector<BAIO> io;
 };
+static const int NPF = 6;
 
 static int batch_refresh(hslam_ba_batch* B) {
   const int n = (int)B->items.size();
@@ -826,8 +813,8 @@ static int batch_refresh(hslam_ba_batch* B) {
   }
   if (!dirty) return 0;
   HS_CUDA(cudaEventSynchronize(B->copied));
-  int* pf[5];
-  for (int k = 0; k < 5; ++k) { pf[k] = B->h_prefix + k * (n + 1); pf[k][0] = 0; }
+  int* pf[NPF];
+  for (int k = 0; k < NPF; ++k) { pf[k] = B->h_prefix + k * (n + 1); pf[k][0] = 0; }
   B->smem = 0;
   for (int i = 0; i < n; ++i) {
     hslam_ba* ba = B->items[i];
@@ -840,11 +827,12 @@ static int batch_refresh(hslam_ba_batch* B) {
     pf[2][i + 1] = pf[2][i] + ba->n_ptchunks;
     pf[3][i + 1] = pf[3][i] + 3 * (ba->n + 1) * (ba->n + 1);
     pf[4][i + 1] = pf[4][i] + ba->n * ((ba->LD * ba->LD + 255) / 256);
+    pf[5][i + 1] = pf[5][i] + (ba->P + 127) / 128;
     B->smem = std::max(B->smem, schur_smem(ba->LD, ba->maxres));
   }
-  for (int k = 0; k < 5; ++k) B->blocks[k] = pf[k][n];
+  for (int k = 0; k < NPF; ++k) B->blocks[k] = pf[k][n];
   HS_CUDA(cudaMemcpyAsync(B->d_descs.p, B->h_descs, n * sizeof(BADesc), cudaMemcpyHostToDevice, B->ctx->stream));
-  HS_CUDA(cudaMemcpyAsync(B->d_prefix.p, B->h_prefix, 5 * (n + 1) * sizeof(int), cudaMemcpyHostToDevice, B->ctx->stream));
+  HS_CUDA(cudaMemcpyAsync(B->d_prefix.p, B->h_prefix, NPF * (n + 1) * sizeof(int), cudaMemcpyHostToDevice, B->ctx->stream));
   HS_CUDA(cudaEventRecord(B->copied, B->ctx->stream));
   return 0;
 }
@@ -862,9 +850,11 @@ int hslam_ba_batch_create(hslam_ctx* ctx, hslam_ba* const* items, int count, hsl
   }
   B->versions.assign(count, 0);
   TRY(B->d_descs.ensure(count));
-  TRY(B->d_prefix.ensure(5 * (size_t)(count + 1)));
+  TRY(B->d_prefix.ensure(NPF * (size_t)(count + 1)));
+  TRY(B->d_io.ensure(count));
+  B->io.resize(count);
   HS_CUDA(cudaMallocHost((void**)&B->h_descs, count * sizeof(BADesc)));
-  HS_CUDA(cudaMallocHost((void**)&B->h_prefix, 5 * (size_t)(count + 1) * sizeof(int)));
+  HS_CUDA(cudaMallocHost((void**)&B->h_prefix, NPF * (size_t)(count + 1) * sizeof(int)));
   HS_CUDA(cudaEventCreateWithFlags(&B->copied, cudaEventDisableTiming));
   *out = B;
   return 0;
@@ -874,19 +864,18 @@ int hslam_ba_batch_destroy(hslam_ba_batch* B) {
   if (!B) return 0;
   cudaSetDevice(B->ctx->device);
   cudaStreamSynchronize(B->ctx->stream);
-  B->d_descs.release(); B->d_prefix.release();
+  B->d_descs.release(); B->d_prefix.release(); B->d_up.release(); B->d_dn.release(); B->d_io.release();
   cudaFreeHost(B->h_descs); cudaFreeHost(B->h_prefix);
+  if (B->h_up) cudaFreeHost(B->h_up);
+  if (B->h_dn) cudaFreeHost(B->h_dn);
   cudaEventDestroy(B->copied);
   delete B;
   return 0;
 }
 
-// One GN iteration's hot path for EVERY window of the batch: four launches in total.
-int hslam_ba_batch_iteration(hslam_ba_batch* B) {
-  HS_ARG(B, "hslam_ba_batch_iteration: null");
+// One GN iteration's hot path for EVERY window of the batch: five launches in total.
+static int batch_enqueue_iteration(hslam_ba_batch* B) {
   hslam_ctx* ctx = B->ctx;
-  HS_CUDA(cudaSetDevice(ctx->device));
-  TRY(batch_refresh(B));
   const int n = (int)B->items.size();
   const int* pf = B->d_prefix.p;
   TRY(schur_attr(B->smem));
@@ -898,6 +887,205 @@ int hslam_ba_batch_iteration(hslam_ba_batch* B) {
   HS_LAUNCH(ctx, HSLAM_K_BA_FOLD_SC, (ba_fold_sc_kernel<<<B->blocks[4], 256, 0, ctx->stream>>>(B->d_descs.p, pf + 4 * (n + 1), n)));
   HS_LAUNCH(ctx, HSLAM_K_BA_STITCH, (ba_stitch_kernel<<<B->blocks[3], ST_THREADS, 0, ctx->stream>>>(B->d_descs.p, pf + 3 * (n + 1), n, 0, 3, 1)));
   HS_CUDA(cudaGetLastError());
+  return 0;
+}
+
+int hslam_ba_batch_iteration(hslam_ba_batch* B) {
+  HS_ARG(B, "hslam_ba_batch_iteration: null");
+  HS_CUDA(cudaSetDevice(B->ctx->device));
+  TRY(batch_refresh(B));
+  return batch_enqueue_iteration(B);
+}
+
+// ---- host-buffer API of a batch: one staging block up, one down per call ------------------------------
+static int pinned_ensure(char** p, size_t* cap, size_t bytes) {
+  if (bytes <= *cap) return 0;
+  if (*p) cudaFreeHost(*p);
+  *p = nullptr;
+  *cap = bytes + bytes / 4 + 4096;
+  HS_CUDA(cudaMallocHost((void**)p, *cap));
+  return 0;
+}
+static inline size_t al256(size_t x) { return (x + 255) & ~(size_t)255; }
+
+// Scalar part of hslam_ba_set_window (the tables travel through the staging block).
+static int window_scalars(hslam_ba* ba, const hslam_window* w) {
+  HS_ARG(w->n_frames == ba->n, "hslam_ba_batch_step_host: n_frames differs from the window's topology");
+  HS_ARG(w->frames && w->frameEnergyTH && w->precalc && w->adHost && w->adTarget && w->adHTdeltaF && w->framePrior &&
+             w->frameDeltaPrior, "hslam_ba_batch_step_host: null table");
+  hslam_ctx* ctx = ba->ctx;
+  BAWin W = ba->hdesc.W;
+  W.w = w->w; W.h = w->h;
+  W.fx = w->fx; W.fy = w->fy; W.cx = w->cx; W.cy = w->cy; W.fxi = w->fxi; W.fyi = w->fyi;
+  for (int i = 0; i < 4; ++i) W.cDeltaF[i] = w->cDeltaF[i];
+  for (int f = 0; f < ba->n; ++f) {
+    HS_ARG(w->frames[f] && w->frames[f]->ctx == ctx, "hslam_ba_batch_step_host: frame missing or from another context");
+    HS_ARG(w->frames[f]->w == w->w && w->frames[f]->h == w->h, "hslam_ba_batch_step_host: frame size mismatch");
+    W.img[f] = w->frames[f]->dI[0];
+    W.frameEnergyTH[f] = w->frameEnergyTH[f];
+  }
+  StitchArgs S = ba->hdesc.S;
+  for (int i = 0; i < 4; ++i) { S.cPrior[i] = w->cPrior[i]; S.cDeltaF[i] = w->cDeltaF[i]; }
+  if (memcmp(&W, &ba->hdesc.W, sizeof(BAWin)) != 0 || memcmp(&S, &ba->hdesc.S, sizeof(StitchArgs)) != 0) {
+    ba->hdesc.W = W; ba->hdesc.S = S;
+    ba->desc_version++;
+  }
+  return 0;
+}
+
+int hslam_ba_batch_step_host(hslam_ba_batch* B, const hslam_ba_step_io* io) {
+  HS_ARG(B && io, "hslam_ba_batch_step_host: null argument");
+  hslam_ctx* ctx = B->ctx;
+  HS_CUDA(cudaSetDevice(ctx->device));
+  const int n = (int)B->items.size();
+  // ---- layout of the two staging blocks
+  size_t up = 0, dn = 0;
+  int maxP = 1, maxR = 1;
+  for (int i = 0; i < n; ++i) {
+    hslam_ba* ba = B->items[i];
+    HS_ARG(ba->have_window && ba->have_topology, "hslam_ba_batch_step_host: a window has no window/topology set");
+    const hslam_ba_step_io& o = io[i];
+    BAIO& L = B->io[i];
+    const size_t nn = (size_t)ba->n * ba->n, P = ba->P, R = ba->R, N = ba->N;
+    auto take = [](size_t& cur, size_t bytes) { long long off = (long long)cur; cur = al256(cur + bytes); return off; };
+    if (o.window) {
+      TRY(window_scalars(ba, o.window));
+      L.up_precalc = take(up, nn * HSLAM_PRECALC_STRIDE * 4); L.up_adHTd = take(up, nn * 8 * 4);
+      L.up_adH = take(up, nn * 64 * 8); L.up_adT = take(up, nn * 64 * 8);
+      L.up_fprior = take(up, (size_t)ba->n * 8 * 8); L.up_fdprior = take(up, (size_t)ba->n * 8 * 8);
+    } else {
+      L.up_precalc = L.up_adHTd = L.up_adH = L.up_adT = L.up_fprior = L.up_fdprior = -1;
+    }
+    L.up_idepth = o.idepth ? take(up, P * 4) : -1;
+    L.up_deltaF = o.deltaF ? take(up, P * 4) : -1;
+    L.up_idz = o.idepth_zero ? take(up, P * 4) : -1;
+    L.up_x = -1;
+    L.dn_energy = o.energy ? take(dn, 8) : -1;
+    L.dn_nres = o.nres2 ? take(dn, 8) : -1;
+    L.dn_Hb = o.Hb ? take(dn, 3 * (N * N + N) * 8) : -1;
+    L.dn_newEnergy = o.newEnergy ? take(dn, R * 4) : -1;
+    L.dn_newEnergyWO = o.newEnergyWithOutlier ? take(dn, R * 4) : -1;
+    L.dn_newState = o.newState ? take(dn, R) : -1;
+    L.dn_step = -1;
+    maxP = std::max(maxP, ba->P); maxR = std::max(maxR, ba->R);
+  }
+  const size_t io_bytes = al256(n * sizeof(BAIO));
+  TRY(pinned_ensure(&B->h_up, &B->h_up_cap, up + io_bytes));
+  TRY(B->d_up.ensure(up + io_bytes));
+  TRY(B->d_dn.ensure(std::max(dn, (size_t)256)));
+  // ---- pack: [BAIO table][window 0 tables + point arrays][window 1 ...]
+  memcpy(B->h_up + up, B->io.data(), n * sizeof(BAIO));
+  for (int i = 0; i < n; ++i) {
+    hslam_ba* ba = B->items[i];
+    const hslam_ba_step_io& o = io[i];
+    const BAIO& L = B->io[i];
+    const size_t nn = (size_t)ba->n * ba->n, P = ba->P;
+    if (o.window) {
+      const hslam_window* w = o.window;
+      memcpy(B->h_up + L.up_precalc, w->precalc, nn * HSLAM_PRECALC_STRIDE * 4);
+      memcpy(B->h_up + L.up_adHTd, w->adHTdeltaF, nn * 8 * 4);
+      memcpy(B->h_up + L.up_adH, w->adHost, nn * 64 * 8);
+      memcpy(B->h_up + L.up_adT, w->adTarget, nn * 64 * 8);
+      memcpy(B->h_up + L.up_fprior, w->framePrior, (size_t)ba->n * 8 * 8);
+      memcpy(B->h_up + L.up_fdprior, w->frameDeltaPrior, (size_t)ba->n * 8 * 8);
+    }
+    if (o.idepth) memcpy(B->h_up + L.up_idepth, o.idepth, P * 4);
+    if (o.deltaF) memcpy(B->h_up + L.up_deltaF, o.deltaF, P * 4);
+    if (o.idepth_zero) memcpy(B->h_up + L.up_idz, o.idepth_zero, P * 4);
+  }
+  TRY(batch_refresh(B));   // descriptors (only if a scalar changed) and block-prefix tables
+  HS_CUDA(cudaMemcpyAsync(B->d_up.p, B->h_up, up + io_bytes, cudaMemcpyHostToDevice, ctx->stream));
+  const BAIO* d_io = reinterpret_cast<const BAIO*>(B->d_up.p + up);
+  {
+    dim3 grid((unsigned)std::max(1, std::min(64, (maxP + 255) / 256)), (unsigned)n);
+    HS_LAUNCH(ctx, HSLAM_K_BA_EXPORT, (ba_batch_import_kernel<<<grid, 256, 0, ctx->stream>>>(B->d_descs.p, d_io, B->d_up.p)));
+  }
+  TRY(batch_enqueue_iteration(B));
+  if (dn > 0) {
+    dim3 grid((unsigned)std::max(1, std::min(128, (maxR + 255) / 256)), (unsigned)n);
+    HS_LAUNCH(ctx, HSLAM_K_BA_EXPORT, (ba_batch_export_kernel<<<grid, 256, 0, ctx->stream>>>(B->d_descs.p, d_io, B->d_dn.p)));
+    HS_CUDA(cudaGetLastError());
+  }
+  // ---- results: straight into the caller's buffers where they are pinned (hslam_host_alloc), else one
+  // staged copy + memcpy after the synchronisation
+  struct Out { void* dst; long long off; size_t bytes; };
+  std::vector<Out> staged;
+  auto emit = [&](void* dst, long long off, size_t bytes) -> int {
+    if (!dst || off < 0 || bytes == 0) return 0;
+    if (ctx->is_pinned(dst, bytes)) {
+      HS_CUDA(cudaMemcpyAsync(dst, B->d_dn.p + off, bytes, cudaMemcpyDeviceToHost, ctx->stream));
+    } else {
+      staged.push_back({dst, off, bytes});
+    }
+    return 0;
+  };
+  for (int i = 0; i < n; ++i) {
+    hslam_ba* ba = B->items[i];
+    const hslam_ba_step_io& o = io[i];
+    const BAIO& L = B->io[i];
+    const size_t R = ba->R, N = ba->N;
+    TRY(emit(o.energy, L.dn_energy, 8)); TRY(emit(o.nres2, L.dn_nres, 8));
+    TRY(emit(o.Hb, L.dn_Hb, 3 * (N * N + N) * 8));
+    TRY(emit(o.newEnergy, L.dn_newEnergy, R * 4)); TRY(emit(o.newEnergyWithOutlier, L.dn_newEnergyWO, R * 4));
+    TRY(emit(o.newState, L.dn_newState, R));
+  }
+  if (!staged.empty()) {
+    TRY(pinned_ensure(&B->h_dn, &B->h_dn_cap, dn));
+    HS_CUDA(cudaMemcpyAsync(B->h_dn, B->d_dn.p, dn, cudaMemcpyDeviceToHost, ctx->stream));
+  }
+  HS_CUDA(cudaStreamSynchronize(ctx->stream));
+  for (const Out& s : staged) memcpy(s.dst, B->h_dn + s.off, s.bytes);
+  return 0;
+}
+
+int hslam_ba_batch_resubstitute_host(hslam_ba_batch* B, const double* const* x, float* const* step_out) {
+  HS_ARG(B && x && step_out, "hslam_ba_batch_resubstitute_host: null argument");
+  hslam_ctx* ctx = B->ctx;
+  HS_CUDA(cudaSetDevice(ctx->device));
+  const int n = (int)B->items.size();
+  size_t up = 0, dn = 0;
+  for (int i = 0; i < n; ++i) {
+    hslam_ba* ba = B->items[i];
+    HS_ARG(ba->have_window && ba->have_topology && x[i], "hslam_ba_batch_resubstitute_host: window not set or null x");
+    BAIO& L = B->io[i];
+    memset(&L, 0xff, sizeof(BAIO));   // every offset = -1
+    L.up_x = (long long)up; up = al256(up + (size_t)ba->N * 8);
+    if (step_out[i]) { L.dn_step = (long long)dn; dn = al256(dn + (size_t)ba->P * 4); }
+  }
+  const size_t io_bytes = al256(n * sizeof(BAIO));
+  TRY(pinned_ensure(&B->h_up, &B->h_up_cap, up + io_bytes));
+  TRY(B->d_up.ensure(up + io_bytes));
+  TRY(B->d_dn.ensure(std::max(dn, (size_t)256)));
+  memcpy(B->h_up + up, B->io.data(), n * sizeof(BAIO));
+  for (int i = 0; i < n; ++i) memcpy(B->h_up + B->io[i].up_x, x[i], (size_t)B->items[i]->N * 8);
+  TRY(batch_refresh(B));
+  HS_CUDA(cudaMemcpyAsync(B->d_up.p, B->h_up, up + io_bytes, cudaMemcpyHostToDevice, ctx->stream));
+  const BAIO* d_io = reinterpret_cast<const BAIO*>(B->d_up.p + up);
+  HS_LAUNCH(ctx, HSLAM_K_BA_EXPORT, (ba_batch_import_kernel<<<dim3(1, (unsigned)n), 256, 0, ctx->stream>>>(B->d_descs.p, d_io, B->d_up.p)));
+  HS_LAUNCH(ctx, HSLAM_K_BA_RESUB, (ba_xad_kernel<<<n, 256, 0, ctx->stream>>>(B->d_descs.p)));
+  if (B->blocks[5] > 0)
+    HS_LAUNCH(ctx, HSLAM_K_BA_RESUB, (ba_resub_kernel<<<B->blocks[5], 128, 0, ctx->stream>>>(
+                                         B->d_descs.p, B->d_prefix.p + 5 * (n + 1), n, d_io, B->d_dn.p)));
+  HS_CUDA(cudaGetLastError());
+  bool any_staged = false;
+  for (int i = 0; i < n; ++i) {
+    if (!step_out[i]) continue;
+    const size_t bytes = (size_t)B->items[i]->P * 4;
+    if (ctx->is_pinned(step_out[i], bytes))
+      HS_CUDA(cudaMemcpyAsync(step_out[i], B->d_dn.p + B->io[i].dn_step, bytes, cudaMemcpyDeviceToHost, ctx->stream));
+    else
+      any_staged = true;
+  }
+  if (any_staged) {
+    TRY(pinned_ensure(&B->h_dn, &B->h_dn_cap, dn));
+    HS_CUDA(cudaMemcpyAsync(B->h_dn, B->d_dn.p, dn, cudaMemcpyDeviceToHost, ctx->stream));
+  }
+  HS_CUDA(cudaStreamSynchronize(ctx->stream));
+  if (any_staged)
+    for (int i = 0; i < n; ++i) {
+      const size_t bytes = (size_t)B->items[i]->P * 4;
+      if (step_out[i] && !ctx->is_pinned(step_out[i], bytes)) memcpy(step_out[i], B->h_dn + B->io[i].dn_step, bytes);
+    }
   return 0;
 }
 

@@ -28,7 +28,21 @@ constexpr int J_RESF = 0, J_XI0 = 8, J_XI1 = 14, J_C0 = 20, J_C1 = 24, J_DD = 28
 #ifndef LIN_MINB
 #define LIN_MINB 6   /* measured on B200: 3 -> 209 us, 4 -> 185, 5 -> 176, 6 -> 170, 8 -> 189 per 672k residuals */
 #endif
-constexpr int LIN_THREADS = 128;
+#ifndef LIN_THREADS_
+#define LIN_THREADS_ 128
+#endif
+constexpr int LIN_THREADS = LIN_THREADS_;
+// Streaming (evict-first) stores for the big per-residual output streams: they are written once per
+// iteration and are larger than what L2 can usefully keep, while the target images that the gathers hit
+// (7 x 4.9 MB per window) should stay L2-resident.
+#ifndef LIN_STREAM_STORES
+#define LIN_STREAM_STORES 1
+#endif
+#if LIN_STREAM_STORES
+#define STJ(ptr, v) __stcs((ptr), (v))
+#else
+#define STJ(ptr, v) (*(ptr) = (v))
+#endif
 constexpr int TOP_THREADS = 128;
 constexpr int TOP_PART = 96;           // 91 accumulators + nres + pad
 constexpr int SC_THREADS = 256;
@@ -116,6 +130,19 @@ struct BADesc {
   int maxres;                // longest residual list of a point (<= HSLAM_MAX_FRAMES)
   // stitch
   StitchArgs S;
+  // host <-> device layout conversion (caller order <-> sorted order) and back-substitution
+  const int* r_s2o;          // sorted residual position -> caller residual id
+  const int* p_s2o;          // sorted point position -> caller point id
+  double* x;                 // (8n+4) solution of the reduced system (uploaded by resubstitute)
+  float* xc;                 // [4]      calibration step, float
+  float* xAd;                // [n*n][8] per-pair adjoint-mapped frame steps (EnergyFunctional.cpp:236-238)
+};
+
+// Per-window byte offsets into the batch staging blocks (one H2D block `up`, one D2H block `dn`);
+// a negative offset means "absent / not requested".
+struct BAIO {
+  long long up_precalc, up_adHTd, up_adH, up_adT, up_fprior, up_fdprior, up_idepth, up_deltaF, up_idz, up_x;
+  long long dn_energy, dn_nres, dn_Hb, dn_newEnergy, dn_newEnergyWO, dn_newState, dn_step;
 };
 
 __device__ __forceinline__ int find_window(const int* __restrict__ prefix, int nwin, int b, int& local) {
@@ -168,12 +195,16 @@ __global__ void __launch_bounds__(LIN_THREADS, LIN_MINB) ba_linearize_kernel(con
   const int k = lb * LIN_THREADS + threadIdx.x;
   const int s = r.rs;
   double energy_ret = 0.0;
-  if (k < r.R && !r.isLin[k]) {
+  // every per-residual input is loaded up front (independent loads, one round trip)
+  const bool valid = k < r.R;
+  const bool lin = valid ? (r.isLin[k] != 0) : true;
+  const int8_t st0 = valid ? r.state_state[k] : (int8_t)HSLAM_RES_OOB;
+  const float old_energy = valid ? r.state_energy[k] : 0.f;
+  const int p = valid ? r.point[k] : 0, pair = valid ? r.pair[k] : 0;
+  if (valid && !lin) {
     float* J = r.J + k;
-    r.newEnergyWO[k] = -1.f;
-    bool oob = (r.state_state[k] == HSLAM_RES_OOB);
-    const float old_energy = r.state_energy[k];
-    const int p = r.point[k], pair = r.pair[k];
+    STJ(r.newEnergyWO + k, -1.f);
+    bool oob = (st0 == HSLAM_RES_OOB);
     const int hostI = pair % W.n, tgtI = pair / W.n;
     float energyLeft = 0.f, wJI2 = 0.f;
     if (!oob) {
@@ -205,7 +236,7 @@ __global__ void __launch_bounds__(LIN_THREADS, LIN_MINB) ba_linearize_kernel(con
       const float Ku = xadd(xmul(u, W.fx), W.cx), Kv = xadd(xmul(v, W.fy), W.cy);
       if (!oob && !(Ku > 1.1f && Kv > 1.1f && Ku < wm3 && Kv < hm3)) oob = true;
       if (!oob) {
-        r.cpt[k] = Ku; r.cpt[s + k] = Kv; r.cpt[2 * s + k] = new_idepth;
+        STJ(r.cpt + k, Ku); STJ(r.cpt + s + k, Kv); STJ(r.cpt + 2 * s + k, new_idepth);
         // OptimizationClasses.cpp:85-121
         float ddx = xmul(xmul(xmul(drescale, xsub(t0[0], xmul(t0[2], u))), W.scale_idepth), W.fx);
         float ddy = xmul(xmul(xmul(drescale, xsub(t0[1], xmul(t0[2], v))), W.scale_idepth), W.fy);
@@ -219,21 +250,17 @@ __global__ void __launch_bounds__(LIN_THREADS, LIN_MINB) ba_linearize_kernel(con
         cx2 = xmul(xadd(cx2, 1.f), W.scale_c); cx3 = xmul(cx3, W.scale_c);
         cy0 = xmul(cy0, W.scale_f); cy1 = xmul(xadd(cy1, v), W.scale_f);
         cy2 = xmul(cy2, W.scale_c); cy3 = xmul(xadd(cy3, 1.f), W.scale_c);
-        J[(J_XI0 + 0) * s] = xmul(new_idepth, W.fx);
-        J[(J_XI0 + 1) * s] = 0.f;
-        J[(J_XI0 + 2) * s] = xmul(xmul(-new_idepth, u), W.fx);
-        J[(J_XI0 + 3) * s] = xmul(xmul(-u, v), W.fx);
-        J[(J_XI0 + 4) * s] = xmul(xadd(1.f, xmul(u, u)), W.fx);
-        J[(J_XI0 + 5) * s] = xmul(-v, W.fx);
-        J[(J_XI1 + 0) * s] = 0.f;
-        J[(J_XI1 + 1) * s] = xmul(new_idepth, W.fy);
-        J[(J_XI1 + 2) * s] = xmul(xmul(-new_idepth, v), W.fy);
-        J[(J_XI1 + 3) * s] = xmul(-xadd(1.f, xmul(v, v)), W.fy);
-        J[(J_XI1 + 4) * s] = xmul(xmul(u, v), W.fy);
-        J[(J_XI1 + 5) * s] = xmul(u, W.fy);
-        J[(J_C0 + 0) * s] = cx0; J[(J_C0 + 1) * s] = cx1; J[(J_C0 + 2) * s] = cx2; J[(J_C0 + 3) * s] = cx3;
-        J[(J_C1 + 0) * s] = cy0; J[(J_C1 + 1) * s] = cy1; J[(J_C1 + 2) * s] = cy2; J[(J_C1 + 3) * s] = cy3;
-        J[J_DD * s] = ddx; J[(J_DD + 1) * s] = ddy;
+        // Jpdxi rows (OptimizationClasses.cpp:109-121); re-formed from (u, v, new_idepth) at takeData time
+        // instead of being kept live across the pattern loop (register pressure)
+#define HS_XI0(i) ((i) == 0 ? xmul(new_idepth, W.fx) : (i) == 1 ? 0.f : (i) == 2 ? xmul(xmul(-new_idepth, u), W.fx) : \
+                   (i) == 3 ? xmul(xmul(-u, v), W.fx) : (i) == 4 ? xmul(xadd(1.f, xmul(u, u)), W.fx) : xmul(-v, W.fx))
+#define HS_XI1(i) ((i) == 0 ? 0.f : (i) == 1 ? xmul(new_idepth, W.fy) : (i) == 2 ? xmul(xmul(-new_idepth, v), W.fy) : \
+                   (i) == 3 ? xmul(-xadd(1.f, xmul(v, v)), W.fy) : (i) == 4 ? xmul(xmul(u, v), W.fy) : xmul(u, W.fy))
+#pragma unroll
+        for (int i = 0; i < 6; ++i) { STJ(J + (J_XI0 + i) * s, HS_XI0(i)); STJ(J + (J_XI1 + i) * s, HS_XI1(i)); }
+        STJ(J + (J_C0 + 0) * s, cx0); STJ(J + (J_C0 + 1) * s, cx1); STJ(J + (J_C0 + 2) * s, cx2); STJ(J + (J_C0 + 3) * s, cx3);
+        STJ(J + (J_C1 + 0) * s, cy0); STJ(J + (J_C1 + 1) * s, cy1); STJ(J + (J_C1 + 2) * s, cy2); STJ(J + (J_C1 + 3) * s, cy3);
+        STJ(J + J_DD * s, ddx); STJ(J + (J_DD + 1) * s, ddy);
         // ---- 8-pixel pattern at the current state, :141-204.  Pass 1: projections + bounds.
         float Kup[8], Kvp[8];
         int n_ok = 8;   // number of leading pattern pixels that are in bounds (the source returns at the first OOB)
@@ -250,7 +277,7 @@ __global__ void __launch_bounds__(LIN_THREADS, LIN_MINB) ba_linearize_kernel(con
         // the source stores projectedTo before it tests the next pixel: pixels [0, n_ok) are written
 #pragma unroll
         for (int idx = 0; idx < 8; ++idx)
-          if (idx < n_ok) { r.pto[(2 * idx) * s + k] = Kup[idx]; r.pto[(2 * idx + 1) * s + k] = Kvp[idx]; }
+          if (idx < n_ok) { STJ(r.pto + (2 * idx) * s + k, Kup[idx]); STJ(r.pto + (2 * idx + 1) * s + k, Kvp[idx]); }
         if (n_ok < 8) {
           oob = true;
           // Jacobian entries of the pixels before the first OOB one are written by the source as well;
@@ -283,12 +310,12 @@ __global__ void __launch_bounds__(LIN_THREADS, LIN_MINB) ba_linearize_kernel(con
             hw = xmul(hw, w);
             float h1 = xmul(hdx, hw), h2 = xmul(hdy, hw);
             float rF = xmul(residual, hw), ja = xmul(drdA, hw);
-            J[(J_RESF + idx) * s] = rF;
-            J[(J_IDX0 + idx) * s] = h1;
-            J[(J_IDX1 + idx) * s] = h2;
+            STJ(J + (J_RESF + idx) * s, rF);
+            STJ(J + (J_IDX0 + idx) * s, h1);
+            STJ(J + (J_IDX1 + idx) * s, h2);
             float jab0 = W.affA < 0.f ? 0.f : ja, jab1 = W.affB < 0.f ? 0.f : hw;
-            J[(J_AB0 + idx) * s] = jab0;
-            J[(J_AB1 + idx) * s] = jab1;
+            STJ(J + (J_AB0 + idx) * s, jab0);
+            STJ(J + (J_AB1 + idx) * s, jab1);
             II00 = xadd(II00, xmul(h1, h1)); II11 = xadd(II11, xmul(h2, h2)); II10 = xadd(II10, xmul(h1, h2));
             AI00 = xadd(AI00, xmul(ja, h1)); AI01 = xadd(AI01, xmul(ja, h2));
             AI10 = xadd(AI10, xmul(hw, h1)); AI11 = xadd(AI11, xmul(hw, h2));
@@ -305,11 +332,35 @@ __global__ void __launch_bounds__(LIN_THREADS, LIN_MINB) ba_linearize_kernel(con
           if (nonfinite) {
             oob = true;
           } else {
-            J[(J_IDX2 + 0) * s] = II00; J[(J_IDX2 + 1) * s] = II10; J[(J_IDX2 + 2) * s] = II10; J[(J_IDX2 + 3) * s] = II11;
-            J[(J_ABIDX + 0) * s] = AI00; J[(J_ABIDX + 1) * s] = AI10; J[(J_ABIDX + 2) * s] = AI01; J[(J_ABIDX + 3) * s] = AI11;
-            J[(J_AB2 + 0) * s] = AA00; J[(J_AB2 + 1) * s] = AA01; J[(J_AB2 + 2) * s] = AA01; J[(J_AB2 + 3) * s] = AA11;
-            J[(J_JIR + 0) * s] = JIr0; J[(J_JIR + 1) * s] = JIr1; J[(J_JABR + 0) * s] = Jabr0; J[(J_JABR + 1) * s] = Jabr1;
-            J[J_RR * s] = rr;
+            STJ(J + (J_IDX2 + 0) * s, II00); STJ(J + (J_IDX2 + 1) * s, II10); STJ(J + (J_IDX2 + 2) * s, II10); STJ(J + (J_IDX2 + 3) * s, II11);
+            STJ(J + (J_ABIDX + 0) * s, AI00); STJ(J + (J_ABIDX + 1) * s, AI10); STJ(J + (J_ABIDX + 2) * s, AI01); STJ(J + (J_ABIDX + 3) * s, AI11);
+            STJ(J + (J_AB2 + 0) * s, AA00); STJ(J + (J_AB2 + 1) * s, AA01); STJ(J + (J_AB2 + 2) * s, AA01); STJ(J + (J_AB2 + 3) * s, AA11);
+            STJ(J + (J_JIR + 0) * s, JIr0); STJ(J + (J_JIR + 1) * s, JIr1); STJ(J + (J_JABR + 0) * s, Jabr0); STJ(J + (J_JABR + 1) * s, Jabr1);
+            STJ(J + J_RR * s, rr);
+            // ---- classification (:221-231) and, when APPLY, applyRes(true)/takeData (:235-256, .h:155-161)
+            // straight from registers
+            STJ(r.newEnergyWO + k, energyLeft);
+            const float th = fmaxf(W.frameEnergyTH[hostI], W.frameEnergyTH[tgtI]);
+            int8_t ns = HSLAM_RES_IN;
+            if (energyLeft > th || wJI2 < 2.f) { energyLeft = th; ns = HSLAM_RES_OUT; }
+            STJ(r.newEnergy + k, energyLeft);
+            energy_ret = (double)energyLeft;
+            r.newState[k] = ns;
+            if (APPLY) {   // the old state cannot be OOB here
+              if (ns == HSLAM_RES_IN) {
+                r.isActive[k] = 1;
+                const float JJ0 = xadd(xmul(II00, ddx), xmul(II10, ddy)), JJ1 = xadd(xmul(II10, ddx), xmul(II11, ddy));
+                float* o = r.JpJdF + k;
+#pragma unroll
+                for (int i = 0; i < 6; ++i) STJ(o + i * s, xadd(xmul(HS_XI0(i), JJ0), xmul(HS_XI1(i), JJ1)));
+                STJ(o + 6 * s, xadd(xmul(AI00, ddx), xmul(AI01, ddy)));
+                STJ(o + 7 * s, xadd(xmul(AI10, ddx), xmul(AI11, ddy)));
+              } else {
+                r.isActive[k] = 0;
+              }
+              r.state_state[k] = ns;
+              r.state_energy[k] = energyLeft;
+            }
           }
         }
       }
@@ -317,15 +368,13 @@ __global__ void __launch_bounds__(LIN_THREADS, LIN_MINB) ba_linearize_kernel(con
     if (oob) {
       r.newState[k] = HSLAM_RES_OOB;
       energy_ret = (double)old_energy;
-    } else {
-      r.newEnergyWO[k] = energyLeft;
-      float th = fmaxf(W.frameEnergyTH[hostI], W.frameEnergyTH[tgtI]);
-      if (energyLeft > th || wJI2 < 2.f) { energyLeft = th; r.newState[k] = HSLAM_RES_OUT; }
-      else r.newState[k] = HSLAM_RES_IN;
-      r.newEnergy[k] = energyLeft;
-      energy_ret = (double)energyLeft;
+      if (APPLY && st0 != HSLAM_RES_OOB) {
+        // went OOB in THIS pass: applyRes copies the newEnergy of its last non-OOB linearisation
+        r.isActive[k] = 0;
+        r.state_state[k] = HSLAM_RES_OOB;
+        r.state_energy[k] = r.newEnergy[k];
+      }
     }
-    if (APPLY) apply_one(r, k);
   }
   // ---- energy: warp tree in fp64, one partial per WARP, no fence and no block barrier: a warp retires
   // as soon as its residuals are done (a __threadfence here made every warp wait for its ~100 Jacobian
@@ -1040,31 +1089,132 @@ __global__ void ba_import_kernel(const T* __restrict__ src, int count, const int
   dst[(size_t)k * dst_stride_elems + dst_offset] = src[sorted2orig[k]];
 }
 
-// EnergyFunctional::resubstituteFPt (EnergyFunctional.cpp:249-274); xAd[n*h+t] uploaded by the host
-__global__ void ba_resub_kernel(BAWin W, BARes r, BAPts pts, const float* __restrict__ xc, const float* __restrict__ xAd) {
-  int p = blockIdx.x * blockDim.x + threadIdx.x;
-  if (p >= pts.P) return;
-  const int s = r.rs, n = W.n;
-  int ngood = 0;
-  for (int i = pts.res_begin[p]; i < pts.res_begin[p + 1]; ++i) if (r.isActive[pts.res_index[i]]) ngood++;
-  if (ngood == 0) { pts.step[p] = 0.f; return; }
-  float b = pts.bdSumF[p];
-  float4 ha = pts.Hcd[0][p], hl = pts.Hcd[1][p];
-  float dot = 0.f;
-  dot = xadd(dot, xmul(xc[0], xadd(ha.x, hl.x))); dot = xadd(dot, xmul(xc[1], xadd(ha.y, hl.y)));
-  dot = xadd(dot, xmul(xc[2], xadd(ha.z, hl.z))); dot = xadd(dot, xmul(xc[3], xadd(ha.w, hl.w)));
-  b = xsub(b, dot);
-  for (int i = pts.res_begin[p]; i < pts.res_begin[p + 1]; ++i) {
-    int k = pts.res_index[i];
-    if (!r.isActive[k]) continue;
-    int pair = r.pair[k], h = pair % n, t = pair / n;
-    const float* xa = xAd + 8 * (n * h + t);
-    float d = 0.f;
+// xAd[n*h+t] = x_h^T adHostF[h,t] + x_t^T adTargetF[h,t] in float, index order (EnergyFunctional.cpp:228-238);
+// one block per window.  The adjoints are the fp64 tables of the window cast to float element by element,
+// exactly like adHostF/adTargetF (EnergyFunctional.cpp:73-74).
+__global__ void __launch_bounds__(256) ba_xad_kernel(const BADesc* __restrict__ descs) {
+  const BADesc& D = descs[blockIdx.x];
+  const int n = D.W.n, N = 8 * n + 4;
+  __shared__ float xF[8 * HSLAM_MAX_FRAMES + 4];
+  for (int i = threadIdx.x; i < N; i += blockDim.x) xF[i] = (float)D.x[i];
+  __syncthreads();
+  if (threadIdx.x < 4) D.xc[threadIdx.x] = xF[threadIdx.x];
+  for (int idx = threadIdx.x; idx < n * n * 8; idx += blockDim.x) {
+    const int c = idx & 7, ht = idx >> 3, h = ht / n, t = ht % n;
+    const double* aH = D.S.adHost + 64 * (size_t)(h + n * t);
+    const double* aT = D.S.adTarget + 64 * (size_t)(h + n * t);
+    float a = 0.f, b = 0.f;
 #pragma unroll
-    for (int j = 0; j < 8; ++j) d = xadd(d, xmul(xa[j], r.JpJdF[j * s + k]));
-    b = xsub(b, d);
+    for (int r = 0; r < 8; ++r) {
+      a = xadd(a, xmul(xF[4 + 8 * h + r], (float)aH[r + 8 * c]));
+      b = xadd(b, xmul(xF[4 + 8 * t + r], (float)aT[r + 8 * c]));
+    }
+    D.xAd[8 * (size_t)(n * h + t) + c] = xadd(a, b);
   }
-  pts.step[p] = xmul(-b, pts.HdiF[p]);
+}
+
+// EnergyFunctional::resubstituteFPt (EnergyFunctional.cpp:249-274).  With `io` the step is also written
+// in CALLER order into the batch's D2H staging block.
+__global__ void __launch_bounds__(128) ba_resub_kernel(const BADesc* __restrict__ descs, const int* __restrict__ prefix,
+                                                       int nwin, const BAIO* __restrict__ io, char* __restrict__ dn) {
+  int lb;
+  const int win = find_window(prefix, nwin, blockIdx.x, lb);
+  const BADesc& D = descs[win];
+  const BARes& r = D.r;
+  const BAPts& pts = D.p;
+  const int p = lb * 128 + threadIdx.x;
+  if (p >= pts.P) return;
+  const int s = r.rs, n = D.W.n;
+  const float* xc = D.xc;
+  const float* xAd = D.xAd;
+  int ngood = 0;
+  const int rb = pts.res_begin[p], re = pts.res_begin[p + 1];
+  for (int i = rb; i < re; ++i) if (r.isActive[pts.res_index[i]]) ngood++;
+  float step = 0.f;
+  if (ngood != 0) {
+    float b = pts.bdSumF[p];
+    float4 ha = pts.Hcd[0][p], hl = pts.Hcd[1][p];
+    float dot = 0.f;
+    dot = xadd(dot, xmul(xc[0], xadd(ha.x, hl.x))); dot = xadd(dot, xmul(xc[1], xadd(ha.y, hl.y)));
+    dot = xadd(dot, xmul(xc[2], xadd(ha.z, hl.z))); dot = xadd(dot, xmul(xc[3], xadd(ha.w, hl.w)));
+    b = xsub(b, dot);
+    for (int i = rb; i < re; ++i) {
+      int k = pts.res_index[i];
+      if (!r.isActive[k]) continue;
+      int pair = r.pair[k], h = pair % n, t = pair / n;
+      const float* xa = xAd + 8 * (n * h + t);
+      float d = 0.f;
+#pragma unroll
+      for (int j = 0; j < 8; ++j) d = xadd(d, xmul(xa[j], r.JpJdF[j * s + k]));
+      b = xsub(b, d);
+    }
+    step = xmul(-b, pts.HdiF[p]);
+  }
+  pts.step[p] = step;
+  if (io && io[win].dn_step >= 0) reinterpret_cast<float*>(dn + io[win].dn_step)[D.p_s2o[p]] = step;
+}
+
+// ---- batched host API: ONE staging block up, ONE down (hslam_ba_batch_step_host) -----------------------
+// Import: window tables are plain copies into the window's own buffers; per-point arrays arrive in caller
+// order and are scattered into the host-sorted point records.  grid = (blocks per window, windows).
+template <class T>
+__device__ __forceinline__ void staged_copy(T* dst, const char* up, long long off, int count, int tid, int stride) {
+  if (off < 0) return;
+  const T* src = reinterpret_cast<const T*>(up + off);
+  for (int i = tid; i < count; i += stride) dst[i] = src[i];
+}
+__global__ void __launch_bounds__(256) ba_batch_import_kernel(const BADesc* __restrict__ descs, const BAIO* __restrict__ io,
+                                                              const char* __restrict__ up) {
+  const BADesc& D = descs[blockIdx.y];
+  const BAIO o = io[blockIdx.y];
+  const int tid = blockIdx.x * blockDim.x + threadIdx.x, stride = gridDim.x * blockDim.x;
+  const int n = D.W.n, nn = n * n;
+  staged_copy(const_cast<float*>(D.W.precalc), up, o.up_precalc, nn * HSLAM_PRECALC_STRIDE, tid, stride);
+  staged_copy(const_cast<float*>(D.W.adHTdeltaF), up, o.up_adHTd, nn * 8, tid, stride);
+  staged_copy(const_cast<double*>(D.S.adHost), up, o.up_adH, nn * 64, tid, stride);
+  staged_copy(const_cast<double*>(D.S.adTarget), up, o.up_adT, nn * 64, tid, stride);
+  staged_copy(const_cast<double*>(D.S.framePrior), up, o.up_fprior, n * 8, tid, stride);
+  staged_copy(const_cast<double*>(D.S.frameDeltaPrior), up, o.up_fdprior, n * 8, tid, stride);
+  staged_copy(D.x, up, o.up_x, 8 * n + 4, tid, stride);
+  const int P = D.p.P;
+  float* uvid = reinterpret_cast<float*>(const_cast<float4*>(D.p.uvid));
+  float* deltaF = const_cast<float*>(D.p.deltaF);
+  const float* s_id = o.up_idepth >= 0 ? reinterpret_cast<const float*>(up + o.up_idepth) : nullptr;
+  const float* s_iz = o.up_idz >= 0 ? reinterpret_cast<const float*>(up + o.up_idz) : nullptr;
+  const float* s_dF = o.up_deltaF >= 0 ? reinterpret_cast<const float*>(up + o.up_deltaF) : nullptr;
+  if (s_id || s_iz || s_dF)
+    for (int p = tid; p < P; p += stride) {
+      const int q = D.p_s2o[p];
+      if (s_id) uvid[4 * (size_t)p + 2] = s_id[q];
+      if (s_iz) uvid[4 * (size_t)p + 3] = s_iz[q];
+      if (s_dF) deltaF[p] = s_dF[q];
+    }
+}
+// Export: per-residual results back to caller order, the stitched systems, counts and energy, all into
+// the window's slice of the D2H staging block.
+__global__ void __launch_bounds__(256) ba_batch_export_kernel(const BADesc* __restrict__ descs, const BAIO* __restrict__ io,
+                                                              char* __restrict__ dn) {
+  const BADesc& D = descs[blockIdx.y];
+  const BAIO o = io[blockIdx.y];
+  const int tid = blockIdx.x * blockDim.x + threadIdx.x, stride = gridDim.x * blockDim.x;
+  const int R = D.r.R;
+  float* oE = o.dn_newEnergy >= 0 ? reinterpret_cast<float*>(dn + o.dn_newEnergy) : nullptr;
+  float* oW = o.dn_newEnergyWO >= 0 ? reinterpret_cast<float*>(dn + o.dn_newEnergyWO) : nullptr;
+  int8_t* oS = o.dn_newState >= 0 ? reinterpret_cast<int8_t*>(dn + o.dn_newState) : nullptr;
+  if (oE || oW || oS)
+    for (int k = tid; k < R; k += stride) {
+      const int q = D.r_s2o[k];
+      if (oE) oE[q] = D.r.newEnergy[k];
+      if (oW) oW[q] = D.r.newEnergyWO[k];
+      if (oS) oS[q] = D.r.newState[k];
+    }
+  if (o.dn_Hb >= 0) {
+    const int N = 8 * D.W.n + 4, cnt = 3 * (N * N + N);
+    double* dst = reinterpret_cast<double*>(dn + o.dn_Hb);
+    for (int i = tid; i < cnt; i += stride) dst[i] = D.S.Hb[i];
+  }
+  if (tid < 2 && o.dn_nres >= 0) reinterpret_cast<int*>(dn + o.dn_nres)[tid] = D.S.nres[tid];
+  if (tid == 0 && o.dn_energy >= 0) *reinterpret_cast<double*>(dn + o.dn_energy) = *D.energy;
 }
 
 }  // namespace hs

@@ -91,6 +91,14 @@ struct hslam_ctx {
   struct ProfRec { int k; cudaEvent_t a, b; };
   std::vector<ProfRec> prof_recs;
   std::vector<cudaEvent_t> prof_pool;
+  // pinned host blocks handed out by hslam_host_alloc (copies to/from them are direct DMA)
+  struct HostBlock { char* p; size_t bytes; };
+  std::vector<HostBlock> host_blocks;
+  bool is_pinned(const void* q, size_t bytes) const {
+    const char* c = (const char*)q;
+    for (const auto& b : host_blocks) if (c >= b.p && c + bytes <= b.p + b.bytes) return true;
+    return false;
+  }
 };
 
 namespace hs {

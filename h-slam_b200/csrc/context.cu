@@ -63,6 +63,7 @@ int hslam_destroy(hslam_ctx* c) {
   cudaStreamSynchronize(c->stream);
   for (auto& r : c->prof_recs) { cudaEventDestroy(r.a); cudaEventDestroy(r.b); }
   for (auto e : c->prof_pool) cudaEventDestroy(e);
+  for (auto& b : c->host_blocks) cudaFreeHost(b.p);
   cudaStreamDestroy(c->stream);
   delete c;
   return 0;
@@ -82,6 +83,30 @@ int hslam_get_stream(hslam_ctx* c, void** s) {
 }
 
 int64_t hslam_launch_count(hslam_ctx* c) { return c ? c->launches : -1; }
+
+int hslam_host_alloc(hslam_ctx* c, size_t bytes, void** out) {
+  HS_ARG(c && out && bytes > 0, "hslam_host_alloc: bad argument");
+  HS_CUDA(cudaSetDevice(c->device));
+  char* p = nullptr;
+  HS_CUDA(cudaMallocHost((void**)&p, bytes));
+  c->host_blocks.push_back({p, bytes});
+  *out = p;
+  return 0;
+}
+
+int hslam_host_free(hslam_ctx* c, void* p) {
+  HS_ARG(c, "hslam_host_free: null context");
+  if (!p) return 0;
+  for (size_t i = 0; i < c->host_blocks.size(); ++i)
+    if (c->host_blocks[i].p == (char*)p) {
+      cudaStreamSynchronize(c->stream);
+      cudaFreeHost(p);
+      c->host_blocks.erase(c->host_blocks.begin() + i);
+      return 0;
+    }
+  hs::set_error("hslam_host_free: pointer was not returned by hslam_host_alloc");
+  return HSLAM_ERR_ARG;
+}
 
 static const char* k_names[HSLAM_K_COUNT] = {"pyramid_level", "trk_eval", "trk_track", "ba_linearize", "ba_apply",
                                              "ba_top", "ba_fold_top", "ba_point_sum", "ba_schur", "ba_fold_sc",

@@ -24,6 +24,7 @@
 #ifndef HSLAM_B200_H
 #define HSLAM_B200_H
 
+#include <stddef.h>
 #include <stdint.h>
 
 #ifdef __cplusplus
@@ -87,6 +88,12 @@ int hslam_synchronize(hslam_ctx* ctx);
 int hslam_get_stream(hslam_ctx* ctx, void** cuda_stream_out);
 /* Number of kernels this context has launched so far (bench.py's gpu_launches). */
 int64_t hslam_launch_count(hslam_ctx* ctx);
+/* Page-locked host memory owned by the context.  Buffers that cross the boundary every iteration
+ * (the Eigen storage behind MatXX H / VecX b, the per-residual state arrays) can be placed here:
+ * copies to and from such memory are direct DMA, any other host pointer is staged through an
+ * internal pinned block and memcpy'd.  Freed by hslam_host_free or hslam_destroy. */
+int hslam_host_alloc(hslam_ctx* ctx, size_t bytes, void** out);
+int hslam_host_free(hslam_ctx* ctx, void* p);
 /* Per-kernel device timing with CUDA events on the context stream (measurement only).
  * enable=1 starts bracketing every launch with a pair of events; hslam_profile_read
  * synchronises, returns for each kernel class its summed duration (ms) and launch count
@@ -310,6 +317,31 @@ typedef struct hslam_ba_batch hslam_ba_batch;
 int hslam_ba_batch_create(hslam_ctx* ctx, hslam_ba* const* windows, int count, hslam_ba_batch** out);
 int hslam_ba_batch_iteration(hslam_ba_batch* batch);
 int hslam_ba_batch_destroy(hslam_ba_batch* batch);
+/* The same GN iteration with HOST buffers, for every window of the batch in one call (the form
+ * System::optimize's loop body takes when the windows' state lives on the host: setPrecalcValues /
+ * setDeltaF results up, linearizeAll + applyRes + accumulate{A,L,SC}F_MT, energies / residual states /
+ * the three stitched systems down; FullSystemOptimize.cpp:380-497, EnergyFunctional.cpp:717-724).
+ * All inputs of all windows travel in ONE host->device copy, all outputs in one device->host copy
+ * (or straight into caller buffers obtained from hslam_host_alloc); the call returns when the outputs
+ * are valid.  io[i] belongs to the i-th window of the batch; null members are skipped. */
+typedef struct hslam_ba_step_io {
+  /* inputs (host pointers, caller order) */
+  const hslam_window* window;      /* tables + scalars, as hslam_ba_set_window (n_frames must not change) */
+  const float* idepth;             /* P */
+  const float* deltaF;             /* P */
+  const float* idepth_zero;        /* P */
+  /* outputs (host pointers, caller order) */
+  double* energy;                  /* 1: stats[0] of linearizeAll */
+  int8_t* newState;                /* R */
+  float* newEnergy;                /* R */
+  float* newEnergyWithOutlier;     /* R */
+  double* Hb;                      /* [H_A|b_A|H_L|b_L|H_SC|b_SC] as hslam_ba_accumulate_all */
+  int32_t* nres2;                  /* {resInA, resInL} */
+} hslam_ba_step_io;
+int hslam_ba_batch_step_host(hslam_ba_batch* batch, const hslam_ba_step_io* io /* one per window */);
+/* EnergyFunctional::resubstituteF_MT for every window of the batch: x[i] = (8n+4) host doubles,
+ * step_out[i] = P host floats (nullable). */
+int hslam_ba_batch_resubstitute_host(hslam_ba_batch* batch, const double* const* x, float* const* step_out);
 /* Copy the device Hb block to the host (after an external all-reduce). */
 int hslam_ba_download_Hb(hslam_ba* ba, double* Hb_out_host);
 /* Sum the stitched [H|b] block across ranks with ONE ncclAllReduce(sum, fp64)

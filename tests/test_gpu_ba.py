@@ -247,3 +247,49 @@ def test_async_calls_match_sync(ctx, capi, synth, window_small):
     a.close(); b.close()
     for f in frames:
         f.close()
+
+
+@pytest.mark.parametrize("pinned", [True, False])
+def test_batch_step_host_matches_single_window_calls(ctx, capi, synth, pinned):
+    """hslam_ba_batch_step_host / _resubstitute_host (one staging block up, one down) == the per-window
+    host calls (set_window, update_points, linearize, applyRes, accumulate_all, resubstitute), bit for bit,
+    with page-locked (direct DMA) and with pageable (staged) caller buffers."""
+    kf = synth.render_keyframes(320, 240, 5, seed=78)
+    wins = [synth.make_window(points_per_frame=90 + 40 * i, seed=400 + i, keyframes=kf, frac_linearized=0.2 * i)[0] for i in range(3)]
+    frames = [capi.Frame(ctx, im, 1) for im in kf.images]
+    singles, batched = [], []
+    for w in wins:
+        a = capi.EnergyFunctional(ctx); a.set_window(w, frames); a.set_topology(w); singles.append(a)
+        b = capi.EnergyFunctional(ctx); b.set_window(w, frames); b.set_topology(w); batched.append(b)
+    batch = capi.EnergyFunctionalBatch(ctx, batched)
+    io = batch.make_io(wins, [frames] * len(wins), pinned=pinned)
+    rng = np.random.default_rng(9)
+    for it in range(2):
+        # new point state every iteration, through the io block's input arrays
+        for w, (ws, ka, inp) in zip(wins, io["keep"]):
+            inp["idepth"][:] = (w.idepth * np.float32(1.0 + 0.001 * it)).astype(np.float32)
+            inp["deltaF"][:] = inp["idepth"] - w.idepth_zero
+        outs = batch.step_host(io)
+        xs = [rng.normal(0, 1e-3, 8 * w.n + 4) for w in wins]
+        steps = batch.resubstitute_host(io, xs)
+        for a, w, o, (ws, ka, inp), x, st in zip(singles, wins, outs, io["keep"], xs, steps):
+            a.set_window(w, frames)
+            a.update_points(idepth=inp["idepth"], deltaF=inp["deltaF"])
+            lin = a.linearizeAll(False, outputs="states"); a.applyRes()
+            sys3 = a.accumulate_all()
+            assert lin["energy"] == o["energy"][0]
+            assert np.array_equal(lin["newState"], o["newState"])
+            assert np.array_equal(lin["newEnergy"], o["newEnergy"])
+            assert np.array_equal(lin["newEnergyWithOutlier"], o["newEnergyWithOutlier"])
+            assert (a.resInA, a.resInL) == (int(o["nres2"][0]), int(o["nres2"][1]))
+            N = a.N; per = N * N + N
+            for s3, (H, b) in enumerate(sys3):
+                blk = o["Hb"][s3 * per:(s3 + 1) * per]
+                assert np.array_equal(H, blk[:N * N].reshape(N, N).T) and np.array_equal(b, blk[N * N:])
+            assert np.array_equal(a.resubstituteF_MT(x), st)
+            assert np.abs(st).max() > 0
+    batch.close()
+    for e in singles + batched:
+        e.close()
+    for f in frames:
+        f.close()
