@@ -422,6 +422,14 @@ class EnergyFunctional:
             p.value, p.done = p.fn(), True
         self._pendings, self._alive = [], []
 
+    def set_parallelism(self, target_blocks):
+        _chk(self.L.hslam_ba_set_parallelism(self.h, C.c_int(int(target_blocks))))
+
+    def get_parallelism(self):
+        v = C.c_int(0)
+        _chk(self.L.hslam_ba_get_parallelism(self.h, C.byref(v)))
+        return v.value
+
     def set_add_priors(self, flag):
         _chk(self.L.hslam_ba_set_add_priors(self.h, C.c_int(int(flag))))
 

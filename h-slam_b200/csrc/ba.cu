@@ -45,7 +45,7 @@ struct hslam_ba {
   // points
   DevBuf<float4> d_uvid, d_color, d_weights, d_Hcd[2];
   DevBuf<float> d_priorF, d_deltaF, d_HdiF, d_bdSumF, d_idh, d_Hdd[2], d_bd[2], d_step;
-  DevBuf<int> d_phost, d_res_begin, d_res_index;
+  DevBuf<int> d_phost, d_res_begin, d_res_index, d_slot;
   std::vector<int> p_sorted2orig, p_orig2sorted;
   std::vector<float4> h_uvid;
   // residuals
@@ -70,6 +70,8 @@ struct hslam_ba {
   DevBuf<unsigned int> d_host_ticket;
   int n_ptchunks = 0;
   int maxres = 1;
+  int target_blocks = 0;                 // blocks per stage this window should fill (0 = 2 x SM count)
+  std::vector<int> h_pairBegin, h_hostBegin;   // kept for re-chunking (hslam_ba_set_parallelism)
   DevBuf<double> d_accTop, d_G, d_Hb, d_epart, d_energy;
   DevBuf<int> d_nres;          // [2]
   DevBuf<unsigned int> d_ticket;
@@ -188,7 +190,7 @@ static void fill_desc(hslam_ba* ba) {
   BAPts& p = D.p;
   p.P = ba->P; p.uvid = ba->d_uvid.p; p.color = ba->d_color.p; p.weights = ba->d_weights.p;
   p.priorF = ba->d_priorF.p; p.deltaF = ba->d_deltaF.p; p.host = ba->d_phost.p;
-  p.res_begin = ba->d_res_begin.p; p.res_index = ba->d_res_index.p;
+  p.res_begin = ba->d_res_begin.p; p.res_index = ba->d_res_index.p; p.slot = ba->d_slot.p;
   p.HdiF = ba->d_HdiF.p; p.bdSumF = ba->d_bdSumF.p; p.idepth_hessian = ba->d_idh.p;
   for (int m = 0; m < 2; ++m) { p.Hdd[m] = ba->d_Hdd[m].p; p.bd[m] = ba->d_bd[m].p; p.Hcd[m] = ba->d_Hcd[m].p; }
   p.step = ba->d_step.p;
@@ -214,6 +216,61 @@ static int sync_desc(hslam_ba* ba) {
   TRY(ba->d_desc.ensure(1));
   TRY(upload(ba, ba->d_desc.p, &ba->hdesc, 1));
   ba->desc_uploaded = ba->desc_version;
+  return 0;
+}
+
+// Chunk tables of the top-Hessian and Schur kernels.  A chunk is the unit one block reduces into ONE fp32
+// partial; the partials of a pair / host are folded in chunk order into fp64.  The target is ~2 waves of
+// blocks over the SMs for a window that runs alone; a batch of windows shares the SMs, so
+// hslam_ba_batch_create asks every member for proportionally fewer, larger chunks (fewer partials to
+// write and fold, fewer block-level reductions).
+static int build_chunks(hslam_ba* ba) {
+  hslam_ctx* ctx = ba->ctx;
+  const int n = ba->n, nn = n * n, R = ba->R, P = ba->P;
+  const std::vector<int>& pairBegin = ba->h_pairBegin;
+  const std::vector<int>& hostBegin = ba->h_hostBegin;
+  const int target_blocks = ba->target_blocks > 0 ? ba->target_blocks : 2 * ctx->sm_count;
+  {
+    int chunk = ((R + target_blocks - 1) / target_blocks + TOP_THREADS - 1) / TOP_THREADS * TOP_THREADS;
+    if (chunk < TOP_THREADS) chunk = TOP_THREADS;
+    std::vector<TopChunk> ch;
+    std::vector<int> pcb(2 * nn + 1, 0);
+    for (int mode = 0; mode < 2; ++mode) {
+      for (int k = 0; k < nn; ++k) {
+        pcb[mode * nn + k] = (int)ch.size();
+        for (int s0 = pairBegin[k]; s0 < pairBegin[k + 1]; s0 += chunk)
+          ch.push_back(TopChunk{k, s0, std::min(chunk, pairBegin[k + 1] - s0), mode});
+      }
+      ba->n_topchunks[mode] = (int)ch.size() - (mode ? ba->n_topchunks[0] : 0);
+    }
+    pcb[2 * nn] = (int)ch.size();
+    TRY(ba->d_topchunks.ensure(ch.size() + 1)); TRY(ba->d_pair_chunk_begin.ensure(pcb.size()));
+    TRY(ba->d_toppartial.ensure((ch.size() + 1) * TOP_PART));
+    TRY(ba->d_pair_ticket.ensure(2 * nn + 1));
+    HS_CUDA(cudaMemsetAsync(ba->d_pair_ticket.p, 0, (2 * nn + 1) * sizeof(unsigned int), ctx->stream));
+    TRY(upload(ba, ba->d_topchunks.p, ch.data(), ch.size())); TRY(upload(ba, ba->d_pair_chunk_begin.p, pcb.data(), pcb.size()));
+    // pairs without any chunk are never folded: their accumulators must read as zero
+    HS_CUDA(cudaMemsetAsync(ba->d_accTop.p, 0, 2 * (size_t)nn * TOP_PART * sizeof(double), ctx->stream));
+  }
+  {
+    int chunk = ((P + target_blocks - 1) / target_blocks + SC_PTS - 1) / SC_PTS * SC_PTS;
+    if (chunk < SC_PTS) chunk = SC_PTS;
+    std::vector<PtChunk> ch;
+    std::vector<int> hcb(n + 1, 0);
+    for (int h = 0; h < n; ++h) {
+      hcb[h] = (int)ch.size();
+      for (int s0 = hostBegin[h]; s0 < hostBegin[h + 1]; s0 += chunk)
+        ch.push_back(PtChunk{h, s0, std::min(chunk, hostBegin[h + 1] - s0), 0});
+    }
+    hcb[n] = (int)ch.size();
+    ba->n_ptchunks = (int)ch.size();
+    TRY(ba->d_ptchunks.ensure(ch.size() + 1)); TRY(ba->d_host_chunk_begin.ensure(hcb.size()));
+    TRY(ba->d_scpartial.ensure((ch.size() + 1) * (size_t)ba->LD * ba->LD));
+    TRY(ba->d_host_ticket.ensure(n + 1));
+    HS_CUDA(cudaMemsetAsync(ba->d_host_ticket.p, 0, (n + 1) * sizeof(unsigned int), ctx->stream));
+    TRY(upload(ba, ba->d_ptchunks.p, ch.data(), ch.size())); TRY(upload(ba, ba->d_host_chunk_begin.p, hcb.data(), hcb.size()));
+    HS_CUDA(cudaMemsetAsync(ba->d_G.p, 0, (size_t)n * ba->LD * ba->LD * sizeof(double), ctx->stream));
+  }
   return 0;
 }
 
@@ -245,7 +302,7 @@ int hslam_ba_destroy(hslam_ba* ba) {
   ba->d_priorF.release(); ba->d_deltaF.release(); ba->d_HdiF.release(); ba->d_bdSumF.release(); ba->d_idh.release();
   for (int m = 0; m < 2; ++m) { ba->d_Hdd[m].release(); ba->d_bd[m].release(); ba->d_Hcd[m].release(); ba->d_ptc[m].release(); }
   ba->d_accTop.release();
-  ba->d_step.release(); ba->d_phost.release(); ba->d_res_begin.release(); ba->d_res_index.release();
+  ba->d_step.release(); ba->d_phost.release(); ba->d_res_begin.release(); ba->d_res_index.release(); ba->d_slot.release();
   ba->d_rpoint.release(); ba->d_rpair.release(); ba->d_state.release(); ba->d_newState.release();
   ba->d_isLin.release(); ba->d_isActive.release(); ba->d_senergy.release(); ba->d_newEnergy.release();
   ba->d_newEnergyWO.release(); ba->d_J.release(); ba->d_JpJdF.release(); ba->d_rtz.release(); ba->d_cpt.release();
@@ -270,6 +327,24 @@ int hslam_ba_wait(hslam_ba* ba) {
   HS_CUDA(cudaSetDevice(ba->ctx->device));
   ba->async_mode = false;
   return ba_flush(ba);
+}
+
+int hslam_ba_set_parallelism(hslam_ba* ba, int target_blocks) {
+  HS_ARG(ba && target_blocks >= 0, "hslam_ba_set_parallelism: bad argument");
+  if (ba->target_blocks == target_blocks) return 0;
+  ba->target_blocks = target_blocks;
+  if (!ba->have_topology) return 0;
+  HS_CUDA(cudaSetDevice(ba->ctx->device));
+  TRY(ba_flush(ba));
+  TRY(build_chunks(ba));
+  fill_desc(ba);
+  return ba_flush(ba);
+}
+
+int hslam_ba_get_parallelism(hslam_ba* ba, int* target_blocks_out) {
+  HS_ARG(ba && target_blocks_out, "hslam_ba_get_parallelism: null");
+  *target_blocks_out = ba->target_blocks;
+  return 0;
 }
 
 int hslam_ba_set_add_priors(hslam_ba* ba, int add) {
@@ -342,6 +417,7 @@ int hslam_ba_set_topology(hslam_ba* ba, const hslam_point_soa* pt, const hslam_r
   ba->maxres = 1;
   for (int p = 0; p < P; ++p) ba->maxres = std::max(ba->maxres, pt->res_begin[p + 1] - pt->res_begin[p]);
   HS_ARG(ba->maxres <= HSLAM_MAX_FRAMES, "hslam_ba_set_topology: a point has more residuals than HSLAM_MAX_FRAMES");
+  HS_ARG(R < (1 << 26), "hslam_ba_set_topology: more than 2^26 residuals in one window");
   TRY(ba_flush(ba));
   // ---- points sorted by host (stable counting sort)
   std::vector<int> hostCount(n + 1, 0);
@@ -413,6 +489,15 @@ int hslam_ba_set_topology(hslam_ba* ba, const hslam_point_soa* pt, const hslam_r
       for (int i = pt->res_begin[p]; i < pt->res_begin[p + 1]; ++i) ri[pos++] = ba->r_orig2sorted[pt->res_index[i]];
     }
     rb[P] = pos;
+    // slot table of the Schur kernel: sorted residual position and target of every (point, slot)
+    std::vector<int> slot((size_t)P * ba->maxres + 1, -1);
+    for (int sp = 0; sp < P; ++sp) {
+      int p = ba->p_sorted2orig[sp];
+      for (int i = pt->res_begin[p], j = 0; i < pt->res_begin[p + 1]; ++i, ++j)
+        slot[(size_t)sp * ba->maxres + j] = ba->r_orig2sorted[pt->res_index[i]] | (rs->target_idx[pt->res_index[i]] << 26);
+    }
+    TRY(ba->d_slot.ensure(slot.size()));
+    TRY(upload(ba, ba->d_slot.p, slot.data(), slot.size()));
     ba->h_uvid = uvid;
     TRY(upload(ba, ba->d_uvid.p, uvid.data(), P)); TRY(upload(ba, ba->d_color.p, col.data(), 2 * (size_t)P));
     TRY(upload(ba, ba->d_weights.p, wgt.data(), 2 * (size_t)P)); TRY(upload(ba, ba->d_priorF.p, prior.data(), P));
@@ -455,50 +540,8 @@ int hslam_ba_set_topology(hslam_ba* ba, const hslam_point_soa* pt, const hslam_r
   HS_CUDA(cudaMemsetAsync(ba->d_HdiF.p, 0, (P + 1) * sizeof(float), ctx->stream));
   HS_CUDA(cudaMemsetAsync(ba->d_bdSumF.p, 0, (P + 1) * sizeof(float), ctx->stream));
   HS_CUDA(cudaMemsetAsync(ba->d_idh.p, 0, (P + 1) * sizeof(float), ctx->stream));
-  // ---- chunk tables.  Target ~2 waves of blocks over the SMs, chunk a multiple of the block size.
-  {
-    int target_blocks = 2 * ctx->sm_count;
-    int chunk = ((R + target_blocks - 1) / target_blocks + TOP_THREADS - 1) / TOP_THREADS * TOP_THREADS;
-    if (chunk < TOP_THREADS) chunk = TOP_THREADS;
-    std::vector<TopChunk> ch;
-    std::vector<int> pcb(2 * nn + 1, 0);
-    for (int mode = 0; mode < 2; ++mode) {
-      for (int k = 0; k < nn; ++k) {
-        pcb[mode * nn + k] = (int)ch.size();
-        for (int s0 = pairBegin[k]; s0 < pairBegin[k + 1]; s0 += chunk)
-          ch.push_back(TopChunk{k, s0, std::min(chunk, pairBegin[k + 1] - s0), mode});
-      }
-      ba->n_topchunks[mode] = (int)ch.size() - (mode ? ba->n_topchunks[0] : 0);
-    }
-    pcb[2 * nn] = (int)ch.size();
-    TRY(ba->d_topchunks.ensure(ch.size() + 1)); TRY(ba->d_pair_chunk_begin.ensure(pcb.size()));
-    TRY(ba->d_toppartial.ensure((ch.size() + 1) * TOP_PART));
-    TRY(ba->d_pair_ticket.ensure(2 * nn + 1));
-    HS_CUDA(cudaMemsetAsync(ba->d_pair_ticket.p, 0, (2 * nn + 1) * sizeof(unsigned int), ctx->stream));
-    TRY(upload(ba, ba->d_topchunks.p, ch.data(), ch.size())); TRY(upload(ba, ba->d_pair_chunk_begin.p, pcb.data(), pcb.size()));
-    // pairs without any chunk are never folded: their accumulators must read as zero
-    HS_CUDA(cudaMemsetAsync(ba->d_accTop.p, 0, 2 * (size_t)nn * TOP_PART * sizeof(double), ctx->stream));
-  }
-  {
-    int target_blocks = 2 * ctx->sm_count;
-    int chunk = ((P + target_blocks - 1) / target_blocks + SC_PTS - 1) / SC_PTS * SC_PTS;
-    if (chunk < SC_PTS) chunk = SC_PTS;
-    std::vector<PtChunk> ch;
-    std::vector<int> hcb(n + 1, 0);
-    for (int h = 0; h < n; ++h) {
-      hcb[h] = (int)ch.size();
-      for (int s0 = hostBegin[h]; s0 < hostBegin[h + 1]; s0 += chunk)
-        ch.push_back(PtChunk{h, s0, std::min(chunk, hostBegin[h + 1] - s0), 0});
-    }
-    hcb[n] = (int)ch.size();
-    ba->n_ptchunks = (int)ch.size();
-    TRY(ba->d_ptchunks.ensure(ch.size() + 1)); TRY(ba->d_host_chunk_begin.ensure(hcb.size()));
-    TRY(ba->d_scpartial.ensure((ch.size() + 1) * (size_t)ba->LD * ba->LD));
-    TRY(ba->d_host_ticket.ensure(n + 1));
-    HS_CUDA(cudaMemsetAsync(ba->d_host_ticket.p, 0, (n + 1) * sizeof(unsigned int), ctx->stream));
-    TRY(upload(ba, ba->d_ptchunks.p, ch.data(), ch.size())); TRY(upload(ba, ba->d_host_chunk_begin.p, hcb.data(), hcb.size()));
-    HS_CUDA(cudaMemsetAsync(ba->d_G.p, 0, (size_t)n * ba->LD * ba->LD * sizeof(double), ctx->stream));
-  }
+  ba->h_pairBegin = pairBegin; ba->h_hostBegin = hostBegin;
+  TRY(build_chunks(ba));
   TRY(ba->d_epart.ensure((size_t)(ba->rs / 32 + 2 * LIN_THREADS / 32)));   // one energy partial per warp
   ba->have_topology = true;
   fill_desc(ba);
@@ -558,14 +601,20 @@ static int launch_top(hslam_ba* ba, int modes) {
   return 0;
 }
 
-static size_t schur_smem(int LD, int maxres) { return (size_t)(SC_PTS * LD + SC_PTS + SC_PTS * maxres * 8) * sizeof(float); }
+static size_t schur_smem(int LD, int maxres) { return sc_smem_floats(LD, maxres) * sizeof(float); }
+static int schur_maxt(int LD) { int NT = LD / 4; return NT * (NT + 1) / 2 <= SC_THREADS ? 1 : 3; }
 static int schur_attr(size_t smem) {
   static size_t configured = 48 * 1024;
   if (smem > configured) {
-    HS_CUDA(cudaFuncSetAttribute(ba_schur_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    HS_CUDA(cudaFuncSetAttribute(ba_schur_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    HS_CUDA(cudaFuncSetAttribute(ba_schur_kernel<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     configured = smem;
   }
   return 0;
+}
+static void schur_launch(int maxt, int blocks, size_t smem, cudaStream_t st, const BADesc* d, const int* pf, int n) {
+  if (maxt == 1) ba_schur_kernel<1><<<blocks, SC_THREADS, smem, st>>>(d, pf, n);
+  else ba_schur_kernel<3><<<blocks, SC_THREADS, smem, st>>>(d, pf, n);
 }
 
 static int launch_schur(hslam_ba* ba) {
@@ -574,7 +623,7 @@ static int launch_schur(hslam_ba* ba) {
   size_t smem = schur_smem(ba->LD, ba->maxres);
   TRY(schur_attr(smem));
   if (ba->n_ptchunks > 0)
-    HS_LAUNCH(ctx, HSLAM_K_BA_SCHUR, (ba_schur_kernel<<<ba->n_ptchunks, SC_THREADS, smem, ctx->stream>>>(ba->d_desc.p, nullptr, 1)));
+    HS_LAUNCH(ctx, HSLAM_K_BA_SCHUR, schur_launch(schur_maxt(ba->LD), ba->n_ptchunks, smem, ctx->stream, ba->d_desc.p, nullptr, 1));
   HS_LAUNCH(ctx, HSLAM_K_BA_FOLD_SC, (ba_fold_sc_kernel<<<ba->n * ((ba->LD * ba->LD + 255) / 256), 256, 0, ctx->stream>>>(ba->d_desc.p, nullptr, 1)));
   HS_CUDA(cudaGetLastError());
   return 0;
@@ -794,6 +843,7 @@ struct hslam_ba_batch {
   cudaEvent_t copied = nullptr;
   int blocks[6] = {0, 0, 0, 0, 0, 0};
   size_t smem = 0;
+  int maxt = 1;
   // host API staging: one pinned block up, one down, their device twins, and the per-window offset table
   char* h_up = nullptr; char* h_dn = nullptr;
   size_t h_up_cap = 0, h_dn_cap = 0;
@@ -815,7 +865,7 @@ static int batch_refresh(hslam_ba_batch* B) {
   HS_CUDA(cudaEventSynchronize(B->copied));
   int* pf[NPF];
   for (int k = 0; k < NPF; ++k) { pf[k] = B->h_prefix + k * (n + 1); pf[k][0] = 0; }
-  B->smem = 0;
+  B->smem = 0; B->maxt = 1;
   for (int i = 0; i < n; ++i) {
     hslam_ba* ba = B->items[i];
     B->h_descs[i] = ba->hdesc;
@@ -829,6 +879,7 @@ static int batch_refresh(hslam_ba_batch* B) {
     pf[4][i + 1] = pf[4][i] + ba->n * ((ba->LD * ba->LD + 255) / 256);
     pf[5][i + 1] = pf[5][i] + (ba->P + 127) / 128;
     B->smem = std::max(B->smem, schur_smem(ba->LD, ba->maxres));
+    B->maxt = std::max(B->maxt, schur_maxt(ba->LD));
   }
   for (int k = 0; k < NPF; ++k) B->blocks[k] = pf[k][n];
   HS_CUDA(cudaMemcpyAsync(B->d_descs.p, B->h_descs, n * sizeof(BADesc), cudaMemcpyHostToDevice, B->ctx->stream));
@@ -848,6 +899,9 @@ int hslam_ba_batch_create(hslam_ctx* ctx, hslam_ba* const* items, int count, hsl
     HS_ARG(items[i] && items[i]->ctx == ctx, "hslam_ba_batch_create: window missing or from another context");
     B->items.push_back(items[i]);
   }
+  // the members share the SMs: fewer, larger chunks per window (~3 waves of blocks for the whole batch)
+  for (int i = 0; i < count; ++i)
+    if (items[i]->target_blocks == 0) TRY(hslam_ba_set_parallelism(items[i], std::max(16, 3 * ctx->sm_count / count)));
   B->versions.assign(count, 0);
   TRY(B->d_descs.ensure(count));
   TRY(B->d_prefix.ensure(NPF * (size_t)(count + 1)));
@@ -874,16 +928,22 @@ int hslam_ba_batch_destroy(hslam_ba_batch* B) {
 }
 
 // One GN iteration's hot path for EVERY window of the batch: five launches in total.
-static int batch_enqueue_iteration(hslam_ba_batch* B) {
+static int batch_enqueue_linearize(hslam_ba_batch* B) {
+  hslam_ctx* ctx = B->ctx;
+  const int n = (int)B->items.size();
+  HS_LAUNCH(ctx, HSLAM_K_BA_LINEARIZE, (ba_linearize_kernel<true><<<B->blocks[0], LIN_THREADS, 0, ctx->stream>>>(B->d_descs.p, B->d_prefix.p, n)));
+  HS_CUDA(cudaGetLastError());
+  return 0;
+}
+static int batch_enqueue_accumulate(hslam_ba_batch* B) {
   hslam_ctx* ctx = B->ctx;
   const int n = (int)B->items.size();
   const int* pf = B->d_prefix.p;
   TRY(schur_attr(B->smem));
-  HS_LAUNCH(ctx, HSLAM_K_BA_LINEARIZE, (ba_linearize_kernel<true><<<B->blocks[0], LIN_THREADS, 0, ctx->stream>>>(B->d_descs.p, pf, n)));
   if (B->blocks[1] > 0)
     HS_LAUNCH(ctx, HSLAM_K_BA_TOP, (ba_top_kernel<<<B->blocks[1], 2 * TOP_THREADS, 0, ctx->stream>>>(B->d_descs.p, pf + (n + 1), n, 0)));
   if (B->blocks[2] > 0)
-    HS_LAUNCH(ctx, HSLAM_K_BA_SCHUR, (ba_schur_kernel<<<B->blocks[2], SC_THREADS, B->smem, ctx->stream>>>(B->d_descs.p, pf + 2 * (n + 1), n)));
+    HS_LAUNCH(ctx, HSLAM_K_BA_SCHUR, schur_launch(B->maxt, B->blocks[2], B->smem, ctx->stream, B->d_descs.p, pf + 2 * (n + 1), n));
   HS_LAUNCH(ctx, HSLAM_K_BA_FOLD_SC, (ba_fold_sc_kernel<<<B->blocks[4], 256, 0, ctx->stream>>>(B->d_descs.p, pf + 4 * (n + 1), n)));
   HS_LAUNCH(ctx, HSLAM_K_BA_STITCH, (ba_stitch_kernel<<<B->blocks[3], ST_THREADS, 0, ctx->stream>>>(B->d_descs.p, pf + 3 * (n + 1), n, 0, 3, 1)));
   HS_CUDA(cudaGetLastError());
@@ -894,7 +954,8 @@ int hslam_ba_batch_iteration(hslam_ba_batch* B) {
   HS_ARG(B, "hslam_ba_batch_iteration: null");
   HS_CUDA(cudaSetDevice(B->ctx->device));
   TRY(batch_refresh(B));
-  return batch_enqueue_iteration(B);
+  TRY(batch_enqueue_linearize(B));
+  return batch_enqueue_accumulate(B);
 }
 
 // ---- host-buffer API of a batch: one staging block up, one down per call ------------------------------
@@ -973,6 +1034,7 @@ int hslam_ba_batch_step_host(hslam_ba_batch* B, const hslam_ba_step_io* io) {
   TRY(pinned_ensure(&B->h_up, &B->h_up_cap, up + io_bytes));
   TRY(B->d_up.ensure(up + io_bytes));
   TRY(B->d_dn.ensure(std::max(dn, (size_t)256)));
+  TRY(pinned_ensure(&B->h_dn, &B->h_dn_cap, std::max(dn, (size_t)256)));   // staging for pageable caller buffers
   // ---- pack: [BAIO table][window 0 tables + point arrays][window 1 ...]
   memcpy(B->h_up + up, B->io.data(), n * sizeof(BAIO));
   for (int i = 0; i < n; ++i) {
@@ -1000,39 +1062,53 @@ int hslam_ba_batch_step_host(hslam_ba_batch* B, const hslam_ba_step_io* io) {
     dim3 grid((unsigned)std::max(1, std::min(64, (maxP + 255) / 256)), (unsigned)n);
     HS_LAUNCH(ctx, HSLAM_K_BA_EXPORT, (ba_batch_import_kernel<<<grid, 256, 0, ctx->stream>>>(B->d_descs.p, d_io, B->d_up.p)));
   }
-  TRY(batch_enqueue_iteration(B));
-  if (dn > 0) {
-    dim3 grid((unsigned)std::max(1, std::min(128, (maxR + 255) / 256)), (unsigned)n);
-    HS_LAUNCH(ctx, HSLAM_K_BA_EXPORT, (ba_batch_export_kernel<<<grid, 256, 0, ctx->stream>>>(B->d_descs.p, d_io, B->d_dn.p)));
-    HS_CUDA(cudaGetLastError());
-  }
-  // ---- results: straight into the caller's buffers where they are pinned (hslam_host_alloc), else one
-  // staged copy + memcpy after the synchronisation
+  // ---- results: straight into the caller's buffers where they are pinned (hslam_host_alloc), else through
+  // the pinned block + memcpy after the synchronisation.  The per-residual arrays are final after the
+  // linearise kernel: they are exported and copied on the side stream WHILE the accumulate kernels run.
   struct Out { void* dst; long long off; size_t bytes; };
   std::vector<Out> staged;
-  auto emit = [&](void* dst, long long off, size_t bytes) -> int {
+  auto emit = [&](cudaStream_t st, void* dst, long long off, size_t bytes) -> int {
     if (!dst || off < 0 || bytes == 0) return 0;
     if (ctx->is_pinned(dst, bytes)) {
-      HS_CUDA(cudaMemcpyAsync(dst, B->d_dn.p + off, bytes, cudaMemcpyDeviceToHost, ctx->stream));
+      HS_CUDA(cudaMemcpyAsync(dst, B->d_dn.p + off, bytes, cudaMemcpyDeviceToHost, st));
     } else {
+      HS_CUDA(cudaMemcpyAsync(B->h_dn + off, B->d_dn.p + off, bytes, cudaMemcpyDeviceToHost, st));
       staged.push_back({dst, off, bytes});
     }
     return 0;
   };
+  TRY(batch_enqueue_linearize(B));
+  bool any_res = false, any_sys = false;
   for (int i = 0; i < n; ++i) {
-    hslam_ba* ba = B->items[i];
-    const hslam_ba_step_io& o = io[i];
-    const BAIO& L = B->io[i];
-    const size_t R = ba->R, N = ba->N;
-    TRY(emit(o.energy, L.dn_energy, 8)); TRY(emit(o.nres2, L.dn_nres, 8));
-    TRY(emit(o.Hb, L.dn_Hb, 3 * (N * N + N) * 8));
-    TRY(emit(o.newEnergy, L.dn_newEnergy, R * 4)); TRY(emit(o.newEnergyWithOutlier, L.dn_newEnergyWO, R * 4));
-    TRY(emit(o.newState, L.dn_newState, R));
+    any_res |= io[i].newEnergy || io[i].newEnergyWithOutlier || io[i].newState;
+    any_sys |= io[i].Hb || io[i].nres2 || io[i].energy;
   }
-  if (!staged.empty()) {
-    TRY(pinned_ensure(&B->h_dn, &B->h_dn_cap, dn));
-    HS_CUDA(cudaMemcpyAsync(B->h_dn, B->d_dn.p, dn, cudaMemcpyDeviceToHost, ctx->stream));
+  if (any_res) {
+    HS_CUDA(cudaEventRecord(ctx->ev_fork, ctx->stream));
+    HS_CUDA(cudaStreamWaitEvent(ctx->side, ctx->ev_fork, 0));
+    dim3 grid((unsigned)std::max(1, std::min(128, (maxR + 255) / 256)), (unsigned)n);
+    ctx->launches++;   // side stream: counted, not event-timed
+    ba_batch_export_kernel<<<grid, 256, 0, ctx->side>>>(B->d_descs.p, d_io, B->d_dn.p, 1);
+    HS_CUDA(cudaGetLastError());
+    for (int i = 0; i < n; ++i) {
+      const size_t R = B->items[i]->R;
+      TRY(emit(ctx->side, io[i].newEnergy, B->io[i].dn_newEnergy, R * 4));
+      TRY(emit(ctx->side, io[i].newEnergyWithOutlier, B->io[i].dn_newEnergyWO, R * 4));
+      TRY(emit(ctx->side, io[i].newState, B->io[i].dn_newState, R));
+    }
+    HS_CUDA(cudaEventRecord(ctx->ev_join, ctx->side));
   }
+  TRY(batch_enqueue_accumulate(B));
+  if (any_sys) {
+    HS_LAUNCH(ctx, HSLAM_K_BA_EXPORT, (ba_batch_export_kernel<<<dim3(2, (unsigned)n), 256, 0, ctx->stream>>>(B->d_descs.p, d_io, B->d_dn.p, 2)));
+    HS_CUDA(cudaGetLastError());
+    for (int i = 0; i < n; ++i) {
+      const size_t N = B->items[i]->N;
+      TRY(emit(ctx->stream, io[i].energy, B->io[i].dn_energy, 8)); TRY(emit(ctx->stream, io[i].nres2, B->io[i].dn_nres, 8));
+      TRY(emit(ctx->stream, io[i].Hb, B->io[i].dn_Hb, 3 * (N * N + N) * 8));
+    }
+  }
+  if (any_res) HS_CUDA(cudaStreamWaitEvent(ctx->stream, ctx->ev_join, 0));   // the context stream stays the one to wait on
   HS_CUDA(cudaStreamSynchronize(ctx->stream));
   for (const Out& s : staged) memcpy(s.dst, B->h_dn + s.off, s.bytes);
   return 0;

@@ -92,6 +92,7 @@ struct BAPts {               // per-point SoA, sorted by host
   const int* host;
   const int* res_begin;      // CSR over sorted residual positions, in the point's own order
   const int* res_index;
+  const int* slot;           // [P][maxres]: (sorted residual position | target << 26) of the point's slot-th residual, -1 if none
   float* HdiF; float* bdSumF; float* idepth_hessian;
   float* Hdd[2]; float* bd[2]; float4* Hcd[2];
   float* step;
@@ -640,8 +641,6 @@ __global__ void ba_point_sum_kernel(BARes r, BAPts pts, int do_A, int do_L) {
 // the upper triangle of G; points are visited sequentially, so the sum order is fixed.  fp32 SIMT:
 // the matrix is only (8n+5) wide — tensor cores are deliberately not used (north_star).
 // ------------------------------------------------------------------------------------------------
-constexpr int SC_MAXT = 3;   // upper-triangular tiles per thread: NT(NT+1)/2 <= 3*256 (n <= 16: NT=34 -> 595)
-
 __device__ __forceinline__ void tri_decode(int t, int NT, int& ti, int& tj) {
   // t-th tile of the upper triangle enumerated row by row: row ti has NT-ti tiles
   int row = 0, rem = t;
@@ -649,6 +648,18 @@ __device__ __forceinline__ void tri_decode(int t, int NT, int& ti, int& tj) {
   ti = row; tj = row + rem;
 }
 
+// Shared-memory layout (floats): A[SC_PTS][LD+4] | wv[SC_PTS] | stg[7][SC_PTS*MR], MR = maxres|1.
+// The row stride LD+4 and the odd MR keep every access pattern of the kernel free of bank conflicts:
+//   staging stores  A[lp][8t+j]      lanes differ in (lp,t): (LD+4) % 32 = 4 or 12 rotates the rows;
+//   point sums      stg[c][lp*MR+s]  lanes differ in lp: odd stride;
+//   Gram tiles      A[lp][4ti..]     all lanes share lp: float4 broadcast per distinct tile.
+__host__ __device__ inline int sc_mr(int maxres) { return maxres | 1; }
+__host__ __device__ inline size_t sc_smem_floats(int LD, int maxres) {
+  return (size_t)SC_PTS * (LD + 4) + SC_PTS + 7 * (size_t)SC_PTS * sc_mr(maxres);
+}
+
+// MAXT = upper-triangular 4x4 tiles per thread: NT(NT+1)/2 <= MAXT*256 (MAXT=1: n <= 10, MAXT=3: n <= 16).
+template <int MAXT>
 __global__ void __launch_bounds__(SC_THREADS) ba_schur_kernel(const BADesc* __restrict__ descs,
                                                               const int* __restrict__ prefix, int nwin) {
   extern __shared__ __align__(16) float smem[];
@@ -657,19 +668,18 @@ __global__ void __launch_bounds__(SC_THREADS) ba_schur_kernel(const BADesc* __re
   const BADesc& D = descs[win];
   const BARes& r = D.r;
   const BAPts& pts = D.p;
-  const int LD = D.LD;
-  float* A = smem;                       // [SC_PTS][LD]
-  float* wv = smem + SC_PTS * LD;        // [SC_PTS] HdiF
-  float* stg = wv + SC_PTS;              // [SC_PTS][maxres][8]: 6 point terms + mode flag per residual slot
-  const int maxres = D.maxres;
-  __shared__ int cntS[SC_PTS];
+  const int LD = D.LD, LDP = LD + 4;
+  const int maxres = D.maxres, MR = sc_mr(maxres), SN = SC_PTS * MR;
+  float* A = smem;                        // [SC_PTS][LDP]
+  float* wv = smem + SC_PTS * LDP;        // [SC_PTS] HdiF
+  float* stg = wv + SC_PTS;               // [7][SN]: 6 point terms + mode flag per (point, residual slot)
   const PtChunk ch = D.ptchunks[lb];
   const int s = r.rs, n = D.W.n;
   const int NT = LD / 4, ntiles = NT * (NT + 1) / 2;
-  int tI[SC_MAXT], tJ[SC_MAXT];
-  float acc[SC_MAXT][16];
+  int tI[MAXT], tJ[MAXT];
+  float acc[MAXT][16];
 #pragma unroll
-  for (int j = 0; j < SC_MAXT; ++j) {
+  for (int j = 0; j < MAXT; ++j) {
     int tile = threadIdx.x + j * SC_THREADS;
     tI[j] = tJ[j] = -1;
     if (tile < ntiles) tri_decode(tile, NT, tI[j], tJ[j]);
@@ -679,34 +689,37 @@ __global__ void __launch_bounds__(SC_THREADS) ba_schur_kernel(const BADesc* __re
 
   for (int base = 0; base < ch.count; base += SC_PTS) {
     const int cnt = min(SC_PTS, ch.count - base);
-    for (int i = threadIdx.x; i < SC_PTS * LD; i += SC_THREADS) A[i] = 0.f;
+    // per-point scalars of phase 1b: issued now, consumed two barriers later
+    float prior = 0.f, delta = 0.f;
+    if (threadIdx.x < cnt) { prior = pts.priorF[ch.start + base + threadIdx.x]; delta = pts.deltaF[ch.start + base + threadIdx.x]; }
+    for (int i = threadIdx.x; i < SC_PTS * LDP / 4; i += SC_THREADS) reinterpret_cast<float4*>(A)[i] = make_float4(0.f, 0.f, 0.f, 0.f);
     __syncthreads();
-    // phase 1a: one thread per (point, residual slot): every load of the staging step is independent
-    // of the others, so the whole sub-tile costs a few memory round trips instead of one per residual.
+    // phase 1a: one thread per (point, residual slot).  The slot table gives the residual's sorted position
+    // and target in ONE coalesced load; every load after it is independent of the others.
     for (int it = threadIdx.x; it < SC_PTS * maxres; it += SC_THREADS) {
       const int lp = it / maxres, slot = it - lp * maxres;
-      float* st = stg + (size_t)it * 8;
+      const int si = lp * MR + slot;
       float flag = 0.f;
       if (lp < cnt) {
-        const int p = ch.start + base + lp;
-        const int rb = pts.res_begin[p], re = pts.res_begin[p + 1];
-        if (slot == 0) cntS[lp] = re - rb;
-        if (rb + slot < re) {
-          const int k = pts.res_index[rb + slot];
+        const int e = pts.slot[(size_t)(ch.start + base + lp) * maxres + slot];
+        if (e >= 0) {
+          const int k = e & 0x3ffffff, t = e >> 26;
           if (r.isActive[k]) {
             const int m = r.isLin[k] ? 1 : 0;
-            const int t = r.pair[k] / n;
-            float* dst = A + lp * LD + 8 * t;
-#pragma unroll
-            for (int j = 0; j < 8; ++j) dst[j] = r.JpJdF[j * s + k];
+            const float* jp = r.JpJdF + k;
+            const float4 j0 = make_float4(jp[0], jp[s], jp[2 * s], jp[3 * s]);
+            const float4 j1 = make_float4(jp[4 * s], jp[5 * s], jp[6 * s], jp[7 * s]);
             const float* o = r.ptc[m] + k;
-#pragma unroll
-            for (int j = 0; j < 6; ++j) st[j] = o[j * s];
+            const float o0 = o[0], o1 = o[s], o2 = o[2 * s], o3 = o[3 * s], o4 = o[4 * s], o5 = o[5 * s];
+            float4* dst = reinterpret_cast<float4*>(A + lp * LDP + 8 * t);
+            dst[0] = j0; dst[1] = j1;
+            stg[si] = o0; stg[SN + si] = o1; stg[2 * SN + si] = o2; stg[3 * SN + si] = o3;
+            stg[4 * SN + si] = o4; stg[5 * SN + si] = o5;
             flag = (float)(m + 1);
           }
         }
       }
-      st[6] = flag;
+      stg[6 * SN + si] = flag;
     }
     __syncthreads();
     // phase 1b: one thread per point forms Hdd/bd/Hcd sequentially in the point's residual order
@@ -718,17 +731,16 @@ __global__ void __launch_bounds__(SC_THREADS) ba_schur_kernel(const BADesc* __re
         float bdv[2] = {0.f, 0.f}, Hddv[2] = {0.f, 0.f};
         float Hcdv[2][4] = {{0.f, 0.f, 0.f, 0.f}, {0.f, 0.f, 0.f, 0.f}};
         int ngood = 0;
-        const int nr = min(cntS[lp], maxres);
-        for (int slot = 0; slot < nr; ++slot) {
-          const float* st = stg + ((size_t)lp * maxres + slot) * 8;
-          const int f = (int)st[6];
+        for (int slot = 0; slot < maxres; ++slot) {
+          const int si = lp * MR + slot;
+          const int f = (int)stg[6 * SN + si];
           if (f == 0) continue;
           const int m = f - 1;
           ngood++;
-          bdv[m] = xadd(bdv[m], st[0]);
-          Hddv[m] = xadd(Hddv[m], st[1]);
+          bdv[m] = xadd(bdv[m], stg[si]);
+          Hddv[m] = xadd(Hddv[m], stg[SN + si]);
 #pragma unroll
-          for (int j = 0; j < 4; ++j) Hcdv[m][j] = xadd(Hcdv[m][j], st[2 + j]);
+          for (int j = 0; j < 4; ++j) Hcdv[m][j] = xadd(Hcdv[m][j], stg[(2 + j) * SN + si]);
         }
         for (int m = 0; m < 2; ++m) {
           pts.Hdd[m][p] = Hddv[m]; pts.bd[m][p] = bdv[m];
@@ -737,18 +749,18 @@ __global__ void __launch_bounds__(SC_THREADS) ba_schur_kernel(const BADesc* __re
         float hdi = 0.f, bds = 0.f, idh = 0.f;
         float4 hcd = make_float4(0.f, 0.f, 0.f, 0.f);
         if (ngood > 0) {
-          float H = xadd(xadd(Hddv[0], Hddv[1]), pts.priorF[p]);
+          float H = xadd(xadd(Hddv[0], Hddv[1]), prior);
           if (H < 1e-10f) H = 1e-10f;
           idh = H;
           hdi = xdiv(1.0f, H);
           bds = xadd(bdv[0], bdv[1]);
-          bds = xadd(bds, xmul(pts.priorF[p], pts.deltaF[p]));  // shiftPriorToZero = true (EnergyFunctional.cpp:209)
+          bds = xadd(bds, xmul(prior, delta));  // shiftPriorToZero = true (EnergyFunctional.cpp:209)
           hcd = make_float4(xadd(Hcdv[0][0], Hcdv[1][0]), xadd(Hcdv[0][1], Hcdv[1][1]), xadd(Hcdv[0][2], Hcdv[1][2]),
                             xadd(Hcdv[0][3], Hcdv[1][3]));
         }
         pts.HdiF[p] = hdi; pts.bdSumF[p] = bds; pts.idepth_hessian[p] = idh;
-        float* dst = A + lp * LD + 8 * n;
-        dst[0] = hcd.x; dst[1] = hcd.y; dst[2] = hcd.z; dst[3] = hcd.w; dst[4] = bds;
+        float* dst = A + lp * LDP + 8 * n;
+        *reinterpret_cast<float4*>(dst) = hcd; dst[4] = bds;
         wv[lp] = hdi;
       } else {
         wv[lp] = 0.f;
@@ -757,16 +769,17 @@ __global__ void __launch_bounds__(SC_THREADS) ba_schur_kernel(const BADesc* __re
     __syncthreads();
     // phase 2: G += sum_p (w_p a_p) a_p^T, 4x4 register tiles of the upper triangle, points in order
 #pragma unroll
-    for (int j = 0; j < SC_MAXT; ++j) {
+    for (int j = 0; j < MAXT; ++j) {
       if (tI[j] >= 0) {
         const float* ap = A + 4 * tI[j];
         const float* bp = A + 4 * tJ[j];
+#pragma unroll 4
         for (int lp = 0; lp < cnt; ++lp) {
-          float w = wv[lp];
-          float4 av = *reinterpret_cast<const float4*>(ap + lp * LD);
-          float4 bv = *reinterpret_cast<const float4*>(bp + lp * LD);
-          float a4[4] = {w * av.x, w * av.y, w * av.z, w * av.w};
-          float b4[4] = {bv.x, bv.y, bv.z, bv.w};
+          const float w = wv[lp];
+          const float4 av = *reinterpret_cast<const float4*>(ap + lp * LDP);
+          const float4 bv = *reinterpret_cast<const float4*>(bp + lp * LDP);
+          const float a4[4] = {w * av.x, w * av.y, w * av.z, w * av.w};
+          const float b4[4] = {bv.x, bv.y, bv.z, bv.w};
 #pragma unroll
           for (int ii = 0; ii < 4; ++ii)
 #pragma unroll
@@ -778,7 +791,7 @@ __global__ void __launch_bounds__(SC_THREADS) ba_schur_kernel(const BADesc* __re
   }
   float* out = D.scpartial + (size_t)lb * LD * LD;
 #pragma unroll
-  for (int j = 0; j < SC_MAXT; ++j) {
+  for (int j = 0; j < MAXT; ++j) {
     if (tI[j] >= 0) {
 #pragma unroll
       for (int ii = 0; ii < 4; ++ii)
@@ -1192,8 +1205,10 @@ __global__ void __launch_bounds__(256) ba_batch_import_kernel(const BADesc* __re
 }
 // Export: per-residual results back to caller order, the stitched systems, counts and energy, all into
 // the window's slice of the D2H staging block.
+// `what`: bit 0 = per-residual arrays (valid as soon as the linearise kernel is done: exported and copied on a
+// side stream while the accumulate kernels run), bit 1 = systems / counts / energy (after the stitch).
 __global__ void __launch_bounds__(256) ba_batch_export_kernel(const BADesc* __restrict__ descs, const BAIO* __restrict__ io,
-                                                              char* __restrict__ dn) {
+                                                              char* __restrict__ dn, int what) {
   const BADesc& D = descs[blockIdx.y];
   const BAIO o = io[blockIdx.y];
   const int tid = blockIdx.x * blockDim.x + threadIdx.x, stride = gridDim.x * blockDim.x;
@@ -1201,13 +1216,14 @@ __global__ void __launch_bounds__(256) ba_batch_export_kernel(const BADesc* __re
   float* oE = o.dn_newEnergy >= 0 ? reinterpret_cast<float*>(dn + o.dn_newEnergy) : nullptr;
   float* oW = o.dn_newEnergyWO >= 0 ? reinterpret_cast<float*>(dn + o.dn_newEnergyWO) : nullptr;
   int8_t* oS = o.dn_newState >= 0 ? reinterpret_cast<int8_t*>(dn + o.dn_newState) : nullptr;
-  if (oE || oW || oS)
+  if ((what & 1) && (oE || oW || oS))
     for (int k = tid; k < R; k += stride) {
       const int q = D.r_s2o[k];
       if (oE) oE[q] = D.r.newEnergy[k];
       if (oW) oW[q] = D.r.newEnergyWO[k];
       if (oS) oS[q] = D.r.newState[k];
     }
+  if (!(what & 2)) return;
   if (o.dn_Hb >= 0) {
     const int N = 8 * D.W.n + 4, cnt = 3 * (N * N + N);
     double* dst = reinterpret_cast<double*>(dn + o.dn_Hb);

@@ -83,6 +83,8 @@ __device__ __forceinline__ int warp_sum(int v) {
 struct hslam_ctx {
   int device = 0;
   cudaStream_t stream = nullptr;
+  cudaStream_t side = nullptr;        // copy/export stream that overlaps D2H with the accumulate kernels
+  cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
   hslam_params prm;
   int sm_count = 148;
   int64_t launches = 0;

@@ -53,6 +53,9 @@ int hslam_create(const hslam_params* params, int device, hslam_ctx** out) {
     return HSLAM_ERR_CUDA;
   }
   HS_CUDA(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
+  HS_CUDA(cudaStreamCreateWithFlags(&c->side, cudaStreamNonBlocking));
+  HS_CUDA(cudaEventCreateWithFlags(&c->ev_fork, cudaEventDisableTiming));
+  HS_CUDA(cudaEventCreateWithFlags(&c->ev_join, cudaEventDisableTiming));
   *out = c;
   return 0;
 }
@@ -64,6 +67,9 @@ int hslam_destroy(hslam_ctx* c) {
   for (auto& r : c->prof_recs) { cudaEventDestroy(r.a); cudaEventDestroy(r.b); }
   for (auto e : c->prof_pool) cudaEventDestroy(e);
   for (auto& b : c->host_blocks) cudaFreeHost(b.p);
+  cudaStreamSynchronize(c->side);
+  cudaEventDestroy(c->ev_fork); cudaEventDestroy(c->ev_join);
+  cudaStreamDestroy(c->side);
   cudaStreamDestroy(c->stream);
   delete c;
   return 0;

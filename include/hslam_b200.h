@@ -350,6 +350,13 @@ int hslam_ba_download_Hb(hslam_ba* ba, double* Hb_out_host);
  * prior_rank: priors were added by every rank; this call removes the
  * duplicates so that the sum holds them once (AccumulatedTopHessian.cpp:268). */
 int hslam_ba_allreduce(hslam_ba* ba, void* nccl_comm);
+/* How many thread blocks per stage this window should fill (0 = default, two waves over the SMs).  The
+ * residual / point lists are cut into that many chunks, each reduced into one fp32 partial, the partials
+ * are folded in chunk order in fp64: the value changes the grouping of the fp32 sums (results agree to
+ * fp32 round-off, each setting is deterministic).  hslam_ba_batch_create sets it for members that still
+ * have the default, so that the whole batch fills the device about three times. */
+int hslam_ba_set_parallelism(hslam_ba* ba, int target_blocks);
+int hslam_ba_get_parallelism(hslam_ba* ba, int* target_blocks_out);
 /* In a sharded window only one rank may add the priors (cPrior, frame priors):
  * 1 (default) = add, 0 = skip. */
 int hslam_ba_set_add_priors(hslam_ba* ba, int add_priors);

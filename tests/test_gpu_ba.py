@@ -210,6 +210,9 @@ def test_batch_matches_single_windows(ctx, capi, O, synth):
         a = capi.EnergyFunctional(ctx); a.set_window(w, frames); a.set_topology(w); singles.append(a)
         b = capi.EnergyFunctional(ctx); b.set_window(w, frames); b.set_topology(w); batched.append(b)
     batch = capi.EnergyFunctionalBatch(ctx, batched)
+    for a, b in zip(singles, batched):   # same chunking => same grouping of the fp32 partial sums
+        assert b.get_parallelism() > 0
+        a.set_parallelism(b.get_parallelism())
     for _ in range(2):   # two iterations: tickets / partial buffers are reusable
         batch.iteration()
         for a in singles:
@@ -262,6 +265,8 @@ def test_batch_step_host_matches_single_window_calls(ctx, capi, synth, pinned):
         a = capi.EnergyFunctional(ctx); a.set_window(w, frames); a.set_topology(w); singles.append(a)
         b = capi.EnergyFunctional(ctx); b.set_window(w, frames); b.set_topology(w); batched.append(b)
     batch = capi.EnergyFunctionalBatch(ctx, batched)
+    for a, b in zip(singles, batched):
+        a.set_parallelism(b.get_parallelism())
     io = batch.make_io(wins, [frames] * len(wins), pinned=pinned)
     rng = np.random.default_rng(9)
     for it in range(2):
