@@ -186,7 +186,7 @@ static void fill_desc(hslam_ba* ba) {
   r.state_state = ba->d_state.p; r.newState = ba->d_newState.p; r.isLin = ba->d_isLin.p; r.isActive = ba->d_isActive.p;
   r.state_energy = ba->d_senergy.p; r.newEnergy = ba->d_newEnergy.p; r.newEnergyWO = ba->d_newEnergyWO.p;
   r.J = ba->d_J.p; r.JpJdF = ba->d_JpJdF.p; r.rtz = ba->d_rtz.p; r.cpt = ba->d_cpt.p; r.pto = ba->d_pto.p;
-  r.ptc[0] = ba->d_ptc[0].p; r.ptc[1] = ba->d_ptc[1].p;
+  r.ptc[0] = r.ptc[1] = ba->d_ptc[0].p;   // a residual is in exactly one of the modes A / L: one array serves both
   BAPts& p = D.p;
   p.P = ba->P; p.uvid = ba->d_uvid.p; p.color = ba->d_color.p; p.weights = ba->d_weights.p;
   p.priorF = ba->d_priorF.p; p.deltaF = ba->d_deltaF.p; p.host = ba->d_phost.p;
@@ -238,8 +238,12 @@ static int build_chunks(hslam_ba* ba) {
     for (int mode = 0; mode < 2; ++mode) {
       for (int k = 0; k < nn; ++k) {
         pcb[mode * nn + k] = (int)ch.size();
-        for (int s0 = pairBegin[k]; s0 < pairBegin[k + 1]; s0 += chunk)
-          ch.push_back(TopChunk{k, s0, std::min(chunk, pairBegin[k + 1] - s0), mode});
+        const int len = pairBegin[k + 1] - pairBegin[k];
+        if (len == 0) continue;
+        const int parts = (len + chunk - 1) / chunk;   // equal-sized chunks within a pair
+        const int sz = ((len + parts - 1) / parts + TOP_THREADS - 1) / TOP_THREADS * TOP_THREADS;
+        for (int s0 = pairBegin[k]; s0 < pairBegin[k + 1]; s0 += sz)
+          ch.push_back(TopChunk{k, s0, std::min(sz, pairBegin[k + 1] - s0), mode});
       }
       ba->n_topchunks[mode] = (int)ch.size() - (mode ? ba->n_topchunks[0] : 0);
     }
@@ -259,8 +263,12 @@ static int build_chunks(hslam_ba* ba) {
     std::vector<int> hcb(n + 1, 0);
     for (int h = 0; h < n; ++h) {
       hcb[h] = (int)ch.size();
-      for (int s0 = hostBegin[h]; s0 < hostBegin[h + 1]; s0 += chunk)
-        ch.push_back(PtChunk{h, s0, std::min(chunk, hostBegin[h + 1] - s0), 0});
+      const int len = hostBegin[h + 1] - hostBegin[h];
+      if (len == 0) continue;
+      const int parts = (len + chunk - 1) / chunk;
+      const int sz = ((len + parts - 1) / parts + SC_PTS - 1) / SC_PTS * SC_PTS;
+      for (int s0 = hostBegin[h]; s0 < hostBegin[h + 1]; s0 += sz)
+        ch.push_back(PtChunk{h, s0, std::min(sz, hostBegin[h + 1] - s0), 0});
     }
     hcb[n] = (int)ch.size();
     ba->n_ptchunks = (int)ch.size();
@@ -467,7 +475,8 @@ int hslam_ba_set_topology(hslam_ba* ba, const hslam_point_soa* pt, const hslam_r
   TRY(ba->d_priorF.ensure(P + 1)); TRY(ba->d_deltaF.ensure(P + 1)); TRY(ba->d_phost.ensure(P + 1));
   TRY(ba->d_res_begin.ensure(P + 2)); TRY(ba->d_res_index.ensure(R + 1));
   TRY(ba->d_HdiF.ensure(P + 1)); TRY(ba->d_bdSumF.ensure(P + 1)); TRY(ba->d_idh.ensure(P + 1)); TRY(ba->d_step.ensure(P + 1));
-  for (int m = 0; m < 2; ++m) { TRY(ba->d_Hdd[m].ensure(P + 1)); TRY(ba->d_bd[m].ensure(P + 1)); TRY(ba->d_Hcd[m].ensure(P + 1)); TRY(ba->d_ptc[m].ensure(6 * rsz)); }
+  for (int m = 0; m < 2; ++m) { TRY(ba->d_Hdd[m].ensure(P + 1)); TRY(ba->d_bd[m].ensure(P + 1)); TRY(ba->d_Hcd[m].ensure(P + 1)); }
+  TRY(ba->d_ptc[0].ensure(6 * rsz));
   TRY(ba->d_rpoint.ensure(rsz)); TRY(ba->d_rpair.ensure(rsz)); TRY(ba->d_state.ensure(rsz)); TRY(ba->d_newState.ensure(rsz));
   TRY(ba->d_isLin.ensure(rsz)); TRY(ba->d_isActive.ensure(rsz)); TRY(ba->d_senergy.ensure(rsz)); TRY(ba->d_newEnergy.ensure(rsz));
   TRY(ba->d_newEnergyWO.ensure(rsz)); TRY(ba->d_J.ensure((size_t)JS * rsz)); TRY(ba->d_JpJdF.ensure(8 * rsz));
@@ -531,8 +540,8 @@ int hslam_ba_set_topology(hslam_ba* ba, const hslam_point_soa* pt, const hslam_r
   HS_CUDA(cudaMemsetAsync(ba->d_newState.p, HSLAM_RES_OUT, rsz, ctx->stream));
   HS_CUDA(cudaMemsetAsync(ba->d_newEnergy.p, 0, rsz * sizeof(float), ctx->stream));
   HS_CUDA(cudaMemsetAsync(ba->d_newEnergyWO.p, 0, rsz * sizeof(float), ctx->stream));
+  HS_CUDA(cudaMemsetAsync(ba->d_ptc[0].p, 0, 6 * rsz * sizeof(float), ctx->stream));
   for (int m = 0; m < 2; ++m) {
-    HS_CUDA(cudaMemsetAsync(ba->d_ptc[m].p, 0, 6 * rsz * sizeof(float), ctx->stream));
     HS_CUDA(cudaMemsetAsync(ba->d_Hdd[m].p, 0, (P + 1) * sizeof(float), ctx->stream));
     HS_CUDA(cudaMemsetAsync(ba->d_bd[m].p, 0, (P + 1) * sizeof(float), ctx->stream));
     HS_CUDA(cudaMemsetAsync(ba->d_Hcd[m].p, 0, (P + 1) * sizeof(float4), ctx->stream));
@@ -842,6 +851,7 @@ struct hslam_ba_batch {
   int* h_prefix = nullptr;       // pinned
   cudaEvent_t copied = nullptr;
   int blocks[6] = {0, 0, 0, 0, 0, 0};
+  int uniform[6] = {0, 0, 0, 0, 0, 0};   // blocks per window of a stage when every window has the same count, else 0
   size_t smem = 0;
   int maxt = 1;
   // host API staging: one pinned block up, one down, their device twins, and the per-window offset table
@@ -881,7 +891,12 @@ static int batch_refresh(hslam_ba_batch* B) {
     B->smem = std::max(B->smem, schur_smem(ba->LD, ba->maxres));
     B->maxt = std::max(B->maxt, schur_maxt(ba->LD));
   }
-  for (int k = 0; k < NPF; ++k) B->blocks[k] = pf[k][n];
+  for (int k = 0; k < NPF; ++k) {
+    B->blocks[k] = pf[k][n];
+    B->uniform[k] = pf[k][1];
+    for (int i = 1; i < n; ++i) if (pf[k][i + 1] - pf[k][i] != pf[k][1]) B->uniform[k] = 0;
+    if (n < 2 || pf[k][1] == 0) B->uniform[k] = 0;
+  }
   HS_CUDA(cudaMemcpyAsync(B->d_descs.p, B->h_descs, n * sizeof(BADesc), cudaMemcpyHostToDevice, B->ctx->stream));
   HS_CUDA(cudaMemcpyAsync(B->d_prefix.p, B->h_prefix, NPF * (n + 1) * sizeof(int), cudaMemcpyHostToDevice, B->ctx->stream));
   HS_CUDA(cudaEventRecord(B->copied, B->ctx->stream));
@@ -944,8 +959,8 @@ static int batch_enqueue_accumulate(hslam_ba_batch* B) {
     HS_LAUNCH(ctx, HSLAM_K_BA_TOP, (ba_top_kernel<<<B->blocks[1], 2 * TOP_THREADS, 0, ctx->stream>>>(B->d_descs.p, pf + (n + 1), n, 0)));
   if (B->blocks[2] > 0)
     HS_LAUNCH(ctx, HSLAM_K_BA_SCHUR, schur_launch(B->maxt, B->blocks[2], B->smem, ctx->stream, B->d_descs.p, pf + 2 * (n + 1), n));
-  HS_LAUNCH(ctx, HSLAM_K_BA_FOLD_SC, (ba_fold_sc_kernel<<<B->blocks[4], 256, 0, ctx->stream>>>(B->d_descs.p, pf + 4 * (n + 1), n)));
-  HS_LAUNCH(ctx, HSLAM_K_BA_STITCH, (ba_stitch_kernel<<<B->blocks[3], ST_THREADS, 0, ctx->stream>>>(B->d_descs.p, pf + 3 * (n + 1), n, 0, 3, 1)));
+  HS_LAUNCH(ctx, HSLAM_K_BA_FOLD_SC, (ba_fold_sc_kernel<<<B->blocks[4], 256, 0, ctx->stream>>>(B->d_descs.p, pf + 4 * (n + 1), B->uniform[4] ? -B->uniform[4] : n)));
+  HS_LAUNCH(ctx, HSLAM_K_BA_STITCH, (ba_stitch_kernel<<<B->blocks[3], ST_THREADS, 0, ctx->stream>>>(B->d_descs.p, pf + 3 * (n + 1), B->uniform[3] ? -B->uniform[3] : n, 0, 3, 1)));
   HS_CUDA(cudaGetLastError());
   return 0;
 }

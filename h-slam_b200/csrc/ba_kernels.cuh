@@ -47,7 +47,7 @@ constexpr int TOP_THREADS = 128;
 constexpr int TOP_PART = 96;           // 91 accumulators + nres + pad
 constexpr int SC_THREADS = 256;
 constexpr int SC_PTS = 64;             // points staged in shared memory per sub-tile
-constexpr int ST_WARPS = 16;           // warps per stitch block
+constexpr int ST_WARPS = 8;            // warps per stitch block (80 regs x 256 threads: 3 blocks per SM)
 constexpr int ST_THREADS = ST_WARPS * 32;
 
 __constant__ int c_pat[8][2] = {{0, -2}, {-1, -1}, {1, -1}, {-2, 0}, {0, 0}, {2, 0}, {-1, 1}, {0, 2}};
@@ -148,6 +148,7 @@ struct BAIO {
 
 __device__ __forceinline__ int find_window(const int* __restrict__ prefix, int nwin, int b, int& local) {
   if (nwin == 1) { local = b; return 0; }
+  if (nwin < 0) { const int per = -nwin; const int w = b / per; local = b - w * per; return w; }   // every window owns `per` blocks
   int lo = 0, hi = nwin;   // prefix[lo] <= b < prefix[hi]
   while (hi - lo > 1) {
     int m = (lo + hi) >> 1;
@@ -462,8 +463,11 @@ __device__ __forceinline__ void top_accumulate(const BADesc& D, const TopChunk& 
     for (int j = 0; j < 8; ++j) dp[j] = __ldg(W.adHTdeltaF + 8 * ch.pair + j);
   }
   for (int k = ch.start + (threadIdx.x & (TOP_THREADS - 1)); k < ch.start + ch.count; k += TOP_THREADS) {
-    bool lin = r.isLin[k] != 0, act = r.isActive[k] != 0;
-    if (MODE == 0 ? (lin || !act) : (!lin || !act)) continue;
+    // The residual filter (AccumulatedTopHessian.cpp:37-49) is applied AFTER the loads: every load of an
+    // iteration is independent of the flags, so an iteration costs one memory round trip instead of two.  A
+    // filtered-out residual contributes exact zeros (its x, y and bottom-right terms are zeroed).
+    const bool lin = r.isLin[k] != 0, act = r.isActive[k] != 0;
+    const bool use = (MODE == 0) ? (!lin && act) : (lin && act);
     const float* J = r.J + k;
     float x[10], y[10];
 #pragma unroll
@@ -471,15 +475,19 @@ __device__ __forceinline__ void top_accumulate(const BADesc& D, const TopChunk& 
 #pragma unroll
     for (int j = 0; j < 6; ++j) { x[4 + j] = J[(J_XI0 + j) * s]; y[4 + j] = J[(J_XI1 + j) * s]; }
     const float d0 = J[J_DD * s], d1 = J[(J_DD + 1) * s];
-    const float a = J[(J_IDX2 + 0) * s], b = J[(J_IDX2 + 2) * s], c = J[(J_IDX2 + 3) * s];
-    const float AI00 = J[(J_ABIDX + 0) * s], AI10 = J[(J_ABIDX + 1) * s], AI01 = J[(J_ABIDX + 2) * s],
-                AI11 = J[(J_ABIDX + 3) * s];
-    const float AA00 = J[(J_AB2 + 0) * s], AA01 = J[(J_AB2 + 2) * s], AA11 = J[(J_AB2 + 3) * s];
-    float JIr0, JIr1, Jabr0, Jabr1, rr;
+    float a = J[(J_IDX2 + 0) * s], b = J[(J_IDX2 + 2) * s], c = J[(J_IDX2 + 3) * s];
+    float AI00 = 0.f, AI10 = 0.f, AI01 = 0.f, AI11 = 0.f, AA00 = 0.f, AA01 = 0.f, AA11 = 0.f;
+    float JIr0 = 0.f, JIr1 = 0.f, Jabr0 = 0.f, Jabr1 = 0.f, rr = 0.f;
+    if (PART == 1) {
+      AI00 = J[(J_ABIDX + 0) * s]; AI10 = J[(J_ABIDX + 1) * s]; AI01 = J[(J_ABIDX + 2) * s]; AI11 = J[(J_ABIDX + 3) * s];
+      AA00 = J[(J_AB2 + 0) * s]; AA01 = J[(J_AB2 + 2) * s]; AA11 = J[(J_AB2 + 3) * s];
+    }
     if (MODE == 0) {
-      JIr0 = J[(J_JIR + 0) * s]; JIr1 = J[(J_JIR + 1) * s];
-      Jabr0 = J[(J_JABR + 0) * s]; Jabr1 = J[(J_JABR + 1) * s]; rr = J[J_RR * s];
-    } else {
+      if (PART == 1) {
+        JIr0 = J[(J_JIR + 0) * s]; JIr1 = J[(J_JIR + 1) * s];
+        Jabr0 = J[(J_JABR + 0) * s]; Jabr1 = J[(J_JABR + 1) * s]; rr = J[J_RR * s];
+      }
+    } else if (PART == 1) {
       // resApprox = res_toZeroF + J*delta, AccumulatedTopHessian.cpp:63-81 (sequential sums)
       float dx = 0.f, dy = 0.f, cxs = 0.f, cys = 0.f;
 #pragma unroll
@@ -488,7 +496,6 @@ __device__ __forceinline__ void top_accumulate(const BADesc& D, const TopChunk& 
       for (int j = 0; j < 4; ++j) { cxs = xadd(cxs, xmul(x[j], W.cDeltaF[j])); cys = xadd(cys, xmul(y[j], W.cDeltaF[j])); }
       float dd = D.p.deltaF[r.point[k]];
       float Jpx = xadd(xadd(dx, cxs), xmul(d0, dd)), Jpy = xadd(xadd(dy, cys), xmul(d1, dd));
-      JIr0 = JIr1 = Jabr0 = Jabr1 = rr = 0.f;
 #pragma unroll
       for (int j = 0; j < 8; ++j) {
         float i0 = J[(J_IDX0 + j) * s], i1 = J[(J_IDX1 + j) * s], a0 = J[(J_AB0 + j) * s], a1 = J[(J_AB1 + j) * s];
@@ -499,6 +506,12 @@ __device__ __forceinline__ void top_accumulate(const BADesc& D, const TopChunk& 
         Jabr0 = xadd(Jabr0, xmul(rz, a0)); Jabr1 = xadd(Jabr1, xmul(rz, a1));
         rr = xadd(rr, xmul(rz, rz));
       }
+    }
+    if (!use) {
+#pragma unroll
+      for (int j = 0; j < 10; ++j) { x[j] = 0.f; y[j] = 0.f; }
+      a = b = c = AI00 = AI10 = AI01 = AI11 = JIr0 = JIr1 = 0.f;   // stale Jacobians may hold anything
+      AA00 = AA01 = AA11 = Jabr0 = Jabr1 = rr = 0.f;
     }
     if (PART == 0) {
       // 10x10 upper triangle: [x y] [[a b],[b c]] [x y]^T
@@ -518,6 +531,7 @@ __device__ __forceinline__ void top_accumulate(const BADesc& D, const TopChunk& 
         acc[3 * rI + 2] += fmaf(x[rI], JIr0, y[rI] * JIr1);
       }
       acc[30] += AA00; acc[31] += AA01; acc[32] += Jabr0; acc[33] += AA11; acc[34] += Jabr1; acc[35] += rr;
+      if (!use) continue;
       nres++;
       // per-residual contribution to the point sums (:114-117), exact ops: they are summed per point in
       // the point's own order by the Schur kernel, which keeps Hdd/bd/Hcd bit-identical to the oracle.
@@ -704,13 +718,15 @@ __global__ void __launch_bounds__(SC_THREADS) ba_schur_kernel(const BADesc* __re
         const int e = pts.slot[(size_t)(ch.start + base + lp) * maxres + slot];
         if (e >= 0) {
           const int k = e & 0x3ffffff, t = e >> 26;
-          if (r.isActive[k]) {
-            const int m = r.isLin[k] ? 1 : 0;
-            const float* jp = r.JpJdF + k;
-            const float4 j0 = make_float4(jp[0], jp[s], jp[2 * s], jp[3 * s]);
-            const float4 j1 = make_float4(jp[4 * s], jp[5 * s], jp[6 * s], jp[7 * s]);
-            const float* o = r.ptc[m] + k;
-            const float o0 = o[0], o1 = o[s], o2 = o[2 * s], o3 = o[3 * s], o4 = o[4 * s], o5 = o[5 * s];
+          // all loads of the residual are independent of its flags (one round trip); filtered afterwards
+          const bool act = r.isActive[k] != 0;
+          const int m = r.isLin[k] ? 1 : 0;
+          const float* jp = r.JpJdF + k;
+          const float4 j0 = make_float4(jp[0], jp[s], jp[2 * s], jp[3 * s]);
+          const float4 j1 = make_float4(jp[4 * s], jp[5 * s], jp[6 * s], jp[7 * s]);
+          const float* o = r.ptc[0] + k;   // modes A and L share the array (a residual is in exactly one)
+          const float o0 = o[0], o1 = o[s], o2 = o[2 * s], o3 = o[3 * s], o4 = o[4 * s], o5 = o[5 * s];
+          if (act) {
             float4* dst = reinterpret_cast<float4*>(A + lp * LDP + 8 * t);
             dst[0] = j0; dst[1] = j1;
             stg[si] = o0; stg[SN + si] = o1; stg[2 * SN + si] = o2; stg[3 * SN + si] = o3;
@@ -852,27 +868,32 @@ __device__ __forceinline__ double Gsym(const double* G, int LD, int i, int j) {
   return ((j >> 2) >= (i >> 2)) ? G[(size_t)i * LD + j] : G[(size_t)j * LD + i];
 }
 
-// out(r, c0) and out(r, c1) of A1 * M * A2^T for one warp: lane -> r = lane&7, c0 = lane>>3, c1 = c0+4
-template <class MF>
+// out(r, c0) and out(r, c1) of A1 * M * A2^T for one warp: lane -> r = lane&7, c0 = lane>>3, c1 = c0+4.
+// Every global load (M, A2 and A1) is issued before the first use, so a sandwich costs one memory round trip.
+// SYM: add the transpose as well (X + X^T), for the pairs (j,k),(k,j) of a symmetric Gram block.
+template <bool SYM, class MF>
 __device__ __forceinline__ void sandwich_warp(const double* __restrict__ A1, const double* __restrict__ A2, MF M,
                                               double (*tmp)[9], int lane, double& o0, double& o1) {
   const int r = lane & 7, c0 = lane >> 3, c1 = c0 + 4;
+  double m[8], a20[8], a21[8], a1[8];
+#pragma unroll
+  for (int y = 0; y < 8; ++y) { m[y] = M(r, y); a20[y] = A2[c0 + 8 * y]; a21[y] = A2[c1 + 8 * y]; a1[y] = A1[r + 8 * y]; }
   double t0 = 0.0, t1 = 0.0;
 #pragma unroll
-  for (int y = 0; y < 8; ++y) {
-    double m = M(r, y);
-    t0 += m * A2[c0 + 8 * y];
-    t1 += m * A2[c1 + 8 * y];
-  }
+  for (int y = 0; y < 8; ++y) { t0 += m[y] * a20[y]; t1 += m[y] * a21[y]; }
   __syncwarp();
   tmp[r][c0] = t0; tmp[r][c1] = t1;
   __syncwarp();
+  double x0 = 0.0, x1 = 0.0;
 #pragma unroll
-  for (int x = 0; x < 8; ++x) {
-    double a = A1[r + 8 * x];
-    o0 += a * tmp[x][c0];
-    o1 += a * tmp[x][c1];
+  for (int x = 0; x < 8; ++x) { x0 += a1[x] * tmp[x][c0]; x1 += a1[x] * tmp[x][c1]; }
+  if (SYM) {
+    __syncwarp();
+    tmp[r][c0] = x0; tmp[r][c1] = x1;
+    __syncwarp();
+    x0 += tmp[c0][r]; x1 += tmp[c1][r];
   }
+  o0 += x0; o1 += x1;
 }
 
 __global__ void __launch_bounds__(ST_THREADS) ba_stitch_kernel(const BADesc* __restrict__ descs,
@@ -898,7 +919,7 @@ __global__ void __launch_bounds__(ST_THREADS) ba_stitch_kernel(const BADesc* __r
   int ci = 0;   // contribution counter, identical in every warp
 #define CONTRIB(A1, A2, MF)                                                                 \
   do {                                                                                      \
-    if ((ci % ST_WARPS) == warp) sandwich_warp((A1), (A2), (MF), tmp[warp], lane, o0, o1);   \
+    if ((ci % ST_WARPS) == warp) sandwich_warp<false>((A1), (A2), (MF), tmp[warp], lane, o0, o1);   \
     ci++;                                                                                   \
   } while (0)
 
@@ -1009,10 +1030,17 @@ __global__ void __launch_bounds__(ST_THREADS) ba_stitch_kernel(const BADesc* __r
   auto Gh = [&](int i) { return S.G + (size_t)i * LD * LD; };
   if (a < n && b < n) {
     if (a == b) {   // sum_{j,k} AdH[a,j] D_a[j,k] AdH[a,k]^T   (AccumulatedSCHessian.cpp:108)
+      // D_a[k,j] = D_a[j,k]^T (one symmetric Gram matrix per host), so the (k,j) term is the transpose of (j,k)
       const double* G = Gh(a);
-      for (int j = 0; j < n; ++j)
-        for (int k = 0; k < n; ++k)
-          CONTRIB(AdH(a, j), AdH(a, k), [&](int x, int y) { return Gsym(G, LD, 8 * j + x, 8 * k + y); });
+      for (int j = 0; j < n; ++j) {
+        CONTRIB(AdH(a, j), AdH(a, j), [&](int x, int y) { return Gsym(G, LD, 8 * j + x, 8 * j + y); });
+        for (int k = j + 1; k < n; ++k) {
+          if ((ci % ST_WARPS) == warp)
+            sandwich_warp<true>(AdH(a, j), AdH(a, k), [&](int x, int y) { return Gsym(G, LD, 8 * j + x, 8 * k + y); },
+                                tmp[warp], lane, o0, o1);
+          ci++;
+        }
+      }
     }
     {   // :111  H[i,k] += AdH[ij] D AdT[ik]^T with i=a, k=b
       const double* G = Gh(a);
