@@ -63,7 +63,10 @@ struct hslam_ba {
   DevBuf<int> d_pair_chunk_begin;
   DevBuf<float> d_toppartial;
   DevBuf<unsigned int> d_pair_ticket;
-  int n_topchunks[2] = {0, 0};   // mode 0 chunks first, then mode 1
+  int n_topchunks[2] = {0, 0};   // top-kernel BLOCKS per mode (mode 0 blocks first, then mode 1)
+  int top_chunks0 = 0;           // chunks (partials) per mode
+  DevBuf<TopTile> d_toptiles;
+  DevBuf<int> d_top_block_begin;
   DevBuf<PtChunk> d_ptchunks;
   DevBuf<int> d_host_chunk_begin;
   DevBuf<float> d_scpartial;
@@ -199,6 +202,8 @@ static void fill_desc(hslam_ba* ba) {
   D.lin_warps = std::max(1, (ba->R + LIN_THREADS - 1) / LIN_THREADS) * (LIN_THREADS / 32);
   D.topchunks = ba->d_topchunks.p; D.toppartial = ba->d_toppartial.p; D.pair_ticket = ba->d_pair_ticket.p;
   D.pair_chunk_begin = ba->d_pair_chunk_begin.p; D.accTop = ba->d_accTop.p;
+  D.toptiles = ba->d_toptiles.p; D.top_block_begin = ba->d_top_block_begin.p;
+  D.top_blocks = ba->n_topchunks[0]; D.top_chunks0 = ba->top_chunks0;
   D.ptchunks = ba->d_ptchunks.p; D.scpartial = ba->d_scpartial.p; D.host_ticket = ba->d_host_ticket.p;
   D.host_chunk_begin = ba->d_host_chunk_begin.p; D.G = ba->d_G.p; D.LD = ba->LD; D.maxres = ba->maxres;
   StitchArgs& S = D.S;
@@ -231,33 +236,55 @@ static int build_chunks(hslam_ba* ba) {
   const std::vector<int>& hostBegin = ba->h_hostBegin;
   const int target_blocks = ba->target_blocks > 0 ? ba->target_blocks : 2 * ctx->sm_count;
   {
-    int chunk = ((R + target_blocks - 1) / target_blocks + TOP_THREADS - 1) / TOP_THREADS * TOP_THREADS;
-    if (chunk < TOP_THREADS) chunk = TOP_THREADS;
+    // tiles of <= TOP_THREADS residuals that never cross a pair; equal runs of tiles per block; chunks =
+    // maximal same-pair runs inside a block (see ba_top_kernel)
+    struct HT { int start, count, pair; };
+    std::vector<HT> ht;
+    for (int k = 0; k < nn; ++k)
+      for (int s0 = pairBegin[k]; s0 < pairBegin[k + 1]; s0 += TOP_THREADS)
+        ht.push_back({s0, std::min(TOP_THREADS, pairBegin[k + 1] - s0), k});
+    const int NT = (int)ht.size();
+    const int per = std::max(1, (NT + target_blocks - 1) / target_blocks);
+    const int T = (NT + per - 1) / per;
+    std::vector<int> bb(T + 1, 0);
+    std::vector<TopTile> tiles(NT);
     std::vector<TopChunk> ch;
+    for (int b = 0; b < T; ++b) {
+      bb[b] = b * per;
+      const int e = std::min(NT, (b + 1) * per);
+      for (int t = b * per; t < e; ++t) {
+        if (t == b * per || ht[t].pair != ht[t - 1].pair) ch.push_back(TopChunk{ht[t].pair, ht[t].start, 0, 0});
+        ch.back().count += ht[t].count;
+        tiles[t] = TopTile{ht[t].start, ht[t].count, (int)ch.size() - 1, 0};
+      }
+    }
+    bb[T] = NT;
+    const int nch0 = (int)ch.size();
+    for (int c = 0; c < nch0; ++c) { TopChunk m = ch[c]; m.mode = 1; ch.push_back(m); }
     std::vector<int> pcb(2 * nn + 1, 0);
     for (int mode = 0; mode < 2; ++mode) {
+      int c = mode * nch0;
       for (int k = 0; k < nn; ++k) {
-        pcb[mode * nn + k] = (int)ch.size();
-        const int len = pairBegin[k + 1] - pairBegin[k];
-        if (len == 0) continue;
-        const int parts = (len + chunk - 1) / chunk;   // equal-sized chunks within a pair
-        const int sz = ((len + parts - 1) / parts + TOP_THREADS - 1) / TOP_THREADS * TOP_THREADS;
-        for (int s0 = pairBegin[k]; s0 < pairBegin[k + 1]; s0 += sz)
-          ch.push_back(TopChunk{k, s0, std::min(sz, pairBegin[k + 1] - s0), mode});
+        pcb[mode * nn + k] = c;
+        while (c < (mode + 1) * nch0 && ch[c].pair == k) ++c;
       }
-      ba->n_topchunks[mode] = (int)ch.size() - (mode ? ba->n_topchunks[0] : 0);
     }
-    pcb[2 * nn] = (int)ch.size();
+    pcb[2 * nn] = 2 * nch0;
+    ba->n_topchunks[0] = ba->n_topchunks[1] = T;   // BLOCKS per mode
+    ba->top_chunks0 = nch0;
     TRY(ba->d_topchunks.ensure(ch.size() + 1)); TRY(ba->d_pair_chunk_begin.ensure(pcb.size()));
+    TRY(ba->d_toptiles.ensure(tiles.size() + 1)); TRY(ba->d_top_block_begin.ensure(bb.size()));
     TRY(ba->d_toppartial.ensure((ch.size() + 1) * TOP_PART));
     TRY(ba->d_pair_ticket.ensure(2 * nn + 1));
     HS_CUDA(cudaMemsetAsync(ba->d_pair_ticket.p, 0, (2 * nn + 1) * sizeof(unsigned int), ctx->stream));
     TRY(upload(ba, ba->d_topchunks.p, ch.data(), ch.size())); TRY(upload(ba, ba->d_pair_chunk_begin.p, pcb.data(), pcb.size()));
+    TRY(upload(ba, ba->d_toptiles.p, tiles.data(), tiles.size())); TRY(upload(ba, ba->d_top_block_begin.p, bb.data(), bb.size()));
     // pairs without any chunk are never folded: their accumulators must read as zero
     HS_CUDA(cudaMemsetAsync(ba->d_accTop.p, 0, 2 * (size_t)nn * TOP_PART * sizeof(double), ctx->stream));
   }
   {
-    int chunk = ((P + target_blocks - 1) / target_blocks + SC_PTS - 1) / SC_PTS * SC_PTS;
+    const int sc_blocks = 2 * target_blocks;   // the Schur kernel holds 4 blocks per SM, the top kernel 2
+    int chunk = ((P + sc_blocks - 1) / sc_blocks + SC_PTS - 1) / SC_PTS * SC_PTS;
     if (chunk < SC_PTS) chunk = SC_PTS;
     std::vector<PtChunk> ch;
     std::vector<int> hcb(n + 1, 0);
@@ -315,7 +342,7 @@ int hslam_ba_destroy(hslam_ba* ba) {
   ba->d_isLin.release(); ba->d_isActive.release(); ba->d_senergy.release(); ba->d_newEnergy.release();
   ba->d_newEnergyWO.release(); ba->d_J.release(); ba->d_JpJdF.release(); ba->d_rtz.release(); ba->d_cpt.release();
   ba->d_pto.release(); ba->d_topchunks.release(); ba->d_pair_chunk_begin.release(); ba->d_toppartial.release();
-  ba->d_pair_ticket.release(); ba->d_host_ticket.release();
+  ba->d_pair_ticket.release(); ba->d_host_ticket.release(); ba->d_toptiles.release(); ba->d_top_block_begin.release();
   ba->d_ptchunks.release(); ba->d_host_chunk_begin.release(); ba->d_scpartial.release(); ba->d_G.release();
   ba->d_Hb.release(); ba->d_epart.release(); ba->d_energy.release(); ba->d_nres.release(); ba->d_ticket.release();
   ba->d_xc.release(); ba->d_xAd.release(); ba->d_x.release(); ba->d_ids.release(); ba->d_desc.release();
@@ -479,7 +506,7 @@ int hslam_ba_set_topology(hslam_ba* ba, const hslam_point_soa* pt, const hslam_r
   TRY(ba->d_ptc[0].ensure(6 * rsz));
   TRY(ba->d_rpoint.ensure(rsz)); TRY(ba->d_rpair.ensure(rsz)); TRY(ba->d_state.ensure(rsz)); TRY(ba->d_newState.ensure(rsz));
   TRY(ba->d_isLin.ensure(rsz)); TRY(ba->d_isActive.ensure(rsz)); TRY(ba->d_senergy.ensure(rsz)); TRY(ba->d_newEnergy.ensure(rsz));
-  TRY(ba->d_newEnergyWO.ensure(rsz)); TRY(ba->d_J.ensure((size_t)JS * rsz)); TRY(ba->d_JpJdF.ensure(8 * rsz));
+  TRY(ba->d_newEnergyWO.ensure(rsz)); TRY(ba->d_J.ensure((size_t)JS * rsz + 2 * TOP_ROW)); /* + slack: the top kernel stages whole rows */ TRY(ba->d_JpJdF.ensure(8 * rsz));
   TRY(ba->d_rtz.ensure(8 * rsz)); TRY(ba->d_cpt.ensure(3 * rsz)); TRY(ba->d_pto.ensure(16 * rsz));
   // ---- pack + upload points
   {
@@ -598,14 +625,26 @@ static int launch_linearize(hslam_ba* ba, bool apply) {
   return 0;
 }
 
+static const size_t kTopSmem = TOP_STAGES * sizeof(TopStage);
+static int top_attr() {
+  static bool done = false;
+  if (!done) {
+    HS_CUDA(cudaFuncSetAttribute(ba_top_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kTopSmem));
+    HS_CUDA(cudaFuncSetAttribute(ba_top_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kTopSmem));
+    done = true;
+  }
+  return 0;
+}
 // modes: bit 0 = A, bit 1 = L
 static int launch_top(hslam_ba* ba, int modes) {
   hslam_ctx* ctx = ba->ctx;
   TRY(sync_desc(ba));
-  int first = (modes & 1) ? 0 : ba->n_topchunks[0];
-  int count = ((modes & 1) ? ba->n_topchunks[0] : 0) + ((modes & 2) ? ba->n_topchunks[1] : 0);
-  if (count > 0)
-    HS_LAUNCH(ctx, HSLAM_K_BA_TOP, (ba_top_kernel<<<count, 2 * TOP_THREADS, 0, ctx->stream>>>(ba->d_desc.p, nullptr, 1, first)));
+  TRY(top_attr());
+  const int T = ba->n_topchunks[0];
+  if (T > 0 && (modes & 1))
+    HS_LAUNCH(ctx, HSLAM_K_BA_TOP, (ba_top_kernel<0><<<T, 2 * TOP_THREADS, kTopSmem, ctx->stream>>>(ba->d_desc.p, nullptr, 1)));
+  if (T > 0 && (modes & 2))
+    HS_LAUNCH(ctx, HSLAM_K_BA_TOP, (ba_top_kernel<1><<<T, 2 * TOP_THREADS, kTopSmem, ctx->stream>>>(ba->d_desc.p, nullptr, 1)));
   HS_CUDA(cudaGetLastError());
   return 0;
 }
@@ -854,6 +893,7 @@ struct hslam_ba_batch {
   int uniform[6] = {0, 0, 0, 0, 0, 0};   // blocks per window of a stage when every window has the same count, else 0
   size_t smem = 0;
   int maxt = 1;
+  bool any_L = false;
   // host API staging: one pinned block up, one down, their device twins, and the per-window offset table
   char* h_up = nullptr; char* h_dn = nullptr;
   size_t h_up_cap = 0, h_dn_cap = 0;
@@ -875,13 +915,14 @@ static int batch_refresh(hslam_ba_batch* B) {
   HS_CUDA(cudaEventSynchronize(B->copied));
   int* pf[NPF];
   for (int k = 0; k < NPF; ++k) { pf[k] = B->h_prefix + k * (n + 1); pf[k][0] = 0; }
-  B->smem = 0; B->maxt = 1;
+  B->smem = 0; B->maxt = 1; B->any_L = false;
   for (int i = 0; i < n; ++i) {
     hslam_ba* ba = B->items[i];
     B->h_descs[i] = ba->hdesc;
     B->versions[i] = ba->desc_version;
     int lin = std::max(1, (ba->R + LIN_THREADS - 1) / LIN_THREADS);
-    int top = ba->n_topchunks[0] + (ba->n_linearized != 0 ? ba->n_topchunks[1] : 0);
+    int top = ba->n_topchunks[0];
+    B->any_L = B->any_L || ba->n_linearized != 0;
     pf[0][i + 1] = pf[0][i] + lin;
     pf[1][i + 1] = pf[1][i] + top;
     pf[2][i + 1] = pf[2][i] + ba->n_ptchunks;
@@ -916,7 +957,7 @@ int hslam_ba_batch_create(hslam_ctx* ctx, hslam_ba* const* items, int count, hsl
   }
   // the members share the SMs: fewer, larger chunks per window (~3 waves of blocks for the whole batch)
   for (int i = 0; i < count; ++i)
-    if (items[i]->target_blocks == 0) TRY(hslam_ba_set_parallelism(items[i], std::max(16, 3 * ctx->sm_count / count)));
+    if (items[i]->target_blocks == 0) TRY(hslam_ba_set_parallelism(items[i], std::max(8, 2 * ctx->sm_count / count)));
   B->versions.assign(count, 0);
   TRY(B->d_descs.ensure(count));
   TRY(B->d_prefix.ensure(NPF * (size_t)(count + 1)));
@@ -955,8 +996,12 @@ static int batch_enqueue_accumulate(hslam_ba_batch* B) {
   const int n = (int)B->items.size();
   const int* pf = B->d_prefix.p;
   TRY(schur_attr(B->smem));
-  if (B->blocks[1] > 0)
-    HS_LAUNCH(ctx, HSLAM_K_BA_TOP, (ba_top_kernel<<<B->blocks[1], 2 * TOP_THREADS, 0, ctx->stream>>>(B->d_descs.p, pf + (n + 1), n, 0)));
+  TRY(top_attr());
+  if (B->blocks[1] > 0) {
+    HS_LAUNCH(ctx, HSLAM_K_BA_TOP, (ba_top_kernel<0><<<B->blocks[1], 2 * TOP_THREADS, kTopSmem, ctx->stream>>>(B->d_descs.p, pf + (n + 1), n)));
+    if (B->any_L)
+      HS_LAUNCH(ctx, HSLAM_K_BA_TOP, (ba_top_kernel<1><<<B->blocks[1], 2 * TOP_THREADS, kTopSmem, ctx->stream>>>(B->d_descs.p, pf + (n + 1), n)));
+  }
   if (B->blocks[2] > 0)
     HS_LAUNCH(ctx, HSLAM_K_BA_SCHUR, schur_launch(B->maxt, B->blocks[2], B->smem, ctx->stream, B->d_descs.p, pf + 2 * (n + 1), n));
   HS_LAUNCH(ctx, HSLAM_K_BA_FOLD_SC, (ba_fold_sc_kernel<<<B->blocks[4], 256, 0, ctx->stream>>>(B->d_descs.p, pf + 4 * (n + 1), B->uniform[4] ? -B->uniform[4] : n)));

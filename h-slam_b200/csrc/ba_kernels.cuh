@@ -99,6 +99,7 @@ struct BAPts {               // per-point SoA, sorted by host
 };
 
 struct TopChunk { int pair, start, count, mode; };
+struct TopTile { int start, count, chunk, pad; };   // <= 128 residuals of one pair; chunk = partial it is reduced into
 struct PtChunk { int host, start, count, pad; };
 
 struct StitchArgs {
@@ -126,6 +127,7 @@ struct BADesc {
   double* epart; unsigned int* ticket; double* energy; int lin_warps;   // lin_warps = 4 * linearise blocks
   // top
   const TopChunk* topchunks; float* toppartial; unsigned int* pair_ticket; const int* pair_chunk_begin; double* accTop;
+  const TopTile* toptiles; const int* top_block_begin; int top_blocks, top_chunks0;   // tile schedule (see ba_top_kernel)
   // schur
   const PtChunk* ptchunks; float* scpartial; unsigned int* host_ticket; const int* host_chunk_begin; double* G; int LD;
   int maxres;                // longest residual list of a point (<= HSLAM_MAX_FRAMES)
@@ -288,8 +290,9 @@ __global__ void __launch_bounds__(LIN_THREADS, LIN_MINB) ba_linearize_kernel(con
           // Pass 2: all 32 texel loads in flight at once.
           const float4* img = W.img[tgtI];
           Hit3 hit[8];
+          const uint64_t pol = l2_keep_policy();
 #pragma unroll
-          for (int idx = 0; idx < 8; ++idx) hit[idx] = interp33(img, Kup[idx], Kvp[idx], W.w);
+          for (int idx = 0; idx < 8; ++idx) hit[idx] = interp33(img, Kup[idx], Kvp[idx], W.w, pol);
           const float color[8] = {c0.x, c0.y, c0.z, c0.w, c1.x, c1.y, c1.z, c1.w};
           const float wgt[8] = {w0.x, w0.y, w0.z, w0.w, w1.x, w1.y, w1.z, w1.w};
           float II00 = 0.f, II11 = 0.f, II10 = 0.f, AI00 = 0.f, AI01 = 0.f, AI10 = 0.f, AI11 = 0.f;
@@ -545,65 +548,90 @@ __device__ __forceinline__ void top_accumulate(const BADesc& D, const TopChunk& 
   }
 }
 
-__global__ void __launch_bounds__(2 * TOP_THREADS, 2) ba_top_kernel(const BADesc* __restrict__ descs,
-                                                                    const int* __restrict__ prefix, int nwin,
-                                                                    int lb_offset) {
-  int lb;
-  const int win = find_window(prefix, nwin, blockIdx.x, lb);
-  lb += lb_offset;   // single-window launches of mode L only start at the first mode-1 chunk
-  const BADesc& D = descs[win];
-  const TopChunk ch = D.topchunks[lb];
-  const int part = threadIdx.x / TOP_THREADS;   // warp-uniform
-  float acc[55];
-#pragma unroll
-  for (int i = 0; i < 55; ++i) acc[i] = 0.f;
-  int nres = 0;
-  if (ch.mode == 0) { if (part == 0) top_accumulate<0, 0>(D, ch, acc, nres); else top_accumulate<0, 1>(D, ch, acc, nres); }
-  else              { if (part == 0) top_accumulate<1, 0>(D, ch, acc, nres); else top_accumulate<1, 1>(D, ch, acc, nres); }
+// ---- tile-scheduled top-Hessian kernel -------------------------------------------------------------------
+// The sorted residual array is cut into TILES of <= 128 residuals that never cross a (host,target) pair.
+// Block b of a window owns the contiguous run of tiles [top_block_begin[b], top_block_begin[b+1]): every
+// block of a window has the same amount of work (no wave-quantisation tail), a batch launches exactly as
+// many blocks as the device holds.  A maximal run of tiles of one pair inside a block is a CHUNK: it is
+// reduced into one fp32 partial, and the last block of a pair folds that pair's partials in chunk order.
+// Mode-A tiles are staged through shared memory with cp.async, double-buffered: the 39 Jacobian
+// components of tile i+1 stream in while tile i is accumulated (one block-wide set of loads instead of two
+// per-thread sets, and no load latency on the critical path).  Mode-L tiles (linearised residuals: few,
+// 80 components each) keep the direct per-thread path.
+constexpr int TOP_NC = 39;   // staged components: J[8..29] (Jpdxi, Jpdc, Jpdd) and J[62..78] (the 2x2 sums, JI_r, Jab_r, rr)
+__device__ __forceinline__ int top_comp(int c) { return c < 22 ? J_XI0 + c : J_IDX2 + (c - 22); }
+constexpr int TS_XI0 = 0, TS_XI1 = 6, TS_C0 = 12, TS_C1 = 16, TS_DD = 20, TS_IDX2 = 22, TS_ABIDX = 26, TS_AB2 = 30,
+              TS_JIR = 34, TS_JABR = 36, TS_RR = 38;
 
-  __shared__ float red[TOP_THREADS / 32][TOP_PART];
-  __shared__ bool last;
+__device__ __forceinline__ void cp_async16(void* smem_dst, const void* gsrc) {
+  unsigned sa = (unsigned)__cvta_generic_to_shared(smem_dst);
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(sa), "l"(gsrc) : "memory");
+}
+__device__ __forceinline__ void cp_async4(void* smem_dst, const void* gsrc) {
+  unsigned sa = (unsigned)__cvta_generic_to_shared(smem_dst);
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(sa), "l"(gsrc) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N> __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
+
+// Staging ring of the top kernel.  A tile starts anywhere in the sorted array (pair segments are not
+// aligned), cp.async wants 16-byte-aligned sources: the ring rows hold the 4-aligned span that covers the
+// tile, [start & ~3, start + count) rounded up, at most 128 + 3 + 3 -> TOP_ROW columns; residual l of the tile
+// sits in column (start & 3) + l.
+constexpr int TOP_STAGES = 4;
+constexpr int TOP_ROW = 136;
+struct TopStage {
+  float v[TOP_NC][TOP_ROW];
+  unsigned char lin[TOP_ROW], act[TOP_ROW];
+};
+static_assert(sizeof(TopStage) % 16 == 0, "stage must keep 16-byte alignment");
+
+// chunk partial -> global, then the per-(mode,pair) fold by the last block of that pair (chunks in index order)
+__device__ __forceinline__ void top_flush(const BADesc& D, int chunk, int part, float (&acc)[55], int nres,
+                                          float (*red)[33], bool* last) {
+  // two shuffle levels take a warp's 32 lanes to 8, the remaining 8 lanes x 4 warps = 32 values per
+  // accumulator are summed in a fixed order by one thread per accumulator (a full shuffle tree per
+  // accumulator costs 10 instructions x 91 per warp; this is 4 x 91 + a 32-term sum by 92 threads)
   const int lane = threadIdx.x & 31, wid = (threadIdx.x >> 5) & (TOP_THREADS / 32 - 1);
-  if (part == 0) {
+  const int nacc = part == 0 ? 55 : 36, base = part == 0 ? 0 : 55;
 #pragma unroll
-    for (int i = 0; i < 55; ++i) {
-      float v = warp_sum(acc[i]);
-      if (lane == 0) red[wid][i] = v;
+  for (int i = 0; i < 55; ++i) {
+    if (i < nacc) {
+      float v = acc[i];
+      v += __shfl_down_sync(0xffffffffu, v, 16);
+      v += __shfl_down_sync(0xffffffffu, v, 8);
+      if (lane < 8) red[base + i][wid * 8 + lane] = v;
     }
-  } else {
-#pragma unroll
-    for (int i = 0; i < 36; ++i) {
-      float v = warp_sum(acc[i]);
-      if (lane == 0) red[wid][55 + i] = v;
-    }
+  }
+  if (part == 1) {
     int q = warp_sum(nres);
-    if (lane == 0) red[wid][91] = __int_as_float(q);
+    if (lane == 0) red[91][wid] = __int_as_float(q);
   }
   __syncthreads();
-  float* out = D.toppartial + (size_t)lb * TOP_PART;
+  float* out = D.toppartial + (size_t)chunk * TOP_PART;
   if (threadIdx.x < 92) {
     int t = threadIdx.x;
     if (t == 91) {
       int n = 0;
 #pragma unroll
-      for (int w = 0; w < TOP_THREADS / 32; ++w) n += __float_as_int(red[w][91]);
+      for (int w = 0; w < TOP_THREADS / 32; ++w) n += __float_as_int(red[91][w]);
       out[91] = __int_as_float(n);
     } else {
       float v = 0.f;
 #pragma unroll
-      for (int w = 0; w < TOP_THREADS / 32; ++w) v += red[w][t];
+      for (int w = 0; w < 32; ++w) v += red[t][w];
       out[t] = v;
     }
     __threadfence();
   }
   __syncthreads();
-  // ---- per-(mode,pair) fold by the last block of that pair, chunks visited in index order
+  const TopChunk ch = D.topchunks[chunk];
   const int nn = D.W.n * D.W.n;
   const int slot = ch.mode * nn + ch.pair;
   const int cb = D.pair_chunk_begin[slot], ce = D.pair_chunk_begin[slot + 1];
-  if (threadIdx.x == 0) last = (atomicAdd(D.pair_ticket + slot, 1u) == (unsigned)(ce - cb) - 1);
+  if (threadIdx.x == 0) *last = (atomicAdd(D.pair_ticket + slot, 1u) == (unsigned)(ce - cb) - 1);
   __syncthreads();
-  if (last) {
+  if (*last) {
     __threadfence();
     if (threadIdx.x < 92) {
       int t = threadIdx.x;
@@ -620,6 +648,122 @@ __global__ void __launch_bounds__(2 * TOP_THREADS, 2) ba_top_kernel(const BADesc
     }
     if (threadIdx.x == 0) D.pair_ticket[slot] = 0;
   }
+  __syncthreads();   // `last` and `red` are reused by the next chunk
+}
+
+template <int MODE>
+__global__ void __launch_bounds__(2 * TOP_THREADS, 2) ba_top_kernel(const BADesc* __restrict__ descs,
+                                                                    const int* __restrict__ prefix, int nwin) {
+  extern __shared__ __align__(16) unsigned char top_smem[];
+  TopStage* ring = reinterpret_cast<TopStage*>(top_smem);
+  __shared__ float red[92][33];   // [accumulator][4 warps x 8 lanes], padded: conflict-free both ways
+  __shared__ bool last;
+  int lb;
+  const int win = find_window(prefix, nwin, blockIdx.x, lb);
+  const BADesc& D = descs[win];
+  const BARes& r = D.r;
+  const int s = r.rs;
+  constexpr int mode = MODE;   // modes A and L are separate launches over the same tile schedule
+  const int bIdx = lb;
+  const int t0 = D.top_block_begin[bIdx], t1 = D.top_block_begin[bIdx + 1];
+  const int part = threadIdx.x / TOP_THREADS;   // warp-uniform
+  const int l = threadIdx.x & (TOP_THREADS - 1);
+  float acc[55];
+#pragma unroll
+  for (int i = 0; i < 55; ++i) acc[i] = 0.f;
+  int nres = 0, cur = -1;
+
+  // all 256 threads: 39 rows x 34 sixteen-byte copies (always the full row: constant trip count and constant
+  // divisor; the columns past the tile are never read) + the two flag rows; one commit group per tile
+  constexpr int RQ = TOP_ROW / 4;
+  auto issue = [&](int t) {
+    if (mode == 0 && t < t1) {
+      const TopTile tl = D.toptiles[t];
+      TopStage& st = ring[(t - t0) % TOP_STAGES];
+      const float* src = r.J + (tl.start & ~3);
+#pragma unroll
+      for (int j = 0; j < (TOP_NC * RQ + 2 * TOP_THREADS - 1) / (2 * TOP_THREADS); ++j) {
+        const int i = threadIdx.x + j * 2 * TOP_THREADS;
+        const int c = i / RQ, q = i - c * RQ;
+        if (i < TOP_NC * RQ) cp_async16(&st.v[c][4 * q], src + (size_t)top_comp(c) * s + 4 * q);
+      }
+      const int nq = ((tl.start + tl.count + 3) >> 2) - (tl.start >> 2);   // flag words that cover the tile
+      if (threadIdx.x < nq) cp_async4(&st.lin[4 * threadIdx.x], r.isLin + (tl.start & ~3) + 4 * threadIdx.x);
+      else if (threadIdx.x >= 64 && threadIdx.x < 64 + nq)
+        cp_async4(&st.act[4 * (threadIdx.x - 64)], r.isActive + (tl.start & ~3) + 4 * (threadIdx.x - 64));
+    }
+    cp_async_commit();   // always: keeps the group count in step with the tile count
+  };
+#pragma unroll
+  for (int i = 0; i < TOP_STAGES - 1; ++i) issue(t0 + i);
+
+  for (int t = t0; t < t1; ++t) {
+    const TopTile tl = D.toptiles[t];
+    issue(t + TOP_STAGES - 1);   // refills the stage that was consumed in the previous iteration
+    const int chunk = tl.chunk + mode * D.top_chunks0;
+    if (chunk != cur) {
+      if (cur >= 0) {
+        top_flush(D, cur, part, acc, nres, red, &last);
+#pragma unroll
+        for (int i = 0; i < 55; ++i) acc[i] = 0.f;
+        nres = 0;
+      }
+      cur = chunk;
+    }
+    if (mode == 1) {
+      const TopChunk ch = {D.topchunks[chunk].pair, tl.start, tl.count, 1};
+      if (part == 0) top_accumulate<1, 0>(D, ch, acc, nres); else top_accumulate<1, 1>(D, ch, acc, nres);
+      continue;
+    }
+    cp_async_wait<TOP_STAGES - 1>();   // the group of tile t has landed (for this thread's copies)
+    __syncthreads();                   // ... and for everyone's
+    const TopStage& S = ring[(t - t0) % TOP_STAGES];
+    const int col = (tl.start & 3) + l;
+    // AccumulatedTopHessian.cpp:37-49, mode 0: !isLinearized && isActive
+    if (l < tl.count && S.lin[col] == 0 && S.act[col] != 0) {
+      float x[10], y[10];
+#pragma unroll
+      for (int j = 0; j < 4; ++j) { x[j] = S.v[TS_C0 + j][col]; y[j] = S.v[TS_C1 + j][col]; }
+#pragma unroll
+      for (int j = 0; j < 6; ++j) { x[4 + j] = S.v[TS_XI0 + j][col]; y[4 + j] = S.v[TS_XI1 + j][col]; }
+      const float a = S.v[TS_IDX2 + 0][col], b = S.v[TS_IDX2 + 2][col], c = S.v[TS_IDX2 + 3][col];
+      if (part == 0) {
+        // 10x10 upper triangle: [x y] [[a b],[b c]] [x y]^T
+        int idx = 0;
+#pragma unroll
+        for (int rI = 0; rI < 10; ++rI) {
+          float px = fmaf(a, x[rI], b * y[rI]), py = fmaf(b, x[rI], c * y[rI]);
+#pragma unroll
+          for (int cI = rI; cI < 10; ++cI, ++idx) acc[idx] += fmaf(x[cI], px, y[cI] * py);
+        }
+      } else {
+        const float AI00 = S.v[TS_ABIDX + 0][col], AI10 = S.v[TS_ABIDX + 1][col], AI01 = S.v[TS_ABIDX + 2][col],
+                    AI11 = S.v[TS_ABIDX + 3][col];
+        const float AA00 = S.v[TS_AB2 + 0][col], AA01 = S.v[TS_AB2 + 2][col], AA11 = S.v[TS_AB2 + 3][col];
+        const float JIr0 = S.v[TS_JIR][col], JIr1 = S.v[TS_JIR + 1][col], Jabr0 = S.v[TS_JABR][col], Jabr1 = S.v[TS_JABR + 1][col];
+        const float rr = S.v[TS_RR][col], d0 = S.v[TS_DD][col], d1 = S.v[TS_DD + 1][col];
+        // 10x3 top-right: columns a, b, r  (MatrixAccumulators.h:859-901); entries 55..84 -> acc[0..29]
+#pragma unroll
+        for (int rI = 0; rI < 10; ++rI) {
+          acc[3 * rI + 0] += fmaf(x[rI], AI00, y[rI] * AI01);
+          acc[3 * rI + 1] += fmaf(x[rI], AI10, y[rI] * AI11);
+          acc[3 * rI + 2] += fmaf(x[rI], JIr0, y[rI] * JIr1);
+        }
+        acc[30] += AA00; acc[31] += AA01; acc[32] += Jabr0; acc[33] += AA11; acc[34] += Jabr1; acc[35] += rr;
+        nres++;
+        // per-residual contribution to the point sums (:114-117), exact ops: they are summed per point in
+        // the point's own order by the Schur kernel, which keeps Hdd/bd/Hcd bit-identical to the oracle.
+        const float Ji0 = xadd(xmul(a, d0), xmul(b, d1)), Ji1 = xadd(xmul(b, d0), xmul(c, d1));
+        float* o = r.ptc[0] + tl.start + l;
+        o[0] = xadd(xmul(JIr0, d0), xmul(JIr1, d1));
+        o[s] = xadd(xmul(Ji0, d0), xmul(Ji1, d1));
+#pragma unroll
+        for (int j = 0; j < 4; ++j) o[(2 + j) * s] = xadd(xmul(x[j], Ji0), xmul(y[j], Ji1));
+      }
+    }
+    __syncthreads();   // everyone is done with this stage before the next iteration refills it
+  }
+  if (cur >= 0) top_flush(D, cur, part, acc, nres, red, &last);
 }
 
 // Per-point sums of Hdd/bd/Hcd over the point's residuals in the point's own order (the tail of

@@ -46,12 +46,35 @@ __device__ __forceinline__ float xdot3(float m0, float m1, float m2, float x, fl
 // getInterpolatedElement33 (Include/GlobalTypes.h:377-388) on the float4 {I,dx,dy,absgrad} image.
 // Four 16-byte texel loads through the read-only path.
 struct Hit3 { float I, dx, dy; };
-__device__ __forceinline__ Hit3 interp33(const float4* __restrict__ img, float x, float y, int width) {
+// L2 "evict_last" policy for the pyramid texels: the images are re-read by every residual of the window
+// (and by every LM iteration of the tracker) while the Jacobian streams are written once, so the images
+// are the lines worth keeping in L2.
+__device__ __forceinline__ uint64_t l2_keep_policy() {
+  uint64_t pol;
+  asm("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(pol));
+  return pol;
+}
+__device__ __forceinline__ float4 ldg_keep(const float4* p, uint64_t pol) {
+  float4 v;
+  asm("ld.global.nc.L2::cache_hint.v4.f32 {%0, %1, %2, %3}, [%4], %5;"
+      : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "l"(p), "l"(pol));
+  return v;
+}
+#ifndef HS_TEXEL_L2_KEEP
+#define HS_TEXEL_L2_KEEP 1
+#endif
+__device__ __forceinline__ Hit3 interp33(const float4* __restrict__ img, float x, float y, int width, uint64_t pol = 0) {
   int ix = (int)x, iy = (int)y;
   float dx = xsub(x, (float)ix), dy = xsub(y, (float)iy);
   float dxdy = xmul(dx, dy);
   const float4* bp = img + ix + iy * width;
+#if HS_TEXEL_L2_KEEP
+  float4 tl, tr, bl, br;
+  if (pol) { tl = ldg_keep(bp, pol); tr = ldg_keep(bp + 1, pol); bl = ldg_keep(bp + width, pol); br = ldg_keep(bp + width + 1, pol); }
+  else { tl = __ldg(bp); tr = __ldg(bp + 1); bl = __ldg(bp + width); br = __ldg(bp + width + 1); }
+#else
   float4 tl = __ldg(bp), tr = __ldg(bp + 1), bl = __ldg(bp + width), br = __ldg(bp + width + 1);
+#endif
   float wBR = dxdy, wBL = xsub(dy, dxdy), wTR = xsub(dx, dxdy);
   float wTL = xadd(xsub(xsub(1.0f, dx), dy), dxdy);
   Hit3 h;

@@ -354,7 +354,7 @@ int hslam_ba_allreduce(hslam_ba* ba, void* nccl_comm);
  * residual / point lists are cut into that many chunks, each reduced into one fp32 partial, the partials
  * are folded in chunk order in fp64: the value changes the grouping of the fp32 sums (results agree to
  * fp32 round-off, each setting is deterministic).  hslam_ba_batch_create sets it for members that still
- * have the default, so that the whole batch fills the device about three times. */
+ * have the default, so that the whole batch launches about two blocks per SM and stage. */
 int hslam_ba_set_parallelism(hslam_ba* ba, int target_blocks);
 int hslam_ba_get_parallelism(hslam_ba* ba, int* target_blocks_out);
 /* In a sharded window only one rank may add the priors (cPrior, frame priors):
