@@ -238,9 +238,9 @@ def main():
 
     # ---- e2e: the same GN iteration through the C ABI with HOST buffers, copies inside the timed region
     N = 8 * N_FRAMES + 4
-    xs = [np.random.default_rng(i).normal(0, 1e-4, N) for i in range(len(wins))]
+    xs = [np.ascontiguousarray(np.random.default_rng(i).normal(0, 1e-4, N)) for i in range(len(wins))]
 
-    io = batch.make_io(wins, frames_all, pinned=True)     # caller-side buffers (page-locked via hslam_host_alloc)
+    io = batch.make_io(wins, frames_all, pinned="bound")  # outputs live in the batch's page-locked result block (zero-copy views)
 
     def step_e2e():
         # phase 1: ONE C-ABI call for the batch — host tables + per-point state up (one H2D block), linearizeAll +

@@ -481,24 +481,44 @@ class EnergyFunctionalBatch:
 
     def make_io(self, wins, frames_per_window, pinned=True):
         """Persistent host-side I/O block for step_host(): per window the hslam_window struct, the per-point
-        inputs and the output arrays (page-locked when `pinned`)."""
+        inputs and the output arrays.  pinned="bound": the outputs are views of the batch's own page-locked
+        result block (hslam_ba_batch_io_bind, zero-copy); True: separate page-locked arrays (hslam_host_alloc,
+        direct DMA); False: ordinary numpy arrays (staged + memcpy)."""
         n = len(self.efs)
         arr = (StepIO * n)()
         keep, outs = [], []
         for i, (ef, w, fr) in enumerate(zip(self.efs, wins, frames_per_window)):
             ws, ka = EnergyFunctional.window_struct(w, fr)
-            N = 8 * w.n + 4
-            mk = (lambda shape, dt: self.ctx.host_empty(shape, dt)) if pinned else (lambda shape, dt: np.zeros(shape, dt))
-            o = dict(energy=mk(1, np.float64), newState=mk(ef.R, np.int8), newEnergy=mk(ef.R, np.float32),
-                     newEnergyWithOutlier=mk(ef.R, np.float32), Hb=mk(3 * (N * N + N), np.float64), nres2=mk(2, np.int32),
-                     step=mk(ef.P, np.float32))
             inp = dict(idepth=np.ascontiguousarray(w.idepth, np.float32), deltaF=np.ascontiguousarray(w.deltaF, np.float32))
             arr[i].window = C.cast(C.pointer(ws), C.c_void_p)
             arr[i].idepth, arr[i].deltaF, arr[i].idepth_zero = _ptr(inp["idepth"]), _ptr(inp["deltaF"]), None
-            for k in ("energy", "newState", "newEnergy", "newEnergyWithOutlier", "Hb", "nres2"):
-                setattr(arr[i], k, _ptr(o[k]))
             keep.append((ws, ka, inp))
-            outs.append(o)
+        names = ("energy", "newState", "newEnergy", "newEnergyWithOutlier", "Hb", "nres2")
+        if pinned == "bound":
+            steps = (C.c_void_p * n)()
+            _chk(self.L.hslam_ba_batch_io_bind(self.h, arr, steps))
+
+            def view(addr, count, dt):
+                dt = np.dtype(dt)
+                buf = (C.c_char * (count * dt.itemsize)).from_address(addr)
+                return np.frombuffer(buf, dtype=dt, count=count)
+            for i, (ef, w) in enumerate(zip(self.efs, wins)):
+                N = 8 * w.n + 4
+                outs.append(dict(energy=view(arr[i].energy, 1, np.float64), newState=view(arr[i].newState, ef.R, np.int8),
+                                 newEnergy=view(arr[i].newEnergy, ef.R, np.float32),
+                                 newEnergyWithOutlier=view(arr[i].newEnergyWithOutlier, ef.R, np.float32),
+                                 Hb=view(arr[i].Hb, 3 * (N * N + N), np.float64), nres2=view(arr[i].nres2, 2, np.int32),
+                                 step=view(steps[i], ef.P, np.float32)))
+        else:
+            mk = (lambda shape, dt: self.ctx.host_empty(shape, dt)) if pinned else (lambda shape, dt: np.zeros(shape, dt))
+            for i, (ef, w) in enumerate(zip(self.efs, wins)):
+                N = 8 * w.n + 4
+                o = dict(energy=mk(1, np.float64), newState=mk(ef.R, np.int8), newEnergy=mk(ef.R, np.float32),
+                         newEnergyWithOutlier=mk(ef.R, np.float32), Hb=mk(3 * (N * N + N), np.float64), nres2=mk(2, np.int32),
+                         step=mk(ef.P, np.float32))
+                for k in names:
+                    setattr(arr[i], k, _ptr(o[k]))
+                outs.append(o)
         return dict(arr=arr, keep=keep, out=outs)
 
     def step_host(self, io):
@@ -510,8 +530,9 @@ class EnergyFunctionalBatch:
         n = len(self.efs)
         xa = [np.ascontiguousarray(x, np.float64) for x in xs]
         xp = (C.c_void_p * n)(*[a.ctypes.data for a in xa])
-        sp = (C.c_void_p * n)(*[o["step"].ctypes.data for o in io["out"]])
-        _chk(self.L.hslam_ba_batch_resubstitute_host(self.h, xp, sp))
+        if "step_ptrs" not in io:
+            io["step_ptrs"] = (C.c_void_p * n)(*[o["step"].ctypes.data for o in io["out"]])
+        _chk(self.L.hslam_ba_batch_resubstitute_host(self.h, xp, io["step_ptrs"]))
         return [o["step"] for o in io["out"]]
 
     def close(self):

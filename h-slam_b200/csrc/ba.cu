@@ -900,6 +900,7 @@ struct hslam_ba_batch {
   DevBuf<char> d_up, d_dn;
   DevBuf<BAIO> d_io;
   std::vector<BAIO> io;
+  size_t dn_res_end = 0, dn_sys_end = 0, dn_end = 0;   // D2H block regions: [0,res) per-residual arrays, [res,sys) systems, [sys,end) steps
 };
 static const int NPF = 6;
 
@@ -1054,20 +1055,61 @@ static int window_scalars(hslam_ba* ba, const hslam_window* w) {
   return 0;
 }
 
+// Fixed layout of the D2H block: every output of every window has its slot, whether or not a call asks for it
+// (hslam_ba_batch_io_bind hands these slots out as the caller's buffers).
+static int batch_layout_down(hslam_ba_batch* B) {
+  const int n = (int)B->items.size();
+  size_t dn = 0;
+  auto take = [&](size_t bytes) { long long off = (long long)dn; dn = al256(dn + bytes); return off; };
+  for (int i = 0; i < n; ++i) {
+    const size_t R = B->items[i]->R;
+    B->io[i].dn_newEnergy = take(R * 4); B->io[i].dn_newEnergyWO = take(R * 4); B->io[i].dn_newState = take(R);
+  }
+  B->dn_res_end = dn;
+  for (int i = 0; i < n; ++i) {
+    const size_t N = B->items[i]->N;
+    B->io[i].dn_energy = take(8); B->io[i].dn_nres = take(8); B->io[i].dn_Hb = take(3 * (N * N + N) * 8);
+  }
+  B->dn_sys_end = dn;
+  for (int i = 0; i < n; ++i) B->io[i].dn_step = take((size_t)B->items[i]->P * 4);
+  B->dn_end = dn;
+  TRY(B->d_dn.ensure(std::max(dn, (size_t)256)));
+  TRY(pinned_ensure(&B->h_dn, &B->h_dn_cap, std::max(dn, (size_t)256)));
+  return 0;
+}
+
+int hslam_ba_batch_io_bind(hslam_ba_batch* B, hslam_ba_step_io* io, float** step_out) {
+  HS_ARG(B && io, "hslam_ba_batch_io_bind: null argument");
+  HS_CUDA(cudaSetDevice(B->ctx->device));
+  HS_CUDA(cudaStreamSynchronize(B->ctx->stream));
+  TRY(batch_layout_down(B));
+  const int n = (int)B->items.size();
+  for (int i = 0; i < n; ++i) {
+    const BAIO& L = B->io[i];
+    io[i].energy = (double*)(B->h_dn + L.dn_energy); io[i].nres2 = (int32_t*)(B->h_dn + L.dn_nres);
+    io[i].Hb = (double*)(B->h_dn + L.dn_Hb);
+    io[i].newEnergy = (float*)(B->h_dn + L.dn_newEnergy); io[i].newEnergyWithOutlier = (float*)(B->h_dn + L.dn_newEnergyWO);
+    io[i].newState = (int8_t*)(B->h_dn + L.dn_newState);
+    if (step_out) step_out[i] = (float*)(B->h_dn + L.dn_step);
+  }
+  return 0;
+}
+
 int hslam_ba_batch_step_host(hslam_ba_batch* B, const hslam_ba_step_io* io) {
   HS_ARG(B && io, "hslam_ba_batch_step_host: null argument");
   hslam_ctx* ctx = B->ctx;
   HS_CUDA(cudaSetDevice(ctx->device));
   const int n = (int)B->items.size();
   // ---- layout of the two staging blocks
-  size_t up = 0, dn = 0;
+  TRY(batch_layout_down(B));
+  size_t up = 0;
   int maxP = 1, maxR = 1;
   for (int i = 0; i < n; ++i) {
     hslam_ba* ba = B->items[i];
     HS_ARG(ba->have_window && ba->have_topology, "hslam_ba_batch_step_host: a window has no window/topology set");
     const hslam_ba_step_io& o = io[i];
     BAIO& L = B->io[i];
-    const size_t nn = (size_t)ba->n * ba->n, P = ba->P, R = ba->R, N = ba->N;
+    const size_t nn = (size_t)ba->n * ba->n, P = ba->P;
     auto take = [](size_t& cur, size_t bytes) { long long off = (long long)cur; cur = al256(cur + bytes); return off; };
     if (o.window) {
       TRY(window_scalars(ba, o.window));
@@ -1081,20 +1123,11 @@ int hslam_ba_batch_step_host(hslam_ba_batch* B, const hslam_ba_step_io* io) {
     L.up_deltaF = o.deltaF ? take(up, P * 4) : -1;
     L.up_idz = o.idepth_zero ? take(up, P * 4) : -1;
     L.up_x = -1;
-    L.dn_energy = o.energy ? take(dn, 8) : -1;
-    L.dn_nres = o.nres2 ? take(dn, 8) : -1;
-    L.dn_Hb = o.Hb ? take(dn, 3 * (N * N + N) * 8) : -1;
-    L.dn_newEnergy = o.newEnergy ? take(dn, R * 4) : -1;
-    L.dn_newEnergyWO = o.newEnergyWithOutlier ? take(dn, R * 4) : -1;
-    L.dn_newState = o.newState ? take(dn, R) : -1;
-    L.dn_step = -1;
     maxP = std::max(maxP, ba->P); maxR = std::max(maxR, ba->R);
   }
   const size_t io_bytes = al256(n * sizeof(BAIO));
   TRY(pinned_ensure(&B->h_up, &B->h_up_cap, up + io_bytes));
   TRY(B->d_up.ensure(up + io_bytes));
-  TRY(B->d_dn.ensure(std::max(dn, (size_t)256)));
-  TRY(pinned_ensure(&B->h_dn, &B->h_dn_cap, std::max(dn, (size_t)256)));   // staging for pageable caller buffers
   // ---- pack: [BAIO table][window 0 tables + point arrays][window 1 ...]
   memcpy(B->h_up + up, B->io.data(), n * sizeof(BAIO));
   for (int i = 0; i < n; ++i) {
@@ -1122,17 +1155,21 @@ int hslam_ba_batch_step_host(hslam_ba_batch* B, const hslam_ba_step_io* io) {
     dim3 grid((unsigned)std::max(1, std::min(64, (maxP + 255) / 256)), (unsigned)n);
     HS_LAUNCH(ctx, HSLAM_K_BA_EXPORT, (ba_batch_import_kernel<<<grid, 256, 0, ctx->stream>>>(B->d_descs.p, d_io, B->d_up.p)));
   }
-  // ---- results: straight into the caller's buffers where they are pinned (hslam_host_alloc), else through
-  // the pinned block + memcpy after the synchronisation.  The per-residual arrays are final after the
-  // linearise kernel: they are exported and copied on the side stream WHILE the accumulate kernels run.
+  // ---- results.  Three kinds of caller buffer: a slot of the batch's own pinned block (hslam_ba_batch_io_bind:
+  // nothing to do, the two bulk copies below fill it), other pinned memory (hslam_host_alloc: direct DMA per
+  // array), pageable memory (memcpy from the pinned block after the synchronisation).  The per-residual arrays
+  // are final after the linearise kernel: they are exported and copied on the side stream WHILE the accumulate
+  // kernels run.
   struct Out { void* dst; long long off; size_t bytes; };
   std::vector<Out> staged;
-  auto emit = [&](cudaStream_t st, void* dst, long long off, size_t bytes) -> int {
-    if (!dst || off < 0 || bytes == 0) return 0;
+  bool bulk_res = false, bulk_sys = false;
+  auto emit = [&](cudaStream_t st, bool& bulk, void* dst, long long off, size_t bytes) -> int {
+    if (!dst || bytes == 0) return 0;
+    if (dst == (void*)(B->h_dn + off)) { bulk = true; return 0; }
     if (ctx->is_pinned(dst, bytes)) {
       HS_CUDA(cudaMemcpyAsync(dst, B->d_dn.p + off, bytes, cudaMemcpyDeviceToHost, st));
     } else {
-      HS_CUDA(cudaMemcpyAsync(B->h_dn + off, B->d_dn.p + off, bytes, cudaMemcpyDeviceToHost, st));
+      bulk = true;
       staged.push_back({dst, off, bytes});
     }
     return 0;
@@ -1152,10 +1189,11 @@ int hslam_ba_batch_step_host(hslam_ba_batch* B, const hslam_ba_step_io* io) {
     HS_CUDA(cudaGetLastError());
     for (int i = 0; i < n; ++i) {
       const size_t R = B->items[i]->R;
-      TRY(emit(ctx->side, io[i].newEnergy, B->io[i].dn_newEnergy, R * 4));
-      TRY(emit(ctx->side, io[i].newEnergyWithOutlier, B->io[i].dn_newEnergyWO, R * 4));
-      TRY(emit(ctx->side, io[i].newState, B->io[i].dn_newState, R));
+      TRY(emit(ctx->side, bulk_res, io[i].newEnergy, B->io[i].dn_newEnergy, R * 4));
+      TRY(emit(ctx->side, bulk_res, io[i].newEnergyWithOutlier, B->io[i].dn_newEnergyWO, R * 4));
+      TRY(emit(ctx->side, bulk_res, io[i].newState, B->io[i].dn_newState, R));
     }
+    if (bulk_res) HS_CUDA(cudaMemcpyAsync(B->h_dn, B->d_dn.p, B->dn_res_end, cudaMemcpyDeviceToHost, ctx->side));
     HS_CUDA(cudaEventRecord(ctx->ev_join, ctx->side));
   }
   TRY(batch_enqueue_accumulate(B));
@@ -1164,9 +1202,12 @@ int hslam_ba_batch_step_host(hslam_ba_batch* B, const hslam_ba_step_io* io) {
     HS_CUDA(cudaGetLastError());
     for (int i = 0; i < n; ++i) {
       const size_t N = B->items[i]->N;
-      TRY(emit(ctx->stream, io[i].energy, B->io[i].dn_energy, 8)); TRY(emit(ctx->stream, io[i].nres2, B->io[i].dn_nres, 8));
-      TRY(emit(ctx->stream, io[i].Hb, B->io[i].dn_Hb, 3 * (N * N + N) * 8));
+      TRY(emit(ctx->stream, bulk_sys, io[i].energy, B->io[i].dn_energy, 8)); TRY(emit(ctx->stream, bulk_sys, io[i].nres2, B->io[i].dn_nres, 8));
+      TRY(emit(ctx->stream, bulk_sys, io[i].Hb, B->io[i].dn_Hb, 3 * (N * N + N) * 8));
     }
+    if (bulk_sys)
+      HS_CUDA(cudaMemcpyAsync(B->h_dn + B->dn_res_end, B->d_dn.p + B->dn_res_end, B->dn_sys_end - B->dn_res_end,
+                              cudaMemcpyDeviceToHost, ctx->stream));
   }
   if (any_res) HS_CUDA(cudaStreamWaitEvent(ctx->stream, ctx->ev_join, 0));   // the context stream stays the one to wait on
   HS_CUDA(cudaStreamSynchronize(ctx->stream));
@@ -1179,19 +1220,18 @@ int hslam_ba_batch_resubstitute_host(hslam_ba_batch* B, const double* const* x, 
   hslam_ctx* ctx = B->ctx;
   HS_CUDA(cudaSetDevice(ctx->device));
   const int n = (int)B->items.size();
-  size_t up = 0, dn = 0;
+  TRY(batch_layout_down(B));
+  size_t up = 0;
   for (int i = 0; i < n; ++i) {
     hslam_ba* ba = B->items[i];
     HS_ARG(ba->have_window && ba->have_topology && x[i], "hslam_ba_batch_resubstitute_host: window not set or null x");
     BAIO& L = B->io[i];
-    memset(&L, 0xff, sizeof(BAIO));   // every offset = -1
+    L.up_precalc = L.up_adHTd = L.up_adH = L.up_adT = L.up_fprior = L.up_fdprior = L.up_idepth = L.up_deltaF = L.up_idz = -1;
     L.up_x = (long long)up; up = al256(up + (size_t)ba->N * 8);
-    if (step_out[i]) { L.dn_step = (long long)dn; dn = al256(dn + (size_t)ba->P * 4); }
   }
   const size_t io_bytes = al256(n * sizeof(BAIO));
   TRY(pinned_ensure(&B->h_up, &B->h_up_cap, up + io_bytes));
   TRY(B->d_up.ensure(up + io_bytes));
-  TRY(B->d_dn.ensure(std::max(dn, (size_t)256)));
   memcpy(B->h_up + up, B->io.data(), n * sizeof(BAIO));
   for (int i = 0; i < n; ++i) memcpy(B->h_up + B->io[i].up_x, x[i], (size_t)B->items[i]->N * 8);
   TRY(batch_refresh(B));
@@ -1203,25 +1243,20 @@ int hslam_ba_batch_resubstitute_host(hslam_ba_batch* B, const double* const* x, 
     HS_LAUNCH(ctx, HSLAM_K_BA_RESUB, (ba_resub_kernel<<<B->blocks[5], 128, 0, ctx->stream>>>(
                                          B->d_descs.p, B->d_prefix.p + 5 * (n + 1), n, d_io, B->d_dn.p)));
   HS_CUDA(cudaGetLastError());
-  bool any_staged = false;
+  bool bulk = false;
+  std::vector<int> staged;
   for (int i = 0; i < n; ++i) {
     if (!step_out[i]) continue;
     const size_t bytes = (size_t)B->items[i]->P * 4;
-    if (ctx->is_pinned(step_out[i], bytes))
+    if ((void*)step_out[i] == (void*)(B->h_dn + B->io[i].dn_step)) bulk = true;
+    else if (ctx->is_pinned(step_out[i], bytes))
       HS_CUDA(cudaMemcpyAsync(step_out[i], B->d_dn.p + B->io[i].dn_step, bytes, cudaMemcpyDeviceToHost, ctx->stream));
-    else
-      any_staged = true;
+    else { bulk = true; staged.push_back(i); }
   }
-  if (any_staged) {
-    TRY(pinned_ensure(&B->h_dn, &B->h_dn_cap, dn));
-    HS_CUDA(cudaMemcpyAsync(B->h_dn, B->d_dn.p, dn, cudaMemcpyDeviceToHost, ctx->stream));
-  }
+  if (bulk)
+    HS_CUDA(cudaMemcpyAsync(B->h_dn + B->dn_sys_end, B->d_dn.p + B->dn_sys_end, B->dn_end - B->dn_sys_end, cudaMemcpyDeviceToHost, ctx->stream));
   HS_CUDA(cudaStreamSynchronize(ctx->stream));
-  if (any_staged)
-    for (int i = 0; i < n; ++i) {
-      const size_t bytes = (size_t)B->items[i]->P * 4;
-      if (step_out[i] && !ctx->is_pinned(step_out[i], bytes)) memcpy(step_out[i], B->h_dn + B->io[i].dn_step, bytes);
-    }
+  for (int i : staged) memcpy(step_out[i], B->h_dn + B->io[i].dn_step, (size_t)B->items[i]->P * 4);
   return 0;
 }
 

@@ -339,6 +339,11 @@ typedef struct hslam_ba_step_io {
   int32_t* nres2;                  /* {resInA, resInL} */
 } hslam_ba_step_io;
 int hslam_ba_batch_step_host(hslam_ba_batch* batch, const hslam_ba_step_io* io /* one per window */);
+/* Zero-copy outputs: point every OUTPUT member of io[0..count) (and step_out[i], if not null) at the window's
+ * slot in the batch's own page-locked result block.  Results then arrive with two bulk copies per call and
+ * no per-array work; the caller reads them in place (e.g. Eigen::Map).  The pointers stay valid until a
+ * member's topology changes or the batch is destroyed. */
+int hslam_ba_batch_io_bind(hslam_ba_batch* batch, hslam_ba_step_io* io, float** step_out /*nullable*/);
 /* EnergyFunctional::resubstituteF_MT for every window of the batch: x[i] = (8n+4) host doubles,
  * step_out[i] = P host floats (nullable). */
 int hslam_ba_batch_resubstitute_host(hslam_ba_batch* batch, const double* const* x, float* const* step_out);

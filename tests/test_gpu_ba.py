@@ -252,7 +252,7 @@ def test_async_calls_match_sync(ctx, capi, synth, window_small):
         f.close()
 
 
-@pytest.mark.parametrize("pinned", [True, False])
+@pytest.mark.parametrize("pinned", ["bound", True, False])
 def test_batch_step_host_matches_single_window_calls(ctx, capi, synth, pinned):
     """hslam_ba_batch_step_host / _resubstitute_host (one staging block up, one down) == the per-window
     host calls (set_window, update_points, linearize, applyRes, accumulate_all, resubstitute), bit for bit,
