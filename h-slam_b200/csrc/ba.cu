@@ -283,24 +283,40 @@ static int build_chunks(hslam_ba* ba) {
     HS_CUDA(cudaMemsetAsync(ba->d_accTop.p, 0, 2 * (size_t)nn * TOP_PART * sizeof(double), ctx->stream));
   }
   {
-    const int sc_blocks = 2 * target_blocks;   // the Schur kernel holds 4 blocks per SM, the top kernel 2
-    int chunk = ((P + sc_blocks - 1) / sc_blocks + SC_PTS - 1) / SC_PTS * SC_PTS;
-    if (chunk < SC_PTS) chunk = SC_PTS;
+    // Chunks are cut in whole
+    // sub-tiles of SC_PTS points, as evenly as possible within a host, and a little below the target so that
+    // every block of a launch is resident at once (no second, nearly empty wave).
+    int total_sub = 0;
+    for (int h = 0; h < n; ++h) total_sub += (hostBegin[h + 1] - hostBegin[h] + SC_PTS - 1) / SC_PTS;
+#ifndef SC_BLOCKS_NUM
+#define SC_BLOCKS_NUM 3
+#define SC_BLOCKS_DEN 2
+#endif
+    int sc_blocks = SC_BLOCKS_NUM * target_blocks / SC_BLOCKS_DEN;
+    if (sc_blocks > 4 * n) sc_blocks -= n;
+    if (sc_blocks < 1) sc_blocks = 1;
+    const int q = std::max(1, (total_sub + sc_blocks - 1) / sc_blocks);   // sub-tiles per chunk
     std::vector<PtChunk> ch;
     std::vector<int> hcb(n + 1, 0);
     for (int h = 0; h < n; ++h) {
       hcb[h] = (int)ch.size();
       const int len = hostBegin[h + 1] - hostBegin[h];
       if (len == 0) continue;
-      const int parts = (len + chunk - 1) / chunk;
-      const int sz = ((len + parts - 1) / parts + SC_PTS - 1) / SC_PTS * SC_PTS;
-      for (int s0 = hostBegin[h]; s0 < hostBegin[h + 1]; s0 += sz)
-        ch.push_back(PtChunk{h, s0, std::min(sz, hostBegin[h + 1] - s0), 0});
+      const int nsub = (len + SC_PTS - 1) / SC_PTS, parts = (nsub + q - 1) / q;
+      int s0 = hostBegin[h];
+      for (int c = 0; c < parts; ++c) {
+        const int subs = nsub / parts + (c < nsub % parts ? 1 : 0);
+        const int cnt = std::min(subs * SC_PTS, hostBegin[h + 1] - s0);
+        ch.push_back(PtChunk{h, s0, cnt, 0});
+        s0 += cnt;
+      }
     }
     hcb[n] = (int)ch.size();
     ba->n_ptchunks = (int)ch.size();
     TRY(ba->d_ptchunks.ensure(ch.size() + 1)); TRY(ba->d_host_chunk_begin.ensure(hcb.size()));
     TRY(ba->d_scpartial.ensure((ch.size() + 1) * (size_t)ba->LD * ba->LD));
+    // tiles of the host's own 8-block are never written by the Schur kernel: they must read as zero
+    HS_CUDA(cudaMemsetAsync(ba->d_scpartial.p, 0, (ch.size() + 1) * (size_t)ba->LD * ba->LD * sizeof(float), ctx->stream));
     TRY(ba->d_host_ticket.ensure(n + 1));
     HS_CUDA(cudaMemsetAsync(ba->d_host_ticket.p, 0, (n + 1) * sizeof(unsigned int), ctx->stream));
     TRY(upload(ba, ba->d_ptchunks.p, ch.data(), ch.size())); TRY(upload(ba, ba->d_host_chunk_begin.p, hcb.data(), hcb.size()));
@@ -650,19 +666,30 @@ static int launch_top(hslam_ba* ba, int modes) {
 }
 
 static size_t schur_smem(int LD, int maxres) { return sc_smem_floats(LD, maxres) * sizeof(float); }
-static int schur_maxt(int LD) { int NT = LD / 4; return NT * (NT + 1) / 2 <= SC_THREADS ? 1 : 3; }
+static int schur_maxt(int LD) { int NTR = LD / 4 - 2, t = NTR * (NTR + 1) / 2; return t <= 128 ? 1 : (t <= 256 ? 2 : 5); }
+static int schur_ni(int maxres) { return SC_PTS * maxres <= 2 * SC_THREADS ? 2 : 4; }
+template <class F> static int schur_dispatch(int maxt, int ni, F f) {
+  if (maxt == 1 && ni == 2) return f(ba_schur_kernel<1, 2>);
+  if (maxt == 1) return f(ba_schur_kernel<1, 4>);
+  if (maxt == 2 && ni == 2) return f(ba_schur_kernel<2, 2>);
+  if (maxt == 2) return f(ba_schur_kernel<2, 4>);
+  return f(ba_schur_kernel<5, 4>);
+}
 static int schur_attr(size_t smem) {
   static size_t configured = 48 * 1024;
   if (smem > configured) {
-    HS_CUDA(cudaFuncSetAttribute(ba_schur_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    HS_CUDA(cudaFuncSetAttribute(ba_schur_kernel<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    for (int maxt : {1, 2, 5})
+      for (int ni : {2, 4})
+        TRY(schur_dispatch(maxt, ni, [&](auto k) -> int {
+          HS_CUDA(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+          return 0;
+        }));
     configured = smem;
   }
   return 0;
 }
-static void schur_launch(int maxt, int blocks, size_t smem, cudaStream_t st, const BADesc* d, const int* pf, int n) {
-  if (maxt == 1) ba_schur_kernel<1><<<blocks, SC_THREADS, smem, st>>>(d, pf, n);
-  else ba_schur_kernel<3><<<blocks, SC_THREADS, smem, st>>>(d, pf, n);
+static void schur_launch(int maxt, int ni, int blocks, size_t smem, cudaStream_t st, const BADesc* d, const int* pf, int n) {
+  schur_dispatch(maxt, ni, [&](auto k) -> int { k<<<blocks, SC_THREADS, smem, st>>>(d, pf, n); return 0; });
 }
 
 static int launch_schur(hslam_ba* ba) {
@@ -671,7 +698,7 @@ static int launch_schur(hslam_ba* ba) {
   size_t smem = schur_smem(ba->LD, ba->maxres);
   TRY(schur_attr(smem));
   if (ba->n_ptchunks > 0)
-    HS_LAUNCH(ctx, HSLAM_K_BA_SCHUR, schur_launch(schur_maxt(ba->LD), ba->n_ptchunks, smem, ctx->stream, ba->d_desc.p, nullptr, 1));
+    HS_LAUNCH(ctx, HSLAM_K_BA_SCHUR, schur_launch(schur_maxt(ba->LD), schur_ni(ba->maxres), ba->n_ptchunks, smem, ctx->stream, ba->d_desc.p, nullptr, 1));
   HS_LAUNCH(ctx, HSLAM_K_BA_FOLD_SC, (ba_fold_sc_kernel<<<ba->n * ((ba->LD * ba->LD + 255) / 256), 256, 0, ctx->stream>>>(ba->d_desc.p, nullptr, 1)));
   HS_CUDA(cudaGetLastError());
   return 0;
@@ -892,7 +919,7 @@ struct hslam_ba_batch {
   int blocks[6] = {0, 0, 0, 0, 0, 0};
   int uniform[6] = {0, 0, 0, 0, 0, 0};   // blocks per window of a stage when every window has the same count, else 0
   size_t smem = 0;
-  int maxt = 1;
+  int maxt = 1, ni = 2;
   bool any_L = false;
   // host API staging: one pinned block up, one down, their device twins, and the per-window offset table
   char* h_up = nullptr; char* h_dn = nullptr;
@@ -916,7 +943,7 @@ static int batch_refresh(hslam_ba_batch* B) {
   HS_CUDA(cudaEventSynchronize(B->copied));
   int* pf[NPF];
   for (int k = 0; k < NPF; ++k) { pf[k] = B->h_prefix + k * (n + 1); pf[k][0] = 0; }
-  B->smem = 0; B->maxt = 1; B->any_L = false;
+  B->smem = 0; B->maxt = 1; B->ni = 2; B->any_L = false;
   for (int i = 0; i < n; ++i) {
     hslam_ba* ba = B->items[i];
     B->h_descs[i] = ba->hdesc;
@@ -932,6 +959,7 @@ static int batch_refresh(hslam_ba_batch* B) {
     pf[5][i + 1] = pf[5][i] + (ba->P + 127) / 128;
     B->smem = std::max(B->smem, schur_smem(ba->LD, ba->maxres));
     B->maxt = std::max(B->maxt, schur_maxt(ba->LD));
+    B->ni = std::max(B->ni, schur_ni(ba->maxres));
   }
   for (int k = 0; k < NPF; ++k) {
     B->blocks[k] = pf[k][n];
@@ -1004,7 +1032,7 @@ static int batch_enqueue_accumulate(hslam_ba_batch* B) {
       HS_LAUNCH(ctx, HSLAM_K_BA_TOP, (ba_top_kernel<1><<<B->blocks[1], 2 * TOP_THREADS, kTopSmem, ctx->stream>>>(B->d_descs.p, pf + (n + 1), n)));
   }
   if (B->blocks[2] > 0)
-    HS_LAUNCH(ctx, HSLAM_K_BA_SCHUR, schur_launch(B->maxt, B->blocks[2], B->smem, ctx->stream, B->d_descs.p, pf + 2 * (n + 1), n));
+    HS_LAUNCH(ctx, HSLAM_K_BA_SCHUR, schur_launch(B->maxt, B->ni, B->blocks[2], B->smem, ctx->stream, B->d_descs.p, pf + 2 * (n + 1), n));
   HS_LAUNCH(ctx, HSLAM_K_BA_FOLD_SC, (ba_fold_sc_kernel<<<B->blocks[4], 256, 0, ctx->stream>>>(B->d_descs.p, pf + 4 * (n + 1), B->uniform[4] ? -B->uniform[4] : n)));
   HS_LAUNCH(ctx, HSLAM_K_BA_STITCH, (ba_stitch_kernel<<<B->blocks[3], ST_THREADS, 0, ctx->stream>>>(B->d_descs.p, pf + 3 * (n + 1), B->uniform[3] ? -B->uniform[3] : n, 0, 3, 1)));
   HS_CUDA(cudaGetLastError());

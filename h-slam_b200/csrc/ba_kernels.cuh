@@ -806,20 +806,34 @@ __device__ __forceinline__ void tri_decode(int t, int NT, int& ti, int& tj) {
   ti = row; tj = row + rem;
 }
 
-// Shared-memory layout (floats): A[SC_PTS][LD+4] | wv[SC_PTS] | stg[7][SC_PTS*MR], MR = maxres|1.
-// The row stride LD+4 and the odd MR keep every access pattern of the kernel free of bank conflicts:
-//   staging stores  A[lp][8t+j]      lanes differ in (lp,t): (LD+4) % 32 = 4 or 12 rotates the rows;
-//   point sums      stg[c][lp*MR+s]  lanes differ in lp: odd stride;
-//   Gram tiles      A[lp][4ti..]     all lanes share lp: float4 broadcast per distinct tile.
+// Shared-memory layout (floats): A[SC_PTS][LD+4] | WA[SC_PTS][LD+4] (= HdiF * A) | wv[SC_PTS] | stg[7][SNP],
+// SNP = SC_PTS*(maxres|1) + 5.
+// The row stride LD+4, the odd per-point stride MR = maxres|1 and the component stride SNP keep the access
+// patterns of the kernel (almost) free of bank conflicts:
+//   staging stores  A[lp][8t+j]       lanes differ in (lp,t): (LD+4) % 32 = 4 or 12 rotates the rows;
+//   point sums      stg[c][lp*MR+s]   8 lanes per point differ in c (stride SNP), 4 points per warp (stride MR);
+//   Gram tiles      A[lp][4ti..]      all lanes share lp: float4 broadcast per distinct tile.
 __host__ __device__ inline int sc_mr(int maxres) { return maxres | 1; }
+__host__ __device__ inline int sc_snp(int maxres) { return SC_PTS * sc_mr(maxres) + 5; }
 __host__ __device__ inline size_t sc_smem_floats(int LD, int maxres) {
-  return (size_t)SC_PTS * (LD + 4) + SC_PTS + 7 * (size_t)SC_PTS * sc_mr(maxres);
+  return 2 * (size_t)SC_PTS * (LD + 4) + SC_PTS + 7 * (size_t)sc_snp(maxres);
 }
 
-// MAXT = upper-triangular 4x4 tiles per thread: NT(NT+1)/2 <= MAXT*256 (MAXT=1: n <= 10, MAXT=3: n <= 16).
-template <int MAXT>
-__global__ void __launch_bounds__(SC_THREADS) ba_schur_kernel(const BADesc* __restrict__ descs,
-                                                              const int* __restrict__ prefix, int nwin) {
+// Gram tiles: 4x4 register tiles of the upper triangle of G_h WITHOUT the two tile rows/columns of the host's
+// own 8-block (a point has no residual into its host: that block of a_p is always zero, the partial buffer is
+// zero-initialised there).  Each tile is owned by TWO threads (tid and tid+128), one for the even and one for the
+// odd points of the sub-tile: all eight warps work in phase 2 and the per-tile dependent FMA chain is halved.
+// MAXT = tiles per thread: (NT-2)(NT-1)/2 <= MAXT*128 (MAXT=1: n <= 7, 2: n <= 10, 5: n <= 16).
+// NI   = (point, residual slot) items per thread and sub-tile: SC_PTS*maxres <= NI*256.
+// Software pipeline over the sub-tiles of the block's chunk: while sub-tile i is summed and folded, the
+// residual data of sub-tile i+1 (the residual's 14 floats + flags, addressed through the slot table) and
+// the slot entries of sub-tile i+2 are already in flight, held in registers.
+template <int MAXT, int NI>
+#ifndef SC_MINB
+#define SC_MINB 3
+#endif
+__global__ void __launch_bounds__(SC_THREADS, (MAXT <= 2 && NI <= 2) ? SC_MINB : 2)
+ba_schur_kernel(const BADesc* __restrict__ descs, const int* __restrict__ prefix, int nwin) {
   extern __shared__ __align__(16) float smem[];
   int lb;
   const int win = find_window(prefix, nwin, blockIdx.x, lb);
@@ -827,118 +841,198 @@ __global__ void __launch_bounds__(SC_THREADS) ba_schur_kernel(const BADesc* __re
   const BARes& r = D.r;
   const BAPts& pts = D.p;
   const int LD = D.LD, LDP = LD + 4;
-  const int maxres = D.maxres, MR = sc_mr(maxres), SN = SC_PTS * MR;
-  float* A = smem;                        // [SC_PTS][LDP]
-  float* wv = smem + SC_PTS * LDP;        // [SC_PTS] HdiF
-  float* stg = wv + SC_PTS;               // [7][SN]: 6 point terms + mode flag per (point, residual slot)
+  const int maxres = D.maxres, MR = sc_mr(maxres), SNP = sc_snp(maxres);
+  float* A = smem;                        // [SC_PTS][LDP]   a_p
+  float* WA = A + SC_PTS * LDP;           // [SC_PTS][LDP]   HdiF_p * a_p
+  float* wv = WA + SC_PTS * LDP;          // [SC_PTS] HdiF
+  float* stg = wv + SC_PTS;               // [7][SNP]: 6 point terms + mode flag per (point, residual slot)
   const PtChunk ch = D.ptchunks[lb];
   const int s = r.rs, n = D.W.n;
-  const int NT = LD / 4, ntiles = NT * (NT + 1) / 2;
+  const int NT = LD / 4, NTR = NT - 2, ntiles = NTR * (NTR + 1) / 2;
+  const int half = threadIdx.x >> 7;      // 0: even points of the sub-tile, 1: odd points
   int tI[MAXT], tJ[MAXT];
   float acc[MAXT][16];
 #pragma unroll
   for (int j = 0; j < MAXT; ++j) {
-    int tile = threadIdx.x + j * SC_THREADS;
+    int tile = (threadIdx.x & 127) + j * 128;
     tI[j] = tJ[j] = -1;
-    if (tile < ntiles) tri_decode(tile, NT, tI[j], tJ[j]);
+    if (tile < ntiles) {
+      tri_decode(tile, NTR, tI[j], tJ[j]);
+      if (tI[j] >= 2 * ch.host) tI[j] += 2;   // skip the host's own two tile rows / columns
+      if (tJ[j] >= 2 * ch.host) tJ[j] += 2;
+    }
 #pragma unroll
     for (int i = 0; i < 16; ++i) acc[j][i] = 0.f;
   }
+  // (point, slot) items of this thread: the same in every sub-tile
+  int ilp[NI], isl[NI];
+#pragma unroll
+  for (int i = 0; i < NI; ++i) {
+    // point index fastest: the lanes of a warp stage the SAME slot of consecutive points, whose residuals sit
+    // next to each other in the pair-sorted arrays (coalesced loads; slot-fastest made every 4-byte load its
+    // own 32-byte sector and the kernel LSU-bound)
+    const int it = threadIdx.x + i * SC_THREADS;
+    isl[i] = it / SC_PTS; ilp[i] = it - isl[i] * SC_PTS;
+    if (isl[i] >= maxres) ilp[i] = SC_PTS;   // beyond the sub-tile
+  }
+  // pipeline registers
+  int en[NI];                         // slot entries of the NEXT sub-tile to be staged
+  float4 dj0[NI], dj1[NI];            // staged residual: JpJdF
+  float dpt[NI][6];                   //                  its six point terms
+  int dfl[NI];                        //                  -1 = nothing, else isActive | isLin << 1 | target << 8 (raw loads:
+                                      //                  nothing here may consume a loaded value before the next sub-tile)
+  unsigned char dact[NI], dlin[NI];
+  float pr[2], de[2];                 // priorF / deltaF of the points this thread finalises in phase 1b
+
+  auto load_slots = [&](int base) {
+    const int cnt = min(SC_PTS, ch.count - base);   // <= 0 beyond the chunk
+#pragma unroll
+    for (int i = 0; i < NI; ++i)
+      en[i] = (ilp[i] < cnt) ? pts.slot[(size_t)(ch.start + base + ilp[i]) * maxres + isl[i]] : -1;
+  };
+  auto load_data = [&](int base) {   // consumes en[]
+    const int cnt = min(SC_PTS, ch.count - base);
+#pragma unroll
+    for (int i = 0; i < NI; ++i) {
+      dfl[i] = -1; dact[i] = 0; dlin[i] = 0;
+      if (en[i] >= 0) {
+        const int k = en[i] & 0x3ffffff;
+        // every load of the residual is independent of its flags (one round trip); filtered at the store
+        dact[i] = r.isActive[k];
+        dlin[i] = r.isLin[k];
+        const float* jp = r.JpJdF + k;
+        dj0[i] = make_float4(jp[0], jp[s], jp[2 * s], jp[3 * s]);
+        dj1[i] = make_float4(jp[4 * s], jp[5 * s], jp[6 * s], jp[7 * s]);
+        const float* o = r.ptc[0] + k;   // modes A and L share the array (a residual is in exactly one)
+#pragma unroll
+        for (int j = 0; j < 6; ++j) dpt[i][j] = o[j * s];
+        dfl[i] = en[i] >> 26;   // target
+      }
+    }
+#pragma unroll
+    for (int rd = 0; rd < 2; ++rd) {
+      const int item = rd * SC_THREADS + threadIdx.x, lp = item >> 3, c = item & 7;
+      pr[rd] = de[rd] = 0.f;
+      if (lp < cnt && c < 2) {
+        pr[rd] = pts.priorF[ch.start + base + lp];
+        if (c == 0) de[rd] = pts.deltaF[ch.start + base + lp];
+      }
+    }
+  };
+
+#ifndef SC_PIPELINE
+#define SC_PIPELINE 0   /* measured on B200 (8 x cfg2 windows): register prefetch of the next sub-tile 63.9 us, plain staging 61.4 us */
+#endif
+#if SC_PIPELINE
+  // prologue: slots of sub-tile 0 -> data of sub-tile 0; slots of sub-tile 1
+  load_slots(0);
+  load_data(0);
+  load_slots(SC_PTS);
+#endif
 
   for (int base = 0; base < ch.count; base += SC_PTS) {
     const int cnt = min(SC_PTS, ch.count - base);
-    // per-point scalars of phase 1b: issued now, consumed two barriers later
-    float prior = 0.f, delta = 0.f;
-    if (threadIdx.x < cnt) { prior = pts.priorF[ch.start + base + threadIdx.x]; delta = pts.deltaF[ch.start + base + threadIdx.x]; }
+#if !SC_PIPELINE
+    load_slots(base);
+    load_data(base);
+#endif
     for (int i = threadIdx.x; i < SC_PTS * LDP / 4; i += SC_THREADS) reinterpret_cast<float4*>(A)[i] = make_float4(0.f, 0.f, 0.f, 0.f);
     __syncthreads();
-    // phase 1a: one thread per (point, residual slot).  The slot table gives the residual's sorted position
-    // and target in ONE coalesced load; every load after it is independent of the others.
-    for (int it = threadIdx.x; it < SC_PTS * maxres; it += SC_THREADS) {
-      const int lp = it / maxres, slot = it - lp * maxres;
-      const int si = lp * MR + slot;
-      float flag = 0.f;
-      if (lp < cnt) {
-        const int e = pts.slot[(size_t)(ch.start + base + lp) * maxres + slot];
-        if (e >= 0) {
-          const int k = e & 0x3ffffff, t = e >> 26;
-          // all loads of the residual are independent of its flags (one round trip); filtered afterwards
-          const bool act = r.isActive[k] != 0;
-          const int m = r.isLin[k] ? 1 : 0;
-          const float* jp = r.JpJdF + k;
-          const float4 j0 = make_float4(jp[0], jp[s], jp[2 * s], jp[3 * s]);
-          const float4 j1 = make_float4(jp[4 * s], jp[5 * s], jp[6 * s], jp[7 * s]);
-          const float* o = r.ptc[0] + k;   // modes A and L share the array (a residual is in exactly one)
-          const float o0 = o[0], o1 = o[s], o2 = o[2 * s], o3 = o[3 * s], o4 = o[4 * s], o5 = o[5 * s];
-          if (act) {
-            float4* dst = reinterpret_cast<float4*>(A + lp * LDP + 8 * t);
-            dst[0] = j0; dst[1] = j1;
-            stg[si] = o0; stg[SN + si] = o1; stg[2 * SN + si] = o2; stg[3 * SN + si] = o3;
-            stg[4 * SN + si] = o4; stg[5 * SN + si] = o5;
-            flag = (float)(m + 1);
-          }
-        }
-      }
-      stg[6 * SN + si] = flag;
-    }
-    __syncthreads();
-    // phase 1b: one thread per point forms Hdd/bd/Hcd sequentially in the point's residual order
-    // (AccumulatedTopHessian.cpp:35-139), then the Schur scalars (AccumulatedSCHessian.cpp:12-33).
-    if (threadIdx.x < SC_PTS) {
-      const int lp = threadIdx.x;
-      if (lp < cnt) {
-        const int p = ch.start + base + lp;
-        float bdv[2] = {0.f, 0.f}, Hddv[2] = {0.f, 0.f};
-        float Hcdv[2][4] = {{0.f, 0.f, 0.f, 0.f}, {0.f, 0.f, 0.f, 0.f}};
-        int ngood = 0;
-        for (int slot = 0; slot < maxres; ++slot) {
-          const int si = lp * MR + slot;
-          const int f = (int)stg[6 * SN + si];
-          if (f == 0) continue;
-          const int m = f - 1;
-          ngood++;
-          bdv[m] = xadd(bdv[m], stg[si]);
-          Hddv[m] = xadd(Hddv[m], stg[SN + si]);
+    // phase 1a: the staged registers of THIS sub-tile go to shared memory ...
 #pragma unroll
-          for (int j = 0; j < 4; ++j) Hcdv[m][j] = xadd(Hcdv[m][j], stg[(2 + j) * SN + si]);
+    for (int i = 0; i < NI; ++i) {
+      if (ilp[i] < SC_PTS) {
+        const int si = ilp[i] * MR + isl[i];
+        const bool on = dfl[i] >= 0 && dact[i] != 0;
+        if (on) {
+          float4* dst = reinterpret_cast<float4*>(A + ilp[i] * LDP + 8 * dfl[i]);
+          dst[0] = dj0[i]; dst[1] = dj1[i];
+#pragma unroll
+          for (int j = 0; j < 6; ++j) stg[j * SNP + si] = dpt[i][j];
         }
-        for (int m = 0; m < 2; ++m) {
-          pts.Hdd[m][p] = Hddv[m]; pts.bd[m][p] = bdv[m];
-          pts.Hcd[m][p] = make_float4(Hcdv[m][0], Hcdv[m][1], Hcdv[m][2], Hcdv[m][3]);
+        stg[6 * SNP + si] = on ? (dlin[i] ? 2.f : 1.f) : 0.f;
+      }
+    }
+    const float prc[2] = {pr[0], pr[1]}, dec[2] = {de[0], de[1]};
+    // ... and the loads of the NEXT sub-tile (data) and the one after (slots) are issued: they complete
+    // while phases 1b and 2 run
+#if SC_PIPELINE
+    load_data(base + SC_PTS);
+    load_slots(base + 2 * SC_PTS);
+#endif
+    __syncthreads();
+    // phase 1b: 8 lanes per point; lane c < 6 owns one of the six per-point sums {bd, Hdd, Hcd[0..3]} for both
+    // modes and adds the point's residuals IN THE POINT'S OWN ORDER (AccumulatedTopHessian.cpp:35-139), then
+    // the Schur scalars (AccumulatedSCHessian.cpp:12-33).
+#pragma unroll
+    for (int rd = 0; rd < 2; ++rd) {
+      const int item = rd * SC_THREADS + threadIdx.x, lp = item >> 3, c = item & 7;
+      float rowv = 0.f, rowh = 0.f;
+      if (c < 6) {
+        if (lp < cnt) {
+          const int p = ch.start + base + lp;
+          float sum[2] = {0.f, 0.f};
+          int ngood = 0;
+          for (int slot = 0; slot < maxres; ++slot) {
+            const int si = lp * MR + slot;
+            const int f = (int)stg[6 * SNP + si];
+            if (f == 0) continue;
+            ngood++;
+            sum[f - 1] = xadd(sum[f - 1], stg[c * SNP + si]);
+          }
+          float mine = 0.f;   // this lane's entry of a_p (columns 8n .. 8n+4)
+          float hdi = 0.f;
+          if (c == 0) {
+            pts.bd[0][p] = sum[0]; pts.bd[1][p] = sum[1];
+            if (ngood > 0) mine = xadd(xadd(sum[0], sum[1]), xmul(prc[rd], dec[rd]));   // shiftPriorToZero (EnergyFunctional.cpp:209)
+            pts.bdSumF[p] = mine;
+          } else if (c == 1) {
+            pts.Hdd[0][p] = sum[0]; pts.Hdd[1][p] = sum[1];
+            float idh = 0.f;
+            if (ngood > 0) {
+              float H = xadd(xadd(sum[0], sum[1]), prc[rd]);
+              if (H < 1e-10f) H = 1e-10f;
+              idh = H;
+              hdi = xdiv(1.0f, H);
+            }
+            pts.HdiF[p] = hdi; pts.idepth_hessian[p] = idh;
+            wv[lp] = hdi;
+          } else {
+            reinterpret_cast<float*>(pts.Hcd[0])[4 * (size_t)p + (c - 2)] = sum[0];
+            reinterpret_cast<float*>(pts.Hcd[1])[4 * (size_t)p + (c - 2)] = sum[1];
+            mine = xadd(sum[0], sum[1]);
+          }
+          rowv = mine; rowh = hdi;
+        } else if (c == 1 && lp < SC_PTS) {
+          wv[lp] = 0.f;
         }
-        float hdi = 0.f, bds = 0.f, idh = 0.f;
-        float4 hcd = make_float4(0.f, 0.f, 0.f, 0.f);
-        if (ngood > 0) {
-          float H = xadd(xadd(Hddv[0], Hddv[1]), prior);
-          if (H < 1e-10f) H = 1e-10f;
-          idh = H;
-          hdi = xdiv(1.0f, H);
-          bds = xadd(bdv[0], bdv[1]);
-          bds = xadd(bds, xmul(prior, delta));  // shiftPriorToZero = true (EnergyFunctional.cpp:209)
-          hcd = make_float4(xadd(Hcdv[0][0], Hcdv[1][0]), xadd(Hcdv[0][1], Hcdv[1][1]), xadd(Hcdv[0][2], Hcdv[1][2]),
-                            xadd(Hcdv[0][3], Hcdv[1][3]));
+      }
+      // the 8 lanes of a point share HdiF and write the scaled copy of the row: lane c < 6 its own entry of the
+      // [Hcd | bdSum] block, all 8 lanes two float4 each of the JpJdF part (staged in phase 1a)
+      const float hd = __shfl_sync(0xffffffffu, rowh, (threadIdx.x & 24) + 1);   // lane c == 1 of this point's 8-lane group
+      if (lp < cnt) {
+        const int colb = 8 * n;
+        if (c == 0) { A[lp * LDP + colb + 4] = rowv; WA[lp * LDP + colb + 4] = hd * rowv; }
+        else if (c >= 2 && c < 6) { A[lp * LDP + colb + (c - 2)] = rowv; WA[lp * LDP + colb + (c - 2)] = hd * rowv; }
+        else if (c >= 6) { for (int q = colb + 5 + (c - 6); q < LD; q += 2) WA[lp * LDP + q] = 0.f; }   // padding columns
+        for (int q4 = c; q4 < 2 * n; q4 += 8) {
+          const float4 v = *reinterpret_cast<const float4*>(A + lp * LDP + 4 * q4);
+          *reinterpret_cast<float4*>(WA + lp * LDP + 4 * q4) = make_float4(hd * v.x, hd * v.y, hd * v.z, hd * v.w);
         }
-        pts.HdiF[p] = hdi; pts.bdSumF[p] = bds; pts.idepth_hessian[p] = idh;
-        float* dst = A + lp * LDP + 8 * n;
-        *reinterpret_cast<float4*>(dst) = hcd; dst[4] = bds;
-        wv[lp] = hdi;
-      } else {
-        wv[lp] = 0.f;
       }
     }
     __syncthreads();
-    // phase 2: G += sum_p (w_p a_p) a_p^T, 4x4 register tiles of the upper triangle, points in order
+    // phase 2: G += sum_p (w_p a_p) a_p^T, 4x4 register tiles, this thread's half of the points in order
 #pragma unroll
     for (int j = 0; j < MAXT; ++j) {
       if (tI[j] >= 0) {
-        const float* ap = A + 4 * tI[j];
+        const float* ap = WA + 4 * tI[j];
         const float* bp = A + 4 * tJ[j];
 #pragma unroll 4
-        for (int lp = 0; lp < cnt; ++lp) {
-          const float w = wv[lp];
+        for (int lp = half; lp < cnt; lp += 2) {
           const float4 av = *reinterpret_cast<const float4*>(ap + lp * LDP);
           const float4 bv = *reinterpret_cast<const float4*>(bp + lp * LDP);
-          const float a4[4] = {w * av.x, w * av.y, w * av.z, w * av.w};
+          const float a4[4] = {av.x, av.y, av.z, av.w};
           const float b4[4] = {bv.x, bv.y, bv.z, bv.w};
 #pragma unroll
           for (int ii = 0; ii < 4; ++ii)
@@ -949,14 +1043,28 @@ __global__ void __launch_bounds__(SC_THREADS) ba_schur_kernel(const BADesc* __re
     }
     __syncthreads();
   }
+  // the odd-point halves go through shared memory (A is free now), the even-point threads add and store
   float* out = D.scpartial + (size_t)lb * LD * LD;
 #pragma unroll
   for (int j = 0; j < MAXT; ++j) {
-    if (tI[j] >= 0) {
+    float* xch = A + (size_t)((threadIdx.x & 127) + j * 128) * 16;   // <= MAXT*128*16 floats <= 2*SC_PTS*LDP
+    if (tI[j] >= 0 && half == 1) {
 #pragma unroll
       for (int ii = 0; ii < 4; ++ii)
+        *reinterpret_cast<float4*>(xch + 4 * ii) = make_float4(acc[j][4 * ii], acc[j][4 * ii + 1], acc[j][4 * ii + 2], acc[j][4 * ii + 3]);
+    }
+  }
+  __syncthreads();
+#pragma unroll
+  for (int j = 0; j < MAXT; ++j) {
+    const float* xch = A + (size_t)((threadIdx.x & 127) + j * 128) * 16;
+    if (tI[j] >= 0 && half == 0) {
+#pragma unroll
+      for (int ii = 0; ii < 4; ++ii) {
+        const float4 o = *reinterpret_cast<const float4*>(xch + 4 * ii);
         *reinterpret_cast<float4*>(out + (size_t)(4 * tI[j] + ii) * LD + 4 * tJ[j]) =
-            make_float4(acc[j][4 * ii], acc[j][4 * ii + 1], acc[j][4 * ii + 2], acc[j][4 * ii + 3]);
+            make_float4(acc[j][4 * ii] + o.x, acc[j][4 * ii + 1] + o.y, acc[j][4 * ii + 2] + o.z, acc[j][4 * ii + 3] + o.w);
+      }
     }
   }
 }
