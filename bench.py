@@ -126,6 +126,7 @@ def main():
     ap.add_argument("--windows", type=int, default=8, help="independent windows per GPU per step")
     ap.add_argument("--mode", default="batched", choices=["batched", "sharded"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-extras", action="store_true", help="skip the tracking / single-window latency figures (profiling runs)")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
 
@@ -287,7 +288,8 @@ def main():
     }
 
     if rank == 0:
-        line["extra"] = extras(ctx, capi, synth, torch, stream, efs[0], wins[0])
+        if not args.no_extras:
+            line["extra"] = extras(ctx, capi, synth, torch, stream, efs[0], wins[0])
         if not args.no_cpu_baseline:
             line["cpu_baseline"] = cpu_baseline(synth, wins[0])
         print(json.dumps(line), flush=True)

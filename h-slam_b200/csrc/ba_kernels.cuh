@@ -191,6 +191,12 @@ __device__ __forceinline__ void apply_one(const BARes& r, int k) {  // Optimizat
 template <bool APPLY>
 __global__ void __launch_bounds__(LIN_THREADS, LIN_MINB) ba_linearize_kernel(const BADesc* __restrict__ descs,
                                                                    const int* __restrict__ prefix, int nwin) {
+#ifndef LIN_PARK
+#define LIN_PARK 0   /* measured: parking colours/weights in smem 149 us vs 146 us in registers */
+#endif
+#if LIN_PARK
+  __shared__ float lin_park[16][LIN_THREADS];
+#endif
   int lb;
   const int win = find_window(prefix, nwin, blockIdx.x, lb);
   const BADesc& D = descs[win];
@@ -226,6 +232,17 @@ __global__ void __launch_bounds__(LIN_THREADS, LIN_MINB) ba_linearize_kernel(con
       // issue them with the point record so their latency overlaps the projections
       const float4 c0 = __ldg(D.p.color + 2 * p), c1 = __ldg(D.p.color + 2 * p + 1);
       const float4 w0 = __ldg(D.p.weights + 2 * p), w1 = __ldg(D.p.weights + 2 * p + 1);
+#if LIN_PARK
+      // parked in shared memory (component-major: conflict-free) until the pattern loop: 16 registers less
+      // through the gather phase, i.e. more texel loads in flight per thread
+      {
+        float* pk = &lin_park[0][threadIdx.x];
+        pk[0 * LIN_THREADS] = c0.x; pk[1 * LIN_THREADS] = c0.y; pk[2 * LIN_THREADS] = c0.z; pk[3 * LIN_THREADS] = c0.w;
+        pk[4 * LIN_THREADS] = c1.x; pk[5 * LIN_THREADS] = c1.y; pk[6 * LIN_THREADS] = c1.z; pk[7 * LIN_THREADS] = c1.w;
+        pk[8 * LIN_THREADS] = w0.x; pk[9 * LIN_THREADS] = w0.y; pk[10 * LIN_THREADS] = w0.z; pk[11 * LIN_THREADS] = w0.w;
+        pk[12 * LIN_THREADS] = w1.x; pk[13 * LIN_THREADS] = w1.y; pk[14 * LIN_THREADS] = w1.z; pk[15 * LIN_THREADS] = w1.w;
+      }
+#endif
       const float u_pt = pu.x, v_pt = pu.y, idp = pu.z, idz = pu.w;
       const float wm3 = (float)(W.w - 3), hm3 = (float)(W.h - 3);
       // ---- centre projection at the FEJ point, DirectProjection.h:20-38
@@ -293,8 +310,15 @@ __global__ void __launch_bounds__(LIN_THREADS, LIN_MINB) ba_linearize_kernel(con
           const uint64_t pol = l2_keep_policy();
 #pragma unroll
           for (int idx = 0; idx < 8; ++idx) hit[idx] = interp33(img, Kup[idx], Kvp[idx], W.w, pol);
+#if !LIN_PARK
           const float color[8] = {c0.x, c0.y, c0.z, c0.w, c1.x, c1.y, c1.z, c1.w};
           const float wgt[8] = {w0.x, w0.y, w0.z, w0.w, w1.x, w1.y, w1.z, w1.w};
+#define LIN_COLOR(i) color[i]
+#define LIN_WGT(i) wgt[i]
+#else
+#define LIN_COLOR(i) lin_park[i][threadIdx.x]
+#define LIN_WGT(i) lin_park[8 + (i)][threadIdx.x]
+#endif
           float II00 = 0.f, II11 = 0.f, II10 = 0.f, AI00 = 0.f, AI01 = 0.f, AI10 = 0.f, AI11 = 0.f;
           float AA00 = 0.f, AA01 = 0.f, AA11 = 0.f;
           float JIr0 = 0.f, JIr1 = 0.f, Jabr0 = 0.f, Jabr1 = 0.f, rr = 0.f;
@@ -304,10 +328,11 @@ __global__ void __launch_bounds__(LIN_THREADS, LIN_MINB) ba_linearize_kernel(con
             if (nonfinite) continue;
             const float hI = hit[idx].I, hdx = hit[idx].dx, hdy = hit[idx].dy;
             if (!isfinite(hI)) { nonfinite = true; continue; }   // :157-161
-            float residual = xsub(hI, xadd(xmul(affLL0, color[idx]), affLL1));
-            float drdA = xsub(color[idx], b0);
+            const float col = LIN_COLOR(idx);
+            float residual = xsub(hI, xadd(xmul(affLL0, col), affLL1));
+            float drdA = xsub(col, b0);
             float w = xsqrt(xdiv(W.outlierTH, xadd(W.outlierTH, xadd(xmul(hdx, hdx), xmul(hdy, hdy)))));
-            w = xmul(0.5f, xadd(w, wgt[idx]));
+            w = xmul(0.5f, xadd(w, LIN_WGT(idx)));
             float ar = fabsf(residual);
             float hw = ar < W.huber ? 1.f : xdiv(W.huber, ar);
             energyLeft = xadd(energyLeft, xmul(xmul(xmul(xmul(xmul(w, w), hw), residual), residual), xsub(2.f, hw)));
