@@ -1,0 +1,40 @@
+"""BASELINE.json configs[2] at reduced size: a rendered sequence tracked frame by frame through the CUDA
+tracker and through the CPU oracle with IDENTICAL decisions (same keyframes, same reference clouds, same
+motion hypotheses); north_star: "trajectories on the synthetic sequence agree in ATE within 1 %".
+The full 640x480 x 500-frame run is tools/run_sequence.py (result under profiles/)."""
+import importlib
+
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+
+class OracleTracker:
+    def __init__(self, O, cam, levels, pc, prec="f"):
+        self.O, self.levels, self.prec = O, levels, prec
+        self.orc = O.TrackerOracle(cam, levels, pc)
+
+    def track(self, img, T0, aff0, coarsest):
+        _, _, dI = self.O.pyramid(img, self.levels)
+        r = self.orc.track(dI, T0, aff0, coarsest, prec=self.prec)
+        return r["ok"], r["T"], r["aff"]
+
+    def close(self):
+        pass
+
+
+def test_sequence_ate_matches_oracle(ctx, capi, O):
+    seq = importlib.import_module("h-slam_b200.sequence")
+    w, h, levels, n = 320, 240, 4, 60
+    cam, Ts, frames = seq.render_sequence(w, h, n, seed=21)
+    g = seq.run_sequence(cam, Ts, frames, levels, lambda c, l, pc: seq.CudaTracker(capi, ctx, c, l, pc), kf_every=8, n_points=1500)
+    f = seq.run_sequence(cam, Ts, frames, levels, lambda c, l, pc: OracleTracker(O, c, l, pc, "f"), kf_every=8, n_points=1500)
+    assert all(g.ok) and all(f.ok)
+    assert g.n_keyframes == f.n_keyframes
+    path = np.linalg.norm(np.diff(np.array([T[9:] for T in Ts]), axis=0), axis=1).sum()
+    assert g.ate_rmse < 0.02 * path, (g.ate_rmse, path)       # the tracker tracks (drift well below 2 % of the path)
+    assert abs(g.ate_rmse - f.ate_rmse) <= 0.01 * f.ate_rmse + 1e-7, (g.ate_rmse, f.ate_rmse)
+    # frame by frame: the two back ends take the same LM path, poses agree far below the ATE itself
+    d = max(np.abs(np.asarray(a) - np.asarray(b)).max() for a, b in zip(g.T_w2c_est, f.T_w2c_est))
+    assert d < 1e-4, d
