@@ -455,6 +455,20 @@ class EnergyFunctional:
             state_state=st, is_active=act, JpJdF=jp.reshape(R, 8), J=None if j74 is None else j74.reshape(R, 74),
             res_toZeroF=rtz.reshape(R, 8)))
 
+    def marginalizePointsF(self, point_ids, prior_scale):
+        """(M, Mb, Msc, Mbsc, nres) of the points to marginalise (EnergyFunctional::marginalizePointsF)."""
+        N = self.N
+        M = np.zeros(N * N); Mb = np.zeros(N); Ms = np.zeros(N * N); Mbs = np.zeros(N); nres = C.c_int(0)
+        ids = np.ascontiguousarray(point_ids, np.int32)
+        _chk(self.L.hslam_ba_marginalize_points(self.h, _ptr(ids), C.c_int(len(ids)), C.c_float(prior_scale), _ptr(M), _ptr(Mb),
+                                                _ptr(Ms), _ptr(Mbs), C.byref(nres)))
+        return M.reshape(N, N).T.copy(), Mb, Ms.reshape(N, N).T.copy(), Mbs, nres.value
+
+    def calcLEnergyF_MT(self):
+        e = C.c_double(0)
+        _chk(self.L.hslam_ba_calc_l_energy(self.h, C.byref(e)))
+        return e.value
+
     def resubstituteF_MT(self, x):
         step = np.zeros(self.P, np.float32)
         _chk(self.L.hslam_ba_resubstitute(self.h, _ptr(np.ascontiguousarray(x, np.float64)), _ptr(step)))

@@ -42,6 +42,7 @@ struct hslam_ba {
   // window tables
   DevBuf<float> d_precalc, d_adHTd;
   DevBuf<double> d_adH, d_adT, d_fprior, d_fdprior;
+  std::vector<double> h_fprior, h_fdprior;   // host copies for calcLEnergy's prior terms
   // points
   DevBuf<float4> d_uvid, d_color, d_weights, d_Hcd[2];
   DevBuf<float> d_priorF, d_deltaF, d_HdiF, d_bdSumF, d_idh, d_Hdd[2], d_bd[2], d_step;
@@ -55,6 +56,7 @@ struct hslam_ba {
   DevBuf<float> d_senergy, d_newEnergy, d_newEnergyWO, d_J, d_JpJdF, d_rtz, d_cpt, d_pto, d_ptc[2];
   std::vector<int> r_sorted2orig, r_orig2sorted;
   DevBuf<int> d_r_s2o, d_p_s2o;          // device copies of the sorted->caller permutations
+  DevBuf<unsigned char> d_marg;          // marginalisation flags per sorted point
   DevBuf<char> d_scratch;                // staging for layout conversion kernels
   size_t scratch_used = 0;
   int n_linearized = 0;
@@ -212,6 +214,7 @@ static void fill_desc(hslam_ba* ba) {
   S.nres = ba->d_nres.p; S.framePrior = ba->d_fprior.p; S.frameDeltaPrior = ba->d_fdprior.p;
   S.add_priors = ba->add_priors; S.has_L = ba->n_linearized != 0;
   for (int i = 0; i < 4; ++i) S.cDeltaF[i] = D.W.cDeltaF[i];
+  D.marg = nullptr; D.shift_prior = 1;
   D.r_s2o = ba->d_r_s2o.p; D.p_s2o = ba->d_p_s2o.p;
   D.x = ba->d_x.p; D.xc = ba->d_xc.p; D.xAd = ba->d_xAd.p;
   ba->desc_version++;
@@ -362,7 +365,7 @@ int hslam_ba_destroy(hslam_ba* ba) {
   ba->d_ptchunks.release(); ba->d_host_chunk_begin.release(); ba->d_scpartial.release(); ba->d_G.release();
   ba->d_Hb.release(); ba->d_epart.release(); ba->d_energy.release(); ba->d_nres.release(); ba->d_ticket.release();
   ba->d_xc.release(); ba->d_xAd.release(); ba->d_x.release(); ba->d_ids.release(); ba->d_desc.release();
-  ba->d_r_s2o.release(); ba->d_p_s2o.release(); ba->d_scratch.release();
+  ba->d_r_s2o.release(); ba->d_p_s2o.release(); ba->d_scratch.release(); ba->d_marg.release();
   if (ba->arena) cudaFreeHost(ba->arena);
   delete ba;
   return 0;
@@ -436,6 +439,8 @@ int hslam_ba_set_window(hslam_ba* ba, const hslam_window* w) {
   TRY(upload(ba, ba->d_adT.p, w->adTarget, nn * 64));
   TRY(upload(ba, ba->d_fprior.p, w->framePrior, (size_t)n * 8));
   TRY(upload(ba, ba->d_fdprior.p, w->frameDeltaPrior, (size_t)n * 8));
+  ba->h_fprior.assign(w->framePrior, w->framePrior + (size_t)n * 8);
+  ba->h_fdprior.assign(w->frameDeltaPrior, w->frameDeltaPrior + (size_t)n * 8);
   TRY(upload(ba, ba->d_precalc.p, w->precalc, nn * HSLAM_PRECALC_STRIDE));
   TRY(upload(ba, ba->d_adHTd.p, w->adHTdeltaF, nn * 8));
   TRY(ba->d_x.ensure(ba->N)); TRY(ba->d_xc.ensure(4)); TRY(ba->d_xAd.ensure(nn * 8));
@@ -647,6 +652,7 @@ static int top_attr() {
   if (!done) {
     HS_CUDA(cudaFuncSetAttribute(ba_top_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kTopSmem));
     HS_CUDA(cudaFuncSetAttribute(ba_top_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kTopSmem));
+    HS_CUDA(cudaFuncSetAttribute(ba_top_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kTopSmem));
     done = true;
   }
   return 0;
@@ -661,6 +667,8 @@ static int launch_top(hslam_ba* ba, int modes) {
     HS_LAUNCH(ctx, HSLAM_K_BA_TOP, (ba_top_kernel<0><<<T, 2 * TOP_THREADS, kTopSmem, ctx->stream>>>(ba->d_desc.p, nullptr, 1)));
   if (T > 0 && (modes & 2))
     HS_LAUNCH(ctx, HSLAM_K_BA_TOP, (ba_top_kernel<1><<<T, 2 * TOP_THREADS, kTopSmem, ctx->stream>>>(ba->d_desc.p, nullptr, 1)));
+  if (T > 0 && (modes & 4))   // addPoint<2> over the points flagged in desc.marg
+    HS_LAUNCH(ctx, HSLAM_K_BA_TOP, (ba_top_kernel<2><<<T, 2 * TOP_THREADS, kTopSmem, ctx->stream>>>(ba->d_desc.p, nullptr, 1)));
   HS_CUDA(cudaGetLastError());
   return 0;
 }
@@ -887,6 +895,62 @@ int hslam_ba_residual_results(hslam_ba* ba, int8_t* state_state, uint8_t* is_act
   TRY(download_res(ba, ba->d_rtz.p, 8, res_toZeroF));
   TRY(download_res(ba, ba->d_J.p, 74, J74));
   return end_call(ba);
+}
+
+int hslam_ba_marginalize_points(hslam_ba* ba, const int32_t* point_ids, int count, float prior_scale, double* M, double* Mb,
+                                double* Msc, double* Mbsc, int* nres) {
+  HS_ARG(ba && ba->have_topology && ba->have_window && (count == 0 || point_ids), "hslam_ba_marginalize_points: bad argument");
+  hslam_ctx* ctx = ba->ctx;
+  HS_CUDA(cudaSetDevice(ctx->device));
+  const int P = ba->P;
+  std::vector<unsigned char> flags((size_t)P + 1, 0);
+  for (int i = 0; i < count; ++i) {
+    HS_ARG(point_ids[i] >= 0 && point_ids[i] < P, "hslam_ba_marginalize_points: point id out of range");
+    flags[ba->p_orig2sorted[point_ids[i]]] = 1;
+  }
+  TRY(ba->d_marg.ensure((size_t)P + 1));
+  TRY(upload(ba, ba->d_marg.p, flags.data(), (size_t)P + 1));
+  if (P > 0)
+    HS_LAUNCH(ctx, HSLAM_K_BA_FIXLIN, (ba_scale_prior_kernel<<<(P + 255) / 256, 256, 0, ctx->stream>>>(ba->hdesc.p, ba->d_marg.p, prior_scale)));
+  // the pass runs on a descriptor with the marginalisation switches set: flagged points only, no prior shift in the
+  // Schur scalars, no priors in the stitch (stitchDouble(..., usePrior=false), EnergyFunctional.cpp:578-579)
+  const BADesc saved = ba->hdesc;
+  ba->hdesc.marg = ba->d_marg.p; ba->hdesc.shift_prior = 0;
+  ba->hdesc.S.add_priors = 0; ba->hdesc.S.has_L = 1;
+  ba->desc_version++;
+  TRY(launch_top(ba, 4));
+  TRY(launch_schur(ba));
+  TRY(launch_stitch(ba, 1, 3));
+  TRY(queue_Hb(ba, 1, M, Mb));
+  TRY(queue_Hb(ba, 2, Msc, Mbsc));
+  TRY(download(ba, nres, ba->d_nres.p + 1, 1));
+  TRY(ba_flush(ba));   // the descriptor is restored only after the pass has run
+  ba->hdesc = saved;
+  ba->desc_version++;
+  return 0;
+}
+
+int hslam_ba_calc_l_energy(hslam_ba* ba, double* energy_out) {
+  HS_ARG(ba && energy_out && ba->have_topology && ba->have_window, "hslam_ba_calc_l_energy: bad argument");
+  hslam_ctx* ctx = ba->ctx;
+  HS_CUDA(cudaSetDevice(ctx->device));
+  TRY(sync_desc(ba));
+  const int blocks = std::max(1, (ba->P + 127) / 128);
+  void* tmp;
+  TRY(scratch_alloc(ba, (size_t)blocks * sizeof(double), &tmp));
+  HS_LAUNCH(ctx, HSLAM_K_BA_ENERGY, (ba_lenergy_kernel<<<blocks, 128, 0, ctx->stream>>>(ba->d_desc.p, (double*)tmp)));
+  HS_CUDA(cudaGetLastError());
+  std::vector<double> part(blocks);
+  TRY(download(ba, part.data(), (const double*)tmp, (size_t)blocks));
+  TRY(ba_flush(ba));
+  // frame and calibration priors (EnergyFunctional.cpp:355-358), then the point partials in block order
+  double E = 0.0;
+  for (int f = 0; f < ba->n; ++f)
+    for (int i = 0; i < 8; ++i) E += ba->h_fdprior[8 * f + i] * ba->h_fprior[8 * f + i] * ba->h_fdprior[8 * f + i];
+  for (int i = 0; i < 4; ++i) E += (double)(ba->hdesc.W.cDeltaF[i] * (float)ba->hdesc.S.cPrior[i] * ba->hdesc.W.cDeltaF[i]);
+  for (double v : part) E += v;
+  *energy_out = E;
+  return 0;
 }
 
 int hslam_ba_resubstitute(hslam_ba* ba, const double* x, float* step_out) {

@@ -134,6 +134,9 @@ struct BADesc {
   // stitch
   StitchArgs S;
   // host <-> device layout conversion (caller order <-> sorted order) and back-substitution
+  // marginalisation pass (EnergyFunctional::marginalizePointsF): per sorted point 1 = to marginalise; null otherwise
+  const unsigned char* marg;
+  int shift_prior;           // SC addPoint's shiftPriorToZero (1 in accumulateSCF_MT, 0 in marginalizePointsF)
   const int* r_s2o;          // sorted residual position -> caller residual id
   const int* p_s2o;          // sorted point position -> caller point id
   double* x;                 // (8n+4) solution of the reduced system (uploaded by resubstitute)
@@ -485,7 +488,7 @@ __device__ __forceinline__ void top_accumulate(const BADesc& D, const TopChunk& 
   const BAWin& W = D.W;
   const BARes& r = D.r;
   const int s = r.rs;
-  float dp[8];
+  float dp[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
   if (MODE == 1) {
 #pragma unroll
     for (int j = 0; j < 8; ++j) dp[j] = __ldg(W.adHTdeltaF + 8 * ch.pair + j);
@@ -495,7 +498,8 @@ __device__ __forceinline__ void top_accumulate(const BADesc& D, const TopChunk& 
     // iteration is independent of the flags, so an iteration costs one memory round trip instead of two.  A
     // filtered-out residual contributes exact zeros (its x, y and bottom-right terms are zeroed).
     const bool lin = r.isLin[k] != 0, act = r.isActive[k] != 0;
-    const bool use = (MODE == 0) ? (!lin && act) : (lin && act);
+    // mode 2 = addPoint<2> (marginalisation): active residuals of the points flagged in D.marg, resApprox = res_toZeroF
+    const bool use = (MODE == 0) ? (!lin && act) : (MODE == 1) ? (lin && act) : (act && D.marg[r.point[k]] != 0);
     const float* J = r.J + k;
     float x[10], y[10];
 #pragma unroll
@@ -528,8 +532,10 @@ __device__ __forceinline__ void top_accumulate(const BADesc& D, const TopChunk& 
       for (int j = 0; j < 8; ++j) {
         float i0 = J[(J_IDX0 + j) * s], i1 = J[(J_IDX1 + j) * s], a0 = J[(J_AB0 + j) * s], a1 = J[(J_AB1 + j) * s];
         float rz = r.rtz[j * s + k];
-        rz = xadd(rz, xmul(i0, Jpx)); rz = xadd(rz, xmul(i1, Jpy));
-        rz = xadd(rz, xmul(a0, dp[6])); rz = xadd(rz, xmul(a1, dp[7]));
+        if (MODE == 1) {   // mode 2 takes res_toZeroF as it is (AccumulatedTopHessian.cpp:61)
+          rz = xadd(rz, xmul(i0, Jpx)); rz = xadd(rz, xmul(i1, Jpy));
+          rz = xadd(rz, xmul(a0, dp[6])); rz = xadd(rz, xmul(a1, dp[7]));
+        }
         JIr0 = xadd(JIr0, xmul(rz, i0)); JIr1 = xadd(JIr1, xmul(rz, i1));
         Jabr0 = xadd(Jabr0, xmul(rz, a0)); Jabr1 = xadd(Jabr1, xmul(rz, a1));
         rr = xadd(rr, xmul(rz, rz));
@@ -564,7 +570,7 @@ __device__ __forceinline__ void top_accumulate(const BADesc& D, const TopChunk& 
       // per-residual contribution to the point sums (:114-117), exact ops: they are summed per point in
       // the point's own order by the Schur kernel, which keeps Hdd/bd/Hcd bit-identical to the oracle.
       float Ji0 = xadd(xmul(a, d0), xmul(b, d1)), Ji1 = xadd(xmul(b, d0), xmul(c, d1));
-      float* o = r.ptc[MODE] + k;
+      float* o = r.ptc[0] + k;
       o[0] = xadd(xmul(JIr0, d0), xmul(JIr1, d1));
       o[s] = xadd(xmul(Ji0, d0), xmul(Ji1, d1));
 #pragma unroll
@@ -725,7 +731,7 @@ __global__ void __launch_bounds__(2 * TOP_THREADS, 2) ba_top_kernel(const BADesc
   for (int t = t0; t < t1; ++t) {
     const TopTile tl = D.toptiles[t];
     issue(t + TOP_STAGES - 1);   // refills the stage that was consumed in the previous iteration
-    const int chunk = tl.chunk + mode * D.top_chunks0;
+    const int chunk = tl.chunk + (mode ? 1 : 0) * D.top_chunks0;   // modes 1 and 2 share the second accumulator set
     if (chunk != cur) {
       if (cur >= 0) {
         top_flush(D, cur, part, acc, nres, red, &last);
@@ -735,9 +741,9 @@ __global__ void __launch_bounds__(2 * TOP_THREADS, 2) ba_top_kernel(const BADesc
       }
       cur = chunk;
     }
-    if (mode == 1) {
+    if (mode != 0) {
       const TopChunk ch = {D.topchunks[chunk].pair, tl.start, tl.count, 1};
-      if (part == 0) top_accumulate<1, 0>(D, ch, acc, nres); else top_accumulate<1, 1>(D, ch, acc, nres);
+      if (part == 0) top_accumulate<(MODE ? MODE : 1), 0>(D, ch, acc, nres); else top_accumulate<(MODE ? MODE : 1), 1>(D, ch, acc, nres);
       continue;
     }
     cp_async_wait<TOP_STAGES - 1>();   // the group of tile t has landed (for this thread's copies)
@@ -912,8 +918,10 @@ ba_schur_kernel(const BADesc* __restrict__ descs, const int* __restrict__ prefix
   auto load_slots = [&](int base) {
     const int cnt = min(SC_PTS, ch.count - base);   // <= 0 beyond the chunk
 #pragma unroll
-    for (int i = 0; i < NI; ++i)
+    for (int i = 0; i < NI; ++i) {
       en[i] = (ilp[i] < cnt) ? pts.slot[(size_t)(ch.start + base + ilp[i]) * maxres + isl[i]] : -1;
+      if (D.marg && ilp[i] < cnt && D.marg[ch.start + base + ilp[i]] == 0) en[i] = -1;   // marginalisation pass: flagged points only
+    }
   };
   auto load_data = [&](int base) {   // consumes en[]
     const int cnt = min(SC_PTS, ch.count - base);
@@ -994,7 +1002,7 @@ ba_schur_kernel(const BADesc* __restrict__ descs, const int* __restrict__ prefix
       const int item = rd * SC_THREADS + threadIdx.x, lp = item >> 3, c = item & 7;
       float rowv = 0.f, rowh = 0.f;
       if (c < 6) {
-        if (lp < cnt) {
+        if (lp < cnt && (!D.marg || D.marg[ch.start + base + lp] != 0)) {
           const int p = ch.start + base + lp;
           float sum[2] = {0.f, 0.f};
           int ngood = 0;
@@ -1009,7 +1017,10 @@ ba_schur_kernel(const BADesc* __restrict__ descs, const int* __restrict__ prefix
           float hdi = 0.f;
           if (c == 0) {
             pts.bd[0][p] = sum[0]; pts.bd[1][p] = sum[1];
-            if (ngood > 0) mine = xadd(xadd(sum[0], sum[1]), xmul(prc[rd], dec[rd]));   // shiftPriorToZero (EnergyFunctional.cpp:209)
+            if (ngood > 0) {
+              mine = xadd(sum[0], sum[1]);
+              if (D.shift_prior) mine = xadd(mine, xmul(prc[rd], dec[rd]));   // shiftPriorToZero (EnergyFunctional.cpp:209)
+            }
             pts.bdSumF[p] = mine;
           } else if (c == 1) {
             pts.Hdd[0][p] = sum[0]; pts.Hdd[1][p] = sum[1];
@@ -1029,7 +1040,7 @@ ba_schur_kernel(const BADesc* __restrict__ descs, const int* __restrict__ prefix
           }
           rowv = mine; rowh = hdi;
         } else if (c == 1 && lp < SC_PTS) {
-          wv[lp] = 0.f;
+          wv[lp] = 0.f;   // beyond the chunk, or not flagged in a marginalisation pass: contributes nothing
         }
       }
       // the 8 lanes of a point share HdiF and write the scaled copy of the row: lane c < 6 its own entry of the
@@ -1536,6 +1547,56 @@ __global__ void __launch_bounds__(256) ba_batch_export_kernel(const BADesc* __re
   }
   if (tid < 2 && o.dn_nres >= 0) reinterpret_cast<int*>(dn + o.dn_nres)[tid] = D.S.nres[tid];
   if (tid == 0 && o.dn_energy >= 0) *reinterpret_cast<double*>(dn + o.dn_energy) = *D.energy;
+}
+
+// marginalizePointsF: priorF *= setting_idepthFixPriorMargFac for the flagged points (EnergyFunctional.cpp:564)
+__global__ void ba_scale_prior_kernel(BAPts pts, const unsigned char* __restrict__ marg, float scale) {
+  int p = blockIdx.x * blockDim.x + threadIdx.x;
+  if (p < pts.P && marg[p]) const_cast<float*>(pts.priorF)[p] = xmul(pts.priorF[p], scale);
+}
+
+// EnergyFunctional::calcLEnergyPt (EnergyFunctional.cpp:289-347): per point the energy of its linearised, active
+// residuals at the current delta, E = sum (2 res_toZeroF + J delta) * J delta, plus deltaF^2 priorF.  One thread per
+// point; per-block fp64 partials (summed in block order by the caller).
+__global__ void __launch_bounds__(128) ba_lenergy_kernel(const BADesc* __restrict__ descs, double* __restrict__ partial) {
+  const BADesc& D = descs[0];
+  const BARes& r = D.r;
+  const BAPts& pts = D.p;
+  const int p = blockIdx.x * 128 + threadIdx.x;
+  const int s = r.rs, n = D.W.n;
+  float E = 0.f;
+  if (p < pts.P) {
+    const float dd = pts.deltaF[p];
+    for (int i = pts.res_begin[p]; i < pts.res_begin[p + 1]; ++i) {
+      const int k = pts.res_index[i];
+      if (!r.isLin[k] || !r.isActive[k]) continue;
+      const float* J = r.J + k;
+      const float* dp = D.W.adHTdeltaF + 8 * r.pair[k];
+      float dx = 0.f, dy = 0.f, cxs = 0.f, cys = 0.f;
+#pragma unroll
+      for (int j = 0; j < 6; ++j) { dx = xadd(dx, xmul(J[(J_XI0 + j) * s], dp[j])); dy = xadd(dy, xmul(J[(J_XI1 + j) * s], dp[j])); }
+#pragma unroll
+      for (int j = 0; j < 4; ++j) { cxs = xadd(cxs, xmul(J[(J_C0 + j) * s], D.W.cDeltaF[j])); cys = xadd(cys, xmul(J[(J_C1 + j) * s], D.W.cDeltaF[j])); }
+      const float jx = xadd(xadd(dx, cxs), xmul(J[J_DD * s], dd)), jy = xadd(xadd(dy, cys), xmul(J[(J_DD + 1) * s], dd));
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        float Jd = xmul(J[(J_IDX0 + j) * s], jx);
+        Jd = xadd(Jd, xmul(J[(J_IDX1 + j) * s], jy));
+        Jd = xadd(Jd, xmul(J[(J_AB0 + j) * s], dp[6]));
+        Jd = xadd(Jd, xmul(J[(J_AB1 + j) * s], dp[7]));
+        float r0 = r.rtz[j * s + k];
+        r0 = xadd(xadd(r0, r0), Jd);
+        E = xadd(E, xmul(Jd, r0));
+      }
+    }
+    E = xadd(E, xmul(xmul(dd, dd), pts.priorF[p]));
+    (void)n;
+  }
+  __shared__ double red[4];
+  double e = warp_sum((double)E);
+  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = e;
+  __syncthreads();
+  if (threadIdx.x == 0) partial[blockIdx.x] = red[0] + red[1] + red[2] + red[3];
 }
 
 }  // namespace hs

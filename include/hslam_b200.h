@@ -379,6 +379,18 @@ int hslam_ba_point_results(hslam_ba* ba, float* HdiF, float* bdSumF, float* idep
 int hslam_ba_residual_results(hslam_ba* ba, int8_t* state_state, uint8_t* is_active,
                               float* JpJdF, float* J74, float* res_toZeroF /*R*8*/);
 
+/* EnergyFunctional::marginalizePointsF (Src/EnergyFunctional.cpp:545-609), its accumulate + stitch part, for the
+ * points listed in point_ids (caller order): priorF *= prior_scale (setting_idepthFixPriorMargFac),
+ * AccumulatedTopHessianSSE::addPoint<2> and AccumulatedSCHessianSSE::addPoint(p, shiftPriorToZero=false) over
+ * them, then stitchDouble(usePrior=false) of both (AccumulatedTopHessian.cpp:148-215, AccumulatedSCHessian.cpp:
+ * 135-195).  Outputs (host, col-major, each nullable): M/Mb, Msc/Mbsc; the caller forms H = M - Msc, b = Mb - Mbsc
+ * and keeps the HM/bM algebra.  nres = accSSE_top_A->nres[0] (resInM increment).  The residuals of these points
+ * must have been fixed with hslam_ba_fix_linearization.   */
+int hslam_ba_marginalize_points(hslam_ba* ba, const int32_t* point_ids, int count, float prior_scale,
+                                double* M, double* Mb, double* Msc, double* Mbsc, int* nres);
+/* EnergyFunctional::calcLEnergyF_MT / calcLEnergyPt (Src/EnergyFunctional.cpp:289-364): energy of the linearised
+ * residuals and of the priors at the current deltas.   */
+int hslam_ba_calc_l_energy(hslam_ba* ba, double* energy_out);
 /* EnergyFunctional::resubstituteF_MT / resubstituteFPt
  * (EnergyFunctional.cpp:222-274): x is the (8n+4) solution; step_out[P] =
  * efPoint->step.   */

@@ -164,6 +164,13 @@ int orc_ba_residual_results(orc_ba* ba, int8_t* state_state, uint8_t* is_active,
 int orc_ba_raw_top(orc_ba* ba, int which, double* acc1313);
 int orc_ba_raw_sc(orc_ba* ba, double* accD, double* accE, double* accEB, double* accHcc, double* accbc);
 int orc_ba_resubstitute(orc_ba* ba, const double* x, float* step_out);
+/* EnergyFunctional::marginalizePointsF (Src/EnergyFunctional.cpp:545-609), accumulate + stitch part, over the listed
+ * points (caller order ids): priorF *= prior_scale, addPoint<2>, SC addPoint(p,false), stitchDouble(usePrior=false).
+ * Outputs col-major (8n+4)^2 / (8n+4): M, Mb (top), Msc, Mbsc (Schur); nres = accSSE_top_A->nres[0]. */
+int orc_ba_marginalize_points(orc_ba* ba, const int32_t* point_ids, int count, float prior_scale, double* M, double* Mb,
+                              double* Msc, double* Mbsc, int* nres);
+/* EnergyFunctional::calcLEnergyF_MT (Src/EnergyFunctional.cpp:349-364). */
+int orc_ba_calc_l_energy(orc_ba* ba, double* out);
 
 #ifdef __cplusplus
 }

@@ -264,6 +264,8 @@ struct BABase {
   virtual int raw_top(int, double*) = 0;
   virtual int raw_sc(double*, double*, double*, double*, double*) = 0;
   virtual int resubstitute(const double*, float*) = 0;
+  virtual int marginalize_points(const int32_t*, int, float, double*, double*, double*, double*, int*) = 0;
+  virtual int calc_l_energy(double*) = 0;
 };
 
 template <class T> struct BA : BABase {
@@ -932,6 +934,74 @@ template <class T> struct BA : BABase {
     });
     return 0;
   }
+
+  // EnergyFunctional::marginalizePointsF, Src/EnergyFunctional.cpp:545-609 (the accumulate + stitch part):
+  // priorF *= setting_idepthFixPriorMargFac, addPoint<2> + SC addPoint(p, shiftPriorToZero=false) over the points
+  // to marginalise on tid 0, stitchDouble(usePrior=false) of both.  The caller forms H = M - Msc, b = Mb - Mbsc.
+  int marginalize_points(const int32_t* pids, int count, float prior_scale, double* M, double* Mb, double* Msc, double* Mbsc,
+                         int* nres) override {
+    accTop[1].assign(nt, std::vector<AccApprox<T>>(n * n));
+    nresTop[1].assign(nt, 0);
+    for (auto& v : accTop[1]) for (auto& a : v) a.init();
+    accD.assign(nt, std::vector<Tier<T, 64>>(n * n * n));
+    accE.assign(nt, std::vector<Tier<T, 32>>(n * n));
+    accEB.assign(nt, std::vector<Tier<T, 8>>(n * n));
+    accHcc.assign(nt, Tier<T, 16>()); accbc.assign(nt, Tier<T, 4>());
+    for (int t = 0; t < nt; ++t) {
+      for (auto& a : accD[t]) a.init();
+      for (auto& a : accE[t]) a.init();
+      for (auto& a : accEB[t]) a.init();
+      accHcc[t].init(); accbc[t].init();
+    }
+    for (int i = 0; i < count; ++i) {
+      const int p = pids[i];
+      if (p < 0 || p >= P) return -1;
+      ppriorF[p] *= prior_scale;
+      add_point_top(2, p, 0);
+      add_point_sc(p, false, 0);
+    }
+    stitch_top(1, false, M, Mb);
+    stitch_sc(Msc, Mbsc);
+    if (nres) *nres = nresTop[1][0];
+    return 0;
+  }
+
+  // EnergyFunctional::calcLEnergyF_MT / calcLEnergyPt, Src/EnergyFunctional.cpp:289-364 (Accumulator11 is a
+  // sequential float sum with 1k / 1M shift-up tiers; restated here as a plain sum in T)
+  int calc_l_energy(double* out) override {
+    double E = 0;
+    for (int f = 0; f < n; ++f)
+      for (int i = 0; i < 8; ++i) E += frameDeltaPrior[8 * f + i] * framePrior[8 * f + i] * frameDeltaPrior[8 * f + i];
+    for (int i = 0; i < 4; ++i) E += (double)((float)cDeltaF[i] * (float)cPrior[i] * (float)cDeltaF[i]);
+    T acc = 0;
+    T dc[4] = {(T)cDeltaF[0], (T)cDeltaF[1], (T)cDeltaF[2], (T)cDeltaF[3]};
+    for (int p = 0; p < P; ++p) {
+      T dd = pdeltaF[p];
+      for (int k = res_begin[p]; k < res_begin[p + 1]; ++k) {
+        int r = res_index[k];
+        if (!isLinearized[r] || !isActive[r]) continue;
+        const T* Jr = &J[(size_t)r * 74];
+        const float* dp = &adHTdeltaF[8 * (size_t)(phost[p] + rtarget[r] * n)];
+        T dx = 0, dy = 0, cxx = 0, cyy = 0;
+        for (int i = 0; i < 6; ++i) { dx += Jr[8 + i] * (T)dp[i]; dy += Jr[14 + i] * (T)dp[i]; }
+        for (int i = 0; i < 4; ++i) { cxx += Jr[20 + i] * dc[i]; cyy += Jr[24 + i] * dc[i]; }
+        T jx = dx + cxx + Jr[28] * dd, jy = dy + cyy + Jr[29] * dd;
+        for (int i = 0; i < 8; ++i) {
+          T Jdelta = Jr[30 + i] * jx;
+          Jdelta = Jdelta + Jr[38 + i] * jy;
+          Jdelta = Jdelta + Jr[46 + i] * (T)dp[6];
+          Jdelta = Jdelta + Jr[54 + i] * (T)dp[7];
+          T r0 = res_toZeroF[(size_t)r * 8 + i];
+          r0 = r0 + r0;
+          r0 = r0 + Jdelta;
+          acc += Jdelta * r0;
+        }
+      }
+      acc += (T)pdeltaF[p] * (T)pdeltaF[p] * (T)ppriorF[p];
+    }
+    *out = E + (double)acc;
+    return 0;
+  }
 };
 }  // namespace
 
@@ -967,4 +1037,9 @@ int orc_ba_raw_sc(orc_ba* ba, double* D, double* E, double* EB, double* Hcc, dou
   return ba->impl->raw_sc(D, E, EB, Hcc, bc);
 }
 int orc_ba_resubstitute(orc_ba* ba, const double* x, float* step) { return ba->impl->resubstitute(x, step); }
+int orc_ba_marginalize_points(orc_ba* ba, const int32_t* pids, int count, float prior_scale, double* M, double* Mb, double* Msc,
+                              double* Mbsc, int* nres) {
+  return ba->impl->marginalize_points(pids, count, prior_scale, M, Mb, Msc, Mbsc, nres);
+}
+int orc_ba_calc_l_energy(orc_ba* ba, double* out) { return ba->impl->calc_l_energy(out); }
 }

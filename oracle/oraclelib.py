@@ -372,6 +372,19 @@ class BAOracle:
         return dict(D=D.reshape(n**3, 8, 8).transpose(0, 2, 1), E=E.reshape(n * n, 4, 8).transpose(0, 2, 1), EB=EB.reshape(n * n, 8),
                     Hcc=Hcc.reshape(4, 4).T, bc=bc)
 
+    def marginalize_points(self, point_ids, prior_scale):
+        N = 8 * self.n + 4
+        M = np.zeros(N * N); Mb = np.zeros(N); Ms = np.zeros(N * N); Mbs = np.zeros(N); nres = C.c_int(0)
+        ids = np.ascontiguousarray(point_ids, np.int32)
+        assert self.L.orc_ba_marginalize_points(self.h, _ptr(ids), C.c_int(len(ids)), C.c_float(prior_scale), _ptr(M), _ptr(Mb),
+                                                _ptr(Ms), _ptr(Mbs), C.byref(nres)) == 0
+        return M.reshape(N, N).T.copy(), Mb, Ms.reshape(N, N).T.copy(), Mbs, nres.value
+
+    def calc_l_energy(self):
+        e = C.c_double(0)
+        assert self.L.orc_ba_calc_l_energy(self.h, C.byref(e)) == 0
+        return e.value
+
     def resubstitute(self, x):
         step = np.zeros(self.P, np.float32)
         assert self.L.orc_ba_resubstitute(self.h, _ptr(np.ascontiguousarray(x, np.float64)), _ptr(step)) == 0

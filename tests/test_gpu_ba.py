@@ -298,3 +298,45 @@ def test_batch_step_host_matches_single_window_calls(ctx, capi, synth, pinned):
         e.close()
     for f in frames:
         f.close()
+
+
+def test_marginalize_points_and_lenergy(ctx, capi, O, synth):
+    """EnergyFunctional::marginalizePointsF (addPoint<2> + SC addPoint(p,false) + stitchDouble without priors) and
+    calcLEnergyF_MT against the oracle: M, Mb, Msc, Mbsc <= 1e-5 vs fp64 and no worse than the float restatement."""
+    win, _ = synth.make_window(w=320, h=240, n_frames=5, points_per_frame=300, seed=31)
+    frames = [capi.Frame(ctx, im, 1) for im in win.images]
+    dIs = [O.pyramid(im, 1)[0][0] for im in win.images]
+    ef = capi.EnergyFunctional(ctx); ef.set_window(win, frames); ef.set_topology(win)
+    of = O.BAOracle(win, dIs, prec="f"); od = O.BAOracle(win, dIs, prec="d")
+    for b in (ef, of, od):
+        (b.linearizeAll if b is ef else b.linearize)(False)
+        (b.applyRes if b is ef else b.apply_res)()
+    rng = np.random.default_rng(4)
+    pts = np.sort(rng.choice(win.P, size=win.P // 5, replace=False)).astype(np.int32)
+    act = ef.residual_results(want_J=False)["is_active"]
+    ids = np.array([r for p in pts for r in win.res_index[win.res_begin[p]:win.res_begin[p + 1]] if act[r]], np.int32)
+    assert len(ids) > 100
+    # move the linearisation point away so that res_toZeroF differs from resF, then fix those residuals
+    idp = (win.idepth * np.float32(1.002)).astype(np.float32)
+    for b in (ef, of, od):
+        b.update_points(idepth=idp, deltaF=(idp - win.idepth_zero).astype(np.float32))
+        (b.fixLinearization if b is ef else b.fix_linearization)(ids)
+    eg, ef_, ed = ef.calcLEnergyF_MT(), of.calc_l_energy(), od.calc_l_energy()
+    assert ed != 0 and abs(eg - ed) <= max(1e-5, 1.5 * abs(ef_ - ed) / abs(ed)) * abs(ed), (eg, ef_, ed)
+    scale = 36.0
+    g = ef.marginalizePointsF(pts, scale)
+    f = of.marginalize_points(pts, scale)
+    d = od.marginalize_points(pts, scale)
+    assert g[4] == f[4] == d[4] and g[4] > 0
+    for k, nm in enumerate(("M", "Mb", "Msc", "Mbsc")):
+        e, fe = rel_fro(g[k], d[k]), rel_fro(f[k], d[k])
+        assert np.abs(d[k]).max() > 0
+        assert e <= max(1e-5, 1.5 * fe), (nm, e, fe)
+    # the pass leaves the handle usable: a normal accumulate afterwards equals the oracle's
+    sys3 = ef.accumulate_all()
+    for k, (H, b) in enumerate(sys3):
+        Hd, bd, _ = od.accumulate(k)
+        assert rel_fro(H, Hd) <= 1e-5 and rel_fro(b, bd) <= 1e-4, k
+    ef.close()
+    for fr in frames:
+        fr.close()

@@ -169,3 +169,28 @@ def test_oob_and_outlier_states(O, synth, setup):
     # once OOB, always OOB (OptimizationClasses.cpp:47-51,239-242)
     lin2 = ba.linearize(False)
     assert np.all(lin2["newState"][first] == 1)
+
+
+def test_marginalisation_pass_reduces_to_active_accumulate_at_zero_delta(O, synth):
+    """Known answer for the marginalisation restatement (EnergyFunctional.cpp:545-609): with every delta zero
+    (state == state_zero, deltaF = 0, cDeltaF = 0) res_toZeroF == resF, so addPoint<2> over ALL points after fixing all
+    active residuals equals addPoint<0> before (M == H_A without priors, Mb == b_A), and the Schur part equals
+    accumulateSCF's (the prior shift is zero).  Also: calcLEnergy is zero at zero delta."""
+    win, _ = synth.make_window(w=320, h=240, points_per_frame=80, n_frames=4, seed=12, state_noise=0.0)
+    win.deltaF[:] = 0
+    win.cDeltaF[:] = 0
+    win.frameDeltaPrior[:] = 0
+    assert np.abs(win.adHTdeltaF).max() == 0
+    dIs = [O.pyramid(im, 1)[0][0] for im in win.images]
+    o = O.BAOracle(win, dIs, prec="d")
+    o.linearize(False); o.apply_res()
+    HA, bA, nA = o.accumulate(0)
+    o.accumulate(1)
+    HS, bS, _ = o.accumulate(2)
+    act = o.residual_results()["is_active"].astype(bool)
+    o.fix_linearization(np.nonzero(act)[0].astype(np.int32))
+    assert abs(o.calc_l_energy()) < 1e-9
+    M, Mb, Ms, Mbs, nres = o.marginalize_points(np.arange(win.P, dtype=np.int32), 1.0)
+    assert nres == nA == act.sum()
+    assert rel_fro(M, HA) < 1e-12 and rel_fro(Mb, bA) < 1e-12
+    assert rel_fro(Ms, HS) < 1e-12 and rel_fro(Mbs, bS) < 1e-12
