@@ -126,7 +126,7 @@ class Context:
 
     def profile_read(self):
         """{kernel class: (summed ms, launches)} measured with CUDA events on the context stream."""
-        K = 16
+        K = 17
         ms = np.zeros(K, np.float32); cnt = np.zeros(K, np.int32)
         _chk(self.L.hslam_profile_read(self.h, _ptr(ms), _ptr(cnt)))
         self.L.hslam_kernel_name.restype = C.c_char_p
@@ -239,6 +239,38 @@ class CoarseTracker:
         if self.h:
             self.L.hslam_tracker_destroy(self.h)
             self.h = C.c_void_p()
+
+
+class TraceSettings(C.Structure):
+    _fields_ = [(k, C.c_float) for k in ("maxPixSearch", "slackInterval", "stepsize", "minImprovementFactor", "GNThreshold",
+                                         "extraSlackOnTH", "huberTH")] + [("minTraceTestRadius", C.c_int), ("GNIterations", C.c_int)]
+
+
+class ImmatureSoA(C.Structure):
+    _fields_ = [("n_points", C.c_int)] + [(k, C.c_void_p) for k in (
+        "host_idx", "u", "v", "gradH", "color", "weights", "energyTH", "idepth_min", "idepth_max", "quality", "lastTraceStatus",
+        "lastTraceUV", "lastTracePixelInterval")]
+
+
+def traceNewCoarse(ctx: "Context", frame: "Frame", ims, settings=None):
+    """System::traceNewCoarse (Src/Mapping.cpp:494-538): ImmaturePoint::traceOn for every point of `ims` (an object
+    with the ImmatureSet fields of synth.py) against `frame`; the in/out members are updated in place."""
+    keep = dict(host_idx=np.ascontiguousarray(ims.host_idx, np.int32), u=np.ascontiguousarray(ims.u, np.float32),
+                v=np.ascontiguousarray(ims.v, np.float32), gradH=np.ascontiguousarray(ims.gradH, np.float32),
+                color=np.ascontiguousarray(ims.color, np.float32), weights=np.ascontiguousarray(ims.weights, np.float32),
+                energyTH=np.ascontiguousarray(ims.energyTH, np.float32))
+    for k in ("idepth_min", "idepth_max", "quality", "lastTraceUV", "lastTracePixelInterval"):
+        assert getattr(ims, k).dtype == np.float32 and getattr(ims, k).flags.c_contiguous
+    assert ims.status.dtype == np.int8
+    s = ImmatureSoA(len(keep["u"]))
+    for k, a in keep.items():
+        setattr(s, k, _ptr(a))
+    s.idepth_min, s.idepth_max, s.quality = _ptr(ims.idepth_min), _ptr(ims.idepth_max), _ptr(ims.quality)
+    s.lastTraceStatus, s.lastTraceUV, s.lastTracePixelInterval = _ptr(ims.status), _ptr(ims.lastTraceUV), _ptr(ims.lastTracePixelInterval)
+    K = np.ascontiguousarray(ims.KRKi, np.float32); T = np.ascontiguousarray(ims.Kt, np.float32); A = np.ascontiguousarray(ims.aff, np.float32)
+    _chk(ctx.L.hslam_trace_immature(ctx.h, frame.h, C.byref(settings) if settings is not None else None, C.c_int(len(K)),
+                                    _ptr(K), _ptr(T), _ptr(A), C.byref(s)))
+    return ims
 
 
 class EnergyFunctional:

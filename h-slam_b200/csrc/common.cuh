@@ -116,6 +116,8 @@ struct hslam_ctx {
   struct ProfRec { int k; cudaEvent_t a, b; };
   std::vector<ProfRec> prof_recs;
   std::vector<cudaEvent_t> prof_pool;
+  // staging of hslam_trace_immature
+  char* trace_dev = nullptr; char* trace_host = nullptr; size_t trace_cap = 0;
   // pinned host blocks handed out by hslam_host_alloc (copies to/from them are direct DMA)
   struct HostBlock { char* p; size_t bytes; };
   std::vector<HostBlock> host_blocks;

@@ -67,6 +67,8 @@ int hslam_destroy(hslam_ctx* c) {
   for (auto& r : c->prof_recs) { cudaEventDestroy(r.a); cudaEventDestroy(r.b); }
   for (auto e : c->prof_pool) cudaEventDestroy(e);
   for (auto& b : c->host_blocks) cudaFreeHost(b.p);
+  if (c->trace_dev) cudaFree(c->trace_dev);
+  if (c->trace_host) cudaFreeHost(c->trace_host);
   cudaStreamSynchronize(c->side);
   cudaEventDestroy(c->ev_fork); cudaEventDestroy(c->ev_join);
   cudaStreamDestroy(c->side);
@@ -116,7 +118,7 @@ int hslam_host_free(hslam_ctx* c, void* p) {
 
 static const char* k_names[HSLAM_K_COUNT] = {"pyramid_level", "trk_eval", "trk_track", "ba_linearize", "ba_apply",
                                              "ba_top", "ba_fold_top", "ba_point_sum", "ba_schur", "ba_fold_sc",
-                                             "ba_stitch", "ba_resub", "ba_fixlin", "unpack_level", "ba_energy", "ba_layout"};
+                                             "ba_stitch", "ba_resub", "ba_fixlin", "unpack_level", "ba_energy", "ba_layout", "trace"};
 const char* hslam_kernel_name(int k) { return (k >= 0 && k < HSLAM_K_COUNT) ? k_names[k] : ""; }
 
 int hslam_profile_enable(hslam_ctx* c, int enable) {

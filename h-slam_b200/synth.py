@@ -519,3 +519,78 @@ def make_window(w=640, h=480, n_frames=7, points_per_frame=2000, seed=4321, frac
         point_idx=np.array(point_idx, np.int32), target_idx=np.array(target_idx, np.int32),
         state_state=np.zeros(R_, np.int8), is_linearized=np.zeros(R_, np.uint8), is_active=np.zeros(R_, np.uint8),
     ), is_lin
+
+
+# ----------------------------------------------------------------------------- immature points (§8f rank 2)
+PATTERN = np.array([[0, -2], [-1, -1], [1, -1], [-2, 0], [0, 0], [2, 0], [-1, 1], [0, 2]], np.int32)  # GlobalTypes.h:181
+
+
+@dataclasses.dataclass
+class ImmatureSet:
+    """SoA of ImmaturePoint members (Include/ImmaturePoint.h:33-66) for the points of several host keyframes, plus the
+    per-host tables System::traceNewCoarse forms for one new frame (Src/Mapping.cpp:503-517)."""
+    cam: Camera
+    host_idx: np.ndarray
+    u: np.ndarray
+    v: np.ndarray
+    gradH: np.ndarray       # n x 4, Mat22f col-major
+    color: np.ndarray       # n x 8
+    weights: np.ndarray     # n x 8
+    energyTH: np.ndarray
+    idepth_min: np.ndarray
+    idepth_max: np.ndarray
+    quality: np.ndarray
+    status: np.ndarray      # int8 HSLAM_IPS_*
+    lastTraceUV: np.ndarray
+    lastTracePixelInterval: np.ndarray
+    idepth_true: np.ndarray
+    KRKi: np.ndarray = None  # n_hosts x 9
+    Kt: np.ndarray = None    # n_hosts x 3
+    aff: np.ndarray = None   # n_hosts x 2
+
+
+def make_immature_points(kf: Keyframes, hosts, points_per_host=500, seed=7, outlierTHSumComponent=2500.0, outlierTH=144.0):
+    """ImmaturePoint::ImmaturePoint (Src/ImmaturePoint.cpp:8-38) at integer pixels of high gradient."""
+    rng = np.random.default_rng(seed)
+    cam = kf.cam
+    cols = {k: [] for k in ("host_idx", "u", "v", "gradH", "color", "weights", "idt")}
+    for hi, f in enumerate(hosts):
+        pyr, ag = build_pyramid_np(kf.images[f], 1)
+        dI = pyr[0]                                   # h x w x 3
+        ys, xs = np.mgrid[6:cam.h - 6, 6:cam.w - 6]
+        ys, xs = ys.reshape(-1), xs.reshape(-1)
+        good = (ag[0][ys, xs] > 60) & np.isfinite(kf.depths[f][ys, xs])
+        ys, xs = ys[good], xs[good]
+        sel = np.sort(rng.choice(len(xs), size=min(points_per_host, len(xs)), replace=False))
+        for x, y in zip(xs[sel], ys[sel]):
+            px = dI[y + PATTERN[:, 1], x + PATTERN[:, 0]]          # integer positions: the bilinear tap is the pixel itself
+            g = px[:, 1:3].astype(np.float32)
+            G = np.zeros((2, 2), np.float32)
+            for k in range(8):                                     # gradH += g g^T, sequential float sums
+                G = (G + np.outer(g[k], g[k]).astype(np.float32)).astype(np.float32)
+            sq = (g[:, 0] * g[:, 0] + g[:, 1] * g[:, 1]).astype(np.float32)
+            wts = np.sqrt(np.float32(outlierTHSumComponent) / (np.float32(outlierTHSumComponent) + sq)).astype(np.float32)
+            cols["host_idx"].append(hi); cols["u"].append(float(x)); cols["v"].append(float(y))
+            cols["gradH"].append([G[0, 0], G[1, 0], G[0, 1], G[1, 1]]); cols["color"].append(px[:, 0]); cols["weights"].append(wts)
+            cols["idt"].append(1.0 / kf.depths[f][y, x])
+    n = len(cols["u"])
+    return ImmatureSet(cam, np.array(cols["host_idx"], np.int32), np.array(cols["u"], np.float32), np.array(cols["v"], np.float32),
+                       np.array(cols["gradH"], np.float32), np.array(cols["color"], np.float32), np.array(cols["weights"], np.float32),
+                       np.full(n, 8 * outlierTH, np.float32), np.zeros(n, np.float32), np.full(n, np.nan, np.float32),
+                       np.full(n, 10000.0, np.float32), np.full(n, 5, np.int8), np.full((n, 2), -1, np.float32), np.zeros(n, np.float32),
+                       np.array(cols["idt"], np.float64))
+
+
+def trace_tables(kf: Keyframes, hosts, new_frame, ims: ImmatureSet):
+    """Per host: KRKi = K R K^-1, Kt = K t of host->new (float), aff = fromToVecExposure (Mapping.cpp:503-517)."""
+    cam = kf.cam
+    K = np.array([[cam.fx, 0, cam.cx], [0, cam.fy, cam.cy], [0, 0, 1]], np.float64)
+    Ki = np.linalg.inv(K)
+    KRKi, Kt, aff = [], [], []
+    for f in hosts:
+        T = se3_mul(kf.T_true[new_frame], se3_inv(kf.T_true[f]))     # host -> new
+        R, t = T12_split(T)
+        KRKi.append((K @ R @ Ki).astype(np.float32).reshape(-1)); Kt.append((K @ t).astype(np.float32))
+        aff.append(np.array(aff_from_to(1.0, 1.0, kf.aff_true[f][0], kf.aff_true[f][1], kf.aff_true[new_frame][0], kf.aff_true[new_frame][1]), np.float32))
+    ims.KRKi, ims.Kt, ims.aff = np.array(KRKi, np.float32), np.array(Kt, np.float32), np.array(aff, np.float32)
+    return ims

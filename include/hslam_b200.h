@@ -114,7 +114,8 @@ int hslam_host_free(hslam_ctx* ctx, void* p);
 #define HSLAM_K_UNPACK 13
 #define HSLAM_K_BA_ENERGY 14
 #define HSLAM_K_BA_EXPORT 15
-#define HSLAM_K_COUNT 16
+#define HSLAM_K_TRACE 16
+#define HSLAM_K_COUNT 17
 int hslam_profile_enable(hslam_ctx* ctx, int enable);
 int hslam_profile_read(hslam_ctx* ctx, float ms_out[HSLAM_K_COUNT], int count_out[HSLAM_K_COUNT]);
 const char* hslam_kernel_name(int k);
@@ -395,6 +396,43 @@ int hslam_ba_calc_l_energy(hslam_ba* ba, double* energy_out);
  * (EnergyFunctional.cpp:222-274): x is the (8n+4) solution; step_out[P] =
  * efPoint->step.   */
 int hslam_ba_resubstitute(hslam_ba* ba, const double* x_host, float* step_out_host);
+
+/* ---------------------------------------------------------------------------
+ * Immature point tracing
+ * ImmaturePoint::traceOn (Src/ImmaturePoint.cpp:40-351) for every immature point of the window against the newest
+ * frame, as System::traceNewCoarse drives it (Src/Mapping.cpp:494-538): per host keyframe the caller passes
+ * KRKi = K * R(host->frame) * K^-1 (row-major 3x3), Kt = K * t and the affine pair of fromToVecExposure
+ * (Mapping.cpp:509-517), per point the members of ImmaturePoint (Include/ImmaturePoint.h:33-66). */
+#define HSLAM_IPS_GOOD 0           /* enum ImmaturePointStatus, Include/ImmaturePoint.h:24-30 */
+#define HSLAM_IPS_OOB 1
+#define HSLAM_IPS_OUTLIER 2
+#define HSLAM_IPS_SKIPPED 3
+#define HSLAM_IPS_BADCONDITION 4
+#define HSLAM_IPS_UNINITIALIZED 5
+typedef struct hslam_trace_settings {      /* Src/Settings.cpp:68,85-93 */
+  float maxPixSearch, slackInterval, stepsize, minImprovementFactor, GNThreshold, extraSlackOnTH, huberTH;
+  int minTraceTestRadius, GNIterations;
+} hslam_trace_settings;
+void hslam_trace_settings_default(hslam_trace_settings* s);
+typedef struct hslam_immature_soa {        /* HOST pointers; the last six arrays are read AND written */
+  int n_points;
+  const int32_t* host_idx;        /* n  index into the per-host tables */
+  const float* u;                 /* n */
+  const float* v;                 /* n */
+  const float* gradH;             /* n*4 Mat22f col-major */
+  const float* color;             /* n*8 */
+  const float* weights;           /* n*8 */
+  const float* energyTH;          /* n */
+  float* idepth_min;              /* n */
+  float* idepth_max;              /* n  (may be +inf / NaN as in the reference) */
+  float* quality;                 /* n */
+  int8_t* lastTraceStatus;        /* n  HSLAM_IPS_* */
+  float* lastTraceUV;             /* n*2 */
+  float* lastTracePixelInterval;  /* n */
+} hslam_immature_soa;
+int hslam_trace_immature(hslam_ctx* ctx, const hslam_frame* frame, const hslam_trace_settings* settings /*nullable*/,
+                         int n_hosts, const float* KRKi /*n_hosts*9*/, const float* Kt /*n_hosts*3*/,
+                         const float* aff /*n_hosts*2*/, const hslam_immature_soa* pts);
 
 #ifdef __cplusplus
 }

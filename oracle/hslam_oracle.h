@@ -172,6 +172,24 @@ int orc_ba_marginalize_points(orc_ba* ba, const int32_t* point_ids, int count, f
 /* EnergyFunctional::calcLEnergyF_MT (Src/EnergyFunctional.cpp:349-364). */
 int orc_ba_calc_l_energy(orc_ba* ba, double* out);
 
+/* ---- immature point tracing ---- */
+#define ORC_IPS_GOOD 0
+#define ORC_IPS_OOB 1
+#define ORC_IPS_OUTLIER 2
+#define ORC_IPS_SKIPPED 3
+#define ORC_IPS_BADCONDITION 4
+#define ORC_IPS_UNINITIALIZED 5
+typedef struct orc_trace_settings {   /* Src/Settings.cpp:68,85-93 */
+  float maxPixSearch, slackInterval, stepsize, minImprovementFactor, GNThreshold, extraSlackOnTH, huberTH;
+  int minTraceTestRadius, GNIterations;
+} orc_trace_settings;
+/* ImmaturePoint::traceOn (Src/ImmaturePoint.cpp:40-351) for n points against one frame (level-0 Vec3f image). */
+int orc_trace_immature(const float* dI0, int w, int h, const orc_trace_settings* S, int n_hosts, const float* KRKi,
+                       const float* Kt, const float* aff, int n, const int32_t* host_idx, const float* u, const float* v,
+                       const float* gradH, const float* color, const float* weights, const float* energyTH,
+                       float* idepth_min_io, float* idepth_max_io, float* quality_io, int8_t* status_io,
+                       float* lastTraceUV, float* lastTracePixelInterval);
+
 #ifdef __cplusplus
 }
 #endif

@@ -229,6 +229,32 @@ def make_coarse_depth(levels, w, h, su, sv, sid, sw, dI_flat):
     return [tuple(a[: pcn[l]] for a in outs[l]) for l in range(levels)]
 
 
+class TraceSettings(C.Structure):
+    _fields_ = [(k, C.c_float) for k in ("maxPixSearch", "slackInterval", "stepsize", "minImprovementFactor", "GNThreshold",
+                                         "extraSlackOnTH", "huberTH")] + [("minTraceTestRadius", C.c_int), ("GNIterations", C.c_int)]
+
+    @staticmethod
+    def default():   # Src/Settings.cpp:68,85-93
+        return TraceSettings(0.027, 1.5, 1.0, 2.0, 0.1, 1.2, 9.0, 2, 3)
+
+
+def trace_immature(dI0, ims, settings=None):
+    """ImmaturePoint::traceOn over every point of `ims` (synth.ImmatureSet) against the level-0 Vec3f image dI0;
+    the in/out members of `ims` are updated in place."""
+    L = lib()
+    S = settings or TraceSettings.default()
+    h, w = dI0.shape[:2]
+    a = lambda x, dt: np.ascontiguousarray(x, dt)
+    K, T, A = a(ims.KRKi, np.float32), a(ims.Kt, np.float32), a(ims.aff, np.float32)
+    rc = L.orc_trace_immature(_ptr(a(dI0, np.float32)), w, h, C.byref(S), len(K), _ptr(K), _ptr(T), _ptr(A), len(ims.u),
+                              _ptr(a(ims.host_idx, np.int32)), _ptr(a(ims.u, np.float32)), _ptr(a(ims.v, np.float32)),
+                              _ptr(a(ims.gradH, np.float32)), _ptr(a(ims.color, np.float32)), _ptr(a(ims.weights, np.float32)),
+                              _ptr(a(ims.energyTH, np.float32)), _ptr(ims.idepth_min), _ptr(ims.idepth_max), _ptr(ims.quality),
+                              _ptr(ims.status), _ptr(ims.lastTraceUV), _ptr(ims.lastTracePixelInterval))
+    assert rc == 0
+    return ims
+
+
 # ------------------------------------------------------------------ window BA
 def prepare_window(cam, T_eval, state, state_zero, exposure, params=None):
     n = len(T_eval)
