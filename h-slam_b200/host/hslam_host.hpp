@@ -362,6 +362,21 @@ class EnergyFunctional {
     HdiF.resize(nPoints); bdSumF.resize(nPoints); idepth_hessian.resize(nPoints);
     check(hslam_ba_point_results(ba_, HdiF.data(), bdSumF.data(), idepth_hessian.data(), nullptr, nullptr, nullptr, nullptr, nullptr, nullptr));
   }
+  // void EnergyFunctional::marginalizePointsF()   (EnergyFunctional.cpp:545-609): the accumulate + stitch part for
+  // the points whose stateFlag is toMarg; the caller keeps H = M - Msc, b = Mb - Mbsc, HM += ..., bM += ...
+  void marginalizePointsF(const std::vector<int32_t>& pointsToMarg, float idepthFixPriorMargFac, MatXX& M, VecX& Mb, MatXX& Msc,
+                          VecX& Mbsc, int& resInM_increment) {
+    const int N = 8 * nFrames + 4;
+    M.resize(N, N); Msc.resize(N, N); Mb.assign(N, 0.0); Mbsc.assign(N, 0.0);
+    check(hslam_ba_marginalize_points(ba_, pointsToMarg.data(), (int)pointsToMarg.size(), idepthFixPriorMargFac, M.v.data(),
+                                      Mb.data(), Msc.v.data(), Mbsc.data(), &resInM_increment));
+  }
+  // double EnergyFunctional::calcLEnergyF_MT()   (EnergyFunctional.cpp:349-364)
+  double calcLEnergyF_MT() {
+    double e = 0;
+    check(hslam_ba_calc_l_energy(ba_, &e));
+    return e;
+  }
   hslam_ba* get() const { return ba_; }
 
  private:
@@ -414,5 +429,13 @@ class EnergyFunctional {
   hslam_ba* ba_ = nullptr;
   hslam_params prm_;
 };
+
+// void System::traceNewCoarse(std::shared_ptr<FrameShell> fh)   (Src/Mapping.cpp:494-538): ImmaturePoint::traceOn for every
+// immature point of every keyframe against the new frame.  `pts` holds the ImmaturePoint members as SoA; the per-host
+// tables are K*R*K^-1, K*t and fromToVecExposure(host, fh) exactly as traceNewCoarse forms them.
+inline void traceNewCoarse(Context& ctx, const Frame& fh, int n_hosts, const float* KRKi, const float* Kt, const float* aff,
+                           const hslam_immature_soa& pts) {
+  check(hslam_trace_immature(ctx.get(), fh.get(), nullptr, n_hosts, KRKi, Kt, aff, &pts));
+}
 
 }  // namespace hslam_b200
