@@ -126,7 +126,7 @@ class Context:
 
     def profile_read(self):
         """{kernel class: (summed ms, launches)} measured with CUDA events on the context stream."""
-        K = 17
+        K = 18
         ms = np.zeros(K, np.float32); cnt = np.zeros(K, np.int32)
         _chk(self.L.hslam_profile_read(self.h, _ptr(ms), _ptr(cnt)))
         self.L.hslam_kernel_name.restype = C.c_char_p
@@ -196,6 +196,20 @@ class CoarseTracker:
             a = [np.ascontiguousarray(x, np.float32) for x in (u, v, idp, col)]
             _chk(self.L.hslam_tracker_set_ref(self.h, l, _ptr(a[0]), _ptr(a[1]), _ptr(a[2]), _ptr(a[3]), len(a[0])))
         _chk(self.L.hslam_tracker_set_ref_aff(self.h, C.c_float(ref_exposure), C.c_double(ref_aff[0]), C.c_double(ref_aff[1])))
+
+    def makeCoarseDepthL0(self, lastRef: Frame, centerProjectedTo, HdiF, ref_exposure=1.0, ref_aff=(0.0, 0.0)):
+        """CoarseTracker::makeCoarseDepthL0 on the device from per-point (centerProjectedTo[3], HdiF)."""
+        c = np.ascontiguousarray(centerProjectedTo, np.float32).reshape(-1, 3)
+        hd = np.ascontiguousarray(HdiF, np.float32)
+        _chk(self.L.hslam_tracker_make_coarse_depth(self.h, lastRef.h, C.c_int(len(hd)), _ptr(c), _ptr(hd)))
+        _chk(self.L.hslam_tracker_set_ref_aff(self.h, C.c_float(ref_exposure), C.c_double(ref_aff[0]), C.c_double(ref_aff[1])))
+
+    def get_ref(self, lvl):
+        n = C.c_int(0)
+        _chk(self.L.hslam_tracker_get_ref(self.h, lvl, 0, None, None, None, None, C.byref(n)))
+        a = [np.zeros(n.value, np.float32) for _ in range(4)]
+        _chk(self.L.hslam_tracker_get_ref(self.h, lvl, n.value, _ptr(a[0]), _ptr(a[1]), _ptr(a[2]), _ptr(a[3]), C.byref(n)))
+        return tuple(a)
 
     def calcRes(self, lvl, frame: Frame, T, aff, cutoffTH, new_exposure=1.0):
         out6 = np.zeros(6)

@@ -118,7 +118,7 @@ int hslam_host_free(hslam_ctx* c, void* p) {
 
 static const char* k_names[HSLAM_K_COUNT] = {"pyramid_level", "trk_eval", "trk_track", "ba_linearize", "ba_apply",
                                              "ba_top", "ba_fold_top", "ba_point_sum", "ba_schur", "ba_fold_sc",
-                                             "ba_stitch", "ba_resub", "ba_fixlin", "unpack_level", "ba_energy", "ba_layout", "trace"};
+                                             "ba_stitch", "ba_resub", "ba_fixlin", "unpack_level", "ba_energy", "ba_layout", "trace", "coarse_depth"};
 const char* hslam_kernel_name(int k) { return (k >= 0 && k < HSLAM_K_COUNT) ? k_names[k] : ""; }
 
 int hslam_profile_enable(hslam_ctx* c, int enable) {

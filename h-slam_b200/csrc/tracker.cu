@@ -19,6 +19,7 @@
 #include <cooperative_groups.h>
 #include <cmath>
 #include <cstring>
+#include <algorithm>
 
 namespace cg = cooperative_groups;
 
@@ -642,6 +643,8 @@ struct hslam_tracker {
   float4* h_pack = nullptr;         // pinned staging for set_ref
   size_t h_pack_cap = 0;
   int coop_blocks = 0;
+  char* cd_buf = nullptr;           // makeCoarseDepthL0 working set (seeds, pixel lists, maps, scan)
+  size_t cd_cap = 0;
 };
 
 static int ensure_partials(hslam_tracker* t, int blocks) {
@@ -687,6 +690,7 @@ int hslam_tracker_destroy(hslam_tracker* t) {
   cudaFree(t->ticket); cudaFree(t->d_result); cudaFreeHost(t->h_result);
   cudaFree(t->d_io); cudaFreeHost(t->h_io);
   if (t->h_pack) cudaFreeHost(t->h_pack);
+  if (t->cd_buf) cudaFree(t->cd_buf);
   delete t;
   return 0;
 }
@@ -891,6 +895,265 @@ int hslam_tracker_track(hslam_tracker* t, const hslam_frame* f, float new_exposu
   int rc = hslam_tracker_track_enqueue(t, f, new_exposure, T_io, aff_io, coarsestLvl, minResForAbort);
   if (rc) return rc;
   return hslam_tracker_track_finish(t, T_io, aff_io, lastResiduals, lastFlow, ok, iterations_out);
+}
+
+}  // extern "C"
+
+// ================================================================================================
+// CoarseTracker::makeCoarseDepthL0 on the device (reference Src/CoarseTracker.cpp:105-263):
+// splat the active points that are IN the newest keyframe, sum-pyramid, one dilation per level, normalise and
+// compact into the per-level reference clouds pc_* — which the tracker reads from HBM anyway, so the per-keyframe
+// host round trip (point side effects down, five pc arrays up) disappears.
+//   * splat: the source accumulates `idepth += new_idepth*weight` in point order; two points in one pixel are rare
+//     but must add in that order.  Points are linked per pixel with atomicExch, the pixel's list head then adds
+//     its list in ascending point index: deterministic and bit-identical to the sequential loop, no sort.
+//   * compaction keeps the source's raster order with a three-kernel ordered scan (block counts, scan of the
+//     counts, ballot-ranked emit).
+// ================================================================================================
+namespace hs {
+
+struct CdSeed { int u, v; float idepth, weight; };
+
+__global__ void cd_link_kernel(const CdSeed* __restrict__ seeds, int n, int w, int h, int* __restrict__ head, int* __restrict__ next) {
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const CdSeed s = seeds[i];
+  next[i] = -2;                                            // not part of any list
+  if (s.u < 0 || s.v < 0 || s.u >= w || s.v >= h) return;
+  next[i] = atomicExch(&head[s.u + w * s.v], i);
+}
+__global__ void cd_splat_kernel(const CdSeed* __restrict__ seeds, int n, int w, const int* __restrict__ head,
+                                const int* __restrict__ next, float* __restrict__ idepth, float* __restrict__ wsum) {
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n || next[i] == -2) return;
+  const int pix = seeds[i].u + w * seeds[i].v;
+  if (head[pix] != i) return;                              // one owner per pixel
+  float accI = 0.f, accW = 0.f;
+  int last = -1;
+  while (true) {                                           // ascending point index = the source's loop order
+    int best = 0x7fffffff;
+    for (int j = i; j >= 0; j = next[j]) if (j > last && j < best) best = j;
+    if (best == 0x7fffffff) break;
+    accI = xadd(accI, xmul(seeds[best].idepth, seeds[best].weight));
+    accW = xadd(accW, seeds[best].weight);
+    last = best;
+  }
+  idepth[pix] = accI; wsum[pix] = accW;
+}
+__global__ void cd_down_kernel(const float* __restrict__ idm, const float* __restrict__ wsm, int wlm1, float* __restrict__ idl,
+                               float* __restrict__ wsl, int wl, int hl) {
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= wl * hl) return;
+  const int x = i % wl, y = i / wl, b = 2 * x + 2 * y * wlm1;
+  idl[i] = xadd(xadd(xadd(idm[b], idm[b + 1]), idm[b + wlm1]), idm[b + wlm1 + 1]);
+  wsl[i] = xadd(xadd(xadd(wsm[b], wsm[b + 1]), wsm[b + wlm1]), wsm[b + wlm1 + 1]);
+}
+// one dilation: pixels without weight take the mean of their weighted neighbours (diagonal on levels 0-1, 4-neighbourhood
+// above); reads only pixels WITH weight, writes only pixels WITHOUT: order-free.  `wbak` is the copy of the weights.
+__global__ void cd_dilate_kernel(float* __restrict__ idl, float* __restrict__ wsl, const float* __restrict__ wbak, int wl, int hl,
+                                 int diagonal) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x + wl;
+  const int tot = wl * hl, wh = tot - wl;
+  if (i >= wh || wbak[i] > 0.f) return;
+  const int o0 = diagonal ? 1 + wl : 1, o1 = diagonal ? -1 - wl : -1, o2 = diagonal ? wl - 1 : wl, o3 = diagonal ? -wl + 1 : -wl;
+  float sum = 0.f, num = 0.f, numn = 0.f;
+  const int offs[4] = {o0, o1, o2, o3};
+#pragma unroll
+  for (int k = 0; k < 4; ++k) {
+    const int j = i + offs[k];
+    if (j < tot && wbak[j] > 0.f) { sum = xadd(sum, idl[j]); num = xadd(num, wbak[j]); numn += 1.f; }   // j == tot: the source reads one past the end
+  }
+  if (numn > 0.f) { idl[i] = xdiv(sum, numn); wsl[i] = xdiv(num, numn); }
+}
+__device__ __forceinline__ bool cd_valid(const float* idl, const float* wsl, const float4* dI, int wl, int hl, int i, float4& out) {
+  if (i >= wl * hl) return false;
+  const int x = i % wl, y = i / wl;
+  if (x < 2 || y < 2 || x >= wl - 2 || y >= hl - 2) return false;
+  const float ws = wsl[i];
+  if (!(ws > 0.f)) return false;
+  const float idp = xdiv(idl[i], ws), col = dI[i].x;
+  if (!isfinite(col) || !(idp > 0.f)) return false;
+  out = make_float4((float)x, (float)y, idp, col);
+  return true;
+}
+constexpr int CD_BLOCK = 1024;
+__global__ void __launch_bounds__(CD_BLOCK) cd_count_kernel(const float* idl, const float* wsl, const float4* dI, int wl, int hl, int* blockcnt) {
+  float4 o;
+  const bool v = cd_valid(idl, wsl, dI, wl, hl, blockIdx.x * CD_BLOCK + threadIdx.x, o);
+  const int c = __syncthreads_count(v);
+  if (threadIdx.x == 0) blockcnt[blockIdx.x] = c;
+}
+__global__ void __launch_bounds__(1024) cd_scan_kernel(int* blockcnt, int nblocks, int* total_out) {   // one block, exclusive scan in place
+  __shared__ int carry, wsum[32];
+  if (threadIdx.x == 0) carry = 0;
+  __syncthreads();
+  for (int base = 0; base < nblocks; base += 1024) {
+    const int i = base + threadIdx.x;
+    const int v = i < nblocks ? blockcnt[i] : 0;
+    int incl = v;
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) { int t = __shfl_up_sync(0xffffffffu, incl, o); if (lane >= o) incl += t; }
+    if (lane == 31) wsum[wid] = incl;
+    __syncthreads();
+    if (wid == 0) {
+      int s = wsum[lane], is = s;
+#pragma unroll
+      for (int o = 1; o < 32; o <<= 1) { int t = __shfl_up_sync(0xffffffffu, is, o); if (lane >= o) is += t; }
+      wsum[lane] = is - s;                                  // exclusive per warp
+    }
+    __syncthreads();
+    const int excl = carry + wsum[wid] + incl - v;
+    if (i < nblocks) blockcnt[i] = excl;
+    __syncthreads();
+    if (threadIdx.x == 1023) carry = excl + v;
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) *total_out = carry;
+}
+__global__ void __launch_bounds__(CD_BLOCK) cd_emit_kernel(const float* idl, const float* wsl, const float4* dI, int wl, int hl,
+                                                            const int* __restrict__ blockoff, float4* __restrict__ pc) {
+  __shared__ int woff[CD_BLOCK / 32];
+  float4 o;
+  const bool v = cd_valid(idl, wsl, dI, wl, hl, blockIdx.x * CD_BLOCK + threadIdx.x, o);
+  const unsigned m = __ballot_sync(0xffffffffu, v);
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+  if (lane == 0) woff[wid] = __popc(m);
+  __syncthreads();
+  if (wid == 0) {
+    int s = woff[lane], is = s;
+#pragma unroll
+    for (int k = 1; k < 32; k <<= 1) { int t = __shfl_up_sync(0xffffffffu, is, k); if (lane >= k) is += t; }
+    woff[lane] = is - s;
+  }
+  __syncthreads();
+  if (v) pc[blockoff[blockIdx.x] + woff[wid] + __popc(m & ((1u << lane) - 1u))] = o;
+}
+// seeds from host arrays: int u = cpt[0] + 0.5f, weight = sqrtf(1e-3 / (HdiF + 1e-12))   (CoarseTracker.cpp:120-123)
+__global__ void cd_seed_kernel(const float* __restrict__ cpt3, const float* __restrict__ hdif, int n, CdSeed* __restrict__ seeds) {
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  CdSeed s;
+  s.u = (int)xadd(cpt3[3 * i], 0.5f); s.v = (int)xadd(cpt3[3 * i + 1], 0.5f);
+  s.idepth = cpt3[3 * i + 2];
+  s.weight = xsqrt((float)(1e-3 / ((double)hdif[i] + 1e-12)));
+  seeds[i] = s;
+}
+
+}  // namespace hs
+
+static int cd_run(hslam_tracker* t, const hslam_frame* ref, const hs::CdSeed* d_seeds, int n, int* d_head, int* d_next, float* d_maps,
+                  int* d_blockcnt, int* d_total) {
+  using namespace hs;
+  hslam_ctx* ctx = t->ctx;
+  cudaStream_t st = ctx->stream;
+  const int levels = t->levels;
+  // maps: per level idepth | wsum, then one wbak of level-0 size
+  std::vector<float*> idp(levels), wsm(levels);
+  size_t off = 0;
+  for (int l = 0; l < levels; ++l) { size_t px = (size_t)t->L[l].w * t->L[l].h; idp[l] = d_maps + off; wsm[l] = d_maps + off + px; off += 2 * px; }
+  float* wbak = d_maps + off;
+  const int w0 = t->L[0].w, h0 = t->L[0].h;
+  HS_CUDA(cudaMemsetAsync(d_maps, 0, off * sizeof(float), st));
+  HS_CUDA(cudaMemsetAsync(d_head, 0xff, (size_t)w0 * h0 * sizeof(int), st));
+  if (n > 0) {
+    HS_LAUNCH(ctx, HSLAM_K_COARSE_DEPTH, (cd_link_kernel<<<(n + 255) / 256, 256, 0, st>>>(d_seeds, n, w0, h0, d_head, d_next)));
+    HS_LAUNCH(ctx, HSLAM_K_COARSE_DEPTH, (cd_splat_kernel<<<(n + 255) / 256, 256, 0, st>>>(d_seeds, n, w0, d_head, d_next, idp[0], wsm[0])));
+  }
+  for (int l = 1; l < levels; ++l) {
+    const int wl = t->L[l].w, hl = t->L[l].h;
+    HS_LAUNCH(ctx, HSLAM_K_COARSE_DEPTH, (cd_down_kernel<<<(wl * hl + 255) / 256, 256, 0, st>>>(idp[l - 1], wsm[l - 1], t->L[l - 1].w, idp[l], wsm[l], wl, hl)));
+  }
+  for (int l = 0; l < levels; ++l) {
+    const int wl = t->L[l].w, hl = t->L[l].h;
+    HS_CUDA(cudaMemcpyAsync(wbak, wsm[l], (size_t)wl * hl * sizeof(float), cudaMemcpyDeviceToDevice, st));
+    HS_LAUNCH(ctx, HSLAM_K_COARSE_DEPTH, (cd_dilate_kernel<<<(wl * hl + 255) / 256, 256, 0, st>>>(idp[l], wsm[l], wbak, wl, hl, l < 2 ? 1 : 0)));
+  }
+  for (int l = 0; l < levels; ++l) {
+    const int wl = t->L[l].w, hl = t->L[l].h, nb = (wl * hl + CD_BLOCK - 1) / CD_BLOCK;
+    if (wl * hl > t->pc_cap[l]) {
+      HS_CUDA(cudaStreamSynchronize(st));
+      cudaFree(t->pc[l]);
+      HS_CUDA(cudaMalloc(&t->pc[l], (size_t)wl * hl * sizeof(float4)));
+      t->pc_cap[l] = wl * hl;
+    }
+    HS_LAUNCH(ctx, HSLAM_K_COARSE_DEPTH, (cd_count_kernel<<<nb, CD_BLOCK, 0, st>>>(idp[l], wsm[l], ref->dI[l], wl, hl, d_blockcnt)));
+    HS_LAUNCH(ctx, HSLAM_K_COARSE_DEPTH, (cd_scan_kernel<<<1, 1024, 0, st>>>(d_blockcnt, nb, d_total + l)));
+    HS_LAUNCH(ctx, HSLAM_K_COARSE_DEPTH, (cd_emit_kernel<<<nb, CD_BLOCK, 0, st>>>(idp[l], wsm[l], ref->dI[l], wl, hl, d_blockcnt, t->pc[l])));
+  }
+  HS_CUDA(cudaGetLastError());
+  int counts[HSLAM_MAX_PYR_LEVELS];
+  HS_CUDA(cudaMemcpyAsync(counts, d_total, levels * sizeof(int), cudaMemcpyDeviceToHost, st));
+  HS_CUDA(cudaStreamSynchronize(st));
+  for (int l = 0; l < levels; ++l) { t->L[l].n = counts[l]; t->L[l].pc = t->pc[l]; }
+  return 0;
+}
+
+static int cd_buffers(hslam_tracker* t, int n, hs::CdSeed** seeds, int** head, int** next, float** maps, int** blockcnt, int** total,
+                      float** in4) {
+  // one allocation, grown on demand: seeds | next | in (4 floats per point) | head | maps | blockcnt | totals
+  size_t px = 0, px0 = (size_t)t->L[0].w * t->L[0].h;
+  for (int l = 0; l < t->levels; ++l) px += (size_t)t->L[l].w * t->L[l].h;
+  auto al = [](size_t x) { return (x + 255) & ~(size_t)255; };
+  const size_t cap_n = (size_t)std::max(n, 1);
+  const size_t b_seed = al(cap_n * sizeof(hs::CdSeed)), b_next = al(cap_n * 4), b_in = al(cap_n * 16), b_head = al(px0 * 4),
+               b_maps = al((2 * px + px0) * 4), b_cnt = al((px0 / hs::CD_BLOCK + 2) * 4), b_tot = 256;
+  const size_t total_b = b_seed + b_next + b_in + b_head + b_maps + b_cnt + b_tot;
+  if (total_b > t->cd_cap) {
+    HS_CUDA(cudaStreamSynchronize(t->ctx->stream));
+    if (t->cd_buf) cudaFree(t->cd_buf);
+    t->cd_buf = nullptr; t->cd_cap = 0;
+    HS_CUDA(cudaMalloc((void**)&t->cd_buf, total_b + total_b / 4));
+    t->cd_cap = total_b + total_b / 4;
+  }
+  char* p = t->cd_buf;
+  *seeds = (hs::CdSeed*)p; p += b_seed; *next = (int*)p; p += b_next; *in4 = (float*)p; p += b_in; *head = (int*)p; p += b_head;
+  *maps = (float*)p; p += b_maps; *blockcnt = (int*)p; p += b_cnt; *total = (int*)p;
+  return 0;
+}
+
+extern "C" {
+
+int hslam_tracker_make_coarse_depth(hslam_tracker* t, const hslam_frame* lastRef, int n, const float* centerProjectedTo,
+                                    const float* HdiF) {
+  HS_ARG(t && lastRef && t->levels > 0 && n >= 0 && (n == 0 || (centerProjectedTo && HdiF)), "hslam_tracker_make_coarse_depth: bad argument");
+  HS_ARG(lastRef->ctx == t->ctx && lastRef->levels >= t->levels && lastRef->w == t->L[0].w && lastRef->h == t->L[0].h,
+         "hslam_tracker_make_coarse_depth: reference frame does not match the tracker (context, size or levels)");
+  hslam_ctx* ctx = t->ctx;
+  HS_CUDA(cudaSetDevice(ctx->device));
+  hs::CdSeed* seeds; int *head, *next, *blockcnt, *total; float *maps, *in4;
+  int rc = cd_buffers(t, n, &seeds, &head, &next, &maps, &blockcnt, &total, &in4);
+  if (rc) return rc;
+  if (n > 0) {
+    if ((size_t)n > t->h_pack_cap) {
+      HS_CUDA(cudaStreamSynchronize(ctx->stream));
+      if (t->h_pack) cudaFreeHost(t->h_pack);
+      t->h_pack_cap = (size_t)n + n / 4 + 256;
+      HS_CUDA(cudaMallocHost(&t->h_pack, t->h_pack_cap * sizeof(float4)));
+    } else {
+      HS_CUDA(cudaStreamSynchronize(ctx->stream));
+    }
+    float* hp = (float*)t->h_pack;
+    memcpy(hp, centerProjectedTo, (size_t)n * 12);
+    memcpy(hp + 3 * (size_t)n, HdiF, (size_t)n * 4);
+    HS_CUDA(cudaMemcpyAsync(in4, hp, (size_t)n * 16, cudaMemcpyHostToDevice, ctx->stream));
+    HS_LAUNCH(ctx, HSLAM_K_COARSE_DEPTH, (hs::cd_seed_kernel<<<(n + 255) / 256, 256, 0, ctx->stream>>>(in4, in4 + 3 * (size_t)n, n, seeds)));
+  }
+  return cd_run(t, lastRef, seeds, n, head, next, maps, blockcnt, total);
+}
+
+int hslam_tracker_get_ref(hslam_tracker* t, int lvl, int capacity, float* u, float* v, float* idepth, float* color, int* n_out) {
+  HS_ARG(t && lvl >= 0 && lvl < t->levels && n_out, "hslam_tracker_get_ref: bad argument");
+  HS_CUDA(cudaSetDevice(t->ctx->device));
+  const int n = t->L[lvl].n;
+  *n_out = n;
+  if (n == 0 || !u) return 0;
+  HS_ARG(capacity >= n && v && idepth && color, "hslam_tracker_get_ref: output arrays too small");
+  std::vector<float4> tmp(n);
+  HS_CUDA(cudaMemcpyAsync(tmp.data(), t->pc[lvl], (size_t)n * sizeof(float4), cudaMemcpyDeviceToHost, t->ctx->stream));
+  HS_CUDA(cudaStreamSynchronize(t->ctx->stream));
+  for (int i = 0; i < n; ++i) { u[i] = tmp[i].x; v[i] = tmp[i].y; idepth[i] = tmp[i].z; color[i] = tmp[i].w; }
+  return 0;
 }
 
 }  // extern "C"

@@ -115,7 +115,8 @@ int hslam_host_free(hslam_ctx* ctx, void* p);
 #define HSLAM_K_BA_ENERGY 14
 #define HSLAM_K_BA_EXPORT 15
 #define HSLAM_K_TRACE 16
-#define HSLAM_K_COUNT 17
+#define HSLAM_K_COARSE_DEPTH 17
+#define HSLAM_K_COUNT 18
 int hslam_profile_enable(hslam_ctx* ctx, int enable);
 int hslam_profile_read(hslam_ctx* ctx, float ms_out[HSLAM_K_COUNT], int count_out[HSLAM_K_COUNT]);
 const char* hslam_kernel_name(int k);
@@ -159,6 +160,15 @@ int hslam_tracker_set_ref(hslam_tracker* trk, int lvl, const float* u, const flo
                           const float* idepth, const float* color, int n);
 /* lastRef->ab_exposure and lastRef_aff_g2l (Src/CoarseTracker.cpp:496-500). */
 int hslam_tracker_set_ref_aff(hslam_tracker* trk, float ref_exposure, double ref_aff_a, double ref_aff_b);
+/* CoarseTracker::makeCoarseDepthL0 on the device (Src/CoarseTracker.cpp:105-263): builds the
+ * per-level reference clouds pc_* of this tracker from the active points that are IN the newest keyframe `lastRef`.
+ * Per contributing point (host arrays): centerProjectedTo (3 floats: u, v, new_idepth of its residual into lastRef,
+ * CoarseTracker.cpp:119-121) and efPoint->HdiF (weight = sqrtf(1e-3/(HdiF+1e-12)), :122).  Replaces the host loop +
+ * hslam_tracker_set_ref for every level; call hslam_tracker_set_ref_aff as before. */
+int hslam_tracker_make_coarse_depth(hslam_tracker* trk, const hslam_frame* lastRef, int n_points,
+                                    const float* centerProjectedTo /*n*3*/, const float* HdiF /*n*/);
+/* The reference cloud of a level as the tracker holds it (pc_u, pc_v, pc_idepth, pc_color, pc_n). */
+int hslam_tracker_get_ref(hslam_tracker* trk, int lvl, int capacity, float* u, float* v, float* idepth, float* color, int* n_out);
 
 /* CoarseTracker::calcRes (Src/CoarseTracker.cpp:329-485).
  * out6 = {E, numTermsInE, sumSqShiftT/(n+0.1), 0, sumSqShiftRT/(n+0.1), numSaturated/numTermsInE}.

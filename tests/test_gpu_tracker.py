@@ -171,3 +171,40 @@ def test_empty_reference_cloud(ctx, capi, O, tracking_pair_small):
     out6, nw = trk.calcRes(0, frame, T_ID, (0.0, 0.0), 20.0)
     assert out6[0] == 0 and out6[1] == 0 and nw == 0 and np.isnan(out6[5])   # 0/0 as in the reference
     trk.close(); frame.close()
+
+
+def test_make_coarse_depth_on_device_bit_exact(ctx, capi, O, synth):
+    """CoarseTracker::makeCoarseDepthL0 on the device (splat with pixel collisions, sum pyramid, dilation, ordered
+    compaction) == the oracle's restatement, per level and in the reference's raster order; tracking with the
+    device-built cloud == tracking with the uploaded one."""
+    tp = synth.make_tracking_pair(w=320, h=240, levels=4, n_seed_points=1500, seed=7)
+    w, h, levels = tp.cam.w, tp.cam.h, tp.levels
+    rng = np.random.default_rng(11)
+    n = 3000
+    cx = rng.uniform(3, w - 4, n).astype(np.float32); cy = rng.uniform(3, h - 4, n).astype(np.float32)
+    cx[100:160] = cx[40:100]; cy[100:160] = cy[40:100]            # 60 pixels hit twice, 20 of them three times
+    cx[160:180] = cx[40:60]; cy[160:180] = cy[40:60]
+    idp = rng.uniform(0.1, 1.5, n).astype(np.float32)
+    hdi = rng.uniform(1e-4, 1e-1, n).astype(np.float32)
+    cpt = np.stack([cx, cy, idp], 1)
+    su = (cx + np.float32(0.5)).astype(np.int32); sv = (cy + np.float32(0.5)).astype(np.int32)
+    sw = np.sqrt((1e-3 / (hdi.astype(np.float64) + 1e-12)).astype(np.float32)).astype(np.float32)
+    lv, _, dI_flat = O.pyramid(tp.img_ref, levels)
+    ref = O.make_coarse_depth(levels, w, h, su, sv, idp, sw, dI_flat)
+    trk = capi.CoarseTracker(ctx, w, h)
+    trk.makeK(tp.cam, levels)
+    fr_ref = capi.Frame(ctx, tp.img_ref, levels)
+    trk.makeCoarseDepthL0(fr_ref, cpt, hdi)
+    for l in range(levels):
+        got = trk.get_ref(l)
+        assert len(got[0]) == len(ref[l][0]) > 0, (l, len(got[0]), len(ref[l][0]))
+        for a, b in zip(got, ref[l]):
+            assert np.array_equal(a, b), l
+    # the tracker runs on the cloud it built
+    fr_new = capi.Frame(ctx, tp.img_new, levels)
+    ok1, T1, aff1 = trk.trackNewestCoarse(fr_new, T_ID, (0.0, 0.0), levels - 1)
+    trk2 = capi.CoarseTracker(ctx, w, h); trk2.makeK(tp.cam, levels); trk2.setCoarseTrackingRef(ref)
+    ok2, T2, aff2 = trk2.trackNewestCoarse(fr_new, T_ID, (0.0, 0.0), levels - 1)
+    assert ok1 == ok2 and np.array_equal(T1, T2) and np.array_equal(aff1, aff2)
+    for o in (trk, trk2, fr_ref, fr_new):
+        o.close()
