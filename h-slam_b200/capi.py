@@ -204,6 +204,11 @@ class CoarseTracker:
         _chk(self.L.hslam_tracker_make_coarse_depth(self.h, lastRef.h, C.c_int(len(hd)), _ptr(c), _ptr(hd)))
         _chk(self.L.hslam_tracker_set_ref_aff(self.h, C.c_float(ref_exposure), C.c_double(ref_aff[0]), C.c_double(ref_aff[1])))
 
+    def makeCoarseDepthL0_from_ba(self, lastRef: Frame, ef, residual_ids, ref_exposure=1.0, ref_aff=(0.0, 0.0)):
+        ids = np.ascontiguousarray(residual_ids, np.int32)
+        _chk(self.L.hslam_tracker_make_coarse_depth_from_ba(self.h, lastRef.h, ef.h, _ptr(ids), C.c_int(len(ids))))
+        _chk(self.L.hslam_tracker_set_ref_aff(self.h, C.c_float(ref_exposure), C.c_double(ref_aff[0]), C.c_double(ref_aff[1])))
+
     def get_ref(self, lvl):
         n = C.c_int(0)
         _chk(self.L.hslam_tracker_get_ref(self.h, lvl, 0, None, None, None, None, C.byref(n)))

@@ -970,6 +970,38 @@ int hslam_ba_resubstitute(hslam_ba* ba, const double* x, float* step_out) {
 
 }  // extern "C"
 
+// ---------------------------------------------------------------- device-resident inputs of makeCoarseDepthL0
+// For the listed residuals (caller ids; the residual of each contributing point into the newest keyframe) gather
+// centerProjectedTo (3 floats) and the HdiF of the residual's point into device arrays: the tracker builds its reference
+// clouds from them without a host round trip (tracker.cu, hslam_tracker_make_coarse_depth_from_ba).
+namespace hs {
+__global__ void ba_gather_coarse_kernel(BARes r, BAPts pts, const int* __restrict__ sorted_ids, int count, float* __restrict__ cpt3,
+                                        float* __restrict__ hdif) {
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= count) return;
+  const int k = sorted_ids[i];
+  cpt3[3 * i] = r.cpt[k]; cpt3[3 * i + 1] = r.cpt[r.rs + k]; cpt3[3 * i + 2] = r.cpt[2 * r.rs + k];
+  hdif[i] = pts.HdiF[r.point[k]];
+}
+}  // namespace hs
+int hs_ba_gather_coarse_inputs(hslam_ba* ba, hslam_ctx* ctx, const int32_t* residual_ids, int count, float* d_cpt3, float* d_hdif) {
+  HS_ARG(ba && ba->have_topology && ba->ctx == ctx, "make_coarse_depth_from_ba: window handle missing or from another context");
+  if (count == 0) return 0;
+  void* s;
+  TRY(ba->d_ids.ensure(count));
+  TRY(arena_alloc(ba, (size_t)count * sizeof(int), &s));
+  int* sorted = (int*)s;
+  for (int i = 0; i < count; ++i) {
+    HS_ARG(residual_ids[i] >= 0 && residual_ids[i] < ba->R, "make_coarse_depth_from_ba: residual id out of range");
+    sorted[i] = ba->r_orig2sorted[residual_ids[i]];
+  }
+  HS_CUDA(cudaMemcpyAsync(ba->d_ids.p, sorted, (size_t)count * sizeof(int), cudaMemcpyHostToDevice, ctx->stream));
+  HS_LAUNCH(ctx, HSLAM_K_COARSE_DEPTH, (hs::ba_gather_coarse_kernel<<<(count + 255) / 256, 256, 0, ctx->stream>>>(
+                                           ba->hdesc.r, ba->hdesc.p, ba->d_ids.p, count, d_cpt3, d_hdif)));
+  HS_CUDA(cudaGetLastError());
+  return 0;
+}
+
 // ---------------------------------------------------------------- batches of independent windows
 struct hslam_ba_batch {
   hslam_ctx* ctx = nullptr;

@@ -1042,6 +1042,8 @@ __global__ void cd_seed_kernel(const float* __restrict__ cpt3, const float* __re
 
 }  // namespace hs
 
+int hs_ba_gather_coarse_inputs(hslam_ba* ba, hslam_ctx* ctx, const int32_t* residual_ids, int count, float* d_cpt3, float* d_hdif);   // ba.cu
+
 static int cd_run(hslam_tracker* t, const hslam_frame* ref, const hs::CdSeed* d_seeds, int n, int* d_head, int* d_next, float* d_maps,
                   int* d_blockcnt, int* d_total) {
   using namespace hs;
@@ -1140,6 +1142,24 @@ int hslam_tracker_make_coarse_depth(hslam_tracker* t, const hslam_frame* lastRef
     HS_LAUNCH(ctx, HSLAM_K_COARSE_DEPTH, (hs::cd_seed_kernel<<<(n + 255) / 256, 256, 0, ctx->stream>>>(in4, in4 + 3 * (size_t)n, n, seeds)));
   }
   return cd_run(t, lastRef, seeds, n, head, next, maps, blockcnt, total);
+}
+
+int hslam_tracker_make_coarse_depth_from_ba(hslam_tracker* t, const hslam_frame* lastRef, hslam_ba* ba, const int32_t* residual_ids,
+                                            int count) {
+  HS_ARG(t && lastRef && ba && t->levels > 0 && count >= 0 && (count == 0 || residual_ids), "hslam_tracker_make_coarse_depth_from_ba: bad argument");
+  HS_ARG(lastRef->ctx == t->ctx && lastRef->levels >= t->levels && lastRef->w == t->L[0].w && lastRef->h == t->L[0].h,
+         "hslam_tracker_make_coarse_depth_from_ba: reference frame does not match the tracker (context, size or levels)");
+  hslam_ctx* ctx = t->ctx;
+  HS_CUDA(cudaSetDevice(ctx->device));
+  hs::CdSeed* seeds; int *head, *next, *blockcnt, *total; float *maps, *in4;
+  int rc = cd_buffers(t, count, &seeds, &head, &next, &maps, &blockcnt, &total, &in4);
+  if (rc) return rc;
+  if (count > 0) {
+    rc = hs_ba_gather_coarse_inputs(ba, ctx, residual_ids, count, in4, in4 + 3 * (size_t)count);
+    if (rc) return rc;
+    HS_LAUNCH(ctx, HSLAM_K_COARSE_DEPTH, (hs::cd_seed_kernel<<<(count + 255) / 256, 256, 0, ctx->stream>>>(in4, in4 + 3 * (size_t)count, count, seeds)));
+  }
+  return cd_run(t, lastRef, seeds, count, head, next, maps, blockcnt, total);
 }
 
 int hslam_tracker_get_ref(hslam_tracker* t, int lvl, int capacity, float* u, float* v, float* idepth, float* color, int* n_out) {

@@ -167,6 +167,11 @@ int hslam_tracker_set_ref_aff(hslam_tracker* trk, float ref_exposure, double ref
  * hslam_tracker_set_ref for every level; call hslam_tracker_set_ref_aff as before. */
 int hslam_tracker_make_coarse_depth(hslam_tracker* trk, const hslam_frame* lastRef, int n_points,
                                     const float* centerProjectedTo /*n*3*/, const float* HdiF /*n*/);
+/* The same, device-resident: the inputs are read from a window handle of the SAME context — for every listed
+ * residual (caller ids: ph->lastResiduals[0] of each contributing point, state IN, target == lastRef) its
+ * centerProjectedTo of the last linearisation and the HdiF of its point from the last Schur pass. */
+int hslam_tracker_make_coarse_depth_from_ba(hslam_tracker* trk, const hslam_frame* lastRef, hslam_ba* ba,
+                                            const int32_t* residual_ids, int count);
 /* The reference cloud of a level as the tracker holds it (pc_u, pc_v, pc_idepth, pc_color, pc_n). */
 int hslam_tracker_get_ref(hslam_tracker* trk, int lvl, int capacity, float* u, float* v, float* idepth, float* color, int* n_out);
 

@@ -208,3 +208,28 @@ def test_make_coarse_depth_on_device_bit_exact(ctx, capi, O, synth):
     assert ok1 == ok2 and np.array_equal(T1, T2) and np.array_equal(aff1, aff2)
     for o in (trk, trk2, fr_ref, fr_new):
         o.close()
+
+
+def test_make_coarse_depth_from_ba_handle(ctx, capi, O, synth):
+    """Device-resident variant: centerProjectedTo / HdiF come straight from a window handle (residuals into the newest
+    keyframe, state IN); equals the host-array variant fed with the downloaded values."""
+    kf = synth.render_keyframes(320, 240, 4, seed=12)
+    win, _ = synth.make_window(points_per_frame=300, seed=40, keyframes=kf)
+    levels = 4
+    frames = [capi.Frame(ctx, im, levels) for im in win.images]
+    ef = capi.EnergyFunctional(ctx); ef.set_window(win, frames); ef.set_topology(win)
+    lin = ef.linearizeAll(False); ef.applyRes(); ef.accumulate_all()
+    newest = win.n - 1
+    ids = np.nonzero((win.target_idx == newest) & (lin["newState"] == 0))[0].astype(np.int32)
+    assert len(ids) > 200
+    hdi = ef.point_results()["HdiF"][win.point_idx[ids]]
+    cpt = lin["centerProjectedTo"][ids]
+    a = capi.CoarseTracker(ctx, 320, 240); a.makeK(win.cam, levels); a.makeCoarseDepthL0(frames[newest], cpt, hdi)
+    b = capi.CoarseTracker(ctx, 320, 240); b.makeK(win.cam, levels); b.makeCoarseDepthL0_from_ba(frames[newest], ef, ids)
+    for l in range(levels):
+        ra, rb = a.get_ref(l), b.get_ref(l)
+        assert len(ra[0]) > 0
+        for x, y in zip(ra, rb):
+            assert np.array_equal(x, y), l
+    for o in [a, b, ef] + frames:
+        o.close()
