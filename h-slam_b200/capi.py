@@ -292,6 +292,32 @@ def traceNewCoarse(ctx: "Context", frame: "Frame", ims, settings=None):
     return ims
 
 
+class ActivateSoA(C.Structure):
+    _fields_ = [("n_points", C.c_int)] + [(k, C.c_void_p) for k in (
+        "host_idx", "u", "v", "color", "weights", "energyTH", "idepth_min", "idepth_max", "ok_out", "idepth_out", "res_state_out")]
+
+
+def optimizeImmaturePoints(ctx: "Context", frames, cam, RtAff, ims, minObs=1, minIdepthH_act=100.0, GNIts=3):
+    """System::optimizeImmaturePoint for every point of `ims`: returns (ok int8[n], idepth float32[n], res_state int8[n, n_frames])."""
+    n, nf = len(ims.u), len(frames)
+    keep = dict(host_idx=np.ascontiguousarray(ims.host_idx, np.int32), u=np.ascontiguousarray(ims.u, np.float32),
+                v=np.ascontiguousarray(ims.v, np.float32), color=np.ascontiguousarray(ims.color, np.float32),
+                weights=np.ascontiguousarray(ims.weights, np.float32), energyTH=np.ascontiguousarray(ims.energyTH, np.float32),
+                idepth_min=np.ascontiguousarray(ims.idepth_min, np.float32), idepth_max=np.ascontiguousarray(ims.idepth_max, np.float32))
+    ok = np.zeros(n, np.int8); idp = np.zeros(n, np.float32); st = np.zeros((n, nf), np.int8)
+    s = ActivateSoA(n)
+    for k, a in keep.items():
+        setattr(s, k, _ptr(a))
+    s.ok_out, s.idepth_out, s.res_state_out = _ptr(ok), _ptr(idp), _ptr(st)
+    fr = (C.c_void_p * nf)(*[f.h for f in frames])
+    T = np.ascontiguousarray(RtAff, np.float32)
+    fxi, fyi = np.float32(1.0) / np.float32(cam.fx), np.float32(1.0) / np.float32(cam.fy)
+    _chk(ctx.L.hslam_activate_immature(ctx.h, C.c_int(nf), fr, C.c_float(cam.fx), C.c_float(cam.fy), C.c_float(cam.cx), C.c_float(cam.cy),
+                                       C.c_float(fxi), C.c_float(fyi), _ptr(T), C.c_float(minIdepthH_act), C.c_int(GNIts), C.c_int(minObs),
+                                       C.byref(s)))
+    return ok, idp, st
+
+
 class EnergyFunctional:
     """Mirror of FSLAM::EnergyFunctional's accumulate path + the residual linearisation it consumes
     (reference Include/EnergyFunctional.h:30-121, Src/FullSystemOptimize.cpp:19-165)."""

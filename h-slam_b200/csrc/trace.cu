@@ -245,6 +245,118 @@ __global__ void __launch_bounds__(128) trace_kernel(TraceArgs a) {
   }
 }
 
+// ------------------------------------------------------------------------------------------------------------------
+// System::optimizeImmaturePoint (Src/FullSystemOptPoint.cpp:24-175) + ImmaturePoint::linearizeResidual
+// (Src/ImmaturePoint.cpp:389-451): the 1-D Gauss-Newton on the inverse depth that decides the activation of an
+// immature point.  One thread per candidate: Hdd / bd are ONE sequential chain of float additions over (residual,
+// pattern pixel) in the source (they are passed by reference through all residuals, and an out-of-bounds pixel
+// leaves the partial sums of the pixels before it), so the chain is kept in one thread; the candidates of a
+// keyframe (~2000 per host) fill the device.
+struct ActArgs {
+  const float4* img[HSLAM_MAX_FRAMES];
+  int n_frames, w, h;
+  float fx, fy, cx, cy, fxi, fyi, huber, minIdepthH_act;
+  int GNIts, minObs;
+  const float* RtAff;
+  int n;
+  const int* host_idx;
+  const float* u; const float* v; const float* color; const float* weights; const float* energyTH;
+  const float* idmin; const float* idmax;
+  int8_t* ok; float* idepth; int8_t* res_state;
+};
+
+struct ActRes { int state, newState; double energy, newEnergy; };
+
+__device__ double act_lin_res(const ActArgs& a, const float4* __restrict__ img, const float* __restrict__ T, float pu, float pv,
+                              const float* color, const float* wgt, float energyTH, float slack, ActRes& r, float& Hdd, float& bd,
+                              float idepth) {
+  if (r.state == HSLAM_RES_OOB) { r.newState = HSLAM_RES_OOB; return r.energy; }
+  const float wm3 = (float)(a.w - 3), hm3 = (float)(a.h - 3);
+  const float t0 = T[9], t1 = T[10], t2 = T[11], aff0 = T[12], aff1 = T[13];
+  float energyLeft = 0.f;
+#pragma unroll 1
+  for (int idx = 0; idx < 8; ++idx) {
+    const float K0 = xmul(xsub(xadd(pu, (float)c_tpat[idx][0]), a.cx), a.fxi), K1 = xmul(xsub(xadd(pv, (float)c_tpat[idx][1]), a.cy), a.fyi);
+    const float p0 = xadd(xdot3(T[0], T[1], T[2], K0, K1, 1.0f), xmul(t0, idepth));
+    const float p1 = xadd(xdot3(T[3], T[4], T[5], K0, K1, 1.0f), xmul(t1, idepth));
+    const float p2 = xadd(xdot3(T[6], T[7], T[8], K0, K1, 1.0f), xmul(t2, idepth));
+    const float drescale = xdiv(1.0f, p2);
+    if (!(drescale > 0.f)) { r.newState = HSLAM_RES_OOB; return r.energy; }
+    const float u = xmul(p0, drescale), v = xmul(p1, drescale);
+    const float Ku = xadd(xmul(u, a.fx), a.cx), Kv = xadd(xmul(v, a.fy), a.cy);
+    if (!(Ku > 1.1f && Kv > 1.1f && Ku < wm3 && Kv < hm3)) { r.newState = HSLAM_RES_OOB; return r.energy; }
+    const Tap4 tp = tap4(img, Ku, Kv, a.w, a.h);
+    const float h0 = TAP_COMP(tp, x), h1 = TAP_COMP(tp, y), h2 = TAP_COMP(tp, z);
+    if (!isfinite(h0)) { r.newState = HSLAM_RES_OOB; return r.energy; }
+    const float residual = xsub(h0, xadd(xmul(aff0, color[idx]), aff1));
+    const float ar = fabsf(residual);
+    float hw = ar < a.huber ? 1.f : xdiv(a.huber, ar);
+    const float ww = xmul(wgt[idx], wgt[idx]);
+    energyLeft = xadd(energyLeft, xmul(xmul(xmul(xmul(ww, hw), residual), residual), xsub(2.f, hw)));
+    const float dxI = xmul(h1, a.fx), dyI = xmul(h2, a.fy);
+    const float d_id = xmul(xadd(xmul(xmul(dxI, drescale), xsub(t0, xmul(t2, u))), xmul(xmul(dyI, drescale), xsub(t1, xmul(t2, v)))), 1.0f);
+    hw = xmul(hw, ww);
+    Hdd = xadd(Hdd, xmul(xmul(hw, d_id), d_id));
+    bd = xadd(bd, xmul(xmul(hw, residual), d_id));
+  }
+  const float lim = xmul(energyTH, slack);
+  if (energyLeft > lim) { energyLeft = lim; r.newState = HSLAM_RES_OUT; } else r.newState = HSLAM_RES_IN;
+  r.newEnergy = (double)energyLeft;
+  return (double)energyLeft;
+}
+
+__global__ void __launch_bounds__(128) activate_kernel(ActArgs a) {
+  const int p = blockIdx.x * blockDim.x + threadIdx.x;
+  if (p >= a.n) return;
+  const int host = a.host_idx[p], nf = a.n_frames;
+  int8_t* out_state = a.res_state + (size_t)p * nf;
+  for (int f = 0; f < nf; ++f) out_state[f] = HSLAM_RES_OOB;
+  a.ok[p] = 0; a.idepth[p] = 0.f;
+  ActRes rs[HSLAM_MAX_FRAMES];
+  int tgt[HSLAM_MAX_FRAMES], nres = 0;
+  for (int f = 0; f < nf; ++f)
+    if (f != host) { rs[nres].energy = rs[nres].newEnergy = 0.0; rs[nres].newState = HSLAM_RES_OUT; rs[nres].state = HSLAM_RES_IN; tgt[nres] = f; nres++; }
+  float col[8], wgt[8];
+#pragma unroll
+  for (int i = 0; i < 8; ++i) { col[i] = a.color[8 * (size_t)p + i]; wgt[i] = a.weights[8 * (size_t)p + i]; }
+  const float pu = a.u[p], pv = a.v[p], eTH = a.energyTH[p];
+  float lastHdd = 0.f, lastbd = 0.f, lastEnergy = 0.f;
+  float cur = xmul(xadd(a.idmax[p], a.idmin[p]), 0.5f);
+  for (int i = 0; i < nres; ++i) {   // :51-56
+    const double e = act_lin_res(a, a.img[tgt[i]], a.RtAff + 14 * (size_t)(host + tgt[i] * nf), pu, pv, col, wgt, eTH, 1000.f, rs[i], lastHdd, lastbd, cur);
+    lastEnergy = (float)((double)lastEnergy + e);
+    rs[i].state = rs[i].newState; rs[i].energy = rs[i].newEnergy;
+  }
+  if (!isfinite(lastEnergy) || lastHdd < a.minIdepthH_act) return;
+  float lambda = 0.1f;
+  for (int it = 0; it < a.GNIts; ++it) {
+    float H = lastHdd;
+    H = xmul(H, xadd(1.f, lambda));
+    const float step = (float)((1.0 / (double)H) * (double)lastbd);
+    const float newId = xsub(cur, step);
+    float newHdd = 0.f, newbd = 0.f, newEnergy = 0.f;
+    for (int i = 0; i < nres; ++i) {
+      const double e = act_lin_res(a, a.img[tgt[i]], a.RtAff + 14 * (size_t)(host + tgt[i] * nf), pu, pv, col, wgt, eTH, 1.f, rs[i], newHdd, newbd, newId);
+      newEnergy = (float)((double)newEnergy + e);
+    }
+    if (!isfinite(lastEnergy) || newHdd < a.minIdepthH_act) return;
+    if (newEnergy < lastEnergy) {
+      cur = newId; lastHdd = newHdd; lastbd = newbd; lastEnergy = newEnergy;
+      for (int i = 0; i < nres; ++i) { rs[i].state = rs[i].newState; rs[i].energy = rs[i].newEnergy; }
+      lambda = xmul(lambda, 0.5f);
+    } else {
+      lambda = xmul(lambda, 5.f);
+    }
+    if ((double)fabsf(step) < 0.0001 * (double)cur) break;
+  }
+  if (!isfinite(cur)) return;
+  int good = 0;
+  for (int i = 0; i < nres; ++i) if (rs[i].state == HSLAM_RES_IN) good++;
+  if (good < a.minObs || !isfinite(eTH)) return;
+  a.ok[p] = 1; a.idepth[p] = cur;
+  for (int i = 0; i < nres; ++i) out_state[tgt[i]] = (int8_t)rs[i].state;
+}
+
 }  // namespace hs
 
 using namespace hs;
@@ -321,6 +433,61 @@ int hslam_trace_immature(hslam_ctx* ctx, const hslam_frame* frame, const hslam_t
   memcpy(pts->idepth_min, hp + o_min, nf * 4); memcpy(pts->idepth_max, hp + o_max, nf * 4); memcpy(pts->quality, hp + o_q, nf * 4);
   memcpy(pts->lastTraceUV, hp + o_uv, nf * 8); memcpy(pts->lastTracePixelInterval, hp + o_iv, nf * 4);
   memcpy(pts->lastTraceStatus, hp + o_st, nf);
+  return 0;
+}
+
+int hslam_activate_immature(hslam_ctx* ctx, int n_frames, const hslam_frame* const* frames, float fx, float fy, float cx, float cy,
+                            float fxi, float fyi, const float* RtAff, float minIdepthH_act, int GNIts, int minObs,
+                            const hslam_activate_soa* pts) {
+  HS_ARG(ctx && frames && RtAff && pts && n_frames >= 2 && n_frames <= HSLAM_MAX_FRAMES, "hslam_activate_immature: bad argument");
+  const int n = pts->n_points;
+  HS_ARG(n >= 0, "hslam_activate_immature: negative point count");
+  if (n == 0) return 0;
+  HS_ARG(pts->host_idx && pts->u && pts->v && pts->color && pts->weights && pts->energyTH && pts->idepth_min && pts->idepth_max &&
+             pts->ok_out && pts->idepth_out && pts->res_state_out, "hslam_activate_immature: null point array");
+  for (int i = 0; i < n; ++i) HS_ARG(pts->host_idx[i] >= 0 && pts->host_idx[i] < n_frames, "hslam_activate_immature: host_idx out of range");
+  HS_CUDA(cudaSetDevice(ctx->device));
+  ActArgs a;
+  for (int f = 0; f < n_frames; ++f) {
+    HS_ARG(frames[f] && frames[f]->ctx == ctx && frames[f]->w == frames[0]->w && frames[f]->h == frames[0]->h,
+           "hslam_activate_immature: frame missing, from another context or of another size");
+    a.img[f] = frames[f]->dI[0];
+  }
+  const size_t nf = (size_t)n, nn = (size_t)n_frames * n_frames;
+  size_t off = 0;
+  auto take = [&](size_t bytes) { size_t o = off; off = (off + bytes + 255) & ~(size_t)255; return o; };
+  const size_t o_T = take(nn * 14 * 4), o_h = take(nf * 4), o_u = take(nf * 4), o_v = take(nf * 4), o_c = take(nf * 32), o_w = take(nf * 32),
+               o_e = take(nf * 4), o_min = take(nf * 4), o_max = take(nf * 4);
+  const size_t o_io = off;
+  const size_t o_ok = take(nf), o_id = take(nf * 4), o_st = take(nf * n_frames);
+  const size_t total = off;
+  if (total > ctx->trace_cap) {
+    HS_CUDA(cudaStreamSynchronize(ctx->stream));
+    if (ctx->trace_dev) cudaFree(ctx->trace_dev);
+    if (ctx->trace_host) cudaFreeHost(ctx->trace_host);
+    ctx->trace_dev = nullptr; ctx->trace_host = nullptr; ctx->trace_cap = 0;
+    HS_CUDA(cudaMalloc((void**)&ctx->trace_dev, total + total / 4));
+    HS_CUDA(cudaMallocHost((void**)&ctx->trace_host, total + total / 4));
+    ctx->trace_cap = total + total / 4;
+  }
+  char* hp = ctx->trace_host;
+  char* dp = ctx->trace_dev;
+  memcpy(hp + o_T, RtAff, nn * 14 * 4); memcpy(hp + o_h, pts->host_idx, nf * 4); memcpy(hp + o_u, pts->u, nf * 4); memcpy(hp + o_v, pts->v, nf * 4);
+  memcpy(hp + o_c, pts->color, nf * 32); memcpy(hp + o_w, pts->weights, nf * 32); memcpy(hp + o_e, pts->energyTH, nf * 4);
+  memcpy(hp + o_min, pts->idepth_min, nf * 4); memcpy(hp + o_max, pts->idepth_max, nf * 4);
+  HS_CUDA(cudaMemcpyAsync(dp, hp, o_io, cudaMemcpyHostToDevice, ctx->stream));
+  a.n_frames = n_frames; a.w = frames[0]->w; a.h = frames[0]->h;
+  a.fx = fx; a.fy = fy; a.cx = cx; a.cy = cy; a.fxi = fxi; a.fyi = fyi; a.huber = ctx->prm.huberTH; a.minIdepthH_act = minIdepthH_act;
+  a.GNIts = GNIts; a.minObs = minObs;
+  a.RtAff = (const float*)(dp + o_T); a.n = n; a.host_idx = (const int*)(dp + o_h);
+  a.u = (const float*)(dp + o_u); a.v = (const float*)(dp + o_v); a.color = (const float*)(dp + o_c); a.weights = (const float*)(dp + o_w);
+  a.energyTH = (const float*)(dp + o_e); a.idmin = (const float*)(dp + o_min); a.idmax = (const float*)(dp + o_max);
+  a.ok = (int8_t*)(dp + o_ok); a.idepth = (float*)(dp + o_id); a.res_state = (int8_t*)(dp + o_st);
+  HS_LAUNCH(ctx, HSLAM_K_TRACE, (activate_kernel<<<(n + 127) / 128, 128, 0, ctx->stream>>>(a)));
+  HS_CUDA(cudaGetLastError());
+  HS_CUDA(cudaMemcpyAsync(hp + o_io, dp + o_io, total - o_io, cudaMemcpyDeviceToHost, ctx->stream));
+  HS_CUDA(cudaStreamSynchronize(ctx->stream));
+  memcpy(pts->ok_out, hp + o_ok, nf); memcpy(pts->idepth_out, hp + o_id, nf * 4); memcpy(pts->res_state_out, hp + o_st, nf * n_frames);
   return 0;
 }
 

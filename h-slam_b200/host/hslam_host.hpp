@@ -438,4 +438,14 @@ inline void traceNewCoarse(Context& ctx, const Frame& fh, int n_hosts, const flo
   check(hslam_trace_immature(ctx.get(), fh.get(), nullptr, n_hosts, KRKi, Kt, aff, &pts));
 }
 
+// std::shared_ptr<MapPoint> System::optimizeImmaturePoint(...)   (Src/FullSystemOptPoint.cpp:24-175) for a list of candidates.
+inline void optimizeImmaturePoints(Context& ctx, const std::vector<const Frame*>& frameHessians, const CalibData& HCalib,
+                                   const float* RtAff, float minIdepthH_act, int GNItsOnPointActivation, int minObs,
+                                   const hslam_activate_soa& pts) {
+  std::vector<const hslam_frame*> fr;
+  for (const Frame* f : frameHessians) fr.push_back(f->get());
+  check(hslam_activate_immature(ctx.get(), (int)fr.size(), fr.data(), HCalib.fxl(), HCalib.fyl(), HCalib.cxl(), HCalib.cyl(), HCalib.fxli(),
+                                HCalib.fyli(), RtAff, minIdepthH_act, GNItsOnPointActivation, minObs, &pts));
+}
+
 }  // namespace hslam_b200

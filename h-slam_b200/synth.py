@@ -594,3 +594,18 @@ def trace_tables(kf: Keyframes, hosts, new_frame, ims: ImmatureSet):
         aff.append(np.array(aff_from_to(1.0, 1.0, kf.aff_true[f][0], kf.aff_true[f][1], kf.aff_true[new_frame][0], kf.aff_true[new_frame][1]), np.float32))
     ims.KRKi, ims.Kt, ims.aff = np.array(KRKi, np.float32), np.array(Kt, np.float32), np.array(aff, np.float32)
     return ims
+
+
+def activation_tables(kf: Keyframes):
+    """Per ordered pair (host + target*n): PRE_RTll row-major, PRE_tTll, PRE_aff_mode (OptimizationClasses.cpp:13-39) as float."""
+    n = len(kf.images)
+    out = np.zeros((n * n, 14), np.float32)
+    for hst in range(n):
+        for tg in range(n):
+            T = se3_mul(kf.T_true[tg], se3_inv(kf.T_true[hst]))
+            R, t = T12_split(T)
+            a = aff_from_to(1.0, 1.0, kf.aff_true[hst][0], kf.aff_true[hst][1], kf.aff_true[tg][0], kf.aff_true[tg][1])
+            out[hst + tg * n, :9] = R.astype(np.float32).reshape(-1)
+            out[hst + tg * n, 9:12] = t.astype(np.float32)
+            out[hst + tg * n, 12:14] = np.array(a, np.float32)
+    return out

@@ -449,6 +449,32 @@ int hslam_trace_immature(hslam_ctx* ctx, const hslam_frame* frame, const hslam_t
                          int n_hosts, const float* KRKi /*n_hosts*9*/, const float* Kt /*n_hosts*3*/,
                          const float* aff /*n_hosts*2*/, const hslam_immature_soa* pts);
 
+/* System::optimizeImmaturePoint (Src/FullSystemOptPoint.cpp:24-175) with ImmaturePoint::linearizeResidual
+ * (Src/ImmaturePoint.cpp:389-451) for a list of activation candidates (System::activatePointsMT, Src/Mapping.cpp:330-480):
+ * the 1-D Gauss-Newton on the inverse depth against every other keyframe.  RtAff: per ordered pair (host + target*n_frames)
+ * 14 floats = FrameFramePrecalc::PRE_RTll (row-major 3x3), PRE_tTll, PRE_aff_mode (Src/OptimizationClasses.cpp:13-39).
+ * Outputs per point: ok_out (1 = the reference would return a MapPoint), idepth_out (the optimised inverse depth:
+ * setIdepthZero / setIdepth), res_state_out[n_frames] = final state of the temporary residual into each frame
+ * (HSLAM_RES_IN => the caller creates the PointFrameResidual; the host's own slot is HSLAM_RES_OOB). */
+typedef struct hslam_activate_soa {
+  int n_points;
+  const int32_t* host_idx;        /* n */
+  const float* u;                 /* n */
+  const float* v;                 /* n */
+  const float* color;             /* n*8 */
+  const float* weights;           /* n*8 */
+  const float* energyTH;          /* n */
+  const float* idepth_min;        /* n */
+  const float* idepth_max;        /* n */
+  int8_t* ok_out;                 /* n */
+  float* idepth_out;              /* n */
+  int8_t* res_state_out;          /* n*n_frames */
+} hslam_activate_soa;
+int hslam_activate_immature(hslam_ctx* ctx, int n_frames, const hslam_frame* const* frames, float fx, float fy, float cx,
+                            float cy, float fxi, float fyi, const float* RtAff /*n*n*14*/,
+                            float minIdepthH_act /*setting_minIdepthH_act = 100*/, int GNIts /*setting_GNItsOnPointActivation = 3*/,
+                            int minObs, const hslam_activate_soa* pts);
+
 #ifdef __cplusplus
 }
 #endif

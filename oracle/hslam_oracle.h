@@ -190,6 +190,15 @@ int orc_trace_immature(const float* dI0, int w, int h, const orc_trace_settings*
                        float* idepth_min_io, float* idepth_max_io, float* quality_io, int8_t* status_io,
                        float* lastTraceUV, float* lastTracePixelInterval);
 
+/* System::optimizeImmaturePoint (Src/FullSystemOptPoint.cpp:24-175) + ImmaturePoint::linearizeResidual
+ * (Src/ImmaturePoint.cpp:389-451).  RtAff: per ordered pair (host + target*n) 14 floats: PRE_RTll row-major, PRE_tTll,
+ * PRE_aff_mode.  res_state_out: per point n_frames states (HSLAM_RES_*; the host's own slot is OOB). */
+int orc_activate_immature(int n_frames, const float* const* dI0, int w, int h, float fx, float fy, float cx, float cy, float fxi,
+                          float fyi, const float* RtAff, float huber, float minIdepthH_act, int GNIts, int minObs, int n,
+                          const int32_t* host_idx, const float* u, const float* v, const float* color, const float* weights,
+                          const float* energyTH, const float* idepth_min, const float* idepth_max, int8_t* ok_out,
+                          float* idepth_out, int8_t* res_state_out);
+
 #ifdef __cplusplus
 }
 #endif

@@ -174,3 +174,114 @@ extern "C" int orc_trace_immature(const float* dI0 /*w*h*3*/, int w, int h, cons
   }
   return 0;
 }
+
+// ---------------------------------------------------------------------------------------------------------------
+// System::optimizeImmaturePoint (Src/FullSystemOptPoint.cpp:24-175) + ImmaturePoint::linearizeResidual
+// (Src/ImmaturePoint.cpp:389-451) + projectPoint / derive_idepth (Include/DirectProjection.h:7-38): the 1-D
+// Gauss-Newton over the inverse depth that decides whether an immature point is activated.  Outputs what the caller
+// needs to create the MapPoint and its PointFrameResiduals: activated?, idepth, the final state of the residual into
+// every other frame.
+namespace {
+struct ActRes { int state, newState; double energy, newEnergy; };
+
+double lin_res(const float* dI, int w, int h, float fx, float fy, float cx, float cy, float fxi, float fyi, const float* R /*9 rm*/,
+               const float* t, float aff0, float aff1, float huber, float pu, float pv, const float* color, const float* weights,
+               float energyTH, float outlierTHSlack, ActRes& r, float& Hdd, float& bd, float idepth) {
+  if (r.state == 1) { r.newState = 1; return r.energy; }   // OOB stays OOB (:392-393)
+  float energyLeft = 0;
+  for (int idx = 0; idx < 8; ++idx) {
+    const int dx = PATT[idx][0], dy = PATT[idx][1];
+    // projectPoint, DirectProjection.h:20-38
+    float K0 = (pu + dx - cx) * fxi, K1 = (pv + dy - cy) * fyi;
+    float p0 = orc::sum3(R[0] * K0, R[1] * K1, R[2] * 1.0f) + t[0] * idepth;
+    float p1 = orc::sum3(R[3] * K0, R[4] * K1, R[5] * 1.0f) + t[1] * idepth;
+    float p2 = orc::sum3(R[6] * K0, R[7] * K1, R[8] * 1.0f) + t[2] * idepth;
+    float drescale = 1.0f / p2;
+    if (!(drescale > 0)) { r.newState = 1; return r.energy; }
+    float u = p0 * drescale, v = p1 * drescale;
+    float Ku = u * fx + cx, Kv = v * fy + cy;
+    if (!(Ku > 1.1f && Kv > 1.1f && Ku < (w - 3) && Kv < (h - 3))) { r.newState = 1; return r.energy; }
+    Tap tp = tap(dI, Ku, Kv, w, h);
+    float h0 = comp(tp, 0), h1 = comp(tp, 1), h2 = comp(tp, 2);
+    if (!std::isfinite(h0)) { r.newState = 1; return r.energy; }
+    float residual = h0 - (aff0 * color[idx] + aff1);
+    float hw = fabsf(residual) < huber ? 1 : huber / fabsf(residual);
+    energyLeft += weights[idx] * weights[idx] * hw * residual * residual * (2 - hw);
+    float dxInterp = h1 * fx, dyInterp = h2 * fy;
+    float d_idepth = (dxInterp * drescale * (t[0] - t[2] * u) + dyInterp * drescale * (t[1] - t[2] * v)) * 1.0f;   // SCALE_IDEPTH = 1
+    hw *= weights[idx] * weights[idx];
+    Hdd += (hw * d_idepth) * d_idepth;
+    bd += (hw * residual) * d_idepth;
+  }
+  if (energyLeft > energyTH * outlierTHSlack) { energyLeft = energyTH * outlierTHSlack; r.newState = 2; }
+  else r.newState = 0;
+  r.newEnergy = energyLeft;
+  return energyLeft;
+}
+}  // namespace
+
+extern "C" int orc_activate_immature(int n_frames, const float* const* dI0 /*n_frames level-0 Vec3f images*/, int w, int h, float fx,
+                                     float fy, float cx, float cy, float fxi, float fyi, const float* RtAff /*n*n*14, host+target*n*/,
+                                     float huber, float minIdepthH_act, int GNIts, int minObs, int n, const int32_t* host_idx,
+                                     const float* u, const float* v, const float* color, const float* weights, const float* energyTH,
+                                     const float* idepth_min, const float* idepth_max, int8_t* ok_out, float* idepth_out,
+                                     int8_t* res_state_out /*n*n_frames*/) {
+  for (int p = 0; p < n; ++p) {
+    const int host = host_idx[p];
+    if (host < 0 || host >= n_frames) return -1;
+    ok_out[p] = 0; idepth_out[p] = 0;
+    for (int f = 0; f < n_frames; ++f) res_state_out[(size_t)p * n_frames + f] = 1;
+    ActRes rs[16];
+    int tgt[16], nres = 0;
+    for (int f = 0; f < n_frames; ++f)
+      if (f != host) { rs[nres].energy = rs[nres].newEnergy = 0; rs[nres].newState = 2; rs[nres].state = 0; tgt[nres] = f; nres++; }
+    auto eval = [&](float slack, float id, float& Hdd, float& bd) {
+      float E = 0;
+      for (int i = 0; i < nres; ++i) {
+        const float* T = RtAff + 14 * (size_t)(host + tgt[i] * n_frames);
+        double e = lin_res(dI0[tgt[i]], w, h, fx, fy, cx, cy, fxi, fyi, T, T + 9, T[12], T[13], huber, u[p], v[p], color + 8 * (size_t)p,
+                           weights + 8 * (size_t)p, energyTH[p], slack, rs[i], Hdd, bd, id);
+        E = (float)((double)E + e);
+      }
+      return E;
+    };
+    float lastHdd = 0, lastbd = 0;
+    float currentIdepth = (idepth_max[p] + idepth_min[p]) * 0.5f;
+    float lastEnergy = 0;
+    for (int i = 0; i < nres; ++i) {   // :51-56 (state committed after every residual)
+      const float* T = RtAff + 14 * (size_t)(host + tgt[i] * n_frames);
+      double e = lin_res(dI0[tgt[i]], w, h, fx, fy, cx, cy, fxi, fyi, T, T + 9, T[12], T[13], huber, u[p], v[p], color + 8 * (size_t)p,
+                         weights + 8 * (size_t)p, energyTH[p], 1000.f, rs[i], lastHdd, lastbd, currentIdepth);
+      lastEnergy = (float)((double)lastEnergy + e);
+      rs[i].state = rs[i].newState; rs[i].energy = rs[i].newEnergy;
+    }
+    if (!std::isfinite(lastEnergy) || lastHdd < minIdepthH_act) continue;
+    float lambda = 0.1f;
+    bool dead = false;
+    for (int it = 0; it < GNIts; ++it) {
+      float H = lastHdd;
+      H *= 1 + lambda;
+      float step = (float)((1.0 / H) * lastbd);   // (1.0/H) is a double expression in the source
+      float newIdepth = currentIdepth - step;
+      float newHdd = 0, newbd = 0;
+      float newEnergy = eval(1.f, newIdepth, newHdd, newbd);
+      if (!std::isfinite(lastEnergy) || newHdd < minIdepthH_act) { dead = true; break; }
+      if (newEnergy < lastEnergy) {
+        currentIdepth = newIdepth; lastHdd = newHdd; lastbd = newbd; lastEnergy = newEnergy;
+        for (int i = 0; i < nres; ++i) { rs[i].state = rs[i].newState; rs[i].energy = rs[i].newEnergy; }
+        lambda *= 0.5f;
+      } else {
+        lambda *= 5;
+      }
+      if (fabsf(step) < 0.0001 * currentIdepth) break;
+    }
+    if (dead || !std::isfinite(currentIdepth)) continue;
+    int good = 0;
+    for (int i = 0; i < nres; ++i) if (rs[i].state == 0) good++;
+    if (good < minObs) continue;
+    if (!std::isfinite(energyTH[p])) continue;
+    ok_out[p] = 1; idepth_out[p] = currentIdepth;
+    for (int i = 0; i < nres; ++i) res_state_out[(size_t)p * n_frames + tgt[i]] = (int8_t)rs[i].state;
+  }
+  return 0;
+}

@@ -42,3 +42,29 @@ def test_trace_bad_arguments(ctx, capi, synth):
     with pytest.raises(capi.HslamError):
         capi.traceNewCoarse(ctx, frame, ims)
     frame.close()
+
+
+def test_activation_bit_exact(ctx, capi, O, synth):
+    """hslam_activate_immature (System::optimizeImmaturePoint) == the oracle: activation flag, optimised idepth and the
+    final residual states, bit for bit, on the candidates left after two traces plus deliberately bad intervals."""
+    w, h, hosts = 640, 480, [0, 1, 2, 3]
+    kf = synth.render_keyframes(w, h, 6, seed=78)
+    ims = synth.make_immature_points(kf, hosts=hosts, points_per_host=1500, seed=5)
+    dIs = [O.pyramid(im, 1)[0][0] for im in kf.images]
+    for new in (4, 5):
+        synth.trace_tables(kf, hosts, new, ims)
+        O.trace_immature(dIs[new], ims)
+    keep = np.nonzero(np.isfinite(ims.idepth_max) & (ims.status != 1))[0]
+    sub = copy.deepcopy(ims)
+    for k in ("host_idx", "u", "v", "gradH", "color", "weights", "energyTH", "idepth_min", "idepth_max", "idepth_true"):
+        setattr(sub, k, np.ascontiguousarray(getattr(ims, k)[keep]))
+    sub.idepth_min[::17] *= np.float32(3.0)          # broken intervals: rejected / OOB paths
+    sub.idepth_max[::17] *= np.float32(5.0)
+    T = synth.activation_tables(kf)
+    frames = [capi.Frame(ctx, im, 1) for im in kf.images]
+    g = capi.optimizeImmaturePoints(ctx, frames, kf.cam, T, sub, minObs=2)
+    o = O.activate_immature(dIs, kf.cam, T, sub, minObs=2)
+    assert np.array_equal(g[0], o[0]) and np.array_equal(g[1], o[1]) and np.array_equal(g[2], o[2])
+    assert 0.3 < g[0].mean() < 1.0 and len(keep) > 2000
+    for f in frames:
+        f.close()

@@ -46,3 +46,26 @@ def test_trace_identity_motion_is_oob_or_skipped(O, synth):
     O.trace_immature(dIs[0], ims)
     assert np.all(ims.status == 3)
     assert np.allclose(ims.lastTraceUV[:, 0], ims.u) and np.all(ims.lastTracePixelInterval == 0)
+
+
+def test_activation_converges_to_true_depth(O, synth):
+    """optimizeImmaturePoint restatement: after two traces the candidates whose interval is tight are activated and the
+    1-D Gauss-Newton lands on the true inverse depth; candidates with a hopeless interval are rejected."""
+    kf, ims, dIs = _setup(synth, O)
+    for new in (2, 3):
+        synth.trace_tables(kf, [0, 1], new, ims)
+        O.trace_immature(dIs[new], ims)
+    cand = np.nonzero((ims.status == 0) & np.isfinite(ims.idepth_max))[0]
+    assert len(cand) > 100
+    import copy
+    sub = copy.deepcopy(ims)
+    for k in ("host_idx", "u", "v", "gradH", "color", "weights", "energyTH", "idepth_min", "idepth_max", "idepth_true"):
+        setattr(sub, k, np.ascontiguousarray(getattr(ims, k)[cand]))
+    ok, idp, st = O.activate_immature(dIs, kf.cam, synth.activation_tables(kf), sub, minObs=2)
+    assert ok.mean() > 0.7, ok.mean()
+    rel = np.abs(idp[ok == 1] - sub.idepth_true[ok == 1]) / sub.idepth_true[ok == 1]
+    assert np.median(rel) < 0.01 and (rel < 0.05).mean() > 0.9, (np.median(rel), (rel < 0.05).mean())
+    # the host's own slot is OOB, activated points have >= minObs residuals IN
+    assert np.all(st[np.arange(len(cand)), sub.host_idx] == 1)
+    assert np.all((st[ok == 1] == 0).sum(1) >= 2)
+    assert np.all(idp[ok == 0] == 0)
