@@ -38,7 +38,9 @@ constexpr int LIN_THREADS = LIN_THREADS_;
 #ifndef LIN_STREAM_STORES
 #define LIN_STREAM_STORES 1
 #endif
-#if LIN_STREAM_STORES
+#if defined(LIN_EXP_NOSTORE)   /* timing experiment only: results are wrong */
+#define STJ(ptr, v) do { if ((v) == 1.2345e-33f) *(ptr) = (v); } while (0)
+#elif LIN_STREAM_STORES
 #define STJ(ptr, v) __stcs((ptr), (v))
 #else
 #define STJ(ptr, v) (*(ptr) = (v))
@@ -202,7 +204,24 @@ __global__ void __launch_bounds__(LIN_THREADS, LIN_MINB) ba_linearize_kernel(con
 #endif
   int lb;
   const int win = find_window(prefix, nwin, blockIdx.x, lb);
+#ifndef LIN_DESC_SMEM
+#define LIN_DESC_SMEM 0   /* measured: descriptor through shared memory 150.5 us, through the pointer 147.4 us */
+#endif
+#if LIN_DESC_SMEM
+  // the window descriptor (camera scalars, ~40 array pointers) is copied to shared memory once per block: every
+  // later field access is an LDS instead of a global load through the pointer
+  __shared__ __align__(16) BADesc sD;
+  {
+    static_assert(sizeof(BADesc) % 4 == 0, "descriptor is copied word by word");
+    const unsigned int* src = reinterpret_cast<const unsigned int*>(descs + win);
+    unsigned int* dst = reinterpret_cast<unsigned int*>(&sD);
+    for (int i = threadIdx.x; i < (int)(sizeof(BADesc) / 4); i += LIN_THREADS) dst[i] = __ldg(src + i);
+  }
+  __syncthreads();
+  const BADesc& D = sD;
+#else
   const BADesc& D = descs[win];
+#endif
   const BAWin& W = D.W;
   const BARes& r = D.r;
   const int k = lb * LIN_THREADS + threadIdx.x;
@@ -312,7 +331,11 @@ __global__ void __launch_bounds__(LIN_THREADS, LIN_MINB) ba_linearize_kernel(con
           Hit3 hit[8];
           const uint64_t pol = l2_keep_policy();
 #pragma unroll
-          for (int idx = 0; idx < 8; ++idx) hit[idx] = interp33(img, Kup[idx], Kvp[idx], W.w, pol);
+#ifdef LIN_EXP_NOGATHER   /* timing experiment only: every gather hits the same few texels */
+          for (int idx = 0; idx < 8; ++idx) hit[idx] = interp33<HS_TEXEL_L2_KEEP != 0>(img, 8.25f + idx, 8.5f, W.w, pol);
+#else
+          for (int idx = 0; idx < 8; ++idx) hit[idx] = interp33<HS_TEXEL_L2_KEEP != 0>(img, Kup[idx], Kvp[idx], W.w, pol);
+#endif
 #if !LIN_PARK
           const float color[8] = {c0.x, c0.y, c0.z, c0.w, c1.x, c1.y, c1.z, c1.w};
           const float wgt[8] = {w0.x, w0.y, w0.z, w0.w, w1.x, w1.y, w1.z, w1.w};

@@ -63,6 +63,7 @@ __device__ __forceinline__ float4 ldg_keep(const float4* p, uint64_t pol) {
 #ifndef HS_TEXEL_L2_KEEP
 #define HS_TEXEL_L2_KEEP 1
 #endif
+template <bool KEEP = false>
 __device__ __forceinline__ Hit3 interp33(const float4* __restrict__ img, float x, float y, int width, uint64_t pol = 0) {
   int ix = (int)x, iy = (int)y;
   float dx = xsub(x, (float)ix), dy = xsub(y, (float)iy);
@@ -70,7 +71,7 @@ __device__ __forceinline__ Hit3 interp33(const float4* __restrict__ img, float x
   const float4* bp = img + ix + iy * width;
 #if HS_TEXEL_L2_KEEP
   float4 tl, tr, bl, br;
-  if (pol) { tl = ldg_keep(bp, pol); tr = ldg_keep(bp + 1, pol); bl = ldg_keep(bp + width, pol); br = ldg_keep(bp + width + 1, pol); }
+  if (KEEP) { tl = ldg_keep(bp, pol); tr = ldg_keep(bp + 1, pol); bl = ldg_keep(bp + width, pol); br = ldg_keep(bp + width + 1, pol); }
   else { tl = __ldg(bp); tr = __ldg(bp + 1); bl = __ldg(bp + width); br = __ldg(bp + width + 1); }
 #else
   float4 tl = __ldg(bp), tr = __ldg(bp + 1), bl = __ldg(bp + width), br = __ldg(bp + width + 1);
