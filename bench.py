@@ -320,15 +320,47 @@ def extras(ctx, capi, synth, torch, stream, ef0, win0):
     trk.setCoarseTrackingRef(tp.pc)
     frame = capi.Frame(ctx, tp.img_new, tp.levels)
     T0 = np.concatenate([np.eye(3).reshape(9), np.zeros(3)])
-    for _ in range(3):
-        trk.trackNewestCoarse(frame, T0, (0.0, 0.0), tp.levels - 1)
-    e0.record(stream)
-    for _ in range(reps):
-        trk.track_enqueue(frame, T0, (0.0, 0.0), tp.levels - 1)
-    e1.record(stream)
-    torch.cuda.synchronize()
-    trk.track_finish()
-    out["tracking_ms_per_frame_device"] = e0.elapsed_time(e1) / reps
+    out["tracking_mode_cluster_ctas"] = trk.get_mode()
+    for mode, key in ((trk.get_mode(), "tracking_ms_per_frame_device"), (0, "tracking_ms_per_frame_device_cooperative")):
+        trk.set_mode(mode)
+        for _ in range(3):
+            trk.trackNewestCoarse(frame, T0, (0.0, 0.0), tp.levels - 1)
+        e0.record(stream)
+        for _ in range(reps):
+            trk.track_enqueue(frame, T0, (0.0, 0.0), tp.levels - 1)
+        e1.record(stream)
+        torch.cuda.synchronize()
+        trk.track_finish()
+        out[key] = e0.elapsed_time(e1) / reps
+        out[key + "_phase_cycles"] = trk.last_profile()
+    trk.set_mode(out["tracking_mode_cluster_ctas"])
+    # throughput with several independent trackers in flight (one context = one stream each): the one-cluster kernel
+    # occupies 16 SMs per frame, so eight frames run side by side; the cooperative kernel wants most of the GPU per frame
+    nb = 8
+    ctxs = [capi.Context(0) for _ in range(nb)]
+    trks, frs = [], []
+    for cx in ctxs:
+        t_ = capi.CoarseTracker(cx, tp.cam.w, tp.cam.h); t_.makeK(tp.cam, tp.levels); t_.setCoarseTrackingRef(tp.pc)
+        trks.append(t_); frs.append(capi.Frame(cx, tp.img_new, tp.levels))
+    for mode, key in ((trk.get_mode(), "tracking_8_streams_ms_per_frame"), (0, "tracking_8_streams_ms_per_frame_cooperative")):
+        for t_ in trks:
+            t_.set_mode(mode)
+        for _ in range(2):
+            for t_, f_ in zip(trks, frs):
+                t_.track_enqueue(f_, T0, (0.0, 0.0), tp.levels - 1)
+            for t_ in trks:
+                t_.track_finish()
+        t0 = time.perf_counter()
+        for _ in range(reps):
+            for t_, f_ in zip(trks, frs):
+                t_.track_enqueue(f_, T0, (0.0, 0.0), tp.levels - 1)
+            for t_ in trks:
+                t_.track_finish()
+        out[key] = 1e3 * (time.perf_counter() - t0) / (reps * nb)
+    for t_, f_ in zip(trks, frs):
+        t_.close(); f_.close()
+    for cx in ctxs:
+        cx.close()
     t0 = time.perf_counter()
     for _ in range(reps):
         frame.update(tp.img_new)                                   # H2D 1.2 MB + 5-level pyramid

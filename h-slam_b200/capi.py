@@ -180,6 +180,19 @@ class CoarseTracker:
         self.lastFlowIndicators = np.full(3, 1000.0)
         self.iterations = np.zeros(5, np.int32)
 
+    def set_mode(self, cluster_ctas):
+        _chk(self.L.hslam_tracker_set_mode(self.h, C.c_int(cluster_ctas)))
+
+    def get_mode(self):
+        v = C.c_int(0)
+        _chk(self.L.hslam_tracker_get_mode(self.h, C.byref(v)))
+        return v.value
+
+    def last_profile(self):
+        cyc = (C.c_longlong * 4)(); ev = C.c_int(0)
+        _chk(self.L.hslam_tracker_last_profile(self.h, cyc, C.byref(ev)))
+        return [int(c) for c in cyc], ev.value
+
     def makeK(self, cam, levels):
         self.levels = levels
         _chk(self.L.hslam_tracker_make_K(self.h, levels, cam.w, cam.h, C.c_float(cam.fx), C.c_float(cam.fy),

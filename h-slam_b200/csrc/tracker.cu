@@ -19,6 +19,7 @@
 #include <cooperative_groups.h>
 #include <cmath>
 #include <cstring>
+#include <cstdlib>
 #include <algorithm>
 
 namespace cg = cooperative_groups;
@@ -26,6 +27,7 @@ namespace cg = cooperative_groups;
 namespace hs {
 
 constexpr int TRK_THREADS = 256;
+constexpr int TRK_CL_THREADS = 512;   // threads per CTA of the cluster kernel
 constexpr int TRK_NACC = 45;      // upper triangle of the 9x9
 constexpr int TRK_PART = 56;      // floats per block partial: 45 H, E, flowT, flowRT, flowNum, nE, nSat, nW (+pad)
 constexpr int P_E = 45, P_FT = 46, P_FRT = 47, P_FN = 48, P_NE = 49, P_NSAT = 50, P_NW = 51;
@@ -87,6 +89,8 @@ __device__ __forceinline__ void make_eval_const(EvalConst& c, const TrkLevelDev&
 
 // One pass over the reference cloud of a level: every thread accumulates its points, the block
 // reduces, thread t<TRK_PART writes partial[blockIdx][t].  smem: float[TRK_THREADS/32][TRK_PART].
+// `partial` points at THIS block's TRK_PART floats (global memory, or shared memory in the cluster kernel).
+template <int THREADS>
 __device__ __forceinline__ void eval_block(const EvalConst& c, float* __restrict__ partial, float (*red)[TRK_PART],
                                            int block, int nblocks) {
   float acc[TRK_NACC];
@@ -96,7 +100,7 @@ __device__ __forceinline__ void eval_block(const EvalConst& c, float* __restrict
   int nE = 0, nSat = 0, nW = 0;
   const float wm3 = (float)(c.w - 3), hm3 = (float)(c.h - 3);
 
-  for (int i = block * TRK_THREADS + threadIdx.x; i < c.n; i += nblocks * TRK_THREADS) {
+  for (int i = block * THREADS + threadIdx.x; i < c.n; i += nblocks * THREADS) {
     float4 p = __ldg(c.pc + i);
     float x = p.x, y = p.y, id = p.z, refColor = p.w;
     // pt = RKi*(x,y,1) + t*id ; CoarseTracker.cpp:377-382
@@ -188,13 +192,13 @@ __device__ __forceinline__ void eval_block(const EvalConst& c, float* __restrict
     if (t >= P_NE && t <= P_NW) {
       int q = 0;
 #pragma unroll
-      for (int w = 0; w < TRK_THREADS / 32; ++w) q += __float_as_int(red[w][t]);
-      partial[(size_t)block * TRK_PART + t] = __int_as_float(q);
+      for (int w = 0; w < THREADS / 32; ++w) q += __float_as_int(red[w][t]);
+      partial[t] = __int_as_float(q);
     } else if (t < P_NE) {
       float s = 0.f;
 #pragma unroll
-      for (int w = 0; w < TRK_THREADS / 32; ++w) s += red[w][t];
-      partial[(size_t)block * TRK_PART + t] = s;
+      for (int w = 0; w < THREADS / 32; ++w) s += red[w][t];
+      partial[t] = s;
     }
     __threadfence();  // partials visible device-wide before the block signals (ticket / grid barrier)
   }
@@ -203,17 +207,18 @@ __device__ __forceinline__ void eval_block(const EvalConst& c, float* __restrict
 
 // Deterministic fold of nblocks partials into fp64; executed by one whole block.
 // smem: double fold[4][TRK_PART].
-__device__ __forceinline__ void fold_partials(const float* __restrict__ partial, int nblocks, EvalResult& out,
-                                              double (*fold)[TRK_PART]) {
+// `get(b, t)` returns element t of block b's partial (global memory or a peer CTA's shared memory).
+template <class GET>
+__device__ __forceinline__ void fold_partials(GET get, int nblocks, EvalResult& out, double (*fold)[TRK_PART]) {
   int t = threadIdx.x & 63, q = threadIdx.x >> 6;  // 4 interleaved groups of 64 threads
   if (t < TRK_PART && q < 4) {
     if (t >= P_NE && t <= P_NW) {
       long long s = 0;
-      for (int b = q; b < nblocks; b += 4) s += __float_as_int(__ldcg(partial + (size_t)b * TRK_PART + t));
+      for (int b = q; b < nblocks; b += 4) s += __float_as_int(get(b, t));
       fold[q][t] = (double)s;
     } else {
       double s = 0.0;
-      for (int b = q; b < nblocks; b += 4) s += (double)__ldcg(partial + (size_t)b * TRK_PART + t);
+      for (int b = q; b < nblocks; b += 4) s += (double)get(b, t);
       fold[q][t] = s;
     }
   }
@@ -255,7 +260,7 @@ __global__ void __launch_bounds__(TRK_THREADS) trk_eval_kernel(EvalArgs a, float
     make_eval_const(c, a.L, a.lvl, a.img, a.T, a.aff_a, a.aff_b, a.ref_exposure, a.new_exposure, a.ref_aff_a,
                     a.ref_aff_b, a.cutoff, a.huber);
   __syncthreads();
-  eval_block(c, partial, red, blockIdx.x, gridDim.x);
+  eval_block<TRK_THREADS>(c, partial + (size_t)blockIdx.x * TRK_PART, red, blockIdx.x, gridDim.x);
   // last block folds (threadfence + ticket); fold order is by block index, not arrival order
   if (threadIdx.x == 0) {
     __threadfence();
@@ -265,7 +270,7 @@ __global__ void __launch_bounds__(TRK_THREADS) trk_eval_kernel(EvalArgs a, float
   __syncthreads();
   if (last) {
     __threadfence();
-    fold_partials(partial, gridDim.x, res, fold);
+    fold_partials([&](int b, int t) { return __ldcg(partial + (size_t)b * TRK_PART + t); }, gridDim.x, res, fold);
     if (threadIdx.x == 0) {
       *result = res;
       *ticket = 0;
@@ -431,6 +436,7 @@ struct TrackIO {           // pinned-host visible struct copied in/out
   int iterations[5];
   int evals;
   int pad;
+  long long phase_cycles[4];   // diagnostics (block 0): solve+exp+constants | evaluation | barrier+fold | accept+make_Hb
 };
 
 struct LMState {
@@ -446,12 +452,39 @@ struct LMState {
 
 __device__ __forceinline__ double sat_ratio(const EvalResult& r) { return (double)((float)r.nSat / (float)r.nE); }
 
-__global__ void __launch_bounds__(TRK_THREADS) trk_track_kernel(TrackArgs a, float* __restrict__ partial0,
-                                                                float* __restrict__ partial1,
-                                                                TrackIO* __restrict__ io) {
-  cg::grid_group grid = cg::this_grid();
+// One evaluation of the LM loop: every participating block evaluates its share, all blocks meet, every block folds all
+// partials in block order (identical result in every block).
+template <int THREADS, bool CLUSTER>
+__device__ __forceinline__ void track_eval_and_fold(const EvalConst& c, float* gpart, float* spart, float (*red)[TRK_PART],
+                                                    double (*fold)[TRK_PART], EvalResult& res, int nb, long long* tk) {
+  const long long t0 = clock64();
+  if (CLUSTER) {
+    cg::cluster_group cluster = cg::this_cluster();
+    if ((int)blockIdx.x < nb) eval_block<THREADS>(c, spart, red, blockIdx.x, nb);
+    if (threadIdx.x == 0) tk[1] += clock64() - t0;
+    cluster.sync();   // release/acquire across the cluster: the shared-memory partials are visible
+    fold_partials([&](int b, int t) { return cluster.map_shared_rank(spart, b)[t]; }, nb, res, fold);
+  } else {
+    if ((int)blockIdx.x < nb) eval_block<THREADS>(c, gpart + (size_t)blockIdx.x * TRK_PART, red, blockIdx.x, nb);
+    if (threadIdx.x == 0) tk[1] += clock64() - t0;
+    __threadfence();
+    cg::this_grid().sync();
+    fold_partials([&](int b, int t) { return __ldcg(gpart + (size_t)b * TRK_PART + t); }, nb, res, fold);
+  }
+}
+
+// CLUSTER = false: cooperative launch over up to 2 blocks per SM, grid barrier per evaluation, partials in global memory.
+// CLUSTER = true : ONE thread-block cluster (8 or 16 CTAs) runs the whole frame: the barrier is the hardware cluster
+//                  barrier, the per-CTA partials stay in shared memory and are folded through distributed shared
+//                  memory, nothing of an evaluation touches global memory except the gathers; the rest of the GPU
+//                  stays free for other trackers / hypotheses.
+template <int THREADS, bool CLUSTER>
+__global__ void __launch_bounds__(THREADS) trk_track_kernel(TrackArgs a, float* __restrict__ partial0,
+                                                            float* __restrict__ partial1,
+                                                            TrackIO* __restrict__ io) {
   __shared__ EvalConst c;
-  __shared__ float red[TRK_THREADS / 32][TRK_PART];
+  __shared__ float red[THREADS / 32][TRK_PART];
+  __shared__ float mypart[2][TRK_PART];   // CLUSTER: this CTA's partial of the current / previous evaluation
   __shared__ double fold[4][TRK_PART];
   __shared__ EvalResult res;
   __shared__ LMState s;
@@ -459,6 +492,8 @@ __global__ void __launch_bounds__(TRK_THREADS) trk_track_kernel(TrackArgs a, flo
   __shared__ double lastRes[5];
   __shared__ double sA[8][9];
   __shared__ double sy[8];
+  __shared__ long long tk[4];   // [0] solve, [1] evaluation (inside [2]), [2] evaluation + barrier + fold, [3] accept
+  if (threadIdx.x < 4) tk[threadIdx.x] = 0;
 
   // Every block carries an identical copy of the LM state and takes identical decisions.
   if (threadIdx.x == 0) {
@@ -473,7 +508,7 @@ __global__ void __launch_bounds__(TRK_THREADS) trk_track_kernel(TrackArgs a, flo
 
   for (int lvl = a.coarsestLvl; lvl >= 0; lvl--) {
     const TrkLevelDev& L = a.L[lvl];
-    int nb = (L.n + TRK_THREADS - 1) / TRK_THREADS;
+    int nb = (L.n + THREADS - 1) / THREADS;
     if (nb > (int)gridDim.x) nb = gridDim.x;
     if (nb < 1) nb = 1;
     // --- initial evaluation with cutoff doubling, CoarseTracker.cpp:530-541
@@ -484,11 +519,7 @@ __global__ void __launch_bounds__(TRK_THREADS) trk_track_kernel(TrackArgs a, flo
         make_eval_const(c, L, lvl, a.img[lvl], s.cur, s.aff_cur[0], s.aff_cur[1], a.ref_exposure, a.new_exposure,
                         a.ref_aff_a, a.ref_aff_b, xmul(a.coarseCutoffTH, s.levelCutoffRepeat), a.huber);
       __syncthreads();
-      float* part = buf ? partial1 : partial0;
-      if ((int)blockIdx.x < nb) eval_block(c, part, red, blockIdx.x, nb);
-      __threadfence();
-      grid.sync();
-      fold_partials(part, nb, res, fold);
+      track_eval_and_fold<THREADS, CLUSTER>(c, buf ? partial1 : partial0, mypart[buf], red, fold, res, nb, tk);
       buf ^= 1;
       bool again = (sat_ratio(res) > 0.6) && (s.levelCutoffRepeat < 50.f);
       __syncthreads();
@@ -510,6 +541,7 @@ __global__ void __launch_bounds__(TRK_THREADS) trk_track_kernel(TrackArgs a, flo
     for (int iteration = 0; iteration < a.maxIterations[lvl]; iteration++) {
       // 8x8 damped solve by the first warp: lanes 0..7 own one row each of a shared-memory LDLT
       // (the serial thread-0 version spent ~10 us per iteration in local-memory traffic).
+      long long tk0 = clock64();
       if (threadIdx.x < 32) {
         const int lane = threadIdx.x;
         const bool fixA = a.affineOptModeA < 0.f, fixB = a.affineOptModeB < 0.f;
@@ -554,11 +586,9 @@ __global__ void __launch_bounds__(TRK_THREADS) trk_track_kernel(TrackArgs a, flo
                         a.ref_aff_a, a.ref_aff_b, xmul(a.coarseCutoffTH, s.levelCutoffRepeat), a.huber);
       }
       __syncthreads();
-      float* part = buf ? partial1 : partial0;
-      if ((int)blockIdx.x < nb) eval_block(c, part, red, blockIdx.x, nb);
-      __threadfence();
-      grid.sync();
-      fold_partials(part, nb, res, fold);
+      long long tk1 = clock64();
+      track_eval_and_fold<THREADS, CLUSTER>(c, buf ? partial1 : partial0, mypart[buf], red, fold, res, nb, tk);
+      long long tk3 = clock64();
       buf ^= 1;
       if (threadIdx.x == 0) {
         s.evals++;
@@ -577,6 +607,7 @@ __global__ void __launch_bounds__(TRK_THREADS) trk_track_kernel(TrackArgs a, flo
         }
       }
       __syncthreads();
+      if (threadIdx.x == 0) { tk[0] += tk1 - tk0; tk[2] += tk3 - tk1; tk[3] += clock64() - tk3; }
       if (!(s.incnorm > 1e-3)) break;   // uniform: s is identical in every block
     }
 
@@ -618,7 +649,9 @@ __global__ void __launch_bounds__(TRK_THREADS) trk_track_kernel(TrackArgs a, flo
     for (int i = 0; i < 5; ++i) { io->lastResiduals[i] = lastRes[i]; io->iterations[i] = iters[i]; }
     for (int i = 0; i < 3; ++i) io->lastFlow[i] = s.flowOld[i];
     io->evals = s.evals;
+    for (int i = 0; i < 4; ++i) io->phase_cycles[i] = tk[i];
   }
+  if (CLUSTER) cg::this_cluster().sync();   // no CTA leaves while a peer may still read its partial
 }
 
 }  // namespace hs
@@ -643,6 +676,9 @@ struct hslam_tracker {
   float4* h_pack = nullptr;         // pinned staging for set_ref
   size_t h_pack_cap = 0;
   int coop_blocks = 0;
+  long long last_phase_cycles[4] = {0, 0, 0, 0};
+  int last_evals = 0;
+  int cluster_ctas = 0;             // 0: cooperative grid kernel; 8 / 16: one thread-block cluster runs the frame
   char* cd_buf = nullptr;           // makeCoarseDepthL0 working set (seeds, pixel lists, maps, scan)
   size_t cd_cap = 0;
 };
@@ -672,12 +708,48 @@ int hslam_tracker_create(hslam_ctx* ctx, int w, int h, hslam_tracker** out) {
   HS_CUDA(cudaMalloc(&t->d_io, sizeof(TrackIO)));
   HS_CUDA(cudaMallocHost(&t->h_io, sizeof(TrackIO)));
   int per_sm = 0;
-  HS_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, trk_track_kernel, TRK_THREADS, 0));
+  HS_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, trk_track_kernel<TRK_THREADS, false>, TRK_THREADS, 0));
   HS_ARG(per_sm >= 1, "hslam_tracker_create: track kernel does not fit on an SM");
   t->coop_blocks = ctx->sm_count * (per_sm > 2 ? 2 : per_sm);
   int rc = ensure_partials(t, t->coop_blocks > 1024 ? t->coop_blocks : 1024);
   if (rc) return rc;
+  // cluster mode: the largest cluster (16 CTAs, non-portable size, else 8) that the device can co-schedule
+  t->cluster_ctas = 0;
+  const char* mode = getenv("HSLAM_TRACKER_MODE");
+  if (!(mode && strcmp(mode, "coop") == 0)) {
+    cudaFuncSetAttribute(trk_track_kernel<TRK_CL_THREADS, true>, cudaFuncAttributeNonPortableClusterSizeAllowed, 1);
+    for (int c : {16, 8}) {
+      cudaLaunchConfig_t cfg = {};
+      cfg.gridDim = dim3(c); cfg.blockDim = dim3(TRK_CL_THREADS);
+      cudaLaunchAttribute at[1];
+      at[0].id = cudaLaunchAttributeClusterDimension; at[0].val.clusterDim.x = c; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
+      cfg.attrs = at; cfg.numAttrs = 1;
+      int nclusters = 0;
+      if (cudaOccupancyMaxActiveClusters(&nclusters, trk_track_kernel<TRK_CL_THREADS, true>, &cfg) == cudaSuccess && nclusters >= 1) {
+        t->cluster_ctas = c;
+        break;
+      }
+    }
+    cudaGetLastError();   // a failed probe is not an error of the handle
+  }
   *out = t;
+  return 0;
+}
+
+int hslam_tracker_set_mode(hslam_tracker* t, int cluster_ctas) {
+  HS_ARG(t && (cluster_ctas == 0 || cluster_ctas == 8 || cluster_ctas == 16), "hslam_tracker_set_mode: cluster_ctas must be 0, 8 or 16");
+  t->cluster_ctas = cluster_ctas;
+  return 0;
+}
+int hslam_tracker_last_profile(hslam_tracker* t, long long phase_cycles[4], int* evals) {
+  HS_ARG(t && phase_cycles && evals, "hslam_tracker_last_profile: null");
+  memcpy(phase_cycles, t->last_phase_cycles, sizeof(t->last_phase_cycles));
+  *evals = t->last_evals;
+  return 0;
+}
+int hslam_tracker_get_mode(hslam_tracker* t, int* cluster_ctas) {
+  HS_ARG(t && cluster_ctas, "hslam_tracker_get_mode: null");
+  *cluster_ctas = t->cluster_ctas;
   return 0;
 }
 
@@ -862,10 +934,21 @@ int hslam_tracker_track_enqueue(hslam_tracker* t, const hslam_frame* f, float ne
   if (blocks > t->coop_blocks) blocks = t->coop_blocks;
   int rc = ensure_partials(t, blocks);
   if (rc) return rc;
-  void* args[] = {&a, &t->partial[0], &t->partial[1], &t->d_io};
   cudaError_t lerr = cudaSuccess;
-  HS_LAUNCH(ctx, HSLAM_K_TRK_TRACK, (lerr = cudaLaunchCooperativeKernel((void*)trk_track_kernel, dim3(blocks),
-                                                                       dim3(TRK_THREADS), args, 0, ctx->stream)));
+  if (t->cluster_ctas > 0) {
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3(t->cluster_ctas); cfg.blockDim = dim3(TRK_CL_THREADS); cfg.stream = ctx->stream;
+    cudaLaunchAttribute at[1];
+    at[0].id = cudaLaunchAttributeClusterDimension;
+    at[0].val.clusterDim.x = t->cluster_ctas; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
+    cfg.attrs = at; cfg.numAttrs = 1;
+    float* nullp = nullptr;
+    HS_LAUNCH(ctx, HSLAM_K_TRK_TRACK, (lerr = cudaLaunchKernelEx(&cfg, trk_track_kernel<TRK_CL_THREADS, true>, a, nullp, nullp, t->d_io)));
+  } else {
+    void* args[] = {&a, &t->partial[0], &t->partial[1], &t->d_io};
+    HS_LAUNCH(ctx, HSLAM_K_TRK_TRACK, (lerr = cudaLaunchCooperativeKernel((void*)trk_track_kernel<TRK_THREADS, false>, dim3(blocks),
+                                                                         dim3(TRK_THREADS), args, 0, ctx->stream)));
+  }
   HS_CUDA(lerr);
   HS_CUDA(cudaMemcpyAsync(t->h_io, t->d_io, sizeof(TrackIO), cudaMemcpyDeviceToHost, ctx->stream));
   return 0;
@@ -886,6 +969,8 @@ int hslam_tracker_track_finish(hslam_tracker* t, double T_out[12], double aff_ou
   if (lastFlow) memcpy(lastFlow, io->lastFlow, sizeof(io->lastFlow));
   if (ok) *ok = io->ok;
   if (iterations_out) memcpy(iterations_out, io->iterations, sizeof(io->iterations));
+  memcpy(t->last_phase_cycles, io->phase_cycles, sizeof(io->phase_cycles));
+  t->last_evals = io->evals;
   return 0;
 }
 

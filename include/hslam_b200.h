@@ -147,6 +147,16 @@ int hslam_frame_destroy(hslam_frame* f);
  * One per CoarseTracker instance (Include/CoarseTracker.h:14-95). */
 int hslam_tracker_create(hslam_ctx* ctx, int w, int h, hslam_tracker** out);
 int hslam_tracker_destroy(hslam_tracker* trk);
+/* How hslam_tracker_track runs the LM loop: cluster_ctas = 8 or 16 -> ONE thread-block cluster runs the whole frame
+ * (cluster barrier + distributed shared memory between evaluations, the other SMs stay free for more trackers);
+ * 0 -> cooperative kernel over up to two blocks per SM with a grid barrier per evaluation.  Default: the largest cluster
+ * the device can schedule (environment HSLAM_TRACKER_MODE=coop selects 0).  Same arithmetic per point in both; the
+ * partial sums are grouped per block, so H,b agree to fp32 round-off between the modes. */
+int hslam_tracker_set_mode(hslam_tracker* trk, int cluster_ctas);
+int hslam_tracker_get_mode(hslam_tracker* trk, int* cluster_ctas);
+/* Diagnostics of the last hslam_tracker_track: SM clock cycles block 0 spent in {solve + SE3 exp + constants,
+ * evaluation, evaluation + barrier + fold, accept + normal equations}, and the number of evaluations. */
+int hslam_tracker_last_profile(hslam_tracker* trk, long long phase_cycles[4], int* evals);
 /* CoarseTracker::makeK (Src/CoarseTracker.cpp:72-101).  The caller passes the
  * level-0 intrinsics (HCalib->fxl() ...); levels 1.. are derived by the
  * reference rule.  Ki = K^-1 is derived with Eigen's 3x3 cofactor formula. */

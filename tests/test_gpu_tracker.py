@@ -233,3 +233,26 @@ def test_make_coarse_depth_from_ba_handle(ctx, capi, O, synth):
             assert np.array_equal(x, y), l
     for o in [a, b, ef] + frames:
         o.close()
+
+
+def test_cluster_and_cooperative_modes_agree(ctx, capi, O, tracking_pair):
+    """The one-cluster LM kernel (cluster barrier + distributed shared memory) and the cooperative grid kernel take the
+    same LM path and land on the same pose (their per-block partial sums are grouped differently: fp32 round-off)."""
+    tp = tracking_pair
+    trk, frame, orc, lv, dI = _setup(ctx, capi, O, tp)
+    mode = trk.get_mode()
+    assert mode in (8, 16), "cluster launch unavailable on this device?"
+    ok1, T1, aff1 = trk.trackNewestCoarse(frame, T_ID, (0.0, 0.0), tp.levels - 1)
+    it1 = trk.iterations.copy(); r1 = trk.lastResiduals.copy()
+    trk.set_mode(0)
+    ok2, T2, aff2 = trk.trackNewestCoarse(frame, T_ID, (0.0, 0.0), tp.levels - 1)
+    assert ok1 and ok2 and np.array_equal(it1, trk.iterations)
+    assert np.abs(O.se3_log(T1) - O.se3_log(T2)).max() < 1e-6 and np.abs(np.asarray(aff1) - np.asarray(aff2)).max() < 1e-5
+    assert np.allclose(r1, trk.lastResiduals, rtol=1e-5)
+    trk.set_mode(8)
+    ok3, T3, _ = trk.trackNewestCoarse(frame, T_ID, (0.0, 0.0), tp.levels - 1)
+    assert ok3 and np.abs(O.se3_log(T1) - O.se3_log(T3)).max() < 1e-6
+    # deterministic within a mode
+    ok4, T4, _ = trk.trackNewestCoarse(frame, T_ID, (0.0, 0.0), tp.levels - 1)
+    assert np.array_equal(T3, T4)
+    trk.close(); frame.close()
