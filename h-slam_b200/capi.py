@@ -608,6 +608,11 @@ class EnergyFunctionalBatch:
                 return np.frombuffer(buf, dtype=dt, count=count)
             for i, (ef, w) in enumerate(zip(self.efs, wins)):
                 N = 8 * w.n + 4
+                # the per-point INPUT slots are bound as well: the caller's idepth / deltaF arrays ARE the pinned block
+                ws, ka, _old = keep[i]
+                inp = dict(idepth=view(arr[i].idepth, ef.P, np.float32), deltaF=view(arr[i].deltaF, ef.P, np.float32))
+                inp["idepth"][:] = w.idepth; inp["deltaF"][:] = w.deltaF
+                keep[i] = (ws, ka, inp)
                 outs.append(dict(energy=view(arr[i].energy, 1, np.float64), newState=view(arr[i].newState, ef.R, np.int8),
                                  newEnergy=view(arr[i].newEnergy, ef.R, np.float32),
                                  newEnergyWithOutlier=view(arr[i].newEnergyWithOutlier, ef.R, np.float32),

@@ -1023,6 +1023,7 @@ struct hslam_ba_batch {
   DevBuf<char> d_up, d_dn;
   DevBuf<BAIO> d_io;
   std::vector<BAIO> io;
+  size_t up_tab_begin = 0, up_tab_end = 0, up_idepth_end = 0, up_deltaF_end = 0, up_end = 0;   // H2D block regions
   size_t dn_res_end = 0, dn_sys_end = 0, dn_end = 0;   // D2H block regions: [0,res) per-residual arrays, [res,sys) systems, [sys,end) steps
 };
 static const int NPF = 6;
@@ -1202,14 +1203,46 @@ static int batch_layout_down(hslam_ba_batch* B) {
   return 0;
 }
 
+// Fixed layout of the H2D block: [BAIO table | x of every window | tables of every window | idepth | deltaF | idepth_zero].
+// A call copies only the leading part that it uses.
+static int batch_layout_up(hslam_ba_batch* B) {
+  const int n = (int)B->items.size();
+  size_t up = al256(n * sizeof(BAIO));
+  auto take = [&](size_t bytes) { long long off = (long long)up; up = al256(up + bytes); return off; };
+  for (int i = 0; i < n; ++i) B->io[i].up_x = take((size_t)B->items[i]->N * 8);   // solution vectors (resubstitute)
+  B->up_tab_begin = up;
+  for (int i = 0; i < n; ++i) {
+    hslam_ba* ba = B->items[i];
+    const size_t nn = (size_t)ba->n * ba->n;
+    BAIO& L = B->io[i];
+    L.up_precalc = take(nn * HSLAM_PRECALC_STRIDE * 4); L.up_adHTd = take(nn * 8 * 4);
+    L.up_adH = take(nn * 64 * 8); L.up_adT = take(nn * 64 * 8);
+    L.up_fprior = take((size_t)ba->n * 8 * 8); L.up_fdprior = take((size_t)ba->n * 8 * 8);
+  }
+  B->up_tab_end = up;
+  for (int i = 0; i < n; ++i) B->io[i].up_idepth = take((size_t)B->items[i]->P * 4);
+  B->up_idepth_end = up;
+  for (int i = 0; i < n; ++i) B->io[i].up_deltaF = take((size_t)B->items[i]->P * 4);
+  B->up_deltaF_end = up;
+  for (int i = 0; i < n; ++i) B->io[i].up_idz = take((size_t)B->items[i]->P * 4);
+  B->up_end = up;
+  TRY(pinned_ensure(&B->h_up, &B->h_up_cap, up));
+  TRY(B->d_up.ensure(up));
+  return 0;
+}
+
 int hslam_ba_batch_io_bind(hslam_ba_batch* B, hslam_ba_step_io* io, float** step_out) {
   HS_ARG(B && io, "hslam_ba_batch_io_bind: null argument");
   HS_CUDA(cudaSetDevice(B->ctx->device));
   HS_CUDA(cudaStreamSynchronize(B->ctx->stream));
   TRY(batch_layout_down(B));
+  TRY(batch_layout_up(B));
   const int n = (int)B->items.size();
   for (int i = 0; i < n; ++i) {
     const BAIO& L = B->io[i];
+    // per-point INPUT slots: the caller writes idepth / deltaF / idepth_zero in place (no staging copy)
+    io[i].idepth = (const float*)(B->h_up + L.up_idepth); io[i].deltaF = (const float*)(B->h_up + L.up_deltaF);
+    io[i].idepth_zero = nullptr; (void)L.up_idz;
     io[i].energy = (double*)(B->h_dn + L.dn_energy); io[i].nres2 = (int32_t*)(B->h_dn + L.dn_nres);
     io[i].Hb = (double*)(B->h_dn + L.dn_Hb);
     io[i].newEnergy = (float*)(B->h_dn + L.dn_newEnergy); io[i].newEnergyWithOutlier = (float*)(B->h_dn + L.dn_newEnergyWO);
@@ -1224,57 +1257,48 @@ int hslam_ba_batch_step_host(hslam_ba_batch* B, const hslam_ba_step_io* io) {
   hslam_ctx* ctx = B->ctx;
   HS_CUDA(cudaSetDevice(ctx->device));
   const int n = (int)B->items.size();
-  // ---- layout of the two staging blocks
+  // ---- layout of the two staging blocks (both fixed: see batch_layout_up / batch_layout_down)
   TRY(batch_layout_down(B));
-  size_t up = 0;
+  TRY(batch_layout_up(B));
+  std::vector<BAIO> eff(B->io);   // offsets of what is absent in this call become -1 for the import kernel
   int maxP = 1, maxR = 1;
+  size_t extent = B->up_tab_begin;   // bytes of the block that actually have to travel
   for (int i = 0; i < n; ++i) {
     hslam_ba* ba = B->items[i];
     HS_ARG(ba->have_window && ba->have_topology, "hslam_ba_batch_step_host: a window has no window/topology set");
     const hslam_ba_step_io& o = io[i];
-    BAIO& L = B->io[i];
-    const size_t nn = (size_t)ba->n * ba->n, P = ba->P;
-    auto take = [](size_t& cur, size_t bytes) { long long off = (long long)cur; cur = al256(cur + bytes); return off; };
-    if (o.window) {
-      TRY(window_scalars(ba, o.window));
-      L.up_precalc = take(up, nn * HSLAM_PRECALC_STRIDE * 4); L.up_adHTd = take(up, nn * 8 * 4);
-      L.up_adH = take(up, nn * 64 * 8); L.up_adT = take(up, nn * 64 * 8);
-      L.up_fprior = take(up, (size_t)ba->n * 8 * 8); L.up_fdprior = take(up, (size_t)ba->n * 8 * 8);
-    } else {
-      L.up_precalc = L.up_adHTd = L.up_adH = L.up_adT = L.up_fprior = L.up_fdprior = -1;
-    }
-    L.up_idepth = o.idepth ? take(up, P * 4) : -1;
-    L.up_deltaF = o.deltaF ? take(up, P * 4) : -1;
-    L.up_idz = o.idepth_zero ? take(up, P * 4) : -1;
-    L.up_x = -1;
-    maxP = std::max(maxP, ba->P); maxR = std::max(maxR, ba->R);
-  }
-  const size_t io_bytes = al256(n * sizeof(BAIO));
-  TRY(pinned_ensure(&B->h_up, &B->h_up_cap, up + io_bytes));
-  TRY(B->d_up.ensure(up + io_bytes));
-  // ---- pack: [BAIO table][window 0 tables + point arrays][window 1 ...]
-  memcpy(B->h_up + up, B->io.data(), n * sizeof(BAIO));
-  for (int i = 0; i < n; ++i) {
-    hslam_ba* ba = B->items[i];
-    const hslam_ba_step_io& o = io[i];
     const BAIO& L = B->io[i];
+    BAIO& E = eff[i];
     const size_t nn = (size_t)ba->n * ba->n, P = ba->P;
     if (o.window) {
       const hslam_window* w = o.window;
+      TRY(window_scalars(ba, w));
       memcpy(B->h_up + L.up_precalc, w->precalc, nn * HSLAM_PRECALC_STRIDE * 4);
       memcpy(B->h_up + L.up_adHTd, w->adHTdeltaF, nn * 8 * 4);
       memcpy(B->h_up + L.up_adH, w->adHost, nn * 64 * 8);
       memcpy(B->h_up + L.up_adT, w->adTarget, nn * 64 * 8);
       memcpy(B->h_up + L.up_fprior, w->framePrior, (size_t)ba->n * 8 * 8);
       memcpy(B->h_up + L.up_fdprior, w->frameDeltaPrior, (size_t)ba->n * 8 * 8);
+      extent = std::max(extent, B->up_tab_end);
+    } else {
+      E.up_precalc = E.up_adHTd = E.up_adH = E.up_adT = E.up_fprior = E.up_fdprior = -1;
     }
-    if (o.idepth) memcpy(B->h_up + L.up_idepth, o.idepth, P * 4);
-    if (o.deltaF) memcpy(B->h_up + L.up_deltaF, o.deltaF, P * 4);
-    if (o.idepth_zero) memcpy(B->h_up + L.up_idz, o.idepth_zero, P * 4);
+    // a per-point input that already lives in its slot of the pinned block (hslam_ba_batch_io_bind) needs no copy
+    auto put = [&](const float* src, long long off, long long& eoff, size_t region_end) {
+      if (!src) { eoff = -1; return; }
+      if ((const char*)src != B->h_up + off) memcpy(B->h_up + off, src, P * 4);
+      extent = std::max(extent, region_end);
+    };
+    put(o.idepth, L.up_idepth, E.up_idepth, B->up_idepth_end);
+    put(o.deltaF, L.up_deltaF, E.up_deltaF, B->up_deltaF_end);
+    put(o.idepth_zero, L.up_idz, E.up_idz, B->up_end);
+    E.up_x = -1;
+    maxP = std::max(maxP, ba->P); maxR = std::max(maxR, ba->R);
   }
+  memcpy(B->h_up, eff.data(), n * sizeof(BAIO));   // the offset table leads the block
   TRY(batch_refresh(B));   // descriptors (only if a scalar changed) and block-prefix tables
-  HS_CUDA(cudaMemcpyAsync(B->d_up.p, B->h_up, up + io_bytes, cudaMemcpyHostToDevice, ctx->stream));
-  const BAIO* d_io = reinterpret_cast<const BAIO*>(B->d_up.p + up);
+  HS_CUDA(cudaMemcpyAsync(B->d_up.p, B->h_up, extent, cudaMemcpyHostToDevice, ctx->stream));
+  const BAIO* d_io = reinterpret_cast<const BAIO*>(B->d_up.p);
   {
     dim3 grid((unsigned)std::max(1, std::min(64, (maxP + 255) / 256)), (unsigned)n);
     HS_LAUNCH(ctx, HSLAM_K_BA_EXPORT, (ba_batch_import_kernel<<<grid, 256, 0, ctx->stream>>>(B->d_descs.p, d_io, B->d_up.p)));
@@ -1345,22 +1369,19 @@ int hslam_ba_batch_resubstitute_host(hslam_ba_batch* B, const double* const* x, 
   HS_CUDA(cudaSetDevice(ctx->device));
   const int n = (int)B->items.size();
   TRY(batch_layout_down(B));
-  size_t up = 0;
+  TRY(batch_layout_up(B));
+  std::vector<BAIO> eff(B->io);
   for (int i = 0; i < n; ++i) {
     hslam_ba* ba = B->items[i];
     HS_ARG(ba->have_window && ba->have_topology && x[i], "hslam_ba_batch_resubstitute_host: window not set or null x");
-    BAIO& L = B->io[i];
-    L.up_precalc = L.up_adHTd = L.up_adH = L.up_adT = L.up_fprior = L.up_fdprior = L.up_idepth = L.up_deltaF = L.up_idz = -1;
-    L.up_x = (long long)up; up = al256(up + (size_t)ba->N * 8);
+    BAIO& E = eff[i];
+    E.up_precalc = E.up_adHTd = E.up_adH = E.up_adT = E.up_fprior = E.up_fdprior = E.up_idepth = E.up_deltaF = E.up_idz = -1;
+    memcpy(B->h_up + E.up_x, x[i], (size_t)ba->N * 8);
   }
-  const size_t io_bytes = al256(n * sizeof(BAIO));
-  TRY(pinned_ensure(&B->h_up, &B->h_up_cap, up + io_bytes));
-  TRY(B->d_up.ensure(up + io_bytes));
-  memcpy(B->h_up + up, B->io.data(), n * sizeof(BAIO));
-  for (int i = 0; i < n; ++i) memcpy(B->h_up + B->io[i].up_x, x[i], (size_t)B->items[i]->N * 8);
+  memcpy(B->h_up, eff.data(), n * sizeof(BAIO));
   TRY(batch_refresh(B));
-  HS_CUDA(cudaMemcpyAsync(B->d_up.p, B->h_up, up + io_bytes, cudaMemcpyHostToDevice, ctx->stream));
-  const BAIO* d_io = reinterpret_cast<const BAIO*>(B->d_up.p + up);
+  HS_CUDA(cudaMemcpyAsync(B->d_up.p, B->h_up, B->up_tab_begin, cudaMemcpyHostToDevice, ctx->stream));   // offset table + x slots
+  const BAIO* d_io = reinterpret_cast<const BAIO*>(B->d_up.p);
   HS_LAUNCH(ctx, HSLAM_K_BA_EXPORT, (ba_batch_import_kernel<<<dim3(1, (unsigned)n), 256, 0, ctx->stream>>>(B->d_descs.p, d_io, B->d_up.p)));
   HS_LAUNCH(ctx, HSLAM_K_BA_RESUB, (ba_xad_kernel<<<n, 256, 0, ctx->stream>>>(B->d_descs.p)));
   if (B->blocks[5] > 0)

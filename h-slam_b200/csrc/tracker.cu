@@ -100,6 +100,11 @@ __device__ __forceinline__ void eval_block(const EvalConst& c, float* __restrict
   int nE = 0, nSat = 0, nW = 0;
   const float wm3 = (float)(c.w - 3), hm3 = (float)(c.h - 3);
 
+#ifndef TRK_UNROLL
+#define TRK_UNROLL 1
+#endif
+  constexpr int kUnroll = TRK_UNROLL;
+#pragma unroll kUnroll
   for (int i = block * THREADS + threadIdx.x; i < c.n; i += nblocks * THREADS) {
     float4 p = __ldg(c.pc + i);
     float x = p.x, y = p.y, id = p.z, refColor = p.w;

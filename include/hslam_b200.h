@@ -365,8 +365,10 @@ typedef struct hslam_ba_step_io {
   int32_t* nres2;                  /* {resInA, resInL} */
 } hslam_ba_step_io;
 int hslam_ba_batch_step_host(hslam_ba_batch* batch, const hslam_ba_step_io* io /* one per window */);
-/* Zero-copy outputs: point every OUTPUT member of io[0..count) (and step_out[i], if not null) at the window's
- * slot in the batch's own page-locked result block.  Results then arrive with two bulk copies per call and
+/* Zero-copy buffers: point every OUTPUT member of io[0..count) (and step_out[i], if not null) at the window's
+ * slot in the batch's own page-locked result block, and the per-point INPUT members idepth / deltaF at their slots
+ * of the page-locked upload block (the caller writes the new point state there in place; idepth_zero is set to
+ * null = unchanged).  Results then arrive with two bulk copies per call and
  * no per-array work; the caller reads them in place (e.g. Eigen::Map).  The pointers stay valid until a
  * member's topology changes or the batch is destroyed. */
 int hslam_ba_batch_io_bind(hslam_ba_batch* batch, hslam_ba_step_io* io, float** step_out /*nullable*/);
