@@ -366,6 +366,47 @@ def extras(ctx, capi, synth, torch, stream, ef0, win0):
         frame.update(tp.img_new)                                   # H2D 1.2 MB + 5-level pyramid
         trk.trackNewestCoarse(frame, T0, (0.0, 0.0), tp.levels - 1)  # LM on device + D2H of the result
     out["tracking_ms_per_frame_e2e"] = 1e3 * (time.perf_counter() - t0) / reps
+    # §8(f) rows that run per frame / per keyframe: immature-point tracing and activation, reference-cloud build
+    try:
+        import copy
+        kf = synth.render_keyframes(640, 480, 7, seed=78)
+        hosts = [0, 1, 2, 3, 4]
+        ims = synth.make_immature_points(kf, hosts=hosts, points_per_host=2000, seed=5)
+        synth.trace_tables(kf, hosts, 5, ims)
+        fr5 = capi.Frame(ctx, kf.images[5], 1)
+        base = copy.deepcopy(ims)
+        capi.traceNewCoarse(ctx, fr5, copy.deepcopy(base))
+        t0 = time.perf_counter()
+        for _ in range(5):
+            work = copy.deepcopy(base)
+            capi.traceNewCoarse(ctx, fr5, work)
+        out["trace_ms_per_frame_e2e"] = 1e3 * (time.perf_counter() - t0) / 5
+        out["trace_points"] = int(len(base.u))
+        synth.trace_tables(kf, hosts, 6, work)
+        fr6 = capi.Frame(ctx, kf.images[6], 1)
+        capi.traceNewCoarse(ctx, fr6, work)
+        keep = np.nonzero(np.isfinite(work.idepth_max) & (work.status != 1))[0]
+        for k in ("host_idx", "u", "v", "gradH", "color", "weights", "energyTH", "idepth_min", "idepth_max"):
+            setattr(work, k, np.ascontiguousarray(getattr(work, k)[keep]))
+        frames7 = [capi.Frame(ctx, im, 1) for im in kf.images]
+        T = synth.activation_tables(kf)
+        capi.optimizeImmaturePoints(ctx, frames7, kf.cam, T, work, minObs=2)
+        t0 = time.perf_counter()
+        for _ in range(5):
+            ok_, _, _ = capi.optimizeImmaturePoints(ctx, frames7, kf.cam, T, work, minObs=2)
+        out["activation_ms_e2e"] = 1e3 * (time.perf_counter() - t0) / 5
+        out["activation_candidates"] = int(len(keep)); out["activation_accepted"] = int(ok_.sum())
+        prof0 = ctx.profile_read() if False else None
+        ctx.profile_enable(True)
+        capi.traceNewCoarse(ctx, fr5, copy.deepcopy(base))
+        capi.optimizeImmaturePoints(ctx, frames7, kf.cam, T, work, minObs=2)
+        pr = ctx.profile_read(); ctx.profile_enable(False)
+        if "trace" in pr:
+            out["trace_plus_activation_kernels_ms_device"] = pr["trace"][0]
+        for f_ in frames7 + [fr5, fr6]:
+            f_.close()
+    except Exception as e:   # measurement extras must not take the bench line down
+        out["trace_error"] = repr(e)
     out["tracking_iterations"] = [int(i) for i in trk.iterations]
     out["tracking_points_per_level"] = [int(len(p[0])) for p in tp.pc]
     trk.close(); frame.close()
