@@ -16,6 +16,7 @@
 #include <cstring>
 #include <functional>
 #include <dlfcn.h>
+#include <cstdlib>
 
 using namespace hs;
 
@@ -1023,6 +1024,10 @@ struct hslam_ba_batch {
   DevBuf<char> d_up, d_dn;
   DevBuf<BAIO> d_io;
   std::vector<BAIO> io;
+  // CUDA graph of the launch chain (re-captured when batch_refresh changes a launch parameter)
+  cudaGraphExec_t graph_iter = nullptr, graph_acc = nullptr;
+  uint64_t refresh_version = 1, graph_iter_version = 0, graph_acc_version = 0;
+  int graph_iter_kernels = 0, graph_acc_kernels = 0;
   size_t up_tab_begin = 0, up_tab_end = 0, up_idepth_end = 0, up_deltaF_end = 0, up_end = 0;   // H2D block regions
   size_t dn_res_end = 0, dn_sys_end = 0, dn_end = 0;   // D2H block regions: [0,res) per-residual arrays, [res,sys) systems, [sys,end) steps
 };
@@ -1067,6 +1072,7 @@ static int batch_refresh(hslam_ba_batch* B) {
   HS_CUDA(cudaMemcpyAsync(B->d_descs.p, B->h_descs, n * sizeof(BADesc), cudaMemcpyHostToDevice, B->ctx->stream));
   HS_CUDA(cudaMemcpyAsync(B->d_prefix.p, B->h_prefix, NPF * (n + 1) * sizeof(int), cudaMemcpyHostToDevice, B->ctx->stream));
   HS_CUDA(cudaEventRecord(B->copied, B->ctx->stream));
+  B->refresh_version++;
   return 0;
 }
 
@@ -1105,6 +1111,8 @@ int hslam_ba_batch_destroy(hslam_ba_batch* B) {
   if (B->h_up) cudaFreeHost(B->h_up);
   if (B->h_dn) cudaFreeHost(B->h_dn);
   cudaEventDestroy(B->copied);
+  if (B->graph_iter) cudaGraphExecDestroy(B->graph_iter);
+  if (B->graph_acc) cudaGraphExecDestroy(B->graph_acc);
   delete B;
   return 0;
 }
@@ -1136,12 +1144,47 @@ static int batch_enqueue_accumulate(hslam_ba_batch* B) {
   return 0;
 }
 
+// The launch chain as a CUDA graph: one graph launch per iteration instead of 4-6 kernel launches (shorter gaps between
+// the kernels on the device, one driver call on the host).  Bypassed while per-kernel event profiling is on.
+static int batch_graph_launch(hslam_ba_batch* B, bool with_linearize) {
+  hslam_ctx* ctx = B->ctx;
+  cudaGraphExec_t& exec = with_linearize ? B->graph_iter : B->graph_acc;
+  uint64_t& ver = with_linearize ? B->graph_iter_version : B->graph_acc_version;
+  int& nk = with_linearize ? B->graph_iter_kernels : B->graph_acc_kernels;
+  static const bool disabled = getenv("HSLAM_NO_GRAPH") != nullptr;
+  if (ctx->profile || disabled) {
+    if (with_linearize) TRY(batch_enqueue_linearize(B));
+    return batch_enqueue_accumulate(B);
+  }
+  if (!exec || ver != B->refresh_version) {
+    TRY(schur_attr(B->smem));
+    TRY(top_attr());
+    if (exec) { cudaGraphExecDestroy(exec); exec = nullptr; }
+    const int64_t l0 = ctx->launches;
+    HS_CUDA(cudaStreamBeginCapture(ctx->stream, cudaStreamCaptureModeThreadLocal));
+    int rc = 0;
+    if (with_linearize) rc = batch_enqueue_linearize(B);
+    if (!rc) rc = batch_enqueue_accumulate(B);
+    cudaGraph_t g = nullptr;
+    cudaError_t e = cudaStreamEndCapture(ctx->stream, &g);
+    if (rc) { if (g) cudaGraphDestroy(g); return rc; }
+    HS_CUDA(e);
+    nk = (int)(ctx->launches - l0);
+    ctx->launches = l0;
+    HS_CUDA(cudaGraphInstantiate(&exec, g, 0));
+    cudaGraphDestroy(g);
+    ver = B->refresh_version;
+  }
+  HS_CUDA(cudaGraphLaunch(exec, ctx->stream));
+  ctx->launches += nk;
+  return 0;
+}
+
 int hslam_ba_batch_iteration(hslam_ba_batch* B) {
   HS_ARG(B, "hslam_ba_batch_iteration: null");
   HS_CUDA(cudaSetDevice(B->ctx->device));
   TRY(batch_refresh(B));
-  TRY(batch_enqueue_linearize(B));
-  return batch_enqueue_accumulate(B);
+  return batch_graph_launch(B, true);
 }
 
 // ---- host-buffer API of a batch: one staging block up, one down per call ------------------------------
@@ -1344,7 +1387,7 @@ int hslam_ba_batch_step_host(hslam_ba_batch* B, const hslam_ba_step_io* io) {
     if (bulk_res) HS_CUDA(cudaMemcpyAsync(B->h_dn, B->d_dn.p, B->dn_res_end, cudaMemcpyDeviceToHost, ctx->side));
     HS_CUDA(cudaEventRecord(ctx->ev_join, ctx->side));
   }
-  TRY(batch_enqueue_accumulate(B));
+  TRY(batch_graph_launch(B, false));
   if (any_sys) {
     HS_LAUNCH(ctx, HSLAM_K_BA_EXPORT, (ba_batch_export_kernel<<<dim3(2, (unsigned)n), 256, 0, ctx->stream>>>(B->d_descs.p, d_io, B->d_dn.p, 2)));
     HS_CUDA(cudaGetLastError());
