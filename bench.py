@@ -123,7 +123,8 @@ def main():
     ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--windows", type=int, default=8, help="independent windows per GPU per step")
+    ap.add_argument("--windows", type=int, default=64,
+                    help="independent windows per GPU per step (BASELINE.json configs[4]: 'batched 64 independent synthetic windows')")
     ap.add_argument("--mode", default="batched", choices=["batched", "sharded"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-extras", action="store_true", help="skip the tracking / single-window latency figures (profiling runs)")

@@ -86,3 +86,31 @@ def test_two_million_residual_window_properties(ctx, capi, synth):
         assert rel_fro(acc, full) < 1e-6, world
     for f in frames:
         f.close()
+
+
+def test_config5_batch_of_64_windows_matches_singles(ctx, capi, synth):
+    """configs[4]: 64 independent windows stepped as ONE batch (five launches, one graph) == each window stepped alone
+    with the same chunking, bit for bit (reduced window size: the property is size-independent)."""
+    kf = [synth.render_keyframes(320, 240, 5, seed=60 + s) for s in range(2)]
+    frames = [[capi.Frame(ctx, im, 1) for im in k.images] for k in kf]
+    wins = [synth.make_window(points_per_frame=60 + (i % 7) * 11, seed=500 + i, keyframes=kf[i % 2])[0] for i in range(64)]
+    batched, singles = [], []
+    for i, w in enumerate(wins):
+        b = capi.EnergyFunctional(ctx); b.set_window(w, frames[i % 2]); b.set_topology(w); batched.append(b)
+    batch = capi.EnergyFunctionalBatch(ctx, batched)
+    for _ in range(2):
+        batch.iteration()
+    for i in (0, 1, 17, 40, 63):
+        a = capi.EnergyFunctional(ctx); a.set_window(wins[i], frames[i % 2]); a.set_topology(wins[i])
+        a.set_parallelism(batched[i].get_parallelism())
+        for _ in range(2):
+            a.iteration_device()
+        for (H1, b1), (H2, b2) in zip(a.download_Hb(), batched[i].download_Hb()):
+            assert np.array_equal(H1, H2) and np.array_equal(b1, b2), i
+        singles.append(a)
+    batch.close()
+    for e in batched + singles:
+        e.close()
+    for fl in frames:
+        for f in fl:
+            f.close()

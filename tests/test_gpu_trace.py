@@ -68,3 +68,27 @@ def test_activation_bit_exact(ctx, capi, O, synth):
     assert 0.3 < g[0].mean() < 1.0 and len(keep) > 2000
     for f in frames:
         f.close()
+
+
+def test_trace_and_activation_empty_and_all_oob(ctx, capi, synth):
+    """Edge cases: no points at all; every point already OOB (traceOn returns at once and leaves every member untouched)."""
+    kf = synth.render_keyframes(160, 120, 3, seed=2)
+    ims = synth.make_immature_points(kf, hosts=[0], points_per_host=50, seed=5)
+    synth.trace_tables(kf, [0], 1, ims)
+    frame = capi.Frame(ctx, kf.images[1], 1)
+    empty = copy.deepcopy(ims)
+    for k in ("host_idx", "u", "v", "gradH", "color", "weights", "energyTH", "idepth_min", "idepth_max", "quality", "status",
+              "lastTraceUV", "lastTracePixelInterval"):
+        setattr(empty, k, getattr(ims, k)[:0].copy())
+    capi.traceNewCoarse(ctx, frame, empty)                       # n = 0: no launch, no error
+    oob = copy.deepcopy(ims)
+    oob.status[:] = 1
+    before = copy.deepcopy(oob)
+    capi.traceNewCoarse(ctx, frame, oob)
+    for k in ("status", "idepth_min", "quality", "lastTraceUV", "lastTracePixelInterval"):
+        assert np.array_equal(getattr(oob, k), getattr(before, k), equal_nan=True), k
+    frames = [capi.Frame(ctx, im, 1) for im in kf.images]
+    ok, idp, st = capi.optimizeImmaturePoints(ctx, frames, kf.cam, synth.activation_tables(kf), empty)
+    assert len(ok) == 0 and st.shape == (0, 3)
+    for f in frames + [frame]:
+        f.close()
