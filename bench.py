@@ -303,7 +303,8 @@ def extras(ctx, capi, synth, torch, stream, ef0, win0):
     """Latency figures of the other two headline quantities: BA ms/window and tracking ms/frame."""
     out = {}
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    # BA: one window, one GN iteration, device time
+    # BA: one window, one GN iteration, device time (with the chunking of a window that runs alone, not the batch's)
+    ef0.set_parallelism(0)
     for _ in range(3):
         ef0.iteration_device()
     ctx.synchronize()

@@ -20,6 +20,8 @@
 
 using namespace hs;
 
+int hs_frame_ensure_pair(hslam_frame* f);   // pyramid.cu
+
 template <class T> struct DevBuf {
   T* p = nullptr;
   size_t cap = 0;
@@ -429,7 +431,9 @@ int hslam_ba_set_window(hslam_ba* ba, const hslam_window* w) {
   for (int f = 0; f < n; ++f) {
     HS_ARG(w->frames[f] && w->frames[f]->ctx == ctx, "hslam_ba_set_window: frame missing or from another context");
     HS_ARG(w->frames[f]->w == w->w && w->frames[f]->h == w->h, "hslam_ba_set_window: frame size mismatch");
+    TRY(hs_frame_ensure_pair(const_cast<hslam_frame*>(w->frames[f])));   // lazily built cache of the frame
     W.img[f] = w->frames[f]->dI[0];
+    W.pimg[f] = w->frames[f]->pair0;
     W.frameEnergyTH[f] = w->frameEnergyTH[f];
   }
   size_t nn = (size_t)n * n;
@@ -1211,7 +1215,9 @@ static int window_scalars(hslam_ba* ba, const hslam_window* w) {
   for (int f = 0; f < ba->n; ++f) {
     HS_ARG(w->frames[f] && w->frames[f]->ctx == ctx, "hslam_ba_batch_step_host: frame missing or from another context");
     HS_ARG(w->frames[f]->w == w->w && w->frames[f]->h == w->h, "hslam_ba_batch_step_host: frame size mismatch");
+    TRY(hs_frame_ensure_pair(const_cast<hslam_frame*>(w->frames[f])));
     W.img[f] = w->frames[f]->dI[0];
+    W.pimg[f] = w->frames[f]->pair0;
     W.frameEnergyTH[f] = w->frameEnergyTH[f];
   }
   StitchArgs S = ba->hdesc.S;

@@ -25,11 +25,14 @@ namespace hs {
 constexpr int JS = 80;                 // floats per residual row: 74 of RawResidualJacobian + JI_r(2) Jab_r(2) rr(1) + pad
 constexpr int J_RESF = 0, J_XI0 = 8, J_XI1 = 14, J_C0 = 20, J_C1 = 24, J_DD = 28, J_IDX0 = 30, J_IDX1 = 38,
               J_AB0 = 46, J_AB1 = 54, J_IDX2 = 62, J_ABIDX = 66, J_AB2 = 70, J_JIR = 74, J_JABR = 76, J_RR = 78;
+// Lineariser launch shape, measured on B200 with the pair-image gather (64 cfg2 windows = 5.4 M residuals per launch):
+//   64 threads x 8 blocks/SM (128 regs, no spills) 1015 us | 64 x 10 (96 regs) 1028 | 32 x 20 1026 | 128 x 5 1041 | 128 x 4 1047
+//   64 x 9 / 96 x 7 (spills) 1180.   With the float4 image (four 16-byte loads per tap): 128 x 6 (80 regs) 1094, 64 x 12 1081.
 #ifndef LIN_MINB
-#define LIN_MINB 6   /* measured on B200: 3 -> 209 us, 4 -> 185, 5 -> 176, 6 -> 170, 8 -> 189 per 672k residuals */
+#define LIN_MINB 8
 #endif
 #ifndef LIN_THREADS_
-#define LIN_THREADS_ 128
+#define LIN_THREADS_ 64
 #endif
 constexpr int LIN_THREADS = LIN_THREADS_;
 // Streaming (evict-first) stores for the big per-residual output streams: they are written once per
@@ -60,6 +63,7 @@ struct BAWin {
   float huber, outlierTH, scale_idepth, scale_f, scale_c, affA, affB;
   float cDeltaF[4];
   const float4* img[HSLAM_MAX_FRAMES];
+  const float4* pimg[HSLAM_MAX_FRAMES];   // level-0 pair images (hslam_frame::pair0): what the lineariser gathers from
   float frameEnergyTH[HSLAM_MAX_FRAMES];
   const float* precalc;      // n*n*28
   const float* adHTdeltaF;   // n*n*8
@@ -327,12 +331,21 @@ __global__ void __launch_bounds__(LIN_THREADS, LIN_MINB) ba_linearize_kernel(con
           // they are never read for an OOB residual, so they are left untouched here.
         } else {
           // Pass 2: all 32 texel loads in flight at once.
+#ifndef LIN_PAIR_IMAGE
+#define LIN_PAIR_IMAGE 1
+#endif
+#if LIN_PAIR_IMAGE
+          const float4* img = W.pimg[tgtI];
+#else
           const float4* img = W.img[tgtI];
+#endif
           Hit3 hit[8];
           const uint64_t pol = l2_keep_policy();
 #pragma unroll
 #ifdef LIN_EXP_NOGATHER   /* timing experiment only: every gather hits the same few texels */
           for (int idx = 0; idx < 8; ++idx) hit[idx] = interp33<HS_TEXEL_L2_KEEP != 0>(img, 8.25f + idx, 8.5f, W.w, pol);
+#elif LIN_PAIR_IMAGE
+          for (int idx = 0; idx < 8; ++idx) hit[idx] = interp33_pair(img, Kup[idx], Kvp[idx], W.w, pol);
 #else
           for (int idx = 0; idx < 8; ++idx) hit[idx] = interp33<HS_TEXEL_L2_KEEP != 0>(img, Kup[idx], Kvp[idx], W.w, pol);
 #endif

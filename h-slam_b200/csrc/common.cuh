@@ -60,6 +60,15 @@ __device__ __forceinline__ float4 ldg_keep(const float4* p, uint64_t pol) {
       : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "l"(p), "l"(pol));
   return v;
 }
+// 256-bit load (sm_100: LDG.E.256) of one record of the level-0 PAIR image: {I,dx,dy}(x,y) | {I,dx,dy}(x+1,y) | 2 pads.
+struct Pair8 { float4 a, b; };
+__device__ __forceinline__ Pair8 ldg_pair_keep(const float4* p, uint64_t pol) {
+  Pair8 v;
+  asm("ld.global.nc.L2::cache_hint.v8.f32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8], %9;"
+      : "=f"(v.a.x), "=f"(v.a.y), "=f"(v.a.z), "=f"(v.a.w), "=f"(v.b.x), "=f"(v.b.y), "=f"(v.b.z), "=f"(v.b.w)
+      : "l"(p), "l"(pol));
+  return v;
+}
 #ifndef HS_TEXEL_L2_KEEP
 #define HS_TEXEL_L2_KEEP 1
 #endif
@@ -82,6 +91,24 @@ __device__ __forceinline__ Hit3 interp33(const float4* __restrict__ img, float x
   h.I = xadd(xadd(xadd(xmul(wBR, br.x), xmul(wBL, bl.x)), xmul(wTR, tr.x)), xmul(wTL, tl.x));
   h.dx = xadd(xadd(xadd(xmul(wBR, br.y), xmul(wBL, bl.y)), xmul(wTR, tr.y)), xmul(wTL, tl.y));
   h.dy = xadd(xadd(xadd(xmul(wBR, br.z), xmul(wBL, bl.z)), xmul(wTR, tr.z)), xmul(wTL, tl.z));
+  return h;
+}
+
+// The same interpolation on the PAIR image (32 bytes per pixel, see hslam_frame::pair0): the two texels of a row arrive
+// in ONE 256-bit load, so a bilinear tap is two loads instead of four (half the load instructions and L1 wavefronts of the
+// gather, every load exactly one 32-byte sector).  Same arithmetic, bit-identical result.
+__device__ __forceinline__ Hit3 interp33_pair(const float4* __restrict__ pimg, float x, float y, int width, uint64_t pol) {
+  int ix = (int)x, iy = (int)y;
+  float dx = xsub(x, (float)ix), dy = xsub(y, (float)iy);
+  float dxdy = xmul(dx, dy);
+  const float4* bp = pimg + 2 * ((size_t)ix + (size_t)iy * width);
+  const Pair8 top = ldg_pair_keep(bp, pol), bot = ldg_pair_keep(bp + 2 * (size_t)width, pol);
+  float wBR = dxdy, wBL = xsub(dy, dxdy), wTR = xsub(dx, dxdy);
+  float wTL = xadd(xsub(xsub(1.0f, dx), dy), dxdy);
+  Hit3 h;
+  h.I = xadd(xadd(xadd(xmul(wBR, bot.a.w), xmul(wBL, bot.a.x)), xmul(wTR, top.a.w)), xmul(wTL, top.a.x));
+  h.dx = xadd(xadd(xadd(xmul(wBR, bot.b.x), xmul(wBL, bot.a.y)), xmul(wTR, top.b.x)), xmul(wTL, top.a.y));
+  h.dy = xadd(xadd(xadd(xmul(wBR, bot.b.y), xmul(wBL, bot.a.z)), xmul(wTR, top.b.y)), xmul(wTL, top.a.z));
   return h;
 }
 
@@ -153,6 +180,7 @@ struct hslam_frame {
   int w = 0, h = 0, levels = 0;
   float4* dI[HSLAM_MAX_PYR_LEVELS] = {nullptr};  // {I,dx,dy,absSquaredGrad} per pixel
   float4* base = nullptr;                        // one allocation for all levels
+  float4* pair0 = nullptr;                       // level-0 PAIR image (2 float4 per pixel), built on first use by a BA window
   float* staging = nullptr;                      // device copy of the input image (H2D target)
   float* gamma = nullptr;                        // 256-entry BGrad table or null
   float* pinned = nullptr;                       // pinned host staging for async H2D

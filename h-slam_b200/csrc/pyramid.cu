@@ -52,6 +52,16 @@ __global__ void __launch_bounds__(256) pyramid_level_kernel(const float* __restr
   }
 }
 
+// level-0 pair image: per pixel {I,dx,dy}(x) | {I,dx,dy}(x+1) | 2 pads  (the last column repeats itself; never sampled)
+__global__ void pair_image_kernel(const float4* __restrict__ in, float4* __restrict__ out, int w, int h) {
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < w * h; i += gridDim.x * blockDim.x) {
+    const float4 a = in[i];
+    const float4 b = ((i % w) + 1 < w) ? in[i + 1] : a;
+    out[2 * (size_t)i] = make_float4(a.x, a.y, a.z, b.x);
+    out[2 * (size_t)i + 1] = make_float4(b.y, b.z, 0.f, 0.f);
+  }
+}
+
 int build_pyramid(hslam_frame* f, const float* img_dev) {
   hslam_ctx* ctx = f->ctx;
   for (int l = 0; l < f->levels; ++l) {
@@ -66,6 +76,8 @@ int build_pyramid(hslam_frame* f, const float* img_dev) {
       HS_LAUNCH(ctx, HSLAM_K_PYRAMID, (pyramid_level_kernel<false><<<blocks, 256, 0, ctx->stream>>>(
                                           nullptr, f->dI[l - 1], f->dI[l], wl, hl, f->w >> (l - 1), f->gamma)));
   }
+  if (f->pair0)   // a BA window uses this frame: keep its pair image in step with the pyramid
+    HS_LAUNCH(ctx, HSLAM_K_PYRAMID, (pair_image_kernel<<<ctx->sm_count * 8, 256, 0, ctx->stream>>>(f->dI[0], f->pair0, f->w, f->h)));
   HS_CUDA(cudaGetLastError());
   return 0;
 }
@@ -141,6 +153,19 @@ int hslam_frame_create_from_device(hslam_ctx* ctx, const float* img_dev, int w, 
   return hslam_frame_update(*out, img_dev, 1);
 }
 
+}  // extern "C"
+// Internal: make sure the frame has its level-0 pair image (allocated and built on the frame's context stream).
+int hs_frame_ensure_pair(hslam_frame* f) {
+  if (f->pair0) return 0;
+  hslam_ctx* ctx = f->ctx;
+  HS_CUDA(cudaSetDevice(ctx->device));
+  HS_CUDA(cudaMalloc(&f->pair0, (size_t)f->w * f->h * 2 * sizeof(float4)));
+  HS_LAUNCH(ctx, HSLAM_K_PYRAMID, (pair_image_kernel<<<ctx->sm_count * 8, 256, 0, ctx->stream>>>(f->dI[0], f->pair0, f->w, f->h)));
+  HS_CUDA(cudaGetLastError());
+  return 0;
+}
+extern "C" {
+
 int hslam_frame_level_size(hslam_frame* f, int lvl, int* w, int* h) {
   HS_ARG(f && lvl >= 0 && lvl < f->levels, "hslam_frame_level_size: bad level");
   if (w) *w = f->w >> lvl;
@@ -170,6 +195,7 @@ int hslam_frame_destroy(hslam_frame* f) {
   cudaSetDevice(f->ctx->device);
   cudaStreamSynchronize(f->ctx->stream);
   cudaFree(f->base);
+  if (f->pair0) cudaFree(f->pair0);
   cudaFree(f->staging);
   cudaFree(f->gamma);
   cudaFreeHost(f->pinned);
