@@ -1093,7 +1093,11 @@ int hslam_ba_batch_create(hslam_ctx* ctx, hslam_ba* const* items, int count, hsl
   }
   // the members share the SMs: fewer, larger chunks per window (~3 waves of blocks for the whole batch)
   for (int i = 0; i < count; ++i)
-    if (items[i]->target_blocks == 0) TRY(hslam_ba_set_parallelism(items[i], std::max(8, 2 * ctx->sm_count / count)));
+    if (items[i]->target_blocks == 0) {
+      int tb = std::max(4, 4 * ctx->sm_count / count);   // ~two full waves of the 2-blocks-per-SM kernels for the whole batch
+      if (const char* e = getenv("HSLAM_BATCH_BLOCKS")) tb = std::max(1, atoi(e));   // tuning override
+      TRY(hslam_ba_set_parallelism(items[i], tb));
+    }
   B->versions.assign(count, 0);
   TRY(B->d_descs.ensure(count));
   TRY(B->d_prefix.ensure(NPF * (size_t)(count + 1)));
