@@ -300,6 +300,11 @@ static int build_chunks(hslam_ba* ba) {
 #endif
     int sc_blocks = SC_BLOCKS_NUM * target_blocks / SC_BLOCKS_DEN;
     if (sc_blocks > 4 * n) sc_blocks -= n;
+    // batched windows: measured (64 x config-2 windows) the Schur launch keeps gaining down to ~6 chunk waves for
+    // the whole batch (finer chunks balance the 3-blocks-per-SM kernel; below that the fold cost grows)
+    // An explicit target (set_parallelism) asks for 9/2 x as many Schur chunks as top blocks.
+    if (ba->target_blocks > 0) sc_blocks = std::min(9 * ba->target_blocks / 2, std::max(n, total_sub / 2));
+    if (const char* e = getenv("HSLAM_SC_BLOCKS")) sc_blocks = atoi(e);   // tuning override (per window)
     if (sc_blocks < 1) sc_blocks = 1;
     const int q = std::max(1, (total_sub + sc_blocks - 1) / sc_blocks);   // sub-tiles per chunk
     std::vector<PtChunk> ch;

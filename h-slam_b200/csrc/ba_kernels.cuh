@@ -237,6 +237,23 @@ __global__ void __launch_bounds__(LIN_THREADS, LIN_MINB) ba_linearize_kernel(con
   const int8_t st0 = valid ? r.state_state[k] : (int8_t)HSLAM_RES_OOB;
   const float old_energy = valid ? r.state_energy[k] : 0.f;
   const int p = valid ? r.point[k] : 0, pair = valid ? r.pair[k] : 0;
+#ifndef LIN_PF
+#define LIN_PF 0
+#endif
+#if LIN_PF > 0
+  // the per-residual index/state streams of the blocks one residency-wave ahead are pulled into L2 now, so that
+  // their first (dependent) round trip is an L2 hit when those blocks start
+  if (k + LIN_PF < r.R) {
+    const int kp = k + LIN_PF;
+    asm volatile("prefetch.global.L2 [%0];" ::"l"(r.point + kp));
+    asm volatile("prefetch.global.L2 [%0];" ::"l"(r.pair + kp));
+    asm volatile("prefetch.global.L2 [%0];" ::"l"(r.state_energy + kp));
+    if ((threadIdx.x & 3) == 0) {
+      asm volatile("prefetch.global.L2 [%0];" ::"l"(r.state_state + kp));
+      asm volatile("prefetch.global.L2 [%0];" ::"l"(r.isLin + kp));
+    }
+  }
+#endif
   if (valid && !lin) {
     float* J = r.J + k;
     STJ(r.newEnergyWO + k, -1.f);
@@ -641,6 +658,34 @@ __device__ __forceinline__ void cp_async4(void* smem_dst, const void* gsrc) {
 __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
 template <int N> __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
 
+// ---- mbarrier + bulk-copy (TMA engine, no tensor map: rows are contiguous) primitives of the top kernel's ring
+__device__ __forceinline__ unsigned smem_u32(const void* p) { return (unsigned)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint64_t* b, unsigned count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(b)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* b, unsigned bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(b)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t* b) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(b)) : "memory");
+}
+__device__ __forceinline__ bool mbar_try_wait(uint64_t* b, unsigned parity) {
+  unsigned ok;
+  asm volatile("{\n .reg .pred p;\n mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n selp.u32 %0, 1, 0, p;\n}"
+               : "=r"(ok) : "r"(smem_u32(b)), "r"(parity) : "memory");
+  return ok != 0;
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* b, unsigned parity) {
+  if (mbar_try_wait(b, parity)) return;
+  const long long t0 = clock64();
+  while (!mbar_try_wait(b, parity))
+    if (clock64() - t0 > 4000000000LL) __trap();   // a protocol bug must fail the launch, not hang the device
+}
+__device__ __forceinline__ void bulk_g2s(void* dst, const void* src, unsigned bytes, uint64_t* bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+               ::"r"(smem_u32(dst)), "l"(src), "r"(bytes), "r"(smem_u32(bar)) : "memory");
+}
+
 // Staging ring of the top kernel.  A tile starts anywhere in the sorted array (pair segments are not
 // aligned), cp.async wants 16-byte-aligned sources: the ring rows hold the 4-aligned span that covers the
 // tile, [start & ~3, start + count) rounded up, at most 128 + 3 + 3 -> TOP_ROW columns; residual l of the tile
@@ -740,6 +785,75 @@ __global__ void __launch_bounds__(2 * TOP_THREADS, 2) ba_top_kernel(const BADesc
   for (int i = 0; i < 55; ++i) acc[i] = 0.f;
   int nres = 0, cur = -1;
 
+#ifndef TOP_BULK
+#define TOP_BULK 1
+#endif
+#if TOP_BULK
+  // Mode A: the 39 component rows of a tile are 39 contiguous 544-byte spans of the SoA Jacobian: one bulk copy
+  // (TMA engine) each, completing on the stage's `full` mbarrier.  The warps take turns as producer (warp j & 7
+  // issues tile j + TOP_DEPTH, lanes in parallel), every warp releases a stage on its `empty` mbarrier when it has
+  // read its residuals: no block-wide barrier in the tile loop, a warp only ever waits for data.
+#ifndef TOP_DEPTH_
+#define TOP_DEPTH_ (TOP_STAGES - 2)
+#endif
+  constexpr int TOP_DEPTH = TOP_DEPTH_;   // S-2: the refilled stage was consumed two tiles ago, its release is old news
+  constexpr int NW = 2 * TOP_THREADS / 32;
+  __shared__ __align__(8) uint64_t full_bar[TOP_STAGES], empty_bar[TOP_STAGES];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  if (mode == 0) {
+    if (threadIdx.x == 0) {
+#pragma unroll
+      for (int i = 0; i < TOP_STAGES; ++i) { mbar_init(&full_bar[i], 1); mbar_init(&empty_bar[i], NW); }
+      asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+      asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    }
+    __syncthreads();
+  }
+  auto produce = [&](int jp) {   // called by one whole warp
+    const int tp = t0 + jp;
+    if (tp >= t1) return;
+    const int stg = jp % TOP_STAGES, use = jp / TOP_STAGES;
+    if (use > 0) mbar_wait(&empty_bar[stg], (unsigned)(use - 1) & 1u);
+    if (lane == 0) mbar_expect_tx(&full_bar[stg], TOP_NC * TOP_ROW * 4);
+    __syncwarp();
+    const TopTile tlp = D.toptiles[tp];
+    const float* src = r.J + (tlp.start & ~3);
+    TopStage& st = ring[stg];
+    for (int c = lane; c < TOP_NC; c += 32) bulk_g2s(&st.v[c][0], src + (size_t)top_comp(c) * s, TOP_ROW * 4, &full_bar[stg]);
+  };
+  if (mode == 0 && warp == 0) {
+#pragma unroll
+    for (int i = 0; i < TOP_DEPTH; ++i) produce(i);
+  }
+
+  for (int t = t0; t < t1; ++t) {
+    const TopTile tl = D.toptiles[t];
+    const int j = t - t0;
+    const int chunk = tl.chunk + (mode ? 1 : 0) * D.top_chunks0;   // modes 1 and 2 share the second accumulator set
+    if (chunk != cur) {
+      if (cur >= 0) {
+        top_flush(D, cur, part, acc, nres, red, &last);
+#pragma unroll
+        for (int i = 0; i < 55; ++i) acc[i] = 0.f;
+        nres = 0;
+      }
+      cur = chunk;
+    }
+    if (mode != 0) {
+      const TopChunk ch = {D.topchunks[chunk].pair, tl.start, tl.count, 1};
+      if (part == 0) top_accumulate<(MODE ? MODE : 1), 0>(D, ch, acc, nres); else top_accumulate<(MODE ? MODE : 1), 1>(D, ch, acc, nres);
+      continue;
+    }
+    // the residual's flags come straight from global memory, issued before the wait
+    unsigned char f_lin = 1, f_act = 0;
+    if (l < tl.count) { f_lin = r.isLin[tl.start + l]; f_act = r.isActive[tl.start + l]; }
+    if (warp == (j & (NW - 1))) produce(j + TOP_DEPTH);
+    mbar_wait(&full_bar[j % TOP_STAGES], (unsigned)(j / TOP_STAGES) & 1u);
+    const TopStage& S = ring[j % TOP_STAGES];
+    const int col = (tl.start & 3) + l;
+    // AccumulatedTopHessian.cpp:37-49, mode 0: !isLinearized && isActive
+    if (f_lin == 0 && f_act != 0) {
+#else
   // all 256 threads: 39 rows x 34 sixteen-byte copies (always the full row: constant trip count and constant
   // divisor; the columns past the tile are never read) + the two flag rows; one commit group per tile
   constexpr int RQ = TOP_ROW / 4;
@@ -788,6 +902,7 @@ __global__ void __launch_bounds__(2 * TOP_THREADS, 2) ba_top_kernel(const BADesc
     const int col = (tl.start & 3) + l;
     // AccumulatedTopHessian.cpp:37-49, mode 0: !isLinearized && isActive
     if (l < tl.count && S.lin[col] == 0 && S.act[col] != 0) {
+#endif
       float x[10], y[10];
 #pragma unroll
       for (int j = 0; j < 4; ++j) { x[j] = S.v[TS_C0 + j][col]; y[j] = S.v[TS_C1 + j][col]; }
@@ -828,7 +943,12 @@ __global__ void __launch_bounds__(2 * TOP_THREADS, 2) ba_top_kernel(const BADesc
         for (int j = 0; j < 4; ++j) o[(2 + j) * s] = xadd(xmul(x[j], Ji0), xmul(y[j], Ji1));
       }
     }
+#if TOP_BULK
+    __syncwarp();
+    if (lane == 0) mbar_arrive(&empty_bar[j % TOP_STAGES]);   // this warp is done with the stage
+#else
     __syncthreads();   // everyone is done with this stage before the next iteration refills it
+#endif
   }
   if (cur >= 0) top_flush(D, cur, part, acc, nres, red, &last);
 }
@@ -918,7 +1038,7 @@ ba_schur_kernel(const BADesc* __restrict__ descs, const int* __restrict__ prefix
   const int NT = LD / 4, NTR = NT - 2, ntiles = NTR * (NTR + 1) / 2;
   const int half = threadIdx.x >> 7;      // 0: even points of the sub-tile, 1: odd points
   int tI[MAXT], tJ[MAXT];
-  float acc[MAXT][16];
+  __align__(8) float acc[MAXT][16];
 #pragma unroll
   for (int j = 0; j < MAXT; ++j) {
     int tile = (threadIdx.x & 127) + j * 128;
@@ -1111,10 +1231,25 @@ ba_schur_kernel(const BADesc* __restrict__ descs, const int* __restrict__ prefix
           const float4 bv = *reinterpret_cast<const float4*>(bp + lp * LDP);
           const float a4[4] = {av.x, av.y, av.z, av.w};
           const float b4[4] = {bv.x, bv.y, bv.z, bv.w};
+#ifndef SC_FFMA2
+#define SC_FFMA2 1
+#endif
+#if SC_FFMA2
+          // packed fp32 FMA (sm_100 FFMA2): two accumulators per instruction, each product rounded exactly like fmaf
+          float2* acc2 = reinterpret_cast<float2*>(acc[j]);
+          const float2 b01 = make_float2(b4[0], b4[1]), b23 = make_float2(b4[2], b4[3]);
+#pragma unroll
+          for (int ii = 0; ii < 4; ++ii) {
+            const float2 aa = make_float2(a4[ii], a4[ii]);
+            acc2[2 * ii] = __ffma2_rn(aa, b01, acc2[2 * ii]);
+            acc2[2 * ii + 1] = __ffma2_rn(aa, b23, acc2[2 * ii + 1]);
+          }
+#else
 #pragma unroll
           for (int ii = 0; ii < 4; ++ii)
 #pragma unroll
             for (int jj = 0; jj < 4; ++jj) acc[j][4 * ii + jj] = fmaf(a4[ii], b4[jj], acc[j][4 * ii + jj]);
+#endif
         }
       }
     }
@@ -1358,6 +1493,9 @@ __global__ void __launch_bounds__(ST_THREADS) ba_stitch_kernel(const BADesc* __r
   // ---- Schur complement system: H_sc = sum_i T_i G_i T_i^T with T_i[a,j] = d(a,i) AdH[i,j] + d(a,j) AdT[i,j]
   auto Gh = [&](int i) { return S.G + (size_t)i * LD * LD; };
   if (a < n && b < n) {
+    // H_sc = sum_i T_i G_i T_i^T is symmetric (every G_i is): block (b,a) is the transpose of block (a,b) and is
+    // written by the mirror block below
+    if (a > b) return;
     if (a == b) {   // sum_{j,k} AdH[a,j] D_a[j,k] AdH[a,k]^T   (AccumulatedSCHessian.cpp:108)
       // D_a[k,j] = D_a[j,k]^T (one symmetric Gram matrix per host), so the (k,j) term is the transpose of (j,k)
       const double* G = Gh(a);
@@ -1394,6 +1532,7 @@ __global__ void __launch_bounds__(ST_THREADS) ba_stitch_kernel(const BADesc* __r
 #pragma unroll
       for (int w = 0; w < ST_WARPS; ++w) o += part[w][threadIdx.x];
       H[(size_t)(4 + 8 * a + rr) + (size_t)N * (4 + 8 * b + cc)] = o;
+      if (a != b) H[(size_t)(4 + 8 * b + cc) + (size_t)N * (4 + 8 * a + rr)] = o;
     }
   } else if (a < n && b == n) {
     if (threadIdx.x < 40) {   // :86-89: H[i,0:4] += AdH[ij] E[ij], H[j,0:4] += AdT[ij] E[ij]; b likewise with EB
