@@ -649,9 +649,9 @@ static int launch_linearize(hslam_ba* ba, bool apply) {
   int blocks = (ba->R + LIN_THREADS - 1) / LIN_THREADS;
   if (blocks < 1) blocks = 1;
   if (apply)
-    HS_LAUNCH(ctx, HSLAM_K_BA_LINEARIZE, (ba_linearize_kernel<true><<<blocks, LIN_THREADS, 0, ctx->stream>>>(ba->d_desc.p, nullptr, 1)));
+    HS_LAUNCH(ctx, HSLAM_K_BA_LINEARIZE, (ba_linearize_kernel<true><<<blocks, LIN_THREADS, 0, ctx->stream>>>(ba->d_desc.p, nullptr, 1, 0)));
   else
-    HS_LAUNCH(ctx, HSLAM_K_BA_LINEARIZE, (ba_linearize_kernel<false><<<blocks, LIN_THREADS, 0, ctx->stream>>>(ba->d_desc.p, nullptr, 1)));
+    HS_LAUNCH(ctx, HSLAM_K_BA_LINEARIZE, (ba_linearize_kernel<false><<<blocks, LIN_THREADS, 0, ctx->stream>>>(ba->d_desc.p, nullptr, 1, 0)));
   HS_CUDA(cudaGetLastError());
   return 0;
 }
@@ -1022,6 +1022,7 @@ struct hslam_ba_batch {
   BADesc* h_descs = nullptr;     // pinned
   int* h_prefix = nullptr;       // pinned
   cudaEvent_t copied = nullptr;
+  cudaEvent_t ev_grp[8] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};   // step_host: per window-group fork points
   int blocks[6] = {0, 0, 0, 0, 0, 0};
   int uniform[6] = {0, 0, 0, 0, 0, 0};   // blocks per window of a stage when every window has the same count, else 0
   size_t smem = 0;
@@ -1037,7 +1038,11 @@ struct hslam_ba_batch {
   cudaGraphExec_t graph_iter = nullptr, graph_acc = nullptr;
   uint64_t refresh_version = 1, graph_iter_version = 0, graph_acc_version = 0;
   int graph_iter_kernels = 0, graph_acc_kernels = 0;
-  size_t up_tab_begin = 0, up_tab_end = 0, up_idepth_end = 0, up_deltaF_end = 0, up_end = 0;   // H2D block regions
+  size_t up_tab_begin = 0, up_idz_begin = 0, up_end = 0;   // H2D block regions: [0,tab) offset table + x slots, [tab,idz) window chunks, [idz,end) idepth_zero slots
+  std::vector<size_t> up_win_begin;   // start of window i's chunk [tables | idepth | deltaF]; [n] = up_idz_begin
+  cudaStream_t up_stream = nullptr;   // step_host: uploads + import of group g+1 run here while group g is linearised
+  cudaEvent_t ev_up[8] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
+  cudaEvent_t ev_begin = nullptr;
   size_t dn_res_end = 0, dn_sys_end = 0, dn_end = 0;   // D2H block regions: [0,res) per-residual arrays, [res,sys) systems, [sys,end) steps
 };
 static const int NPF = 6;
@@ -1111,6 +1116,10 @@ int hslam_ba_batch_create(hslam_ctx* ctx, hslam_ba* const* items, int count, hsl
   HS_CUDA(cudaMallocHost((void**)&B->h_descs, count * sizeof(BADesc)));
   HS_CUDA(cudaMallocHost((void**)&B->h_prefix, NPF * (size_t)(count + 1) * sizeof(int)));
   HS_CUDA(cudaEventCreateWithFlags(&B->copied, cudaEventDisableTiming));
+  for (int g = 0; g < 8; ++g) HS_CUDA(cudaEventCreateWithFlags(&B->ev_grp[g], cudaEventDisableTiming));
+  for (int g = 0; g < 8; ++g) HS_CUDA(cudaEventCreateWithFlags(&B->ev_up[g], cudaEventDisableTiming));
+  HS_CUDA(cudaEventCreateWithFlags(&B->ev_begin, cudaEventDisableTiming));
+  HS_CUDA(cudaStreamCreateWithFlags(&B->up_stream, cudaStreamNonBlocking));
   *out = B;
   return 0;
 }
@@ -1124,6 +1133,10 @@ int hslam_ba_batch_destroy(hslam_ba_batch* B) {
   if (B->h_up) cudaFreeHost(B->h_up);
   if (B->h_dn) cudaFreeHost(B->h_dn);
   cudaEventDestroy(B->copied);
+  for (int g = 0; g < 8; ++g) if (B->ev_grp[g]) cudaEventDestroy(B->ev_grp[g]);
+  for (int g = 0; g < 8; ++g) if (B->ev_up[g]) cudaEventDestroy(B->ev_up[g]);
+  if (B->ev_begin) cudaEventDestroy(B->ev_begin);
+  if (B->up_stream) { cudaStreamSynchronize(B->up_stream); cudaStreamDestroy(B->up_stream); }
   if (B->graph_iter) cudaGraphExecDestroy(B->graph_iter);
   if (B->graph_acc) cudaGraphExecDestroy(B->graph_acc);
   delete B;
@@ -1131,10 +1144,14 @@ int hslam_ba_batch_destroy(hslam_ba_batch* B) {
 }
 
 // One GN iteration's hot path for EVERY window of the batch: five launches in total.
-static int batch_enqueue_linearize(hslam_ba_batch* B) {
+// Windows [g0, g1) of the batch (the whole batch by default).
+static int batch_enqueue_linearize(hslam_ba_batch* B, int g0 = 0, int g1 = -1) {
   hslam_ctx* ctx = B->ctx;
   const int n = (int)B->items.size();
-  HS_LAUNCH(ctx, HSLAM_K_BA_LINEARIZE, (ba_linearize_kernel<true><<<B->blocks[0], LIN_THREADS, 0, ctx->stream>>>(B->d_descs.p, B->d_prefix.p, n)));
+  if (g1 < 0) g1 = n;
+  const int b0 = B->h_prefix[g0], cnt = B->h_prefix[g1] - b0;   // table 0 = linearise blocks
+  if (cnt <= 0) return 0;
+  HS_LAUNCH(ctx, HSLAM_K_BA_LINEARIZE, (ba_linearize_kernel<true><<<cnt, LIN_THREADS, 0, ctx->stream>>>(B->d_descs.p, B->d_prefix.p, n, b0)));
   HS_CUDA(cudaGetLastError());
   return 0;
 }
@@ -1261,27 +1278,28 @@ static int batch_layout_down(hslam_ba_batch* B) {
   return 0;
 }
 
-// Fixed layout of the H2D block: [BAIO table | x of every window | tables of every window | idepth | deltaF | idepth_zero].
-// A call copies only the leading part that it uses.
+// Fixed layout of the H2D block: [BAIO table | x of every window | per window: tables, idepth, deltaF | idepth_zero of
+// every window].  Window-major chunks: the inputs of a GROUP of windows are one contiguous span, so step_host can
+// upload group g+1 while group g is being linearised.
 static int batch_layout_up(hslam_ba_batch* B) {
   const int n = (int)B->items.size();
   size_t up = al256(n * sizeof(BAIO));
   auto take = [&](size_t bytes) { long long off = (long long)up; up = al256(up + bytes); return off; };
   for (int i = 0; i < n; ++i) B->io[i].up_x = take((size_t)B->items[i]->N * 8);   // solution vectors (resubstitute)
   B->up_tab_begin = up;
+  B->up_win_begin.assign(n + 1, 0);
   for (int i = 0; i < n; ++i) {
     hslam_ba* ba = B->items[i];
     const size_t nn = (size_t)ba->n * ba->n;
     BAIO& L = B->io[i];
+    B->up_win_begin[i] = up;
     L.up_precalc = take(nn * HSLAM_PRECALC_STRIDE * 4); L.up_adHTd = take(nn * 8 * 4);
     L.up_adH = take(nn * 64 * 8); L.up_adT = take(nn * 64 * 8);
     L.up_fprior = take((size_t)ba->n * 8 * 8); L.up_fdprior = take((size_t)ba->n * 8 * 8);
+    L.up_idepth = take((size_t)ba->P * 4);
+    L.up_deltaF = take((size_t)ba->P * 4);
   }
-  B->up_tab_end = up;
-  for (int i = 0; i < n; ++i) B->io[i].up_idepth = take((size_t)B->items[i]->P * 4);
-  B->up_idepth_end = up;
-  for (int i = 0; i < n; ++i) B->io[i].up_deltaF = take((size_t)B->items[i]->P * 4);
-  B->up_deltaF_end = up;
+  B->up_win_begin[n] = B->up_idz_begin = up;
   for (int i = 0; i < n; ++i) B->io[i].up_idz = take((size_t)B->items[i]->P * 4);
   B->up_end = up;
   TRY(pinned_ensure(&B->h_up, &B->h_up_cap, up));
@@ -1319,48 +1337,36 @@ int hslam_ba_batch_step_host(hslam_ba_batch* B, const hslam_ba_step_io* io) {
   TRY(batch_layout_down(B));
   TRY(batch_layout_up(B));
   std::vector<BAIO> eff(B->io);   // offsets of what is absent in this call become -1 for the import kernel
-  int maxP = 1, maxR = 1;
-  size_t extent = B->up_tab_begin;   // bytes of the block that actually have to travel
+  // pass 1: scalars, argument checks and the offset table of every window (no bulk data yet)
   for (int i = 0; i < n; ++i) {
     hslam_ba* ba = B->items[i];
     HS_ARG(ba->have_window && ba->have_topology, "hslam_ba_batch_step_host: a window has no window/topology set");
     const hslam_ba_step_io& o = io[i];
-    const BAIO& L = B->io[i];
     BAIO& E = eff[i];
-    const size_t nn = (size_t)ba->n * ba->n, P = ba->P;
-    if (o.window) {
-      const hslam_window* w = o.window;
-      TRY(window_scalars(ba, w));
-      memcpy(B->h_up + L.up_precalc, w->precalc, nn * HSLAM_PRECALC_STRIDE * 4);
-      memcpy(B->h_up + L.up_adHTd, w->adHTdeltaF, nn * 8 * 4);
-      memcpy(B->h_up + L.up_adH, w->adHost, nn * 64 * 8);
-      memcpy(B->h_up + L.up_adT, w->adTarget, nn * 64 * 8);
-      memcpy(B->h_up + L.up_fprior, w->framePrior, (size_t)ba->n * 8 * 8);
-      memcpy(B->h_up + L.up_fdprior, w->frameDeltaPrior, (size_t)ba->n * 8 * 8);
-      extent = std::max(extent, B->up_tab_end);
-    } else {
-      E.up_precalc = E.up_adHTd = E.up_adH = E.up_adT = E.up_fprior = E.up_fdprior = -1;
-    }
-    // a per-point input that already lives in its slot of the pinned block (hslam_ba_batch_io_bind) needs no copy
-    auto put = [&](const float* src, long long off, long long& eoff, size_t region_end) {
-      if (!src) { eoff = -1; return; }
-      if ((const char*)src != B->h_up + off) memcpy(B->h_up + off, src, P * 4);
-      extent = std::max(extent, region_end);
-    };
-    put(o.idepth, L.up_idepth, E.up_idepth, B->up_idepth_end);
-    put(o.deltaF, L.up_deltaF, E.up_deltaF, B->up_deltaF_end);
-    put(o.idepth_zero, L.up_idz, E.up_idz, B->up_end);
+    if (o.window) TRY(window_scalars(ba, o.window));
+    else E.up_precalc = E.up_adHTd = E.up_adH = E.up_adT = E.up_fprior = E.up_fdprior = -1;
+    if (!o.idepth) E.up_idepth = -1;
+    if (!o.deltaF) E.up_deltaF = -1;
+    if (!o.idepth_zero) E.up_idz = -1;
     E.up_x = -1;
-    maxP = std::max(maxP, ba->P); maxR = std::max(maxR, ba->R);
   }
   memcpy(B->h_up, eff.data(), n * sizeof(BAIO));   // the offset table leads the block
   TRY(batch_refresh(B));   // descriptors (only if a scalar changed) and block-prefix tables
-  HS_CUDA(cudaMemcpyAsync(B->d_up.p, B->h_up, extent, cudaMemcpyHostToDevice, ctx->stream));
   const BAIO* d_io = reinterpret_cast<const BAIO*>(B->d_up.p);
-  {
-    dim3 grid((unsigned)std::max(1, std::min(64, (maxP + 255) / 256)), (unsigned)n);
-    HS_LAUNCH(ctx, HSLAM_K_BA_EXPORT, (ba_batch_import_kernel<<<grid, 256, 0, ctx->stream>>>(B->d_descs.p, d_io, B->d_up.p)));
+  bool any_res = false, any_sys = false;
+  for (int i = 0; i < n; ++i) {
+    any_res |= io[i].newEnergy || io[i].newEnergyWithOutlier || io[i].newState;
+    any_sys |= io[i].Hb || io[i].nres2 || io[i].energy;
   }
+  // The batch is processed in up to 8 window groups.  Upload stream: pack + H2D + import of group g+1 while the
+  // context stream linearises group g; side stream (high priority): export + D2H of the per-residual results of
+  // group g while group g+1 is linearised, the last group's under the accumulate kernels.  Per-window results do
+  // not depend on the grouping.
+  int G = n >= 8 ? 4 : 1;
+  if (const char* e = getenv("HSLAM_STEP_GROUPS")) G = std::max(1, std::min(8, std::min(n, atoi(e))));
+  HS_CUDA(cudaEventRecord(B->ev_begin, ctx->stream));          // uploads overwrite state the stream's earlier work may read
+  HS_CUDA(cudaStreamWaitEvent(B->up_stream, B->ev_begin, 0));
+  HS_CUDA(cudaMemcpyAsync(B->d_up.p, B->h_up, al256(n * sizeof(BAIO)), cudaMemcpyHostToDevice, B->up_stream));
   // ---- results.  Three kinds of caller buffer: a slot of the batch's own pinned block (hslam_ba_batch_io_bind:
   // nothing to do, the two bulk copies below fill it), other pinned memory (hslam_host_alloc: direct DMA per
   // array), pageable memory (memcpy from the pinned block after the synchronisation).  The per-residual arrays
@@ -1380,28 +1386,77 @@ int hslam_ba_batch_step_host(hslam_ba_batch* B, const hslam_ba_step_io* io) {
     }
     return 0;
   };
-  TRY(batch_enqueue_linearize(B));
-  bool any_res = false, any_sys = false;
-  for (int i = 0; i < n; ++i) {
-    any_res |= io[i].newEnergy || io[i].newEnergyWithOutlier || io[i].newState;
-    any_sys |= io[i].Hb || io[i].nres2 || io[i].energy;
-  }
-  if (any_res) {
-    HS_CUDA(cudaEventRecord(ctx->ev_fork, ctx->stream));
-    HS_CUDA(cudaStreamWaitEvent(ctx->side, ctx->ev_fork, 0));
-    dim3 grid((unsigned)std::max(1, std::min(128, (maxR + 255) / 256)), (unsigned)n);
-    ctx->launches++;   // side stream: counted, not event-timed
-    ba_batch_export_kernel<<<grid, 256, 0, ctx->side>>>(B->d_descs.p, d_io, B->d_dn.p, 1);
-    HS_CUDA(cudaGetLastError());
-    for (int i = 0; i < n; ++i) {
-      const size_t R = B->items[i]->R;
-      TRY(emit(ctx->side, bulk_res, io[i].newEnergy, B->io[i].dn_newEnergy, R * 4));
-      TRY(emit(ctx->side, bulk_res, io[i].newEnergyWithOutlier, B->io[i].dn_newEnergyWO, R * 4));
-      TRY(emit(ctx->side, bulk_res, io[i].newState, B->io[i].dn_newState, R));
+  for (int g = 0; g < G; ++g) {
+    const int g0 = (int)((long long)n * g / G), g1 = (int)((long long)n * (g + 1) / G);
+    // ---- inputs of the group: pack what is not already in its pinned slot, one H2D of the group's span, import
+    bool any_in = false, any_idz = false;
+    int gP = 1, gR = 1;
+    for (int i = g0; i < g1; ++i) {
+      hslam_ba* ba = B->items[i];
+      const hslam_ba_step_io& o = io[i];
+      const BAIO& L = B->io[i];
+      const size_t nn = (size_t)ba->n * ba->n, P = ba->P;
+      if (o.window) {
+        const hslam_window* w = o.window;
+        memcpy(B->h_up + L.up_precalc, w->precalc, nn * HSLAM_PRECALC_STRIDE * 4);
+        memcpy(B->h_up + L.up_adHTd, w->adHTdeltaF, nn * 8 * 4);
+        memcpy(B->h_up + L.up_adH, w->adHost, nn * 64 * 8);
+        memcpy(B->h_up + L.up_adT, w->adTarget, nn * 64 * 8);
+        memcpy(B->h_up + L.up_fprior, w->framePrior, (size_t)ba->n * 8 * 8);
+        memcpy(B->h_up + L.up_fdprior, w->frameDeltaPrior, (size_t)ba->n * 8 * 8);
+        any_in = true;
+      }
+      // a per-point input that already lives in its slot of the pinned block (hslam_ba_batch_io_bind) needs no copy
+      auto put = [&](const float* src, long long off, bool& flag) {
+        if (!src) return;
+        if ((const char*)src != B->h_up + off) memcpy(B->h_up + off, src, P * 4);
+        flag = true;
+      };
+      put(o.idepth, L.up_idepth, any_in);
+      put(o.deltaF, L.up_deltaF, any_in);
+      put(o.idepth_zero, L.up_idz, any_idz);
+      gP = std::max(gP, ba->P); gR = std::max(gR, ba->R);
     }
-    if (bulk_res) HS_CUDA(cudaMemcpyAsync(B->h_dn, B->d_dn.p, B->dn_res_end, cudaMemcpyDeviceToHost, ctx->side));
-    HS_CUDA(cudaEventRecord(ctx->ev_join, ctx->side));
+    if (any_in) {
+      const size_t lo = B->up_win_begin[g0], hi = B->up_win_begin[g1];
+      HS_CUDA(cudaMemcpyAsync(B->d_up.p + lo, B->h_up + lo, hi - lo, cudaMemcpyHostToDevice, B->up_stream));
+    }
+    if (any_idz) {
+      const size_t lo = (size_t)B->io[g0].up_idz, hi = g1 < n ? (size_t)B->io[g1].up_idz : B->up_end;
+      HS_CUDA(cudaMemcpyAsync(B->d_up.p + lo, B->h_up + lo, hi - lo, cudaMemcpyHostToDevice, B->up_stream));
+    }
+    if (any_in || any_idz) {
+      dim3 grid((unsigned)std::max(1, std::min(64, (gP + 255) / 256)), (unsigned)(g1 - g0));
+      ctx->launches++;   // upload stream: counted, not event-timed
+      ba_batch_import_kernel<<<grid, 256, 0, B->up_stream>>>(B->d_descs.p + g0, d_io + g0, B->d_up.p);
+      HS_CUDA(cudaGetLastError());
+    }
+    HS_CUDA(cudaEventRecord(B->ev_up[g], B->up_stream));
+    HS_CUDA(cudaStreamWaitEvent(ctx->stream, B->ev_up[g], 0));
+    // ---- linearise the group
+    TRY(batch_enqueue_linearize(B, g0, g1));
+    if (!any_res) continue;
+    // ---- per-residual results of the group
+    HS_CUDA(cudaEventRecord(B->ev_grp[g], ctx->stream));
+    HS_CUDA(cudaStreamWaitEvent(ctx->side, B->ev_grp[g], 0));
+    dim3 grid((unsigned)std::max(1, std::min(128, (gR + 255) / 256)), (unsigned)(g1 - g0));
+    ctx->launches++;   // side stream: counted, not event-timed
+    ba_batch_export_kernel<<<grid, 256, 0, ctx->side>>>(B->d_descs.p + g0, d_io + g0, B->d_dn.p, 1);
+    HS_CUDA(cudaGetLastError());
+    bool bulk_g = false;
+    for (int i = g0; i < g1; ++i) {
+      const size_t R = B->items[i]->R;
+      TRY(emit(ctx->side, bulk_g, io[i].newEnergy, B->io[i].dn_newEnergy, R * 4));
+      TRY(emit(ctx->side, bulk_g, io[i].newEnergyWithOutlier, B->io[i].dn_newEnergyWO, R * 4));
+      TRY(emit(ctx->side, bulk_g, io[i].newState, B->io[i].dn_newState, R));
+    }
+    if (bulk_g) {   // the group's slice of the per-residual region is contiguous (batch_layout_down)
+      const size_t lo = (size_t)B->io[g0].dn_newEnergy, hi = g1 < n ? (size_t)B->io[g1].dn_newEnergy : B->dn_res_end;
+      HS_CUDA(cudaMemcpyAsync(B->h_dn + lo, B->d_dn.p + lo, hi - lo, cudaMemcpyDeviceToHost, ctx->side));
+    }
+    bulk_res |= bulk_g;
   }
+  if (any_res) HS_CUDA(cudaEventRecord(ctx->ev_join, ctx->side));
   TRY(batch_graph_launch(B, false));
   if (any_sys) {
     HS_LAUNCH(ctx, HSLAM_K_BA_EXPORT, (ba_batch_export_kernel<<<dim3(2, (unsigned)n), 256, 0, ctx->stream>>>(B->d_descs.p, d_io, B->d_dn.p, 2)));

@@ -51,7 +51,10 @@ constexpr int LIN_THREADS = LIN_THREADS_;
 constexpr int TOP_THREADS = 128;
 constexpr int TOP_PART = 96;           // 91 accumulators + nres + pad
 constexpr int SC_THREADS = 256;
-constexpr int SC_PTS = 64;             // points staged in shared memory per sub-tile
+#ifndef SC_PTS_
+#define SC_PTS_ 64
+#endif
+constexpr int SC_PTS = SC_PTS_;        // points staged in shared memory per sub-tile (32 / 64 / 128)
 constexpr int ST_WARPS = 8;            // warps per stitch block (80 regs x 256 threads: 3 blocks per SM)
 constexpr int ST_THREADS = ST_WARPS * 32;
 
@@ -199,7 +202,7 @@ __device__ __forceinline__ void apply_one(const BARes& r, int k) {  // Optimizat
 
 template <bool APPLY>
 __global__ void __launch_bounds__(LIN_THREADS, LIN_MINB) ba_linearize_kernel(const BADesc* __restrict__ descs,
-                                                                   const int* __restrict__ prefix, int nwin) {
+                                                                   const int* __restrict__ prefix, int nwin, int block0) {
 #ifndef LIN_PARK
 #define LIN_PARK 0   /* measured: parking colours/weights in smem 149 us vs 146 us in registers */
 #endif
@@ -207,7 +210,7 @@ __global__ void __launch_bounds__(LIN_THREADS, LIN_MINB) ba_linearize_kernel(con
   __shared__ float lin_park[16][LIN_THREADS];
 #endif
   int lb;
-  const int win = find_window(prefix, nwin, blockIdx.x, lb);
+  const int win = find_window(prefix, nwin, blockIdx.x + block0, lb);   // block0: a launch may cover a sub-range of the batch
 #ifndef LIN_DESC_SMEM
 #define LIN_DESC_SMEM 0   /* measured: descriptor through shared memory 150.5 us, through the pointer 147.4 us */
 #endif
@@ -1069,7 +1072,9 @@ ba_schur_kernel(const BADesc* __restrict__ descs, const int* __restrict__ prefix
   int dfl[NI];                        //                  -1 = nothing, else isActive | isLin << 1 | target << 8 (raw loads:
                                       //                  nothing here may consume a loaded value before the next sub-tile)
   unsigned char dact[NI], dlin[NI];
-  float pr[2], de[2];                 // priorF / deltaF of the points this thread finalises in phase 1b
+  constexpr int NRD = SC_PTS * 8 / SC_THREADS;   // phase-1b rounds: 8 lanes per point
+  static_assert(NRD >= 1 && NRD * SC_THREADS == SC_PTS * 8, "SC_PTS must be a multiple of 32");
+  float pr[NRD], de[NRD];             // priorF / deltaF of the points this thread finalises in phase 1b
 
   auto load_slots = [&](int base) {
     const int cnt = min(SC_PTS, ch.count - base);   // <= 0 beyond the chunk
@@ -1099,7 +1104,7 @@ ba_schur_kernel(const BADesc* __restrict__ descs, const int* __restrict__ prefix
       }
     }
 #pragma unroll
-    for (int rd = 0; rd < 2; ++rd) {
+    for (int rd = 0; rd < NRD; ++rd) {
       const int item = rd * SC_THREADS + threadIdx.x, lp = item >> 3, c = item & 7;
       pr[rd] = de[rd] = 0.f;
       if (lp < cnt && c < 2) {
@@ -1142,7 +1147,9 @@ ba_schur_kernel(const BADesc* __restrict__ descs, const int* __restrict__ prefix
         stg[6 * SNP + si] = on ? (dlin[i] ? 2.f : 1.f) : 0.f;
       }
     }
-    const float prc[2] = {pr[0], pr[1]}, dec[2] = {de[0], de[1]};
+    float prc[NRD], dec[NRD];
+#pragma unroll
+    for (int rd = 0; rd < NRD; ++rd) { prc[rd] = pr[rd]; dec[rd] = de[rd]; }
     // ... and the loads of the NEXT sub-tile (data) and the one after (slots) are issued: they complete
     // while phases 1b and 2 run
 #if SC_PIPELINE
@@ -1154,7 +1161,7 @@ ba_schur_kernel(const BADesc* __restrict__ descs, const int* __restrict__ prefix
     // modes and adds the point's residuals IN THE POINT'S OWN ORDER (AccumulatedTopHessian.cpp:35-139), then
     // the Schur scalars (AccumulatedSCHessian.cpp:12-33).
 #pragma unroll
-    for (int rd = 0; rd < 2; ++rd) {
+    for (int rd = 0; rd < NRD; ++rd) {
       const int item = rd * SC_THREADS + threadIdx.x, lp = item >> 3, c = item & 7;
       float rowv = 0.f, rowh = 0.f;
       if (c < 6) {

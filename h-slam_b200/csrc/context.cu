@@ -53,7 +53,12 @@ int hslam_create(const hslam_params* params, int device, hslam_ctx** out) {
     return HSLAM_ERR_CUDA;
   }
   HS_CUDA(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
-  HS_CUDA(cudaStreamCreateWithFlags(&c->side, cudaStreamNonBlocking));
+  {
+    // the side stream carries result export + D2H copies that should overlap the main stream's kernels: highest priority
+    int lo = 0, hi = 0;
+    HS_CUDA(cudaDeviceGetStreamPriorityRange(&lo, &hi));
+    HS_CUDA(cudaStreamCreateWithPriority(&c->side, cudaStreamNonBlocking, hi));
+  }
   HS_CUDA(cudaEventCreateWithFlags(&c->ev_fork, cudaEventDisableTiming));
   HS_CUDA(cudaEventCreateWithFlags(&c->ev_join, cudaEventDisableTiming));
   *out = c;

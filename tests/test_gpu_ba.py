@@ -300,6 +300,38 @@ def test_batch_step_host_matches_single_window_calls(ctx, capi, synth, pinned):
         f.close()
 
 
+def test_batch_step_host_window_groups(ctx, capi, synth, monkeypatch):
+    """hslam_ba_batch_step_host pipelines a batch of >= 8 windows in window groups (linearise group g+1 while the
+    results of group g travel): every output is bit-identical to the un-grouped call (HSLAM_STEP_GROUPS=1) and to an
+    odd group count that does not divide the batch."""
+    kf = synth.render_keyframes(320, 240, 4, seed=79)
+    wins = [synth.make_window(points_per_frame=60 + 11 * i, seed=500 + i, keyframes=kf)[0] for i in range(9)]
+    frames = [capi.Frame(ctx, im, 1) for im in kf.images]
+    results = []
+    for groups in (None, "1", "5"):
+        if groups is None:
+            monkeypatch.delenv("HSLAM_STEP_GROUPS", raising=False)
+        else:
+            monkeypatch.setenv("HSLAM_STEP_GROUPS", groups)
+        efs = []
+        for w in wins:
+            b = capi.EnergyFunctional(ctx); b.set_window(w, frames); b.set_topology(w); efs.append(b)
+        batch = capi.EnergyFunctionalBatch(ctx, efs)
+        io = batch.make_io(wins, [frames] * len(wins), pinned="bound")
+        outs = batch.step_host(io)
+        results.append([{k: np.array(v, copy=True) for k, v in o.items() if k != "step"} for o in outs])
+        batch.close()
+        for e in efs:
+            e.close()
+    for other in results[1:]:
+        for o0, o1 in zip(results[0], other):
+            for k in o0:
+                assert np.array_equal(o0[k], o1[k]), k
+    assert all(np.abs(o["Hb"]).max() > 0 and (o["newState"] == 0).any() for o in results[0])
+    for f in frames:
+        f.close()
+
+
 def test_marginalize_points_and_lenergy(ctx, capi, O, synth):
     """EnergyFunctional::marginalizePointsF (addPoint<2> + SC addPoint(p,false) + stitchDouble without priors) and
     calcLEnergyF_MT against the oracle: M, Mb, Msc, Mbsc <= 1e-5 vs fp64 and no worse than the float restatement."""

@@ -37,7 +37,9 @@ WANT = [
     ("sm__warps_active.avg.pct_of_peak_sustained_active", "warps_act_pct"),
     ("smsp__issue_active.avg.pct_of_peak_sustained_active", "issue_pct"),
     ("l1tex__t_sector_hit_rate.pct", "l1_hit"), ("lts__t_sector_hit_rate.pct", "l2_hit"),
-    ("lts__t_bytes.sum", "l2_bytes"),
+    ("lts__t_sectors.sum", "l2_sectors"),
+    ("LTS.TriageCompute.lts__throughput.avg.pct_of_peak_sustained_elapsed", "l2_pct"),
+    ("l1tex__data_pipe_lsu_wavefronts.avg.pct_of_peak_sustained_elapsed", "l1_wavefront_pct"),
     ("l1tex__data_bank_conflicts_pipe_lsu_mem_shared.sum", "smem_bank_conflicts"),
     ("smsp__average_warps_issue_stalled_long_scoreboard_per_issue_active.ratio", "stall_long_sb"),
     ("smsp__average_warps_issue_stalled_short_scoreboard_per_issue_active.ratio", "stall_short_sb"),
@@ -61,6 +63,21 @@ def raw(rep):
             if m in hdr:
                 i = hdr.index(m)
                 print(f"   {short:22s} {r[i]:>16s} {units[i]}")
+        # achieved bandwidths (what north_star asks ncu to report): bytes / duration of this (cold-cache) launch
+        def val(m, to):
+            i = hdr.index(m)
+            v, u = float(r[i].replace(",", "")), units[i]
+            scale = {"ns": 1e-9, "us": 1e-6, "ms": 1e-3, "s": 1.0, "byte": 1.0, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9,
+                     "sector": 32.0}.get(u, 1.0)
+            return v * scale
+        try:
+            t = val("gpu__time_duration.sum", "s")
+            hbm = (val("dram__bytes_read.sum", "B") + val("dram__bytes_write.sum", "B")) / t / 1e9
+            l2 = val("lts__t_sectors.sum", "B") / t / 1e9
+            print(f"   {'hbm_GBps_achieved':22s} {hbm:16.1f} GB/s  ({hbm / 6555.2:.2f} of the measured 6555 GB/s copy peak)")
+            print(f"   {'l2_GBps_achieved':22s} {l2:16.1f} GB/s")
+        except (ValueError, KeyError):
+            pass
 
 
 if __name__ == "__main__":
