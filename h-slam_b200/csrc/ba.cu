@@ -901,7 +901,13 @@ int hslam_ba_residual_results(hslam_ba* ba, int8_t* state_state, uint8_t* is_act
   HS_CUDA(cudaSetDevice(ba->ctx->device));
   TRY(download_res(ba, ba->d_state.p, 1, state_state));
   TRY(download_res(ba, ba->d_isActive.p, 1, is_active));
-  TRY(download_res(ba, ba->d_JpJdF.p, 8, JpJdF));
+  if (JpJdF && ba->R > 0) {   // [R][8] records in sorted order -> caller order
+    void* tmp;
+    TRY(scratch_alloc(ba, (size_t)ba->R * 8 * sizeof(float), &tmp));
+    HS_LAUNCH(ba->ctx, HSLAM_K_BA_EXPORT, (ba_export_aos_kernel<float><<<(ba->R + 255) / 256, 256, 0, ba->ctx->stream>>>(
+                                              ba->d_JpJdF.p, 8, ba->R, ba->d_r_s2o.p, (float*)tmp)));
+    TRY(download(ba, JpJdF, (const float*)tmp, (size_t)ba->R * 8));
+  }
   TRY(download_res(ba, ba->d_rtz.p, 8, res_toZeroF));
   TRY(download_res(ba, ba->d_J.p, 74, J74));
   return end_call(ba);

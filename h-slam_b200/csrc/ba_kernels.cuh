@@ -84,7 +84,7 @@ struct BARes {               // per-residual SoA, sorted by (host,target) pair, 
   float* newEnergy;
   float* newEnergyWO;
   float* J;                  // [JS][rs]
-  float* JpJdF;              // [8][rs]
+  float* JpJdF;              // [rs][8]: one 32-byte record per residual (read whole by the Schur staging and the back-substitution)
   float* rtz;                // [8][rs] res_toZeroF
   float* cpt;                // [3][rs] centerProjectedTo
   float* pto;                // [16][rs] projectedTo
@@ -185,11 +185,13 @@ __device__ __forceinline__ void take_data(const BARes& r, int k) {  // Optimizat
   float d0 = J[J_DD * s], d1 = J[(J_DD + 1) * s];
   float JJ0 = xadd(xmul(J[(J_IDX2 + 0) * s], d0), xmul(J[(J_IDX2 + 2) * s], d1));
   float JJ1 = xadd(xmul(J[(J_IDX2 + 1) * s], d0), xmul(J[(J_IDX2 + 3) * s], d1));
+  float o[8];
 #pragma unroll
-  for (int i = 0; i < 6; ++i)
-    r.JpJdF[i * s + k] = xadd(xmul(J[(J_XI0 + i) * s], JJ0), xmul(J[(J_XI1 + i) * s], JJ1));
-  r.JpJdF[6 * s + k] = xadd(xmul(J[(J_ABIDX + 0) * s], d0), xmul(J[(J_ABIDX + 2) * s], d1));
-  r.JpJdF[7 * s + k] = xadd(xmul(J[(J_ABIDX + 1) * s], d0), xmul(J[(J_ABIDX + 3) * s], d1));
+  for (int i = 0; i < 6; ++i) o[i] = xadd(xmul(J[(J_XI0 + i) * s], JJ0), xmul(J[(J_XI1 + i) * s], JJ1));
+  o[6] = xadd(xmul(J[(J_ABIDX + 0) * s], d0), xmul(J[(J_ABIDX + 2) * s], d1));
+  o[7] = xadd(xmul(J[(J_ABIDX + 1) * s], d0), xmul(J[(J_ABIDX + 3) * s], d1));
+  float4* dst = reinterpret_cast<float4*>(r.JpJdF + 8 * (size_t)k);
+  dst[0] = make_float4(o[0], o[1], o[2], o[3]); dst[1] = make_float4(o[4], o[5], o[6], o[7]);
 }
 
 __device__ __forceinline__ void apply_one(const BARes& r, int k) {  // OptimizationClasses.cpp:235-256
@@ -439,11 +441,13 @@ __global__ void __launch_bounds__(LIN_THREADS, LIN_MINB) ba_linearize_kernel(con
               if (ns == HSLAM_RES_IN) {
                 r.isActive[k] = 1;
                 const float JJ0 = xadd(xmul(II00, ddx), xmul(II10, ddy)), JJ1 = xadd(xmul(II10, ddx), xmul(II11, ddy));
-                float* o = r.JpJdF + k;
+                float o[8];
 #pragma unroll
-                for (int i = 0; i < 6; ++i) STJ(o + i * s, xadd(xmul(HS_XI0(i), JJ0), xmul(HS_XI1(i), JJ1)));
-                STJ(o + 6 * s, xadd(xmul(AI00, ddx), xmul(AI01, ddy)));
-                STJ(o + 7 * s, xadd(xmul(AI10, ddx), xmul(AI11, ddy)));
+                for (int i = 0; i < 6; ++i) o[i] = xadd(xmul(HS_XI0(i), JJ0), xmul(HS_XI1(i), JJ1));
+                o[6] = xadd(xmul(AI00, ddx), xmul(AI01, ddy));
+                o[7] = xadd(xmul(AI10, ddx), xmul(AI11, ddy));
+                float4* dst = reinterpret_cast<float4*>(r.JpJdF + 8 * (size_t)k);   // one 32-byte record
+                dst[0] = make_float4(o[0], o[1], o[2], o[3]); dst[1] = make_float4(o[4], o[5], o[6], o[7]);
               } else {
                 r.isActive[k] = 0;
               }
@@ -1094,9 +1098,9 @@ ba_schur_kernel(const BADesc* __restrict__ descs, const int* __restrict__ prefix
         // every load of the residual is independent of its flags (one round trip); filtered at the store
         dact[i] = r.isActive[k];
         dlin[i] = r.isLin[k];
-        const float* jp = r.JpJdF + k;
-        dj0[i] = make_float4(jp[0], jp[s], jp[2 * s], jp[3 * s]);
-        dj1[i] = make_float4(jp[4 * s], jp[5 * s], jp[6 * s], jp[7 * s]);
+        const float4* jp = reinterpret_cast<const float4*>(r.JpJdF + 8 * (size_t)k);
+        dj0[i] = jp[0];
+        dj1[i] = jp[1];
         const float* o = r.ptc[0] + k;   // modes A and L share the array (a residual is in exactly one)
 #pragma unroll
         for (int j = 0; j < 6; ++j) dpt[i][j] = o[j * s];
@@ -1660,8 +1664,11 @@ __global__ void __launch_bounds__(128) ba_resub_kernel(const BADesc* __restrict_
       int pair = r.pair[k], h = pair % n, t = pair / n;
       const float* xa = xAd + 8 * (n * h + t);
       float d = 0.f;
+      const float4* jp = reinterpret_cast<const float4*>(r.JpJdF + 8 * (size_t)k);
+      const float4 j0 = jp[0], j1 = jp[1];
+      const float jv[8] = {j0.x, j0.y, j0.z, j0.w, j1.x, j1.y, j1.z, j1.w};
 #pragma unroll
-      for (int j = 0; j < 8; ++j) d = xadd(d, xmul(xa[j], r.JpJdF[j * s + k]));
+      for (int j = 0; j < 8; ++j) d = xadd(d, xmul(xa[j], jv[j]));
       b = xsub(b, d);
     }
     step = xmul(-b, pts.HdiF[p]);
