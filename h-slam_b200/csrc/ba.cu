@@ -1049,7 +1049,7 @@ struct hslam_ba_batch {
   cudaStream_t up_stream = nullptr;   // step_host: uploads + import of group g+1 run here while group g is linearised
   cudaEvent_t ev_up[8] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
   cudaEvent_t ev_begin = nullptr;
-  size_t dn_res_end = 0, dn_sys_end = 0, dn_end = 0;   // D2H block regions: [0,res) per-residual arrays, [res,sys) systems, [sys,end) steps
+  size_t dn_state_end = 0, dn_res_end = 0, dn_sys_end = 0, dn_end = 0;   // D2H block regions: [0,res) per-residual arrays, [res,sys) systems, [sys,end) steps
 };
 static const int NPF = 6;
 
@@ -1267,9 +1267,12 @@ static int batch_layout_down(hslam_ba_batch* B) {
   const int n = (int)B->items.size();
   size_t dn = 0;
   auto take = [&](size_t bytes) { long long off = (long long)dn; dn = al256(dn + bytes); return off; };
+  // window-major within each kind: the states / the energies of a GROUP of windows are one contiguous span each
+  for (int i = 0; i < n; ++i) B->io[i].dn_newState = take(B->items[i]->R);
+  B->dn_state_end = dn;
   for (int i = 0; i < n; ++i) {
     const size_t R = B->items[i]->R;
-    B->io[i].dn_newEnergy = take(R * 4); B->io[i].dn_newEnergyWO = take(R * 4); B->io[i].dn_newState = take(R);
+    B->io[i].dn_newEnergy = take(R * 4); B->io[i].dn_newEnergyWO = take(R * 4);
   }
   B->dn_res_end = dn;
   for (int i = 0; i < n; ++i) {
@@ -1355,6 +1358,10 @@ int hslam_ba_batch_step_host(hslam_ba_batch* B, const hslam_ba_step_io* io) {
     if (!o.deltaF) E.up_deltaF = -1;
     if (!o.idepth_zero) E.up_idz = -1;
     E.up_x = -1;
+    // outputs the caller did not ask for are neither exported nor copied
+    if (!o.newEnergy) E.dn_newEnergy = -1;
+    if (!o.newEnergyWithOutlier) E.dn_newEnergyWO = -1;
+    if (!o.newState) E.dn_newState = -1;
   }
   memcpy(B->h_up, eff.data(), n * sizeof(BAIO));   // the offset table leads the block
   TRY(batch_refresh(B));   // descriptors (only if a scalar changed) and block-prefix tables
@@ -1449,18 +1456,23 @@ int hslam_ba_batch_step_host(hslam_ba_batch* B, const hslam_ba_step_io* io) {
     ctx->launches++;   // side stream: counted, not event-timed
     ba_batch_export_kernel<<<grid, 256, 0, ctx->side>>>(B->d_descs.p + g0, d_io + g0, B->d_dn.p, 1);
     HS_CUDA(cudaGetLastError());
-    bool bulk_g = false;
+    bool bulk_st = false, bulk_en = false;
     for (int i = g0; i < g1; ++i) {
       const size_t R = B->items[i]->R;
-      TRY(emit(ctx->side, bulk_g, io[i].newEnergy, B->io[i].dn_newEnergy, R * 4));
-      TRY(emit(ctx->side, bulk_g, io[i].newEnergyWithOutlier, B->io[i].dn_newEnergyWO, R * 4));
-      TRY(emit(ctx->side, bulk_g, io[i].newState, B->io[i].dn_newState, R));
+      TRY(emit(ctx->side, bulk_en, io[i].newEnergy, B->io[i].dn_newEnergy, R * 4));
+      TRY(emit(ctx->side, bulk_en, io[i].newEnergyWithOutlier, B->io[i].dn_newEnergyWO, R * 4));
+      TRY(emit(ctx->side, bulk_st, io[i].newState, B->io[i].dn_newState, R));
     }
-    if (bulk_g) {   // the group's slice of the per-residual region is contiguous (batch_layout_down)
+    // the group's slices of the state region and of the energy region are contiguous (batch_layout_down)
+    if (bulk_st) {
+      const size_t lo = (size_t)B->io[g0].dn_newState, hi = g1 < n ? (size_t)B->io[g1].dn_newState : B->dn_state_end;
+      HS_CUDA(cudaMemcpyAsync(B->h_dn + lo, B->d_dn.p + lo, hi - lo, cudaMemcpyDeviceToHost, ctx->side));
+    }
+    if (bulk_en) {
       const size_t lo = (size_t)B->io[g0].dn_newEnergy, hi = g1 < n ? (size_t)B->io[g1].dn_newEnergy : B->dn_res_end;
       HS_CUDA(cudaMemcpyAsync(B->h_dn + lo, B->d_dn.p + lo, hi - lo, cudaMemcpyDeviceToHost, ctx->side));
     }
-    bulk_res |= bulk_g;
+    bulk_res |= bulk_st || bulk_en;
   }
   if (any_res) HS_CUDA(cudaEventRecord(ctx->ev_join, ctx->side));
   TRY(batch_graph_launch(B, false));
