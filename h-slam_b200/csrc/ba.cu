@@ -978,7 +978,7 @@ int hslam_ba_resubstitute(hslam_ba* ba, const double* x, float* step_out) {
   HS_LAUNCH(ba->ctx, HSLAM_K_BA_RESUB, (ba_xad_kernel<<<1, 256, 0, ba->ctx->stream>>>(ba->d_desc.p)));
   int blocks = (ba->P + 127) / 128;
   if (blocks > 0)
-    HS_LAUNCH(ba->ctx, HSLAM_K_BA_RESUB, (ba_resub_kernel<<<blocks, 128, 0, ba->ctx->stream>>>(ba->d_desc.p, nullptr, 1, nullptr, nullptr)));
+    HS_LAUNCH(ba->ctx, HSLAM_K_BA_RESUB, (ba_resub_kernel<<<blocks, 128, 0, ba->ctx->stream>>>(ba->d_desc.p, nullptr, 1, nullptr, nullptr, 0)));
   HS_CUDA(cudaGetLastError());
   TRY(download_pts(ba, ba->d_step.p, 1, step_out));
   return end_call(ba);
@@ -1515,22 +1515,42 @@ int hslam_ba_batch_resubstitute_host(hslam_ba_batch* B, const double* const* x, 
   const BAIO* d_io = reinterpret_cast<const BAIO*>(B->d_up.p);
   HS_LAUNCH(ctx, HSLAM_K_BA_EXPORT, (ba_batch_import_kernel<<<dim3(1, (unsigned)n), 256, 0, ctx->stream>>>(B->d_descs.p, d_io, B->d_up.p)));
   HS_LAUNCH(ctx, HSLAM_K_BA_RESUB, (ba_xad_kernel<<<n, 256, 0, ctx->stream>>>(B->d_descs.p)));
-  if (B->blocks[5] > 0)
-    HS_LAUNCH(ctx, HSLAM_K_BA_RESUB, (ba_resub_kernel<<<B->blocks[5], 128, 0, ctx->stream>>>(
-                                         B->d_descs.p, B->d_prefix.p + 5 * (n + 1), n, d_io, B->d_dn.p)));
-  HS_CUDA(cudaGetLastError());
-  bool bulk = false;
+  // window groups: the steps of group g travel on the side stream while group g+1 is back-substituted
+  int G = n >= 8 ? 4 : 1;
+  if (const char* e = getenv("HSLAM_STEP_GROUPS")) G = std::max(1, std::min(8, std::min(n, atoi(e))));
+  const int* hp = B->h_prefix + 5 * (n + 1);
   std::vector<int> staged;
-  for (int i = 0; i < n; ++i) {
-    if (!step_out[i]) continue;
-    const size_t bytes = (size_t)B->items[i]->P * 4;
-    if ((void*)step_out[i] == (void*)(B->h_dn + B->io[i].dn_step)) bulk = true;
-    else if (ctx->is_pinned(step_out[i], bytes))
-      HS_CUDA(cudaMemcpyAsync(step_out[i], B->d_dn.p + B->io[i].dn_step, bytes, cudaMemcpyDeviceToHost, ctx->stream));
-    else { bulk = true; staged.push_back(i); }
+  for (int g = 0; g < G; ++g) {
+    const int g0 = (int)((long long)n * g / G), g1 = (int)((long long)n * (g + 1) / G);
+    const int b0 = hp[g0], cnt = hp[g1] - b0;
+    if (cnt > 0)
+      HS_LAUNCH(ctx, HSLAM_K_BA_RESUB, (ba_resub_kernel<<<cnt, 128, 0, ctx->stream>>>(
+                                           B->d_descs.p, B->d_prefix.p + 5 * (n + 1), n, d_io, B->d_dn.p, b0)));
+    HS_CUDA(cudaGetLastError());
+    cudaStream_t cs = ctx->stream;
+    if (G > 1) {
+      HS_CUDA(cudaEventRecord(B->ev_grp[g], ctx->stream));
+      HS_CUDA(cudaStreamWaitEvent(ctx->side, B->ev_grp[g], 0));
+      cs = ctx->side;
+    }
+    bool bulk = false;
+    for (int i = g0; i < g1; ++i) {
+      if (!step_out[i]) continue;
+      const size_t bytes = (size_t)B->items[i]->P * 4;
+      if ((void*)step_out[i] == (void*)(B->h_dn + B->io[i].dn_step)) bulk = true;
+      else if (ctx->is_pinned(step_out[i], bytes))
+        HS_CUDA(cudaMemcpyAsync(step_out[i], B->d_dn.p + B->io[i].dn_step, bytes, cudaMemcpyDeviceToHost, cs));
+      else { bulk = true; staged.push_back(i); }
+    }
+    if (bulk) {   // the group's step slots are contiguous (batch_layout_down)
+      const size_t lo = (size_t)B->io[g0].dn_step, hi = g1 < n ? (size_t)B->io[g1].dn_step : B->dn_end;
+      HS_CUDA(cudaMemcpyAsync(B->h_dn + lo, B->d_dn.p + lo, hi - lo, cudaMemcpyDeviceToHost, cs));
+    }
   }
-  if (bulk)
-    HS_CUDA(cudaMemcpyAsync(B->h_dn + B->dn_sys_end, B->d_dn.p + B->dn_sys_end, B->dn_end - B->dn_sys_end, cudaMemcpyDeviceToHost, ctx->stream));
+  if (G > 1) {
+    HS_CUDA(cudaEventRecord(ctx->ev_join, ctx->side));
+    HS_CUDA(cudaStreamWaitEvent(ctx->stream, ctx->ev_join, 0));
+  }
   HS_CUDA(cudaStreamSynchronize(ctx->stream));
   for (int i : staged) memcpy(step_out[i], B->h_dn + B->io[i].dn_step, (size_t)B->items[i]->P * 4);
   return 0;

@@ -1636,9 +1636,9 @@ __global__ void __launch_bounds__(256) ba_xad_kernel(const BADesc* __restrict__ 
 // EnergyFunctional::resubstituteFPt (EnergyFunctional.cpp:249-274).  With `io` the step is also written
 // in CALLER order into the batch's D2H staging block.
 __global__ void __launch_bounds__(128) ba_resub_kernel(const BADesc* __restrict__ descs, const int* __restrict__ prefix,
-                                                       int nwin, const BAIO* __restrict__ io, char* __restrict__ dn) {
+                                                       int nwin, const BAIO* __restrict__ io, char* __restrict__ dn, int block0) {
   int lb;
-  const int win = find_window(prefix, nwin, blockIdx.x, lb);
+  const int win = find_window(prefix, nwin, blockIdx.x + block0, lb);   // block0: a launch may cover a sub-range of the batch
   const BADesc& D = descs[win];
   const BARes& r = D.r;
   const BAPts& pts = D.p;

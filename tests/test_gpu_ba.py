@@ -319,7 +319,10 @@ def test_batch_step_host_window_groups(ctx, capi, synth, monkeypatch):
         batch = capi.EnergyFunctionalBatch(ctx, efs)
         io = batch.make_io(wins, [frames] * len(wins), pinned="bound")
         outs = batch.step_host(io)
-        results.append([{k: np.array(v, copy=True) for k, v in o.items() if k != "step"} for o in outs])
+        rng = np.random.default_rng(12)
+        steps = batch.resubstitute_host(io, [rng.normal(0, 1e-3, 8 * w.n + 4) for w in wins])
+        assert all(np.abs(st).max() > 0 for st in steps)
+        results.append([{k: np.array(v, copy=True) for k, v in o.items()} for o in outs])
         batch.close()
         for e in efs:
             e.close()
