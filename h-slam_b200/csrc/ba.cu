@@ -683,10 +683,25 @@ static int launch_top(hslam_ba* ba, int modes) {
   return 0;
 }
 
-static size_t schur_smem(int LD, int maxres) { return sc_smem_floats(LD, maxres) * sizeof(float); }
-static int schur_maxt(int LD) { int NTR = LD / 4 - 2, t = NTR * (NTR + 1) / 2; return t <= 128 ? 1 : (t <= 256 ? 2 : 5); }
+#ifndef SC_TILE8
+#define SC_TILE8 0   /* measured (64 x cfg2 windows): 8x8 tiles 409 us vs 4x4 tiles 370 us — at 128 registers only two blocks per SM stay resident and the staging phases, not the Gram loop, set the pace */
+#endif
+// 0: the 8x8-tile variant (LD <= 64, i.e. n <= 7: at most 28 tiles, one per lane); else 4x4 tiles per thread
+static int schur_maxt(int LD) {
+  if (SC_TILE8 && LD <= 64) return 0;
+  int NTR = LD / 4 - 2, t = NTR * (NTR + 1) / 2;
+  return t <= 128 ? 1 : (t <= 256 ? 2 : 5);
+}
 static int schur_ni(int maxres) { return SC_PTS * maxres <= 2 * SC_THREADS ? 2 : 4; }
+// the 8x8-tile variant reduces its eight warps through 4 x 2048 floats of the (then free) staging memory
+static size_t schur_smem(int LD, int maxres) {
+  size_t fl = sc_smem_floats(LD, maxres);
+  if (schur_maxt(LD) == 0) fl = std::max(fl, (size_t)4 * 2048);
+  return fl * sizeof(float);
+}
 template <class F> static int schur_dispatch(int maxt, int ni, F f) {
+  if (maxt == 0 && ni == 2) return f(ba_schur_kernel<0, 2>);
+  if (maxt == 0) return f(ba_schur_kernel<0, 4>);
   if (maxt == 1 && ni == 2) return f(ba_schur_kernel<1, 2>);
   if (maxt == 1) return f(ba_schur_kernel<1, 4>);
   if (maxt == 2 && ni == 2) return f(ba_schur_kernel<2, 2>);
@@ -696,7 +711,7 @@ template <class F> static int schur_dispatch(int maxt, int ni, F f) {
 static int schur_attr(size_t smem) {
   static size_t configured = 48 * 1024;
   if (smem > configured) {
-    for (int maxt : {1, 2, 5})
+    for (int maxt : {0, 1, 2, 5})
       for (int ni : {2, 4})
         TRY(schur_dispatch(maxt, ni, [&](auto k) -> int {
           HS_CUDA(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
@@ -1065,7 +1080,7 @@ static int batch_refresh(hslam_ba_batch* B) {
   HS_CUDA(cudaEventSynchronize(B->copied));
   int* pf[NPF];
   for (int k = 0; k < NPF; ++k) { pf[k] = B->h_prefix + k * (n + 1); pf[k][0] = 0; }
-  B->smem = 0; B->maxt = 1; B->ni = 2; B->any_L = false;
+  B->smem = 0; B->maxt = 0; B->ni = 2; B->any_L = false;
   for (int i = 0; i < n; ++i) {
     hslam_ba* ba = B->items[i];
     B->h_descs[i] = ba->hdesc;

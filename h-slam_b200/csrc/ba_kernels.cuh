@@ -1026,7 +1026,7 @@ template <int MAXT, int NI>
 #ifndef SC_MINB
 #define SC_MINB 3
 #endif
-__global__ void __launch_bounds__(SC_THREADS, (MAXT <= 2 && NI <= 2) ? SC_MINB : 2)
+__global__ void __launch_bounds__(SC_THREADS, (MAXT >= 1 && MAXT <= 2 && NI <= 2) ? SC_MINB : 2)
 ba_schur_kernel(const BADesc* __restrict__ descs, const int* __restrict__ prefix, int nwin) {
   extern __shared__ __align__(16) float smem[];
   int lb;
@@ -1044,10 +1044,27 @@ ba_schur_kernel(const BADesc* __restrict__ descs, const int* __restrict__ prefix
   const int s = r.rs, n = D.W.n;
   const int NT = LD / 4, NTR = NT - 2, ntiles = NTR * (NTR + 1) / 2;
   const int half = threadIdx.x >> 7;      // 0: even points of the sub-tile, 1: odd points
-  int tI[MAXT], tJ[MAXT];
-  __align__(8) float acc[MAXT][16];
+  // MAXT == 0 (n <= 7: at most 28 8x8 tiles): ONE 8x8 tile of the block-upper-triangle per LANE, the eight WARPS
+  // split the points of a sub-tile (warp w takes points w, w+8, ...) and are summed in a fixed tree at the end.
+  // An 8x8 tile costs 4 LDS.128 per 64 FMA instead of 2 per 16: half the shared-memory wavefronts of the Gram loop.
+  constexpr bool T8 = (MAXT == 0);
+  constexpr int MT = T8 ? 1 : MAXT;
+  constexpr int NACC = T8 ? 64 : 16;
+  int tI[MT], tJ[MT];
+  __align__(8) float acc[MT][NACC];
+  if (T8) {
+    const int lane = threadIdx.x & 31, NB = n;   // n block rows: the n+1 8-blocks of a_p without the host's own
+    tI[0] = tJ[0] = -1;
+    if (lane < NB * (NB + 1) / 2) {
+      tri_decode(lane, NB, tI[0], tJ[0]);
+      if (tI[0] >= ch.host) tI[0] += 1;
+      if (tJ[0] >= ch.host) tJ[0] += 1;
+    }
 #pragma unroll
-  for (int j = 0; j < MAXT; ++j) {
+    for (int i = 0; i < NACC; ++i) acc[0][i] = 0.f;
+  }
+#pragma unroll
+  for (int j = 0; j < (T8 ? 0 : MT); ++j) {
     int tile = (threadIdx.x & 127) + j * 128;
     tI[j] = tJ[j] = -1;
     if (tile < ntiles) {
@@ -1231,8 +1248,28 @@ ba_schur_kernel(const BADesc* __restrict__ descs, const int* __restrict__ prefix
     }
     __syncthreads();
     // phase 2: G += sum_p (w_p a_p) a_p^T, 4x4 register tiles, this thread's half of the points in order
+    if (T8) {
+      if (tI[0] >= 0) {
+        const float* ap = WA + 8 * tI[0];
+        const float* bp = A + 8 * tJ[0];
+        float2* acc2 = reinterpret_cast<float2*>(acc[0]);
+#pragma unroll 2
+        for (int lp = threadIdx.x >> 5; lp < cnt; lp += SC_THREADS / 32) {
+          const float4 a0 = *reinterpret_cast<const float4*>(ap + lp * LDP), a1 = *reinterpret_cast<const float4*>(ap + lp * LDP + 4);
+          const float4 b0 = *reinterpret_cast<const float4*>(bp + lp * LDP), b1 = *reinterpret_cast<const float4*>(bp + lp * LDP + 4);
+          const float a8[8] = {a0.x, a0.y, a0.z, a0.w, a1.x, a1.y, a1.z, a1.w};
+          const float2 bb[4] = {make_float2(b0.x, b0.y), make_float2(b0.z, b0.w), make_float2(b1.x, b1.y), make_float2(b1.z, b1.w)};
 #pragma unroll
-    for (int j = 0; j < MAXT; ++j) {
+          for (int ii = 0; ii < 8; ++ii) {
+            const float2 aa = make_float2(a8[ii], a8[ii]);
+#pragma unroll
+            for (int jj = 0; jj < 4; ++jj) acc2[4 * ii + jj] = __ffma2_rn(aa, bb[jj], acc2[4 * ii + jj]);
+          }
+        }
+      }
+    }
+#pragma unroll
+    for (int j = 0; j < (T8 ? 0 : MT); ++j) {
       if (tI[j] >= 0) {
         const float* ap = WA + 4 * tI[j];
         const float* bp = A + 4 * tJ[j];
@@ -1268,6 +1305,35 @@ ba_schur_kernel(const BADesc* __restrict__ descs, const int* __restrict__ prefix
   }
   // the odd-point halves go through shared memory (A is free now), the even-point threads add and store
   float* out = D.scpartial + (size_t)lb * LD * LD;
+  if (T8) {
+    // fixed tree over the eight warps through shared memory (the staging memory is free now; the host sizes it >= 4*2048 floats),
+    // component-major [k][lane]: conflict-free.  (4..7 -> 0..3), (2,3 -> 0,1), (1 -> 0); warp 0 stores.
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+#pragma unroll
+    for (int span = 4; span >= 1; span >>= 1) {
+      if (warp >= span && warp < 2 * span) {
+        float* buf = A + (size_t)(warp - span) * 2048 + lane;
+#pragma unroll
+        for (int k = 0; k < 64; ++k) buf[32 * k] = acc[0][k];
+      }
+      __syncthreads();
+      if (warp < span) {
+        const float* buf = A + (size_t)warp * 2048 + lane;
+#pragma unroll
+        for (int k = 0; k < 64; ++k) acc[0][k] += buf[32 * k];
+      }
+      __syncthreads();
+    }
+    if (warp == 0 && tI[0] >= 0) {
+#pragma unroll
+      for (int ii = 0; ii < 8; ++ii) {
+        float* o = out + (size_t)(8 * tI[0] + ii) * LD + 8 * tJ[0];
+        *reinterpret_cast<float4*>(o) = make_float4(acc[0][8 * ii], acc[0][8 * ii + 1], acc[0][8 * ii + 2], acc[0][8 * ii + 3]);
+        *reinterpret_cast<float4*>(o + 4) = make_float4(acc[0][8 * ii + 4], acc[0][8 * ii + 5], acc[0][8 * ii + 6], acc[0][8 * ii + 7]);
+      }
+    }
+    return;
+  }
 #pragma unroll
   for (int j = 0; j < MAXT; ++j) {
     float* xch = A + (size_t)((threadIdx.x & 127) + j * 128) * 16;   // <= MAXT*128*16 floats <= 2*SC_PTS*LDP
