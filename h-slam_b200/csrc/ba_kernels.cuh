@@ -1138,18 +1138,23 @@ ba_schur_kernel(const BADesc* __restrict__ descs, const int* __restrict__ prefix
 #ifndef SC_PIPELINE
 #define SC_PIPELINE 0   /* measured on B200 (8 x cfg2 windows): register prefetch of the next sub-tile 63.9 us, plain staging 61.4 us */
 #endif
-#if SC_PIPELINE
+#if SC_PIPELINE == 1
   // prologue: slots of sub-tile 0 -> data of sub-tile 0; slots of sub-tile 1
   load_slots(0);
   load_data(0);
   load_slots(SC_PTS);
+#elif SC_PIPELINE == 2
+  load_slots(0);   // slot entries only (one register per item) run one sub-tile ahead: one dependent round trip less
 #endif
 
   for (int base = 0; base < ch.count; base += SC_PTS) {
     const int cnt = min(SC_PTS, ch.count - base);
-#if !SC_PIPELINE
+#if SC_PIPELINE == 0
     load_slots(base);
     load_data(base);
+#elif SC_PIPELINE == 2
+    load_data(base);
+    load_slots(base + SC_PTS);   // consumed at the top of the next iteration
 #endif
     for (int i = threadIdx.x; i < SC_PTS * LDP / 4; i += SC_THREADS) reinterpret_cast<float4*>(A)[i] = make_float4(0.f, 0.f, 0.f, 0.f);
     __syncthreads();
@@ -1173,7 +1178,7 @@ ba_schur_kernel(const BADesc* __restrict__ descs, const int* __restrict__ prefix
     for (int rd = 0; rd < NRD; ++rd) { prc[rd] = pr[rd]; dec[rd] = de[rd]; }
     // ... and the loads of the NEXT sub-tile (data) and the one after (slots) are issued: they complete
     // while phases 1b and 2 run
-#if SC_PIPELINE
+#if SC_PIPELINE == 1
     load_data(base + SC_PTS);
     load_slots(base + 2 * SC_PTS);
 #endif

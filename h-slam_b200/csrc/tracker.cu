@@ -352,6 +352,52 @@ __device__ __forceinline__ void warp_ldlt_solve(double (*A)[9], double* y, int n
   }
 }
 
+// The same factorisation and solves with each row in REGISTERS and warp shuffles instead of shared memory and
+// __syncwarp between dependent steps (the shared-memory version cost ~7000 cycles per solve: eight divisions, each
+// followed by a serial loop of dependent shared-memory read-modify-writes).  Same operations on the same values in
+// the same order per element.  All 32 lanes call; lanes >= n only take part in the shuffles.
+__device__ __forceinline__ void warp_ldlt_solve_reg(double (*A)[9], double* y, int n, int lane) {
+  const int row = lane & 7;
+  double a[8], t[8], yy = y[row];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) { a[j] = A[row][j]; t[j] = 0.0; }
+#pragma unroll
+  for (int k = 0; k < 8; ++k) {
+    if (k < n) {   // uniform
+      const double d = __shfl_sync(0xffffffffu, a[k], k);
+      const bool mine = lane > k && lane < n;
+      double lik = 0.0;
+      if (mine) { lik = a[k] / d; a[k] = lik; }
+#pragma unroll
+      for (int j = k + 1; j < 8; ++j) {
+        const double ljk = __shfl_sync(0xffffffffu, a[k], j);   // L[j][k]
+        if (mine && j <= lane) a[j] -= lik * d * ljk;
+        if (lane == k) t[j] = ljk;                              // column k of L, for the transposed solve
+      }
+    }
+  }
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {          // L z = rhs
+    if (i < n) {
+      const double zi = __shfl_sync(0xffffffffu, yy, i);
+      if (lane > i && lane < n) yy -= a[i] * zi;
+    }
+  }
+  double diag = a[0];
+#pragma unroll
+  for (int j = 1; j < 8; ++j) if (row == j) diag = a[j];
+  if (lane < n) yy = yy / diag;          // D
+#pragma unroll
+  for (int i = 7; i >= 0; --i) {         // L^T x = z
+    if (i < n) {
+      const double xi = __shfl_sync(0xffffffffu, yy, i);
+      if (lane < i) yy -= t[i] * xi;
+    }
+  }
+  if (lane < n) y[lane] = yy;
+  __syncwarp();
+}
+
 __device__ void d_matmul3(const double* A, const double* B, double* C) {
   double t[9];
   for (int i = 0; i < 3; ++i)
@@ -565,7 +611,14 @@ __global__ void __launch_bounds__(THREADS) trk_track_kernel(TrackArgs a, float* 
           sy[lane] = -s.b[sb];
         }
         __syncwarp();
+#ifndef TRK_LDLT_REG
+#define TRK_LDLT_REG 1
+#endif
+#if TRK_LDLT_REG
+        warp_ldlt_solve_reg(sA, sy, nsolve, lane);
+#else
         warp_ldlt_solve(sA, sy, nsolve, lane);
+#endif
       }
       if (threadIdx.x == 0) {
         iters[lvl]++;
