@@ -42,6 +42,7 @@ struct hslam_ba {
   int n = 0, P = 0, R = 0, rs = 0, LD = 0, N = 0;
   bool have_window = false, have_topology = false;
   int add_priors = 1;
+  bool tmap_ok = true;                   // the Jacobian tensor maps of the top kernel could be encoded
   // window tables
   DevBuf<float> d_precalc, d_adHTd;
   DevBuf<double> d_adH, d_adT, d_fprior, d_fdprior;
@@ -186,8 +187,35 @@ template <class T> static int download_pts(hslam_ba* ba, const T* dev, int comps
 }
 
 // ---------------------------------------------------------------- descriptor
+// cuTensorMapEncodeTiled through the runtime's driver entry point (no link against libcuda)
+typedef CUresult (*hs_encode_tiled_fn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                       const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                       CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+static hs_encode_tiled_fn hs_encode_tiled() {
+  static hs_encode_tiled_fn fn = []() -> hs_encode_tiled_fn {
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) != cudaSuccess || q != cudaDriverEntryPointSuccess)
+      return nullptr;
+    return (hs_encode_tiled_fn)p;
+  }();
+  return fn;
+}
+// J[JS][rs] as a 2-D tensor (inner = residual); box = TOP_ROW residuals x `rows` component rows
+static bool encode_J_map(CUtensorMap* out, float* J, int rs, int rows) {
+  hs_encode_tiled_fn fn = hs_encode_tiled();
+  if (!fn || !J) return false;
+  const cuuint64_t gdim[2] = {(cuuint64_t)rs, (cuuint64_t)JS};
+  const cuuint64_t gstride[1] = {(cuuint64_t)rs * sizeof(float)};
+  const cuuint32_t box[2] = {(cuuint32_t)TOP_ROW, (cuuint32_t)rows};
+  const cuuint32_t estr[2] = {1, 1};
+  return fn(out, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, J, gdim, gstride, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+            CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+}
+
 static void fill_desc(hslam_ba* ba) {
   BADesc& D = ba->hdesc;
+  ba->tmap_ok = ba->R == 0 || (encode_J_map(&D.tmapJ[0], ba->d_J.p, ba->rs, 22) && encode_J_map(&D.tmapJ[1], ba->d_J.p, ba->rs, 17));
   BARes& r = D.r;
   r.R = ba->R; r.rs = ba->rs;
   r.point = ba->d_rpoint.p; r.pair = ba->d_rpair.p;
@@ -536,7 +564,7 @@ int hslam_ba_set_topology(hslam_ba* ba, const hslam_point_soa* pt, const hslam_r
   for (int m = 0; m < 2; ++m) { TRY(ba->d_Hdd[m].ensure(P + 1)); TRY(ba->d_bd[m].ensure(P + 1)); TRY(ba->d_Hcd[m].ensure(P + 1)); }
   TRY(ba->d_ptc[0].ensure(6 * rsz));
   TRY(ba->d_rpoint.ensure(rsz)); TRY(ba->d_rpair.ensure(rsz)); TRY(ba->d_state.ensure(rsz)); TRY(ba->d_newState.ensure(rsz));
-  TRY(ba->d_isLin.ensure(rsz)); TRY(ba->d_isActive.ensure(rsz)); TRY(ba->d_senergy.ensure(rsz)); TRY(ba->d_newEnergy.ensure(rsz));
+  TRY(ba->d_isLin.ensure(rsz + 256)); TRY(ba->d_isActive.ensure(rsz + 256)); /* + slack: the top kernel copies whole 160-byte flag rows */ TRY(ba->d_senergy.ensure(rsz)); TRY(ba->d_newEnergy.ensure(rsz));
   TRY(ba->d_newEnergyWO.ensure(rsz)); TRY(ba->d_J.ensure((size_t)JS * rsz + 2 * TOP_ROW)); /* + slack: the top kernel stages whole rows */ TRY(ba->d_JpJdF.ensure(8 * rsz));
   TRY(ba->d_rtz.ensure(8 * rsz)); TRY(ba->d_cpt.ensure(3 * rsz)); TRY(ba->d_pto.ensure(16 * rsz));
   // ---- pack + upload points
@@ -656,7 +684,7 @@ static int launch_linearize(hslam_ba* ba, bool apply) {
   return 0;
 }
 
-static const size_t kTopSmem = TOP_STAGES * sizeof(TopStage);
+static const size_t kTopSmem = TOP_STAGES * sizeof(TopStage) + 128;   // + alignment slack (TMA destinations)
 static int top_attr() {
   static bool done = false;
   if (!done) {
@@ -672,6 +700,7 @@ static int launch_top(hslam_ba* ba, int modes) {
   hslam_ctx* ctx = ba->ctx;
   TRY(sync_desc(ba));
   TRY(top_attr());
+  HS_ARG(ba->tmap_ok, "hslam_ba: cuTensorMapEncodeTiled failed for the Jacobian tensor maps (driver too old?)");
   const int T = ba->n_topchunks[0];
   if (T > 0 && (modes & 1))
     HS_LAUNCH(ctx, HSLAM_K_BA_TOP, (ba_top_kernel<0><<<T, 2 * TOP_THREADS, kTopSmem, ctx->stream>>>(ba->d_desc.p, nullptr, 1)));
@@ -1074,6 +1103,7 @@ static int batch_refresh(hslam_ba_batch* B) {
   for (int i = 0; i < n; ++i) {
     hslam_ba* ba = B->items[i];
     HS_ARG(ba->have_window && ba->have_topology, "hslam_ba_batch: a window has no window/topology set");
+    HS_ARG(ba->tmap_ok, "hslam_ba_batch: cuTensorMapEncodeTiled failed for the Jacobian tensor maps (driver too old?)");
     if (B->versions[i] != ba->desc_version) dirty = true;
   }
   if (!dirty) return 0;

@@ -18,6 +18,7 @@
 // per-chunk partials folded BY CHUNK INDEX (the last-arriving block of a pair/host does the fold, the
 // order of the sum does not depend on which block that is), gather-style stitch.
 #pragma once
+#include <cuda.h>   // CUtensorMap (type only: the encoder is fetched through cudaGetDriverEntryPoint)
 #include "common.cuh"
 
 namespace hs {
@@ -151,6 +152,9 @@ struct BADesc {
   double* x;                 // (8n+4) solution of the reduced system (uploaded by resubstitute)
   float* xc;                 // [4]      calibration step, float
   float* xAd;                // [n*n][8] per-pair adjoint-mapped frame steps (EnergyFunctional.cpp:236-238)
+  // 2-D tensor maps over the SoA Jacobian J[JS][rs] (inner dimension = residual): boxes of TOP_ROW residuals x 22 rows
+  // (rows 8..29) and x 17 rows (rows 62..78): the two TMA loads that fill one stage of the top kernel's ring
+  alignas(64) CUtensorMap tmapJ[2];
 };
 
 // Per-window byte offsets into the batch staging blocks (one H2D block `up`, one D2H block `dn`);
@@ -544,7 +548,7 @@ __global__ void ba_fixlin_kernel(BAWin W, BARes r, BAPts pts, const int* __restr
 // per-residual point terms): half the accumulator registers per thread, twice the warps in flight.
 // Loads that only feed the other part's entries are dead code in each instantiation.
 template <int MODE, int PART>
-__device__ __forceinline__ void top_accumulate(const BADesc& D, const TopChunk& ch, float (&acc)[55], int& nres) {
+__device__ __forceinline__ void top_accumulate(const BADesc& D, const TopChunk& ch, float (&acc)[56], int& nres) {
   const BAWin& W = D.W;
   const BARes& r = D.r;
   const int s = r.rs;
@@ -651,8 +655,12 @@ __device__ __forceinline__ void top_accumulate(const BADesc& D, const TopChunk& 
 // 80 components each) keep the direct per-thread path.
 constexpr int TOP_NC = 39;   // staged components: J[8..29] (Jpdxi, Jpdc, Jpdd) and J[62..78] (the 2x2 sums, JI_r, Jab_r, rr)
 __device__ __forceinline__ int top_comp(int c) { return c < 22 ? J_XI0 + c : J_IDX2 + (c - 22); }
-constexpr int TS_XI0 = 0, TS_XI1 = 6, TS_C0 = 12, TS_C1 = 16, TS_DD = 20, TS_IDX2 = 22, TS_ABIDX = 26, TS_AB2 = 30,
-              TS_JIR = 34, TS_JABR = 36, TS_RR = 38;
+// stage rows: components 0..21 in rows 0..21, components 22..38 in rows 24..40 (row 24 starts on a 128-byte boundary:
+// the destination of the second TMA box)
+constexpr int TS_XI0 = 0, TS_XI1 = 6, TS_C0 = 12, TS_C1 = 16, TS_DD = 20, TS_IDX2 = 24, TS_ABIDX = 28, TS_AB2 = 32,
+              TS_JIR = 36, TS_JABR = 38, TS_RR = 40;
+constexpr int TOP_NR = 41;   // stage rows
+__device__ __forceinline__ int top_row(int c) { return c < 22 ? c : c + 2; }
 
 __device__ __forceinline__ void cp_async16(void* smem_dst, const void* gsrc) {
   unsigned sa = (unsigned)__cvta_generic_to_shared(smem_dst);
@@ -688,6 +696,10 @@ __device__ __forceinline__ void mbar_wait(uint64_t* b, unsigned parity) {
   while (!mbar_try_wait(b, parity))
     if (clock64() - t0 > 4000000000LL) __trap();   // a protocol bug must fail the launch, not hang the device
 }
+__device__ __forceinline__ void tma_load_2d(void* dst, const CUtensorMap* map, int c0, int c1, uint64_t* bar) {
+  asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];"
+               ::"r"(smem_u32(dst)), "l"(map), "r"(c0), "r"(c1), "r"(smem_u32(bar)) : "memory");
+}
 __device__ __forceinline__ void bulk_g2s(void* dst, const void* src, unsigned bytes, uint64_t* bar) {
   asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
                ::"r"(smem_u32(dst)), "l"(src), "r"(bytes), "r"(smem_u32(bar)) : "memory");
@@ -699,14 +711,15 @@ __device__ __forceinline__ void bulk_g2s(void* dst, const void* src, unsigned by
 // sits in column (start & 3) + l.
 constexpr int TOP_STAGES = 4;
 constexpr int TOP_ROW = 136;
-struct TopStage {
-  float v[TOP_NC][TOP_ROW];
-  unsigned char lin[TOP_ROW], act[TOP_ROW];
+constexpr int TOP_FROW = 160;   // flag rows: the 16-byte-aligned span that covers a tile, <= 128 + 15 + 15 bytes
+struct alignas(128) TopStage {
+  float v[TOP_NR][TOP_ROW];
+  unsigned char lin[TOP_FROW], act[TOP_FROW];
 };
-static_assert(sizeof(TopStage) % 16 == 0, "stage must keep 16-byte alignment");
+static_assert(sizeof(TopStage) % 128 == 0 && (24 * TOP_ROW * 4) % 128 == 0, "TMA box destinations are 128-byte aligned");
 
 // chunk partial -> global, then the per-(mode,pair) fold by the last block of that pair (chunks in index order)
-__device__ __forceinline__ void top_flush(const BADesc& D, int chunk, int part, float (&acc)[55], int nres,
+__device__ __forceinline__ void top_flush(const BADesc& D, int chunk, int part, float (&acc)[56], int nres,
                                           float (*red)[33], bool* last) {
   // two shuffle levels take a warp's 32 lanes to 8, the remaining 8 lanes x 4 warps = 32 values per
   // accumulator are summed in a fixed order by one thread per accumulator (a full shuffle tree per
@@ -773,8 +786,9 @@ __device__ __forceinline__ void top_flush(const BADesc& D, int chunk, int part, 
 template <int MODE>
 __global__ void __launch_bounds__(2 * TOP_THREADS, 2) ba_top_kernel(const BADesc* __restrict__ descs,
                                                                     const int* __restrict__ prefix, int nwin) {
-  extern __shared__ __align__(16) unsigned char top_smem[];
-  TopStage* ring = reinterpret_cast<TopStage*>(top_smem);
+  extern __shared__ __align__(128) unsigned char top_smem[];
+  // 128-byte alignment in the shared window (the launch reserves 128 spare bytes)
+  TopStage* ring = reinterpret_cast<TopStage*>(top_smem + ((128u - (smem_u32(top_smem) & 127u)) & 127u));
   __shared__ float red[92][33];   // [accumulator][4 warps x 8 lanes], padded: conflict-free both ways
   __shared__ bool last;
   int lb;
@@ -787,13 +801,13 @@ __global__ void __launch_bounds__(2 * TOP_THREADS, 2) ba_top_kernel(const BADesc
   const int t0 = D.top_block_begin[bIdx], t1 = D.top_block_begin[bIdx + 1];
   const int part = threadIdx.x / TOP_THREADS;   // warp-uniform
   const int l = threadIdx.x & (TOP_THREADS - 1);
-  float acc[55];
+  __align__(8) float acc[56];   // 55 used (+1: packed pairs)
 #pragma unroll
-  for (int i = 0; i < 55; ++i) acc[i] = 0.f;
+  for (int i = 0; i < 56; ++i) acc[i] = 0.f;
   int nres = 0, cur = -1;
 
 #ifndef TOP_BULK
-#define TOP_BULK 1
+#define TOP_BULK 2   /* 0: cp.async ring, 1: one bulk copy per component row, 2: two tensor-map loads per stage */
 #endif
 #if TOP_BULK
   // Mode A: the 39 component rows of a tile are 39 contiguous 544-byte spans of the SoA Jacobian: one bulk copy
@@ -821,12 +835,23 @@ __global__ void __launch_bounds__(2 * TOP_THREADS, 2) ba_top_kernel(const BADesc
     if (tp >= t1) return;
     const int stg = jp % TOP_STAGES, use = jp / TOP_STAGES;
     if (use > 0) mbar_wait(&empty_bar[stg], (unsigned)(use - 1) & 1u);
-    if (lane == 0) mbar_expect_tx(&full_bar[stg], TOP_NC * TOP_ROW * 4);
+    if (lane == 0) mbar_expect_tx(&full_bar[stg], TOP_NC * TOP_ROW * 4 + 2 * TOP_FROW);
     __syncwarp();
     const TopTile tlp = D.toptiles[tp];
-    const float* src = r.J + (tlp.start & ~3);
     TopStage& st = ring[stg];
-    for (int c = lane; c < TOP_NC; c += 32) bulk_g2s(&st.v[c][0], src + (size_t)top_comp(c) * s, TOP_ROW * 4, &full_bar[stg]);
+    // the two flag rows ride along (a consumer that loaded them itself had a DRAM round trip on its critical path)
+    if (lane == 2) bulk_g2s(st.lin, r.isLin + (tlp.start & ~15), TOP_FROW, &full_bar[stg]);
+    else if (lane == 3) bulk_g2s(st.act, r.isActive + (tlp.start & ~15), TOP_FROW, &full_bar[stg]);
+#if TOP_BULK == 2
+    // two tensor-map loads per stage: the TMA unit serves one request in ~46 cycles whatever its size, 39 row copies
+    // per 21 kB stage made the kernel TMA-issue-bound (3.4 TB/s)
+    if (lane == 0) tma_load_2d(&st.v[0][0], &D.tmapJ[0], tlp.start & ~3, J_XI0, &full_bar[stg]);
+    else if (lane == 1) tma_load_2d(&st.v[24][0], &D.tmapJ[1], tlp.start & ~3, J_IDX2, &full_bar[stg]);
+#else
+    const float* src = r.J + (tlp.start & ~3);
+    for (int c = lane >= 4 ? lane - 4 : lane + 28; c < TOP_NC; c += 32)
+      bulk_g2s(&st.v[top_row(c)][0], src + (size_t)top_comp(c) * s, TOP_ROW * 4, &full_bar[stg]);
+#endif
   };
   if (mode == 0 && warp == 0) {
 #pragma unroll
@@ -851,15 +876,12 @@ __global__ void __launch_bounds__(2 * TOP_THREADS, 2) ba_top_kernel(const BADesc
       if (part == 0) top_accumulate<(MODE ? MODE : 1), 0>(D, ch, acc, nres); else top_accumulate<(MODE ? MODE : 1), 1>(D, ch, acc, nres);
       continue;
     }
-    // the residual's flags come straight from global memory, issued before the wait
-    unsigned char f_lin = 1, f_act = 0;
-    if (l < tl.count) { f_lin = r.isLin[tl.start + l]; f_act = r.isActive[tl.start + l]; }
     if (warp == (j & (NW - 1))) produce(j + TOP_DEPTH);
     mbar_wait(&full_bar[j % TOP_STAGES], (unsigned)(j / TOP_STAGES) & 1u);
     const TopStage& S = ring[j % TOP_STAGES];
-    const int col = (tl.start & 3) + l;
+    const int col = (tl.start & 3) + l, cf = (tl.start & 15) + l;
     // AccumulatedTopHessian.cpp:37-49, mode 0: !isLinearized && isActive
-    if (f_lin == 0 && f_act != 0) {
+    if (l < tl.count && S.lin[cf] == 0 && S.act[cf] != 0) {
 #else
   // all 256 threads: 39 rows x 34 sixteen-byte copies (always the full row: constant trip count and constant
   // divisor; the columns past the tile are never read) + the two flag rows; one commit group per tile
@@ -873,7 +895,7 @@ __global__ void __launch_bounds__(2 * TOP_THREADS, 2) ba_top_kernel(const BADesc
       for (int j = 0; j < (TOP_NC * RQ + 2 * TOP_THREADS - 1) / (2 * TOP_THREADS); ++j) {
         const int i = threadIdx.x + j * 2 * TOP_THREADS;
         const int c = i / RQ, q = i - c * RQ;
-        if (i < TOP_NC * RQ) cp_async16(&st.v[c][4 * q], src + (size_t)top_comp(c) * s + 4 * q);
+        if (i < TOP_NC * RQ) cp_async16(&st.v[top_row(c)][4 * q], src + (size_t)top_comp(c) * s + 4 * q);
       }
       const int nq = ((tl.start + tl.count + 3) >> 2) - (tl.start >> 2);   // flag words that cover the tile
       if (threadIdx.x < nq) cp_async4(&st.lin[4 * threadIdx.x], r.isLin + (tl.start & ~3) + 4 * threadIdx.x);
@@ -918,6 +940,29 @@ __global__ void __launch_bounds__(2 * TOP_THREADS, 2) ba_top_kernel(const BADesc
       const float a = S.v[TS_IDX2 + 0][col], b = S.v[TS_IDX2 + 2][col], c = S.v[TS_IDX2 + 3][col];
       if (part == 0) {
         // 10x10 upper triangle: [x y] [[a b],[b c]] [x y]^T
+#ifndef TOP_FFMA2
+#define TOP_FFMA2 1
+#endif
+#if TOP_FFMA2
+        // packed fp32 (FMUL2 / FFMA2 / FADD2): two neighbouring columns per instruction, every lane rounded exactly
+        // like the scalar sequence  acc += fmaf(x, px, y * py)
+        float2* acc2 = reinterpret_cast<float2*>(acc);
+        int idx = 0;
+#pragma unroll
+        for (int rI = 0; rI < 10; ++rI) {
+          const float px = fmaf(a, x[rI], b * y[rI]), py = fmaf(b, x[rI], c * y[rI]);
+          int cI = rI;
+          if (idx & 1) { acc[idx] += fmaf(x[cI], px, y[cI] * py); ++cI; ++idx; }
+          const float2 px2 = make_float2(px, px), py2 = make_float2(py, py);
+#pragma unroll
+          for (; cI + 1 < 10; cI += 2, idx += 2) {
+            const float2 t = __fmul2_rn(make_float2(y[cI], y[cI + 1]), py2);
+            const float2 u = __ffma2_rn(make_float2(x[cI], x[cI + 1]), px2, t);
+            acc2[idx >> 1] = __fadd2_rn(acc2[idx >> 1], u);
+          }
+          if (cI < 10) { acc[idx] += fmaf(x[cI], px, y[cI] * py); ++idx; }
+        }
+#else
         int idx = 0;
 #pragma unroll
         for (int rI = 0; rI < 10; ++rI) {
@@ -925,6 +970,7 @@ __global__ void __launch_bounds__(2 * TOP_THREADS, 2) ba_top_kernel(const BADesc
 #pragma unroll
           for (int cI = rI; cI < 10; ++cI, ++idx) acc[idx] += fmaf(x[cI], px, y[cI] * py);
         }
+#endif
       } else {
         const float AI00 = S.v[TS_ABIDX + 0][col], AI10 = S.v[TS_ABIDX + 1][col], AI01 = S.v[TS_ABIDX + 2][col],
                     AI11 = S.v[TS_ABIDX + 3][col];
