@@ -858,8 +858,10 @@ __global__ void __launch_bounds__(2 * TOP_THREADS, 2) ba_top_kernel(const BADesc
     for (int i = 0; i < TOP_DEPTH; ++i) produce(i);
   }
 
+  TopTile tl_next = t0 < t1 ? D.toptiles[t0] : TopTile{0, 0, 0, 0};
   for (int t = t0; t < t1; ++t) {
-    const TopTile tl = D.toptiles[t];
+    const TopTile tl = tl_next;
+    if (t + 1 < t1) tl_next = D.toptiles[t + 1];   // the next descriptor is in flight while this tile is consumed
     const int j = t - t0;
     const int chunk = tl.chunk + (mode ? 1 : 0) * D.top_chunks0;   // modes 1 and 2 share the second accumulator set
     if (chunk != cur) {
