@@ -1202,7 +1202,7 @@ static int batch_enqueue_linearize(hslam_ba_batch* B, int g0 = 0, int g1 = -1) {
   if (g1 < 0) g1 = n;
   const int b0 = B->h_prefix[g0], cnt = B->h_prefix[g1] - b0;   // table 0 = linearise blocks
   if (cnt <= 0) return 0;
-  HS_LAUNCH(ctx, HSLAM_K_BA_LINEARIZE, (ba_linearize_kernel<true><<<cnt, LIN_THREADS, 0, ctx->stream>>>(B->d_descs.p, B->d_prefix.p, n, b0)));
+  HS_LAUNCH(ctx, HSLAM_K_BA_LINEARIZE, (ba_linearize_kernel<true><<<cnt, LIN_THREADS, 0, ctx->stream>>>(B->d_descs.p, B->d_prefix.p, B->uniform[0] ? -B->uniform[0] : n, b0)));
   HS_CUDA(cudaGetLastError());
   return 0;
 }
@@ -1213,12 +1213,12 @@ static int batch_enqueue_accumulate(hslam_ba_batch* B) {
   TRY(schur_attr(B->smem));
   TRY(top_attr());
   if (B->blocks[1] > 0) {
-    HS_LAUNCH(ctx, HSLAM_K_BA_TOP, (ba_top_kernel<0><<<B->blocks[1], 2 * TOP_THREADS, kTopSmem, ctx->stream>>>(B->d_descs.p, pf + (n + 1), n)));
+    HS_LAUNCH(ctx, HSLAM_K_BA_TOP, (ba_top_kernel<0><<<B->blocks[1], 2 * TOP_THREADS, kTopSmem, ctx->stream>>>(B->d_descs.p, pf + (n + 1), B->uniform[1] ? -B->uniform[1] : n)));
     if (B->any_L)
-      HS_LAUNCH(ctx, HSLAM_K_BA_TOP, (ba_top_kernel<1><<<B->blocks[1], 2 * TOP_THREADS, kTopSmem, ctx->stream>>>(B->d_descs.p, pf + (n + 1), n)));
+      HS_LAUNCH(ctx, HSLAM_K_BA_TOP, (ba_top_kernel<1><<<B->blocks[1], 2 * TOP_THREADS, kTopSmem, ctx->stream>>>(B->d_descs.p, pf + (n + 1), B->uniform[1] ? -B->uniform[1] : n)));
   }
   if (B->blocks[2] > 0)
-    HS_LAUNCH(ctx, HSLAM_K_BA_SCHUR, schur_launch(B->maxt, B->ni, B->blocks[2], B->smem, ctx->stream, B->d_descs.p, pf + 2 * (n + 1), n));
+    HS_LAUNCH(ctx, HSLAM_K_BA_SCHUR, schur_launch(B->maxt, B->ni, B->blocks[2], B->smem, ctx->stream, B->d_descs.p, pf + 2 * (n + 1), B->uniform[2] ? -B->uniform[2] : n));
   HS_LAUNCH(ctx, HSLAM_K_BA_FOLD_SC, (ba_fold_sc_kernel<<<B->blocks[4], 256, 0, ctx->stream>>>(B->d_descs.p, pf + 4 * (n + 1), B->uniform[4] ? -B->uniform[4] : n)));
   HS_LAUNCH(ctx, HSLAM_K_BA_STITCH, (ba_stitch_kernel<<<B->blocks[3], ST_THREADS, 0, ctx->stream>>>(B->d_descs.p, pf + 3 * (n + 1), B->uniform[3] ? -B->uniform[3] : n, 0, 3, 1)));
   HS_CUDA(cudaGetLastError());
@@ -1570,7 +1570,7 @@ int hslam_ba_batch_resubstitute_host(hslam_ba_batch* B, const double* const* x, 
     const int b0 = hp[g0], cnt = hp[g1] - b0;
     if (cnt > 0)
       HS_LAUNCH(ctx, HSLAM_K_BA_RESUB, (ba_resub_kernel<<<cnt, 128, 0, ctx->stream>>>(
-                                           B->d_descs.p, B->d_prefix.p + 5 * (n + 1), n, d_io, B->d_dn.p, b0)));
+                                           B->d_descs.p, B->d_prefix.p + 5 * (n + 1), B->uniform[5] ? -B->uniform[5] : n, d_io, B->d_dn.p, b0)));
     HS_CUDA(cudaGetLastError());
     cudaStream_t cs = ctx->stream;
     if (G > 1) {
