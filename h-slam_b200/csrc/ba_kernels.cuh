@@ -1195,6 +1195,11 @@ ba_schur_kernel(const BADesc* __restrict__ descs, const int* __restrict__ prefix
   load_slots(0);   // slot entries only (one register per item) run one sub-tile ahead: one dependent round trip less
 #endif
 
+  // padding columns [8n+5, LD) of the scaled rows: zero once (phase 1b only ever writes the columns below)
+  for (int i = threadIdx.x; i < SC_PTS * 4; i += SC_THREADS) {
+    const int q = 8 * n + 5 + (i & 3);
+    if (q < LD) WA[(i >> 2) * LDP + q] = 0.f;
+  }
   for (int base = 0; base < ch.count; base += SC_PTS) {
     const int cnt = min(SC_PTS, ch.count - base);
 #if SC_PIPELINE == 0
@@ -1241,14 +1246,17 @@ ba_schur_kernel(const BADesc* __restrict__ descs, const int* __restrict__ prefix
       if (c < 6) {
         if (lp < cnt && (!D.marg || D.marg[ch.start + base + lp] != 0)) {
           const int p = ch.start + base + lp;
+          // branch-free: a slot that is absent / inactive adds +0 (exact), its stale value is never selected
           float sum[2] = {0.f, 0.f};
           int ngood = 0;
+          const float* fl = stg + 6 * SNP + lp * MR;
+          const float* vl = stg + c * SNP + lp * MR;
+#pragma unroll 2
           for (int slot = 0; slot < maxres; ++slot) {
-            const int si = lp * MR + slot;
-            const int f = (int)stg[6 * SNP + si];
-            if (f == 0) continue;
-            ngood++;
-            sum[f - 1] = xadd(sum[f - 1], stg[c * SNP + si]);
+            const float f = fl[slot], v = vl[slot];
+            ngood += (f != 0.f) ? 1 : 0;
+            sum[0] = xadd(sum[0], f == 1.f ? v : 0.f);
+            sum[1] = xadd(sum[1], f == 2.f ? v : 0.f);
           }
           float mine = 0.f;   // this lane's entry of a_p (columns 8n .. 8n+4)
           float hdi = 0.f;
@@ -1292,7 +1300,6 @@ ba_schur_kernel(const BADesc* __restrict__ descs, const int* __restrict__ prefix
         const int colb = 8 * n;
         if (c == 0) { A[lp * LDP + colb + 4] = rowv; WA[lp * LDP + colb + 4] = hd * rowv; }
         else if (c >= 2 && c < 6) { A[lp * LDP + colb + (c - 2)] = rowv; WA[lp * LDP + colb + (c - 2)] = hd * rowv; }
-        else if (c >= 6) { for (int q = colb + 5 + (c - 6); q < LD; q += 2) WA[lp * LDP + q] = 0.f; }   // padding columns
         for (int q4 = c; q4 < 2 * n; q4 += 8) {
           const float4 v = *reinterpret_cast<const float4*>(A + lp * LDP + 4 * q4);
           *reinterpret_cast<float4*>(WA + lp * LDP + 4 * q4) = make_float4(hd * v.x, hd * v.y, hd * v.z, hd * v.w);
