@@ -457,6 +457,7 @@ int hslam_ba_set_window(hslam_ba* ba, const hslam_window* w) {
   ba->n = n; ba->N = 8 * n + 4; ba->LD = ((8 * n + 5) + 3) & ~3;
   BAWin& W = ba->hdesc.W;
   W.n = n; W.w = w->w; W.h = w->h;
+  W.n_rcp = (65536 + n - 1) / n;
   W.fx = w->fx; W.fy = w->fy; W.cx = w->cx; W.cy = w->cy; W.fxi = w->fxi; W.fyi = w->fyi;
   W.huber = ctx->prm.huberTH; W.outlierTH = ctx->prm.outlierTHSumComponent; W.scale_idepth = ctx->prm.scale_idepth;
   W.scale_f = ctx->prm.scale_f; W.scale_c = ctx->prm.scale_c; W.affA = ctx->prm.affineOptModeA; W.affB = ctx->prm.affineOptModeB;

@@ -63,6 +63,7 @@ __constant__ int c_pat[8][2] = {{0, -2}, {-1, -1}, {1, -1}, {-2, 0}, {0, 0}, {2,
 
 struct BAWin {
   int n, w, h;
+  int n_rcp;                 // ceil(2^16 / n): pair / n == (pair * n_rcp) >> 16 for pair < n*n <= 256 (no integer division per residual)
   float fx, fy, cx, cy, fxi, fyi;
   float huber, outlierTH, scale_idepth, scale_f, scale_c, affA, affB;
   float cDeltaF[4];
@@ -267,7 +268,7 @@ __global__ void __launch_bounds__(LIN_THREADS, LIN_MINB) ba_linearize_kernel(con
     float* J = r.J + k;
     STJ(r.newEnergyWO + k, -1.f);
     bool oob = (st0 == HSLAM_RES_OOB);
-    const int hostI = pair % W.n, tgtI = pair / W.n;
+    const int tgtI = (pair * W.n_rcp) >> 16, hostI = pair - tgtI * W.n;   // pair = host + target * n
     float energyLeft = 0.f, wJI2 = 0.f;
     if (!oob) {
       const float4* pc = reinterpret_cast<const float4*>(W.precalc + (size_t)HSLAM_PRECALC_STRIDE * pair);
@@ -1787,7 +1788,7 @@ __global__ void __launch_bounds__(128) ba_resub_kernel(const BADesc* __restrict_
     for (int i = rb; i < re; ++i) {
       int k = pts.res_index[i];
       if (!r.isActive[k]) continue;
-      int pair = r.pair[k], h = pair % n, t = pair / n;
+      int pair = r.pair[k], t = (pair * D.W.n_rcp) >> 16, h = pair - t * n;
       const float* xa = xAd + 8 * (n * h + t);
       float d = 0.f;
       const float4* jp = reinterpret_cast<const float4*>(r.JpJdF + 8 * (size_t)k);
