@@ -695,7 +695,7 @@ __device__ __forceinline__ void mbar_wait(uint64_t* b, unsigned parity) {
   if (mbar_try_wait(b, parity)) return;
   const long long t0 = clock64();
   while (!mbar_try_wait(b, parity))
-    if (clock64() - t0 > 4000000000LL) __trap();   // a protocol bug must fail the launch, not hang the device
+    if (clock64() - t0 > 40000000000LL) __trap();   // ~20 s: a protocol bug must fail the launch, not hang the device
 }
 __device__ __forceinline__ void tma_load_2d(void* dst, const CUtensorMap* map, int c0, int c1, uint64_t* bar) {
   asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];"
