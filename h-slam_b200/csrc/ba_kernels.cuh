@@ -981,12 +981,29 @@ __global__ void __launch_bounds__(2 * TOP_THREADS, 2) ba_top_kernel(const BADesc
         const float JIr0 = S.v[TS_JIR][col], JIr1 = S.v[TS_JIR + 1][col], Jabr0 = S.v[TS_JABR][col], Jabr1 = S.v[TS_JABR + 1][col];
         const float rr = S.v[TS_RR][col], d0 = S.v[TS_DD][col], d1 = S.v[TS_DD + 1][col];
         // 10x3 top-right: columns a, b, r  (MatrixAccumulators.h:859-901); entries 55..84 -> acc[0..29]
+#if TOP_FFMA2
+        // packed: two rows (six accumulators) as three float2 triplets, each lane rounded like the scalar sequence
+        {
+          float2* acc2 = reinterpret_cast<float2*>(acc);
+          const float2 A0 = make_float2(AI00, AI10), B0 = make_float2(AI01, AI11);
+          const float2 A1 = make_float2(JIr0, AI00), B1 = make_float2(JIr1, AI01);
+          const float2 A2 = make_float2(AI10, JIr0), B2 = make_float2(AI11, JIr1);
+#pragma unroll
+          for (int q = 0; q < 5; ++q) {
+            const float xr = x[2 * q], yr = y[2 * q], xs = x[2 * q + 1], ys = y[2 * q + 1];
+            acc2[3 * q + 0] = __fadd2_rn(acc2[3 * q + 0], __ffma2_rn(make_float2(xr, xr), A0, __fmul2_rn(make_float2(yr, yr), B0)));
+            acc2[3 * q + 1] = __fadd2_rn(acc2[3 * q + 1], __ffma2_rn(make_float2(xr, xs), A1, __fmul2_rn(make_float2(yr, ys), B1)));
+            acc2[3 * q + 2] = __fadd2_rn(acc2[3 * q + 2], __ffma2_rn(make_float2(xs, xs), A2, __fmul2_rn(make_float2(ys, ys), B2)));
+          }
+        }
+#else
 #pragma unroll
         for (int rI = 0; rI < 10; ++rI) {
           acc[3 * rI + 0] += fmaf(x[rI], AI00, y[rI] * AI01);
           acc[3 * rI + 1] += fmaf(x[rI], AI10, y[rI] * AI11);
           acc[3 * rI + 2] += fmaf(x[rI], JIr0, y[rI] * JIr1);
         }
+#endif
         acc[30] += AA00; acc[31] += AA01; acc[32] += Jabr0; acc[33] += AA11; acc[34] += Jabr1; acc[35] += rr;
         nres++;
         // per-residual contribution to the point sums (:114-117), exact ops: they are summed per point in
