@@ -114,3 +114,13 @@ def test_config5_batch_of_64_windows_matches_singles(ctx, capi, synth):
     for fl in frames:
         for f in fl:
             f.close()
+
+
+@pytest.mark.parametrize("n_frames,ppf", [(2, 3), (3, 7), (4, 33)])
+def test_tiny_ragged_windows_vs_oracle(ctx, capi, O, synth, n_frames, ppf):
+    """Windows far smaller than one tile of any kernel (R of a few residuals up to ~400: less than one 136-residual TMA
+    box of the top kernel, pair segments shorter than a 16-byte copy granule, fewer points than a Schur sub-tile):
+    same parity bar as the full-size configurations."""
+    win, _ = synth.make_window(w=320, h=240, n_frames=n_frames, points_per_frame=ppf, seed=1000 + 10 * n_frames + ppf)
+    assert 0 < win.R < 400
+    _compare_with_oracle(ctx, capi, O, win, threads=2)
