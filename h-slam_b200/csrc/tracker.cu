@@ -91,7 +91,7 @@ __device__ __forceinline__ void make_eval_const(EvalConst& c, const TrkLevelDev&
 // reduces, thread t<TRK_PART writes partial[blockIdx][t].  smem: float[TRK_THREADS/32][TRK_PART].
 // `partial` points at THIS block's TRK_PART floats (global memory, or shared memory in the cluster kernel).
 template <int THREADS>
-__device__ __forceinline__ void eval_block(const EvalConst& c, float* __restrict__ partial, float (*red)[TRK_PART],
+__device__ __forceinline__ void eval_block(const EvalConst& c, float* __restrict__ partial, float* red,
                                            int block, int nblocks) {
   float acc[TRK_NACC];
 #pragma unroll
@@ -173,37 +173,45 @@ __device__ __forceinline__ void eval_block(const EvalConst& c, float* __restrict
     }
   }
 
-  // warp tree -> smem -> fixed-order cross-warp sum
+  // Block reduction of the 52 sums.  Two shuffle levels take a warp's 32 lanes to 8; the 8 x (THREADS/32) values of
+  // every sum go to shared memory (row stride odd: conflict-free both ways); four threads per sum add a quarter of the
+  // row each in index order and are combined by two more shuffle levels — a fixed association, the same on every
+  // run.  (Five shuffle levels for every sum in every warp were 31 % of the kernel's instructions.)
+  constexpr int RW = THREADS / 4 + 1;          // row stride; THREADS/4 = 8 lanes x THREADS/32 warps entries per sum
   const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+  auto put = [&](int i, float v) {
+    v += __shfl_down_sync(0xffffffffu, v, 16);
+    v += __shfl_down_sync(0xffffffffu, v, 8);
+    if (lane < 8) red[i * RW + wid * 8 + lane] = v;
+  };
+  auto puti = [&](int i, int v) {
+    v += __shfl_down_sync(0xffffffffu, v, 16);
+    v += __shfl_down_sync(0xffffffffu, v, 8);
+    if (lane < 8) red[i * RW + wid * 8 + lane] = __int_as_float(v);
+  };
 #pragma unroll
-  for (int i = 0; i < TRK_NACC; ++i) {
-    float s = warp_sum(acc[i]);
-    if (lane == 0) red[wid][i] = s;
-  }
-  {
-    float s;
-    s = warp_sum(E);      if (lane == 0) red[wid][P_E] = s;
-    s = warp_sum(flowT);  if (lane == 0) red[wid][P_FT] = s;
-    s = warp_sum(flowRT); if (lane == 0) red[wid][P_FRT] = s;
-    s = warp_sum(flowNum); if (lane == 0) red[wid][P_FN] = s;
-    int q;
-    q = warp_sum(nE);   if (lane == 0) red[wid][P_NE] = __int_as_float(q);
-    q = warp_sum(nSat); if (lane == 0) red[wid][P_NSAT] = __int_as_float(q);
-    q = warp_sum(nW);   if (lane == 0) red[wid][P_NW] = __int_as_float(q);
-  }
+  for (int i = 0; i < TRK_NACC; ++i) put(i, acc[i]);
+  put(P_E, E); put(P_FT, flowT); put(P_FRT, flowRT); put(P_FN, flowNum);
+  puti(P_NE, nE); puti(P_NSAT, nSat); puti(P_NW, nW);
   __syncthreads();
-  if (threadIdx.x < TRK_PART) {
-    int t = threadIdx.x;
-    if (t >= P_NE && t <= P_NW) {
+  if (threadIdx.x < 4 * TRK_PART) {            // 224 threads = 7 whole warps (full-mask shuffles); rows 52..55 are padding
+    const int t = threadIdx.x >> 2, part = threadIdx.x & 3;
+    constexpr int Q = THREADS / 16;            // entries per quarter row
+    const float* row = red + t * RW + part * Q;
+    if (t >= P_NE) {
       int q = 0;
-#pragma unroll
-      for (int w = 0; w < THREADS / 32; ++w) q += __float_as_int(red[w][t]);
-      partial[t] = __int_as_float(q);
-    } else if (t < P_NE) {
-      float s = 0.f;
-#pragma unroll
-      for (int w = 0; w < THREADS / 32; ++w) s += red[w][t];
-      partial[t] = s;
+#pragma unroll 8
+      for (int j = 0; j < Q; ++j) q += __float_as_int(row[j]);
+      q += __shfl_down_sync(0xffffffffu, q, 2, 4);
+      q += __shfl_down_sync(0xffffffffu, q, 1, 4);
+      if (part == 0 && t <= P_NW) partial[t] = __int_as_float(q);
+    } else {
+      float v = 0.f;
+#pragma unroll 8
+      for (int j = 0; j < Q; ++j) v += row[j];
+      v += __shfl_down_sync(0xffffffffu, v, 2, 4);
+      v += __shfl_down_sync(0xffffffffu, v, 1, 4);
+      if (part == 0) partial[t] = v;
     }
     __threadfence();  // partials visible device-wide before the block signals (ticket / grid barrier)
   }
@@ -257,7 +265,7 @@ __global__ void __launch_bounds__(TRK_THREADS) trk_eval_kernel(EvalArgs a, float
                                                                unsigned int* __restrict__ ticket,
                                                                EvalResult* __restrict__ result) {
   __shared__ EvalConst c;
-  __shared__ float red[TRK_THREADS / 32][TRK_PART];
+  __shared__ float red[TRK_PART * (TRK_THREADS / 4 + 1)];
   __shared__ double fold[4][TRK_PART];
   __shared__ EvalResult res;
   __shared__ bool last;
@@ -506,7 +514,7 @@ __device__ __forceinline__ double sat_ratio(const EvalResult& r) { return (doubl
 // One evaluation of the LM loop: every participating block evaluates its share, all blocks meet, every block folds all
 // partials in block order (identical result in every block).
 template <int THREADS, bool CLUSTER>
-__device__ __forceinline__ void track_eval_and_fold(const EvalConst& c, float* gpart, float* spart, float (*red)[TRK_PART],
+__device__ __forceinline__ void track_eval_and_fold(const EvalConst& c, float* gpart, float* spart, float* red,
                                                     double (*fold)[TRK_PART], EvalResult& res, int nb, long long* tk) {
   const long long t0 = clock64();
   if (CLUSTER) {
@@ -534,7 +542,7 @@ __global__ void __launch_bounds__(THREADS) trk_track_kernel(TrackArgs a, float* 
                                                             float* __restrict__ partial1,
                                                             TrackIO* __restrict__ io) {
   __shared__ EvalConst c;
-  __shared__ float red[THREADS / 32][TRK_PART];
+  __shared__ float red[TRK_PART * (THREADS / 4 + 1)];
   __shared__ float mypart[2][TRK_PART];   // CLUSTER: this CTA's partial of the current / previous evaluation
   __shared__ double fold[4][TRK_PART];
   __shared__ EvalResult res;
