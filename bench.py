@@ -1,13 +1,14 @@
 #!/usr/bin/env python
 """bench.py — hot-path benchmark (driver contract; see DESIGN.md "Measurement").
 
-Workload (BASELINE.json configs[1]): windowed photometric BA linearisation, 7 keyframes x 2000 points
-per keyframe x 8-px pattern (P=14000 points, R=84000 residuals, 672k pattern pixels per window).
-A *step* = ONE Gauss-Newton iteration's hot path (linearizeAll + applyRes + accumulateAF/LF/SCF with
-the per-point Schur fold + fp64 stitch) over a batch of `--windows` independent windows per GPU, each
-with its own frames/points/Jacobians in HBM (the batch working set is >> the 126 MB L2, so no
-flush is needed between iterations).  Metric: pattern-pixel residuals linearised and reduced into H,b
-per second (Mres/s), whole job.
+Workload (BASELINE.json configs[1] as SURVEY.md §8d specifies it): windowed photometric BA linearisation, 7 keyframes
+x 2000 points per keyframe x 8-px pattern (P=14000 points, R=84000 residuals, 672k pattern pixels per window), 30 % of
+the residuals marked isLinearized (mode L of the top accumulation), the rest re-linearised every iteration.
+A *step* = ONE Gauss-Newton iteration's hot path (linearizeAll + setNewFrameEnergyTH + applyRes + accumulateAF/LF/SCF
+with the per-point Schur fold + fp64 stitch) over a batch of `--windows` independent windows per GPU (8 rendered
+scenes), each with its own frames/points/Jacobians in HBM (the batch working set is >> the 126 MB L2, so no flush is
+needed between iterations).  Metric: pattern-pixel residuals linearised / reduced into H,b per second (Mres/s), whole
+job.  The all-active variant (0 % linearised: every residual goes through the lineariser) is reported next to it.
 
     python bench.py --gpus N --steps K --warmup W           # ours (CUDA through the C ABI)
     python bench.py --impl reference ...                    # the reference's CPU algorithm (oracle port, all host cores)
@@ -70,30 +71,48 @@ def _clock_summary(samples):
             "reasons": reasons}
 
 
-def build_windows(synth, n_windows, seed0, n_scenes=2):
+FRAC_LINEARIZED = 0.3      # "30 % of residuals marked isLinearized (exercise mode 1)"
+N_SCENES = 8
+
+
+def build_windows(synth, n_windows, seed0, n_scenes=N_SCENES, frac_linearized=FRAC_LINEARIZED):
+    """`n_windows` cfg2 windows over `n_scenes` rendered 7-keyframe scenes; returns (windows, per-window isLinearized flags)."""
     kfs = [synth.render_keyframes(640, 480, N_FRAMES, seed=4321 + 17 * s) for s in range(min(n_scenes, n_windows))]
-    wins = []
+    wins, lins = [], []
     for i in range(n_windows):
-        w, _ = synth.make_window(points_per_frame=PTS_PER_FRAME, seed=seed0 + i, keyframes=kfs[i % len(kfs)])
-        wins.append(w)
-    return wins
+        w, is_lin = synth.make_window(points_per_frame=PTS_PER_FRAME, seed=seed0 + i, keyframes=kfs[i % len(kfs)],
+                                      frac_linearized=frac_linearized)
+        wins.append(w); lins.append(is_lin)
+    return wins, lins
 
 
 def reference_arm(args, rank):
     """The reference's own CPU algorithm for the path (oracle port, -O3 -march=native, IndexThreadReduce
-    semantics on all host cores).  One window per step (bounded sample of the batched workload)."""
+    semantics on all host cores) on the SAME workload as our arm: every step runs one GN iteration's hot path over
+    the same `--windows` cfg2 windows (same seeds, 30 % linearised), one after the other."""
     if rank != 0:
         return
     synth = importlib.import_module("h-slam_b200.synth")
     from oracle import oraclelib as O
     cores = os.cpu_count() or 1
-    win, _ = synth.make_window(points_per_frame=PTS_PER_FRAME, seed=1000)
-    dIs = [O.pyramid(im, 1)[0][0] for im in win.images]
-    ba = O.BAOracle(win, dIs, prec="f", threads=cores, fast=True)
+    wins, lins = build_windows(synth, args.windows, seed0=100)
+    pyr = {}
+    bas = []
+    for w, is_lin in zip(wins, lins):
+        dIs = []
+        for im in w.images:
+            if id(im) not in pyr:
+                pyr[id(im)] = O.pyramid(im, 1)[0][0]
+            dIs.append(pyr[id(im)])
+        ba = O.BAOracle(w, dIs, prec="f", threads=cores, fast=True)
+        ba.linearize(False); ba.apply_res()
+        ba.fix_linearization(np.nonzero(is_lin)[0].astype(np.int32))
+        bas.append((ba, w.n - 1))
 
     def step():
-        ba.linearize(False); ba.apply_res()
-        ba.accumulate(0); ba.accumulate(1); ba.accumulate(2)
+        for ba, newest in bas:
+            ba.linearize(False); ba.new_frame_energy_th(newest); ba.apply_res()
+            ba.accumulate(0); ba.accumulate(1); ba.accumulate(2)
 
     for _ in range(args.warmup):
         step()
@@ -101,20 +120,26 @@ def reference_arm(args, rank):
     for _ in range(args.steps):
         step()
     dt = time.perf_counter() - t0
-    px = win.R * 8 * args.steps
-    val = px / dt / 1e6
+    R = sum(w.R for w in wins)
+    val = R * 8 * args.steps / dt / 1e6
     line = {
         "impl": "reference", "metric": METRIC, "value": val, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": 1e3 * dt / args.steps, "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": "cfg2: BA window 7KF x 2000pts/KF x 8px, 1 GN iteration hot path; CPU arm: 1 window per step",
-                   "windows_per_step": 1, "points": int(win.P), "residuals": int(win.R)},
+        "config": workload_config(args.windows),
         "cpu_baseline": {"value": val, "unit": UNIT, "cores": cores, "kind": "port",
-                         "sample": f"{args.steps} GN iterations of one 84k-residual window"},
+                         "sample": f"{args.steps} steps x {args.windows} cfg2 windows (84k residuals each, 30 % linearised), "
+                                   f"oracle port -O3 -march=native on {cores} threads"},
         "e2e": {"value": val, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
     print(json.dumps(line), flush=True)
+
+
+def workload_config(windows):
+    return {"workload": f"cfg2 (SURVEY 8d): BA window 7KF x 2000pts/KF x 8px (P=14000, R=84000), 30% of residuals isLinearized, "
+                        f"1 GN iteration hot path, {windows} independent windows per GPU per step over {N_SCENES} rendered scenes",
+            "windows_per_gpu": windows, "frac_linearized": FRAC_LINEARIZED, "scenes": N_SCENES}
 
 
 def main():
@@ -158,10 +183,11 @@ def main():
 
     ctx = capi.Context(local_rank)
     stream = torch.cuda.ExternalStream(ctx.stream, device=torch.device("cuda", local_rank))
-    wins = build_windows(synth, args.windows, seed0=100 + 1000 * rank)
+    wins, lins = build_windows(synth, args.windows, seed0=100 + 1000 * rank)
     efs, frames_all, host_imgs = [], [], []
     for w in wins:
-        # `value` leg: inputs resident in HBM before the timed region (images uploaded via torch, pyramid built on device)
+        # `value` leg: inputs resident in HBM before the timed region (images uploaded via torch, pyramid built on device);
+        # every window owns device copies of its seven keyframes (independent windows share nothing)
         fr = []
         for im in w.images:
             t = torch.from_numpy(np.ascontiguousarray(im)).cuda(non_blocking=False)
@@ -178,34 +204,47 @@ def main():
     batch = capi.EnergyFunctionalBatch(ctx, efs)
 
     def step_device():
-        batch.iteration()          # 4 launches for all windows of this GPU
+        batch.iteration()          # one CUDA graph of the launch chain for all windows of this GPU
 
     def barrier():
         if world > 1:
             dist.barrier()
         torch.cuda.synchronize()
 
-    for _ in range(args.warmup):
-        step_device()
-    barrier()
+    def timed(fn, k, w):
+        for _ in range(w):
+            fn()
+        barrier()
+        l0 = ctx.launches
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record(stream)
+        for _ in range(k):
+            fn()
+        e1.record(stream)
+        barrier()
+        ms = e0.elapsed_time(e1)
+        if world > 1:
+            tt = torch.tensor([ms], device="cuda")
+            dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+            ms = float(tt.item())
+        return ms, ctx.launches - l0
+
+    # ---- secondary leg first (nothing linearised yet): every residual goes through the lineariser
+    ms_all, _ = timed(step_device, args.steps, args.warmup)
+    value_all_active = world * px_per_step * args.steps / (ms_all * 1e-3) / 1e6
+    # ---- cfg2 proper: 30 % of the residuals are fixed (fixLinearizationF) and accumulate through mode L from now on
+    n_lin = 0
+    for ef, is_lin in zip(efs, lins):
+        ids = np.nonzero(is_lin)[0].astype(np.int32)
+        ef.fixLinearization(ids)
+        n_lin += len(ids)
+    ctx.synchronize()
+    res_lin_per_step = res_per_step - n_lin        # residuals the lineariser actually processes per step
     samples, stop = [], threading.Event()
     th = threading.Thread(target=_clock_sampler, args=(stop, samples, local_rank), daemon=True)
     th.start()
-    l0 = ctx.launches
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    e0.record(stream)
-    for _ in range(args.steps):
-        step_device()
-    e1.record(stream)
-    barrier()
-    ms = e0.elapsed_time(e1)
-    launches = ctx.launches - l0
+    t_max, launches = timed(step_device, args.steps, args.warmup)
     stop.set(); th.join(timeout=2)
-    t_max = ms
-    if world > 1:
-        tt = torch.tensor([ms], device="cuda")
-        dist.all_reduce(tt, op=dist.ReduceOp.MAX)
-        t_max = float(tt.item())
     value = world * px_per_step * args.steps / (t_max * 1e-3) / 1e6
 
     # ---- per-kernel device timing (CUDA events on the launching stream) for the roofline
@@ -223,8 +262,9 @@ def main():
     peak_kind = "measured (MEASURED_PEAKS.json hbm_gbs)" if "hbm_gbs" in peaks else "fallback 6650 GB/s (B200_PROFILING.md)"
     dom = max(prof.items(), key=lambda kv: kv[1][0])[0]
     dom_ms, dom_cnt = prof[dom]
-    per_launch_res = res_per_step          # one launch per stage covers every window of the batch
-    algo_bytes = ALGO_BYTES_PER_RES.get(dom, 0.0) * per_launch_res
+    launches_per_step = max(1, round(dom_cnt / args.steps))      # ba_top runs twice per step (modes A and L)
+    units = {"ba_linearize": res_lin_per_step, "ba_top": res_per_step, "ba_schur": res_per_step}.get(dom, res_per_step)
+    algo_bytes = ALGO_BYTES_PER_RES.get(dom, 0.0) * units / (launches_per_step if dom == "ba_top" else 1)
     avg_s = dom_ms * 1e-3 / max(dom_cnt, 1)
     achieved = algo_bytes / avg_s / 1e9 if avg_s > 0 else 0.0
     traffic = None
@@ -234,88 +274,86 @@ def main():
         pass
     roofline = {"bound": "hbm", "kernel": dom, "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                 "traffic": traffic, "peak_source": peak_kind, "avg_launch_us": avg_s * 1e6,
-                "algorithmic_bytes_per_launch": algo_bytes,
+                "algorithmic_bytes_per_launch": algo_bytes, "units_per_launch": int(units),
+                "bytes_per_unit": ALGO_BYTES_PER_RES.get(dom),
                 "kernel_share_of_step": {k: v[0] / sum(x[0] for x in prof.values()) for k, v in prof.items()},
                 "kernel_avg_us": {k: 1e3 * v[0] / max(v[1], 1) for k, v in prof.items()}}
 
-    # ---- e2e: the same GN iteration through the C ABI with HOST buffers, copies inside the timed region
+    # ---- e2e: the same GN iteration through the C ABI with HOST buffers, copies inside the timed region.
+    # Default result set = what System::optimize's loop body reads on the host per iteration: energy, resInA/L, the three
+    # stitched systems, per-residual newState, the new frameEnergyTH of the newest frame (System::setNewFrameEnergyTH runs
+    # on the device: the per-residual energies stay in HBM), per-point step after the back-substitution.
     N = 8 * N_FRAMES + 4
     xs = [np.ascontiguousarray(np.random.default_rng(i).normal(0, 1e-4, N)) for i in range(len(wins))]
-
-    io = batch.make_io(wins, frames_all, pinned="bound")  # outputs live in the batch's page-locked result block (zero-copy views)
-
-    def step_e2e():
-        # phase 1: ONE C-ABI call for the batch — host tables + per-point state up (one H2D block), linearizeAll +
-        # applyRes + accumulateAF/LF/SCF, energies + residual states + 3 x (H,b) down, returns when they are valid
-        batch.step_host(io)
-        # (the host solves the 60x60 systems here in the real pipeline) phase 2: back-substitution, x up, steps down
-        batch.resubstitute_host(io, xs)
-
     n2 = N_FRAMES * N_FRAMES
-    h2d = sum(n2 * 28 * 4 + n2 * 8 * 4 + 2 * n2 * 64 * 8 + 2 * N_FRAMES * 64 + 2 * w.P * 4 + N * 8 + 2 * 136 for w in wins)
-    d2h = sum(8 + w.R * 9 + 3 * (N * N + N) * 8 + 8 + w.P * 4 for w in wins)
-    for _ in range(2):
-        step_e2e()
-    barrier()
-    k_e2e = max(3, args.steps // 2)
-    e0.record(stream)
-    t0 = time.perf_counter()
-    for _ in range(k_e2e):
-        step_e2e()
-    e1.record(stream)
-    barrier()
-    wall = time.perf_counter() - t0
-    ms_e2e = max(e0.elapsed_time(e1), 1e3 * wall)
-    if world > 1:
-        tt = torch.tensor([ms_e2e], device="cuda")
-        dist.all_reduce(tt, op=dist.ReduceOp.MAX)
-        ms_e2e = float(tt.item())
-    e2e_val = world * px_per_step * k_e2e / (ms_e2e * 1e-3) / 1e6
+    h2d = sum(n2 * 28 * 4 + n2 * 8 * 4 + 2 * n2 * 64 * 8 + 2 * N_FRAMES * 64 + 2 * w.P * 4 + N * 8 + 2 * 144 for w in wins)
 
-    # informational: the same two calls when the caller asks for energy + systems + residual STATES only (the
-    # per-residual energies — 8 of the 9 result bytes per residual — stay on the device until they are wanted:
-    # setNewFrameEnergyTH reads them once per optimisation, not per iteration)
-    io_s = batch.make_io(wins, frames_all, pinned="bound")
-    for o in io_s["arr"]:
-        o.newEnergy = None; o.newEnergyWithOutlier = None
-    for _ in range(2):
-        batch.step_host(io_s); batch.resubstitute_host(io_s, xs)
-    barrier()
-    t0 = time.perf_counter()
-    for _ in range(k_e2e):
-        batch.step_host(io_s); batch.resubstitute_host(io_s, xs)
-    barrier()
-    ms_states = 1e3 * (time.perf_counter() - t0)
-    if world > 1:
-        tt = torch.tensor([ms_states], device="cuda")
-        dist.all_reduce(tt, op=dist.ReduceOp.MAX)
-        ms_states = float(tt.item())
-    e2e_states = {"value": world * px_per_step * k_e2e / (ms_states * 1e-3) / 1e6, "unit": UNIT, "ms_per_step": ms_states / k_e2e,
-                  "d2h_bytes_per_step": int(sum(8 + w.R * 1 + 3 * (N * N + N) * 8 + 8 + w.P * 4 for w in wins))}
+    def e2e_leg(with_energies):
+        io = batch.make_io(wins, frames_all, pinned="bound")  # outputs live in the batch's page-locked result block (zero-copy views)
+        if not with_energies:
+            for o in io["arr"]:
+                o.newEnergy = None; o.newEnergyWithOutlier = None
 
+        def step_e2e():
+            # phase 1: ONE C-ABI call for the batch — host tables + per-point state up, linearizeAll + setNewFrameEnergyTH
+            # + applyRes + accumulateAF/LF/SCF, results down, returns when they are valid
+            outs = batch.step_host(io)
+            # the caller keeps the threshold in its Frame and hands it back in the next hslam_window (as the reference does)
+            for o, (ws, ka, inp), w in zip(outs, io["keep"], wins):
+                ka[1]["frameEnergyTH"][w.n - 1] = o["frameEnergyTH"][0]
+            # (the host solves the 60x60 systems here in the real pipeline) phase 2: back-substitution, x up, steps down
+            batch.resubstitute_host(io, xs)
+
+        for _ in range(2):
+            step_e2e()
+        barrier()
+        k = max(3, args.steps // 2)
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record(stream)
+        t0 = time.perf_counter()
+        for _ in range(k):
+            step_e2e()
+        e1.record(stream)
+        barrier()
+        wall = time.perf_counter() - t0
+        ms = max(e0.elapsed_time(e1), 1e3 * wall)
+        if world > 1:
+            tt = torch.tensor([ms], device="cuda")
+            dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+            ms = float(tt.item())
+        d2h = sum(8 + 8 + 4 + w.R * (9 if with_energies else 1) + 3 * (N * N + N) * 8 + w.P * 4 for w in wins)
+        return world * px_per_step * k / (ms * 1e-3) / 1e6, ms / k, k, int(d2h)
+
+    e2e_val, e2e_ms, k_e2e, d2h = e2e_leg(False)
+    full_val, full_ms, _, d2h_full = e2e_leg(True)
+
+    cfg = workload_config(args.windows)
+    cfg.update({"l2_policy": f"inputs larger than L2 (no flush): batch working set ~{args.windows * 62} MB vs 126 MB L2",
+                "jacobians": "materialised (SoA in HBM)",
+                "e2e_api": "hslam_ba_batch_step_host + hslam_ba_batch_resubstitute_host (host buffers, 2 waits per step)"})
     line = {
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": t_max / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": "f32", "data": "synthetic",
-        "config": {"workload": f"cfg2: BA window 7KF x 2000pts/KF x 8px (P=14000, R=84000), 1 GN iteration hot path, "
-                               f"{args.windows} independent windows per GPU per step",
-                   "windows_per_gpu": args.windows, "l2_policy": "inputs larger than L2 (no flush): batch working set "
-                   f"~{args.windows * 62} MB vs 126 MB L2", "jacobians": "materialised (SoA in HBM)",
-                   "e2e_api": "hslam_ba_batch_step_host + hslam_ba_batch_resubstitute_host (host buffers, 2 waits per step)"},
-        "e2e": {"value": e2e_val, "unit": UNIT, "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
-                "ms_per_step": ms_e2e / k_e2e, "steps": k_e2e,
-                "outputs": "energy, resInA/L, 3x(H,b), per residual newState + newEnergy + newEnergyWithOutlier, per point step",
-                "states_only": e2e_states},
+        "config": cfg,
+        "e2e": {"value": e2e_val, "unit": UNIT, "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": d2h,
+                "ms_per_step": e2e_ms, "steps": k_e2e,
+                "outputs": "energy, resInA/L, 3x(H,b), per residual newState, new frameEnergyTH of the newest frame "
+                           "(setNewFrameEnergyTH on the device), per point step",
+                "with_per_residual_energies": {"value": full_val, "unit": UNIT, "ms_per_step": full_ms,
+                                               "d2h_bytes_per_step": d2h_full}},
         "gpu_launches": int(launches),
         "clocks": _clock_summary(samples),
         "roofline": roofline,
+        "all_active": {"value": value_all_active, "unit": UNIT, "ms_per_step": ms_all / args.steps,
+                       "workload": "same windows before fixLinearizationF: 0 % linearised, every residual is re-linearised"},
     }
 
     if rank == 0:
         if not args.no_extras:
             line["extra"] = extras(ctx, capi, synth, torch, stream, efs[0], wins[0])
         if not args.no_cpu_baseline:
-            line["cpu_baseline"] = cpu_baseline(synth, wins[0])
+            line["cpu_baseline"] = cpu_baseline(synth, wins[0], lins[0])
         print(json.dumps(line), flush=True)
     if world > 1:
         dist.barrier()
@@ -438,14 +476,16 @@ def extras(ctx, capi, synth, torch, stream, ef0, win0):
     return out
 
 
-def cpu_baseline(synth, win):
+def cpu_baseline(synth, win, is_lin):
     from oracle import oraclelib as O
     cores = os.cpu_count() or 1
     dIs = [O.pyramid(im, 1)[0][0] for im in win.images]
     ba = O.BAOracle(win, dIs, prec="f", threads=cores, fast=True)
+    ba.linearize(False); ba.apply_res()
+    ba.fix_linearization(np.nonzero(is_lin)[0].astype(np.int32))
 
     def step():
-        ba.linearize(False); ba.apply_res()
+        ba.linearize(False); ba.new_frame_energy_th(win.n - 1); ba.apply_res()
         ba.accumulate(0); ba.accumulate(1); ba.accumulate(2)
 
     step()
@@ -455,7 +495,7 @@ def cpu_baseline(synth, win):
     dt = time.perf_counter() - t0
     return {"value": win.R * 8 * reps / dt / 1e6, "unit": UNIT, "cores": cores, "kind": "port",
             "ms_per_window": 1e3 * dt / reps,
-            "sample": f"{reps} GN iterations of one cfg2 window (84k residuals) on {cores} threads, oracle port -O3 -march=native"}
+            "sample": f"{reps} GN iterations of one cfg2 window (84k residuals, 30 % linearised) on {cores} threads, oracle port -O3 -march=native"}
 
 
 if __name__ == "__main__":

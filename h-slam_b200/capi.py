@@ -26,6 +26,8 @@ class Params(C.Structure):
         ("affineOptModeA", C.c_float), ("affineOptModeB", C.c_float), ("scale_xi_rot", C.c_float),
         ("scale_xi_trans", C.c_float), ("scale_a", C.c_float), ("scale_b", C.c_float), ("scale_f", C.c_float),
         ("scale_c", C.c_float), ("scale_idepth", C.c_float), ("max_tracker_iterations", C.c_int * 5),
+        ("frameEnergyTHN", C.c_float), ("frameEnergyTHFacMedian", C.c_float), ("frameEnergyTHConstWeight", C.c_float),
+        ("overallEnergyTHWeight", C.c_float),
     ]
 
 
@@ -51,7 +53,7 @@ class ResidualSoA(C.Structure):
 
 class StepIO(C.Structure):
     _fields_ = [(k, C.c_void_p) for k in ("window", "idepth", "deltaF", "idepth_zero", "energy", "newState", "newEnergy",
-                                          "newEnergyWithOutlier", "Hb", "nres2")]
+                                          "newEnergyWithOutlier", "Hb", "nres2", "frameEnergyTH_out")] + [("newest_frame", C.c_int32)]
 
 
 def _ptr(a):
@@ -126,7 +128,7 @@ class Context:
 
     def profile_read(self):
         """{kernel class: (summed ms, launches)} measured with CUDA events on the context stream."""
-        K = 18
+        K = 19
         ms = np.zeros(K, np.float32); cnt = np.zeros(K, np.int32)
         _chk(self.L.hslam_profile_read(self.h, _ptr(ms), _ptr(cnt)))
         self.L.hslam_kernel_name.restype = C.c_char_p
@@ -554,6 +556,12 @@ class EnergyFunctional:
                                                 _ptr(Ms), _ptr(Mbs), C.byref(nres)))
         return M.reshape(N, N).T.copy(), Mb, Ms.reshape(N, N).T.copy(), Mbs, nres.value
 
+    def setNewFrameEnergyTH(self, newest_frame):
+        """System::setNewFrameEnergyTH (FullSystemOptimize.cpp:60-101) on the device; returns the new threshold."""
+        th = np.zeros(1, np.float32)
+        _chk(self.L.hslam_ba_new_frame_energy_th(self.h, C.c_int(int(newest_frame)), _ptr(th)))
+        return self._result((th,), lambda: float(th[0]))
+
     def calcLEnergyF_MT(self):
         e = C.c_double(0)
         _chk(self.L.hslam_ba_calc_l_energy(self.h, C.byref(e)))
@@ -583,7 +591,7 @@ class EnergyFunctionalBatch:
     def iteration(self):
         _chk(self.L.hslam_ba_batch_iteration(self.h))
 
-    def make_io(self, wins, frames_per_window, pinned=True):
+    def make_io(self, wins, frames_per_window, pinned=True, newest_frame=None):
         """Persistent host-side I/O block for step_host(): per window the hslam_window struct, the per-point
         inputs and the output arrays.  pinned="bound": the outputs are views of the batch's own page-locked
         result block (hslam_ba_batch_io_bind, zero-copy); True: separate page-locked arrays (hslam_host_alloc,
@@ -617,16 +625,20 @@ class EnergyFunctionalBatch:
                                  newEnergy=view(arr[i].newEnergy, ef.R, np.float32),
                                  newEnergyWithOutlier=view(arr[i].newEnergyWithOutlier, ef.R, np.float32),
                                  Hb=view(arr[i].Hb, 3 * (N * N + N), np.float64), nres2=view(arr[i].nres2, 2, np.int32),
+                                 frameEnergyTH=view(arr[i].frameEnergyTH_out, 1, np.float32),
                                  step=view(steps[i], ef.P, np.float32)))
+                arr[i].newest_frame = (w.n - 1) if newest_frame is None else int(newest_frame)
         else:
             mk = (lambda shape, dt: self.ctx.host_empty(shape, dt)) if pinned else (lambda shape, dt: np.zeros(shape, dt))
             for i, (ef, w) in enumerate(zip(self.efs, wins)):
                 N = 8 * w.n + 4
                 o = dict(energy=mk(1, np.float64), newState=mk(ef.R, np.int8), newEnergy=mk(ef.R, np.float32),
                          newEnergyWithOutlier=mk(ef.R, np.float32), Hb=mk(3 * (N * N + N), np.float64), nres2=mk(2, np.int32),
-                         step=mk(ef.P, np.float32))
+                         step=mk(ef.P, np.float32), frameEnergyTH=mk(1, np.float32))
                 for k in names:
                     setattr(arr[i], k, _ptr(o[k]))
+                arr[i].frameEnergyTH_out = _ptr(o["frameEnergyTH"])
+                arr[i].newest_frame = (w.n - 1) if newest_frame is None else int(newest_frame)
                 outs.append(o)
         return dict(arr=arr, keep=keep, out=outs)
 

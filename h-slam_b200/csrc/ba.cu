@@ -87,6 +87,7 @@ struct hslam_ba {
   DevBuf<float> d_xc, d_xAd;
   DevBuf<double> d_x;
   DevBuf<int> d_ids;
+  DevBuf<float> d_th;            // result of hslam_ba_new_frame_energy_th
   // descriptor
   BADesc hdesc;
   DevBuf<BADesc> d_desc;
@@ -400,7 +401,7 @@ int hslam_ba_destroy(hslam_ba* ba) {
   ba->d_pair_ticket.release(); ba->d_host_ticket.release(); ba->d_toptiles.release(); ba->d_top_block_begin.release();
   ba->d_ptchunks.release(); ba->d_host_chunk_begin.release(); ba->d_scpartial.release(); ba->d_G.release();
   ba->d_Hb.release(); ba->d_epart.release(); ba->d_energy.release(); ba->d_nres.release(); ba->d_ticket.release();
-  ba->d_xc.release(); ba->d_xAd.release(); ba->d_x.release(); ba->d_ids.release(); ba->d_desc.release();
+  ba->d_xc.release(); ba->d_xAd.release(); ba->d_x.release(); ba->d_ids.release(); ba->d_th.release(); ba->d_desc.release();
   ba->d_r_s2o.release(); ba->d_p_s2o.release(); ba->d_scratch.release(); ba->d_marg.release();
   if (ba->arena) cudaFreeHost(ba->arena);
   delete ba;
@@ -461,6 +462,8 @@ int hslam_ba_set_window(hslam_ba* ba, const hslam_window* w) {
   W.fx = w->fx; W.fy = w->fy; W.cx = w->cx; W.cy = w->cy; W.fxi = w->fxi; W.fyi = w->fyi;
   W.huber = ctx->prm.huberTH; W.outlierTH = ctx->prm.outlierTHSumComponent; W.scale_idepth = ctx->prm.scale_idepth;
   W.scale_f = ctx->prm.scale_f; W.scale_c = ctx->prm.scale_c; W.affA = ctx->prm.affineOptModeA; W.affB = ctx->prm.affineOptModeB;
+  W.thN = ctx->prm.frameEnergyTHN; W.thFac = ctx->prm.frameEnergyTHFacMedian; W.thConst = ctx->prm.frameEnergyTHConstWeight;
+  W.thOverall = ctx->prm.overallEnergyTHWeight;
   for (int i = 0; i < 4; ++i) { W.cDeltaF[i] = w->cDeltaF[i]; ba->hdesc.S.cPrior[i] = w->cPrior[i]; }
   for (int f = 0; f < n; ++f) {
     HS_ARG(w->frames[f] && w->frames[f]->ctx == ctx, "hslam_ba_set_window: frame missing or from another context");
@@ -686,8 +689,8 @@ static int launch_linearize(hslam_ba* ba, bool apply) {
 }
 
 static const size_t kTopSmem = TOP_STAGES * sizeof(TopStage) + 128;   // + alignment slack (TMA destinations)
-static int top_attr() {
-  static bool done = false;
+static int top_attr(hslam_ctx* ctx) {
+  bool& done = ctx->top_attr_done;
   if (!done) {
     HS_CUDA(cudaFuncSetAttribute(ba_top_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kTopSmem));
     HS_CUDA(cudaFuncSetAttribute(ba_top_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kTopSmem));
@@ -700,7 +703,7 @@ static int top_attr() {
 static int launch_top(hslam_ba* ba, int modes) {
   hslam_ctx* ctx = ba->ctx;
   TRY(sync_desc(ba));
-  TRY(top_attr());
+  TRY(top_attr(ctx));
   HS_ARG(ba->tmap_ok, "hslam_ba: cuTensorMapEncodeTiled failed for the Jacobian tensor maps (driver too old?)");
   const int T = ba->n_topchunks[0];
   if (T > 0 && (modes & 1))
@@ -738,8 +741,8 @@ template <class F> static int schur_dispatch(int maxt, int ni, F f) {
   if (maxt == 2) return f(ba_schur_kernel<2, 4>);
   return f(ba_schur_kernel<5, 4>);
 }
-static int schur_attr(size_t smem) {
-  static size_t configured = 48 * 1024;
+static int schur_attr(hslam_ctx* ctx, size_t smem) {
+  size_t& configured = ctx->schur_smem_configured;
   if (smem > configured) {
     for (int maxt : {0, 1, 2, 5})
       for (int ni : {2, 4})
@@ -759,7 +762,7 @@ static int launch_schur(hslam_ba* ba) {
   hslam_ctx* ctx = ba->ctx;
   TRY(sync_desc(ba));
   size_t smem = schur_smem(ba->LD, ba->maxres);
-  TRY(schur_attr(smem));
+  TRY(schur_attr(ctx, smem));
   if (ba->n_ptchunks > 0)
     HS_LAUNCH(ctx, HSLAM_K_BA_SCHUR, schur_launch(schur_maxt(ba->LD), schur_ni(ba->maxres), ba->n_ptchunks, smem, ctx->stream, ba->d_desc.p, nullptr, 1));
   HS_LAUNCH(ctx, HSLAM_K_BA_FOLD_SC, (ba_fold_sc_kernel<<<ba->n * ((ba->LD * ba->LD + 255) / 256), 256, 0, ctx->stream>>>(ba->d_desc.p, nullptr, 1)));
@@ -832,6 +835,24 @@ int hslam_ba_apply_res(hslam_ba* ba) {
   HS_LAUNCH(ba->ctx, HSLAM_K_BA_APPLY, (ba_apply_kernel<<<blocks, 256, 0, ba->ctx->stream>>>(ba->hdesc.r)));
   HS_CUDA(cudaGetLastError());
   return 0;
+}
+
+int hslam_ba_new_frame_energy_th(hslam_ba* ba, int newest, float* th_out) {
+  HS_ARG(ba && ba->have_topology && ba->have_window, "hslam_ba_new_frame_energy_th: window/topology not set");
+  HS_ARG(newest >= 0 && newest < ba->n, "hslam_ba_new_frame_energy_th: frame index out of range");
+  hslam_ctx* ctx = ba->ctx;
+  HS_CUDA(cudaSetDevice(ctx->device));
+  TRY(sync_desc(ba));
+  TRY(ba->d_th.ensure(1));
+  HS_LAUNCH(ctx, HSLAM_K_BA_ENERGY_TH, (ba_energy_th_kernel<<<1, TH_THREADS, 0, ctx->stream>>>(ba->d_desc.p, newest, ba->d_th.p, nullptr, nullptr)));
+  HS_CUDA(cudaGetLastError());
+  // the device descriptor already holds the new threshold; the host mirror follows once the value is known
+  TRY(download_then<float>(ba, ba->d_th.p, 1, [ba, newest, th_out](const float* s) {
+    ba->hdesc.W.frameEnergyTH[newest] = *s;
+    ba->desc_version++;
+    if (th_out) *th_out = *s;
+  }));
+  return end_call(ba);
 }
 
 int hslam_ba_fix_linearization(hslam_ba* ba, const int32_t* ids, int count) {
@@ -1111,6 +1132,7 @@ static int batch_refresh(hslam_ba_batch* B) {
   HS_CUDA(cudaEventSynchronize(B->copied));
   int* pf[NPF];
   for (int k = 0; k < NPF; ++k) { pf[k] = B->h_prefix + k * (n + 1); pf[k][0] = 0; }
+  const size_t smem0 = B->smem; const int maxt0 = B->maxt, ni0 = B->ni; const bool anyL0 = B->any_L;
   B->smem = 0; B->maxt = 0; B->ni = 2; B->any_L = false;
   for (int i = 0; i < n; ++i) {
     hslam_ba* ba = B->items[i];
@@ -1129,16 +1151,22 @@ static int batch_refresh(hslam_ba_batch* B) {
     B->maxt = std::max(B->maxt, schur_maxt(ba->LD));
     B->ni = std::max(B->ni, schur_ni(ba->maxres));
   }
+  // launch parameters of the captured graphs: a change of descriptor CONTENT alone (new thresholds, new camera scalars)
+  // does not invalidate them
+  int blocks0[NPF], uniform0[NPF];
+  for (int k = 0; k < NPF; ++k) { blocks0[k] = B->blocks[k]; uniform0[k] = B->uniform[k]; }
   for (int k = 0; k < NPF; ++k) {
     B->blocks[k] = pf[k][n];
     B->uniform[k] = pf[k][1];
     for (int i = 1; i < n; ++i) if (pf[k][i + 1] - pf[k][i] != pf[k][1]) B->uniform[k] = 0;
     if (n < 2 || pf[k][1] == 0) B->uniform[k] = 0;
   }
+  bool launch_changed = smem0 != B->smem || maxt0 != B->maxt || ni0 != B->ni || anyL0 != B->any_L;
+  for (int k = 0; k < NPF; ++k) launch_changed |= blocks0[k] != B->blocks[k] || uniform0[k] != B->uniform[k];
   HS_CUDA(cudaMemcpyAsync(B->d_descs.p, B->h_descs, n * sizeof(BADesc), cudaMemcpyHostToDevice, B->ctx->stream));
   HS_CUDA(cudaMemcpyAsync(B->d_prefix.p, B->h_prefix, NPF * (n + 1) * sizeof(int), cudaMemcpyHostToDevice, B->ctx->stream));
   HS_CUDA(cudaEventRecord(B->copied, B->ctx->stream));
-  B->refresh_version++;
+  if (launch_changed) B->refresh_version++;
   return 0;
 }
 
@@ -1211,8 +1239,8 @@ static int batch_enqueue_accumulate(hslam_ba_batch* B) {
   hslam_ctx* ctx = B->ctx;
   const int n = (int)B->items.size();
   const int* pf = B->d_prefix.p;
-  TRY(schur_attr(B->smem));
-  TRY(top_attr());
+  TRY(schur_attr(ctx, B->smem));
+  TRY(top_attr(ctx));
   if (B->blocks[1] > 0) {
     HS_LAUNCH(ctx, HSLAM_K_BA_TOP, (ba_top_kernel<0><<<B->blocks[1], 2 * TOP_THREADS, kTopSmem, ctx->stream>>>(B->d_descs.p, pf + (n + 1), B->uniform[1] ? -B->uniform[1] : n)));
     if (B->any_L)
@@ -1239,8 +1267,8 @@ static int batch_graph_launch(hslam_ba_batch* B, bool with_linearize) {
     return batch_enqueue_accumulate(B);
   }
   if (!exec || ver != B->refresh_version) {
-    TRY(schur_attr(B->smem));
-    TRY(top_attr());
+    TRY(schur_attr(ctx, B->smem));
+    TRY(top_attr(ctx));
     if (exec) { cudaGraphExecDestroy(exec); exec = nullptr; }
     const int64_t l0 = ctx->launches;
     HS_CUDA(cudaStreamBeginCapture(ctx->stream, cudaStreamCaptureModeThreadLocal));
@@ -1300,6 +1328,9 @@ static int window_scalars(hslam_ba* ba, const hslam_window* w) {
   }
   StitchArgs S = ba->hdesc.S;
   for (int i = 0; i < 4; ++i) { S.cPrior[i] = w->cPrior[i]; S.cDeltaF[i] = w->cDeltaF[i]; }
+  // host copies of the frame priors: calcLEnergy's prior term reads them (the tables themselves travel in the staging block)
+  ba->h_fprior.assign(w->framePrior, w->framePrior + (size_t)ba->n * 8);
+  ba->h_fdprior.assign(w->frameDeltaPrior, w->frameDeltaPrior + (size_t)ba->n * 8);
   if (memcmp(&W, &ba->hdesc.W, sizeof(BAWin)) != 0 || memcmp(&S, &ba->hdesc.S, sizeof(StitchArgs)) != 0) {
     ba->hdesc.W = W; ba->hdesc.S = S;
     ba->desc_version++;
@@ -1323,7 +1354,8 @@ static int batch_layout_down(hslam_ba_batch* B) {
   B->dn_res_end = dn;
   for (int i = 0; i < n; ++i) {
     const size_t N = B->items[i]->N;
-    B->io[i].dn_energy = take(8); B->io[i].dn_nres = take(8); B->io[i].dn_Hb = take(3 * (N * N + N) * 8);
+    B->io[i].dn_energy = take(8); B->io[i].dn_nres = take(8); B->io[i].dn_th = take(4); B->io[i].dn_Hb = take(3 * (N * N + N) * 8);
+    B->io[i].newest = 0; B->io[i].pad = 0;
   }
   B->dn_sys_end = dn;
   for (int i = 0; i < n; ++i) B->io[i].dn_step = take((size_t)B->items[i]->P * 4);
@@ -1378,6 +1410,7 @@ int hslam_ba_batch_io_bind(hslam_ba_batch* B, hslam_ba_step_io* io, float** step
     io[i].Hb = (double*)(B->h_dn + L.dn_Hb);
     io[i].newEnergy = (float*)(B->h_dn + L.dn_newEnergy); io[i].newEnergyWithOutlier = (float*)(B->h_dn + L.dn_newEnergyWO);
     io[i].newState = (int8_t*)(B->h_dn + L.dn_newState);
+    io[i].frameEnergyTH_out = (float*)(B->h_dn + L.dn_th);
     if (step_out) step_out[i] = (float*)(B->h_dn + L.dn_step);
   }
   return 0;
@@ -1408,14 +1441,21 @@ int hslam_ba_batch_step_host(hslam_ba_batch* B, const hslam_ba_step_io* io) {
     if (!o.newEnergy) E.dn_newEnergy = -1;
     if (!o.newEnergyWithOutlier) E.dn_newEnergyWO = -1;
     if (!o.newState) E.dn_newState = -1;
+    if (o.frameEnergyTH_out) {
+      HS_ARG(o.newest_frame >= 0 && o.newest_frame < ba->n, "hslam_ba_batch_step_host: newest_frame out of range");
+      E.newest = o.newest_frame;
+    } else {
+      E.dn_th = -1;
+    }
   }
   memcpy(B->h_up, eff.data(), n * sizeof(BAIO));   // the offset table leads the block
   TRY(batch_refresh(B));   // descriptors (only if a scalar changed) and block-prefix tables
   const BAIO* d_io = reinterpret_cast<const BAIO*>(B->d_up.p);
-  bool any_res = false, any_sys = false;
+  bool any_res = false, any_sys = false, any_th = false;
   for (int i = 0; i < n; ++i) {
     any_res |= io[i].newEnergy || io[i].newEnergyWithOutlier || io[i].newState;
-    any_sys |= io[i].Hb || io[i].nres2 || io[i].energy;
+    any_th |= io[i].frameEnergyTH_out != nullptr;
+    any_sys |= io[i].Hb || io[i].nres2 || io[i].energy || io[i].frameEnergyTH_out;
   }
   // The batch is processed in up to 8 window groups.  Upload stream: pack + H2D + import of group g+1 while the
   // context stream linearises group g; side stream (high priority): export + D2H of the per-residual results of
@@ -1494,10 +1534,18 @@ int hslam_ba_batch_step_host(hslam_ba_batch* B, const hslam_ba_step_io* io) {
     HS_CUDA(cudaStreamWaitEvent(ctx->stream, B->ev_up[g], 0));
     // ---- linearise the group
     TRY(batch_enqueue_linearize(B, g0, g1));
-    if (!any_res) continue;
-    // ---- per-residual results of the group
+    if (!any_res && !any_th) continue;
     HS_CUDA(cudaEventRecord(B->ev_grp[g], ctx->stream));
     HS_CUDA(cudaStreamWaitEvent(ctx->side, B->ev_grp[g], 0));
+    if (any_th) {
+      // System::setNewFrameEnergyTH of the group's windows (one block each), on the side stream under the next group's
+      // linearisation: writes the threshold into the window's descriptor and into its slot of the D2H block
+      ctx->launches++;
+      ba_energy_th_kernel<<<g1 - g0, TH_THREADS, 0, ctx->side>>>(B->d_descs.p + g0, -1, nullptr, d_io + g0, B->d_dn.p);
+      HS_CUDA(cudaGetLastError());
+    }
+    if (!any_res) continue;
+    // ---- per-residual results of the group
     dim3 grid((unsigned)std::max(1, std::min(128, (gR + 255) / 256)), (unsigned)(g1 - g0));
     ctx->launches++;   // side stream: counted, not event-timed
     ba_batch_export_kernel<<<grid, 256, 0, ctx->side>>>(B->d_descs.p + g0, d_io + g0, B->d_dn.p, 1);
@@ -1520,8 +1568,9 @@ int hslam_ba_batch_step_host(hslam_ba_batch* B, const hslam_ba_step_io* io) {
     }
     bulk_res |= bulk_st || bulk_en;
   }
-  if (any_res) HS_CUDA(cudaEventRecord(ctx->ev_join, ctx->side));
+  if (any_res || any_th) HS_CUDA(cudaEventRecord(ctx->ev_join, ctx->side));
   TRY(batch_graph_launch(B, false));
+  if (any_th) HS_CUDA(cudaStreamWaitEvent(ctx->stream, ctx->ev_join, 0));   // the thresholds ride in the systems region
   if (any_sys) {
     HS_LAUNCH(ctx, HSLAM_K_BA_EXPORT, (ba_batch_export_kernel<<<dim3(2, (unsigned)n), 256, 0, ctx->stream>>>(B->d_descs.p, d_io, B->d_dn.p, 2)));
     HS_CUDA(cudaGetLastError());
@@ -1529,6 +1578,7 @@ int hslam_ba_batch_step_host(hslam_ba_batch* B, const hslam_ba_step_io* io) {
       const size_t N = B->items[i]->N;
       TRY(emit(ctx->stream, bulk_sys, io[i].energy, B->io[i].dn_energy, 8)); TRY(emit(ctx->stream, bulk_sys, io[i].nres2, B->io[i].dn_nres, 8));
       TRY(emit(ctx->stream, bulk_sys, io[i].Hb, B->io[i].dn_Hb, 3 * (N * N + N) * 8));
+      if (io[i].frameEnergyTH_out) bulk_sys = true;   // always through the block: the host mirror below reads it there
     }
     if (bulk_sys)
       HS_CUDA(cudaMemcpyAsync(B->h_dn + B->dn_res_end, B->d_dn.p + B->dn_res_end, B->dn_sys_end - B->dn_res_end,
@@ -1537,6 +1587,20 @@ int hslam_ba_batch_step_host(hslam_ba_batch* B, const hslam_ba_step_io* io) {
   if (any_res) HS_CUDA(cudaStreamWaitEvent(ctx->stream, ctx->ev_join, 0));   // the context stream stays the one to wait on
   HS_CUDA(cudaStreamSynchronize(ctx->stream));
   for (const Out& s : staged) memcpy(s.dst, B->h_dn + s.off, s.bytes);
+  if (any_th)
+    for (int i = 0; i < n; ++i) {
+      if (!io[i].frameEnergyTH_out) continue;
+      // the device descriptor of the batch already holds the new threshold: bring the host mirrors in line without
+      // marking the batch dirty (a caller that hands the same value back in its next hslam_window changes nothing)
+      hslam_ba* ba = B->items[i];
+      const float th = *reinterpret_cast<const float*>(B->h_dn + B->io[i].dn_th);
+      const bool in_sync = B->versions[i] == ba->desc_version;
+      ba->hdesc.W.frameEnergyTH[io[i].newest_frame] = th;
+      B->h_descs[i].W.frameEnergyTH[io[i].newest_frame] = th;
+      ba->desc_version++;
+      if (in_sync) B->versions[i] = ba->desc_version;
+      if (io[i].frameEnergyTH_out != (float*)(B->h_dn + B->io[i].dn_th)) *io[i].frameEnergyTH_out = th;
+    }
   return 0;
 }
 

@@ -67,6 +67,7 @@ struct BAWin {
   float fx, fy, cx, cy, fxi, fyi;
   float huber, outlierTH, scale_idepth, scale_f, scale_c, affA, affB;
   float cDeltaF[4];
+  float thN, thFac, thConst, thOverall;   // setting_frameEnergyTH{N,FacMedian,ConstWeight}, setting_overallEnergyTHWeight
   const float4* img[HSLAM_MAX_FRAMES];
   const float4* pimg[HSLAM_MAX_FRAMES];   // level-0 pair images (hslam_frame::pair0): what the lineariser gathers from
   float frameEnergyTH[HSLAM_MAX_FRAMES];
@@ -163,6 +164,8 @@ struct BADesc {
 struct BAIO {
   long long up_precalc, up_adHTd, up_adH, up_adT, up_fprior, up_fdprior, up_idepth, up_deltaF, up_idz, up_x;
   long long dn_energy, dn_nres, dn_Hb, dn_newEnergy, dn_newEnergyWO, dn_newState, dn_step;
+  long long dn_th;           // new frameEnergyTH of frame `newest` (System::setNewFrameEnergyTH), 1 float
+  int newest, pad;
 };
 
 __device__ __forceinline__ int find_window(const int* __restrict__ prefix, int nwin, int b, int& local) {
@@ -502,6 +505,101 @@ __device__ __forceinline__ void energy_sum_block(const BADesc& D, double* red) {
 __global__ void __launch_bounds__(256) ba_energy_kernel(const BADesc* __restrict__ descs) {
   __shared__ double red[16];
   energy_sum_block(descs[blockIdx.x], red);
+}
+
+
+// ------------------------------------------------------------------------------------------------
+// System::setNewFrameEnergyTH (Src/FullSystemOptimize.cpp:60-101) for ONE window by one block: exact k-th order
+// statistic of state_NewEnergyWithOutlier over the non-linearised residuals into the newest frame (they are one
+// contiguous range of the pair-sorted arrays: pair = host + target*n), k = (int)(THN * count), by a 4-round MSB-first
+// radix select on the float bit patterns (all candidates are >= 0, so the unsigned order is the float order) — the
+// value std::nth_element leaves at index k, without sorting and without the energies leaving HBM.  Then the
+// threshold arithmetic of :86-91 in exactly-rounded fp32.  Integer histogram atomics only: deterministic.
+// ------------------------------------------------------------------------------------------------
+constexpr int TH_THREADS = 512;
+__device__ __forceinline__ float energy_th_block(const BADesc& D, int newest) {
+  __shared__ unsigned int hist[256];
+  __shared__ int sh[6];   // lo, hi, count, prefix, rank, (unused)
+  const BARes& r = D.r;
+  const BAWin& W = D.W;
+  const int n = W.n, R = r.R;
+  if (threadIdx.x < 2) {
+    // lower_bound of pair >= (newest + threadIdx.x) * n over the pair-sorted residual array
+    const int key = (newest + (int)threadIdx.x) * n;
+    int lo = 0, hi = R;
+    while (lo < hi) { const int m = (lo + hi) >> 1; if (r.pair[m] < key) lo = m + 1; else hi = m; }
+    sh[threadIdx.x] = lo;
+  }
+  if (threadIdx.x == 2) sh[2] = 0;
+  __syncthreads();
+  const int lo = sh[0], hi = sh[1];
+  int c = 0;
+  for (int k = lo + threadIdx.x; k < hi; k += TH_THREADS)
+    if (r.isLin[k] == 0 && r.newEnergyWO[k] >= 0.f) c++;
+  c = warp_sum(c);
+  if ((threadIdx.x & 31) == 0 && c) atomicAdd(&sh[2], c);
+  __syncthreads();
+  const int cnt = sh[2];
+  if (cnt == 0) return (float)(12 * 12 * HSLAM_PATTERN_NUM);   // :73-77
+  if (threadIdx.x == 0) { sh[3] = 0; sh[4] = (int)xmul(W.thN, (float)cnt); }   // :80 nthIdx = setting_frameEnergyTHN * size
+  unsigned int mask = 0;
+  for (int shift = 24; shift >= 0; shift -= 8) {
+    if (threadIdx.x < 256) hist[threadIdx.x] = 0;
+    __syncthreads();
+    const unsigned int prefix = (unsigned int)sh[3];
+    for (int k = lo + threadIdx.x; k < hi; k += TH_THREADS) {
+      const float e = r.newEnergyWO[k];
+      if (r.isLin[k] == 0 && e >= 0.f) {
+        const unsigned int key = __float_as_uint(e);
+        if ((key & mask) == prefix) atomicAdd(&hist[(key >> shift) & 255u], 1u);
+      }
+    }
+    __syncthreads();
+    if (threadIdx.x < 32) {
+      // warp 0: lane l owns bins 8l..8l+7; exclusive scan of the lane sums, the lane whose span holds the rank resolves it
+      const int rank = sh[4];
+      unsigned int h8[8], tot = 0;
+#pragma unroll
+      for (int j = 0; j < 8; ++j) { h8[j] = hist[8 * threadIdx.x + j]; tot += h8[j]; }
+      unsigned int inc = tot;
+#pragma unroll
+      for (int o = 1; o < 32; o <<= 1) { const unsigned int v = __shfl_up_sync(0xffffffffu, inc, o); if ((int)threadIdx.x >= o) inc += v; }
+      unsigned int cum = inc - tot;
+      if ((unsigned int)rank >= cum && (unsigned int)rank < inc) {
+        int b = 0;
+        bool open = true;   // rank < cum + tot: the walk stops inside this lane's eight bins
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          if (open && (unsigned int)rank >= cum + h8[j]) { cum += h8[j]; b = j + 1; } else open = false;
+        }
+        sh[3] = (int)(prefix | ((unsigned int)(8 * threadIdx.x + b) << shift));
+        sh[4] = rank - (int)cum;
+      }
+    }
+    mask |= 255u << shift;
+    __syncthreads();
+  }
+  const float nth = xsqrt(__uint_as_float((unsigned int)sh[3]));   // :86
+  float th = xmul(nth, W.thFac);                                    // :88
+  th = xadd(xmul(26.0f, W.thConst), xmul(th, xsub(1.0f, W.thConst)));   // :89
+  th = xmul(th, th);                                                // :90
+  th = xmul(th, xmul(W.thOverall, W.thOverall));                    // :91
+  return th;
+}
+// One block per window.  `newest` < 0: taken from io[win].newest.  The result goes to th_dev[win] (nullable), to the
+// window's slot of the batch D2H block (io / dn, nullable) and INTO the device descriptor (the next linearisation of
+// the window reads it, as the reference's does from Frame::frameEnergyTH).
+__global__ void __launch_bounds__(TH_THREADS) ba_energy_th_kernel(BADesc* __restrict__ descs, int newest, float* __restrict__ th_dev,
+                                                                  const BAIO* __restrict__ io, char* __restrict__ dn) {
+  const int win = blockIdx.x;
+  if (io && io[win].dn_th < 0) return;
+  const int nf = newest >= 0 ? newest : io[win].newest;
+  const float th = energy_th_block(descs[win], nf);
+  if (threadIdx.x == 0) {
+    descs[win].W.frameEnergyTH[nf] = th;
+    if (th_dev) th_dev[win] = th;
+    if (io) *reinterpret_cast<float*>(dn + io[win].dn_th) = th;
+  }
 }
 
 __global__ void ba_apply_kernel(BARes r) {

@@ -139,6 +139,9 @@ struct hslam_ctx {
   hslam_params prm;
   int sm_count = 148;
   int64_t launches = 0;
+  // cudaFuncAttributeMaxDynamicSharedMemorySize is per device: remembered per context, not per process
+  bool top_attr_done = false;
+  size_t schur_smem_configured = 48 * 1024;
   // optional per-kernel event timing (hslam_profile_*)
   bool profile = false;
   struct ProfRec { int k; cudaEvent_t a, b; };

@@ -28,6 +28,10 @@ void hslam_params_default(hslam_params* p) {
   p->scale_idepth = 1.0f;
   const int it[5] = {10, 20, 50, 50, 50};  // Src/CoarseTracker.cpp:518
   for (int i = 0; i < 5; ++i) p->max_tracker_iterations[i] = it[i];
+  p->frameEnergyTHN = 0.7f;            // Src/Settings.cpp:73
+  p->frameEnergyTHFacMedian = 1.5f;    // :74
+  p->frameEnergyTHConstWeight = 0.5f;  // :75
+  p->overallEnergyTHWeight = 1.0f;     // :66
 }
 
 int hslam_create(const hslam_params* params, int device, hslam_ctx** out) {
@@ -123,7 +127,7 @@ int hslam_host_free(hslam_ctx* c, void* p) {
 
 static const char* k_names[HSLAM_K_COUNT] = {"pyramid_level", "trk_eval", "trk_track", "ba_linearize", "ba_apply",
                                              "ba_top", "ba_fold_top", "ba_point_sum", "ba_schur", "ba_fold_sc",
-                                             "ba_stitch", "ba_resub", "ba_fixlin", "unpack_level", "ba_energy", "ba_layout", "trace", "coarse_depth"};
+                                             "ba_stitch", "ba_resub", "ba_fixlin", "unpack_level", "ba_energy", "ba_layout", "trace", "coarse_depth", "ba_energy_th"};
 const char* hslam_kernel_name(int k) { return (k >= 0 && k < HSLAM_K_COUNT) ? k_names[k] : ""; }
 
 int hslam_profile_enable(hslam_ctx* c, int enable) {

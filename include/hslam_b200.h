@@ -31,7 +31,7 @@
 extern "C" {
 #endif
 
-#define HSLAM_ABI_VERSION 1
+#define HSLAM_ABI_VERSION 2
 #define HSLAM_MAX_PYR_LEVELS 10   /* CoarseTracker::PYR_LEVELS, Include/CoarseTracker.h:32 */
 #define HSLAM_PATTERN_NUM 8       /* ChosenPattern 8, Include/GlobalTypes.h:33,181 */
 #define HSLAM_CPARS 4             /* Include/GlobalTypes.h:223 */
@@ -68,6 +68,11 @@ typedef struct hslam_params {
   float scale_c;                 /* SCALE_C = 50          (GlobalTypes.h:38) */
   float scale_idepth;            /* SCALE_IDEPTH = 1      (GlobalTypes.h:34) */
   int   max_tracker_iterations[5]; /* {10,20,50,50,50}    (CoarseTracker.cpp:518) */
+  /* System::setNewFrameEnergyTH (Src/FullSystemOptimize.cpp:60-101) */
+  float frameEnergyTHN;          /* setting_frameEnergyTHN = 0.7          (Settings.cpp:73) */
+  float frameEnergyTHFacMedian;  /* setting_frameEnergyTHFacMedian = 1.5  (Settings.cpp:74) */
+  float frameEnergyTHConstWeight;/* setting_frameEnergyTHConstWeight = 0.5(Settings.cpp:75) */
+  float overallEnergyTHWeight;   /* setting_overallEnergyTHWeight = 1     (Settings.cpp:66) */
 } hslam_params;
 
 typedef struct hslam_ctx hslam_ctx;
@@ -116,7 +121,8 @@ int hslam_host_free(hslam_ctx* ctx, void* p);
 #define HSLAM_K_BA_EXPORT 15
 #define HSLAM_K_TRACE 16
 #define HSLAM_K_COARSE_DEPTH 17
-#define HSLAM_K_COUNT 18
+#define HSLAM_K_BA_ENERGY_TH 18
+#define HSLAM_K_COUNT 19
 int hslam_profile_enable(hslam_ctx* ctx, int enable);
 int hslam_profile_read(hslam_ctx* ctx, float ms_out[HSLAM_K_COUNT], int count_out[HSLAM_K_COUNT]);
 const char* hslam_kernel_name(int k);
@@ -304,6 +310,16 @@ int hslam_ba_update_points(hslam_ba* ba, const float* idepth, const float* delta
 int hslam_ba_linearize(hslam_ba* ba, int fixLinearization, double* energy_sum,
                        int8_t* newState, float* newEnergy, float* newEnergyWithOutlier,
                        float* centerProjectedTo, float* projectedTo);
+/* System::setNewFrameEnergyTH (Src/FullSystemOptimize.cpp:60-101), which System::linearizeAll calls after EVERY
+ * linearisation pass (:124): over the non-linearised residuals whose target is the newest keyframe and whose
+ * state_NewEnergyWithOutlier >= 0, the element std::nth_element puts at index (int)(setting_frameEnergyTHN * count)
+ * (an exact k-th order statistic: radix select on the device, no sort, no host copy of the energies), then
+ * th = sqrtf(nth) * FacMedian; th = 26 * ConstWeight + th * (1 - ConstWeight); th = th * th * overallWeight^2 in
+ * exactly-rounded fp32; 12*12*patternNum when there is no such residual (:73-77).  The settings come from the
+ * context's hslam_params.  Like the reference, the call also STORES the value as the window's
+ * frameEnergyTH[newest_frame_idx] (what the next linearisation reads); th_out (host, nullable) receives it.
+ * The per-residual energies never leave HBM. */
+int hslam_ba_new_frame_energy_th(hslam_ba* ba, int newest_frame_idx, float* th_out);
 /* System::applyRes_Reductor -> PointFrameResidual::applyRes(true) + takeData
  * (FullSystemOptimize.cpp:55-59; OptimizationClasses.cpp:235-256, .h:155-161). */
 int hslam_ba_apply_res(hslam_ba* ba);
@@ -363,6 +379,11 @@ typedef struct hslam_ba_step_io {
   float* newEnergyWithOutlier;     /* R */
   double* Hb;                      /* [H_A|b_A|H_L|b_L|H_SC|b_SC] as hslam_ba_accumulate_all */
   int32_t* nres2;                  /* {resInA, resInL} */
+  /* System::setNewFrameEnergyTH on the device after the linearisation (see hslam_ba_new_frame_energy_th): when
+   * frameEnergyTH_out is not null, the new threshold of frame `newest_frame` is computed, stored in the window and
+   * returned here (1 float) — the caller then needs neither newEnergy nor newEnergyWithOutlier on the host. */
+  float* frameEnergyTH_out;
+  int32_t newest_frame;
 } hslam_ba_step_io;
 int hslam_ba_batch_step_host(hslam_ba_batch* batch, const hslam_ba_step_io* io /* one per window */);
 /* Zero-copy buffers: point every OUTPUT member of io[0..count) (and step_out[i], if not null) at the window's

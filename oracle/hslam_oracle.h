@@ -171,6 +171,10 @@ int orc_ba_marginalize_points(orc_ba* ba, const int32_t* point_ids, int count, f
                               double* Msc, double* Mbsc, int* nres);
 /* EnergyFunctional::calcLEnergyF_MT (Src/EnergyFunctional.cpp:349-364). */
 int orc_ba_calc_l_energy(orc_ba* ba, double* out);
+/* System::setNewFrameEnergyTH (Src/FullSystemOptimize.cpp:60-101) after a linearisation pass: std::nth_element at
+ * (int)(setting_frameEnergyTHN * count) over state_NewEnergyWithOutlier of the non-linearised residuals into frame
+ * `newest`; also stores the threshold as the window's frameEnergyTH[newest]. */
+int orc_ba_new_frame_energy_th(orc_ba* ba, int newest, float* th_out);
 
 /* ---- immature point tracing ---- */
 #define ORC_IPS_GOOD 0

@@ -266,6 +266,7 @@ struct BABase {
   virtual int resubstitute(const double*, float*) = 0;
   virtual int marginalize_points(const int32_t*, int, float, double*, double*, double*, double*, int*) = 0;
   virtual int calc_l_energy(double*) = 0;
+  virtual int new_frame_energy_th(int, float*) = 0;
 };
 
 template <class T> struct BA : BABase {
@@ -968,6 +969,30 @@ template <class T> struct BA : BABase {
 
   // EnergyFunctional::calcLEnergyF_MT / calcLEnergyPt, Src/EnergyFunctional.cpp:289-364 (Accumulator11 is a
   // sequential float sum with 1k / 1M shift-up tiers; restated here as a plain sum in T)
+  // System::setNewFrameEnergyTH, Src/FullSystemOptimize.cpp:60-101 (called by linearizeAll after every pass, :124)
+  int new_frame_energy_th(int newest, float* th_out) override {
+    if (newest < 0 || newest >= n) return -1;
+    std::vector<float> allResVec;                       // System.h:64 vector<float>
+    allResVec.reserve((size_t)R * 2);
+    for (int r : active_list())                         // :67 activeResiduals = the non-linearised residuals
+      if (state_NewEnergyWithOutlier[r] >= 0 && rtarget[r] == newest) allResVec.push_back((float)state_NewEnergyWithOutlier[r]);
+    float th;
+    if (allResVec.size() == 0) {
+      th = 12 * 12 * HSLAM_PATTERN_NUM;                 // :73-77
+    } else {
+      int nthIdx = prm.frameEnergyTHN * allResVec.size();   // :80 float * size_t -> float -> int
+      std::nth_element(allResVec.begin(), allResVec.begin() + nthIdx, allResVec.end());
+      float nthElement = sqrtf(allResVec[nthIdx]);      // :86
+      th = nthElement * prm.frameEnergyTHFacMedian;     // :88
+      th = 26.0f * prm.frameEnergyTHConstWeight + th * (1 - prm.frameEnergyTHConstWeight);   // :89
+      th = th * th;                                     // :90
+      th *= prm.overallEnergyTHWeight * prm.overallEnergyTHWeight;   // :91
+    }
+    frameEnergyTH[newest] = th;
+    if (th_out) *th_out = th;
+    return 0;
+  }
+
   int calc_l_energy(double* out) override {
     double E = 0;
     for (int f = 0; f < n; ++f)
@@ -1042,4 +1067,5 @@ int orc_ba_marginalize_points(orc_ba* ba, const int32_t* pids, int count, float 
   return ba->impl->marginalize_points(pids, count, prior_scale, M, Mb, Msc, Mbsc, nres);
 }
 int orc_ba_calc_l_energy(orc_ba* ba, double* out) { return ba->impl->calc_l_energy(out); }
+int orc_ba_new_frame_energy_th(orc_ba* ba, int newest, float* th_out) { return ba->impl->new_frame_energy_th(newest, th_out); }
 }

@@ -22,6 +22,8 @@ class Params(C.Structure):
         ("affineOptModeA", C.c_float), ("affineOptModeB", C.c_float), ("scale_xi_rot", C.c_float),
         ("scale_xi_trans", C.c_float), ("scale_a", C.c_float), ("scale_b", C.c_float), ("scale_f", C.c_float),
         ("scale_c", C.c_float), ("scale_idepth", C.c_float), ("max_tracker_iterations", C.c_int * 5),
+        ("frameEnergyTHN", C.c_float), ("frameEnergyTHFacMedian", C.c_float), ("frameEnergyTHConstWeight", C.c_float),
+        ("overallEnergyTHWeight", C.c_float),
     ]
 
     @staticmethod
@@ -29,6 +31,7 @@ class Params(C.Structure):
         p = Params(9.0, 20.0, 2500.0, 1e12, 1e8, 1.0, 0.5, 10.0, 1000.0, 50.0, 50.0, 1.0)
         for i, v in enumerate([10, 20, 50, 50, 50]):
             p.max_tracker_iterations[i] = v
+        p.frameEnergyTHN, p.frameEnergyTHFacMedian, p.frameEnergyTHConstWeight, p.overallEnergyTHWeight = 0.7, 1.5, 0.5, 1.0
         return p
 
 
@@ -429,6 +432,12 @@ class BAOracle:
         e = C.c_double(0)
         assert self.L.orc_ba_calc_l_energy(self.h, C.byref(e)) == 0
         return e.value
+
+    def new_frame_energy_th(self, newest):
+        """System::setNewFrameEnergyTH (FullSystemOptimize.cpp:60-101); also stored as the window's frameEnergyTH[newest]."""
+        th = C.c_float(0)
+        assert self.L.orc_ba_new_frame_energy_th(self.h, C.c_int(int(newest)), C.byref(th)) == 0
+        return np.float32(th.value)
 
     def resubstitute(self, x):
         step = np.zeros(self.P, np.float32)

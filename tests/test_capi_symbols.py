@@ -47,7 +47,7 @@ def test_defaults_match_reference_settings(lib, capi):
     assert (p.huberTH, p.coarseCutoffTH, p.outlierTHSumComponent) == (9.0, 20.0, 2500.0)      # Src/Settings.cpp:68,77,64
     assert (p.scale_xi_rot, p.scale_xi_trans, p.scale_a, p.scale_b) == (1.0, 0.5, 10.0, 1000.0)  # GlobalTypes.h:34-41
     assert list(p.max_tracker_iterations) == [10, 20, 50, 50, 50]                              # CoarseTracker.cpp:518
-    assert lib.hslam_abi_version() == 1
+    assert lib.hslam_abi_version() == 2
 
 
 def test_fails_loudly_without_a_gpu(lib, capi):

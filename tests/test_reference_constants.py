@@ -78,5 +78,11 @@ def test_trace_and_robust_settings_match_Settings_cpp():
                         ("scale_b", "SCALE_B"), ("scale_f", "SCALE_F"), ("scale_c", "SCALE_C"), ("scale_idepth", "SCALE_IDEPTH")):
         ref = float(re.search(r"#define\s+" + name + r"\s+([0-9.]+)f", gt).group(1))
         assert getattr(p, field) == np.float32(ref), field
+    # System::setNewFrameEnergyTH settings (FullSystemOptimize.cpp:80-91)
+    for field, name in (("frameEnergyTHN", "setting_frameEnergyTHN"), ("frameEnergyTHFacMedian", "setting_frameEnergyTHFacMedian"),
+                        ("frameEnergyTHConstWeight", "setting_frameEnergyTHConstWeight"), ("overallEnergyTHWeight", "setting_overallEnergyTHWeight")):
+        assert np.float32(getattr(p, field)) == np.float32(_setting(st, name)), field
+    fso = _read("Src/FullSystemOptimize.cpp")
+    assert "12*12*patternNum" in fso and "26.0f*setting_frameEnergyTHConstWeight" in fso and "setNewFrameEnergyTH();" in fso
     # values the synthetic generators hard-code
     assert _setting(st, "setting_outlierTH") == 144.0 and _setting(st, "setting_idepthFixPrior") == 2500.0
