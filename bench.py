@@ -40,7 +40,9 @@ UNIT = "Mres/s"
 
 # algorithmic bytes per residual of each kernel class (DESIGN.md "Kernels and rooflines")
 ALGO_BYTES_PER_RES = {
-    "ba_linearize": 384 + 13.3 + 12 + 296 + 64,   # 8 px x 4 texels x 12 B, point record/6, indices; J + projectedTo written
+    # 8 px x 4 texels x 12 B, point record/6, indices/state; written: the 34 geometric + summed floats of RawResidualJacobian
+    # (GN-loop mode: the 40 per-pixel floats and projectedTo, 160 + 64 B, are not materialised; 769 B with them)
+    "ba_linearize": 384 + 13.3 + 12 + 136,
     "ba_top": 148 + 2 + 24,                       # 37 Jacobian floats + flags read; 6 per-residual point terms written
     "ba_schur": 32 + 2,                           # JpJdF read per residual
 }
@@ -196,6 +198,7 @@ def main():
         ef = capi.EnergyFunctional(ctx)
         ef.set_window(w, fr)
         ef.set_topology(w)
+        ef.set_jacobian_mode(1)       # GN-loop mode (hslam_ba_set_jacobian_mode): per-pixel Jacobian rows only for fixLinearizationF
         efs.append(ef); frames_all.append(fr)
     ctx.synchronize()
     px_per_step = sum(w.R for w in wins) * 8
@@ -329,7 +332,8 @@ def main():
 
     cfg = workload_config(args.windows)
     cfg.update({"l2_policy": f"inputs larger than L2 (no flush): batch working set ~{args.windows * 62} MB vs 126 MB L2",
-                "jacobians": "materialised (SoA in HBM)",
+                "jacobians": "GN-loop mode: the 34 geometric + summed Jacobian floats per residual are materialised (SoA in HBM), "
+                             "the 40 per-pixel floats + projectedTo only when a residual is fixed (fixLinearizationF)",
                 "e2e_api": "hslam_ba_batch_step_host + hslam_ba_batch_resubstitute_host (host buffers, 2 waits per step)"})
     line = {
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,

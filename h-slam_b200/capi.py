@@ -556,6 +556,10 @@ class EnergyFunctional:
                                                 _ptr(Ms), _ptr(Mbs), C.byref(nres)))
         return M.reshape(N, N).T.copy(), Mb, Ms.reshape(N, N).T.copy(), Mbs, nres.value
 
+    def set_jacobian_mode(self, mode):
+        """0: all 74 Jacobian floats stored; 1: GN-loop mode (per-pixel rows + projectedTo only on fixLinearization)."""
+        _chk(self.L.hslam_ba_set_jacobian_mode(self.h, C.c_int(int(mode))))
+
     def setNewFrameEnergyTH(self, newest_frame):
         """System::setNewFrameEnergyTH (FullSystemOptimize.cpp:60-101) on the device; returns the new threshold."""
         th = np.zeros(1, np.float32)

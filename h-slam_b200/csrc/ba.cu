@@ -59,6 +59,12 @@ struct hslam_ba {
   DevBuf<uint8_t> d_isLin, d_isActive;
   DevBuf<float> d_senergy, d_newEnergy, d_newEnergyWO, d_J, d_JpJdF, d_rtz, d_cpt, d_pto, d_ptc[2];
   std::vector<int> r_sorted2orig, r_orig2sorted;
+  // host mirrors of the sorted residual order (for re-grouping when residuals become linearised)
+  std::vector<int> h_rpair, h_rpoint, h_rb, h_ri;   // per sorted residual: pair, sorted point; CSR of sorted points over sorted residual positions
+  std::vector<uint8_t> h_lin;                        // per sorted residual: isLinearized
+  std::vector<int> h_segBegin;                       // [2*n*n+1]: segment (pair, isLinearized) -> first sorted position
+  DevBuf<int> d_perm;
+  DevBuf<float> d_permF;                             // scratch of the re-grouping gather
   DevBuf<int> d_r_s2o, d_p_s2o;          // device copies of the sorted->caller permutations
   DevBuf<unsigned char> d_marg;          // marginalisation flags per sorted point
   DevBuf<char> d_scratch;                // staging for layout conversion kernels
@@ -69,10 +75,13 @@ struct hslam_ba {
   DevBuf<int> d_pair_chunk_begin;
   DevBuf<float> d_toppartial;
   DevBuf<unsigned int> d_pair_ticket;
-  int n_topchunks[2] = {0, 0};   // top-kernel BLOCKS per mode (mode 0 blocks first, then mode 1)
-  int top_chunks0 = 0;           // chunks (partials) per mode
+  int n_topblocks[3] = {0, 0, 0};   // top-kernel BLOCKS per tile schedule (A, L, marginalisation)
   DevBuf<TopTile> d_toptiles;
   DevBuf<int> d_top_block_begin;
+  DevBuf<LinTile> d_lintiles;
+  int sched_tile0[3] = {0, 0, 0}, sched_bb0[3] = {0, 0, 0};   // offsets of every schedule in d_toptiles / d_top_block_begin
+  int n_lintiles = 0;
+  int jmode = 0;                 // 0 = full Jacobians stored, 1 = GN-loop mode (see hslam_ba_set_jacobian_mode)
   DevBuf<PtChunk> d_ptchunks;
   DevBuf<int> d_host_chunk_begin;
   DevBuf<float> d_scpartial;
@@ -80,7 +89,7 @@ struct hslam_ba {
   int n_ptchunks = 0;
   int maxres = 1;
   int target_blocks = 0;                 // blocks per stage this window should fill (0 = 2 x SM count)
-  std::vector<int> h_pairBegin, h_hostBegin;   // kept for re-chunking (hslam_ba_set_parallelism)
+  std::vector<int> h_hostBegin;   // kept for re-chunking (hslam_ba_set_parallelism)
   DevBuf<double> d_accTop, d_G, d_Hb, d_epart, d_energy;
   DevBuf<int> d_nres;          // [2]
   DevBuf<unsigned int> d_ticket;
@@ -233,18 +242,22 @@ static void fill_desc(hslam_ba* ba) {
   p.step = ba->d_step.p;
   D.W.precalc = ba->d_precalc.p; D.W.adHTdeltaF = ba->d_adHTd.p;
   D.epart = ba->d_epart.p; D.ticket = ba->d_ticket.p; D.energy = ba->d_energy.p;
-  D.lin_warps = std::max(1, (ba->R + LIN_THREADS - 1) / LIN_THREADS) * (LIN_THREADS / 32);
+  D.lin_warps = ba->n_lintiles * (LIN_THREADS / 32);
+  D.lintiles = ba->d_lintiles.p; D.jmode = ba->jmode;
   D.topchunks = ba->d_topchunks.p; D.toppartial = ba->d_toppartial.p; D.pair_ticket = ba->d_pair_ticket.p;
   D.pair_chunk_begin = ba->d_pair_chunk_begin.p; D.accTop = ba->d_accTop.p;
-  D.toptiles = ba->d_toptiles.p; D.top_block_begin = ba->d_top_block_begin.p;
-  D.top_blocks = ba->n_topchunks[0]; D.top_chunks0 = ba->top_chunks0;
+  for (int m = 0; m < 3; ++m) {
+    D.sched[m].tiles = ba->d_toptiles.p + ba->sched_tile0[m];
+    D.sched[m].block_begin = ba->d_top_block_begin.p + ba->sched_bb0[m];
+    D.sched[m].blocks = ba->n_topblocks[m]; D.sched[m].pad = 0;
+  }
   D.ptchunks = ba->d_ptchunks.p; D.scpartial = ba->d_scpartial.p; D.host_ticket = ba->d_host_ticket.p;
   D.host_chunk_begin = ba->d_host_chunk_begin.p; D.G = ba->d_G.p; D.LD = ba->LD; D.maxres = ba->maxres;
   StitchArgs& S = D.S;
   S.n = ba->n; S.LD = ba->LD;
   S.adHost = ba->d_adH.p; S.adTarget = ba->d_adT.p; S.accTop = ba->d_accTop.p; S.G = ba->d_G.p; S.Hb = ba->d_Hb.p;
   S.nres = ba->d_nres.p; S.framePrior = ba->d_fprior.p; S.frameDeltaPrior = ba->d_fdprior.p;
-  S.add_priors = ba->add_priors; S.has_L = ba->n_linearized != 0;
+  S.add_priors = ba->add_priors; S.has_L = ba->n_linearized != 0; S.L_set = 1;
   for (int i = 0; i < 4; ++i) S.cDeltaF[i] = D.W.cDeltaF[i];
   D.marg = nullptr; D.shift_prior = 1;
   D.r_s2o = ba->d_r_s2o.p; D.p_s2o = ba->d_p_s2o.p;
@@ -266,56 +279,68 @@ static int sync_desc(hslam_ba* ba) {
 // write and fold, fewer block-level reductions).
 static int build_chunks(hslam_ba* ba) {
   hslam_ctx* ctx = ba->ctx;
-  const int n = ba->n, nn = n * n, R = ba->R, P = ba->P;
-  const std::vector<int>& pairBegin = ba->h_pairBegin;
+  const int n = ba->n, nn = n * n;
   const std::vector<int>& hostBegin = ba->h_hostBegin;
   const int target_blocks = ba->target_blocks > 0 ? ba->target_blocks : 2 * ctx->sm_count;
   {
-    // tiles of <= TOP_THREADS residuals that never cross a pair; equal runs of tiles per block; chunks =
-    // maximal same-pair runs inside a block (see ba_top_kernel)
+    // Three tile schedules over the (pair, isLinearized) segments of the sorted residual array: A = the non-linearised
+    // half of every pair, L = the linearised half, marginalisation = the whole pair.  Tiles of <= TOP_THREADS residuals
+    // that never cross a pair; equal runs of tiles per block; chunks = maximal same-pair runs inside a block (see
+    // ba_top_kernel).  Chunk indices are global: schedule m's chunks follow schedule m-1's.
+    const std::vector<int>& seg = ba->h_segBegin;
     struct HT { int start, count, pair; };
-    std::vector<HT> ht;
-    for (int k = 0; k < nn; ++k)
-      for (int s0 = pairBegin[k]; s0 < pairBegin[k + 1]; s0 += TOP_THREADS)
-        ht.push_back({s0, std::min(TOP_THREADS, pairBegin[k + 1] - s0), k});
-    const int NT = (int)ht.size();
-    const int per = std::max(1, (NT + target_blocks - 1) / target_blocks);
-    const int T = (NT + per - 1) / per;
-    std::vector<int> bb(T + 1, 0);
-    std::vector<TopTile> tiles(NT);
+    std::vector<TopTile> tiles;
     std::vector<TopChunk> ch;
-    for (int b = 0; b < T; ++b) {
-      bb[b] = b * per;
-      const int e = std::min(NT, (b + 1) * per);
-      for (int t = b * per; t < e; ++t) {
-        if (t == b * per || ht[t].pair != ht[t - 1].pair) ch.push_back(TopChunk{ht[t].pair, ht[t].start, 0, 0});
-        ch.back().count += ht[t].count;
-        tiles[t] = TopTile{ht[t].start, ht[t].count, (int)ch.size() - 1, 0};
-      }
-    }
-    bb[T] = NT;
-    const int nch0 = (int)ch.size();
-    for (int c = 0; c < nch0; ++c) { TopChunk m = ch[c]; m.mode = 1; ch.push_back(m); }
-    std::vector<int> pcb(2 * nn + 1, 0);
-    for (int mode = 0; mode < 2; ++mode) {
-      int c = mode * nch0;
+    std::vector<int> bb;
+    std::vector<int> pcb(3 * nn + 1, 0);
+    for (int m = 0; m < 3; ++m) {
+      std::vector<HT> ht;
       for (int k = 0; k < nn; ++k) {
-        pcb[mode * nn + k] = c;
-        while (c < (mode + 1) * nch0 && ch[c].pair == k) ++c;
+        const int lo = m == 1 ? seg[2 * k + 1] : seg[2 * k], hi = m == 0 ? seg[2 * k + 1] : seg[2 * k + 2];
+        for (int s0 = lo; s0 < hi; s0 += TOP_THREADS) ht.push_back({s0, std::min(TOP_THREADS, hi - s0), k});
+      }
+      const int NT = (int)ht.size();
+      const int per = std::max(1, (NT + target_blocks - 1) / target_blocks);
+      const int T = (NT + per - 1) / per;
+      ba->sched_tile0[m] = (int)tiles.size();
+      ba->sched_bb0[m] = (int)bb.size();
+      ba->n_topblocks[m] = T;
+      const int c0 = (int)ch.size();
+      for (int b = 0; b < T; ++b) {
+        bb.push_back(b * per);
+        const int e = std::min(NT, (b + 1) * per);
+        for (int t = b * per; t < e; ++t) {
+          if (t == b * per || ht[t].pair != ht[t - 1].pair) ch.push_back(TopChunk{ht[t].pair, ht[t].start, 0, m});
+          ch.back().count += ht[t].count;
+          tiles.push_back(TopTile{ht[t].start, ht[t].count, (int)ch.size() - 1, 0});
+        }
+      }
+      bb.push_back(NT);
+      int c = c0;
+      for (int k = 0; k < nn; ++k) {
+        pcb[m * nn + k] = c;
+        while (c < (int)ch.size() && ch[c].pair == k) ++c;
       }
     }
-    pcb[2 * nn] = 2 * nch0;
-    ba->n_topchunks[0] = ba->n_topchunks[1] = T;   // BLOCKS per mode
-    ba->top_chunks0 = nch0;
+    pcb[3 * nn] = (int)ch.size();
     TRY(ba->d_topchunks.ensure(ch.size() + 1)); TRY(ba->d_pair_chunk_begin.ensure(pcb.size()));
-    TRY(ba->d_toptiles.ensure(tiles.size() + 1)); TRY(ba->d_top_block_begin.ensure(bb.size()));
+    TRY(ba->d_toptiles.ensure(tiles.size() + 1)); TRY(ba->d_top_block_begin.ensure(bb.size() + 1));
     TRY(ba->d_toppartial.ensure((ch.size() + 1) * TOP_PART));
-    TRY(ba->d_pair_ticket.ensure(2 * nn + 1));
-    HS_CUDA(cudaMemsetAsync(ba->d_pair_ticket.p, 0, (2 * nn + 1) * sizeof(unsigned int), ctx->stream));
+    TRY(ba->d_pair_ticket.ensure(3 * nn + 1));
+    HS_CUDA(cudaMemsetAsync(ba->d_pair_ticket.p, 0, (3 * nn + 1) * sizeof(unsigned int), ctx->stream));
     TRY(upload(ba, ba->d_topchunks.p, ch.data(), ch.size())); TRY(upload(ba, ba->d_pair_chunk_begin.p, pcb.data(), pcb.size()));
     TRY(upload(ba, ba->d_toptiles.p, tiles.data(), tiles.size())); TRY(upload(ba, ba->d_top_block_begin.p, bb.data(), bb.size()));
-    // pairs without any chunk are never folded: their accumulators must read as zero
-    HS_CUDA(cudaMemsetAsync(ba->d_accTop.p, 0, 2 * (size_t)nn * TOP_PART * sizeof(double), ctx->stream));
+    // pairs without any chunk in a schedule are never folded: their accumulators must read as zero
+    HS_CUDA(cudaMemsetAsync(ba->d_accTop.p, 0, 3 * (size_t)nn * TOP_PART * sizeof(double), ctx->stream));
+    // lineariser: tiles of <= LIN_THREADS non-linearised residuals of one pair
+    std::vector<LinTile> lt;
+    for (int k = 0; k < nn; ++k)
+      for (int s0 = seg[2 * k]; s0 < seg[2 * k + 1]; s0 += LIN_THREADS)
+        lt.push_back(LinTile{s0, std::min(LIN_THREADS, seg[2 * k + 1] - s0), k, 0});
+    ba->n_lintiles = (int)lt.size();
+    TRY(ba->d_lintiles.ensure(lt.size() + 1));
+    TRY(upload(ba, ba->d_lintiles.p, lt.data(), lt.size()));
+    TRY(ba->d_epart.ensure((size_t)(lt.size() + 2) * (LIN_THREADS / 32)));   // one energy partial per warp
   }
   {
     // Chunks are cut in whole
@@ -365,6 +390,84 @@ static int build_chunks(hslam_ba* ba) {
   return 0;
 }
 
+// Slot table of the Schur kernel from the host mirrors: sorted residual position and target of every (point, slot).
+static int upload_slots(hslam_ba* ba) {
+  const int P = ba->P, n = ba->n;
+  std::vector<int> slot((size_t)P * ba->maxres + 1, -1);
+  for (int sp = 0; sp < P; ++sp)
+    for (int i = ba->h_rb[sp], j = 0; i < ba->h_rb[sp + 1]; ++i, ++j) {
+      const int pos = ba->h_ri[i];
+      slot[(size_t)sp * ba->maxres + j] = pos | ((ba->h_rpair[pos] / n) << 26);
+    }
+  TRY(ba->d_slot.ensure(slot.size()));
+  return upload(ba, ba->d_slot.p, slot.data(), slot.size());
+}
+
+// Residuals have changed their isLinearized flag (hslam_ba_fix_linearization): restore the sorted order's invariant —
+// inside every (host,target) pair the non-linearised residuals first, then the linearised ones, each group in its old
+// (stable) order — by permuting every per-residual device array once, and rebuild the tables that hold sorted positions.
+static int regroup(hslam_ba* ba) {
+  hslam_ctx* ctx = ba->ctx;
+  const int R = ba->R, n = ba->n, nn = n * n;
+  TRY(ba_flush(ba));
+  std::vector<int> seg(2 * nn + 1, 0);
+  for (int k = 0; k < R; ++k) seg[2 * ba->h_rpair[k] + (ba->h_lin[k] ? 1 : 0) + 1]++;
+  for (int k = 0; k < 2 * nn; ++k) seg[k + 1] += seg[k];
+  std::vector<int> newpos(R), perm(R);
+  bool identity = true;
+  {
+    std::vector<int> cur(seg.begin(), seg.end() - 1);
+    for (int k = 0; k < R; ++k) {
+      const int q = cur[2 * ba->h_rpair[k] + (ba->h_lin[k] ? 1 : 0)]++;
+      newpos[k] = q; perm[q] = k;
+      identity = identity && q == k;
+    }
+  }
+  ba->h_segBegin = seg;
+  if (!identity) {
+    std::vector<int> s2o(R), rpair(R), rpoint(R);
+    std::vector<uint8_t> lin(R);
+    for (int q = 0; q < R; ++q) {
+      const int k = perm[q];
+      s2o[q] = ba->r_sorted2orig[k]; rpair[q] = ba->h_rpair[k]; rpoint[q] = ba->h_rpoint[k]; lin[q] = ba->h_lin[k];
+    }
+    ba->r_sorted2orig.swap(s2o); ba->h_rpair.swap(rpair); ba->h_rpoint.swap(rpoint); ba->h_lin.swap(lin);
+    for (int q = 0; q < R; ++q) ba->r_orig2sorted[ba->r_sorted2orig[q]] = q;
+    for (int& v : ba->h_ri) v = newpos[v];
+    // device: every per-residual array through one scratch buffer
+    const size_t rsz = ba->rs;
+    TRY(ba->d_perm.ensure(R));
+    TRY(ba->d_permF.ensure((size_t)JS * rsz));
+    TRY(upload(ba, ba->d_perm.p, perm.data(), R));
+    const unsigned gx = (unsigned)((R + 255) / 256);
+    auto permF = [&](float* arr, int comps) -> int {
+      HS_LAUNCH(ctx, HSLAM_K_BA_EXPORT, (ba_permute_kernel<float><<<dim3(gx, comps), 256, 0, ctx->stream>>>(arr, ba->d_permF.p, rsz, R, ba->d_perm.p)));
+      HS_CUDA(cudaMemcpyAsync(arr, ba->d_permF.p, (size_t)comps * rsz * sizeof(float), cudaMemcpyDeviceToDevice, ctx->stream));
+      return 0;
+    };
+    auto permB = [&](void* arr) -> int {
+      HS_LAUNCH(ctx, HSLAM_K_BA_EXPORT, (ba_permute_kernel<unsigned char><<<dim3(gx, 1), 256, 0, ctx->stream>>>(
+                                            (const unsigned char*)arr, (unsigned char*)ba->d_permF.p, rsz, R, ba->d_perm.p)));
+      HS_CUDA(cudaMemcpyAsync(arr, ba->d_permF.p, (size_t)R, cudaMemcpyDeviceToDevice, ctx->stream));
+      return 0;
+    };
+    TRY(permF(ba->d_J.p, JS)); TRY(permF(ba->d_rtz.p, 8)); TRY(permF(ba->d_cpt.p, 3)); TRY(permF(ba->d_pto.p, 16));
+    TRY(permF(ba->d_ptc[0].p, 6)); TRY(permF(ba->d_senergy.p, 1)); TRY(permF(ba->d_newEnergy.p, 1)); TRY(permF(ba->d_newEnergyWO.p, 1));
+    TRY(permB(ba->d_state.p)); TRY(permB(ba->d_newState.p)); TRY(permB(ba->d_isLin.p)); TRY(permB(ba->d_isActive.p));
+    HS_LAUNCH(ctx, HSLAM_K_BA_EXPORT, (ba_permute_rec32_kernel<<<gx, 256, 0, ctx->stream>>>(
+                                          (const float4*)ba->d_JpJdF.p, (float4*)ba->d_permF.p, R, ba->d_perm.p)));
+    HS_CUDA(cudaMemcpyAsync(ba->d_JpJdF.p, ba->d_permF.p, (size_t)R * 8 * sizeof(float), cudaMemcpyDeviceToDevice, ctx->stream));
+    HS_CUDA(cudaGetLastError());
+    TRY(upload(ba, ba->d_rpoint.p, ba->h_rpoint.data(), R)); TRY(upload(ba, ba->d_rpair.p, ba->h_rpair.data(), R));
+    TRY(upload(ba, ba->d_r_s2o.p, ba->r_sorted2orig.data(), R));
+    TRY(upload(ba, ba->d_res_index.p, ba->h_ri.data(), R));
+    TRY(upload_slots(ba));
+  }
+  TRY(build_chunks(ba));
+  fill_desc(ba);
+  return ba_flush(ba);
+}
+
 extern "C" {
 
 int hslam_ba_create(hslam_ctx* ctx, hslam_ba** out) {
@@ -399,7 +502,7 @@ int hslam_ba_destroy(hslam_ba* ba) {
   ba->d_newEnergyWO.release(); ba->d_J.release(); ba->d_JpJdF.release(); ba->d_rtz.release(); ba->d_cpt.release();
   ba->d_pto.release(); ba->d_topchunks.release(); ba->d_pair_chunk_begin.release(); ba->d_toppartial.release();
   ba->d_pair_ticket.release(); ba->d_host_ticket.release(); ba->d_toptiles.release(); ba->d_top_block_begin.release();
-  ba->d_ptchunks.release(); ba->d_host_chunk_begin.release(); ba->d_scpartial.release(); ba->d_G.release();
+  ba->d_ptchunks.release(); ba->d_host_chunk_begin.release(); ba->d_lintiles.release(); ba->d_perm.release(); ba->d_permF.release(); ba->d_scpartial.release(); ba->d_G.release();
   ba->d_Hb.release(); ba->d_epart.release(); ba->d_energy.release(); ba->d_nres.release(); ba->d_ticket.release();
   ba->d_xc.release(); ba->d_xAd.release(); ba->d_x.release(); ba->d_ids.release(); ba->d_th.release(); ba->d_desc.release();
   ba->d_r_s2o.release(); ba->d_p_s2o.release(); ba->d_scratch.release(); ba->d_marg.release();
@@ -487,9 +590,9 @@ int hslam_ba_set_window(hslam_ba* ba, const hslam_window* w) {
   TRY(upload(ba, ba->d_adHTd.p, w->adHTdeltaF, nn * 8));
   TRY(ba->d_x.ensure(ba->N)); TRY(ba->d_xc.ensure(4)); TRY(ba->d_xAd.ensure(nn * 8));
   TRY(ba->d_Hb.ensure(3 * ((size_t)ba->N * ba->N + ba->N)));
-  if (ba->d_accTop.cap < 2 * nn * TOP_PART) {
-    TRY(ba->d_accTop.ensure(2 * nn * TOP_PART));
-    HS_CUDA(cudaMemsetAsync(ba->d_accTop.p, 0, 2 * nn * TOP_PART * sizeof(double), ctx->stream));
+  if (ba->d_accTop.cap < 3 * nn * TOP_PART) {
+    TRY(ba->d_accTop.ensure(3 * nn * TOP_PART));
+    HS_CUDA(cudaMemsetAsync(ba->d_accTop.p, 0, 3 * nn * TOP_PART * sizeof(double), ctx->stream));
   }
   if (ba->d_G.cap < (size_t)n * ba->LD * ba->LD) {
     TRY(ba->d_G.ensure((size_t)n * ba->LD * ba->LD));
@@ -546,15 +649,18 @@ int hslam_ba_set_topology(hslam_ba* ba, const hslam_point_soa* pt, const hslam_r
   }
   HS_ARG((int)walk.size() == R, "hslam_ba_set_topology: some residuals belong to no point");
   const int nn = n * n;
-  std::vector<int> pairBegin(nn + 1, 0);
+  // segments: (pair, isLinearized) -> the non-linearised residuals of a pair first, then its linearised ones
+  std::vector<int> segBegin(2 * nn + 1, 0);
   auto pair_of = [&](int r) { return pt->host_idx[rs->point_idx[r]] + rs->target_idx[r] * n; };
-  for (int r : walk) pairBegin[pair_of(r) + 1]++;
-  for (int k = 0; k < nn; ++k) pairBegin[k + 1] += pairBegin[k];
+  auto seg_of = [&](int r) { return 2 * pair_of(r) + (rs->is_linearized[r] ? 1 : 0); };
+  for (int r : walk) segBegin[seg_of(r) + 1]++;
+  for (int k = 0; k < 2 * nn; ++k) segBegin[k + 1] += segBegin[k];
   ba->r_sorted2orig.assign(R, 0); ba->r_orig2sorted.assign(R, 0);
   {
-    std::vector<int> cur(pairBegin.begin(), pairBegin.end() - 1);
-    for (int r : walk) { int k = cur[pair_of(r)]++; ba->r_sorted2orig[k] = r; ba->r_orig2sorted[r] = k; }
+    std::vector<int> cur(segBegin.begin(), segBegin.end() - 1);
+    for (int r : walk) { int k = cur[seg_of(r)]++; ba->r_sorted2orig[k] = r; ba->r_orig2sorted[r] = k; }
   }
+  ba->h_segBegin = segBegin;
   ba->P = P; ba->R = R; ba->rs = (R + 31) & ~31;
   if (ba->rs == 0) ba->rs = 32;
   const size_t rsz = ba->rs;
@@ -588,15 +694,7 @@ int hslam_ba_set_topology(hslam_ba* ba, const hslam_point_soa* pt, const hslam_r
       for (int i = pt->res_begin[p]; i < pt->res_begin[p + 1]; ++i) ri[pos++] = ba->r_orig2sorted[pt->res_index[i]];
     }
     rb[P] = pos;
-    // slot table of the Schur kernel: sorted residual position and target of every (point, slot)
-    std::vector<int> slot((size_t)P * ba->maxres + 1, -1);
-    for (int sp = 0; sp < P; ++sp) {
-      int p = ba->p_sorted2orig[sp];
-      for (int i = pt->res_begin[p], j = 0; i < pt->res_begin[p + 1]; ++i, ++j)
-        slot[(size_t)sp * ba->maxres + j] = ba->r_orig2sorted[pt->res_index[i]] | (rs->target_idx[pt->res_index[i]] << 26);
-    }
-    TRY(ba->d_slot.ensure(slot.size()));
-    TRY(upload(ba, ba->d_slot.p, slot.data(), slot.size()));
+    ba->h_rb = rb; ba->h_ri = ri;
     ba->h_uvid = uvid;
     TRY(upload(ba, ba->d_uvid.p, uvid.data(), P)); TRY(upload(ba, ba->d_color.p, col.data(), 2 * (size_t)P));
     TRY(upload(ba, ba->d_weights.p, wgt.data(), 2 * (size_t)P)); TRY(upload(ba, ba->d_priorF.p, prior.data(), P));
@@ -618,9 +716,11 @@ int hslam_ba_set_topology(hslam_ba* ba, const hslam_point_soa* pt, const hslam_r
       se[k] = rs->state_energy ? (float)rs->state_energy[r] : 0.f;
       ba->n_linearized += lin[k];
     }
+    ba->h_rpair = rpair; ba->h_rpoint = rp; ba->h_lin = lin;
     TRY(upload(ba, ba->d_rpoint.p, rp.data(), R)); TRY(upload(ba, ba->d_rpair.p, rpair.data(), R));
     TRY(upload(ba, ba->d_state.p, st.data(), R)); TRY(upload(ba, ba->d_isLin.p, lin.data(), R));
     TRY(upload(ba, ba->d_isActive.p, act.data(), R)); TRY(upload(ba, ba->d_senergy.p, se.data(), R));
+    TRY(upload_slots(ba));   // needs the pair mirror
   }
   HS_CUDA(cudaMemsetAsync(ba->d_J.p, 0, (size_t)JS * rsz * sizeof(float), ctx->stream));
   HS_CUDA(cudaMemsetAsync(ba->d_JpJdF.p, 0, 8 * rsz * sizeof(float), ctx->stream));
@@ -639,9 +739,8 @@ int hslam_ba_set_topology(hslam_ba* ba, const hslam_point_soa* pt, const hslam_r
   HS_CUDA(cudaMemsetAsync(ba->d_HdiF.p, 0, (P + 1) * sizeof(float), ctx->stream));
   HS_CUDA(cudaMemsetAsync(ba->d_bdSumF.p, 0, (P + 1) * sizeof(float), ctx->stream));
   HS_CUDA(cudaMemsetAsync(ba->d_idh.p, 0, (P + 1) * sizeof(float), ctx->stream));
-  ba->h_pairBegin = pairBegin; ba->h_hostBegin = hostBegin;
+  ba->h_hostBegin = hostBegin;
   TRY(build_chunks(ba));
-  TRY(ba->d_epart.ensure((size_t)(ba->rs / 32 + 2 * LIN_THREADS / 32)));   // one energy partial per warp
   ba->have_topology = true;
   fill_desc(ba);
   TRY(ba_flush(ba));
@@ -675,15 +774,19 @@ int hslam_ba_update_points(hslam_ba* ba, const float* idepth, const float* delta
 }  // extern "C"
 
 // ---------------------------------------------------------------- launches (single window)
+template <class... A>
+static void lin_launch(bool apply, bool fullj, int blocks, cudaStream_t st, A... args) {
+  if (apply && fullj) ba_linearize_kernel<true, true><<<blocks, LIN_THREADS, 0, st>>>(args...);
+  else if (apply) ba_linearize_kernel<true, false><<<blocks, LIN_THREADS, 0, st>>>(args...);
+  else if (fullj) ba_linearize_kernel<false, true><<<blocks, LIN_THREADS, 0, st>>>(args...);
+  else ba_linearize_kernel<false, false><<<blocks, LIN_THREADS, 0, st>>>(args...);
+}
 static int launch_linearize(hslam_ba* ba, bool apply) {
   hslam_ctx* ctx = ba->ctx;
   TRY(sync_desc(ba));
-  int blocks = (ba->R + LIN_THREADS - 1) / LIN_THREADS;
-  if (blocks < 1) blocks = 1;
-  if (apply)
-    HS_LAUNCH(ctx, HSLAM_K_BA_LINEARIZE, (ba_linearize_kernel<true><<<blocks, LIN_THREADS, 0, ctx->stream>>>(ba->d_desc.p, nullptr, 1, 0)));
-  else
-    HS_LAUNCH(ctx, HSLAM_K_BA_LINEARIZE, (ba_linearize_kernel<false><<<blocks, LIN_THREADS, 0, ctx->stream>>>(ba->d_desc.p, nullptr, 1, 0)));
+  if (ba->n_lintiles > 0)
+    HS_LAUNCH(ctx, HSLAM_K_BA_LINEARIZE, lin_launch(apply, ba->jmode == 0, ba->n_lintiles, ctx->stream, (const BADesc*)ba->d_desc.p,
+                                                    (const int*)nullptr, 1, 0, (const int*)nullptr, 0));
   HS_CUDA(cudaGetLastError());
   return 0;
 }
@@ -705,13 +808,12 @@ static int launch_top(hslam_ba* ba, int modes) {
   TRY(sync_desc(ba));
   TRY(top_attr(ctx));
   HS_ARG(ba->tmap_ok, "hslam_ba: cuTensorMapEncodeTiled failed for the Jacobian tensor maps (driver too old?)");
-  const int T = ba->n_topchunks[0];
-  if (T > 0 && (modes & 1))
-    HS_LAUNCH(ctx, HSLAM_K_BA_TOP, (ba_top_kernel<0><<<T, 2 * TOP_THREADS, kTopSmem, ctx->stream>>>(ba->d_desc.p, nullptr, 1)));
-  if (T > 0 && (modes & 2))
-    HS_LAUNCH(ctx, HSLAM_K_BA_TOP, (ba_top_kernel<1><<<T, 2 * TOP_THREADS, kTopSmem, ctx->stream>>>(ba->d_desc.p, nullptr, 1)));
-  if (T > 0 && (modes & 4))   // addPoint<2> over the points flagged in desc.marg
-    HS_LAUNCH(ctx, HSLAM_K_BA_TOP, (ba_top_kernel<2><<<T, 2 * TOP_THREADS, kTopSmem, ctx->stream>>>(ba->d_desc.p, nullptr, 1)));
+  if (ba->n_topblocks[0] > 0 && (modes & 1))
+    HS_LAUNCH(ctx, HSLAM_K_BA_TOP, (ba_top_kernel<0><<<ba->n_topblocks[0], 2 * TOP_THREADS, kTopSmem, ctx->stream>>>(ba->d_desc.p, nullptr, 1)));
+  if (ba->n_topblocks[1] > 0 && (modes & 2))
+    HS_LAUNCH(ctx, HSLAM_K_BA_TOP, (ba_top_kernel<1><<<ba->n_topblocks[1], 2 * TOP_THREADS, kTopSmem, ctx->stream>>>(ba->d_desc.p, nullptr, 1)));
+  if (ba->n_topblocks[2] > 0 && (modes & 4))   // addPoint<2> over the points flagged in desc.marg
+    HS_LAUNCH(ctx, HSLAM_K_BA_TOP, (ba_top_kernel<2><<<ba->n_topblocks[2], 2 * TOP_THREADS, kTopSmem, ctx->stream>>>(ba->d_desc.p, nullptr, 1)));
   HS_CUDA(cudaGetLastError());
   return 0;
 }
@@ -857,7 +959,8 @@ int hslam_ba_new_frame_energy_th(hslam_ba* ba, int newest, float* th_out) {
 
 int hslam_ba_fix_linearization(hslam_ba* ba, const int32_t* ids, int count) {
   HS_ARG(ba && ba->have_topology && (count == 0 || ids), "hslam_ba_fix_linearization: bad argument");
-  HS_CUDA(cudaSetDevice(ba->ctx->device));
+  hslam_ctx* ctx = ba->ctx;
+  HS_CUDA(cudaSetDevice(ctx->device));
   if (count == 0) return 0;
   void* s;
   TRY(ba->d_ids.ensure(count));
@@ -867,12 +970,30 @@ int hslam_ba_fix_linearization(hslam_ba* ba, const int32_t* ids, int count) {
     HS_ARG(ids[i] >= 0 && ids[i] < ba->R, "hslam_ba_fix_linearization: id out of range");
     sorted[i] = ba->r_orig2sorted[ids[i]];
   }
-  HS_CUDA(cudaMemcpyAsync(ba->d_ids.p, sorted, (size_t)count * sizeof(int), cudaMemcpyHostToDevice, ba->ctx->stream));
-  HS_LAUNCH(ba->ctx, HSLAM_K_BA_FIXLIN, (ba_fixlin_kernel<<<(count + 127) / 128, 128, 0, ba->ctx->stream>>>(
-                                            ba->hdesc.W, ba->hdesc.r, ba->hdesc.p, ba->d_ids.p, count)));
+  HS_CUDA(cudaMemcpyAsync(ba->d_ids.p, sorted, (size_t)count * sizeof(int), cudaMemcpyHostToDevice, ctx->stream));
+  if (ba->jmode != 0) {
+    // GN-loop mode: the per-pixel rows of the Jacobian were not stored by the last pass; re-form them for these
+    // residuals at the window's current state (the reference re-linearises right before fixLinearizationF, Mapping.cpp:286-293)
+    TRY(sync_desc(ba));
+    HS_LAUNCH(ctx, HSLAM_K_BA_LINEARIZE, lin_launch(false, true, (count + LIN_THREADS - 1) / LIN_THREADS, ctx->stream, (const BADesc*)ba->d_desc.p,
+                                                    (const int*)nullptr, 1, 0, (const int*)ba->d_ids.p, count));
+  }
+  HS_LAUNCH(ctx, HSLAM_K_BA_FIXLIN, (ba_fixlin_kernel<<<(count + 127) / 128, 128, 0, ctx->stream>>>(
+                                        ba->hdesc.W, ba->hdesc.r, ba->hdesc.p, ba->d_ids.p, count)));
   HS_CUDA(cudaGetLastError());
-  if (ba->n_linearized == 0) { ba->n_linearized = count; ba->hdesc.S.has_L = 1; ba->desc_version++; }
-  else ba->n_linearized += count;
+  int fresh = 0;
+  for (int i = 0; i < count; ++i) { uint8_t& f = ba->h_lin[sorted[i]]; fresh += f ? 0 : 1; f = 1; }
+  ba->n_linearized += fresh;
+  // keep the sorted order's invariant (linearised residuals behind the others of their pair) and re-cut the schedules
+  return regroup(ba);
+}
+
+int hslam_ba_set_jacobian_mode(hslam_ba* ba, int mode) {
+  HS_ARG(ba && (mode == 0 || mode == 1), "hslam_ba_set_jacobian_mode: mode must be 0 (full) or 1 (GN loop)");
+  if (ba->jmode == mode) return 0;
+  ba->jmode = mode;
+  ba->hdesc.jmode = mode;
+  ba->desc_version++;
   return 0;
 }
 
@@ -998,7 +1119,7 @@ int hslam_ba_marginalize_points(hslam_ba* ba, const int32_t* point_ids, int coun
   // Schur scalars, no priors in the stitch (stitchDouble(..., usePrior=false), EnergyFunctional.cpp:578-579)
   const BADesc saved = ba->hdesc;
   ba->hdesc.marg = ba->d_marg.p; ba->hdesc.shift_prior = 0;
-  ba->hdesc.S.add_priors = 0; ba->hdesc.S.has_L = 1;
+  ba->hdesc.S.add_priors = 0; ba->hdesc.S.has_L = 1; ba->hdesc.S.L_set = 2;
   ba->desc_version++;
   TRY(launch_top(ba, 4));
   TRY(launch_schur(ba));
@@ -1090,13 +1211,14 @@ struct hslam_ba_batch {
   std::vector<hslam_ba*> items;
   std::vector<uint64_t> versions;
   DevBuf<BADesc> d_descs;
-  DevBuf<int> d_prefix;          // NPF tables of (count+1): linearize, top, schur, stitch, schur fold, resubstitute
+  DevBuf<int> d_prefix;          // NPF tables of (count+1): linearize, top A, schur, stitch, schur fold, resubstitute, top L
   BADesc* h_descs = nullptr;     // pinned
   int* h_prefix = nullptr;       // pinned
   cudaEvent_t copied = nullptr;
   cudaEvent_t ev_grp[8] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};   // step_host: per window-group fork points
-  int blocks[6] = {0, 0, 0, 0, 0, 0};
-  int uniform[6] = {0, 0, 0, 0, 0, 0};   // blocks per window of a stage when every window has the same count, else 0
+  int blocks[7] = {0, 0, 0, 0, 0, 0, 0};
+  int uniform[7] = {0, 0, 0, 0, 0, 0, 0};
+  bool fullJ = true;             // some member stores full Jacobians: the batch launch does for all   // blocks per window of a stage when every window has the same count, else 0
   size_t smem = 0;
   int maxt = 1, ni = 2;
   bool any_L = false;
@@ -1117,7 +1239,7 @@ struct hslam_ba_batch {
   cudaEvent_t ev_begin = nullptr;
   size_t dn_state_end = 0, dn_res_end = 0, dn_sys_end = 0, dn_end = 0;   // D2H block regions: [0,res) per-residual arrays, [res,sys) systems, [sys,end) steps
 };
-static const int NPF = 6;
+static const int NPF = 7;
 
 static int batch_refresh(hslam_ba_batch* B) {
   const int n = (int)B->items.size();
@@ -1134,13 +1256,16 @@ static int batch_refresh(hslam_ba_batch* B) {
   for (int k = 0; k < NPF; ++k) { pf[k] = B->h_prefix + k * (n + 1); pf[k][0] = 0; }
   const size_t smem0 = B->smem; const int maxt0 = B->maxt, ni0 = B->ni; const bool anyL0 = B->any_L;
   B->smem = 0; B->maxt = 0; B->ni = 2; B->any_L = false;
+  bool fullJ = false;
   for (int i = 0; i < n; ++i) {
     hslam_ba* ba = B->items[i];
     B->h_descs[i] = ba->hdesc;
     B->versions[i] = ba->desc_version;
-    int lin = std::max(1, (ba->R + LIN_THREADS - 1) / LIN_THREADS);
-    int top = ba->n_topchunks[0];
+    int lin = ba->n_lintiles;
+    int top = ba->n_topblocks[0];
     B->any_L = B->any_L || ba->n_linearized != 0;
+    fullJ = fullJ || ba->jmode == 0;
+    pf[6][i + 1] = pf[6][i] + ba->n_topblocks[1];
     pf[0][i + 1] = pf[0][i] + lin;
     pf[1][i + 1] = pf[1][i] + top;
     pf[2][i + 1] = pf[2][i] + ba->n_ptchunks;
@@ -1161,7 +1286,8 @@ static int batch_refresh(hslam_ba_batch* B) {
     for (int i = 1; i < n; ++i) if (pf[k][i + 1] - pf[k][i] != pf[k][1]) B->uniform[k] = 0;
     if (n < 2 || pf[k][1] == 0) B->uniform[k] = 0;
   }
-  bool launch_changed = smem0 != B->smem || maxt0 != B->maxt || ni0 != B->ni || anyL0 != B->any_L;
+  bool launch_changed = smem0 != B->smem || maxt0 != B->maxt || ni0 != B->ni || anyL0 != B->any_L || fullJ != B->fullJ;
+  B->fullJ = fullJ;
   for (int k = 0; k < NPF; ++k) launch_changed |= blocks0[k] != B->blocks[k] || uniform0[k] != B->uniform[k];
   HS_CUDA(cudaMemcpyAsync(B->d_descs.p, B->h_descs, n * sizeof(BADesc), cudaMemcpyHostToDevice, B->ctx->stream));
   HS_CUDA(cudaMemcpyAsync(B->d_prefix.p, B->h_prefix, NPF * (n + 1) * sizeof(int), cudaMemcpyHostToDevice, B->ctx->stream));
@@ -1231,7 +1357,8 @@ static int batch_enqueue_linearize(hslam_ba_batch* B, int g0 = 0, int g1 = -1) {
   if (g1 < 0) g1 = n;
   const int b0 = B->h_prefix[g0], cnt = B->h_prefix[g1] - b0;   // table 0 = linearise blocks
   if (cnt <= 0) return 0;
-  HS_LAUNCH(ctx, HSLAM_K_BA_LINEARIZE, (ba_linearize_kernel<true><<<cnt, LIN_THREADS, 0, ctx->stream>>>(B->d_descs.p, B->d_prefix.p, B->uniform[0] ? -B->uniform[0] : n, b0)));
+  HS_LAUNCH(ctx, HSLAM_K_BA_LINEARIZE, lin_launch(true, B->fullJ, cnt, ctx->stream, (const BADesc*)B->d_descs.p, (const int*)B->d_prefix.p,
+                                                  B->uniform[0] ? -B->uniform[0] : n, b0, (const int*)nullptr, 0));
   HS_CUDA(cudaGetLastError());
   return 0;
 }
@@ -1243,9 +1370,9 @@ static int batch_enqueue_accumulate(hslam_ba_batch* B) {
   TRY(top_attr(ctx));
   if (B->blocks[1] > 0) {
     HS_LAUNCH(ctx, HSLAM_K_BA_TOP, (ba_top_kernel<0><<<B->blocks[1], 2 * TOP_THREADS, kTopSmem, ctx->stream>>>(B->d_descs.p, pf + (n + 1), B->uniform[1] ? -B->uniform[1] : n)));
-    if (B->any_L)
-      HS_LAUNCH(ctx, HSLAM_K_BA_TOP, (ba_top_kernel<1><<<B->blocks[1], 2 * TOP_THREADS, kTopSmem, ctx->stream>>>(B->d_descs.p, pf + (n + 1), B->uniform[1] ? -B->uniform[1] : n)));
   }
+  if (B->any_L && B->blocks[6] > 0)
+    HS_LAUNCH(ctx, HSLAM_K_BA_TOP, (ba_top_kernel<1><<<B->blocks[6], 2 * TOP_THREADS, kTopSmem, ctx->stream>>>(B->d_descs.p, pf + 6 * (n + 1), B->uniform[6] ? -B->uniform[6] : n)));
   if (B->blocks[2] > 0)
     HS_LAUNCH(ctx, HSLAM_K_BA_SCHUR, schur_launch(B->maxt, B->ni, B->blocks[2], B->smem, ctx->stream, B->d_descs.p, pf + 2 * (n + 1), B->uniform[2] ? -B->uniform[2] : n));
   HS_LAUNCH(ctx, HSLAM_K_BA_FOLD_SC, (ba_fold_sc_kernel<<<B->blocks[4], 256, 0, ctx->stream>>>(B->d_descs.p, pf + 4 * (n + 1), B->uniform[4] ? -B->uniform[4] : n)));

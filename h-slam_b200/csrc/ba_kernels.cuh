@@ -110,15 +110,18 @@ struct BAPts {               // per-point SoA, sorted by host
   float* step;
 };
 
-struct TopChunk { int pair, start, count, mode; };
-struct TopTile { int start, count, chunk, pad; };   // <= 128 residuals of one pair; chunk = partial it is reduced into
+struct TopChunk { int pair, start, count, mode; };   // mode = schedule index: 0 = A, 1 = L, 2 = marginalisation
+struct TopTile { int start, count, chunk, pad; };   // <= 128 residuals of one pair; chunk = partial it is reduced into (global index)
+struct TopSched { const TopTile* tiles; const int* block_begin; int blocks, pad; };   // tile schedule of one mode (see ba_top_kernel)
+struct LinTile { int start, count, pair, pad; };    // <= LIN_THREADS non-linearised residuals of one (host,target) pair
 struct PtChunk { int host, start, count, pad; };
 
 struct StitchArgs {
   int n, LD;
   const double* adHost;      // n*n*64 col-major
   const double* adTarget;
-  const double* accTop;      // [2][n*n][TOP_PART] fp64 (A, L)
+  const double* accTop;      // [3][n*n][TOP_PART] fp64 (A, L, marginalisation)
+  int L_set;                 // accumulator set the L system is stitched from: 1 (accumulateLF) or 2 (marginalizePointsF)
   const double* G;           // [host][LD*LD]
   double* Hb;                // 3 x (N*N + N)
   int* nres;                 // [2]
@@ -136,10 +139,13 @@ struct BADesc {
   BARes r;
   BAPts p;
   // linearise
-  double* epart; unsigned int* ticket; double* energy; int lin_warps;   // lin_warps = 4 * linearise blocks
+  double* epart; unsigned int* ticket; double* energy; int lin_warps;   // lin_warps = warps per block * linearise blocks
+  const LinTile* lintiles;   // tile schedule of the lineariser: the non-linearised residuals, pair by pair
+  int jmode;                 // 0: every Jacobian float is stored; 1: GN-loop mode, the per-pixel rows (resF, JIdx, JabF) and
+                             //    projectedTo are not stored (only fixLinearizationF / mode L read them: re-formed on demand)
   // top
   const TopChunk* topchunks; float* toppartial; unsigned int* pair_ticket; const int* pair_chunk_begin; double* accTop;
-  const TopTile* toptiles; const int* top_block_begin; int top_blocks, top_chunks0;   // tile schedule (see ba_top_kernel)
+  TopSched sched[3];         // tile schedules: A over the non-linearised, L over the linearised, marginalisation over all residuals
   // schur
   const PtChunk* ptchunks; float* scpartial; unsigned int* host_ticket; const int* host_chunk_begin; double* G; int LD;
   int maxres;                // longest residual list of a point (<= HSLAM_MAX_FRAMES)
@@ -210,9 +216,14 @@ __device__ __forceinline__ void apply_one(const BARes& r, int k) {  // Optimizat
   r.state_energy[k] = r.newEnergy[k];
 }
 
-template <bool APPLY>
+// Indexing: block b of a window owns lintiles[b]: <= LIN_THREADS NON-linearised residuals of ONE (host,target) pair (the
+// sorted order keeps the linearised residuals of a pair behind the others), so linearised residuals cost nothing and no
+// store of a warp is a partial sector.  With `ids` (sorted positions, one window, J-refresh pass of
+// hslam_ba_fix_linearization in GN-loop mode): thread i re-forms every Jacobian float of residual ids[i] and writes nothing else.
+template <bool APPLY, bool FULLJ>
 __global__ void __launch_bounds__(LIN_THREADS, LIN_MINB) ba_linearize_kernel(const BADesc* __restrict__ descs,
-                                                                   const int* __restrict__ prefix, int nwin, int block0) {
+                                                                   const int* __restrict__ prefix, int nwin, int block0,
+                                                                   const int* __restrict__ ids, int n_ids) {
 #ifndef LIN_PARK
 #define LIN_PARK 0   /* measured: parking colours/weights in smem 149 us vs 146 us in registers */
 #endif
@@ -221,55 +232,32 @@ __global__ void __launch_bounds__(LIN_THREADS, LIN_MINB) ba_linearize_kernel(con
 #endif
   int lb;
   const int win = find_window(prefix, nwin, blockIdx.x + block0, lb);   // block0: a launch may cover a sub-range of the batch
-#ifndef LIN_DESC_SMEM
-#define LIN_DESC_SMEM 0   /* measured: descriptor through shared memory 150.5 us, through the pointer 147.4 us */
-#endif
-#if LIN_DESC_SMEM
-  // the window descriptor (camera scalars, ~40 array pointers) is copied to shared memory once per block: every
-  // later field access is an LDS instead of a global load through the pointer
-  __shared__ __align__(16) BADesc sD;
-  {
-    static_assert(sizeof(BADesc) % 4 == 0, "descriptor is copied word by word");
-    const unsigned int* src = reinterpret_cast<const unsigned int*>(descs + win);
-    unsigned int* dst = reinterpret_cast<unsigned int*>(&sD);
-    for (int i = threadIdx.x; i < (int)(sizeof(BADesc) / 4); i += LIN_THREADS) dst[i] = __ldg(src + i);
-  }
-  __syncthreads();
-  const BADesc& D = sD;
-#else
   const BADesc& D = descs[win];
-#endif
   const BAWin& W = D.W;
   const BARes& r = D.r;
-  const int k = lb * LIN_THREADS + threadIdx.x;
   const int s = r.rs;
+  const bool refresh = ids != nullptr;
+  int k, pair;
+  bool valid;
+  if (refresh) {
+    const int i = lb * LIN_THREADS + threadIdx.x;
+    valid = i < n_ids;
+    k = valid ? ids[i] : 0;
+    pair = valid ? r.pair[k] : 0;
+  } else {
+    const LinTile tl = D.lintiles[lb];
+    valid = (int)threadIdx.x < tl.count;
+    k = tl.start + threadIdx.x;
+    pair = tl.pair;
+  }
   double energy_ret = 0.0;
   // every per-residual input is loaded up front (independent loads, one round trip)
-  const bool valid = k < r.R;
-  const bool lin = valid ? (r.isLin[k] != 0) : true;
   const int8_t st0 = valid ? r.state_state[k] : (int8_t)HSLAM_RES_OOB;
   const float old_energy = valid ? r.state_energy[k] : 0.f;
-  const int p = valid ? r.point[k] : 0, pair = valid ? r.pair[k] : 0;
-#ifndef LIN_PF
-#define LIN_PF 0
-#endif
-#if LIN_PF > 0
-  // the per-residual index/state streams of the blocks one residency-wave ahead are pulled into L2 now, so that
-  // their first (dependent) round trip is an L2 hit when those blocks start
-  if (k + LIN_PF < r.R) {
-    const int kp = k + LIN_PF;
-    asm volatile("prefetch.global.L2 [%0];" ::"l"(r.point + kp));
-    asm volatile("prefetch.global.L2 [%0];" ::"l"(r.pair + kp));
-    asm volatile("prefetch.global.L2 [%0];" ::"l"(r.state_energy + kp));
-    if ((threadIdx.x & 3) == 0) {
-      asm volatile("prefetch.global.L2 [%0];" ::"l"(r.state_state + kp));
-      asm volatile("prefetch.global.L2 [%0];" ::"l"(r.isLin + kp));
-    }
-  }
-#endif
-  if (valid && !lin) {
+  const int p = valid ? r.point[k] : 0;
+  if (valid) {
     float* J = r.J + k;
-    STJ(r.newEnergyWO + k, -1.f);
+    if (!refresh) STJ(r.newEnergyWO + k, -1.f);
     bool oob = (st0 == HSLAM_RES_OOB);
     const int tgtI = (pair * W.n_rcp) >> 16, hostI = pair - tgtI * W.n;   // pair = host + target * n
     float energyLeft = 0.f, wJI2 = 0.f;
@@ -313,7 +301,7 @@ __global__ void __launch_bounds__(LIN_THREADS, LIN_MINB) ba_linearize_kernel(con
       const float Ku = xadd(xmul(u, W.fx), W.cx), Kv = xadd(xmul(v, W.fy), W.cy);
       if (!oob && !(Ku > 1.1f && Kv > 1.1f && Ku < wm3 && Kv < hm3)) oob = true;
       if (!oob) {
-        STJ(r.cpt + k, Ku); STJ(r.cpt + s + k, Kv); STJ(r.cpt + 2 * s + k, new_idepth);
+        if (!refresh) { STJ(r.cpt + k, Ku); STJ(r.cpt + s + k, Kv); STJ(r.cpt + 2 * s + k, new_idepth); }
         // OptimizationClasses.cpp:85-121
         float ddx = xmul(xmul(xmul(drescale, xsub(t0[0], xmul(t0[2], u))), W.scale_idepth), W.fx);
         float ddy = xmul(xmul(xmul(drescale, xsub(t0[1], xmul(t0[2], v))), W.scale_idepth), W.fy);
@@ -352,9 +340,11 @@ __global__ void __launch_bounds__(LIN_THREADS, LIN_MINB) ba_linearize_kernel(con
           if (!in && n_ok == 8) n_ok = idx;
         }
         // the source stores projectedTo before it tests the next pixel: pixels [0, n_ok) are written
+        if (FULLJ) {
 #pragma unroll
-        for (int idx = 0; idx < 8; ++idx)
-          if (idx < n_ok) { STJ(r.pto + (2 * idx) * s + k, Kup[idx]); STJ(r.pto + (2 * idx + 1) * s + k, Kvp[idx]); }
+          for (int idx = 0; idx < 8; ++idx)
+            if (idx < n_ok) { STJ(r.pto + (2 * idx) * s + k, Kup[idx]); STJ(r.pto + (2 * idx + 1) * s + k, Kvp[idx]); }
+        }
         if (n_ok < 8) {
           oob = true;
           // Jacobian entries of the pixels before the first OOB one are written by the source as well;
@@ -409,12 +399,14 @@ __global__ void __launch_bounds__(LIN_THREADS, LIN_MINB) ba_linearize_kernel(con
             hw = xmul(hw, w);
             float h1 = xmul(hdx, hw), h2 = xmul(hdy, hw);
             float rF = xmul(residual, hw), ja = xmul(drdA, hw);
-            STJ(J + (J_RESF + idx) * s, rF);
-            STJ(J + (J_IDX0 + idx) * s, h1);
-            STJ(J + (J_IDX1 + idx) * s, h2);
             float jab0 = W.affA < 0.f ? 0.f : ja, jab1 = W.affB < 0.f ? 0.f : hw;
-            STJ(J + (J_AB0 + idx) * s, jab0);
-            STJ(J + (J_AB1 + idx) * s, jab1);
+            if (FULLJ) {   // the per-pixel rows: read only by fixLinearizationF, mode L and calcLEnergyPt
+              STJ(J + (J_RESF + idx) * s, rF);
+              STJ(J + (J_IDX0 + idx) * s, h1);
+              STJ(J + (J_IDX1 + idx) * s, h2);
+              STJ(J + (J_AB0 + idx) * s, jab0);
+              STJ(J + (J_AB1 + idx) * s, jab1);
+            }
             II00 = xadd(II00, xmul(h1, h1)); II11 = xadd(II11, xmul(h2, h2)); II10 = xadd(II10, xmul(h1, h2));
             AI00 = xadd(AI00, xmul(ja, h1)); AI01 = xadd(AI01, xmul(ja, h2));
             AI10 = xadd(AI10, xmul(hw, h1)); AI11 = xadd(AI11, xmul(hw, h2));
@@ -438,6 +430,7 @@ __global__ void __launch_bounds__(LIN_THREADS, LIN_MINB) ba_linearize_kernel(con
             STJ(J + J_RR * s, rr);
             // ---- classification (:221-231) and, when APPLY, applyRes(true)/takeData (:235-256, .h:155-161)
             // straight from registers
+            if (refresh) return;   // J-refresh pass: states, energies and JpJdF stay what the last pass left
             STJ(r.newEnergyWO + k, energyLeft);
             const float th = fmaxf(W.frameEnergyTH[hostI], W.frameEnergyTH[tgtI]);
             int8_t ns = HSLAM_RES_IN;
@@ -466,7 +459,7 @@ __global__ void __launch_bounds__(LIN_THREADS, LIN_MINB) ba_linearize_kernel(con
         }
       }
     }
-    if (oob) {
+    if (oob && !refresh) {
       r.newState[k] = HSLAM_RES_OOB;
       energy_ret = (double)old_energy;
       if (APPLY && st0 != HSLAM_RES_OOB) {
@@ -481,6 +474,7 @@ __global__ void __launch_bounds__(LIN_THREADS, LIN_MINB) ba_linearize_kernel(con
   // as soon as its residuals are done (a __threadfence here made every warp wait for its ~100 Jacobian
   // stores to drain: ~20 % of the kernel).  The partials are summed in index order by the next kernel
   // of the stream (ba_energy_kernel, or the stitch kernel in the fused/batched path).
+  if (refresh) return;
   const double e = warp_sum(energy_ret);
   if ((threadIdx.x & 31) == 0) D.epart[lb * (LIN_THREADS / 32) + (threadIdx.x >> 5)] = e;
 }
@@ -895,9 +889,12 @@ __global__ void __launch_bounds__(2 * TOP_THREADS, 2) ba_top_kernel(const BADesc
   const BADesc& D = descs[win];
   const BARes& r = D.r;
   const int s = r.rs;
-  constexpr int mode = MODE;   // modes A and L are separate launches over the same tile schedule
-  const int bIdx = lb;
-  const int t0 = D.top_block_begin[bIdx], t1 = D.top_block_begin[bIdx + 1];
+  constexpr int mode = MODE;   // every mode has its own tile schedule: A over the non-linearised residuals, L over the
+                               // linearised ones, marginalisation (2) over all of them
+  const TopSched& SC = D.sched[MODE];
+  if (lb >= SC.blocks) return;   // a batch launches max-over-windows blocks per window
+  const TopTile* __restrict__ toptiles = SC.tiles;
+  const int t0 = SC.block_begin[lb], t1 = SC.block_begin[lb + 1];
   const int part = threadIdx.x / TOP_THREADS;   // warp-uniform
   const int l = threadIdx.x & (TOP_THREADS - 1);
   __align__(8) float acc[56];   // 55 used (+1: packed pairs)
@@ -936,7 +933,7 @@ __global__ void __launch_bounds__(2 * TOP_THREADS, 2) ba_top_kernel(const BADesc
     if (use > 0) mbar_wait(&empty_bar[stg], (unsigned)(use - 1) & 1u);
     if (lane == 0) mbar_expect_tx(&full_bar[stg], TOP_NC * TOP_ROW * 4 + 2 * TOP_FROW);
     __syncwarp();
-    const TopTile tlp = D.toptiles[tp];
+    const TopTile tlp = toptiles[tp];
     TopStage& st = ring[stg];
     // the two flag rows ride along (a consumer that loaded them itself had a DRAM round trip on its critical path)
     if (lane == 2) bulk_g2s(st.lin, r.isLin + (tlp.start & ~15), TOP_FROW, &full_bar[stg]);
@@ -957,12 +954,12 @@ __global__ void __launch_bounds__(2 * TOP_THREADS, 2) ba_top_kernel(const BADesc
     for (int i = 0; i < TOP_DEPTH; ++i) produce(i);
   }
 
-  TopTile tl_next = t0 < t1 ? D.toptiles[t0] : TopTile{0, 0, 0, 0};
+  TopTile tl_next = t0 < t1 ? toptiles[t0] : TopTile{0, 0, 0, 0};
   for (int t = t0; t < t1; ++t) {
     const TopTile tl = tl_next;
-    if (t + 1 < t1) tl_next = D.toptiles[t + 1];   // the next descriptor is in flight while this tile is consumed
+    if (t + 1 < t1) tl_next = toptiles[t + 1];   // the next descriptor is in flight while this tile is consumed
     const int j = t - t0;
-    const int chunk = tl.chunk + (mode ? 1 : 0) * D.top_chunks0;   // modes 1 and 2 share the second accumulator set
+    const int chunk = tl.chunk;
     if (chunk != cur) {
       if (cur >= 0) {
         top_flush(D, cur, part, acc, nres, red, &last);
@@ -989,7 +986,7 @@ __global__ void __launch_bounds__(2 * TOP_THREADS, 2) ba_top_kernel(const BADesc
   constexpr int RQ = TOP_ROW / 4;
   auto issue = [&](int t) {
     if (mode == 0 && t < t1) {
-      const TopTile tl = D.toptiles[t];
+      const TopTile tl = toptiles[t];
       TopStage& st = ring[(t - t0) % TOP_STAGES];
       const float* src = r.J + (tl.start & ~3);
 #pragma unroll
@@ -1009,9 +1006,9 @@ __global__ void __launch_bounds__(2 * TOP_THREADS, 2) ba_top_kernel(const BADesc
   for (int i = 0; i < TOP_STAGES - 1; ++i) issue(t0 + i);
 
   for (int t = t0; t < t1; ++t) {
-    const TopTile tl = D.toptiles[t];
+    const TopTile tl = toptiles[t];
     issue(t + TOP_STAGES - 1);   // refills the stage that was consumed in the previous iteration
-    const int chunk = tl.chunk + (mode ? 1 : 0) * D.top_chunks0;   // modes 1 and 2 share the second accumulator set
+    const int chunk = tl.chunk;
     if (chunk != cur) {
       if (cur >= 0) {
         top_flush(D, cur, part, acc, nres, red, &last);
@@ -1641,7 +1638,7 @@ __global__ void __launch_bounds__(ST_THREADS) ba_stitch_kernel(const BADesc* __r
   } while (0)
 
   if (sys < 2) {
-    const double* acc = S.accTop + (size_t)sys * nn * TOP_PART;
+    const double* acc = S.accTop + (size_t)(sys == 0 ? 0 : S.L_set) * nn * TOP_PART;
     auto ACC = [&](int h, int t) { return acc + (size_t)(h + t * n) * TOP_PART; };
     const bool usePrior = (sys == 1) && S.add_priors;
     const bool live = (sys == 0) || S.has_L;   // without linearised residuals the L accumulators are zero
@@ -1841,6 +1838,21 @@ __global__ void ba_export_aos_kernel(const T* __restrict__ src, int comps, int c
   if (k >= count) return;
   size_t o = (size_t)sorted2orig[k] * comps;
   for (int c = 0; c < comps; ++c) dst[o + c] = src[(size_t)k * comps + c];
+}
+// Re-grouping of the sorted residual order (a residual became linearised: it moves behind the non-linearised ones of its
+// pair): dst[c][k] = src[c][perm[k]] for component-major arrays (grid.y = component), and the same for records.
+template <class T>
+__global__ void ba_permute_kernel(const T* __restrict__ src, T* __restrict__ dst, size_t stride, int count, const int* __restrict__ perm) {
+  const int k = blockIdx.x * blockDim.x + threadIdx.x;
+  if (k >= count) return;
+  const size_t o = (size_t)blockIdx.y * stride;
+  dst[o + k] = src[o + perm[k]];
+}
+__global__ void ba_permute_rec32_kernel(const float4* __restrict__ src, float4* __restrict__ dst, int count, const int* __restrict__ perm) {
+  const int k = blockIdx.x * blockDim.x + threadIdx.x;
+  if (k >= count) return;
+  const int q = perm[k];
+  dst[2 * (size_t)k] = src[2 * (size_t)q]; dst[2 * (size_t)k + 1] = src[2 * (size_t)q + 1];
 }
 // and the other way for per-point uploads: caller order [count] -> sorted order
 template <class T>

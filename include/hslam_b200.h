@@ -310,6 +310,16 @@ int hslam_ba_update_points(hslam_ba* ba, const float* idepth, const float* delta
 int hslam_ba_linearize(hslam_ba* ba, int fixLinearization, double* energy_sum,
                        int8_t* newState, float* newEnergy, float* newEnergyWithOutlier,
                        float* centerProjectedTo, float* projectedTo);
+/* What the lineariser keeps of RawResidualJacobian (Include/OptimizationClasses.h:48-77).  0 (default): all 74 floats +
+ * projectedTo, as the reference.  1, "GN-loop mode": the per-pixel rows resF[8], JIdx[2][8], JabF[2][8] (160 B) and
+ * projectedTo[8] (64 B, written at OptimizationClasses.cpp:150-151 and read nowhere) are NOT stored for the residuals
+ * that are re-linearised every iteration — accumulate{A,SC}F, applyRes/takeData and resubstitute only read the 34
+ * geometric / summed floats.  Their only readers, fixLinearizationF, addPoint<1>/<2> and calcLEnergyPt, work on
+ * linearised residuals: hslam_ba_fix_linearization re-forms the rows for the residuals it fixes, at the window's
+ * current state (the reference re-linearises right before fixLinearizationF as well, Src/Mapping.cpp:286-293).  In mode
+ * 1 hslam_ba_residual_results returns stale per-pixel rows for non-linearised residuals and hslam_ba_linearize
+ * returns stale projectedTo. */
+int hslam_ba_set_jacobian_mode(hslam_ba* ba, int mode);
 /* System::setNewFrameEnergyTH (Src/FullSystemOptimize.cpp:60-101), which System::linearizeAll calls after EVERY
  * linearisation pass (:124): over the non-linearised residuals whose target is the newest keyframe and whose
  * state_NewEnergyWithOutlier >= 0, the element std::nth_element puts at index (int)(setting_frameEnergyTHN * count)

@@ -493,3 +493,44 @@ def test_calc_l_energy_after_step_host_with_new_window(ctx, capi, O, synth):
     batch.close(); ef.close()
     for f in frames:
         f.close()
+
+
+def test_gn_loop_jacobian_mode_matches_full_mode(ctx, capi, O, synth, window_small):
+    """hslam_ba_set_jacobian_mode(1): the lineariser does not store resF / JIdx / JabF / projectedTo for the residuals it
+    re-linearises every iteration; fix_linearization re-forms them.  States, energies, JpJdF, res_toZeroF, every
+    Jacobian float of the linearised residuals, the three systems, L energy and the back-substitution are bit-identical
+    to full mode."""
+    win, is_lin = window_small
+    frames = [capi.Frame(ctx, im, 1) for im in win.images]
+    res = []
+    for mode in (0, 1):
+        ef = capi.EnergyFunctional(ctx); ef.set_window(win, frames); ef.set_topology(win)
+        ef.set_jacobian_mode(mode)
+        lin, lin2 = run_sequence(ef, win, is_lin, "gpu")
+        sys3 = ef.accumulate_all()
+        rr = ef.residual_results()
+        x = np.random.default_rng(5).normal(0, 1e-3, ef.N)
+        res.append(dict(lin=lin, lin2=lin2, sys3=sys3, rr=rr, E=ef.calcLEnergyF_MT(), step=ef.resubstituteF_MT(x), pr=ef.point_results()))
+        ef.close()
+    a, b = res
+    for k in ("newState", "newEnergy", "newEnergyWithOutlier", "centerProjectedTo"):
+        assert np.array_equal(a["lin"][k], b["lin"][k]) and np.array_equal(a["lin2"][k], b["lin2"][k]), k
+    assert a["lin2"]["energy"] == b["lin2"]["energy"] and a["E"] == b["E"]
+    for (Ha, ba_), (Hb, bb) in zip(a["sys3"], b["sys3"]):
+        assert np.array_equal(Ha, Hb) and np.array_equal(ba_, bb)
+    assert np.array_equal(a["step"], b["step"])
+    for k in a["pr"]:
+        assert np.array_equal(a["pr"][k], b["pr"][k]), k
+    ra, rb = a["rr"], b["rr"]
+    for k in ra:
+        va, vb = np.asarray(ra[k]), np.asarray(rb[k])
+        if va.ndim == 2 and va.shape[1] == 74:
+            # geometric + summed floats always; per-pixel rows for the linearised residuals
+            geo = np.r_[8:30, 62:74]
+            assert np.array_equal(va[:, geo], vb[:, geo])
+            m = is_lin.astype(bool)
+            assert m.any() and np.array_equal(va[m], vb[m])
+        else:
+            assert np.array_equal(va, vb), k
+    for f in frames:
+        f.close()

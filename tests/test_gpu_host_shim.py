@@ -20,7 +20,8 @@ def build_exe():
     if not os.path.exists(os.path.join(lib_dir, "libhslam_b200.so")):
         subprocess.check_call(["make", "-C", os.path.join(lib_dir, "csrc")], stdout=subprocess.DEVNULL)
     hdr = os.path.join(lib_dir, "host", "hslam_host.hpp")
-    if (not os.path.exists(EXE)) or max(os.path.getmtime(SRC), os.path.getmtime(hdr)) > os.path.getmtime(EXE):
+    chdr = os.path.join(ROOT, "include", "hslam_b200.h")   # struct layouts: a stale binary would smash its stack
+    if (not os.path.exists(EXE)) or max(os.path.getmtime(SRC), os.path.getmtime(hdr), os.path.getmtime(chdr)) > os.path.getmtime(EXE):
         subprocess.check_call(["g++", "-std=c++11", "-O2", "-Wall", "-o", EXE, SRC, f"-L{lib_dir}", "-lhslam_b200",
                                f"-Wl,-rpath,{lib_dir}"])
     return EXE
