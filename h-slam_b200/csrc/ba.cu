@@ -50,14 +50,15 @@ struct hslam_ba {
   // points
   DevBuf<float4> d_uvid, d_color, d_weights, d_Hcd[2];
   DevBuf<float> d_priorF, d_deltaF, d_HdiF, d_bdSumF, d_idh, d_Hdd[2], d_bd[2], d_step;
-  DevBuf<int> d_phost, d_res_begin, d_res_index, d_slot;
+  DevBuf<int> d_phost, d_res_begin, d_res_index, d_slotpos;
+  int pstr = 12;                         // floats per point in the record arrays (sc_pstr(maxres))
   std::vector<int> p_sorted2orig, p_orig2sorted;
   std::vector<float4> h_uvid;
   // residuals
   DevBuf<int> d_rpoint, d_rpair;
   DevBuf<int8_t> d_state, d_newState;
   DevBuf<uint8_t> d_isLin, d_isActive;
-  DevBuf<float> d_senergy, d_newEnergy, d_newEnergyWO, d_J, d_JpJdF, d_rtz, d_cpt, d_pto, d_ptc[2];
+  DevBuf<float> d_senergy, d_newEnergy, d_newEnergyWO, d_J, d_JpJdF, d_rtz, d_cpt, d_pto, d_prec;
   std::vector<int> r_sorted2orig, r_orig2sorted;
   // host mirrors of the sorted residual order (for re-grouping when residuals become linearised)
   std::vector<int> h_rpair, h_rpoint, h_rb, h_ri;   // per sorted residual: pair, sorted point; CSR of sorted points over sorted residual positions
@@ -232,11 +233,11 @@ static void fill_desc(hslam_ba* ba) {
   r.state_state = ba->d_state.p; r.newState = ba->d_newState.p; r.isLin = ba->d_isLin.p; r.isActive = ba->d_isActive.p;
   r.state_energy = ba->d_senergy.p; r.newEnergy = ba->d_newEnergy.p; r.newEnergyWO = ba->d_newEnergyWO.p;
   r.J = ba->d_J.p; r.JpJdF = ba->d_JpJdF.p; r.rtz = ba->d_rtz.p; r.cpt = ba->d_cpt.p; r.pto = ba->d_pto.p;
-  r.ptc[0] = r.ptc[1] = ba->d_ptc[0].p;   // a residual is in exactly one of the modes A / L: one array serves both
+  r.prec = ba->d_prec.p; r.slotpos = ba->d_slotpos.p; r.pstr = ba->pstr;
   BAPts& p = D.p;
   p.P = ba->P; p.uvid = ba->d_uvid.p; p.color = ba->d_color.p; p.weights = ba->d_weights.p;
   p.priorF = ba->d_priorF.p; p.deltaF = ba->d_deltaF.p; p.host = ba->d_phost.p;
-  p.res_begin = ba->d_res_begin.p; p.res_index = ba->d_res_index.p; p.slot = ba->d_slot.p;
+  p.res_begin = ba->d_res_begin.p; p.res_index = ba->d_res_index.p;
   p.HdiF = ba->d_HdiF.p; p.bdSumF = ba->d_bdSumF.p; p.idepth_hessian = ba->d_idh.p;
   for (int m = 0; m < 2; ++m) { p.Hdd[m] = ba->d_Hdd[m].p; p.bd[m] = ba->d_bd[m].p; p.Hcd[m] = ba->d_Hcd[m].p; }
   p.step = ba->d_step.p;
@@ -312,7 +313,7 @@ static int build_chunks(hslam_ba* ba) {
         for (int t = b * per; t < e; ++t) {
           if (t == b * per || ht[t].pair != ht[t - 1].pair) ch.push_back(TopChunk{ht[t].pair, ht[t].start, 0, m});
           ch.back().count += ht[t].count;
-          tiles.push_back(TopTile{ht[t].start, ht[t].count, (int)ch.size() - 1, 0});
+          tiles.push_back(TopTile{ht[t].start, ht[t].count, (int)ch.size() - 1, ht[t].pair});
         }
       }
       bb.push_back(NT);
@@ -331,7 +332,7 @@ static int build_chunks(hslam_ba* ba) {
     TRY(upload(ba, ba->d_topchunks.p, ch.data(), ch.size())); TRY(upload(ba, ba->d_pair_chunk_begin.p, pcb.data(), pcb.size()));
     TRY(upload(ba, ba->d_toptiles.p, tiles.data(), tiles.size())); TRY(upload(ba, ba->d_top_block_begin.p, bb.data(), bb.size()));
     // pairs without any chunk in a schedule are never folded: their accumulators must read as zero
-    HS_CUDA(cudaMemsetAsync(ba->d_accTop.p, 0, 3 * (size_t)nn * TOP_PART * sizeof(double), ctx->stream));
+    HS_CUDA(cudaMemsetAsync(ba->d_accTop.p, 0, 3 * (size_t)nn * TOP_DENSE * sizeof(double), ctx->stream));
     // lineariser: tiles of <= LIN_THREADS non-linearised residuals of one pair
     std::vector<LinTile> lt;
     for (int k = 0; k < nn; ++k)
@@ -390,17 +391,14 @@ static int build_chunks(hslam_ba* ba) {
   return 0;
 }
 
-// Slot table of the Schur kernel from the host mirrors: sorted residual position and target of every (point, slot).
-static int upload_slots(hslam_ba* ba) {
-  const int P = ba->P, n = ba->n;
-  std::vector<int> slot((size_t)P * ba->maxres + 1, -1);
-  for (int sp = 0; sp < P; ++sp)
-    for (int i = ba->h_rb[sp], j = 0; i < ba->h_rb[sp + 1]; ++i, ++j) {
-      const int pos = ba->h_ri[i];
-      slot[(size_t)sp * ba->maxres + j] = pos | ((ba->h_rpair[pos] / n) << 26);
-    }
-  TRY(ba->d_slot.ensure(slot.size()));
-  return upload(ba, ba->d_slot.p, slot.data(), slot.size());
+// slotpos of every sorted residual: the float offset of its 32-byte records in the point-major record arrays
+// (BARes::JpJdF / prec), from the host mirrors of the points' residual lists.
+static int upload_slotpos(hslam_ba* ba) {
+  const int P = ba->P, R = ba->R;
+  std::vector<int> sp((size_t)R + 1, 0);
+  for (int p = 0; p < P; ++p)
+    for (int i = ba->h_rb[p], j = 0; i < ba->h_rb[p + 1]; ++i, ++j) sp[ba->h_ri[i]] = p * ba->pstr + 8 * j;
+  return upload(ba, ba->d_slotpos.p, sp.data(), (size_t)R);
 }
 
 // Residuals have changed their isLinearized flag (hslam_ba_fix_linearization): restore the sorted order's invariant —
@@ -452,16 +450,14 @@ static int regroup(hslam_ba* ba) {
       return 0;
     };
     TRY(permF(ba->d_J.p, JS)); TRY(permF(ba->d_rtz.p, 8)); TRY(permF(ba->d_cpt.p, 3)); TRY(permF(ba->d_pto.p, 16));
-    TRY(permF(ba->d_ptc[0].p, 6)); TRY(permF(ba->d_senergy.p, 1)); TRY(permF(ba->d_newEnergy.p, 1)); TRY(permF(ba->d_newEnergyWO.p, 1));
+    TRY(permF(ba->d_senergy.p, 1)); TRY(permF(ba->d_newEnergy.p, 1)); TRY(permF(ba->d_newEnergyWO.p, 1));
     TRY(permB(ba->d_state.p)); TRY(permB(ba->d_newState.p)); TRY(permB(ba->d_isLin.p)); TRY(permB(ba->d_isActive.p));
-    HS_LAUNCH(ctx, HSLAM_K_BA_EXPORT, (ba_permute_rec32_kernel<<<gx, 256, 0, ctx->stream>>>(
-                                          (const float4*)ba->d_JpJdF.p, (float4*)ba->d_permF.p, R, ba->d_perm.p)));
-    HS_CUDA(cudaMemcpyAsync(ba->d_JpJdF.p, ba->d_permF.p, (size_t)R * 8 * sizeof(float), cudaMemcpyDeviceToDevice, ctx->stream));
+    // (the JpJdF / point-term records are indexed by (point, slot): they do not move)
     HS_CUDA(cudaGetLastError());
     TRY(upload(ba, ba->d_rpoint.p, ba->h_rpoint.data(), R)); TRY(upload(ba, ba->d_rpair.p, ba->h_rpair.data(), R));
     TRY(upload(ba, ba->d_r_s2o.p, ba->r_sorted2orig.data(), R));
     TRY(upload(ba, ba->d_res_index.p, ba->h_ri.data(), R));
-    TRY(upload_slots(ba));
+    TRY(upload_slotpos(ba));
   }
   TRY(build_chunks(ba));
   fill_desc(ba);
@@ -494,9 +490,10 @@ int hslam_ba_destroy(hslam_ba* ba) {
   ba->d_fprior.release(); ba->d_fdprior.release();
   ba->d_uvid.release(); ba->d_color.release(); ba->d_weights.release();
   ba->d_priorF.release(); ba->d_deltaF.release(); ba->d_HdiF.release(); ba->d_bdSumF.release(); ba->d_idh.release();
-  for (int m = 0; m < 2; ++m) { ba->d_Hdd[m].release(); ba->d_bd[m].release(); ba->d_Hcd[m].release(); ba->d_ptc[m].release(); }
+  for (int m = 0; m < 2; ++m) { ba->d_Hdd[m].release(); ba->d_bd[m].release(); ba->d_Hcd[m].release(); }
+  ba->d_prec.release(); ba->d_slotpos.release();
   ba->d_accTop.release();
-  ba->d_step.release(); ba->d_phost.release(); ba->d_res_begin.release(); ba->d_res_index.release(); ba->d_slot.release();
+  ba->d_step.release(); ba->d_phost.release(); ba->d_res_begin.release(); ba->d_res_index.release();
   ba->d_rpoint.release(); ba->d_rpair.release(); ba->d_state.release(); ba->d_newState.release();
   ba->d_isLin.release(); ba->d_isActive.release(); ba->d_senergy.release(); ba->d_newEnergy.release();
   ba->d_newEnergyWO.release(); ba->d_J.release(); ba->d_JpJdF.release(); ba->d_rtz.release(); ba->d_cpt.release();
@@ -590,9 +587,9 @@ int hslam_ba_set_window(hslam_ba* ba, const hslam_window* w) {
   TRY(upload(ba, ba->d_adHTd.p, w->adHTdeltaF, nn * 8));
   TRY(ba->d_x.ensure(ba->N)); TRY(ba->d_xc.ensure(4)); TRY(ba->d_xAd.ensure(nn * 8));
   TRY(ba->d_Hb.ensure(3 * ((size_t)ba->N * ba->N + ba->N)));
-  if (ba->d_accTop.cap < 3 * nn * TOP_PART) {
-    TRY(ba->d_accTop.ensure(3 * nn * TOP_PART));
-    HS_CUDA(cudaMemsetAsync(ba->d_accTop.p, 0, 3 * nn * TOP_PART * sizeof(double), ctx->stream));
+  if (ba->d_accTop.cap < 3 * nn * TOP_DENSE) {
+    TRY(ba->d_accTop.ensure(3 * nn * TOP_DENSE));
+    HS_CUDA(cudaMemsetAsync(ba->d_accTop.p, 0, 3 * nn * TOP_DENSE * sizeof(double), ctx->stream));
   }
   if (ba->d_G.cap < (size_t)n * ba->LD * ba->LD) {
     TRY(ba->d_G.ensure((size_t)n * ba->LD * ba->LD));
@@ -672,10 +669,12 @@ int hslam_ba_set_topology(hslam_ba* ba, const hslam_point_soa* pt, const hslam_r
   TRY(ba->d_res_begin.ensure(P + 2)); TRY(ba->d_res_index.ensure(R + 1));
   TRY(ba->d_HdiF.ensure(P + 1)); TRY(ba->d_bdSumF.ensure(P + 1)); TRY(ba->d_idh.ensure(P + 1)); TRY(ba->d_step.ensure(P + 1));
   for (int m = 0; m < 2; ++m) { TRY(ba->d_Hdd[m].ensure(P + 1)); TRY(ba->d_bd[m].ensure(P + 1)); TRY(ba->d_Hcd[m].ensure(P + 1)); }
-  TRY(ba->d_ptc[0].ensure(6 * rsz));
+  ba->pstr = sc_pstr(ba->maxres);
+  const size_t recsz = (size_t)(P + 1) * ba->pstr;
+  TRY(ba->d_prec.ensure(recsz)); TRY(ba->d_slotpos.ensure(rsz + TOP_ROW)); /* + slack: the top kernel stages whole rows */
   TRY(ba->d_rpoint.ensure(rsz)); TRY(ba->d_rpair.ensure(rsz)); TRY(ba->d_state.ensure(rsz)); TRY(ba->d_newState.ensure(rsz));
   TRY(ba->d_isLin.ensure(rsz + 256)); TRY(ba->d_isActive.ensure(rsz + 256)); /* + slack: the top kernel copies whole 160-byte flag rows */ TRY(ba->d_senergy.ensure(rsz)); TRY(ba->d_newEnergy.ensure(rsz));
-  TRY(ba->d_newEnergyWO.ensure(rsz)); TRY(ba->d_J.ensure((size_t)JS * rsz + 2 * TOP_ROW)); /* + slack: the top kernel stages whole rows */ TRY(ba->d_JpJdF.ensure(8 * rsz));
+  TRY(ba->d_newEnergyWO.ensure(rsz)); TRY(ba->d_J.ensure((size_t)JS * rsz + 2 * TOP_ROW)); /* + slack: the top kernel stages whole rows */ TRY(ba->d_JpJdF.ensure(recsz));
   TRY(ba->d_rtz.ensure(8 * rsz)); TRY(ba->d_cpt.ensure(3 * rsz)); TRY(ba->d_pto.ensure(16 * rsz));
   // ---- pack + upload points
   {
@@ -720,17 +719,18 @@ int hslam_ba_set_topology(hslam_ba* ba, const hslam_point_soa* pt, const hslam_r
     TRY(upload(ba, ba->d_rpoint.p, rp.data(), R)); TRY(upload(ba, ba->d_rpair.p, rpair.data(), R));
     TRY(upload(ba, ba->d_state.p, st.data(), R)); TRY(upload(ba, ba->d_isLin.p, lin.data(), R));
     TRY(upload(ba, ba->d_isActive.p, act.data(), R)); TRY(upload(ba, ba->d_senergy.p, se.data(), R));
-    TRY(upload_slots(ba));   // needs the pair mirror
   }
   HS_CUDA(cudaMemsetAsync(ba->d_J.p, 0, (size_t)JS * rsz * sizeof(float), ctx->stream));
-  HS_CUDA(cudaMemsetAsync(ba->d_JpJdF.p, 0, 8 * rsz * sizeof(float), ctx->stream));
+  HS_CUDA(cudaMemsetAsync(ba->d_JpJdF.p, 0, recsz * sizeof(float), ctx->stream));
+  HS_CUDA(cudaMemsetAsync(ba->d_slotpos.p, 0, (rsz + TOP_ROW) * sizeof(int), ctx->stream));
+  TRY(upload_slotpos(ba));
   HS_CUDA(cudaMemsetAsync(ba->d_rtz.p, 0, 8 * rsz * sizeof(float), ctx->stream));
   HS_CUDA(cudaMemsetAsync(ba->d_cpt.p, 0, 3 * rsz * sizeof(float), ctx->stream));
   HS_CUDA(cudaMemsetAsync(ba->d_pto.p, 0, 16 * rsz * sizeof(float), ctx->stream));
   HS_CUDA(cudaMemsetAsync(ba->d_newState.p, HSLAM_RES_OUT, rsz, ctx->stream));
   HS_CUDA(cudaMemsetAsync(ba->d_newEnergy.p, 0, rsz * sizeof(float), ctx->stream));
   HS_CUDA(cudaMemsetAsync(ba->d_newEnergyWO.p, 0, rsz * sizeof(float), ctx->stream));
-  HS_CUDA(cudaMemsetAsync(ba->d_ptc[0].p, 0, 6 * rsz * sizeof(float), ctx->stream));
+  HS_CUDA(cudaMemsetAsync(ba->d_prec.p, 0, recsz * sizeof(float), ctx->stream));   // flag 0: no active residual in any slot yet
   for (int m = 0; m < 2; ++m) {
     HS_CUDA(cudaMemsetAsync(ba->d_Hdd[m].p, 0, (P + 1) * sizeof(float), ctx->stream));
     HS_CUDA(cudaMemsetAsync(ba->d_bd[m].p, 0, (P + 1) * sizeof(float), ctx->stream));
@@ -818,46 +818,35 @@ static int launch_top(hslam_ba* ba, int modes) {
   return 0;
 }
 
-#ifndef SC_TILE8
-#define SC_TILE8 0   /* measured (64 x cfg2 windows): 8x8 tiles 409 us vs 4x4 tiles 370 us — at 128 registers only two blocks per SM stay resident and the staging phases, not the Gram loop, set the pace */
-#endif
-// 0: the 8x8-tile variant (LD <= 64, i.e. n <= 7: at most 28 tiles, one per lane); else 4x4 tiles per thread
+// tiles per thread of the Schur kernel: (NT-2)(NT-1)/2 4x4 tiles over 128 thread pairs
 static int schur_maxt(int LD) {
-  if (SC_TILE8 && LD <= 64) return 0;
   int NTR = LD / 4 - 2, t = NTR * (NTR + 1) / 2;
   return t <= 128 ? 1 : (t <= 256 ? 2 : 5);
 }
-static int schur_ni(int maxres) { return SC_PTS * maxres <= 2 * SC_THREADS ? 2 : 4; }
-// the 8x8-tile variant reduces its eight warps through 4 x 2048 floats of the (then free) staging memory
+// rows + staged records; the final exchange of the two point halves needs MAXT * 128 * 16 floats
 static size_t schur_smem(int LD, int maxres) {
-  size_t fl = sc_smem_floats(LD, maxres);
-  if (schur_maxt(LD) == 0) fl = std::max(fl, (size_t)4 * 2048);
+  size_t fl = std::max(sc_smem_floats(LD, maxres), (size_t)schur_maxt(LD) * 128 * 16 + 4);
   return fl * sizeof(float);
 }
-template <class F> static int schur_dispatch(int maxt, int ni, F f) {
-  if (maxt == 0 && ni == 2) return f(ba_schur_kernel<0, 2>);
-  if (maxt == 0) return f(ba_schur_kernel<0, 4>);
-  if (maxt == 1 && ni == 2) return f(ba_schur_kernel<1, 2>);
-  if (maxt == 1) return f(ba_schur_kernel<1, 4>);
-  if (maxt == 2 && ni == 2) return f(ba_schur_kernel<2, 2>);
-  if (maxt == 2) return f(ba_schur_kernel<2, 4>);
-  return f(ba_schur_kernel<5, 4>);
+template <class F> static int schur_dispatch(int maxt, F f) {
+  if (maxt == 1) return f(ba_schur_kernel<1>);
+  if (maxt == 2) return f(ba_schur_kernel<2>);
+  return f(ba_schur_kernel<5>);
 }
 static int schur_attr(hslam_ctx* ctx, size_t smem) {
   size_t& configured = ctx->schur_smem_configured;
   if (smem > configured) {
-    for (int maxt : {0, 1, 2, 5})
-      for (int ni : {2, 4})
-        TRY(schur_dispatch(maxt, ni, [&](auto k) -> int {
-          HS_CUDA(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-          return 0;
-        }));
+    for (int maxt : {1, 2, 5})
+      TRY(schur_dispatch(maxt, [&](auto k) -> int {
+        HS_CUDA(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        return 0;
+      }));
     configured = smem;
   }
   return 0;
 }
-static void schur_launch(int maxt, int ni, int blocks, size_t smem, cudaStream_t st, const BADesc* d, const int* pf, int n) {
-  schur_dispatch(maxt, ni, [&](auto k) -> int { k<<<blocks, SC_THREADS, smem, st>>>(d, pf, n); return 0; });
+static void schur_launch(int maxt, int blocks, size_t smem, cudaStream_t st, const BADesc* d, const int* pf, int n) {
+  schur_dispatch(maxt, [&](auto k) -> int { k<<<blocks, SC_THREADS, smem, st>>>(d, pf, n); return 0; });
 }
 
 static int launch_schur(hslam_ba* ba) {
@@ -866,7 +855,7 @@ static int launch_schur(hslam_ba* ba) {
   size_t smem = schur_smem(ba->LD, ba->maxres);
   TRY(schur_attr(ctx, smem));
   if (ba->n_ptchunks > 0)
-    HS_LAUNCH(ctx, HSLAM_K_BA_SCHUR, schur_launch(schur_maxt(ba->LD), schur_ni(ba->maxres), ba->n_ptchunks, smem, ctx->stream, ba->d_desc.p, nullptr, 1));
+    HS_LAUNCH(ctx, HSLAM_K_BA_SCHUR, schur_launch(schur_maxt(ba->LD), ba->n_ptchunks, smem, ctx->stream, ba->d_desc.p, nullptr, 1));
   HS_LAUNCH(ctx, HSLAM_K_BA_FOLD_SC, (ba_fold_sc_kernel<<<ba->n * ((ba->LD * ba->LD + 255) / 256), 256, 0, ctx->stream>>>(ba->d_desc.p, nullptr, 1)));
   HS_CUDA(cudaGetLastError());
   return 0;
@@ -886,7 +875,7 @@ static int launch_point_sum(hslam_ba* ba, int modes) {
   int pblocks = (ba->P + 127) / 128;
   if (pblocks > 0)
     HS_LAUNCH(ctx, HSLAM_K_BA_POINT_SUM,
-              (ba_point_sum_kernel<<<pblocks, 128, 0, ctx->stream>>>(ba->hdesc.r, ba->hdesc.p, modes & 1, (modes >> 1) & 1)));
+              (ba_point_sum_kernel<<<pblocks, 128, 0, ctx->stream>>>(ba->hdesc.r, ba->hdesc.p, modes & 1, (modes >> 1) & 1, ba->maxres)));
   HS_CUDA(cudaGetLastError());
   return 0;
 }
@@ -1091,8 +1080,8 @@ int hslam_ba_residual_results(hslam_ba* ba, int8_t* state_state, uint8_t* is_act
   if (JpJdF && ba->R > 0) {   // [R][8] records in sorted order -> caller order
     void* tmp;
     TRY(scratch_alloc(ba, (size_t)ba->R * 8 * sizeof(float), &tmp));
-    HS_LAUNCH(ba->ctx, HSLAM_K_BA_EXPORT, (ba_export_aos_kernel<float><<<(ba->R + 255) / 256, 256, 0, ba->ctx->stream>>>(
-                                              ba->d_JpJdF.p, 8, ba->R, ba->d_r_s2o.p, (float*)tmp)));
+    HS_LAUNCH(ba->ctx, HSLAM_K_BA_EXPORT, (ba_export_jpjd_kernel<<<(ba->R + 255) / 256, 256, 0, ba->ctx->stream>>>(
+                                              ba->hdesc.r, ba->d_r_s2o.p, (float*)tmp)));
     TRY(download(ba, JpJdF, (const float*)tmp, (size_t)ba->R * 8));
   }
   TRY(download_res(ba, ba->d_rtz.p, 8, res_toZeroF));
@@ -1274,7 +1263,6 @@ static int batch_refresh(hslam_ba_batch* B) {
     pf[5][i + 1] = pf[5][i] + (ba->P + 127) / 128;
     B->smem = std::max(B->smem, schur_smem(ba->LD, ba->maxres));
     B->maxt = std::max(B->maxt, schur_maxt(ba->LD));
-    B->ni = std::max(B->ni, schur_ni(ba->maxres));
   }
   // launch parameters of the captured graphs: a change of descriptor CONTENT alone (new thresholds, new camera scalars)
   // does not invalidate them
@@ -1374,7 +1362,7 @@ static int batch_enqueue_accumulate(hslam_ba_batch* B) {
   if (B->any_L && B->blocks[6] > 0)
     HS_LAUNCH(ctx, HSLAM_K_BA_TOP, (ba_top_kernel<1><<<B->blocks[6], 2 * TOP_THREADS, kTopSmem, ctx->stream>>>(B->d_descs.p, pf + 6 * (n + 1), B->uniform[6] ? -B->uniform[6] : n)));
   if (B->blocks[2] > 0)
-    HS_LAUNCH(ctx, HSLAM_K_BA_SCHUR, schur_launch(B->maxt, B->ni, B->blocks[2], B->smem, ctx->stream, B->d_descs.p, pf + 2 * (n + 1), B->uniform[2] ? -B->uniform[2] : n));
+    HS_LAUNCH(ctx, HSLAM_K_BA_SCHUR, schur_launch(B->maxt, B->blocks[2], B->smem, ctx->stream, B->d_descs.p, pf + 2 * (n + 1), B->uniform[2] ? -B->uniform[2] : n));
   HS_LAUNCH(ctx, HSLAM_K_BA_FOLD_SC, (ba_fold_sc_kernel<<<B->blocks[4], 256, 0, ctx->stream>>>(B->d_descs.p, pf + 4 * (n + 1), B->uniform[4] ? -B->uniform[4] : n)));
   HS_LAUNCH(ctx, HSLAM_K_BA_STITCH, (ba_stitch_kernel<<<B->blocks[3], ST_THREADS, 0, ctx->stream>>>(B->d_descs.p, pf + 3 * (n + 1), B->uniform[3] ? -B->uniform[3] : n, 0, 3, 1)));
   HS_CUDA(cudaGetLastError());

@@ -50,7 +50,8 @@ constexpr int LIN_THREADS = LIN_THREADS_;
 #define STJ(ptr, v) (*(ptr) = (v))
 #endif
 constexpr int TOP_THREADS = 128;
-constexpr int TOP_PART = 96;           // 91 accumulators + nres + pad
+constexpr int TOP_PART = 96;           // 91 accumulators + nres + pad (fp32 chunk partials)
+constexpr int TOP_DENSE = 176;         // folded fp64 accumulator of a pair: dense symmetric 13x13 (169) + nres at [169] + pad
 constexpr int SC_THREADS = 256;
 #ifndef SC_PTS_
 #define SC_PTS_ 64
@@ -87,11 +88,15 @@ struct BARes {               // per-residual SoA, sorted by (host,target) pair, 
   float* newEnergy;
   float* newEnergyWO;
   float* J;                  // [JS][rs]
-  float* JpJdF;              // [rs][8]: one 32-byte record per residual (read whole by the Schur staging and the back-substitution)
+  const int* slotpos;        // float offset of the residual's 32-byte records in JpJdF / prec: point * pstr + 8 * slot
+  int pstr;                  // floats per point in the record arrays: 8 * maxres + 4 (the pad keeps shared-memory reads conflict-free)
+  float* JpJdF;              // [P][pstr]: one 32-byte record per (point, residual slot), in the point's own order: the Schur
+                             // kernel and the back-substitution read a point's residuals as ONE contiguous span
+  float* prec;               // [P][pstr]: per (point, slot) {bd, Hdd, Hcd[4], flag (0 inactive / 1 active A / 2 active L), target}:
+                             // the residual's contribution to the point sums (AccumulatedTopHessian.cpp:114-117), written by addPoint<mode>
   float* rtz;                // [8][rs] res_toZeroF
   float* cpt;                // [3][rs] centerProjectedTo
   float* pto;                // [16][rs] projectedTo
-  float* ptc[2];             // [6][rs] per-residual contribution to (bd,Hdd,Hcd[4]) for mode A / L
 };
 
 struct BAPts {               // per-point SoA, sorted by host
@@ -104,14 +109,13 @@ struct BAPts {               // per-point SoA, sorted by host
   const int* host;
   const int* res_begin;      // CSR over sorted residual positions, in the point's own order
   const int* res_index;
-  const int* slot;           // [P][maxres]: (sorted residual position | target << 26) of the point's slot-th residual, -1 if none
   float* HdiF; float* bdSumF; float* idepth_hessian;
   float* Hdd[2]; float* bd[2]; float4* Hcd[2];
   float* step;
 };
 
 struct TopChunk { int pair, start, count, mode; };   // mode = schedule index: 0 = A, 1 = L, 2 = marginalisation
-struct TopTile { int start, count, chunk, pad; };   // <= 128 residuals of one pair; chunk = partial it is reduced into (global index)
+struct TopTile { int start, count, chunk, pair; };  // <= 128 residuals of one pair; chunk = partial it is reduced into (global index)
 struct TopSched { const TopTile* tiles; const int* block_begin; int blocks, pad; };   // tile schedule of one mode (see ba_top_kernel)
 struct LinTile { int start, count, pair, pad; };    // <= LIN_THREADS non-linearised residuals of one (host,target) pair
 struct PtChunk { int host, start, count, pad; };
@@ -204,7 +208,7 @@ __device__ __forceinline__ void take_data(const BARes& r, int k) {  // Optimizat
   for (int i = 0; i < 6; ++i) o[i] = xadd(xmul(J[(J_XI0 + i) * s], JJ0), xmul(J[(J_XI1 + i) * s], JJ1));
   o[6] = xadd(xmul(J[(J_ABIDX + 0) * s], d0), xmul(J[(J_ABIDX + 2) * s], d1));
   o[7] = xadd(xmul(J[(J_ABIDX + 1) * s], d0), xmul(J[(J_ABIDX + 3) * s], d1));
-  float4* dst = reinterpret_cast<float4*>(r.JpJdF + 8 * (size_t)k);
+  float4* dst = reinterpret_cast<float4*>(r.JpJdF + r.slotpos[k]);
   dst[0] = make_float4(o[0], o[1], o[2], o[3]); dst[1] = make_float4(o[4], o[5], o[6], o[7]);
 }
 
@@ -255,6 +259,7 @@ __global__ void __launch_bounds__(LIN_THREADS, LIN_MINB) ba_linearize_kernel(con
   const int8_t st0 = valid ? r.state_state[k] : (int8_t)HSLAM_RES_OOB;
   const float old_energy = valid ? r.state_energy[k] : 0.f;
   const int p = valid ? r.point[k] : 0;
+  const int sp = (APPLY && valid && !refresh) ? r.slotpos[k] : 0;
   if (valid) {
     float* J = r.J + k;
     if (!refresh) STJ(r.newEnergyWO + k, -1.f);
@@ -447,7 +452,7 @@ __global__ void __launch_bounds__(LIN_THREADS, LIN_MINB) ba_linearize_kernel(con
                 for (int i = 0; i < 6; ++i) o[i] = xadd(xmul(HS_XI0(i), JJ0), xmul(HS_XI1(i), JJ1));
                 o[6] = xadd(xmul(AI00, ddx), xmul(AI01, ddy));
                 o[7] = xadd(xmul(AI10, ddx), xmul(AI11, ddy));
-                float4* dst = reinterpret_cast<float4*>(r.JpJdF + 8 * (size_t)k);   // one 32-byte record
+                float4* dst = reinterpret_cast<float4*>(r.JpJdF + sp);   // one 32-byte record, in the point's slot
                 dst[0] = make_float4(o[0], o[1], o[2], o[3]); dst[1] = make_float4(o[4], o[5], o[6], o[7]);
               } else {
                 r.isActive[k] = 0;
@@ -722,16 +727,21 @@ __device__ __forceinline__ void top_accumulate(const BADesc& D, const TopChunk& 
         acc[3 * rI + 2] += fmaf(x[rI], JIr0, y[rI] * JIr1);
       }
       acc[30] += AA00; acc[31] += AA01; acc[32] += Jabr0; acc[33] += AA11; acc[34] += Jabr1; acc[35] += rr;
-      if (!use) continue;
+      const float tgt = (float)((ch.pair * W.n_rcp) >> 16);
+      float4* o = reinterpret_cast<float4*>(r.prec + r.slotpos[k]);   // the residual's 32-byte record in its point's slot
+      if (!use) {
+        // modes A / L own every residual of their tiles: an inactive one gets a record that says so.  The
+        // marginalisation pass (2) leaves the records of the points it does not touch alone.
+        if (MODE != 2) { o[0] = make_float4(0.f, 0.f, 0.f, 0.f); o[1] = make_float4(0.f, 0.f, 0.f, tgt); }
+        continue;
+      }
       nres++;
       // per-residual contribution to the point sums (:114-117), exact ops: they are summed per point in
       // the point's own order by the Schur kernel, which keeps Hdd/bd/Hcd bit-identical to the oracle.
       float Ji0 = xadd(xmul(a, d0), xmul(b, d1)), Ji1 = xadd(xmul(b, d0), xmul(c, d1));
-      float* o = r.ptc[0] + k;
-      o[0] = xadd(xmul(JIr0, d0), xmul(JIr1, d1));
-      o[s] = xadd(xmul(Ji0, d0), xmul(Ji1, d1));
-#pragma unroll
-      for (int j = 0; j < 4; ++j) o[(2 + j) * s] = xadd(xmul(x[j], Ji0), xmul(y[j], Ji1));
+      o[0] = make_float4(xadd(xmul(JIr0, d0), xmul(JIr1, d1)), xadd(xmul(Ji0, d0), xmul(Ji1, d1)),
+                         xadd(xmul(x[0], Ji0), xmul(y[0], Ji1)), xadd(xmul(x[1], Ji0), xmul(y[1], Ji1)));
+      o[1] = make_float4(xadd(xmul(x[2], Ji0), xmul(y[2], Ji1)), xadd(xmul(x[3], Ji0), xmul(y[3], Ji1)), lin ? 2.f : 1.f, tgt);
     }
   }
 }
@@ -808,9 +818,17 @@ constexpr int TOP_FROW = 160;   // flag rows: the 16-byte-aligned span that cove
 struct alignas(128) TopStage {
   float v[TOP_NR][TOP_ROW];
   unsigned char lin[TOP_FROW], act[TOP_FROW];
+  int sp[TOP_ROW];           // slotpos of the tile's residuals (same 4-aligned span as the Jacobian rows)
 };
 static_assert(sizeof(TopStage) % 128 == 0 && (24 * TOP_ROW * 4) % 128 == 0, "TMA box destinations are 128-byte aligned");
 
+// packed index of the 91 accumulators -> (row, col), row <= col, of the 13x13 block [C(4); xi(6); a, b; r]:
+// 0..54 the row-major upper triangle of the 10x10, 55..84 the 10x3 top-right, 85..90 the upper triangle of the 3x3
+__device__ __forceinline__ void top_unpack_index(int t, int& r, int& c) {
+  if (t < 55) { r = 0; while (t >= 10 - r) { t -= 10 - r; ++r; } c = r + t; }
+  else if (t < 85) { r = (t - 55) / 3; c = 10 + (t - 55) % 3; }
+  else { const int m[6][2] = {{10, 10}, {10, 11}, {10, 12}, {11, 11}, {11, 12}, {12, 12}}; r = m[t - 85][0]; c = m[t - 85][1]; }
+}
 // chunk partial -> global, then the per-(mode,pair) fold by the last block of that pair (chunks in index order)
 __device__ __forceinline__ void top_flush(const BADesc& D, int chunk, int part, float (&acc)[56], int nres,
                                           float (*red)[33], bool* last) {
@@ -860,15 +878,18 @@ __device__ __forceinline__ void top_flush(const BADesc& D, int chunk, int part, 
     __threadfence();
     if (threadIdx.x < 92) {
       int t = threadIdx.x;
-      double* dst = D.accTop + (size_t)slot * TOP_PART;
+      // the folded accumulator is stored as a DENSE symmetric 13x13 (what the stitch reads with plain indexing)
+      double* dst = D.accTop + (size_t)slot * TOP_DENSE;
       if (t == 91) {
         int n = 0;
         for (int c = cb; c < ce; ++c) n += __float_as_int(__ldcg(D.toppartial + (size_t)c * TOP_PART + 91));
-        dst[91] = (double)n;
+        dst[169] = (double)n;
       } else {
         double sum = 0.0;
         for (int c = cb; c < ce; ++c) sum += (double)__ldcg(D.toppartial + (size_t)c * TOP_PART + t);
-        dst[t] = sum;
+        int rr, cc;
+        top_unpack_index(t, rr, cc);
+        dst[rr * 13 + cc] = sum; dst[cc * 13 + rr] = sum;
       }
     }
     if (threadIdx.x == 0) D.pair_ticket[slot] = 0;
@@ -902,10 +923,6 @@ __global__ void __launch_bounds__(2 * TOP_THREADS, 2) ba_top_kernel(const BADesc
   for (int i = 0; i < 56; ++i) acc[i] = 0.f;
   int nres = 0, cur = -1;
 
-#ifndef TOP_BULK
-#define TOP_BULK 2   /* 0: cp.async ring, 1: one bulk copy per component row, 2: two tensor-map loads per stage */
-#endif
-#if TOP_BULK
   // Mode A: the 39 component rows of a tile are 39 contiguous 544-byte spans of the SoA Jacobian: one bulk copy
   // (TMA engine) each, completing on the stage's `full` mbarrier.  The warps take turns as producer (warp j & 7
   // issues tile j + TOP_DEPTH, lanes in parallel), every warp releases a stage on its `empty` mbarrier when it has
@@ -931,23 +948,18 @@ __global__ void __launch_bounds__(2 * TOP_THREADS, 2) ba_top_kernel(const BADesc
     if (tp >= t1) return;
     const int stg = jp % TOP_STAGES, use = jp / TOP_STAGES;
     if (use > 0) mbar_wait(&empty_bar[stg], (unsigned)(use - 1) & 1u);
-    if (lane == 0) mbar_expect_tx(&full_bar[stg], TOP_NC * TOP_ROW * 4 + 2 * TOP_FROW);
+    if (lane == 0) mbar_expect_tx(&full_bar[stg], TOP_NC * TOP_ROW * 4 + 2 * TOP_FROW + TOP_ROW * 4);
     __syncwarp();
     const TopTile tlp = toptiles[tp];
     TopStage& st = ring[stg];
     // the two flag rows ride along (a consumer that loaded them itself had a DRAM round trip on its critical path)
     if (lane == 2) bulk_g2s(st.lin, r.isLin + (tlp.start & ~15), TOP_FROW, &full_bar[stg]);
     else if (lane == 3) bulk_g2s(st.act, r.isActive + (tlp.start & ~15), TOP_FROW, &full_bar[stg]);
-#if TOP_BULK == 2
+    else if (lane == 4) bulk_g2s(st.sp, r.slotpos + (tlp.start & ~3), TOP_ROW * 4, &full_bar[stg]);
     // two tensor-map loads per stage: the TMA unit serves one request in ~46 cycles whatever its size, 39 row copies
     // per 21 kB stage made the kernel TMA-issue-bound (3.4 TB/s)
     if (lane == 0) tma_load_2d(&st.v[0][0], &D.tmapJ[0], tlp.start & ~3, J_XI0, &full_bar[stg]);
     else if (lane == 1) tma_load_2d(&st.v[24][0], &D.tmapJ[1], tlp.start & ~3, J_IDX2, &full_bar[stg]);
-#else
-    const float* src = r.J + (tlp.start & ~3);
-    for (int c = lane >= 4 ? lane - 4 : lane + 28; c < TOP_NC; c += 32)
-      bulk_g2s(&st.v[top_row(c)][0], src + (size_t)top_comp(c) * s, TOP_ROW * 4, &full_bar[stg]);
-#endif
   };
   if (mode == 0 && warp == 0) {
 #pragma unroll
@@ -980,56 +992,6 @@ __global__ void __launch_bounds__(2 * TOP_THREADS, 2) ba_top_kernel(const BADesc
     const int col = (tl.start & 3) + l, cf = (tl.start & 15) + l;
     // AccumulatedTopHessian.cpp:37-49, mode 0: !isLinearized && isActive
     if (l < tl.count && S.lin[cf] == 0 && S.act[cf] != 0) {
-#else
-  // all 256 threads: 39 rows x 34 sixteen-byte copies (always the full row: constant trip count and constant
-  // divisor; the columns past the tile are never read) + the two flag rows; one commit group per tile
-  constexpr int RQ = TOP_ROW / 4;
-  auto issue = [&](int t) {
-    if (mode == 0 && t < t1) {
-      const TopTile tl = toptiles[t];
-      TopStage& st = ring[(t - t0) % TOP_STAGES];
-      const float* src = r.J + (tl.start & ~3);
-#pragma unroll
-      for (int j = 0; j < (TOP_NC * RQ + 2 * TOP_THREADS - 1) / (2 * TOP_THREADS); ++j) {
-        const int i = threadIdx.x + j * 2 * TOP_THREADS;
-        const int c = i / RQ, q = i - c * RQ;
-        if (i < TOP_NC * RQ) cp_async16(&st.v[top_row(c)][4 * q], src + (size_t)top_comp(c) * s + 4 * q);
-      }
-      const int nq = ((tl.start + tl.count + 3) >> 2) - (tl.start >> 2);   // flag words that cover the tile
-      if (threadIdx.x < nq) cp_async4(&st.lin[4 * threadIdx.x], r.isLin + (tl.start & ~3) + 4 * threadIdx.x);
-      else if (threadIdx.x >= 64 && threadIdx.x < 64 + nq)
-        cp_async4(&st.act[4 * (threadIdx.x - 64)], r.isActive + (tl.start & ~3) + 4 * (threadIdx.x - 64));
-    }
-    cp_async_commit();   // always: keeps the group count in step with the tile count
-  };
-#pragma unroll
-  for (int i = 0; i < TOP_STAGES - 1; ++i) issue(t0 + i);
-
-  for (int t = t0; t < t1; ++t) {
-    const TopTile tl = toptiles[t];
-    issue(t + TOP_STAGES - 1);   // refills the stage that was consumed in the previous iteration
-    const int chunk = tl.chunk;
-    if (chunk != cur) {
-      if (cur >= 0) {
-        top_flush(D, cur, part, acc, nres, red, &last);
-#pragma unroll
-        for (int i = 0; i < 55; ++i) acc[i] = 0.f;
-        nres = 0;
-      }
-      cur = chunk;
-    }
-    if (mode != 0) {
-      const TopChunk ch = {D.topchunks[chunk].pair, tl.start, tl.count, 1};
-      if (part == 0) top_accumulate<(MODE ? MODE : 1), 0>(D, ch, acc, nres); else top_accumulate<(MODE ? MODE : 1), 1>(D, ch, acc, nres);
-      continue;
-    }
-    cp_async_wait<TOP_STAGES - 1>();   // the group of tile t has landed (for this thread's copies)
-    __syncthreads();                   // ... and for everyone's
-    const TopStage& S = ring[(t - t0) % TOP_STAGES];
-    const int col = (tl.start & 3) + l;
-    // AccumulatedTopHessian.cpp:37-49, mode 0: !isLinearized && isActive
-    if (l < tl.count && S.lin[col] == 0 && S.act[col] != 0) {
-#endif
       float x[10], y[10];
 #pragma unroll
       for (int j = 0; j < 4; ++j) { x[j] = S.v[TS_C0 + j][col]; y[j] = S.v[TS_C1 + j][col]; }
@@ -1104,19 +1066,20 @@ __global__ void __launch_bounds__(2 * TOP_THREADS, 2) ba_top_kernel(const BADesc
         // per-residual contribution to the point sums (:114-117), exact ops: they are summed per point in
         // the point's own order by the Schur kernel, which keeps Hdd/bd/Hcd bit-identical to the oracle.
         const float Ji0 = xadd(xmul(a, d0), xmul(b, d1)), Ji1 = xadd(xmul(b, d0), xmul(c, d1));
-        float* o = r.ptc[0] + tl.start + l;
-        o[0] = xadd(xmul(JIr0, d0), xmul(JIr1, d1));
-        o[s] = xadd(xmul(Ji0, d0), xmul(Ji1, d1));
-#pragma unroll
-        for (int j = 0; j < 4; ++j) o[(2 + j) * s] = xadd(xmul(x[j], Ji0), xmul(y[j], Ji1));
+        float4* o = reinterpret_cast<float4*>(r.prec + S.sp[col]);   // the residual's 32-byte record in its point's slot
+        o[0] = make_float4(xadd(xmul(JIr0, d0), xmul(JIr1, d1)), xadd(xmul(Ji0, d0), xmul(Ji1, d1)),
+                           xadd(xmul(x[0], Ji0), xmul(y[0], Ji1)), xadd(xmul(x[1], Ji0), xmul(y[1], Ji1)));
+        o[1] = make_float4(xadd(xmul(x[2], Ji0), xmul(y[2], Ji1)), xadd(xmul(x[3], Ji0), xmul(y[3], Ji1)), 1.f,
+                           (float)((tl.pair * D.W.n_rcp) >> 16));
       }
+    } else if (part == 1 && l < tl.count) {
+      // inactive residual: its record says so (the Schur kernel and the point sums skip it)
+      float4* o = reinterpret_cast<float4*>(r.prec + S.sp[col]);
+      o[0] = make_float4(0.f, 0.f, 0.f, 0.f);
+      o[1] = make_float4(0.f, 0.f, 0.f, (float)((tl.pair * D.W.n_rcp) >> 16));
     }
-#if TOP_BULK
     __syncwarp();
     if (lane == 0) mbar_arrive(&empty_bar[j % TOP_STAGES]);   // this warp is done with the stage
-#else
-    __syncthreads();   // everyone is done with this stage before the next iteration refills it
-#endif
   }
   if (cur >= 0) top_flush(D, cur, part, acc, nres, red, &last);
 }
@@ -1124,21 +1087,20 @@ __global__ void __launch_bounds__(2 * TOP_THREADS, 2) ba_top_kernel(const BADesc
 // Per-point sums of Hdd/bd/Hcd over the point's residuals in the point's own order (the tail of
 // addPoint<mode>, AccumulatedTopHessian.cpp:122-139).  Only used by the stand-alone accumulate(A|L)
 // entry points; the fused path does this inside the Schur kernel.
-__global__ void ba_point_sum_kernel(BARes r, BAPts pts, int do_A, int do_L) {
+__global__ void ba_point_sum_kernel(BARes r, BAPts pts, int do_A, int do_L, int maxres) {
   int p = blockIdx.x * blockDim.x + threadIdx.x;
   if (p >= pts.P) return;
-  const int s = r.rs;
   float bdv[2] = {0.f, 0.f}, Hddv[2] = {0.f, 0.f}, Hcdv[2][4] = {{0.f, 0.f, 0.f, 0.f}, {0.f, 0.f, 0.f, 0.f}};
-  for (int i = pts.res_begin[p]; i < pts.res_begin[p + 1]; ++i) {
-    int k = pts.res_index[i];
-    if (!r.isActive[k]) continue;
-    int m = r.isLin[k] ? 1 : 0;
+  const float4* rec = reinterpret_cast<const float4*>(r.prec + (size_t)p * r.pstr);
+  for (int j = 0; j < maxres; ++j) {
+    const float4 q0 = rec[2 * j], q1 = rec[2 * j + 1];
+    if (q1.z == 0.f) continue;            // no residual in this slot, or inactive
+    const int m = q1.z == 2.f ? 1 : 0;
     if ((m == 0 && !do_A) || (m == 1 && !do_L)) continue;
-    const float* o = r.ptc[m] + k;
-    bdv[m] = xadd(bdv[m], o[0]);
-    Hddv[m] = xadd(Hddv[m], o[s]);
-#pragma unroll
-    for (int j = 0; j < 4; ++j) Hcdv[m][j] = xadd(Hcdv[m][j], o[(2 + j) * s]);
+    bdv[m] = xadd(bdv[m], q0.x);
+    Hddv[m] = xadd(Hddv[m], q0.y);
+    Hcdv[m][0] = xadd(Hcdv[m][0], q0.z); Hcdv[m][1] = xadd(Hcdv[m][1], q0.w);
+    Hcdv[m][2] = xadd(Hcdv[m][2], q1.x); Hcdv[m][3] = xadd(Hcdv[m][3], q1.y);
   }
   if (do_A) { pts.Hdd[0][p] = Hddv[0]; pts.bd[0][p] = bdv[0]; pts.Hcd[0][p] = make_float4(Hcdv[0][0], Hcdv[0][1], Hcdv[0][2], Hcdv[0][3]); }
   if (do_L) { pts.Hdd[1][p] = Hddv[1]; pts.bd[1][p] = bdv[1]; pts.Hcd[1][p] = make_float4(Hcdv[1][0], Hcdv[1][1], Hcdv[1][2], Hcdv[1][3]); }
@@ -1161,34 +1123,32 @@ __device__ __forceinline__ void tri_decode(int t, int NT, int& ti, int& tj) {
   ti = row; tj = row + rem;
 }
 
-// Shared-memory layout (floats): A[SC_PTS][LD+4] | WA[SC_PTS][LD+4] (= HdiF * A) | wv[SC_PTS] | stg[7][SNP],
-// SNP = SC_PTS*(maxres|1) + 5.
-// The row stride LD+4, the odd per-point stride MR = maxres|1 and the component stride SNP keep the access
-// patterns of the kernel (almost) free of bank conflicts:
-//   staging stores  A[lp][8t+j]       lanes differ in (lp,t): (LD+4) % 32 = 4 or 12 rotates the rows;
-//   point sums      stg[c][lp*MR+s]   8 lanes per point differ in c (stride SNP), 4 points per warp (stride MR);
-//   Gram tiles      A[lp][4ti..]      all lanes share lp: float4 broadcast per distinct tile.
-__host__ __device__ inline int sc_mr(int maxres) { return maxres | 1; }
-__host__ __device__ inline int sc_snp(int maxres) { return SC_PTS * sc_mr(maxres) + 5; }
+// Data path.  The residual records of a point — JpJdF (32 B) and {bd, Hdd, Hcd[4], flag, target} (32 B) per residual
+// slot — are stored POINT-MAJOR (BARes::JpJdF / prec, pstr floats per point), so the records of SC_PTS consecutive points
+// are two contiguous spans: one elected thread fetches them with two bulk copies (cp.async.bulk, TMA engine) that
+// complete on an mbarrier, for sub-tile i+1 while sub-tile i is in the Gram phase.  No slot table, no flag loads, no
+// gathers, no global load on the critical path.
+// Phase 1 (four lanes per point, only __syncwarp inside): the six ordered per-point sums {bd, Hdd, Hcd[0..3]} for modes
+// A and L IN THE POINT'S OWN ORDER (AccumulatedTopHessian.cpp:35-139), the Schur scalars (AccumulatedSCHessian.cpp:12-33),
+// and the row  s_p = sqrt(HdiF_p) * a_p  into shared memory, so that the Gram phase needs ONE matrix:
+// G_h = sum_p s_p s_p^T  (= sum_p HdiF_p a_p a_p^T up to fp32 rounding; HdiF / bdSumF / Hdd / bd / Hcd themselves are
+// written exactly as before).
+// Phase 2: 4x4 register tiles of the upper triangle of G WITHOUT the two tile rows/columns of the host's own 8-block (a
+// point has no residual into its host).  Each tile is owned by TWO threads (tid and tid+128), one for the even and one
+// for the odd points of the sub-tile.  MAXT = tiles per thread: (NT-2)(NT-1)/2 <= MAXT*128 (1: n <= 7, 2: n <= 10, 5: n <= 16).
+// Shared memory (floats): A[SC_PTS][LD+4] | jp[SC_PTS*pstr] | pt[SC_PTS*pstr] | mbarrier.
+__host__ __device__ inline int sc_pstr(int maxres) { return 8 * maxres + 4; }
 __host__ __device__ inline size_t sc_smem_floats(int LD, int maxres) {
-  return 2 * (size_t)SC_PTS * (LD + 4) + SC_PTS + 7 * (size_t)sc_snp(maxres);
+  return (size_t)SC_PTS * (LD + 4) + 2 * (size_t)SC_PTS * sc_pstr(maxres) + 4;
 }
 
-// Gram tiles: 4x4 register tiles of the upper triangle of G_h WITHOUT the two tile rows/columns of the host's
-// own 8-block (a point has no residual into its host: that block of a_p is always zero, the partial buffer is
-// zero-initialised there).  Each tile is owned by TWO threads (tid and tid+128), one for the even and one for the
-// odd points of the sub-tile: all eight warps work in phase 2 and the per-tile dependent FMA chain is halved.
-// MAXT = tiles per thread: (NT-2)(NT-1)/2 <= MAXT*128 (MAXT=1: n <= 7, 2: n <= 10, 5: n <= 16).
-// NI   = (point, residual slot) items per thread and sub-tile: SC_PTS*maxres <= NI*256.
-// Software pipeline over the sub-tiles of the block's chunk: while sub-tile i is summed and folded, the
-// residual data of sub-tile i+1 (the residual's 14 floats + flags, addressed through the slot table) and
-// the slot entries of sub-tile i+2 are already in flight, held in registers.
-template <int MAXT, int NI>
+template <int MAXT>
 #ifndef SC_MINB
 #define SC_MINB 3
 #endif
-__global__ void __launch_bounds__(SC_THREADS, (MAXT >= 1 && MAXT <= 2 && NI <= 2) ? SC_MINB : 2)
+__global__ void __launch_bounds__(SC_THREADS, MAXT <= 2 ? SC_MINB : 2)
 ba_schur_kernel(const BADesc* __restrict__ descs, const int* __restrict__ prefix, int nwin) {
+  static_assert(SC_PTS * 4 == SC_THREADS, "phase 1 gives four lanes to every point of a sub-tile");
   extern __shared__ __align__(16) float smem[];
   int lb;
   const int win = find_window(prefix, nwin, blockIdx.x, lb);
@@ -1196,36 +1156,19 @@ ba_schur_kernel(const BADesc* __restrict__ descs, const int* __restrict__ prefix
   const BARes& r = D.r;
   const BAPts& pts = D.p;
   const int LD = D.LD, LDP = LD + 4;
-  const int maxres = D.maxres, MR = sc_mr(maxres), SNP = sc_snp(maxres);
-  float* A = smem;                        // [SC_PTS][LDP]   a_p
-  float* WA = A + SC_PTS * LDP;           // [SC_PTS][LDP]   HdiF_p * a_p
-  float* wv = WA + SC_PTS * LDP;          // [SC_PTS] HdiF
-  float* stg = wv + SC_PTS;               // [7][SNP]: 6 point terms + mode flag per (point, residual slot)
+  const int maxres = D.maxres, PSTR = r.pstr;
+  float* A = smem;                               // [SC_PTS][LDP]  sqrt(HdiF_p) * a_p
+  float* jp = A + SC_PTS * LDP;                  // [SC_PTS][PSTR] staged JpJdF records
+  float* pt = jp + SC_PTS * PSTR;                // [SC_PTS][PSTR] staged point-term records
+  uint64_t* full = reinterpret_cast<uint64_t*>(pt + SC_PTS * PSTR);
   const PtChunk ch = D.ptchunks[lb];
-  const int s = r.rs, n = D.W.n;
+  const int n = D.W.n;
   const int NT = LD / 4, NTR = NT - 2, ntiles = NTR * (NTR + 1) / 2;
-  const int half = threadIdx.x >> 7;      // 0: even points of the sub-tile, 1: odd points
-  // MAXT == 0 (n <= 7: at most 28 8x8 tiles): ONE 8x8 tile of the block-upper-triangle per LANE, the eight WARPS
-  // split the points of a sub-tile (warp w takes points w, w+8, ...) and are summed in a fixed tree at the end.
-  // An 8x8 tile costs 4 LDS.128 per 64 FMA instead of 2 per 16: half the shared-memory wavefronts of the Gram loop.
-  constexpr bool T8 = (MAXT == 0);
-  constexpr int MT = T8 ? 1 : MAXT;
-  constexpr int NACC = T8 ? 64 : 16;
-  int tI[MT], tJ[MT];
-  __align__(8) float acc[MT][NACC];
-  if (T8) {
-    const int lane = threadIdx.x & 31, NB = n;   // n block rows: the n+1 8-blocks of a_p without the host's own
-    tI[0] = tJ[0] = -1;
-    if (lane < NB * (NB + 1) / 2) {
-      tri_decode(lane, NB, tI[0], tJ[0]);
-      if (tI[0] >= ch.host) tI[0] += 1;
-      if (tJ[0] >= ch.host) tJ[0] += 1;
-    }
+  const int half = threadIdx.x >> 7;             // 0: even points of the sub-tile, 1: odd points
+  int tI[MAXT], tJ[MAXT];
+  __align__(8) float acc[MAXT][16];
 #pragma unroll
-    for (int i = 0; i < NACC; ++i) acc[0][i] = 0.f;
-  }
-#pragma unroll
-  for (int j = 0; j < (T8 ? 0 : MT); ++j) {
+  for (int j = 0; j < MAXT; ++j) {
     int tile = (threadIdx.x & 127) + j * 128;
     tI[j] = tJ[j] = -1;
     if (tile < ntiles) {
@@ -1236,280 +1179,135 @@ ba_schur_kernel(const BADesc* __restrict__ descs, const int* __restrict__ prefix
 #pragma unroll
     for (int i = 0; i < 16; ++i) acc[j][i] = 0.f;
   }
-  // (point, slot) items of this thread: the same in every sub-tile
-  int ilp[NI], isl[NI];
-#pragma unroll
-  for (int i = 0; i < NI; ++i) {
-    // point index fastest: the lanes of a warp stage the SAME slot of consecutive points, whose residuals sit
-    // next to each other in the pair-sorted arrays (coalesced loads; slot-fastest made every 4-byte load its
-    // own 32-byte sector and the kernel LSU-bound)
-    const int it = threadIdx.x + i * SC_THREADS;
-    isl[i] = it / SC_PTS; ilp[i] = it - isl[i] * SC_PTS;
-    if (isl[i] >= maxres) ilp[i] = SC_PTS;   // beyond the sub-tile
+  if (threadIdx.x == 0) {
+    mbar_init(full, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
   }
-  // pipeline registers
-  int en[NI];                         // slot entries of the NEXT sub-tile to be staged
-  float4 dj0[NI], dj1[NI];            // staged residual: JpJdF
-  float dpt[NI][6];                   //                  its six point terms
-  int dfl[NI];                        //                  -1 = nothing, else isActive | isLin << 1 | target << 8 (raw loads:
-                                      //                  nothing here may consume a loaded value before the next sub-tile)
-  unsigned char dact[NI], dlin[NI];
-  constexpr int NRD = SC_PTS * 8 / SC_THREADS;   // phase-1b rounds: 8 lanes per point
-  static_assert(NRD >= 1 && NRD * SC_THREADS == SC_PTS * 8, "SC_PTS must be a multiple of 32");
-  float pr[NRD], de[NRD];             // priorF / deltaF of the points this thread finalises in phase 1b
-
-  auto load_slots = [&](int base) {
-    const int cnt = min(SC_PTS, ch.count - base);   // <= 0 beyond the chunk
-#pragma unroll
-    for (int i = 0; i < NI; ++i) {
-      en[i] = (ilp[i] < cnt) ? pts.slot[(size_t)(ch.start + base + ilp[i]) * maxres + isl[i]] : -1;
-      if (D.marg && ilp[i] < cnt && D.marg[ch.start + base + ilp[i]] == 0) en[i] = -1;   // marginalisation pass: flagged points only
-    }
-  };
-  auto load_data = [&](int base) {   // consumes en[]
+  __syncthreads();
+  auto fetch = [&](int base) {   // thread 0: the records of sub-tile [base, base + SC_PTS) of the chunk
     const int cnt = min(SC_PTS, ch.count - base);
-#pragma unroll
-    for (int i = 0; i < NI; ++i) {
-      dfl[i] = -1; dact[i] = 0; dlin[i] = 0;
-      if (en[i] >= 0) {
-        const int k = en[i] & 0x3ffffff;
-        // every load of the residual is independent of its flags (one round trip); filtered at the store
-        dact[i] = r.isActive[k];
-        dlin[i] = r.isLin[k];
-        const float4* jp = reinterpret_cast<const float4*>(r.JpJdF + 8 * (size_t)k);
-        dj0[i] = jp[0];
-        dj1[i] = jp[1];
-        const float* o = r.ptc[0] + k;   // modes A and L share the array (a residual is in exactly one)
-#pragma unroll
-        for (int j = 0; j < 6; ++j) dpt[i][j] = o[j * s];
-        dfl[i] = en[i] >> 26;   // target
-      }
-    }
-#pragma unroll
-    for (int rd = 0; rd < NRD; ++rd) {
-      const int item = rd * SC_THREADS + threadIdx.x, lp = item >> 3, c = item & 7;
-      pr[rd] = de[rd] = 0.f;
-      if (lp < cnt && c < 2) {
-        pr[rd] = pts.priorF[ch.start + base + lp];
-        if (c == 0) de[rd] = pts.deltaF[ch.start + base + lp];
-      }
-    }
+    if (cnt <= 0) return;
+    const unsigned bytes = (unsigned)cnt * PSTR * 4;
+    mbar_expect_tx(full, 2 * bytes);
+    bulk_g2s(jp, r.JpJdF + (size_t)(ch.start + base) * PSTR, bytes, full);
+    bulk_g2s(pt, r.prec + (size_t)(ch.start + base) * PSTR, bytes, full);
   };
-
-#ifndef SC_PIPELINE
-#define SC_PIPELINE 0   /* measured on B200 (8 x cfg2 windows): register prefetch of the next sub-tile 63.9 us, plain staging 61.4 us */
-#endif
-#if SC_PIPELINE == 1
-  // prologue: slots of sub-tile 0 -> data of sub-tile 0; slots of sub-tile 1
-  load_slots(0);
-  load_data(0);
-  load_slots(SC_PTS);
-#elif SC_PIPELINE == 2
-  load_slots(0);   // slot entries only (one register per item) run one sub-tile ahead: one dependent round trip less
-#endif
-
-  // padding columns [8n+5, LD) of the scaled rows: zero once (phase 1b only ever writes the columns below)
-  for (int i = threadIdx.x; i < SC_PTS * 4; i += SC_THREADS) {
-    const int q = 8 * n + 5 + (i & 3);
-    if (q < LD) WA[(i >> 2) * LDP + q] = 0.f;
-  }
-  for (int base = 0; base < ch.count; base += SC_PTS) {
+  if (threadIdx.x == 0) fetch(0);
+  const int lp = threadIdx.x >> 2, q = threadIdx.x & 3;   // phase 1: point of the sub-tile, lane within the point
+  // priorF / deltaF of this thread's point, loaded one sub-tile ahead (lanes 0 and 1 of a point need them)
+  float pr_n = 0.f, de_n = 0.f;
+  if (q < 2 && lp < ch.count) { pr_n = pts.priorF[ch.start + lp]; if (q == 0) de_n = pts.deltaF[ch.start + lp]; }
+  unsigned parity = 0;
+  for (int base = 0; base < ch.count; base += SC_PTS, parity ^= 1u) {
     const int cnt = min(SC_PTS, ch.count - base);
-#if SC_PIPELINE == 0
-    load_slots(base);
-    load_data(base);
-#elif SC_PIPELINE == 2
-    load_data(base);
-    load_slots(base + SC_PTS);   // consumed at the top of the next iteration
-#endif
-    for (int i = threadIdx.x; i < SC_PTS * LDP / 4; i += SC_THREADS) reinterpret_cast<float4*>(A)[i] = make_float4(0.f, 0.f, 0.f, 0.f);
-    __syncthreads();
-    // phase 1a: the staged registers of THIS sub-tile go to shared memory ...
-#pragma unroll
-    for (int i = 0; i < NI; ++i) {
-      if (ilp[i] < SC_PTS) {
-        const int si = ilp[i] * MR + isl[i];
-        const bool on = dfl[i] >= 0 && dact[i] != 0;
-        if (on) {
-          float4* dst = reinterpret_cast<float4*>(A + ilp[i] * LDP + 8 * dfl[i]);
-          dst[0] = dj0[i]; dst[1] = dj1[i];
-#pragma unroll
-          for (int j = 0; j < 6; ++j) stg[j * SNP + si] = dpt[i][j];
-        }
-        stg[6 * SNP + si] = on ? (dlin[i] ? 2.f : 1.f) : 0.f;
-      }
+    const float prc = pr_n, dec = de_n;
+    {
+      const int nb = base + SC_PTS + lp;
+      pr_n = de_n = 0.f;
+      if (q < 2 && nb < ch.count) { pr_n = pts.priorF[ch.start + nb]; if (q == 0) de_n = pts.deltaF[ch.start + nb]; }
     }
-    float prc[NRD], dec[NRD];
-#pragma unroll
-    for (int rd = 0; rd < NRD; ++rd) { prc[rd] = pr[rd]; dec[rd] = de[rd]; }
-    // ... and the loads of the NEXT sub-tile (data) and the one after (slots) are issued: they complete
-    // while phases 1b and 2 run
-#if SC_PIPELINE == 1
-    load_data(base + SC_PTS);
-    load_slots(base + 2 * SC_PTS);
-#endif
-    __syncthreads();
-    // phase 1b: 8 lanes per point; lane c < 6 owns one of the six per-point sums {bd, Hdd, Hcd[0..3]} for both
-    // modes and adds the point's residuals IN THE POINT'S OWN ORDER (AccumulatedTopHessian.cpp:35-139), then
-    // the Schur scalars (AccumulatedSCHessian.cpp:12-33).
-#pragma unroll
-    for (int rd = 0; rd < NRD; ++rd) {
-      const int item = rd * SC_THREADS + threadIdx.x, lp = item >> 3, c = item & 7;
-      float rowv = 0.f, rowh = 0.f;
-      if (c < 6) {
-        if (lp < cnt && (!D.marg || D.marg[ch.start + base + lp] != 0)) {
-          const int p = ch.start + base + lp;
-          // branch-free: a slot that is absent / inactive adds +0 (exact), its stale value is never selected
-          float sum[2] = {0.f, 0.f};
-          int ngood = 0;
-          const float* fl = stg + 6 * SNP + lp * MR;
-          const float* vl = stg + c * SNP + lp * MR;
+    mbar_wait(full, parity);
+    // ---- phase 1
+    {
+      float* row = A + lp * LDP;
+      // zero the row (blocks without an active residual, the host's own block, the padding columns)
+      for (int i = q; i < LDP / 4; i += 4) reinterpret_cast<float4*>(row)[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+      const int p = ch.start + base + lp;
+      const bool live = lp < cnt && (!D.marg || D.marg[p] != 0);   // marginalisation pass: flagged points only
+      float hdi = 0.f, mine0 = 0.f, mine1 = 0.f;   // this lane's entries of a_p: component q, and q+4 for lanes 0 / 1
+      if (live) {
+        const float* pl = pt + lp * PSTR;
+        // branch-free ordered sums: a slot that is absent / inactive adds +0 (exact)
+        float s0[2] = {0.f, 0.f}, s1[2] = {0.f, 0.f};
+        int ngood = 0;
 #pragma unroll 2
-          for (int slot = 0; slot < maxres; ++slot) {
-            const float f = fl[slot], v = vl[slot];
-            ngood += (f != 0.f) ? 1 : 0;
-            sum[0] = xadd(sum[0], f == 1.f ? v : 0.f);
-            sum[1] = xadd(sum[1], f == 2.f ? v : 0.f);
+        for (int slot = 0; slot < maxres; ++slot) {
+          const float f = pl[8 * slot + 6], v0 = pl[8 * slot + q], v1 = pl[8 * slot + (q < 2 ? q + 4 : q)];
+          ngood += (f != 0.f) ? 1 : 0;
+          s0[0] = xadd(s0[0], f == 1.f ? v0 : 0.f); s0[1] = xadd(s0[1], f == 2.f ? v0 : 0.f);
+          s1[0] = xadd(s1[0], f == 1.f ? v1 : 0.f); s1[1] = xadd(s1[1], f == 2.f ? v1 : 0.f);
+        }
+        // components: 0 = bd, 1 = Hdd, 2..5 = Hcd[0..3]; lane q owns q, lanes 0 / 1 also own 4 / 5
+        if (q == 0) {
+          pts.bd[0][p] = s0[0]; pts.bd[1][p] = s0[1];
+          if (ngood > 0) {
+            mine0 = xadd(s0[0], s0[1]);
+            if (D.shift_prior) mine0 = xadd(mine0, xmul(prc, dec));   // shiftPriorToZero (EnergyFunctional.cpp:209)
           }
-          float mine = 0.f;   // this lane's entry of a_p (columns 8n .. 8n+4)
-          float hdi = 0.f;
-#ifdef SC_EXP_NO1BSTORE   /* timing experiment only */
-#define SC_ST(lhs, rhs) do { if ((rhs) == 1.2345e-33f) lhs = (rhs); } while (0)
-#else
-#define SC_ST(lhs, rhs) lhs = (rhs)
-#endif
-          if (c == 0) {
-            SC_ST(pts.bd[0][p], sum[0]); SC_ST(pts.bd[1][p], sum[1]);
-            if (ngood > 0) {
-              mine = xadd(sum[0], sum[1]);
-              if (D.shift_prior) mine = xadd(mine, xmul(prc[rd], dec[rd]));   // shiftPriorToZero (EnergyFunctional.cpp:209)
-            }
-            SC_ST(pts.bdSumF[p], mine);
-          } else if (c == 1) {
-            SC_ST(pts.Hdd[0][p], sum[0]); SC_ST(pts.Hdd[1][p], sum[1]);
-            float idh = 0.f;
-            if (ngood > 0) {
-              float H = xadd(xadd(sum[0], sum[1]), prc[rd]);
-              if (H < 1e-10f) H = 1e-10f;
-              idh = H;
-              hdi = xdiv(1.0f, H);
-            }
-            SC_ST(pts.HdiF[p], hdi); SC_ST(pts.idepth_hessian[p], idh);
-            wv[lp] = hdi;
-          } else {
-            SC_ST(reinterpret_cast<float*>(pts.Hcd[0])[4 * (size_t)p + (c - 2)], sum[0]);
-            SC_ST(reinterpret_cast<float*>(pts.Hcd[1])[4 * (size_t)p + (c - 2)], sum[1]);
-            mine = xadd(sum[0], sum[1]);
+          pts.bdSumF[p] = mine0;
+        } else if (q == 1) {
+          pts.Hdd[0][p] = s0[0]; pts.Hdd[1][p] = s0[1];
+          float idh = 0.f;
+          if (ngood > 0) {
+            float H = xadd(xadd(s0[0], s0[1]), prc);
+            if (H < 1e-10f) H = 1e-10f;
+            idh = H;
+            hdi = xdiv(1.0f, H);
           }
-          rowv = mine; rowh = hdi;
-        } else if (c == 1 && lp < SC_PTS) {
-          wv[lp] = 0.f;   // beyond the chunk, or not flagged in a marginalisation pass: contributes nothing
+          pts.HdiF[p] = hdi; pts.idepth_hessian[p] = idh;
+        } else {
+          reinterpret_cast<float*>(pts.Hcd[0])[4 * (size_t)p + (q - 2)] = s0[0];
+          reinterpret_cast<float*>(pts.Hcd[1])[4 * (size_t)p + (q - 2)] = s0[1];
+          mine0 = xadd(s0[0], s0[1]);
+        }
+        if (q < 2) {
+          reinterpret_cast<float*>(pts.Hcd[0])[4 * (size_t)p + (q + 2)] = s1[0];
+          reinterpret_cast<float*>(pts.Hcd[1])[4 * (size_t)p + (q + 2)] = s1[1];
+          mine1 = xadd(s1[0], s1[1]);
         }
       }
-      // the 8 lanes of a point share HdiF and write the scaled copy of the row: lane c < 6 its own entry of the
-      // [Hcd | bdSum] block, all 8 lanes two float4 each of the JpJdF part (staged in phase 1a)
-      const float hd = __shfl_sync(0xffffffffu, rowh, (threadIdx.x & 24) + 1);   // lane c == 1 of this point's 8-lane group
-      if (lp < cnt) {
-        const int colb = 8 * n;
-        if (c == 0) { A[lp * LDP + colb + 4] = rowv; WA[lp * LDP + colb + 4] = hd * rowv; }
-        else if (c >= 2 && c < 6) { A[lp * LDP + colb + (c - 2)] = rowv; WA[lp * LDP + colb + (c - 2)] = hd * rowv; }
-        for (int q4 = c; q4 < 2 * n; q4 += 8) {
-          const float4 v = *reinterpret_cast<const float4*>(A + lp * LDP + 4 * q4);
-          *reinterpret_cast<float4*>(WA + lp * LDP + 4 * q4) = make_float4(hd * v.x, hd * v.y, hd * v.z, hd * v.w);
-        }
-      }
-    }
-    __syncthreads();
-    // phase 2: G += sum_p (w_p a_p) a_p^T, 4x4 register tiles, this thread's half of the points in order
-    if (T8) {
-      if (tI[0] >= 0) {
-        const float* ap = WA + 8 * tI[0];
-        const float* bp = A + 8 * tJ[0];
-        float2* acc2 = reinterpret_cast<float2*>(acc[0]);
-#pragma unroll 2
-        for (int lp = threadIdx.x >> 5; lp < cnt; lp += SC_THREADS / 32) {
-          const float4 a0 = *reinterpret_cast<const float4*>(ap + lp * LDP), a1 = *reinterpret_cast<const float4*>(ap + lp * LDP + 4);
-          const float4 b0 = *reinterpret_cast<const float4*>(bp + lp * LDP), b1 = *reinterpret_cast<const float4*>(bp + lp * LDP + 4);
-          const float a8[8] = {a0.x, a0.y, a0.z, a0.w, a1.x, a1.y, a1.z, a1.w};
-          const float2 bb[4] = {make_float2(b0.x, b0.y), make_float2(b0.z, b0.w), make_float2(b1.x, b1.y), make_float2(b1.z, b1.w)};
-#pragma unroll
-          for (int ii = 0; ii < 8; ++ii) {
-            const float2 aa = make_float2(a8[ii], a8[ii]);
-#pragma unroll
-            for (int jj = 0; jj < 4; ++jj) acc2[4 * ii + jj] = __ffma2_rn(aa, bb[jj], acc2[4 * ii + jj]);
-          }
+      // the four lanes of a point share sqrt(HdiF) (lane 1 holds HdiF)
+      const float sw = sqrtf(__shfl_sync(0xffffffffu, hdi, (threadIdx.x & 28) + 1));
+      __syncwarp();   // the row is zeroed
+      if (live) {
+        const int colb = 8 * n;   // a_p tail: Hcd[0..3] at 8n..8n+3, bdSum at 8n+4
+        if (q == 0) { row[colb + 4] = sw * mine0; row[colb + 2] = sw * mine1; }
+        else if (q == 1) { row[colb + 3] = sw * mine1; }
+        else { row[colb + (q - 2)] = sw * mine0; }
+        const float* pl = pt + lp * PSTR;
+        const float* jl = jp + lp * PSTR;
+        for (int slot = q; slot < maxres; slot += 4) {
+          if (pl[8 * slot + 6] == 0.f) continue;
+          const int t = (int)pl[8 * slot + 7];
+          const float4 j0 = *reinterpret_cast<const float4*>(jl + 8 * slot), j1 = *reinterpret_cast<const float4*>(jl + 8 * slot + 4);
+          *reinterpret_cast<float4*>(row + 8 * t) = make_float4(sw * j0.x, sw * j0.y, sw * j0.z, sw * j0.w);
+          *reinterpret_cast<float4*>(row + 8 * t + 4) = make_float4(sw * j1.x, sw * j1.y, sw * j1.z, sw * j1.w);
         }
       }
     }
+    __syncthreads();   // rows complete; the staged records are free again
+    if (threadIdx.x == 0) fetch(base + SC_PTS);   // lands while the Gram phase runs
+    // ---- phase 2: G += sum_p s_p s_p^T, 4x4 register tiles, this thread's half of the points in order
 #pragma unroll
-    for (int j = 0; j < (T8 ? 0 : MT); ++j) {
+    for (int j = 0; j < MAXT; ++j) {
       if (tI[j] >= 0) {
-        const float* ap = WA + 4 * tI[j];
+        const float* ap = A + 4 * tI[j];
         const float* bp = A + 4 * tJ[j];
 #pragma unroll 4
-        for (int lp = half; lp < cnt; lp += 2) {
-          const float4 av = *reinterpret_cast<const float4*>(ap + lp * LDP);
-          const float4 bv = *reinterpret_cast<const float4*>(bp + lp * LDP);
+        for (int l2 = half; l2 < cnt; l2 += 2) {
+          const float4 av = *reinterpret_cast<const float4*>(ap + l2 * LDP);
+          const float4 bv = *reinterpret_cast<const float4*>(bp + l2 * LDP);
           const float a4[4] = {av.x, av.y, av.z, av.w};
-          const float b4[4] = {bv.x, bv.y, bv.z, bv.w};
-#ifndef SC_FFMA2
-#define SC_FFMA2 1
-#endif
-#if SC_FFMA2
           // packed fp32 FMA (sm_100 FFMA2): two accumulators per instruction, each product rounded exactly like fmaf
           float2* acc2 = reinterpret_cast<float2*>(acc[j]);
-          const float2 b01 = make_float2(b4[0], b4[1]), b23 = make_float2(b4[2], b4[3]);
+          const float2 b01 = make_float2(bv.x, bv.y), b23 = make_float2(bv.z, bv.w);
 #pragma unroll
           for (int ii = 0; ii < 4; ++ii) {
             const float2 aa = make_float2(a4[ii], a4[ii]);
             acc2[2 * ii] = __ffma2_rn(aa, b01, acc2[2 * ii]);
             acc2[2 * ii + 1] = __ffma2_rn(aa, b23, acc2[2 * ii + 1]);
           }
-#else
-#pragma unroll
-          for (int ii = 0; ii < 4; ++ii)
-#pragma unroll
-            for (int jj = 0; jj < 4; ++jj) acc[j][4 * ii + jj] = fmaf(a4[ii], b4[jj], acc[j][4 * ii + jj]);
-#endif
         }
       }
     }
-    __syncthreads();
+    __syncthreads();   // A is free again
   }
   // the odd-point halves go through shared memory (A is free now), the even-point threads add and store
   float* out = D.scpartial + (size_t)lb * LD * LD;
-  if (T8) {
-    // fixed tree over the eight warps through shared memory (the staging memory is free now; the host sizes it >= 4*2048 floats),
-    // component-major [k][lane]: conflict-free.  (4..7 -> 0..3), (2,3 -> 0,1), (1 -> 0); warp 0 stores.
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-#pragma unroll
-    for (int span = 4; span >= 1; span >>= 1) {
-      if (warp >= span && warp < 2 * span) {
-        float* buf = A + (size_t)(warp - span) * 2048 + lane;
-#pragma unroll
-        for (int k = 0; k < 64; ++k) buf[32 * k] = acc[0][k];
-      }
-      __syncthreads();
-      if (warp < span) {
-        const float* buf = A + (size_t)warp * 2048 + lane;
-#pragma unroll
-        for (int k = 0; k < 64; ++k) acc[0][k] += buf[32 * k];
-      }
-      __syncthreads();
-    }
-    if (warp == 0 && tI[0] >= 0) {
-#pragma unroll
-      for (int ii = 0; ii < 8; ++ii) {
-        float* o = out + (size_t)(8 * tI[0] + ii) * LD + 8 * tJ[0];
-        *reinterpret_cast<float4*>(o) = make_float4(acc[0][8 * ii], acc[0][8 * ii + 1], acc[0][8 * ii + 2], acc[0][8 * ii + 3]);
-        *reinterpret_cast<float4*>(o + 4) = make_float4(acc[0][8 * ii + 4], acc[0][8 * ii + 5], acc[0][8 * ii + 6], acc[0][8 * ii + 7]);
-      }
-    }
-    return;
-  }
 #pragma unroll
   for (int j = 0; j < MAXT; ++j) {
-    float* xch = A + (size_t)((threadIdx.x & 127) + j * 128) * 16;   // <= MAXT*128*16 floats <= 2*SC_PTS*LDP
+    float* xch = A + (size_t)((threadIdx.x & 127) + j * 128) * 16;   // <= MAXT*128*16 floats (the host sizes the block for it)
     if (tI[j] >= 0 && half == 1) {
 #pragma unroll
       for (int ii = 0; ii < 4; ++ii)
@@ -1560,7 +1358,9 @@ __global__ void __launch_bounds__(256) ba_fold_sc_kernel(const BADesc* __restric
     src += 8 * stride;
   }
   for (; c < ce; ++c) { sum += (double)__ldcg(src); src += stride; }
+  // G_h is symmetric; the Schur kernel produces its upper 4x4 tiles only: store the mirror too, the stitch reads a dense matrix
   D.G[(size_t)host * LD * LD + i] = sum;
+  if ((col >> 2) > (row >> 2)) D.G[(size_t)host * LD * LD + (size_t)col * LD + row] = sum;
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -1570,46 +1370,36 @@ __global__ void __launch_bounds__(256) ba_fold_sc_kernel(const BADesc* __restric
 // warp computes one 8x8 sandwich with two elements per lane through a private shared-memory stage),
 // then the warps' partial blocks are summed in warp order.
 // ------------------------------------------------------------------------------------------------
-// element (r,c) of the 13x13 relative accumulator from its packed 91-value form
-__device__ __forceinline__ double acc13(const double* a, int r, int c) {
-  if (r > c) { int t = r; r = c; c = t; }
-  if (c < 10) return a[r * 10 - (r * (r - 1)) / 2 + (c - r)];   // row-major upper triangle of 10x10
-  if (r < 10) return a[55 + 3 * r + (c - 10)];
-  const int br[3][3] = {{85, 86, 87}, {86, 88, 89}, {87, 89, 90}};
-  return a[br[r - 10][c - 10]];
+// fp64 tensor-core step D(8x8) += A(8x4) * B(4x8) of one warp (mma.sync.m8n8k4.f64, DMMA): lane (g = lane>>2, t = lane&3)
+// holds A[g][t], B[t][g] and the accumulator pair D[g][2t], D[g][2t+1].
+__device__ __forceinline__ void dmma884(double& d0, double& d1, double a, double b) {
+  asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0, %1}, {%2}, {%3}, {%0, %1};" : "+d"(d0), "+d"(d1) : "d"(a), "d"(b));
 }
-__device__ __forceinline__ double Gsym(const double* G, int LD, int i, int j) {
-  return ((j >> 2) >= (i >> 2)) ? G[(size_t)i * LD + j] : G[(size_t)j * LD + i];
-}
-
-// out(r, c0) and out(r, c1) of A1 * M * A2^T for one warp: lane -> r = lane&7, c0 = lane>>3, c1 = c0+4.
-// Every global load (M, A2 and A1) is issued before the first use, so a sandwich costs one memory round trip.
-// SYM: add the transpose as well (X + X^T), for the pairs (j,k),(k,j) of a symmetric Gram block.
-template <bool SYM, class MF>
-__device__ __forceinline__ void sandwich_warp(const double* __restrict__ A1, const double* __restrict__ A2, MF M,
-                                              double (*tmp)[9], int lane, double& o0, double& o1) {
-  const int r = lane & 7, c0 = lane >> 3, c1 = c0 + 4;
-  double m[8], a20[8], a21[8], a1[8];
-#pragma unroll
-  for (int y = 0; y < 8; ++y) { m[y] = M(r, y); a20[y] = A2[c0 + 8 * y]; a21[y] = A2[c1 + 8 * y]; a1[y] = A1[r + 8 * y]; }
-  double t0 = 0.0, t1 = 0.0;
-#pragma unroll
-  for (int y = 0; y < 8; ++y) { t0 += m[y] * a20[y]; t1 += m[y] * a21[y]; }
-  __syncwarp();
-  tmp[r][c0] = t0; tmp[r][c1] = t1;
-  __syncwarp();
-  double x0 = 0.0, x1 = 0.0;
-#pragma unroll
-  for (int x = 0; x < 8; ++x) { x0 += a1[x] * tmp[x][c0]; x1 += a1[x] * tmp[x][c1]; }
-  if (SYM) {
-    __syncwarp();
-    tmp[r][c0] = x0; tmp[r][c1] = x1;
-    __syncwarp();
-    x0 += tmp[c0][r]; x1 += tmp[c1][r];
-  }
-  o0 += x0; o1 += x1;
+// (o0, o1) += A1 * M * A2^T for one warp, as four DMMAs: T = A1 * M (two k-steps), T from accumulator layout to A-operand
+// layout with two quad shuffles, then o += T * A2^T (two k-steps).  A1, A2: 8x8 column-major (the adjoints); M(row, col) =
+// Mb[row * ldm + col] (dense 13x13 top accumulator or dense Gram matrix).  6 loads per lane, one memory round trip.
+__device__ __forceinline__ void sandwich_dmma(const double* __restrict__ A1, const double* __restrict__ A2,
+                                              const double* __restrict__ Mb, int ldm, int lane, double& o0, double& o1) {
+  const int g = lane >> 2, t = lane & 3;
+  const double a1lo = A1[g + 8 * t], a1hi = A1[g + 8 * (t + 4)];
+  const double mlo = Mb[t * ldm + g], mhi = Mb[(t + 4) * ldm + g];
+  const double a2lo = A2[g + 8 * t], a2hi = A2[g + 8 * (t + 4)];
+  double T0 = 0.0, T1 = 0.0;
+  dmma884(T0, T1, a1lo, mlo);
+  dmma884(T0, T1, a1hi, mhi);
+  // T[g][t] lives in lane (quad | t>>1), slot t&1; T[g][t+4] two lanes further
+  const int src = (lane & ~3) | (t >> 1);
+  const double s0 = __shfl_sync(0xffffffffu, T0, src), s1 = __shfl_sync(0xffffffffu, T1, src);
+  const double u0 = __shfl_sync(0xffffffffu, T0, src + 2), u1 = __shfl_sync(0xffffffffu, T1, src + 2);
+  const double tlo = (t & 1) ? s1 : s0, thi = (t & 1) ? u1 : u0;
+  dmma884(o0, o1, tlo, a2lo);
+  dmma884(o0, o1, thi, a2hi);
 }
 
+// K7: stitch — relative accumulators -> (8n+4)^2 system in fp64, gather form.  One block per output 8x8 block (a,b) of one
+// system; index n is the calibration block.  The Ad * M * Ad^T sandwiches that land in a block are dealt round-robin to the
+// block's warps (four fp64 tensor-core steps each, accumulated in the warp's DMMA accumulators), then the warps' partial
+// blocks are summed in warp order.  The 8x8x8 fp64 products are the one true contraction on the path (and exact fp64 FMAs).
 __global__ void __launch_bounds__(ST_THREADS) ba_stitch_kernel(const BADesc* __restrict__ descs,
                                                                const int* __restrict__ prefix, int nwin,
                                                                int sys_begin, int sys_end, int with_energy) {
@@ -1622,7 +1412,6 @@ __global__ void __launch_bounds__(ST_THREADS) ba_stitch_kernel(const BADesc* __r
   const int a = ab % nb1, b = ab / nb1;
   if (sys < sys_begin || sys >= sys_end) return;   // systems (0=A, 1=L, 2=SC) this launch produces
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  __shared__ double tmp[ST_WARPS][8][9];
   __shared__ double part[ST_WARPS][64];
   double* H = S.Hb + (size_t)sys * ((size_t)N * N + N);
   double* bv = H + (size_t)N * N;
@@ -1631,17 +1420,30 @@ __global__ void __launch_bounds__(ST_THREADS) ba_stitch_kernel(const BADesc* __r
   auto AdT = [&](int h, int t) { return S.adTarget + 64 * (size_t)(h + t * n); };
   double o0 = 0.0, o1 = 0.0;
   int ci = 0;   // contribution counter, identical in every warp
-#define CONTRIB(A1, A2, MF)                                                                 \
+#define CONTRIB(A1, A2, MB, LDM)                                                            \
   do {                                                                                      \
-    if ((ci % ST_WARPS) == warp) sandwich_warp<false>((A1), (A2), (MF), tmp[warp], lane, o0, o1);   \
+    if ((ci % ST_WARPS) == warp) sandwich_dmma((A1), (A2), (MB), (LDM), lane, o0, o1);      \
     ci++;                                                                                   \
   } while (0)
+  // the warps' accumulator pairs (row g, columns 2t, 2t+1) -> part[warp][row + 8 col], summed in warp order by 64 threads
+  auto reduce_block = [&](auto&& store) {
+    const int g = lane >> 2, t = lane & 3;
+    part[warp][g + 8 * (2 * t)] = o0; part[warp][g + 8 * (2 * t + 1)] = o1;
+    __syncthreads();
+    if (threadIdx.x < 64) {
+      double o = 0.0;
+#pragma unroll
+      for (int w = 0; w < ST_WARPS; ++w) o += part[w][threadIdx.x];
+      store(threadIdx.x & 7, threadIdx.x >> 3, o);
+    }
+  };
 
   if (sys < 2) {
-    const double* acc = S.accTop + (size_t)(sys == 0 ? 0 : S.L_set) * nn * TOP_PART;
-    auto ACC = [&](int h, int t) { return acc + (size_t)(h + t * n) * TOP_PART; };
+    const double* acc = S.accTop + (size_t)(sys == 0 ? 0 : S.L_set) * nn * TOP_DENSE;
+    auto ACC = [&](int h, int t) { return acc + (size_t)(h + t * n) * TOP_DENSE; };
     const bool usePrior = (sys == 1) && S.add_priors;
     const bool live = (sys == 0) || S.has_L;   // without linearised residuals the L accumulators are zero
+    constexpr int FB = 4 * 13 + 4;              // the 8x8 frame block of the dense 13x13 starts at (4,4)
     if (a < n && b < n) {
       if (a > b) return;                        // written by the mirror block (AccumulatedTopHessian.h:105-116)
       if (live) {
@@ -1649,32 +1451,25 @@ __global__ void __launch_bounds__(ST_THREADS) ba_stitch_kernel(const BADesc* __r
           // S[a,a] = sum_t AdH[a,t] M[a,t] AdH[a,t]^T + sum_h AdT[h,a] M[h,a] AdT[h,a]^T + AdH[a,a] M[a,a] AdT[a,a]^T
           for (int t = 0; t < n; ++t) {
             const double* m = ACC(a, t);
-            if (m[91] == 0.0) continue;   // acc.num == 0 (AccumulatedTopHessian.cpp:243)
-            CONTRIB(AdH(a, t), AdH(a, t), [&](int x, int y) { return acc13(m, 4 + x, 4 + y); });
+            if (m[169] == 0.0) continue;   // acc.num == 0 (AccumulatedTopHessian.cpp:243)
+            CONTRIB(AdH(a, t), AdH(a, t), m + FB, 13);
           }
           for (int h = 0; h < n; ++h) {
             const double* m = ACC(h, a);
-            if (m[91] == 0.0) continue;
-            CONTRIB(AdT(h, a), AdT(h, a), [&](int x, int y) { return acc13(m, 4 + x, 4 + y); });
+            if (m[169] == 0.0) continue;
+            CONTRIB(AdT(h, a), AdT(h, a), m + FB, 13);
           }
           const double* m = ACC(a, a);
-          if (m[91] != 0.0) CONTRIB(AdH(a, a), AdT(a, a), [&](int x, int y) { return acc13(m, 4 + x, 4 + y); });
+          if (m[169] != 0.0) CONTRIB(AdH(a, a), AdT(a, a), m + FB, 13);
         } else {
-          // H[a,b] = S[a,b] + S[b,a]^T
+          // H[a,b] = S[a,b] + S[b,a]^T  (M is symmetric)
           const double* m1 = ACC(a, b);
-          if (m1[91] != 0.0) CONTRIB(AdH(a, b), AdT(a, b), [&](int x, int y) { return acc13(m1, 4 + x, 4 + y); });
+          if (m1[169] != 0.0) CONTRIB(AdH(a, b), AdT(a, b), m1 + FB, 13);
           const double* m2 = ACC(b, a);
-          if (m2[91] != 0.0) CONTRIB(AdT(b, a), AdH(b, a), [&](int x, int y) { return acc13(m2, 4 + y, 4 + x); });
+          if (m2[169] != 0.0) CONTRIB(AdT(b, a), AdH(b, a), m2 + FB, 13);
         }
       }
-      const int r = lane & 7, c0 = lane >> 3;
-      part[warp][r + 8 * c0] = o0; part[warp][r + 8 * (c0 + 4)] = o1;
-      __syncthreads();
-      if (threadIdx.x < 64) {
-        const int rr = threadIdx.x & 7, cc = threadIdx.x >> 3;
-        double o = 0.0;
-#pragma unroll
-        for (int w = 0; w < ST_WARPS; ++w) o += part[w][threadIdx.x];
+      reduce_block([&](int rr, int cc, double o) {
         if (a == b) {
           if (usePrior && rr == cc) o += S.framePrior[8 * a + rr];
           H[(size_t)(4 + 8 * a + rr) + (size_t)N * (4 + 8 * a + cc)] = o;
@@ -1682,26 +1477,27 @@ __global__ void __launch_bounds__(ST_THREADS) ba_stitch_kernel(const BADesc* __r
           H[(size_t)(4 + 8 * a + rr) + (size_t)N * (4 + 8 * b + cc)] = o;
           H[(size_t)(4 + 8 * b + cc) + (size_t)N * (4 + 8 * a + rr)] = o;
         }
-      }
+      });
     } else if (a < n && b == n) {
       // H[a, 0:4] (8x4), its transpose, and b[a]: mat-vec products, one thread per output element
       if (threadIdx.x < 40) {
         const int r = threadIdx.x & 7, c = threadIdx.x >> 3;
+        const int col = c < 4 ? c : 12;
         double o = 0.0;
         if (live) {
           for (int t = 0; t < n; ++t) {
             const double* m = ACC(a, t);
-            if (m[91] == 0.0) continue;
+            if (m[169] == 0.0) continue;
             const double* A1 = AdH(a, t);
 #pragma unroll
-            for (int x = 0; x < 8; ++x) o += A1[r + 8 * x] * (c < 4 ? acc13(m, 4 + x, c) : acc13(m, 4 + x, 12));
+            for (int x = 0; x < 8; ++x) o += A1[r + 8 * x] * m[(4 + x) * 13 + col];
           }
           for (int h = 0; h < n; ++h) {
             const double* m = ACC(h, a);
-            if (m[91] == 0.0) continue;
+            if (m[169] == 0.0) continue;
             const double* A1 = AdT(h, a);
 #pragma unroll
-            for (int x = 0; x < 8; ++x) o += A1[r + 8 * x] * (c < 4 ? acc13(m, 4 + x, c) : acc13(m, 4 + x, 12));
+            for (int x = 0; x < 8; ++x) o += A1[r + 8 * x] * m[(4 + x) * 13 + col];
           }
         }
         if (c < 4) {
@@ -1715,12 +1511,13 @@ __global__ void __launch_bounds__(ST_THREADS) ba_stitch_kernel(const BADesc* __r
     } else if (a == n && b == n) {
       if (threadIdx.x < 20) {
         const int r = threadIdx.x & 3, c = threadIdx.x >> 2;
+        const int col = c < 4 ? c : 12;
         double o = 0.0;
         if (live)
           for (int k = 0; k < nn; ++k) {
-            const double* m = acc + (size_t)k * TOP_PART;
-            if (m[91] == 0.0) continue;
-            o += (c < 4) ? acc13(m, r, c) : acc13(m, r, 12);
+            const double* m = acc + (size_t)k * TOP_DENSE;
+            if (m[169] == 0.0) continue;
+            o += m[r * 13 + col];
           }
         if (c < 4) {
           if (usePrior && r == c) o += S.cPrior[r];
@@ -1732,7 +1529,7 @@ __global__ void __launch_bounds__(ST_THREADS) ba_stitch_kernel(const BADesc* __r
       } else if (threadIdx.x == 32) {
         int tot = 0;
         if (live)
-          for (int k = 0; k < nn; ++k) tot += (int)acc[(size_t)k * TOP_PART + 91];
+          for (int k = 0; k < nn; ++k) tot += (int)acc[(size_t)k * TOP_DENSE + 169];
         S.nres[sys] = tot;   // resInA / resInL (EnergyFunctional.cpp:163,186)
       }
       if (sys == 0 && with_energy) energy_sum_block(descs[win], &part[0][0]);   // uniform per block
@@ -1741,49 +1538,33 @@ __global__ void __launch_bounds__(ST_THREADS) ba_stitch_kernel(const BADesc* __r
   }
 
   // ---- Schur complement system: H_sc = sum_i T_i G_i T_i^T with T_i[a,j] = d(a,i) AdH[i,j] + d(a,j) AdT[i,j]
+  // (G_i = dense symmetric Gram matrix of host i, ba_fold_sc_kernel)
   auto Gh = [&](int i) { return S.G + (size_t)i * LD * LD; };
   if (a < n && b < n) {
-    // H_sc = sum_i T_i G_i T_i^T is symmetric (every G_i is): block (b,a) is the transpose of block (a,b) and is
-    // written by the mirror block below
+    // H_sc is symmetric (every G_i is): block (b,a) is the transpose of block (a,b) and is written by the mirror store
     if (a > b) return;
     if (a == b) {   // sum_{j,k} AdH[a,j] D_a[j,k] AdH[a,k]^T   (AccumulatedSCHessian.cpp:108)
-      // D_a[k,j] = D_a[j,k]^T (one symmetric Gram matrix per host), so the (k,j) term is the transpose of (j,k)
       const double* G = Gh(a);
-      for (int j = 0; j < n; ++j) {
-        CONTRIB(AdH(a, j), AdH(a, j), [&](int x, int y) { return Gsym(G, LD, 8 * j + x, 8 * j + y); });
-        for (int k = j + 1; k < n; ++k) {
-          if ((ci % ST_WARPS) == warp)
-            sandwich_warp<true>(AdH(a, j), AdH(a, k), [&](int x, int y) { return Gsym(G, LD, 8 * j + x, 8 * k + y); },
-                                tmp[warp], lane, o0, o1);
-          ci++;
-        }
-      }
+      for (int j = 0; j < n; ++j)
+        for (int k = 0; k < n; ++k)
+          CONTRIB(AdH(a, j), AdH(a, k), G + (size_t)(8 * j) * LD + 8 * k, LD);
     }
     {   // :111  H[i,k] += AdH[ij] D AdT[ik]^T with i=a, k=b
       const double* G = Gh(a);
-      for (int j = 0; j < n; ++j)
-        CONTRIB(AdH(a, j), AdT(a, b), [&](int x, int y) { return Gsym(G, LD, 8 * j + x, 8 * b + y); });
+      for (int j = 0; j < n; ++j) CONTRIB(AdH(a, j), AdT(a, b), G + (size_t)(8 * j) * LD + 8 * b, LD);
     }
     {   // :110  H[j,i] += AdT[ij] D AdH[ik]^T with j=a, i=b
       const double* G = Gh(b);
-      for (int k = 0; k < n; ++k)
-        CONTRIB(AdT(b, a), AdH(b, k), [&](int x, int y) { return Gsym(G, LD, 8 * a + x, 8 * k + y); });
+      for (int k = 0; k < n; ++k) CONTRIB(AdT(b, a), AdH(b, k), G + (size_t)(8 * a) * LD + 8 * k, LD);
     }
     for (int i = 0; i < n; ++i) {   // :109  H[j,k] += AdT[ij] D AdT[ik]^T with j=a, k=b
       const double* G = Gh(i);
-      CONTRIB(AdT(i, a), AdT(i, b), [&](int x, int y) { return Gsym(G, LD, 8 * a + x, 8 * b + y); });
+      CONTRIB(AdT(i, a), AdT(i, b), G + (size_t)(8 * a) * LD + 8 * b, LD);
     }
-    const int r = lane & 7, c0 = lane >> 3;
-    part[warp][r + 8 * c0] = o0; part[warp][r + 8 * (c0 + 4)] = o1;
-    __syncthreads();
-    if (threadIdx.x < 64) {
-      const int rr = threadIdx.x & 7, cc = threadIdx.x >> 3;
-      double o = 0.0;
-#pragma unroll
-      for (int w = 0; w < ST_WARPS; ++w) o += part[w][threadIdx.x];
+    reduce_block([&](int rr, int cc, double o) {
       H[(size_t)(4 + 8 * a + rr) + (size_t)N * (4 + 8 * b + cc)] = o;
       if (a != b) H[(size_t)(4 + 8 * b + cc) + (size_t)N * (4 + 8 * a + rr)] = o;
-    }
+    });
   } else if (a < n && b == n) {
     if (threadIdx.x < 40) {   // :86-89: H[i,0:4] += AdH[ij] E[ij], H[j,0:4] += AdT[ij] E[ij]; b likewise with EB
       const int r = threadIdx.x & 7, c = threadIdx.x >> 3;
@@ -1794,14 +1575,14 @@ __global__ void __launch_bounds__(ST_THREADS) ba_stitch_kernel(const BADesc* __r
         for (int j = 0; j < n; ++j) {
           const double* A1 = AdH(a, j);
 #pragma unroll
-          for (int x = 0; x < 8; ++x) o += A1[r + 8 * x] * Gsym(G, LD, 8 * j + x, col);
+          for (int x = 0; x < 8; ++x) o += A1[r + 8 * x] * G[(size_t)(8 * j + x) * LD + col];
         }
       }
       for (int i = 0; i < n; ++i) {
         const double* G = Gh(i);
         const double* A1 = AdT(i, a);
 #pragma unroll
-        for (int x = 0; x < 8; ++x) o += A1[r + 8 * x] * Gsym(G, LD, 8 * a + x, col);
+        for (int x = 0; x < 8; ++x) o += A1[r + 8 * x] * G[(size_t)(8 * a + x) * LD + col];
       }
       if (c < 4) {
         H[(size_t)(4 + 8 * a + r) + (size_t)N * c] = o;
@@ -1814,7 +1595,7 @@ __global__ void __launch_bounds__(ST_THREADS) ba_stitch_kernel(const BADesc* __r
     if (threadIdx.x < 20) {
       const int r = threadIdx.x & 3, c = threadIdx.x >> 2;
       double o = 0.0;
-      for (int i = 0; i < n; ++i) o += Gsym(Gh(i), LD, 8 * n + r, 8 * n + c);
+      for (int i = 0; i < n; ++i) o += Gh(i)[(size_t)(8 * n + r) * LD + 8 * n + c];
       if (c < 4) H[(size_t)r + (size_t)N * c] = o; else bv[r] = o;
     }
   }
@@ -1838,6 +1619,14 @@ __global__ void ba_export_aos_kernel(const T* __restrict__ src, int comps, int c
   if (k >= count) return;
   size_t o = (size_t)sorted2orig[k] * comps;
   for (int c = 0; c < comps; ++c) dst[o + c] = src[(size_t)k * comps + c];
+}
+// JpJdF records (point-major slots) -> caller order [R][8]
+__global__ void ba_export_jpjd_kernel(BARes r, const int* __restrict__ sorted2orig, float* __restrict__ dst) {
+  int k = blockIdx.x * blockDim.x + threadIdx.x;
+  if (k >= r.R) return;
+  const float4* src = reinterpret_cast<const float4*>(r.JpJdF + r.slotpos[k]);
+  float4* d = reinterpret_cast<float4*>(dst + 8 * (size_t)sorted2orig[k]);
+  d[0] = src[0]; d[1] = src[1];
 }
 // Re-grouping of the sorted residual order (a residual became linearised: it moves behind the non-linearised ones of its
 // pair): dst[c][k] = src[c][perm[k]] for component-major arrays (grid.y = component), and the same for records.
@@ -1918,7 +1707,7 @@ __global__ void __launch_bounds__(128) ba_resub_kernel(const BADesc* __restrict_
       int pair = r.pair[k], t = (pair * D.W.n_rcp) >> 16, h = pair - t * n;
       const float* xa = xAd + 8 * (n * h + t);
       float d = 0.f;
-      const float4* jp = reinterpret_cast<const float4*>(r.JpJdF + 8 * (size_t)k);
+      const float4* jp = reinterpret_cast<const float4*>(r.JpJdF + (size_t)p * r.pstr + 8 * (i - rb));   // slot order = the point's own order
       const float4 j0 = jp[0], j1 = jp[1];
       const float jv[8] = {j0.x, j0.y, j0.z, j0.w, j1.x, j1.y, j1.z, j1.w};
 #pragma unroll
