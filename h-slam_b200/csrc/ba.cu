@@ -212,21 +212,22 @@ static hs_encode_tiled_fn hs_encode_tiled() {
   }();
   return fn;
 }
-// J[JS][rs] as a 2-D tensor (inner = residual); box = TOP_ROW residuals x `rows` component rows
-static bool encode_J_map(CUtensorMap* out, float* J, int rs, int rows) {
+// A component-major per-residual array [nrows][rs] as a 2-D tensor (inner = residual); box = TOP_ROW residuals x `rows` rows
+static bool encode_rows_map(CUtensorMap* out, float* base, int rs, int nrows, int rows) {
   hs_encode_tiled_fn fn = hs_encode_tiled();
-  if (!fn || !J) return false;
-  const cuuint64_t gdim[2] = {(cuuint64_t)rs, (cuuint64_t)JS};
+  if (!fn || !base) return false;
+  const cuuint64_t gdim[2] = {(cuuint64_t)rs, (cuuint64_t)nrows};
   const cuuint64_t gstride[1] = {(cuuint64_t)rs * sizeof(float)};
   const cuuint32_t box[2] = {(cuuint32_t)TOP_ROW, (cuuint32_t)rows};
   const cuuint32_t estr[2] = {1, 1};
-  return fn(out, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, J, gdim, gstride, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+  return fn(out, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, base, gdim, gstride, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
             CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
 }
 
 static void fill_desc(hslam_ba* ba) {
   BADesc& D = ba->hdesc;
-  ba->tmap_ok = ba->R == 0 || (encode_J_map(&D.tmapJ[0], ba->d_J.p, ba->rs, 22) && encode_J_map(&D.tmapJ[1], ba->d_J.p, ba->rs, 17));
+  ba->tmap_ok = ba->R == 0 || (encode_rows_map(&D.tmapJ[0], ba->d_J.p, ba->rs, JS, 22) && encode_rows_map(&D.tmapJ[1], ba->d_J.p, ba->rs, JS, 17) &&
+                               encode_rows_map(&D.tmapJ[2], ba->d_J.p, ba->rs, JS, TOP_NJ_L) && encode_rows_map(&D.tmapJ[3], ba->d_rtz.p, ba->rs, 8, 8));
   BARes& r = D.r;
   r.R = ba->R; r.rs = ba->rs;
   r.point = ba->d_rpoint.p; r.pair = ba->d_rpair.p;
@@ -791,7 +792,7 @@ static int launch_linearize(hslam_ba* ba, bool apply) {
   return 0;
 }
 
-static const size_t kTopSmem = TOP_STAGES * sizeof(TopStage) + 128;   // + alignment slack (TMA destinations)
+static const size_t kTopSmem = std::max(TOP_STAGES * sizeof(TopStage), TOP_STAGES_L * sizeof(TopStageL)) + 128;   // + alignment slack (TMA destinations)
 static int top_attr(hslam_ctx* ctx) {
   bool& done = ctx->top_attr_done;
   if (!done) {

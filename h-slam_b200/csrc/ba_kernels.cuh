@@ -20,6 +20,7 @@
 #pragma once
 #include <cuda.h>   // CUtensorMap (type only: the encoder is fetched through cudaGetDriverEntryPoint)
 #include "common.cuh"
+#include <type_traits>
 
 namespace hs {
 
@@ -89,7 +90,7 @@ struct BARes {               // per-residual SoA, sorted by (host,target) pair, 
   float* newEnergyWO;
   float* J;                  // [JS][rs]
   const int* slotpos;        // float offset of the residual's 32-byte records in JpJdF / prec: point * pstr + 8 * slot
-  int pstr;                  // floats per point in the record arrays: 8 * maxres + 4 (the pad keeps shared-memory reads conflict-free)
+  int pstr;                  // floats per point in the record arrays: 8 * (maxres + 1), see sc_pstr
   float* JpJdF;              // [P][pstr]: one 32-byte record per (point, residual slot), in the point's own order: the Schur
                              // kernel and the back-substitution read a point's residuals as ONE contiguous span
   float* prec;               // [P][pstr]: per (point, slot) {bd, Hdd, Hcd[4], flag (0 inactive / 1 active A / 2 active L), target}:
@@ -166,7 +167,7 @@ struct BADesc {
   float* xAd;                // [n*n][8] per-pair adjoint-mapped frame steps (EnergyFunctional.cpp:236-238)
   // 2-D tensor maps over the SoA Jacobian J[JS][rs] (inner dimension = residual): boxes of TOP_ROW residuals x 22 rows
   // (rows 8..29) and x 17 rows (rows 62..78): the two TMA loads that fill one stage of the top kernel's ring
-  alignas(64) CUtensorMap tmapJ[2];
+  alignas(64) CUtensorMap tmapJ[4];   // [2]: J rows 8..78 (mode L box of 71 rows), [3]: res_toZeroF[8][rs] (box of 8 rows)
 };
 
 // Per-window byte offsets into the batch staging blocks (one H2D block `up`, one D2H block `dn`);
@@ -452,8 +453,7 @@ __global__ void __launch_bounds__(LIN_THREADS, LIN_MINB) ba_linearize_kernel(con
                 for (int i = 0; i < 6; ++i) o[i] = xadd(xmul(HS_XI0(i), JJ0), xmul(HS_XI1(i), JJ1));
                 o[6] = xadd(xmul(AI00, ddx), xmul(AI01, ddy));
                 o[7] = xadd(xmul(AI10, ddx), xmul(AI11, ddy));
-                float4* dst = reinterpret_cast<float4*>(r.JpJdF + sp);   // one 32-byte record, in the point's slot
-                dst[0] = make_float4(o[0], o[1], o[2], o[3]); dst[1] = make_float4(o[4], o[5], o[6], o[7]);
+                stg256(r.JpJdF + sp, make_float4(o[0], o[1], o[2], o[3]), make_float4(o[4], o[5], o[6], o[7]));   // one 32-byte record, in the point's slot
               } else {
                 r.isActive[k] = 0;
               }
@@ -728,20 +728,20 @@ __device__ __forceinline__ void top_accumulate(const BADesc& D, const TopChunk& 
       }
       acc[30] += AA00; acc[31] += AA01; acc[32] += Jabr0; acc[33] += AA11; acc[34] += Jabr1; acc[35] += rr;
       const float tgt = (float)((ch.pair * W.n_rcp) >> 16);
-      float4* o = reinterpret_cast<float4*>(r.prec + r.slotpos[k]);   // the residual's 32-byte record in its point's slot
+      float* o = r.prec + r.slotpos[k];   // the residual's 32-byte record in its point's slot
       if (!use) {
         // modes A / L own every residual of their tiles: an inactive one gets a record that says so.  The
         // marginalisation pass (2) leaves the records of the points it does not touch alone.
-        if (MODE != 2) { o[0] = make_float4(0.f, 0.f, 0.f, 0.f); o[1] = make_float4(0.f, 0.f, 0.f, tgt); }
+        if (MODE != 2) stg256(o, make_float4(0.f, 0.f, 0.f, 0.f), make_float4(0.f, 0.f, 0.f, tgt));
         continue;
       }
       nres++;
       // per-residual contribution to the point sums (:114-117), exact ops: they are summed per point in
       // the point's own order by the Schur kernel, which keeps Hdd/bd/Hcd bit-identical to the oracle.
       float Ji0 = xadd(xmul(a, d0), xmul(b, d1)), Ji1 = xadd(xmul(b, d0), xmul(c, d1));
-      o[0] = make_float4(xadd(xmul(JIr0, d0), xmul(JIr1, d1)), xadd(xmul(Ji0, d0), xmul(Ji1, d1)),
-                         xadd(xmul(x[0], Ji0), xmul(y[0], Ji1)), xadd(xmul(x[1], Ji0), xmul(y[1], Ji1)));
-      o[1] = make_float4(xadd(xmul(x[2], Ji0), xmul(y[2], Ji1)), xadd(xmul(x[3], Ji0), xmul(y[3], Ji1)), lin ? 2.f : 1.f, tgt);
+      stg256(o, make_float4(xadd(xmul(JIr0, d0), xmul(JIr1, d1)), xadd(xmul(Ji0, d0), xmul(Ji1, d1)),
+                            xadd(xmul(x[0], Ji0), xmul(y[0], Ji1)), xadd(xmul(x[1], Ji0), xmul(y[1], Ji1))),
+             make_float4(xadd(xmul(x[2], Ji0), xmul(y[2], Ji1)), xadd(xmul(x[3], Ji0), xmul(y[3], Ji1)), lin ? 2.f : 1.f, tgt));
     }
   }
 }
@@ -815,19 +815,28 @@ __device__ __forceinline__ void bulk_g2s(void* dst, const void* src, unsigned by
 constexpr int TOP_STAGES = 4;
 constexpr int TOP_ROW = 136;
 constexpr int TOP_FROW = 160;   // flag rows: the 16-byte-aligned span that covers a tile, <= 128 + 15 + 15 bytes
-struct alignas(128) TopStage {
-  float v[TOP_NR][TOP_ROW];
+template <int NR> struct alignas(128) TopStageT {
+  float v[NR][TOP_ROW];
   unsigned char lin[TOP_FROW], act[TOP_FROW];
   int sp[TOP_ROW];           // slotpos of the tile's residuals (same 4-aligned span as the Jacobian rows)
 };
+using TopStage = TopStageT<TOP_NR>;
 static_assert(sizeof(TopStage) % 128 == 0 && (24 * TOP_ROW * 4) % 128 == 0, "TMA box destinations are 128-byte aligned");
+// Mode L (linearised residuals) stages J rows 8..78 in stage rows 0..70 (one tensor-map box of 71 rows: the geometric
+// rows, the per-pixel rows JIdx / JabF and the 2x2 sums) and res_toZeroF in rows 72..79 (a second box): 80 rows.
+constexpr int TL_XI0 = 0, TL_XI1 = 6, TL_C0 = 12, TL_C1 = 16, TL_DD = 20, TL_IDX0 = 22, TL_IDX1 = 30, TL_AB0 = 38, TL_AB1 = 46,
+              TL_IDX2 = 54, TL_ABIDX = 58, TL_AB2 = 62, TL_RTZ = 72;
+constexpr int TOP_NR_L = 80, TOP_NJ_L = 71;
+using TopStageL = TopStageT<TOP_NR_L>;
+static_assert(sizeof(TopStageL) % 128 == 0 && (TL_RTZ * TOP_ROW * 4) % 128 == 0, "TMA box destinations are 128-byte aligned");
+constexpr int TOP_STAGES_L = 2;
 
 // packed index of the 91 accumulators -> (row, col), row <= col, of the 13x13 block [C(4); xi(6); a, b; r]:
 // 0..54 the row-major upper triangle of the 10x10, 55..84 the 10x3 top-right, 85..90 the upper triangle of the 3x3
 __device__ __forceinline__ void top_unpack_index(int t, int& r, int& c) {
   if (t < 55) { r = 0; while (t >= 10 - r) { t -= 10 - r; ++r; } c = r + t; }
   else if (t < 85) { r = (t - 55) / 3; c = 10 + (t - 55) % 3; }
-  else { const int m[6][2] = {{10, 10}, {10, 11}, {10, 12}, {11, 11}, {11, 12}, {12, 12}}; r = m[t - 85][0]; c = m[t - 85][1]; }
+  else { const int u = t - 85; r = u < 3 ? 10 : (u < 5 ? 11 : 12); c = u < 3 ? 10 + u : (u < 5 ? 8 + u : 12); }
 }
 // chunk partial -> global, then the per-(mode,pair) fold by the last block of that pair (chunks in index order)
 __device__ __forceinline__ void top_flush(const BADesc& D, int chunk, int part, float (&acc)[56], int nres,
@@ -897,19 +906,61 @@ __device__ __forceinline__ void top_flush(const BADesc& D, int chunk, int part, 
   __syncthreads();   // `last` and `red` are reused by the next chunk
 }
 
+// 10x10 upper triangle of [x y] [[a b],[b c]] [x y]^T into acc[0..54] (PART 0 threads).  Packed fp32 (FMUL2 / FFMA2 /
+// FADD2): two neighbouring columns per instruction, every lane rounded exactly like  acc += fmaf(x, px, y * py).
+__device__ __forceinline__ void top_acc_part0(float (&acc)[56], const float (&x)[10], const float (&y)[10], float a, float b, float c) {
+  float2* acc2 = reinterpret_cast<float2*>(acc);
+  int idx = 0;
+#pragma unroll
+  for (int rI = 0; rI < 10; ++rI) {
+    const float px = fmaf(a, x[rI], b * y[rI]), py = fmaf(b, x[rI], c * y[rI]);
+    int cI = rI;
+    if (idx & 1) { acc[idx] += fmaf(x[cI], px, y[cI] * py); ++cI; ++idx; }
+    const float2 px2 = make_float2(px, px), py2 = make_float2(py, py);
+#pragma unroll
+    for (; cI + 1 < 10; cI += 2, idx += 2) {
+      const float2 t = __fmul2_rn(make_float2(y[cI], y[cI + 1]), py2);
+      const float2 u = __ffma2_rn(make_float2(x[cI], x[cI + 1]), px2, t);
+      acc2[idx >> 1] = __fadd2_rn(acc2[idx >> 1], u);
+    }
+    if (cI < 10) { acc[idx] += fmaf(x[cI], px, y[cI] * py); ++idx; }
+  }
+}
+// 10x3 top-right (columns a, b, r; MatrixAccumulators.h:859-901) into acc[0..29] and the 3x3 bottom-right into acc[30..35]
+// (PART 1 threads); packed: two rows (six accumulators) as three float2 triplets, each lane rounded like the scalar sequence.
+__device__ __forceinline__ void top_acc_part1(float (&acc)[56], const float (&x)[10], const float (&y)[10], float AI00, float AI10,
+                                              float AI01, float AI11, float JIr0, float JIr1, float AA00, float AA01, float AA11,
+                                              float Jabr0, float Jabr1, float rr) {
+  float2* acc2 = reinterpret_cast<float2*>(acc);
+  const float2 A0 = make_float2(AI00, AI10), B0 = make_float2(AI01, AI11);
+  const float2 A1 = make_float2(JIr0, AI00), B1 = make_float2(JIr1, AI01);
+  const float2 A2 = make_float2(AI10, JIr0), B2 = make_float2(AI11, JIr1);
+#pragma unroll
+  for (int q = 0; q < 5; ++q) {
+    const float xr = x[2 * q], yr = y[2 * q], xs = x[2 * q + 1], ys = y[2 * q + 1];
+    acc2[3 * q + 0] = __fadd2_rn(acc2[3 * q + 0], __ffma2_rn(make_float2(xr, xr), A0, __fmul2_rn(make_float2(yr, yr), B0)));
+    acc2[3 * q + 1] = __fadd2_rn(acc2[3 * q + 1], __ffma2_rn(make_float2(xr, xs), A1, __fmul2_rn(make_float2(yr, ys), B1)));
+    acc2[3 * q + 2] = __fadd2_rn(acc2[3 * q + 2], __ffma2_rn(make_float2(xs, xs), A2, __fmul2_rn(make_float2(ys, ys), B2)));
+  }
+  acc[30] += AA00; acc[31] += AA01; acc[32] += Jabr0; acc[33] += AA11; acc[34] += Jabr1; acc[35] += rr;
+}
+
 template <int MODE>
 __global__ void __launch_bounds__(2 * TOP_THREADS, 2) ba_top_kernel(const BADesc* __restrict__ descs,
                                                                     const int* __restrict__ prefix, int nwin) {
   extern __shared__ __align__(128) unsigned char top_smem[];
+  // modes A and L run on the staging ring (L with wider, fewer stages), the marginalisation pass on the direct path
+  using Stage = typename std::conditional<MODE == 1, TopStageL, TopStage>::type;
+  constexpr int STAGES = MODE == 1 ? TOP_STAGES_L : TOP_STAGES;
+  constexpr bool RING = MODE != 2;
   // 128-byte alignment in the shared window (the launch reserves 128 spare bytes)
-  TopStage* ring = reinterpret_cast<TopStage*>(top_smem + ((128u - (smem_u32(top_smem) & 127u)) & 127u));
+  Stage* ring = reinterpret_cast<Stage*>(top_smem + ((128u - (smem_u32(top_smem) & 127u)) & 127u));
   __shared__ float red[92][33];   // [accumulator][4 warps x 8 lanes], padded: conflict-free both ways
   __shared__ bool last;
   int lb;
   const int win = find_window(prefix, nwin, blockIdx.x, lb);
   const BADesc& D = descs[win];
   const BARes& r = D.r;
-  const int s = r.rs;
   constexpr int mode = MODE;   // every mode has its own tile schedule: A over the non-linearised residuals, L over the
                                // linearised ones, marginalisation (2) over all of them
   const TopSched& SC = D.sched[MODE];
@@ -923,21 +974,21 @@ __global__ void __launch_bounds__(2 * TOP_THREADS, 2) ba_top_kernel(const BADesc
   for (int i = 0; i < 56; ++i) acc[i] = 0.f;
   int nres = 0, cur = -1;
 
-  // Mode A: the 39 component rows of a tile are 39 contiguous 544-byte spans of the SoA Jacobian: one bulk copy
-  // (TMA engine) each, completing on the stage's `full` mbarrier.  The warps take turns as producer (warp j & 7
-  // issues tile j + TOP_DEPTH, lanes in parallel), every warp releases a stage on its `empty` mbarrier when it has
+  // The component rows of a tile are contiguous spans of the SoA Jacobian: TMA tensor-map loads into one stage of a
+  // shared-memory ring, completing on the stage's `full` mbarrier.  The warps take turns as producer (warp j & 7
+  // issues tile j + DEPTH, lanes in parallel), every warp releases a stage on its `empty` mbarrier when it has
   // read its residuals: no block-wide barrier in the tile loop, a warp only ever waits for data.
 #ifndef TOP_DEPTH_
 #define TOP_DEPTH_ (TOP_STAGES - 2)
 #endif
-  constexpr int TOP_DEPTH = TOP_DEPTH_;   // S-2: the refilled stage was consumed two tiles ago, its release is old news
+  constexpr int DEPTH = MODE == 1 ? 1 : TOP_DEPTH_;   // S-2: the refilled stage was consumed two tiles ago, its release is old news
   constexpr int NW = 2 * TOP_THREADS / 32;
   __shared__ __align__(8) uint64_t full_bar[TOP_STAGES], empty_bar[TOP_STAGES];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  if (mode == 0) {
+  if (RING) {
     if (threadIdx.x == 0) {
 #pragma unroll
-      for (int i = 0; i < TOP_STAGES; ++i) { mbar_init(&full_bar[i], 1); mbar_init(&empty_bar[i], NW); }
+      for (int i = 0; i < STAGES; ++i) { mbar_init(&full_bar[i], 1); mbar_init(&empty_bar[i], NW); }
       asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
       asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
     }
@@ -946,25 +997,34 @@ __global__ void __launch_bounds__(2 * TOP_THREADS, 2) ba_top_kernel(const BADesc
   auto produce = [&](int jp) {   // called by one whole warp
     const int tp = t0 + jp;
     if (tp >= t1) return;
-    const int stg = jp % TOP_STAGES, use = jp / TOP_STAGES;
+    const int stg = jp % STAGES, use = jp / STAGES;
     if (use > 0) mbar_wait(&empty_bar[stg], (unsigned)(use - 1) & 1u);
-    if (lane == 0) mbar_expect_tx(&full_bar[stg], TOP_NC * TOP_ROW * 4 + 2 * TOP_FROW + TOP_ROW * 4);
+    constexpr unsigned jbytes = (MODE == 1 ? (TOP_NJ_L + 8) : TOP_NC) * TOP_ROW * 4;
+    if (lane == 0) mbar_expect_tx(&full_bar[stg], jbytes + 2 * TOP_FROW + TOP_ROW * 4);
     __syncwarp();
     const TopTile tlp = toptiles[tp];
-    TopStage& st = ring[stg];
-    // the two flag rows ride along (a consumer that loaded them itself had a DRAM round trip on its critical path)
+    Stage& st = ring[stg];
+    // the two flag rows and the record positions ride along (a consumer that loaded them itself had a DRAM round trip
+    // on its critical path)
     if (lane == 2) bulk_g2s(st.lin, r.isLin + (tlp.start & ~15), TOP_FROW, &full_bar[stg]);
     else if (lane == 3) bulk_g2s(st.act, r.isActive + (tlp.start & ~15), TOP_FROW, &full_bar[stg]);
     else if (lane == 4) bulk_g2s(st.sp, r.slotpos + (tlp.start & ~3), TOP_ROW * 4, &full_bar[stg]);
-    // two tensor-map loads per stage: the TMA unit serves one request in ~46 cycles whatever its size, 39 row copies
-    // per 21 kB stage made the kernel TMA-issue-bound (3.4 TB/s)
-    if (lane == 0) tma_load_2d(&st.v[0][0], &D.tmapJ[0], tlp.start & ~3, J_XI0, &full_bar[stg]);
-    else if (lane == 1) tma_load_2d(&st.v[24][0], &D.tmapJ[1], tlp.start & ~3, J_IDX2, &full_bar[stg]);
+    // two tensor-map loads per stage: the TMA unit serves one request in ~46 cycles whatever its size, one bulk copy
+    // per component row made the kernel TMA-issue-bound (3.4 TB/s)
+    if (MODE == 1) {
+      if (lane == 0) tma_load_2d(&st.v[0][0], &D.tmapJ[2], tlp.start & ~3, J_XI0, &full_bar[stg]);
+      else if (lane == 1) tma_load_2d(&st.v[TL_RTZ][0], &D.tmapJ[3], tlp.start & ~3, 0, &full_bar[stg]);
+    } else {
+      if (lane == 0) tma_load_2d(&st.v[0][0], &D.tmapJ[0], tlp.start & ~3, J_XI0, &full_bar[stg]);
+      else if (lane == 1) tma_load_2d(&st.v[24][0], &D.tmapJ[1], tlp.start & ~3, J_IDX2, &full_bar[stg]);
+    }
   };
-  if (mode == 0 && warp == 0) {
+  if (RING && warp == 0) {
 #pragma unroll
-    for (int i = 0; i < TOP_DEPTH; ++i) produce(i);
+    for (int i = 0; i < DEPTH; ++i) produce(i);
   }
+  float dp[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};   // mode L: adHTdeltaF of the current tile's pair
+  int dp_pair = -1;
 
   TopTile tl_next = t0 < t1 ? toptiles[t0] : TopTile{0, 0, 0, 0};
   for (int t = t0; t < t1; ++t) {
@@ -981,105 +1041,84 @@ __global__ void __launch_bounds__(2 * TOP_THREADS, 2) ba_top_kernel(const BADesc
       }
       cur = chunk;
     }
-    if (mode != 0) {
-      const TopChunk ch = {D.topchunks[chunk].pair, tl.start, tl.count, 1};
+    if (!RING) {
+      const TopChunk ch = {tl.pair, tl.start, tl.count, 1};
       if (part == 0) top_accumulate<(MODE ? MODE : 1), 0>(D, ch, acc, nres); else top_accumulate<(MODE ? MODE : 1), 1>(D, ch, acc, nres);
       continue;
     }
-    if (warp == (j & (NW - 1))) produce(j + TOP_DEPTH);
-    mbar_wait(&full_bar[j % TOP_STAGES], (unsigned)(j / TOP_STAGES) & 1u);
-    const TopStage& S = ring[j % TOP_STAGES];
+    if (warp == (j & (NW - 1))) produce(j + DEPTH);
+    // mode L: what does not come through the ring is requested before the wait (its latency hides behind the stage's)
+    float dd = 0.f;
+    if (MODE == 1 && part == 1) {
+      if (l < tl.count) dd = D.p.deltaF[r.point[tl.start + l]];
+      if (tl.pair != dp_pair) {
+        dp_pair = tl.pair;
+#pragma unroll
+        for (int q = 0; q < 8; ++q) dp[q] = __ldg(D.W.adHTdeltaF + 8 * tl.pair + q);
+      }
+    }
+    mbar_wait(&full_bar[j % STAGES], (unsigned)(j / STAGES) & 1u);
+    const Stage& S = ring[j % STAGES];
     const int col = (tl.start & 3) + l, cf = (tl.start & 15) + l;
-    // AccumulatedTopHessian.cpp:37-49, mode 0: !isLinearized && isActive
-    if (l < tl.count && S.lin[cf] == 0 && S.act[cf] != 0) {
+    constexpr int RC0 = MODE == 1 ? TL_C0 : TS_C0, RC1 = MODE == 1 ? TL_C1 : TS_C1, RXI0 = MODE == 1 ? TL_XI0 : TS_XI0,
+                  RXI1 = MODE == 1 ? TL_XI1 : TS_XI1, RIDX2 = MODE == 1 ? TL_IDX2 : TS_IDX2, RABIDX = MODE == 1 ? TL_ABIDX : TS_ABIDX,
+                  RAB2 = MODE == 1 ? TL_AB2 : TS_AB2, RDD = MODE == 1 ? TL_DD : TS_DD;
+    // AccumulatedTopHessian.cpp:37-49: mode 0 = !isLinearized && isActive, mode 1 = isLinearized && isActive
+    if (l < tl.count && (S.lin[cf] != 0) == (MODE == 1) && S.act[cf] != 0) {
       float x[10], y[10];
 #pragma unroll
-      for (int j = 0; j < 4; ++j) { x[j] = S.v[TS_C0 + j][col]; y[j] = S.v[TS_C1 + j][col]; }
+      for (int q = 0; q < 4; ++q) { x[q] = S.v[RC0 + q][col]; y[q] = S.v[RC1 + q][col]; }
 #pragma unroll
-      for (int j = 0; j < 6; ++j) { x[4 + j] = S.v[TS_XI0 + j][col]; y[4 + j] = S.v[TS_XI1 + j][col]; }
-      const float a = S.v[TS_IDX2 + 0][col], b = S.v[TS_IDX2 + 2][col], c = S.v[TS_IDX2 + 3][col];
+      for (int q = 0; q < 6; ++q) { x[4 + q] = S.v[RXI0 + q][col]; y[4 + q] = S.v[RXI1 + q][col]; }
+      const float a = S.v[RIDX2 + 0][col], b = S.v[RIDX2 + 2][col], c = S.v[RIDX2 + 3][col];
       if (part == 0) {
-        // 10x10 upper triangle: [x y] [[a b],[b c]] [x y]^T
-#ifndef TOP_FFMA2
-#define TOP_FFMA2 1
-#endif
-#if TOP_FFMA2
-        // packed fp32 (FMUL2 / FFMA2 / FADD2): two neighbouring columns per instruction, every lane rounded exactly
-        // like the scalar sequence  acc += fmaf(x, px, y * py)
-        float2* acc2 = reinterpret_cast<float2*>(acc);
-        int idx = 0;
-#pragma unroll
-        for (int rI = 0; rI < 10; ++rI) {
-          const float px = fmaf(a, x[rI], b * y[rI]), py = fmaf(b, x[rI], c * y[rI]);
-          int cI = rI;
-          if (idx & 1) { acc[idx] += fmaf(x[cI], px, y[cI] * py); ++cI; ++idx; }
-          const float2 px2 = make_float2(px, px), py2 = make_float2(py, py);
-#pragma unroll
-          for (; cI + 1 < 10; cI += 2, idx += 2) {
-            const float2 t = __fmul2_rn(make_float2(y[cI], y[cI + 1]), py2);
-            const float2 u = __ffma2_rn(make_float2(x[cI], x[cI + 1]), px2, t);
-            acc2[idx >> 1] = __fadd2_rn(acc2[idx >> 1], u);
-          }
-          if (cI < 10) { acc[idx] += fmaf(x[cI], px, y[cI] * py); ++idx; }
-        }
-#else
-        int idx = 0;
-#pragma unroll
-        for (int rI = 0; rI < 10; ++rI) {
-          float px = fmaf(a, x[rI], b * y[rI]), py = fmaf(b, x[rI], c * y[rI]);
-#pragma unroll
-          for (int cI = rI; cI < 10; ++cI, ++idx) acc[idx] += fmaf(x[cI], px, y[cI] * py);
-        }
-#endif
+        top_acc_part0(acc, x, y, a, b, c);
       } else {
-        const float AI00 = S.v[TS_ABIDX + 0][col], AI10 = S.v[TS_ABIDX + 1][col], AI01 = S.v[TS_ABIDX + 2][col],
-                    AI11 = S.v[TS_ABIDX + 3][col];
-        const float AA00 = S.v[TS_AB2 + 0][col], AA01 = S.v[TS_AB2 + 2][col], AA11 = S.v[TS_AB2 + 3][col];
-        const float JIr0 = S.v[TS_JIR][col], JIr1 = S.v[TS_JIR + 1][col], Jabr0 = S.v[TS_JABR][col], Jabr1 = S.v[TS_JABR + 1][col];
-        const float rr = S.v[TS_RR][col], d0 = S.v[TS_DD][col], d1 = S.v[TS_DD + 1][col];
-        // 10x3 top-right: columns a, b, r  (MatrixAccumulators.h:859-901); entries 55..84 -> acc[0..29]
-#if TOP_FFMA2
-        // packed: two rows (six accumulators) as three float2 triplets, each lane rounded like the scalar sequence
-        {
-          float2* acc2 = reinterpret_cast<float2*>(acc);
-          const float2 A0 = make_float2(AI00, AI10), B0 = make_float2(AI01, AI11);
-          const float2 A1 = make_float2(JIr0, AI00), B1 = make_float2(JIr1, AI01);
-          const float2 A2 = make_float2(AI10, JIr0), B2 = make_float2(AI11, JIr1);
+        const float AI00 = S.v[RABIDX + 0][col], AI10 = S.v[RABIDX + 1][col], AI01 = S.v[RABIDX + 2][col], AI11 = S.v[RABIDX + 3][col];
+        const float AA00 = S.v[RAB2 + 0][col], AA01 = S.v[RAB2 + 2][col], AA11 = S.v[RAB2 + 3][col];
+        const float d0 = S.v[RDD][col], d1 = S.v[RDD + 1][col];
+        float JIr0, JIr1, Jabr0, Jabr1, rr;
+        if (MODE == 1) {
+          // resApprox = res_toZeroF + J*delta, AccumulatedTopHessian.cpp:63-81 (sequential sums)
+          float dx = 0.f, dy = 0.f, cxs = 0.f, cys = 0.f;
 #pragma unroll
-          for (int q = 0; q < 5; ++q) {
-            const float xr = x[2 * q], yr = y[2 * q], xs = x[2 * q + 1], ys = y[2 * q + 1];
-            acc2[3 * q + 0] = __fadd2_rn(acc2[3 * q + 0], __ffma2_rn(make_float2(xr, xr), A0, __fmul2_rn(make_float2(yr, yr), B0)));
-            acc2[3 * q + 1] = __fadd2_rn(acc2[3 * q + 1], __ffma2_rn(make_float2(xr, xs), A1, __fmul2_rn(make_float2(yr, ys), B1)));
-            acc2[3 * q + 2] = __fadd2_rn(acc2[3 * q + 2], __ffma2_rn(make_float2(xs, xs), A2, __fmul2_rn(make_float2(ys, ys), B2)));
+          for (int q = 0; q < 6; ++q) { dx = xadd(dx, xmul(x[4 + q], dp[q])); dy = xadd(dy, xmul(y[4 + q], dp[q])); }
+#pragma unroll
+          for (int q = 0; q < 4; ++q) { cxs = xadd(cxs, xmul(x[q], D.W.cDeltaF[q])); cys = xadd(cys, xmul(y[q], D.W.cDeltaF[q])); }
+          const float Jpx = xadd(xadd(dx, cxs), xmul(d0, dd)), Jpy = xadd(xadd(dy, cys), xmul(d1, dd));
+          JIr0 = JIr1 = Jabr0 = Jabr1 = rr = 0.f;
+#pragma unroll
+          for (int q = 0; q < 8; ++q) {
+            const float i0 = S.v[TL_IDX0 + q][col], i1 = S.v[TL_IDX1 + q][col], a0 = S.v[TL_AB0 + q][col], a1 = S.v[TL_AB1 + q][col];
+            float rz = S.v[TL_RTZ + q][col];
+            rz = xadd(rz, xmul(i0, Jpx)); rz = xadd(rz, xmul(i1, Jpy));
+            rz = xadd(rz, xmul(a0, dp[6])); rz = xadd(rz, xmul(a1, dp[7]));
+            JIr0 = xadd(JIr0, xmul(rz, i0)); JIr1 = xadd(JIr1, xmul(rz, i1));
+            Jabr0 = xadd(Jabr0, xmul(rz, a0)); Jabr1 = xadd(Jabr1, xmul(rz, a1));
+            rr = xadd(rr, xmul(rz, rz));
           }
+        } else {
+          JIr0 = S.v[TS_JIR][col]; JIr1 = S.v[TS_JIR + 1][col]; Jabr0 = S.v[TS_JABR][col]; Jabr1 = S.v[TS_JABR + 1][col];
+          rr = S.v[TS_RR][col];
         }
-#else
-#pragma unroll
-        for (int rI = 0; rI < 10; ++rI) {
-          acc[3 * rI + 0] += fmaf(x[rI], AI00, y[rI] * AI01);
-          acc[3 * rI + 1] += fmaf(x[rI], AI10, y[rI] * AI11);
-          acc[3 * rI + 2] += fmaf(x[rI], JIr0, y[rI] * JIr1);
-        }
-#endif
-        acc[30] += AA00; acc[31] += AA01; acc[32] += Jabr0; acc[33] += AA11; acc[34] += Jabr1; acc[35] += rr;
+        top_acc_part1(acc, x, y, AI00, AI10, AI01, AI11, JIr0, JIr1, AA00, AA01, AA11, Jabr0, Jabr1, rr);
         nres++;
         // per-residual contribution to the point sums (:114-117), exact ops: they are summed per point in
         // the point's own order by the Schur kernel, which keeps Hdd/bd/Hcd bit-identical to the oracle.
         const float Ji0 = xadd(xmul(a, d0), xmul(b, d1)), Ji1 = xadd(xmul(b, d0), xmul(c, d1));
-        float4* o = reinterpret_cast<float4*>(r.prec + S.sp[col]);   // the residual's 32-byte record in its point's slot
-        o[0] = make_float4(xadd(xmul(JIr0, d0), xmul(JIr1, d1)), xadd(xmul(Ji0, d0), xmul(Ji1, d1)),
-                           xadd(xmul(x[0], Ji0), xmul(y[0], Ji1)), xadd(xmul(x[1], Ji0), xmul(y[1], Ji1)));
-        o[1] = make_float4(xadd(xmul(x[2], Ji0), xmul(y[2], Ji1)), xadd(xmul(x[3], Ji0), xmul(y[3], Ji1)), 1.f,
-                           (float)((tl.pair * D.W.n_rcp) >> 16));
+        // the residual's 32-byte record in its point's slot: one 256-bit store
+        stg256(r.prec + S.sp[col],
+               make_float4(xadd(xmul(JIr0, d0), xmul(JIr1, d1)), xadd(xmul(Ji0, d0), xmul(Ji1, d1)),
+                           xadd(xmul(x[0], Ji0), xmul(y[0], Ji1)), xadd(xmul(x[1], Ji0), xmul(y[1], Ji1))),
+               make_float4(xadd(xmul(x[2], Ji0), xmul(y[2], Ji1)), xadd(xmul(x[3], Ji0), xmul(y[3], Ji1)), MODE == 1 ? 2.f : 1.f,
+                           (float)((tl.pair * D.W.n_rcp) >> 16)));
       }
     } else if (part == 1 && l < tl.count) {
       // inactive residual: its record says so (the Schur kernel and the point sums skip it)
-      float4* o = reinterpret_cast<float4*>(r.prec + S.sp[col]);
-      o[0] = make_float4(0.f, 0.f, 0.f, 0.f);
-      o[1] = make_float4(0.f, 0.f, 0.f, (float)((tl.pair * D.W.n_rcp) >> 16));
+      stg256(r.prec + S.sp[col], make_float4(0.f, 0.f, 0.f, 0.f), make_float4(0.f, 0.f, 0.f, (float)((tl.pair * D.W.n_rcp) >> 16)));
     }
     __syncwarp();
-    if (lane == 0) mbar_arrive(&empty_bar[j % TOP_STAGES]);   // this warp is done with the stage
+    if (lane == 0) mbar_arrive(&empty_bar[j % STAGES]);   // this warp is done with the stage
   }
   if (cur >= 0) top_flush(D, cur, part, acc, nres, red, &last);
 }
@@ -1137,7 +1176,9 @@ __device__ __forceinline__ void tri_decode(int t, int NT, int& ti, int& tj) {
 // point has no residual into its host).  Each tile is owned by TWO threads (tid and tid+128), one for the even and one
 // for the odd points of the sub-tile.  MAXT = tiles per thread: (NT-2)(NT-1)/2 <= MAXT*128 (1: n <= 7, 2: n <= 10, 5: n <= 16).
 // Shared memory (floats): A[SC_PTS][LD+4] | jp[SC_PTS*pstr] | pt[SC_PTS*pstr] | mbarrier.
-__host__ __device__ inline int sc_pstr(int maxres) { return 8 * maxres + 4; }
+// floats per point in the record arrays: 32-byte records (256-bit stores) -> a multiple of 8; maxres + 1 records make the
+// stride an odd multiple of 8 for even maxres (2-way instead of 4-way bank conflicts on the scalar reads of phase 1)
+__host__ __device__ inline int sc_pstr(int maxres) { return 8 * (maxres + 1); }
 __host__ __device__ inline size_t sc_smem_floats(int LD, int maxres) {
   return (size_t)SC_PTS * (LD + 4) + 2 * (size_t)SC_PTS * sc_pstr(maxres) + 4;
 }

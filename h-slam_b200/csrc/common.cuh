@@ -69,6 +69,11 @@ __device__ __forceinline__ Pair8 ldg_pair_keep(const float4* p, uint64_t pol) {
       : "l"(p), "l"(pol));
   return v;
 }
+// 256-bit store (sm_100: STG.E.256): one 32-byte record = one full sector in one instruction
+__device__ __forceinline__ void stg256(float* p, float4 a, float4 b) {
+  asm volatile("st.global.v8.f32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};"
+               ::"l"(p), "f"(a.x), "f"(a.y), "f"(a.z), "f"(a.w), "f"(b.x), "f"(b.y), "f"(b.z), "f"(b.w) : "memory");
+}
 #ifndef HS_TEXEL_L2_KEEP
 #define HS_TEXEL_L2_KEEP 1
 #endif

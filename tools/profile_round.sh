@@ -13,7 +13,7 @@ case $what in
     timeout 600 python bench.py --impl reference --steps 3 --warmup 1 > gpurun_out/bench_ref_$tag.json 2>> gpurun_out/bench_$tag.err; tail -c 400 gpurun_out/bench_ref_$tag.json ;;
   list)
     timeout 300 $SHORT > gpurun_out/short_$tag.log 2>&1 || exit 1
-    timeout 900 ncu --metrics gpu__time_duration.sum --clock-control none -k regex:"ba_|trk_" -c 200 --csv \
+    timeout 900 ncu --metrics gpu__time_duration.sum --clock-control none -k regex:"ba_|trk_" -c 500 --csv \
       --log-file gpurun_out/launches_$tag.csv $SHORT > gpurun_out/ncu_list_$tag.log 2>&1; tail -3 gpurun_out/ncu_list_$tag.log ;;
   full)
     timeout 300 $SHORT > gpurun_out/short_$tag.log 2>&1 || exit 1
