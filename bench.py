@@ -155,6 +155,7 @@ def main():
     ap.add_argument("--mode", default="batched", choices=["batched", "sharded"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-extras", action="store_true", help="skip the tracking / single-window latency figures (profiling runs)")
+    ap.add_argument("--no-sharded", action="store_true", help="skip the sharded 2M-residual window sub-record")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
 
@@ -353,9 +354,26 @@ def main():
                        "workload": "same windows before fixLinearizationF: 0 % linearised, every residual is re-linearised"},
     }
 
+    # ---- the other multi-GPU axis (BASELINE.json configs[4]): ONE 2M-residual window, points sharded over the ranks, one
+    # hslam_ba_allreduce per iteration (strong scaling; at N=1 the whole window runs on the one GPU)
+    if not args.no_sharded:
+        batch.close()
+        for ef in efs:
+            ef.close()        # the batched windows' HBM is not needed any more
+        for fr in frames_all:
+            for f in fr:
+                f.close()
+        host_imgs.clear()
+        from bench_sharded import sharded_record
+        try:
+            line["sharded"] = sharded_record(args, rank, local_rank, world, capi, synth, ctx=ctx)
+        except Exception as e:   # must not take the bench line down
+            line["sharded"] = {"error": repr(e)}
+            if world > 1:
+                raise
     if rank == 0:
         if not args.no_extras:
-            line["extra"] = extras(ctx, capi, synth, torch, stream, efs[0], wins[0])
+            line["extra"] = extras(ctx, capi, synth, torch, stream, None, wins[0])
         if not args.no_cpu_baseline:
             line["cpu_baseline"] = cpu_baseline(synth, wins[0], lins[0])
         print(json.dumps(line), flush=True)
@@ -369,7 +387,9 @@ def extras(ctx, capi, synth, torch, stream, ef0, win0):
     out = {}
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     # BA: one window, one GN iteration, device time (with the chunking of a window that runs alone, not the batch's)
-    ef0.set_parallelism(0)
+    fr0 = [capi.Frame(ctx, im, 1) for im in win0.images]
+    ef0 = capi.EnergyFunctional(ctx)
+    ef0.set_window(win0, fr0); ef0.set_topology(win0); ef0.set_jacobian_mode(1)
     for _ in range(3):
         ef0.iteration_device()
     ctx.synchronize()
@@ -380,6 +400,33 @@ def extras(ctx, capi, synth, torch, stream, ef0, win0):
     e1.record(stream)
     torch.cuda.synchronize()
     out["ba_ms_per_window_device"] = e0.elapsed_time(e1) / reps
+    out["ba_window_note"] = "one cfg2 window alone (84k residuals, all re-linearised), the launch chain as one CUDA graph"
+    # cfg4 (BASELINE.json configs[3]): 1280x1024, 10-keyframe window, 8000 points per keyframe (R = 720k), one GN iteration
+    try:
+        kf4 = synth.render_keyframes(1280, 1024, 10, seed=4444)
+        win4, _ = synth.make_window(points_per_frame=8000, seed=4445, keyframes=kf4)
+        fr4 = [capi.Frame(ctx, im, 1) for im in win4.images]
+        ef4 = capi.EnergyFunctional(ctx)
+        ef4.set_window(win4, fr4); ef4.set_topology(win4); ef4.set_jacobian_mode(1)
+        for _ in range(3):
+            ef4.iteration_device()
+        ctx.synchronize()
+        e0.record(stream)
+        for _ in range(reps):
+            ef4.iteration_device()
+        e1.record(stream)
+        torch.cuda.synchronize()
+        out["cfg4_ba_ms_per_window_device"] = e0.elapsed_time(e1) / reps
+        out["cfg4_residuals"] = int(win4.R)
+        out["cfg4_mres_per_s"] = win4.R * 8 / (out["cfg4_ba_ms_per_window_device"] * 1e-3) / 1e6
+        ef4.close()
+        for f_ in fr4:
+            f_.close()
+    except Exception as e:
+        out["cfg4_error"] = repr(e)
+    ef0.close()
+    for f_ in fr0:
+        f_.close()
     # tracking: config 1 (640x480, 5 levels, ~28k level-0 points)
     tp = synth.make_tracking_pair()
     trk = capi.CoarseTracker(ctx, tp.cam.w, tp.cam.h)

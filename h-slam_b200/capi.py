@@ -503,6 +503,12 @@ class EnergyFunctional:
         return self._result((out,), lambda: [(out[s * per:s * per + N * N].reshape(N, N).T.copy(),
                                               out[s * per + N * N:(s + 1) * per].copy()) for s in range(3)])
 
+    def download_stats(self):
+        """(energy, resInA, resInL) as the device holds them (window totals after allreduce())."""
+        e = C.c_double(0); nres = np.zeros(2, np.int32)
+        _chk(self.L.hslam_ba_download_stats(self.h, C.byref(e), _ptr(nres)))
+        return self._result((e, nres), lambda: (e.value, int(nres[0]), int(nres[1])))
+
     def begin_async(self):
         _chk(self.L.hslam_ba_begin_async(self.h))
         self._async = True
@@ -556,6 +562,10 @@ class EnergyFunctional:
                                                 _ptr(Ms), _ptr(Mbs), C.byref(nres)))
         return M.reshape(N, N).T.copy(), Mb, Ms.reshape(N, N).T.copy(), Mbs, nres.value
 
+    def allreduce(self, comm: "NcclComm"):
+        """Sharded window: ONE fp64 NCCL all-reduce of the stitched systems (+ energy, resInA/L) on the context stream."""
+        _chk(self.L.hslam_ba_allreduce(self.h, comm.h))
+
     def set_jacobian_mode(self, mode):
         """0: all 74 Jacobian floats stored; 1: GN-loop mode (per-pixel rows + projectedTo only on fixLinearization)."""
         _chk(self.L.hslam_ba_set_jacobian_mode(self.h, C.c_int(int(mode))))
@@ -579,6 +589,43 @@ class EnergyFunctional:
     def close(self):
         if self.h:
             self.L.hslam_ba_destroy(self.h)
+            self.h = C.c_void_p()
+
+
+def use_torch_nccl():
+    """Point the library at the libnccl that torch bundles (HSLAM_NCCL_LIB), so that hslam_nccl_* / hslam_ba_allreduce and
+    torch.distributed share one NCCL build.  Must run before the first NCCL call of the library; a no-op if the
+    variable is already set or the wheel is not there (then the library falls back to the process / libnccl.so.2)."""
+    if os.environ.get("HSLAM_NCCL_LIB"):
+        return os.environ["HSLAM_NCCL_LIB"]
+    try:
+        import nvidia.nccl as _n
+        cand = os.path.join(list(_n.__path__)[0], "lib", "libnccl.so.2")
+        if os.path.exists(cand):
+            os.environ["HSLAM_NCCL_LIB"] = cand
+            return cand
+    except Exception:
+        pass
+    return None
+
+
+def nccl_unique_id():
+    buf = C.create_string_buffer(128)
+    _chk(load().hslam_nccl_get_unique_id(buf))
+    return bytes(buf.raw)
+
+
+class NcclComm:
+    """ncclComm_t created through the library's own NCCL handle (hslam_nccl_comm_init)."""
+
+    def __init__(self, ctx: Context, unique_id: bytes, n_ranks: int, rank: int):
+        self.L = ctx.L
+        self.h = C.c_void_p()
+        _chk(self.L.hslam_nccl_comm_init(ctx.h, C.c_char_p(unique_id), C.c_int(n_ranks), C.c_int(rank), C.byref(self.h)))
+
+    def close(self):
+        if self.h:
+            self.L.hslam_nccl_comm_destroy(self.h)
             self.h = C.c_void_p()
 
 

@@ -107,6 +107,10 @@ struct hslam_ba {
   size_t arena_cap = 0, arena_used = 0;
   std::vector<std::function<void()>> pending;
   bool async_mode = false;
+  // CUDA graph of the single-window GN iteration (hslam_ba_iteration_device): re-captured when a launch parameter changes
+  cudaGraphExec_t g_iter = nullptr;
+  long long g_key[12] = {0};
+  int g_kernels = 0;
 };
 
 #define TRY(x) do { int rc__ = (x); if (rc__) return rc__; } while (0)
@@ -504,6 +508,7 @@ int hslam_ba_destroy(hslam_ba* ba) {
   ba->d_Hb.release(); ba->d_epart.release(); ba->d_energy.release(); ba->d_nres.release(); ba->d_ticket.release();
   ba->d_xc.release(); ba->d_xAd.release(); ba->d_x.release(); ba->d_ids.release(); ba->d_th.release(); ba->d_desc.release();
   ba->d_r_s2o.release(); ba->d_p_s2o.release(); ba->d_scratch.release(); ba->d_marg.release();
+  if (ba->g_iter) cudaGraphExecDestroy(ba->g_iter);
   if (ba->arena) cudaFreeHost(ba->arena);
   delete ba;
   return 0;
@@ -587,7 +592,7 @@ int hslam_ba_set_window(hslam_ba* ba, const hslam_window* w) {
   TRY(upload(ba, ba->d_precalc.p, w->precalc, nn * HSLAM_PRECALC_STRIDE));
   TRY(upload(ba, ba->d_adHTd.p, w->adHTdeltaF, nn * 8));
   TRY(ba->d_x.ensure(ba->N)); TRY(ba->d_xc.ensure(4)); TRY(ba->d_xAd.ensure(nn * 8));
-  TRY(ba->d_Hb.ensure(3 * ((size_t)ba->N * ba->N + ba->N)));
+  TRY(ba->d_Hb.ensure(3 * ((size_t)ba->N * ba->N + ba->N) + 4));   // + the all-reduce tail (energy, resInA, resInL)
   if (ba->d_accTop.cap < 3 * nn * TOP_DENSE) {
     TRY(ba->d_accTop.ensure(3 * nn * TOP_DENSE));
     HS_CUDA(cudaMemsetAsync(ba->d_accTop.p, 0, 3 * nn * TOP_DENSE * sizeof(double), ctx->stream));
@@ -1016,11 +1021,40 @@ int hslam_ba_accumulate_all_device(hslam_ba* ba, double** Hb_dev_out, int* count
 
 int hslam_ba_iteration_device(hslam_ba* ba, double** Hb_dev_out, int* count_out) {
   HS_ARG(ba && ba->have_topology && ba->have_window, "hslam_ba_iteration: window/topology not set");
-  HS_CUDA(cudaSetDevice(ba->ctx->device));
-  TRY(launch_linearize(ba, true));
-  TRY(enqueue_accumulate_all(ba, 1));   // the stitch also sums the energy partials of the linearise pass
+  hslam_ctx* ctx = ba->ctx;
+  HS_CUDA(cudaSetDevice(ctx->device));
   if (Hb_dev_out) *Hb_dev_out = ba->d_Hb.p;
   if (count_out) *count_out = 3 * (ba->N * ba->N + ba->N);
+  static const bool no_graph = getenv("HSLAM_NO_GRAPH") != nullptr;
+  if (ctx->profile || no_graph) {
+    TRY(launch_linearize(ba, true));
+    return enqueue_accumulate_all(ba, 1);   // the stitch also sums the energy partials of the linearise pass
+  }
+  // The launch chain (linearise, top A [+ L], Schur, fold, stitch) as ONE graph launch: a window that runs alone is
+  // latency-bound, the gaps between five dependent launches cost more than the kernels.
+  TRY(sync_desc(ba));   // descriptor upload stays outside the graph
+  const long long key[12] = {ba->n_lintiles, ba->n_topblocks[0], ba->n_topblocks[1], ba->n_ptchunks, ba->n, ba->LD, ba->maxres,
+                             ba->jmode, ba->n_linearized != 0, (long long)(size_t)ba->d_desc.p, ba->P, ba->R};
+  if (!ba->g_iter || memcmp(key, ba->g_key, sizeof(key)) != 0) {
+    TRY(top_attr(ctx));
+    TRY(schur_attr(ctx, schur_smem(ba->LD, ba->maxres)));
+    if (ba->g_iter) { cudaGraphExecDestroy(ba->g_iter); ba->g_iter = nullptr; }
+    const int64_t l0 = ctx->launches;
+    HS_CUDA(cudaStreamBeginCapture(ctx->stream, cudaStreamCaptureModeThreadLocal));
+    int rc = launch_linearize(ba, true);
+    if (!rc) rc = enqueue_accumulate_all(ba, 1);
+    cudaGraph_t g = nullptr;
+    cudaError_t e = cudaStreamEndCapture(ctx->stream, &g);
+    if (rc) { if (g) cudaGraphDestroy(g); return rc; }
+    HS_CUDA(e);
+    ba->g_kernels = (int)(ctx->launches - l0);
+    ctx->launches = l0;
+    HS_CUDA(cudaGraphInstantiate(&ba->g_iter, g, 0));
+    cudaGraphDestroy(g);
+    memcpy(ba->g_key, key, sizeof(key));
+  }
+  HS_CUDA(cudaGraphLaunch(ba->g_iter, ctx->stream));
+  ctx->launches += ba->g_kernels;
   return 0;
 }
 
@@ -1028,6 +1062,14 @@ int hslam_ba_download_Hb(hslam_ba* ba, double* out) {
   HS_ARG(ba && out && ba->have_window, "hslam_ba_download_Hb: bad argument");
   HS_CUDA(cudaSetDevice(ba->ctx->device));
   TRY(download(ba, out, ba->d_Hb.p, 3 * ((size_t)ba->N * ba->N + ba->N)));
+  return end_call(ba);
+}
+
+int hslam_ba_download_stats(hslam_ba* ba, double* energy, int* nres2) {
+  HS_ARG(ba && ba->have_window, "hslam_ba_download_stats: bad argument");
+  HS_CUDA(cudaSetDevice(ba->ctx->device));
+  TRY(download(ba, energy, ba->d_energy.p, 1));
+  TRY(download(ba, nres2, ba->d_nres.p, 2));
   return end_call(ba);
 }
 
@@ -1039,23 +1081,80 @@ int hslam_ba_accumulate_all(hslam_ba* ba, double* Hb_out_host, int* nres2) {
   return end_call(ba);
 }
 
-typedef int (*nccl_allreduce_fn)(const void*, void*, size_t, int, int, void*, cudaStream_t);
+// ---- NCCL, resolved at run time (no link-time dependency): the library named by HSLAM_NCCL_LIB, else whatever libnccl
+// the process has already loaded (torch's), else libnccl.so.2.  Communicator creation goes through the SAME handle, so a
+// comm made by hslam_nccl_comm_init is used by the library version that made it.
+struct NcclApi {
+  int (*GetUniqueId)(void*) = nullptr;
+  int (*CommInitRank)(void**, int, /* ncclUniqueId by value: 128 bytes */ struct Id128, int) = nullptr;
+  int (*CommDestroy)(void*) = nullptr;
+  int (*AllReduce)(const void*, void*, size_t, int, int, void*, cudaStream_t) = nullptr;
+  const char* (*GetErrorString)(int) = nullptr;
+  bool ok = false;
+};
+struct Id128 { char b[128]; };
+static NcclApi* nccl_api() {
+  static NcclApi api = []() {
+    NcclApi a;
+    void* h = nullptr;
+    if (const char* path = getenv("HSLAM_NCCL_LIB")) h = dlopen(path, RTLD_NOW | RTLD_GLOBAL);
+    auto sym = [&](const char* name) -> void* {
+      void* p = h ? dlsym(h, name) : dlsym(RTLD_DEFAULT, name);
+      return p;
+    };
+    if (!h && !dlsym(RTLD_DEFAULT, "ncclAllReduce")) h = dlopen("libnccl.so.2", RTLD_NOW | RTLD_GLOBAL);
+    a.GetUniqueId = (int (*)(void*))sym("ncclGetUniqueId");
+    a.CommInitRank = (int (*)(void**, int, Id128, int))sym("ncclCommInitRank");
+    a.CommDestroy = (int (*)(void*))sym("ncclCommDestroy");
+    a.AllReduce = (int (*)(const void*, void*, size_t, int, int, void*, cudaStream_t))sym("ncclAllReduce");
+    a.GetErrorString = (const char* (*)(int))sym("ncclGetErrorString");
+    a.ok = a.GetUniqueId && a.CommInitRank && a.CommDestroy && a.AllReduce;
+    return a;
+  }();
+  return &api;
+}
+static int nccl_fail(const char* what, int rc) {
+  NcclApi* a = nccl_api();
+  hs::set_error(std::string(what) + ": NCCL error " + std::to_string(rc) + (a->GetErrorString ? std::string(" (") + a->GetErrorString(rc) + ")" : ""));
+  return HSLAM_ERR_NCCL;
+}
+#define HS_NCCL_READY(what) do { if (!nccl_api()->ok) { hs::set_error(std::string(what) + ": libnccl not found (set HSLAM_NCCL_LIB)"); return HSLAM_ERR_NCCL; } } while (0)
+
+int hslam_nccl_get_unique_id(char id_out[128]) {
+  HS_ARG(id_out, "hslam_nccl_get_unique_id: null");
+  HS_NCCL_READY("hslam_nccl_get_unique_id");
+  int rc = nccl_api()->GetUniqueId(id_out);
+  return rc ? nccl_fail("ncclGetUniqueId", rc) : 0;
+}
+int hslam_nccl_comm_init(hslam_ctx* ctx, const char id[128], int n_ranks, int rank, void** comm_out) {
+  HS_ARG(ctx && id && comm_out && n_ranks >= 1 && rank >= 0 && rank < n_ranks, "hslam_nccl_comm_init: bad argument");
+  HS_NCCL_READY("hslam_nccl_comm_init");
+  HS_CUDA(cudaSetDevice(ctx->device));
+  Id128 uid;
+  memcpy(uid.b, id, 128);
+  int rc = nccl_api()->CommInitRank(comm_out, n_ranks, uid, rank);
+  return rc ? nccl_fail("ncclCommInitRank", rc) : 0;
+}
+int hslam_nccl_comm_destroy(void* comm) {
+  if (!comm) return 0;
+  HS_NCCL_READY("hslam_nccl_comm_destroy");
+  int rc = nccl_api()->CommDestroy(comm);
+  return rc ? nccl_fail("ncclCommDestroy", rc) : 0;
+}
+
 int hslam_ba_allreduce(hslam_ba* ba, void* nccl_comm) {
   HS_ARG(ba && nccl_comm && ba->have_window, "hslam_ba_allreduce: bad argument");
-  static nccl_allreduce_fn fn = nullptr;
-  if (!fn) {
-    fn = (nccl_allreduce_fn)dlsym(RTLD_DEFAULT, "ncclAllReduce");
-    if (!fn) {
-      void* h = dlopen("libnccl.so.2", RTLD_NOW | RTLD_GLOBAL);
-      if (h) fn = (nccl_allreduce_fn)dlsym(h, "ncclAllReduce");
-    }
-    if (!fn) { hs::set_error("hslam_ba_allreduce: ncclAllReduce not found in the process or libnccl.so.2"); return HSLAM_ERR_NCCL; }
-  }
-  HS_CUDA(cudaSetDevice(ba->ctx->device));
-  size_t count = 3 * ((size_t)ba->N * ba->N + ba->N);
+  HS_NCCL_READY("hslam_ba_allreduce");
+  hslam_ctx* ctx = ba->ctx;
+  HS_CUDA(cudaSetDevice(ctx->device));
+  const size_t count = 3 * ((size_t)ba->N * ba->N + ba->N);
+  // energy (stats[0] of linearizeAll) and resInA / resInL ride in three spare doubles behind the systems
+  HS_LAUNCH(ctx, HSLAM_K_BA_EXPORT, (ba_allreduce_tail_kernel<<<1, 32, 0, ctx->stream>>>(ba->d_Hb.p + count, ba->d_energy.p, ba->d_nres.p, 0)));
   // ncclDouble = 8, ncclSum = 0 (nccl.h)
-  int rc = fn(ba->d_Hb.p, ba->d_Hb.p, count, 8, 0, nccl_comm, ba->ctx->stream);
-  if (rc != 0) { hs::set_error("hslam_ba_allreduce: ncclAllReduce failed with code " + std::to_string(rc)); return HSLAM_ERR_NCCL; }
+  int rc = nccl_api()->AllReduce(ba->d_Hb.p, ba->d_Hb.p, count + 3, 8, 0, nccl_comm, ctx->stream);
+  if (rc != 0) return nccl_fail("ncclAllReduce", rc);
+  HS_LAUNCH(ctx, HSLAM_K_BA_EXPORT, (ba_allreduce_tail_kernel<<<1, 32, 0, ctx->stream>>>(ba->d_Hb.p + count, ba->d_energy.p, ba->d_nres.p, 1)));
+  HS_CUDA(cudaGetLastError());
   return 0;
 }
 

@@ -406,13 +406,25 @@ int hslam_ba_batch_io_bind(hslam_ba_batch* batch, hslam_ba_step_io* io, float** 
 /* EnergyFunctional::resubstituteF_MT for every window of the batch: x[i] = (8n+4) host doubles,
  * step_out[i] = P host floats (nullable). */
 int hslam_ba_batch_resubstitute_host(hslam_ba_batch* batch, const double* const* x, float* const* step_out);
-/* Copy the device Hb block to the host (after an external all-reduce). */
+/* Copy the device Hb block to the host (after hslam_ba_allreduce / an external all-reduce). */
 int hslam_ba_download_Hb(hslam_ba* ba, double* Hb_out_host);
-/* Sum the stitched [H|b] block across ranks with ONE ncclAllReduce(sum, fp64)
- * on the context stream.  nccl_comm is a ncclComm_t; libnccl is resolved at
- * run time from the process (dlsym), there is no link-time dependency.
- * prior_rank: priors were added by every rank; this call removes the
- * duplicates so that the sum holds them once (AccumulatedTopHessian.cpp:268). */
+/* Energy (stats[0] of the last fused linearise pass) and {resInA, resInL} as the device holds them (summed over the
+ * ranks after hslam_ba_allreduce).  Host pointers, each nullable. */
+int hslam_ba_download_stats(hslam_ba* ba, double* energy, int* nres2);
+/* Sharded window (BASELINE.json configs[4]: one window's points split over the GPUs of a box).  Every
+ * rank runs the hot path on its shard (hslam_ba_iteration_device / hslam_ba_accumulate_all_device) and then sums the
+ * stitched [H_A|b_A|H_L|b_L|H_SC|b_SC] block — plus energy, resInA, resInL — across ranks with ONE
+ * ncclAllReduce(sum, fp64) on the context stream; afterwards every rank's block (hslam_ba_download_Hb) and its energy /
+ * counts are the window's.  CONTRACT: the priors (cPrior, frame priors) enter the L system on every rank that has
+ * hslam_ba_set_add_priors(ba, 1) — exactly ONE rank of the communicator must (AccumulatedTopHessian.cpp:268 "only do
+ * this on one thread").  System::setNewFrameEnergyTH of a sharded window needs the per-residual energies of all
+ * shards: request them through hslam_ba_linearize on every rank (hslam_ba_new_frame_energy_th is per shard).
+ * nccl_comm is an ncclComm_t.  libnccl is resolved at run time (no link-time dependency): the library named by the
+ * environment variable HSLAM_NCCL_LIB, else the libnccl already loaded in the process, else libnccl.so.2.  The
+ * hslam_nccl_* helpers create the communicator through the same library (id from rank 0, distributed by the caller). */
+int hslam_nccl_get_unique_id(char id_out[128]);
+int hslam_nccl_comm_init(hslam_ctx* ctx, const char id[128], int n_ranks, int rank, void** nccl_comm_out);
+int hslam_nccl_comm_destroy(void* nccl_comm);
 int hslam_ba_allreduce(hslam_ba* ba, void* nccl_comm);
 /* How many thread blocks per stage this window should fill (0 = default, two waves over the SMs).  The
  * residual / point lists are cut into that many chunks, each reduced into one fp32 partial, the partials

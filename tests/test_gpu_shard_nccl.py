@@ -34,20 +34,25 @@ def _worker(rank, world, port, q):
     sub = shard.shard_window(win, rank, world)
     ef = capi.EnergyFunctional(ctx)
     ef.set_window(sub, frames); ef.set_topology(sub); ef.set_add_priors(rank == 0)
+    # the communicator is created through the library's own NCCL handle; the id travels over torch.distributed
+    capi.use_torch_nccl()
+    ids = [capi.nccl_unique_id() if rank == 0 else None]
+    dist.broadcast_object_list(ids, src=0)
+    comm = capi.NcclComm(ctx, ids[0], world, rank)
     ptr, cnt = ef.iteration_device()
-    Hb = torch.as_tensor(_DevArray(ptr, cnt), device=torch.device("cuda", rank))
-    stream = torch.cuda.ExternalStream(ctx.stream, device=torch.device("cuda", rank))
-    with torch.cuda.stream(stream):
-        dist.all_reduce(Hb, op=dist.ReduceOp.SUM)
-    torch.cuda.synchronize()
-    got = Hb.cpu().numpy().copy()
+    ef.allreduce(comm)                        # hslam_ba_allreduce: ONE ncclAllReduce(sum, fp64) on the context stream
+    got = np.concatenate([np.concatenate([H.T.reshape(-1), b]) for H, b in ef.download_Hb()])   # synchronises
+    stats = ef.download_stats()               # energy and resInA/L travelled with the systems
     if rank == 0:
         full = capi.EnergyFunctional(ctx)
         full.set_window(win, frames); full.set_topology(win)
         p2, c2 = full.iteration_device()
         ctx.synchronize()
         ref = torch.as_tensor(_DevArray(p2, c2), device=torch.device("cuda", 0)).cpu().numpy()
+        fs = full.download_stats()
+        assert stats[1:] == fs[1:] and abs(stats[0] - fs[0]) <= 1e-9 * abs(fs[0]), (stats, fs)
         q.put((float(np.linalg.norm(got - ref) / np.linalg.norm(ref)), int(sub.P), int(win.P)))
+    comm.close()
     dist.barrier()
     dist.destroy_process_group()
 

@@ -18,5 +18,5 @@ case $what in
   full)
     timeout 300 $SHORT > gpurun_out/short_$tag.log 2>&1 || exit 1
     timeout 1200 ncu --set full --clock-control none --import-source on -k regex:"ba_(linearize|top|schur|fold_sc|stitch)" \
-      --launch-skip 24 --launch-count 6 -f -o gpurun_out/prof_ba_$tag $SHORT > gpurun_out/ncu_full_$tag.log 2>&1; tail -3 gpurun_out/ncu_full_$tag.log ;;
+      --launch-skip 101 --launch-count 6 -f -o gpurun_out/prof_ba_$tag $SHORT > gpurun_out/ncu_full_$tag.log 2>&1; tail -3 gpurun_out/ncu_full_$tag.log ;;
 esac
