@@ -58,9 +58,12 @@ def sharded_record(args, rank, local_rank, world, capi, synth, ctx=None):
         comm = capi.NcclComm(ctx, ids[0], world, rank)
 
     def step():
-        ef.iteration_device()                 # one CUDA graph: linearise + applyRes + top + Schur + fold + stitch of the shard
         if comm is not None:
-            ef.allreduce(comm)                # hslam_ba_allreduce: ONE ncclAllReduce(sum, fp64) of 3 x (H,b) + energy + counts
+            # one CUDA graph (linearise + applyRes + top + Schur + fold + stitch of the shard), then hslam_ba_allreduce's
+            # ncclAllReduce(sum, fp64) of 3 x (H,b) + energy + counts on the same stream
+            ef.iteration_allreduce(comm)
+        else:
+            ef.iteration_device()
 
     def barrier():
         if world > 1:

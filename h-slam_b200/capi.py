@@ -566,6 +566,10 @@ class EnergyFunctional:
         """Sharded window: ONE fp64 NCCL all-reduce of the stitched systems (+ energy, resInA/L) on the context stream."""
         _chk(self.L.hslam_ba_allreduce(self.h, comm.h))
 
+    def iteration_allreduce(self, comm: "NcclComm"):
+        """One GN iteration of this rank's shard (one CUDA graph launch) + the all-reduce on the same stream."""
+        _chk(self.L.hslam_ba_iteration_allreduce(self.h, comm.h))
+
     def set_jacobian_mode(self, mode):
         """0: all 74 Jacobian floats stored; 1: GN-loop mode (per-pixel rows + projectedTo only on fixLinearization)."""
         _chk(self.L.hslam_ba_set_jacobian_mode(self.h, C.c_int(int(mode))))

@@ -1019,68 +1019,6 @@ int hslam_ba_accumulate_all_device(hslam_ba* ba, double** Hb_dev_out, int* count
   return 0;
 }
 
-int hslam_ba_iteration_device(hslam_ba* ba, double** Hb_dev_out, int* count_out) {
-  HS_ARG(ba && ba->have_topology && ba->have_window, "hslam_ba_iteration: window/topology not set");
-  hslam_ctx* ctx = ba->ctx;
-  HS_CUDA(cudaSetDevice(ctx->device));
-  if (Hb_dev_out) *Hb_dev_out = ba->d_Hb.p;
-  if (count_out) *count_out = 3 * (ba->N * ba->N + ba->N);
-  static const bool no_graph = getenv("HSLAM_NO_GRAPH") != nullptr;
-  if (ctx->profile || no_graph) {
-    TRY(launch_linearize(ba, true));
-    return enqueue_accumulate_all(ba, 1);   // the stitch also sums the energy partials of the linearise pass
-  }
-  // The launch chain (linearise, top A [+ L], Schur, fold, stitch) as ONE graph launch: a window that runs alone is
-  // latency-bound, the gaps between five dependent launches cost more than the kernels.
-  TRY(sync_desc(ba));   // descriptor upload stays outside the graph
-  const long long key[12] = {ba->n_lintiles, ba->n_topblocks[0], ba->n_topblocks[1], ba->n_ptchunks, ba->n, ba->LD, ba->maxres,
-                             ba->jmode, ba->n_linearized != 0, (long long)(size_t)ba->d_desc.p, ba->P, ba->R};
-  if (!ba->g_iter || memcmp(key, ba->g_key, sizeof(key)) != 0) {
-    TRY(top_attr(ctx));
-    TRY(schur_attr(ctx, schur_smem(ba->LD, ba->maxres)));
-    if (ba->g_iter) { cudaGraphExecDestroy(ba->g_iter); ba->g_iter = nullptr; }
-    const int64_t l0 = ctx->launches;
-    HS_CUDA(cudaStreamBeginCapture(ctx->stream, cudaStreamCaptureModeThreadLocal));
-    int rc = launch_linearize(ba, true);
-    if (!rc) rc = enqueue_accumulate_all(ba, 1);
-    cudaGraph_t g = nullptr;
-    cudaError_t e = cudaStreamEndCapture(ctx->stream, &g);
-    if (rc) { if (g) cudaGraphDestroy(g); return rc; }
-    HS_CUDA(e);
-    ba->g_kernels = (int)(ctx->launches - l0);
-    ctx->launches = l0;
-    HS_CUDA(cudaGraphInstantiate(&ba->g_iter, g, 0));
-    cudaGraphDestroy(g);
-    memcpy(ba->g_key, key, sizeof(key));
-  }
-  HS_CUDA(cudaGraphLaunch(ba->g_iter, ctx->stream));
-  ctx->launches += ba->g_kernels;
-  return 0;
-}
-
-int hslam_ba_download_Hb(hslam_ba* ba, double* out) {
-  HS_ARG(ba && out && ba->have_window, "hslam_ba_download_Hb: bad argument");
-  HS_CUDA(cudaSetDevice(ba->ctx->device));
-  TRY(download(ba, out, ba->d_Hb.p, 3 * ((size_t)ba->N * ba->N + ba->N)));
-  return end_call(ba);
-}
-
-int hslam_ba_download_stats(hslam_ba* ba, double* energy, int* nres2) {
-  HS_ARG(ba && ba->have_window, "hslam_ba_download_stats: bad argument");
-  HS_CUDA(cudaSetDevice(ba->ctx->device));
-  TRY(download(ba, energy, ba->d_energy.p, 1));
-  TRY(download(ba, nres2, ba->d_nres.p, 2));
-  return end_call(ba);
-}
-
-int hslam_ba_accumulate_all(hslam_ba* ba, double* Hb_out_host, int* nres2) {
-  HS_ARG(Hb_out_host, "hslam_ba_accumulate_all: null output");
-  TRY(hslam_ba_accumulate_all_device(ba, nullptr, nullptr));
-  TRY(download(ba, Hb_out_host, ba->d_Hb.p, 3 * ((size_t)ba->N * ba->N + ba->N)));
-  TRY(download(ba, nres2, ba->d_nres.p, 2));
-  return end_call(ba);
-}
-
 // ---- NCCL, resolved at run time (no link-time dependency): the library named by HSLAM_NCCL_LIB, else whatever libnccl
 // the process has already loaded (torch's), else libnccl.so.2.  Communicator creation goes through the SAME handle, so a
 // comm made by hslam_nccl_comm_init is used by the library version that made it.
@@ -1142,20 +1080,101 @@ int hslam_nccl_comm_destroy(void* comm) {
   return rc ? nccl_fail("ncclCommDestroy", rc) : 0;
 }
 
+// the all-reduce itself: the stitched systems plus three doubles behind them — energy (stats[0] of linearizeAll) and
+// resInA / resInL, which the stitch / energy kernels write there
+static int enqueue_allreduce(hslam_ba* ba, void* nccl_comm) {
+  const size_t count = 3 * ((size_t)ba->N * ba->N + ba->N) + 3;
+  // ncclDouble = 8, ncclSum = 0 (nccl.h)
+  int rc = nccl_api()->AllReduce(ba->d_Hb.p, ba->d_Hb.p, count, 8, 0, nccl_comm, ba->ctx->stream);
+  return rc ? nccl_fail("ncclAllReduce", rc) : 0;
+}
+
 int hslam_ba_allreduce(hslam_ba* ba, void* nccl_comm) {
   HS_ARG(ba && nccl_comm && ba->have_window, "hslam_ba_allreduce: bad argument");
   HS_NCCL_READY("hslam_ba_allreduce");
+  HS_CUDA(cudaSetDevice(ba->ctx->device));
+  return enqueue_allreduce(ba, nccl_comm);
+}
+
+static int iteration_impl(hslam_ba* ba, void* nccl_comm) {
   hslam_ctx* ctx = ba->ctx;
-  HS_CUDA(cudaSetDevice(ctx->device));
+  static const bool no_graph = getenv("HSLAM_NO_GRAPH") != nullptr;
+  if (ctx->profile || no_graph) {
+    TRY(launch_linearize(ba, true));
+    TRY(enqueue_accumulate_all(ba, 1));   // the stitch also sums the energy partials of the linearise pass
+    return nccl_comm ? enqueue_allreduce(ba, nccl_comm) : 0;
+  }
+  // The launch chain (linearise, top A [+ L], Schur, fold, stitch) as ONE graph launch: a window that runs
+  // alone is latency-bound, the gaps between the dependent launches cost more than the kernels.
+  TRY(sync_desc(ba));   // descriptor upload stays outside the graph
+  const long long key[12] = {ba->n_lintiles, ba->n_topblocks[0], ba->n_topblocks[1], ba->n_ptchunks, ba->n, ba->LD,
+                             ba->maxres * 4 + ba->jmode * 2 + (ba->n_linearized != 0), 0,
+                             (long long)(size_t)ba->d_Hb.p, (long long)(size_t)ba->d_desc.p, ba->P, ba->R};
+  if (!ba->g_iter || memcmp(key, ba->g_key, sizeof(key)) != 0) {
+    TRY(top_attr(ctx));
+    TRY(schur_attr(ctx, schur_smem(ba->LD, ba->maxres)));
+    if (ba->g_iter) { cudaGraphExecDestroy(ba->g_iter); ba->g_iter = nullptr; }
+    const int64_t l0 = ctx->launches;
+    HS_CUDA(cudaStreamBeginCapture(ctx->stream, cudaStreamCaptureModeThreadLocal));
+    int rc = launch_linearize(ba, true);
+    if (!rc) rc = enqueue_accumulate_all(ba, 1);
+    cudaGraph_t g = nullptr;
+    cudaError_t e = cudaStreamEndCapture(ctx->stream, &g);
+    if (rc) { if (g) cudaGraphDestroy(g); return rc; }
+    HS_CUDA(e);
+    ba->g_kernels = (int)(ctx->launches - l0);
+    ctx->launches = l0;
+    HS_CUDA(cudaGraphInstantiate(&ba->g_iter, g, 0));
+    cudaGraphDestroy(g);
+    memcpy(ba->g_key, key, sizeof(key));
+  }
+  HS_CUDA(cudaGraphLaunch(ba->g_iter, ctx->stream));
+  ctx->launches += ba->g_kernels;
+  // the all-reduce follows the graph on the same stream (NCCL is kept out of the capture: its first collective on a
+  // communicator sets up connections, which is not capturable)
+  return nccl_comm ? enqueue_allreduce(ba, nccl_comm) : 0;
+}
+
+int hslam_ba_iteration_device(hslam_ba* ba, double** Hb_dev_out, int* count_out) {
+  HS_ARG(ba && ba->have_topology && ba->have_window, "hslam_ba_iteration: window/topology not set");
+  HS_CUDA(cudaSetDevice(ba->ctx->device));
+  if (Hb_dev_out) *Hb_dev_out = ba->d_Hb.p;
+  if (count_out) *count_out = 3 * (ba->N * ba->N + ba->N);
+  return iteration_impl(ba, nullptr);
+}
+
+int hslam_ba_iteration_allreduce(hslam_ba* ba, void* nccl_comm) {
+  HS_ARG(ba && nccl_comm && ba->have_topology && ba->have_window, "hslam_ba_iteration_allreduce: bad argument");
+  HS_NCCL_READY("hslam_ba_iteration_allreduce");
+  HS_CUDA(cudaSetDevice(ba->ctx->device));
+  return iteration_impl(ba, nccl_comm);
+}
+
+int hslam_ba_download_Hb(hslam_ba* ba, double* out) {
+  HS_ARG(ba && out && ba->have_window, "hslam_ba_download_Hb: bad argument");
+  HS_CUDA(cudaSetDevice(ba->ctx->device));
+  TRY(download(ba, out, ba->d_Hb.p, 3 * ((size_t)ba->N * ba->N + ba->N)));
+  return end_call(ba);
+}
+
+int hslam_ba_download_stats(hslam_ba* ba, double* energy, int* nres2) {
+  HS_ARG(ba && ba->have_window, "hslam_ba_download_stats: bad argument");
+  HS_CUDA(cudaSetDevice(ba->ctx->device));
+  // the three doubles behind the systems: this rank's values, or the window's totals after hslam_ba_allreduce
   const size_t count = 3 * ((size_t)ba->N * ba->N + ba->N);
-  // energy (stats[0] of linearizeAll) and resInA / resInL ride in three spare doubles behind the systems
-  HS_LAUNCH(ctx, HSLAM_K_BA_EXPORT, (ba_allreduce_tail_kernel<<<1, 32, 0, ctx->stream>>>(ba->d_Hb.p + count, ba->d_energy.p, ba->d_nres.p, 0)));
-  // ncclDouble = 8, ncclSum = 0 (nccl.h)
-  int rc = nccl_api()->AllReduce(ba->d_Hb.p, ba->d_Hb.p, count + 3, 8, 0, nccl_comm, ctx->stream);
-  if (rc != 0) return nccl_fail("ncclAllReduce", rc);
-  HS_LAUNCH(ctx, HSLAM_K_BA_EXPORT, (ba_allreduce_tail_kernel<<<1, 32, 0, ctx->stream>>>(ba->d_Hb.p + count, ba->d_energy.p, ba->d_nres.p, 1)));
-  HS_CUDA(cudaGetLastError());
-  return 0;
+  TRY(download_then<double>(ba, ba->d_Hb.p + count, 3, [energy, nres2](const double* s) {
+    if (energy) *energy = s[0];
+    if (nres2) { nres2[0] = (int)(s[1] + 0.5); nres2[1] = (int)(s[2] + 0.5); }
+  }));
+  return end_call(ba);
+}
+
+int hslam_ba_accumulate_all(hslam_ba* ba, double* Hb_out_host, int* nres2) {
+  HS_ARG(Hb_out_host, "hslam_ba_accumulate_all: null output");
+  TRY(hslam_ba_accumulate_all_device(ba, nullptr, nullptr));
+  TRY(download(ba, Hb_out_host, ba->d_Hb.p, 3 * ((size_t)ba->N * ba->N + ba->N)));
+  TRY(download(ba, nres2, ba->d_nres.p, 2));
+  return end_call(ba);
 }
 
 int hslam_ba_point_results(hslam_ba* ba, float* HdiF, float* bdSumF, float* idepth_hessian, float* Hdd_accAF,

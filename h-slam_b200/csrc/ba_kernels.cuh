@@ -498,6 +498,7 @@ __device__ __forceinline__ void energy_sum_block(const BADesc& D, double* red) {
     double t = 0.0;
     for (int w = 0; w < (int)(blockDim.x >> 5); ++w) t += red[w];
     *D.energy = t;
+    if (D.S.Hb) { const int N = 8 * D.S.n + 4; D.S.Hb[3 * ((size_t)N * N + N)] = t; }   // rides with the systems through hslam_ba_allreduce
   }
 }
 
@@ -1412,30 +1413,23 @@ __device__ __forceinline__ void dmma884(double& d0, double& d1, double a, double
 }
 // (o0, o1) += A1 * M * A2^T for one warp, as four DMMAs: T = A1 * M (two k-steps), T from accumulator layout to A-operand
 // layout with two quad shuffles, then o += T * A2^T (two k-steps).  A1, A2: 8x8 column-major (the adjoints); M(row, col) =
-// Mb[row * ldm + col] (dense 13x13 top accumulator or dense Gram matrix).  6 loads per lane, one memory round trip;
-// split in a load half and a compute half so that a warp's NEXT sandwich is in flight while it computes the current one.
-struct SandwichOps { double a1lo, a1hi, mlo, mhi, a2lo, a2hi; };
-__device__ __forceinline__ SandwichOps sandwich_load(const double* __restrict__ A1, const double* __restrict__ A2,
-                                                     const double* __restrict__ Mb, int ldm, int lane) {
+// Mb[row * ldm + col] (dense 13x13 top accumulator or dense Gram matrix).  6 loads per lane, one memory round trip.
+__device__ __forceinline__ void sandwich_dmma(const double* __restrict__ A1, const double* __restrict__ A2,
+                                              const double* __restrict__ Mb, int ldm, int lane, double& o0, double& o1) {
   const int g = lane >> 2, t = lane & 3;
-  SandwichOps o;
-  o.a1lo = A1[g + 8 * t]; o.a1hi = A1[g + 8 * (t + 4)];
-  o.mlo = Mb[t * ldm + g]; o.mhi = Mb[(t + 4) * ldm + g];
-  o.a2lo = A2[g + 8 * t]; o.a2hi = A2[g + 8 * (t + 4)];
-  return o;
-}
-__device__ __forceinline__ void sandwich_compute(const SandwichOps& q, int lane, double& o0, double& o1) {
-  const int t = lane & 3;
+  const double a1lo = A1[g + 8 * t], a1hi = A1[g + 8 * (t + 4)];
+  const double mlo = Mb[t * ldm + g], mhi = Mb[(t + 4) * ldm + g];
+  const double a2lo = A2[g + 8 * t], a2hi = A2[g + 8 * (t + 4)];
   double T0 = 0.0, T1 = 0.0;
-  dmma884(T0, T1, q.a1lo, q.mlo);
-  dmma884(T0, T1, q.a1hi, q.mhi);
+  dmma884(T0, T1, a1lo, mlo);
+  dmma884(T0, T1, a1hi, mhi);
   // T[g][t] lives in lane (quad | t>>1), slot t&1; T[g][t+4] two lanes further
   const int src = (lane & ~3) | (t >> 1);
   const double s0 = __shfl_sync(0xffffffffu, T0, src), s1 = __shfl_sync(0xffffffffu, T1, src);
   const double u0 = __shfl_sync(0xffffffffu, T0, src + 2), u1 = __shfl_sync(0xffffffffu, T1, src + 2);
   const double tlo = (t & 1) ? s1 : s0, thi = (t & 1) ? u1 : u0;
-  dmma884(o0, o1, tlo, q.a2lo);
-  dmma884(o0, o1, thi, q.a2hi);
+  dmma884(o0, o1, tlo, a2lo);
+  dmma884(o0, o1, thi, a2hi);
 }
 
 // K7: stitch — relative accumulators -> (8n+4)^2 system in fp64, gather form.  One block per output 8x8 block (a,b) of one
@@ -1462,22 +1456,13 @@ __global__ void __launch_bounds__(ST_THREADS) ba_stitch_kernel(const BADesc* __r
   auto AdT = [&](int h, int t) { return S.adTarget + 64 * (size_t)(h + t * n); };
   double o0 = 0.0, o1 = 0.0;
   int ci = 0;   // contribution counter, identical in every warp
-#define CONTRIB(A1, A2, MB, LDM)                                              \
-  do {                                                                        \
-    if ((ci % ST_WARPS) == warp) {                                            \
-      const SandwichOps nx = sandwich_load((A1), (A2), (MB), (LDM), lane);    \
-      if (have_ops) sandwich_compute(cur_ops, lane, o0, o1);                  \
-      cur_ops = nx; have_ops = true;                                          \
-    }                                                                         \
-    ci++;                                                                     \
+#define CONTRIB(A1, A2, MB, LDM)                                                            \
+  do {                                                                                      \
+    if ((ci % ST_WARPS) == warp) sandwich_dmma((A1), (A2), (MB), (LDM), lane, o0, o1);      \
+    ci++;                                                                                   \
   } while (0)
-  // one-deep software pipeline per warp: the operands of this warp's next sandwich are requested before the current one is
-  // multiplied (a stitch block is a chain of small dependent round trips otherwise)
-  SandwichOps cur_ops = {0.0, 0.0, 0.0, 0.0, 0.0, 0.0};
-  bool have_ops = false;
   // the warps' accumulator pairs (row g, columns 2t, 2t+1) -> part[warp][row + 8 col], summed in warp order by 64 threads
   auto reduce_block = [&](auto&& store) {
-    if (have_ops) sandwich_compute(cur_ops, lane, o0, o1);   // drain the pipeline
     const int g = lane >> 2, t = lane & 3;
     part[warp][g + 8 * (2 * t)] = o0; part[warp][g + 8 * (2 * t + 1)] = o1;
     __syncthreads();
@@ -1501,18 +1486,23 @@ __global__ void __launch_bounds__(ST_THREADS) ba_stitch_kernel(const BADesc* __r
         if (a == b) {
           // S[a,a] = sum_t AdH[a,t] M[a,t] AdH[a,t]^T + sum_h AdT[h,a] M[h,a] AdT[h,a]^T + AdH[a,a] M[a,a] AdT[a,a]^T
           for (int t = 0; t < n; ++t) {
-            // (the reference skips accumulators with num == 0, AccumulatedTopHessian.cpp:243: an all-zero block adds exact
-            // zeros here, and testing it first would put a dependent load in front of every sandwich)
-            CONTRIB(AdH(a, t), AdH(a, t), ACC(a, t) + FB, 13);
+            const double* m = ACC(a, t);
+            if (m[169] == 0.0) continue;   // acc.num == 0 (AccumulatedTopHessian.cpp:243)
+            CONTRIB(AdH(a, t), AdH(a, t), m + FB, 13);
           }
           for (int h = 0; h < n; ++h) {
-            CONTRIB(AdT(h, a), AdT(h, a), ACC(h, a) + FB, 13);
+            const double* m = ACC(h, a);
+            if (m[169] == 0.0) continue;
+            CONTRIB(AdT(h, a), AdT(h, a), m + FB, 13);
           }
-          CONTRIB(AdH(a, a), AdT(a, a), ACC(a, a) + FB, 13);
+          const double* m = ACC(a, a);
+          if (m[169] != 0.0) CONTRIB(AdH(a, a), AdT(a, a), m + FB, 13);
         } else {
           // H[a,b] = S[a,b] + S[b,a]^T  (M is symmetric)
-          CONTRIB(AdH(a, b), AdT(a, b), ACC(a, b) + FB, 13);
-          CONTRIB(AdT(b, a), AdH(b, a), ACC(b, a) + FB, 13);
+          const double* m1 = ACC(a, b);
+          if (m1[169] != 0.0) CONTRIB(AdH(a, b), AdT(a, b), m1 + FB, 13);
+          const double* m2 = ACC(b, a);
+          if (m2[169] != 0.0) CONTRIB(AdT(b, a), AdH(b, a), m2 + FB, 13);
         }
       }
       reduce_block([&](int rr, int cc, double o) {
@@ -1577,6 +1567,7 @@ __global__ void __launch_bounds__(ST_THREADS) ba_stitch_kernel(const BADesc* __r
         if (live)
           for (int k = 0; k < nn; ++k) tot += (int)acc[(size_t)k * TOP_DENSE + 169];
         S.nres[sys] = tot;   // resInA / resInL (EnergyFunctional.cpp:163,186)
+        S.Hb[3 * ((size_t)N * N + N) + 1 + sys] = (double)tot;   // ... and behind the systems, for the sharded window's all-reduce
       }
       if (sys == 0 && with_energy) energy_sum_block(descs[win], &part[0][0]);   // uniform per block
     }
@@ -1665,13 +1656,6 @@ __global__ void ba_export_aos_kernel(const T* __restrict__ src, int comps, int c
   if (k >= count) return;
   size_t o = (size_t)sorted2orig[k] * comps;
   for (int c = 0; c < comps; ++c) dst[o + c] = src[(size_t)k * comps + c];
-}
-// Sharded window: energy and the residual counts travel with the systems through the one all-reduce (three doubles
-// behind the block): dir 0 packs them, dir 1 unpacks the sums.
-__global__ void ba_allreduce_tail_kernel(double* tail, double* energy, int* nres, int dir) {
-  if (threadIdx.x != 0) return;
-  if (dir == 0) { tail[0] = *energy; tail[1] = (double)nres[0]; tail[2] = (double)nres[1]; }
-  else { *energy = tail[0]; nres[0] = (int)(tail[1] + 0.5); nres[1] = (int)(tail[2] + 0.5); }
 }
 // JpJdF records (point-major slots) -> caller order [R][8]
 __global__ void ba_export_jpjd_kernel(BARes r, const int* __restrict__ sorted2orig, float* __restrict__ dst) {

@@ -426,6 +426,9 @@ int hslam_nccl_get_unique_id(char id_out[128]);
 int hslam_nccl_comm_init(hslam_ctx* ctx, const char id[128], int n_ranks, int rank, void** nccl_comm_out);
 int hslam_nccl_comm_destroy(void* nccl_comm);
 int hslam_ba_allreduce(hslam_ba* ba, void* nccl_comm);
+/* hslam_ba_iteration_device of this rank's shard (one CUDA graph launch) followed by hslam_ba_allreduce on the same
+ * stream: what a rank runs per GN iteration of a sharded window. */
+int hslam_ba_iteration_allreduce(hslam_ba* ba, void* nccl_comm);
 /* How many thread blocks per stage this window should fill (0 = default, two waves over the SMs).  The
  * residual / point lists are cut into that many chunks, each reduced into one fp32 partial, the partials
  * are folded in chunk order in fp64: the value changes the grouping of the fp32 sums (results agree to

@@ -534,3 +534,22 @@ def test_gn_loop_jacobian_mode_matches_full_mode(ctx, capi, O, synth, window_sma
             assert np.array_equal(va, vb), k
     for f in frames:
         f.close()
+
+
+def test_download_stats_matches_stepwise(ctx, capi, synth, window_small):
+    """hslam_ba_download_stats (the three doubles behind the systems that ride through hslam_ba_allreduce) == energy of
+    linearizeAll and resInA / resInL of the step-wise calls."""
+    win, is_lin = window_small
+    frames = [capi.Frame(ctx, im, 1) for im in win.images]
+    a = capi.EnergyFunctional(ctx); a.set_window(win, frames); a.set_topology(win)
+    b = capi.EnergyFunctional(ctx); b.set_window(win, frames); b.set_topology(win)
+    for ef in (a, b):
+        ef.linearizeAll(False, outputs=False); ef.applyRes()
+        ef.fixLinearization(np.nonzero(is_lin)[0].astype(np.int32))
+    lin = a.linearizeAll(False, outputs=False); a.applyRes(); a.accumulate_all()
+    b.iteration_device()
+    e, nA, nL = b.download_stats()
+    assert e == lin["energy"] and (nA, nL) == (a.resInA, a.resInL) and nA > 0 and nL > 0
+    a.close(); b.close()
+    for f in frames:
+        f.close()

@@ -43,6 +43,9 @@ def _worker(rank, world, port, q):
     ef.allreduce(comm)                        # hslam_ba_allreduce: ONE ncclAllReduce(sum, fp64) on the context stream
     got = np.concatenate([np.concatenate([H.T.reshape(-1), b]) for H, b in ef.download_Hb()])   # synchronises
     stats = ef.download_stats()               # energy and resInA/L travelled with the systems
+    ef.iteration_allreduce(comm)              # the same through the one-call form
+    got2 = np.concatenate([np.concatenate([H.T.reshape(-1), b]) for H, b in ef.download_Hb()])
+    assert np.array_equal(got, got2) and ef.download_stats() == stats
     if rank == 0:
         full = capi.EnergyFunctional(ctx)
         full.set_window(win, frames); full.set_topology(win)
