@@ -475,6 +475,52 @@ def extras(ctx, capi, synth, torch, stream, ef0, win0):
         t_.close(); f_.close()
     for cx in ctxs:
         cx.close()
+    # batched entry point (hslam_tracker_track_batch): n members — motion hypotheses of one frame (System.cpp:348-481) or
+    # several frames — in ONE launch, one 16-CTA cluster each; per-member results are bit-identical to single calls
+    trk.set_mode(out["tracking_mode_cluster_ctas"])
+    its = None
+    if trk.get_mode() > 0:
+        for nb_ in (8, 32):
+            args_ = ([frame] * nb_, [T0] * nb_, [(0.0, 0.0)] * nb_, tp.levels - 1)
+            for _ in range(2):
+                r_ = trk.trackNewestCoarse_batch(*args_)
+            t0 = time.perf_counter()
+            for _ in range(reps):
+                r_ = trk.trackNewestCoarse_batch(*args_)
+            out[f"tracking_batch{nb_}_ms_per_frame"] = 1e3 * (time.perf_counter() - t0) / (reps * nb_)
+            its = r_["iterations"][0]
+    # roofline of Stage T: 64 algorithmic bytes per point-evaluation, evaluations ~ sum_l (1 + iterations_l) * N_l
+    if its is not None:
+        peak_ = 6555.2
+        try:
+            peak_ = float(json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))["hbm_gbs"])
+        except Exception:
+            pass
+        evals = sum((1 + int(i)) * len(p_[0]) for i, p_ in zip(its, tp.pc))
+        out["tracking_point_evaluations_per_frame"] = int(evals)
+        for key in ("tracking_ms_per_frame_device", "tracking_8_streams_ms_per_frame", "tracking_batch8_ms_per_frame", "tracking_batch32_ms_per_frame"):
+            if key in out:
+                out[key.replace("_ms_per_frame", "") + "_roofline_frac"] = evals * 64 / (out[key] * 1e-3) / 1e9 / peak_
+        out["tracking_roofline_note"] = ("64 B per point-evaluation / measured HBM peak; a single frame is latency-bound by construction "
+                                         "(SURVEY 8d), the batched launch is where the fraction is meaningful")
+    # cfg1 as the reference builds it at 640x480: 4 pyramid levels (CalibData.h:110), next to the 5-level variant above
+    try:
+        tp4 = synth.make_tracking_pair(levels=4)
+        trk4 = capi.CoarseTracker(ctx, tp4.cam.w, tp4.cam.h); trk4.makeK(tp4.cam, 4); trk4.setCoarseTrackingRef(tp4.pc)
+        fr4_ = capi.Frame(ctx, tp4.img_new, 4)
+        for _ in range(3):
+            trk4.trackNewestCoarse(fr4_, T0, (0.0, 0.0), 3)
+        e0.record(stream)
+        for _ in range(reps):
+            trk4.track_enqueue(fr4_, T0, (0.0, 0.0), 3)
+        e1.record(stream)
+        torch.cuda.synchronize()
+        trk4.track_finish()
+        out["tracking_4levels_ms_per_frame_device"] = e0.elapsed_time(e1) / reps
+        out["tracking_4levels_iterations"] = [int(i) for i in trk4.iterations[:4]]
+        trk4.close(); fr4_.close()
+    except Exception as e:
+        out["tracking_4levels_error"] = repr(e)
     t0 = time.perf_counter()
     for _ in range(reps):
         frame.update(tp.img_new)                                   # H2D 1.2 MB + 5-level pyramid
@@ -544,7 +590,22 @@ def cpu_baseline(synth, win, is_lin):
     while reps < 200 and (time.perf_counter() - t0 < 10.0 or reps < 5):
         step(); reps += 1
     dt = time.perf_counter() - t0
-    return {"value": win.R * 8 * reps / dt / 1e6, "unit": UNIT, "cores": cores, "kind": "port",
+    # Stage T on the CPU: the oracle's trackNewestCoarse (single-threaded like the reference's, CoarseTracker.cpp:506-683), cfg1
+    trk_cpu = None
+    try:
+        tp = synth.make_tracking_pair()
+        orc = O.TrackerOracle(tp.cam, tp.levels, tp.pc, fast=True)
+        _, _, dI = O.pyramid(tp.img_new, tp.levels)
+        T0 = np.concatenate([np.eye(3).reshape(9), np.zeros(3)])
+        orc.track(dI, T0, (0.0, 0.0), tp.levels - 1, prec="f")
+        tt0, nrep = time.perf_counter(), 0
+        while nrep < 50 and (time.perf_counter() - tt0 < 3.0 or nrep < 3):
+            r_ = orc.track(dI, T0, (0.0, 0.0), tp.levels - 1, prec="f"); nrep += 1
+        trk_cpu = {"tracking_ms_per_frame": 1e3 * (time.perf_counter() - tt0) / nrep, "cores": 1,
+                   "sample": f"{nrep} x trackNewestCoarse on cfg1 (640x480, 5 levels), oracle port -O3 -march=native, single thread"}
+    except Exception as e:
+        trk_cpu = {"error": repr(e)}
+    return {"value": win.R * 8 * reps / dt / 1e6, "unit": UNIT, "cores": cores, "kind": "port", "tracking": trk_cpu,
             "ms_per_window": 1e3 * dt / reps,
             "sample": f"{reps} GN iterations of one cfg2 window (84k residuals, 30 % linearised) on {cores} threads, oracle port -O3 -march=native"}
 

@@ -256,6 +256,20 @@ class CoarseTracker:
                                         _ptr(self.iterations)))
         return bool(ok.value), T, aff
 
+    def trackNewestCoarse_batch(self, frames, Ts, affs, coarsestLvl, minResForAbort=None, new_exposures=None):
+        """hslam_tracker_track_batch: n members (frames and/or initial poses) in ONE launch, one cluster each.
+        Returns dict(ok[n], T[n,12], aff[n,2], lastResiduals[n,5], lastFlow[n,3], iterations[n,5])."""
+        n = len(frames)
+        T = np.ascontiguousarray(np.array(Ts, np.float64).reshape(n, 12)).copy()
+        aff = np.ascontiguousarray(np.array(affs, np.float64).reshape(n, 2)).copy()
+        mra = np.full(5, np.nan) if minResForAbort is None else np.ascontiguousarray(minResForAbort, np.float64)
+        ne = None if new_exposures is None else np.ascontiguousarray(new_exposures, np.float32)
+        fr = (C.c_void_p * n)(*[f.h for f in frames])
+        res = np.zeros((n, 5)); flow = np.zeros((n, 3)); ok = np.zeros(n, np.int32); its = np.zeros((n, 5), np.int32)
+        _chk(self.L.hslam_tracker_track_batch(self.h, C.c_int(n), fr, _ptr(ne), _ptr(T), _ptr(aff), C.c_int(coarsestLvl), _ptr(mra),
+                                              _ptr(res), _ptr(flow), _ptr(ok), _ptr(its)))
+        return dict(ok=ok.astype(bool), T=T, aff=aff, lastResiduals=res, lastFlow=flow, iterations=its)
+
     def track_enqueue(self, frame: Frame, T, aff, coarsestLvl, minResForAbort=None, new_exposure=1.0):
         T = np.ascontiguousarray(T, np.float64)
         aff = np.ascontiguousarray(aff, np.float64)

@@ -494,7 +494,8 @@ struct TrackIO {           // pinned-host visible struct copied in/out
   int ok;
   int iterations[5];
   int evals;
-  int pad;
+  float new_exposure;          // of THIS member's frame
+  const float4* img[5];        // pyramid levels of THIS member's frame (a batch tracks several frames / hypotheses at once)
   long long phase_cycles[4];   // diagnostics (block 0): solve+exp+constants | evaluation | barrier+fold | accept+make_Hb
 };
 
@@ -515,16 +516,16 @@ __device__ __forceinline__ double sat_ratio(const EvalResult& r) { return (doubl
 // partials in block order (identical result in every block).
 template <int THREADS, bool CLUSTER>
 __device__ __forceinline__ void track_eval_and_fold(const EvalConst& c, float* gpart, float* spart, float* red,
-                                                    double (*fold)[TRK_PART], EvalResult& res, int nb, long long* tk) {
+                                                    double (*fold)[TRK_PART], EvalResult& res, int nb, long long* tk, int brank) {
   const long long t0 = clock64();
   if (CLUSTER) {
     cg::cluster_group cluster = cg::this_cluster();
-    if ((int)blockIdx.x < nb) eval_block<THREADS>(c, spart, red, blockIdx.x, nb);
+    if (brank < nb) eval_block<THREADS>(c, spart, red, brank, nb);
     if (threadIdx.x == 0) tk[1] += clock64() - t0;
     cluster.sync();   // release/acquire across the cluster: the shared-memory partials are visible
     fold_partials([&](int b, int t) { return cluster.map_shared_rank(spart, b)[t]; }, nb, res, fold);
   } else {
-    if ((int)blockIdx.x < nb) eval_block<THREADS>(c, gpart + (size_t)blockIdx.x * TRK_PART, red, blockIdx.x, nb);
+    if (brank < nb) eval_block<THREADS>(c, gpart + (size_t)brank * TRK_PART, red, brank, nb);
     if (threadIdx.x == 0) tk[1] += clock64() - t0;
     __threadfence();
     cg::this_grid().sync();
@@ -553,6 +554,14 @@ __global__ void __launch_bounds__(THREADS) trk_track_kernel(TrackArgs a, float* 
   __shared__ double sy[8];
   __shared__ long long tk[4];   // [0] solve, [1] evaluation (inside [2]), [2] evaluation + barrier + fold, [3] accept
   if (threadIdx.x < 4) tk[threadIdx.x] = 0;
+  // CLUSTER: the grid is a BATCH of clusters, cluster m tracks member m (its own frame, initial pose and result slot);
+  // the members share nothing, so each is bit-identical to a launch of its own.
+  int brank = blockIdx.x, nblk = gridDim.x;
+  if (CLUSTER) {
+    cg::cluster_group cl = cg::this_cluster();
+    brank = (int)cl.block_rank(); nblk = (int)cl.num_blocks();
+    io += blockIdx.x / nblk;
+  }
 
   // Every block carries an identical copy of the LM state and takes identical decisions.
   if (threadIdx.x == 0) {
@@ -568,17 +577,17 @@ __global__ void __launch_bounds__(THREADS) trk_track_kernel(TrackArgs a, float* 
   for (int lvl = a.coarsestLvl; lvl >= 0; lvl--) {
     const TrkLevelDev& L = a.L[lvl];
     int nb = (L.n + THREADS - 1) / THREADS;
-    if (nb > (int)gridDim.x) nb = gridDim.x;
+    if (nb > nblk) nb = nblk;
     if (nb < 1) nb = 1;
     // --- initial evaluation with cutoff doubling, CoarseTracker.cpp:530-541
     if (threadIdx.x == 0) { s.levelCutoffRepeat = 1.f; }
     __syncthreads();
     while (true) {
       if (threadIdx.x == 0)
-        make_eval_const(c, L, lvl, a.img[lvl], s.cur, s.aff_cur[0], s.aff_cur[1], a.ref_exposure, a.new_exposure,
+        make_eval_const(c, L, lvl, io->img[lvl], s.cur, s.aff_cur[0], s.aff_cur[1], a.ref_exposure, io->new_exposure,
                         a.ref_aff_a, a.ref_aff_b, xmul(a.coarseCutoffTH, s.levelCutoffRepeat), a.huber);
       __syncthreads();
-      track_eval_and_fold<THREADS, CLUSTER>(c, buf ? partial1 : partial0, mypart[buf], red, fold, res, nb, tk);
+      track_eval_and_fold<THREADS, CLUSTER>(c, buf ? partial1 : partial0, mypart[buf], red, fold, res, nb, tk, brank);
       buf ^= 1;
       bool again = (sat_ratio(res) > 0.6) && (s.levelCutoffRepeat < 50.f);
       __syncthreads();
@@ -648,12 +657,12 @@ __global__ void __launch_bounds__(THREADS) trk_track_kernel(TrackArgs a, float* 
         s.aff_cand[0] = s.aff_cur[0] + incS[6];
         s.aff_cand[1] = s.aff_cur[1] + incS[7];
         s.incnorm = sqrt(nrm);
-        make_eval_const(c, L, lvl, a.img[lvl], s.cand, s.aff_cand[0], s.aff_cand[1], a.ref_exposure, a.new_exposure,
+        make_eval_const(c, L, lvl, io->img[lvl], s.cand, s.aff_cand[0], s.aff_cand[1], a.ref_exposure, io->new_exposure,
                         a.ref_aff_a, a.ref_aff_b, xmul(a.coarseCutoffTH, s.levelCutoffRepeat), a.huber);
       }
       __syncthreads();
       long long tk1 = clock64();
-      track_eval_and_fold<THREADS, CLUSTER>(c, buf ? partial1 : partial0, mypart[buf], red, fold, res, nb, tk);
+      track_eval_and_fold<THREADS, CLUSTER>(c, buf ? partial1 : partial0, mypart[buf], red, fold, res, nb, tk, brank);
       long long tk3 = clock64();
       buf ^= 1;
       if (threadIdx.x == 0) {
@@ -691,14 +700,14 @@ __global__ void __launch_bounds__(THREADS) trk_track_kernel(TrackArgs a, float* 
     }
   }
 
-  if (blockIdx.x == 0 && threadIdx.x == 0) {
+  if (brank == 0 && threadIdx.x == 0) {
     int ok = 0;
     if (!s.done) {
       ok = 1;
       double aa = s.aff_cur[0], ab = s.aff_cur[1];
       if ((a.affineOptModeA != 0.f && fabsf((float)aa) > 1.2f) || (a.affineOptModeB != 0.f && fabsf((float)ab) > 200.f))
         ok = 0;
-      float eF = a.ref_exposure, eT = a.new_exposure;
+      float eF = a.ref_exposure, eT = io->new_exposure;
       if (eF == 0.f || eT == 0.f) { eF = eT = 1.f; }
       double ra = exp(aa - a.ref_aff_a) * (double)eT / (double)eF;
       double rb = ab - ra * a.ref_aff_b;
@@ -737,8 +746,9 @@ struct hslam_tracker {
   unsigned int* ticket = nullptr;
   EvalResult* d_result = nullptr;
   EvalResult* h_result = nullptr;   // pinned
-  TrackIO* d_io = nullptr;
+  TrackIO* d_io = nullptr;          // [io_cap]: one slot per member of a batched launch
   TrackIO* h_io = nullptr;          // pinned
+  int io_cap = 0, n_inflight = 0;
   float4* h_pack = nullptr;         // pinned staging for set_ref
   size_t h_pack_cap = 0;
   int coop_blocks = 0;
@@ -773,6 +783,7 @@ int hslam_tracker_create(hslam_ctx* ctx, int w, int h, hslam_tracker** out) {
   HS_CUDA(cudaMallocHost(&t->h_result, sizeof(EvalResult)));
   HS_CUDA(cudaMalloc(&t->d_io, sizeof(TrackIO)));
   HS_CUDA(cudaMallocHost(&t->h_io, sizeof(TrackIO)));
+  t->io_cap = 1;
   int per_sm = 0;
   HS_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, trk_track_kernel<TRK_THREADS, false>, TRK_THREADS, 0));
   HS_ARG(per_sm >= 1, "hslam_tracker_create: track kernel does not fit on an SM");
@@ -967,20 +978,30 @@ int hslam_tracker_calc_gs(hslam_tracker* t, int lvl, const hslam_frame* f, const
   return 0;
 }
 
-int hslam_tracker_track_enqueue(hslam_tracker* t, const hslam_frame* f, float new_exposure, const double T[12],
-                                const double aff[2], int coarsestLvl, const double minResForAbort[5]) {
-  HS_ARG(t && f && T && aff, "hslam_tracker_track: null argument");
-  HS_ARG(coarsestLvl >= 0 && coarsestLvl < 5 && coarsestLvl < t->levels && coarsestLvl < f->levels,
+// Enqueue one launch that tracks `n` members (frames / pose hypotheses) against this tracker's reference: member m gets
+// its own thread-block cluster, its own TrackIO slot (initial pose in, results out) and its own frame.
+static int track_enqueue_n(hslam_tracker* t, int n, const hslam_frame* const* frames, const float* new_exposure,
+                           const double* T /*n*12*/, const double* aff /*n*2*/, int coarsestLvl, const double minResForAbort[5]) {
+  HS_ARG(t && frames && T && aff && n >= 1, "hslam_tracker_track: null argument");
+  HS_ARG(coarsestLvl >= 0 && coarsestLvl < 5 && coarsestLvl < t->levels,
          "hslam_tracker_track: coarsestLvl out of range (reference asserts < 5, CoarseTracker.cpp:511)");
-  HS_ARG(f->ctx == t->ctx, "hslam_tracker_track: frame belongs to another context");
-  HS_ARG(t->L[0].w == f->w && t->L[0].h == f->h, "hslam_tracker_track: frame size != tracker K size");
+  HS_ARG(n == 1 || t->cluster_ctas > 0, "hslam_tracker_track_batch: needs the cluster mode (hslam_tracker_set_mode(trk, 8 or 16))");
   hslam_ctx* ctx = t->ctx;
   HS_CUDA(cudaSetDevice(ctx->device));
+  if (n > t->io_cap) {
+    HS_CUDA(cudaStreamSynchronize(ctx->stream));   // nothing of the old slots is in flight
+    if (t->d_io) cudaFree(t->d_io);
+    if (t->h_io) cudaFreeHost(t->h_io);
+    t->d_io = nullptr; t->h_io = nullptr;
+    t->io_cap = std::max(n, 2 * t->io_cap);
+    HS_CUDA(cudaMalloc(&t->d_io, (size_t)t->io_cap * sizeof(TrackIO)));
+    HS_CUDA(cudaMallocHost((void**)&t->h_io, (size_t)t->io_cap * sizeof(TrackIO)));
+  }
   TrackArgs a;
   memset(&a, 0, sizeof(a));
   int maxn = 0;
   for (int l = 0; l <= coarsestLvl; ++l) {
-    a.L[l] = t->L[l]; a.img[l] = f->dI[l];
+    a.L[l] = t->L[l];
     if (t->L[l].n > maxn) maxn = t->L[l].n;
   }
   a.coarsestLvl = coarsestLvl;
@@ -988,22 +1009,26 @@ int hslam_tracker_track_enqueue(hslam_tracker* t, const hslam_frame* f, float ne
   scales_from(ctx->prm, a.scales8);
   a.coarseCutoffTH = ctx->prm.coarseCutoffTH; a.huber = ctx->prm.huberTH;
   a.affineOptModeA = ctx->prm.affineOptModeA; a.affineOptModeB = ctx->prm.affineOptModeB;
-  a.ref_exposure = t->ref_exposure; a.new_exposure = new_exposure;
+  a.ref_exposure = t->ref_exposure;
   a.ref_aff_a = t->ref_aff_a; a.ref_aff_b = t->ref_aff_b;
-  TrackIO* io = t->h_io;
-  memcpy(io->T, T, sizeof(io->T));
-  io->aff[0] = aff[0]; io->aff[1] = aff[1];
-  for (int i = 0; i < 5; ++i) io->minResForAbort[i] = minResForAbort ? minResForAbort[i] : NAN;
-  HS_CUDA(cudaMemcpyAsync(t->d_io, io, sizeof(TrackIO), cudaMemcpyHostToDevice, ctx->stream));
-  int blocks = (maxn + TRK_THREADS - 1) / TRK_THREADS;
-  if (blocks < 1) blocks = 1;
-  if (blocks > t->coop_blocks) blocks = t->coop_blocks;
-  int rc = ensure_partials(t, blocks);
-  if (rc) return rc;
+  for (int m = 0; m < n; ++m) {
+    const hslam_frame* f = frames[m];
+    HS_ARG(f && f->ctx == t->ctx, "hslam_tracker_track: frame missing or from another context");
+    HS_ARG(coarsestLvl < f->levels, "hslam_tracker_track: coarsestLvl beyond the frame's pyramid");
+    HS_ARG(t->L[0].w == f->w && t->L[0].h == f->h, "hslam_tracker_track: frame size != tracker K size");
+    TrackIO* io = t->h_io + m;
+    memset(io, 0, sizeof(TrackIO));
+    memcpy(io->T, T + 12 * m, sizeof(io->T));
+    io->aff[0] = aff[2 * m]; io->aff[1] = aff[2 * m + 1];
+    for (int i = 0; i < 5; ++i) io->minResForAbort[i] = minResForAbort ? minResForAbort[i] : NAN;
+    for (int l = 0; l <= coarsestLvl; ++l) io->img[l] = f->dI[l];
+    io->new_exposure = new_exposure ? new_exposure[m] : 1.f;
+  }
+  HS_CUDA(cudaMemcpyAsync(t->d_io, t->h_io, (size_t)n * sizeof(TrackIO), cudaMemcpyHostToDevice, ctx->stream));
   cudaError_t lerr = cudaSuccess;
   if (t->cluster_ctas > 0) {
     cudaLaunchConfig_t cfg = {};
-    cfg.gridDim = dim3(t->cluster_ctas); cfg.blockDim = dim3(TRK_CL_THREADS); cfg.stream = ctx->stream;
+    cfg.gridDim = dim3(t->cluster_ctas * n); cfg.blockDim = dim3(TRK_CL_THREADS); cfg.stream = ctx->stream;
     cudaLaunchAttribute at[1];
     at[0].id = cudaLaunchAttributeClusterDimension;
     at[0].val.clusterDim.x = t->cluster_ctas; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
@@ -1011,13 +1036,37 @@ int hslam_tracker_track_enqueue(hslam_tracker* t, const hslam_frame* f, float ne
     float* nullp = nullptr;
     HS_LAUNCH(ctx, HSLAM_K_TRK_TRACK, (lerr = cudaLaunchKernelEx(&cfg, trk_track_kernel<TRK_CL_THREADS, true>, a, nullp, nullp, t->d_io)));
   } else {
+    int blocks = (maxn + TRK_THREADS - 1) / TRK_THREADS;
+    if (blocks < 1) blocks = 1;
+    if (blocks > t->coop_blocks) blocks = t->coop_blocks;
+    int rc = ensure_partials(t, blocks);
+    if (rc) return rc;
     void* args[] = {&a, &t->partial[0], &t->partial[1], &t->d_io};
     HS_LAUNCH(ctx, HSLAM_K_TRK_TRACK, (lerr = cudaLaunchCooperativeKernel((void*)trk_track_kernel<TRK_THREADS, false>, dim3(blocks),
                                                                          dim3(TRK_THREADS), args, 0, ctx->stream)));
   }
   HS_CUDA(lerr);
-  HS_CUDA(cudaMemcpyAsync(t->h_io, t->d_io, sizeof(TrackIO), cudaMemcpyDeviceToHost, ctx->stream));
+  HS_CUDA(cudaMemcpyAsync(t->h_io, t->d_io, (size_t)n * sizeof(TrackIO), cudaMemcpyDeviceToHost, ctx->stream));
+  t->n_inflight = n;
   return 0;
+}
+
+static void track_unpack(hslam_tracker* t, int m, double T_out[12], double aff_out[2], double lastResiduals[5], double lastFlow[3],
+                         int* ok, int* iterations_out) {
+  const TrackIO* io = t->h_io + m;
+  // the reference writes lastToNew_out/aff_g2l_out only when all levels ran (:663-664); the kernel mirrors that
+  if (T_out) memcpy(T_out, io->T, sizeof(io->T));
+  if (aff_out) { aff_out[0] = io->aff[0]; aff_out[1] = io->aff[1]; }
+  if (lastResiduals) memcpy(lastResiduals, io->lastResiduals, sizeof(io->lastResiduals));
+  if (lastFlow) memcpy(lastFlow, io->lastFlow, sizeof(io->lastFlow));
+  if (ok) *ok = io->ok;
+  if (iterations_out) memcpy(iterations_out, io->iterations, sizeof(io->iterations));
+}
+
+int hslam_tracker_track_enqueue(hslam_tracker* t, const hslam_frame* f, float new_exposure, const double T[12],
+                                const double aff[2], int coarsestLvl, const double minResForAbort[5]) {
+  HS_ARG(t && f && T && aff, "hslam_tracker_track: null argument");
+  return track_enqueue_n(t, 1, &f, &new_exposure, T, aff, coarsestLvl, minResForAbort);
 }
 
 int hslam_tracker_track_finish(hslam_tracker* t, double T_out[12], double aff_out[2], double lastResiduals[5],
@@ -1025,18 +1074,24 @@ int hslam_tracker_track_finish(hslam_tracker* t, double T_out[12], double aff_ou
   HS_ARG(t, "hslam_tracker_track_finish: null");
   HS_CUDA(cudaSetDevice(t->ctx->device));
   HS_CUDA(cudaStreamSynchronize(t->ctx->stream));
-  const TrackIO* io = t->h_io;
-  if (io->ok || true) {
-    // the reference writes lastToNew_out/aff_g2l_out only when all levels ran (:663-664)
-    if (T_out) memcpy(T_out, io->T, sizeof(io->T));
-    if (aff_out) { aff_out[0] = io->aff[0]; aff_out[1] = io->aff[1]; }
-  }
-  if (lastResiduals) memcpy(lastResiduals, io->lastResiduals, sizeof(io->lastResiduals));
-  if (lastFlow) memcpy(lastFlow, io->lastFlow, sizeof(io->lastFlow));
-  if (ok) *ok = io->ok;
-  if (iterations_out) memcpy(iterations_out, io->iterations, sizeof(io->iterations));
-  memcpy(t->last_phase_cycles, io->phase_cycles, sizeof(io->phase_cycles));
-  t->last_evals = io->evals;
+  track_unpack(t, 0, T_out, aff_out, lastResiduals, lastFlow, ok, iterations_out);
+  memcpy(t->last_phase_cycles, t->h_io->phase_cycles, sizeof(t->h_io->phase_cycles));
+  t->last_evals = t->h_io->evals;
+  return 0;
+}
+
+int hslam_tracker_track_batch(hslam_tracker* t, int n, const hslam_frame* const* frames, const float* new_exposure,
+                              double* T_io, double* aff_io, int coarsestLvl, const double minResForAbort[5],
+                              double* lastResiduals, double* lastFlow, int* ok, int* iterations_out) {
+  HS_ARG(t && n >= 1 && frames && T_io && aff_io, "hslam_tracker_track_batch: bad argument");
+  int rc = track_enqueue_n(t, n, frames, new_exposure, T_io, aff_io, coarsestLvl, minResForAbort);
+  if (rc) return rc;
+  HS_CUDA(cudaStreamSynchronize(t->ctx->stream));
+  for (int m = 0; m < n; ++m)
+    track_unpack(t, m, T_io + 12 * m, aff_io + 2 * m, lastResiduals ? lastResiduals + 5 * m : nullptr,
+                 lastFlow ? lastFlow + 3 * m : nullptr, ok ? ok + m : nullptr, iterations_out ? iterations_out + 5 * m : nullptr);
+  memcpy(t->last_phase_cycles, t->h_io->phase_cycles, sizeof(t->h_io->phase_cycles));
+  t->last_evals = t->h_io->evals;
   return 0;
 }
 

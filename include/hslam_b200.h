@@ -225,6 +225,16 @@ int hslam_tracker_track_finish(hslam_tracker* trk, double refToNew_out[12], doub
                                double lastResiduals[5], double lastFlow[3], int* ok,
                                int* iterations_out);
 
+/* Batched form: `n` members — several incoming frames, or several initial poses (the motion hypotheses
+ * lastF_2_fh_tries of System::trackNewCoarse, Src/System.cpp:348-481; pass the same frame n times) — are tracked against
+ * this tracker's reference in ONE launch, one thread-block cluster per member (needs the cluster mode).  All arrays are
+ * member-major: T_io n*12, aff_io n*2, new_exposure n (nullable: 1), lastResiduals n*5, lastFlow n*3, ok n,
+ * iterations_out n*5 (each output nullable).  Every member's result is bit-identical to hslam_tracker_track of that
+ * member alone; the caller applies the reference's sequential acceptance rule (System.cpp:428-481) to the results. */
+int hslam_tracker_track_batch(hslam_tracker* trk, int n, const hslam_frame* const* frames, const float* new_exposure,
+                              double* T_io, double* aff_io, int coarsestLvl, const double minResForAbort[5],
+                              double* lastResiduals, double* lastFlow, int* ok, int* iterations_out);
+
 /* -------------------------------------------------------------- window BA ---
  * Device-resident mirror of EnergyFunctional + its points/residuals
  * (Include/EnergyFunctional.h:30-121).  Re-pack only when the reference

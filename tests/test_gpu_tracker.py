@@ -256,3 +256,40 @@ def test_cluster_and_cooperative_modes_agree(ctx, capi, O, tracking_pair):
     ok4, T4, _ = trk.trackNewestCoarse(frame, T_ID, (0.0, 0.0), tp.levels - 1)
     assert np.array_equal(T3, T4)
     trk.close(); frame.close()
+
+
+def test_track_batch_members_bit_identical_to_single_calls(ctx, capi, synth, tracking_pair_small):
+    """hslam_tracker_track_batch: several initial poses (motion hypotheses, System.cpp:348-481) and two different frames
+    in ONE launch, one cluster per member: every member's pose, affine parameters, residuals, flow indicators, iteration
+    counts and return value are bit-identical to hslam_tracker_track of that member alone."""
+    tp = tracking_pair_small
+    trk = capi.CoarseTracker(ctx, tp.cam.w, tp.cam.h)
+    trk.makeK(tp.cam, tp.levels)
+    trk.setCoarseTrackingRef(tp.pc)
+    if trk.get_mode() == 0:
+        pytest.skip("no cluster launch on this device")
+    f_new = capi.Frame(ctx, tp.img_new, tp.levels)
+    f_ref = capi.Frame(ctx, tp.img_ref, tp.levels)
+    rng = np.random.default_rng(4)
+    Ts, affs, frames = [], [], []
+    for m in range(9):
+        xi = np.zeros(6) if m == 0 else rng.normal(0, [0.01, 0.01, 0.01, 0.004, 0.004, 0.004])
+        R, t = synth.se3_exp(xi)
+        Ts.append(synth.T12(R, t)); affs.append((0.0, 0.0) if m < 5 else (0.01 * m, 0.5 * m))
+        frames.append(f_ref if m in (3, 7) else f_new)
+    # a hopeless start (tracking is expected to fail or to abort): the failure must be reproduced too
+    R, t = synth.se3_exp(np.array([0.5, -0.4, 0.3, 0.3, -0.2, 0.25]))
+    Ts.append(synth.T12(R, t)); affs.append((0.0, 0.0)); frames.append(f_new)
+    mra = np.array([np.nan, np.nan, np.nan, np.nan, np.nan])
+    got = trk.trackNewestCoarse_batch(frames, Ts, affs, tp.levels - 1, mra)
+    n_ok = 0
+    for m in range(len(frames)):
+        ok, T, aff = trk.trackNewestCoarse(frames[m], Ts[m], affs[m], tp.levels - 1, mra)
+        assert ok == got["ok"][m]
+        assert np.array_equal(T, got["T"][m]) and np.array_equal(aff, got["aff"][m]), m
+        assert np.array_equal(trk.lastResiduals, got["lastResiduals"][m], equal_nan=True)
+        assert np.array_equal(trk.lastFlowIndicators, got["lastFlow"][m])
+        assert np.array_equal(trk.iterations, got["iterations"][m])
+        n_ok += int(ok)
+    assert n_ok >= 8
+    trk.close(); f_new.close(); f_ref.close()
