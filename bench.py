@@ -489,6 +489,19 @@ def extras(ctx, capi, synth, torch, stream, ef0, win0):
                 r_ = trk.trackNewestCoarse_batch(*args_)
             out[f"tracking_batch{nb_}_ms_per_frame"] = 1e3 * (time.perf_counter() - t0) / (reps * nb_)
             its = r_["iterations"][0]
+        # the same 32 members with 8-CTA clusters (twice as many clusters resident at once)
+        try:
+            trk.set_mode(8)
+            args_ = ([frame] * 32, [T0] * 32, [(0.0, 0.0)] * 32, tp.levels - 1)
+            for _ in range(2):
+                trk.trackNewestCoarse_batch(*args_)
+            t0 = time.perf_counter()
+            for _ in range(reps):
+                trk.trackNewestCoarse_batch(*args_)
+            out["tracking_batch32_cluster8_ms_per_frame"] = 1e3 * (time.perf_counter() - t0) / (reps * 32)
+        except Exception as e:
+            out["tracking_batch32_cluster8_error"] = repr(e)
+        trk.set_mode(out["tracking_mode_cluster_ctas"])
     # roofline of Stage T: 64 algorithmic bytes per point-evaluation, evaluations ~ sum_l (1 + iterations_l) * N_l
     if its is not None:
         peak_ = 6555.2
@@ -498,7 +511,8 @@ def extras(ctx, capi, synth, torch, stream, ef0, win0):
             pass
         evals = sum((1 + int(i)) * len(p_[0]) for i, p_ in zip(its, tp.pc))
         out["tracking_point_evaluations_per_frame"] = int(evals)
-        for key in ("tracking_ms_per_frame_device", "tracking_8_streams_ms_per_frame", "tracking_batch8_ms_per_frame", "tracking_batch32_ms_per_frame"):
+        for key in ("tracking_ms_per_frame_device", "tracking_8_streams_ms_per_frame", "tracking_batch8_ms_per_frame", "tracking_batch32_ms_per_frame",
+                    "tracking_batch32_cluster8_ms_per_frame"):
             if key in out:
                 out[key.replace("_ms_per_frame", "") + "_roofline_frac"] = evals * 64 / (out[key] * 1e-3) / 1e9 / peak_
         out["tracking_roofline_note"] = ("64 B per point-evaluation / measured HBM peak; a single frame is latency-bound by construction "
