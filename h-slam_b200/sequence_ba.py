@@ -20,7 +20,7 @@ tracking reference.
 Out of scope here, replaced by documented stand-ins (they are host-side policy / algebra):
   * immature points + activation: new points start from the rendered depth with 5 % noise;
   * marginalisation (HM, bM): the oldest keyframe is dropped, and the TWO oldest keyframes of the window carry the strong
-    first-frame prior (Frame.h:229-256) so that gauge and scale stay fixed;
+    first-frame prior (Frame.h:229-256) at their latest estimate, so that gauge and scale stay fixed;
   * nullspace orthogonalisation of x; the calibration is held by its prior (setting_initialCalibHessian).
 """
 from __future__ import annotations
@@ -120,7 +120,8 @@ def build_window(cam, kfs):
         cam=cam, n=n, images=[k.img for k in kfs], T_w2c_eval=np.array(T_eval), state=state, state_zero=state_zero,
         ab_exposure=exposure, frameEnergyTH=np.array([k.frameEnergyTH for k in kfs], np.float32), precalc=precalc, adHost=adH,
         adTarget=adT, adHTdeltaF=adHTd, cDeltaF=np.zeros(4, np.float32), cPrior=np.full(4, 5e9), framePrior=prior.reshape(-1),
-        frameDeltaPrior=(state[:, :8] - state_zero[:, :8]).reshape(-1).copy(), u=u, v=v, idepth=idepth.copy(), idepth_zero=idepth.copy(),
+        frameDeltaPrior=state[:, :8].reshape(-1).copy(),   # delta_prior = state - getPriorZero() = state (Frame.h:259-266)
+        u=u, v=v, idepth=idepth.copy(), idepth_zero=idepth.copy(),
         color=color, weights=weights, priorF=np.zeros(P, np.float32), deltaF=np.zeros(P, np.float32), host_idx=host_idx,
         res_begin=(np.arange(P + 1, dtype=np.int32) * (n - 1)), res_index=np.arange(R_, dtype=np.int32),
         point_idx=np.repeat(np.arange(P, dtype=np.int32), n - 1), target_idx=others.reshape(-1).astype(np.int32),
@@ -175,7 +176,7 @@ def optimize_window(cam, kfs, ba, max_iters, log):
         win.state = np.array([k.state for k in kfs])
         win.precalc, win.adHost, win.adTarget, win.adHTdeltaF = synth.prepare_window_tables(
             cam, [k.T_eval for k in kfs], win.state, win.state_zero, win.ab_exposure)
-        win.frameDeltaPrior = (win.state[:, :8] - win.state_zero[:, :8]).reshape(-1).copy()
+        win.frameDeltaPrior = win.state[:, :8].reshape(-1).copy()
         ba.set_tables(win)
         ba.update_points(win.idepth, win.deltaF, win.idepth_zero)
         lin = linearize(False)
@@ -242,6 +243,11 @@ def run_sequence_ba(cam, Ts_true, frames, levels, backend, kf_every=8, pts_per_k
             if len(kfs) > max_kf:
                 old = kfs.pop(0)
                 backend.free_frame(old.handle)
+            # the two oldest keyframes are the gauge: they are held (strong prior, build_window) at their LATEST estimate,
+            # i.e. their linearisation point is re-based on it (stand-in for the marginalisation prior, which would
+            # carry that information in the reference)
+            for q in kfs[:2]:
+                q.T_eval = q.T_now(); q.state[:6] = 0.0; q.state_zero[:6] = 0.0
             t0 = time.perf_counter()
             win = build_window(cam, kfs)
             ba = backend.open_ba(win, [q.handle for q in kfs])
