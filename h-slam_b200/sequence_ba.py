@@ -141,6 +141,28 @@ def solve_system(sys3, n, lam=1e-5):
     return sv * np.linalg.solve(Hs, sv * bF)
 
 
+class _Timed:
+    """Forwards to the back end's BA object and accumulates the wall time spent inside it (the hot-path share of a
+    keyframe, as opposed to the host code both back ends share)."""
+
+    def __init__(self, ba, wall):
+        self._ba, self._wall = ba, wall
+        self.win = ba.win
+
+    def __getattr__(self, name):
+        fn = getattr(self._ba, name)
+        if not callable(fn):
+            return fn
+
+        def call(*a, **k):
+            t0 = time.perf_counter()
+            try:
+                return fn(*a, **k)
+            finally:
+                self._wall["ba_backend"] += time.perf_counter() - t0
+        return call
+
+
 def optimize_window(cam, kfs, ba, max_iters, log):
     """System::optimize (FullSystemOptimize.cpp:362-546) over the current window through the back end's BA object."""
     n = len(kfs)
@@ -205,7 +227,7 @@ def run_sequence_ba(cam, Ts_true, frames, levels, backend, kf_every=8, pts_per_k
     rng = np.random.default_rng(seed)
     n = len(frames)
     log = dict(ba_iterations=[], ba_states=[], ba_energy=[], thresholds=[])
-    wall = dict(track=0.0, ba=0.0, reference=0.0)
+    wall = dict(track=0.0, ba=0.0, ba_backend=0.0, reference=0.0)
     est = [np.array(Ts_true[0], np.float64)]
     oks = [True]
 
@@ -250,8 +272,10 @@ def run_sequence_ba(cam, Ts_true, frames, levels, backend, kf_every=8, pts_per_k
                 q.T_eval = q.T_now(); q.state[:6] = 0.0; q.state_zero[:6] = 0.0
             t0 = time.perf_counter()
             win = build_window(cam, kfs)
+            tb = time.perf_counter()
             ba = backend.open_ba(win, [q.handle for q in kfs])
-            lin = optimize_window(cam, kfs, ba, max_iters, log)
+            wall["ba_backend"] += time.perf_counter() - tb
+            lin = optimize_window(cam, kfs, _Timed(ba, wall), max_iters, log)
             wall["ba"] += time.perf_counter() - t0
             # setEvalPT of the newest frame (FullSystemOptimize.cpp:498-506): its linearisation point becomes the estimate
             kf.T_eval = kf.T_now(); kf.state[:6] = 0.0; kf.state_zero = kf.state.copy()
@@ -261,13 +285,15 @@ def run_sequence_ba(cam, Ts_true, frames, levels, backend, kf_every=8, pts_per_k
             t0 = time.perf_counter()
             ids = np.nonzero((win.target_idx == len(kfs) - 1) & (lin["newState"] == RES_IN))[0].astype(np.int32)
             trk.close()
-            trk = backend.tracker_from_ba(cam, levels, kf, ba, win, lin, ids)
+            trk = backend.tracker_from_ba(cam, levels, kf, getattr(ba, "_ba", ba), win, lin, ids)
             wall["reference"] += time.perf_counter() - t0
             ba.close()
             last, last2, aff = synth.T12(np.eye(3), np.zeros(3)), None, np.array(kf.aff_now())
     trk.close()
     for q in kfs:
         backend.free_frame(q.handle)
+    if hasattr(backend, "close"):
+        backend.close()
 
     def centre(T):
         R, t = synth.T12_split(T)
@@ -279,20 +305,22 @@ def run_sequence_ba(cam, Ts_true, frames, levels, backend, kf_every=8, pts_per_k
 
 # ------------------------------------------------------------------------------------------------ CUDA back end
 class _CudaTracker:
-    def __init__(self, capi, ctx, trk, levels):
-        self.capi, self.ctx, self.trk, self.levels, self.frame = capi, ctx, trk, levels, None
+    """The tracker and the incoming-frame buffers live as long as the back end (the reference keeps two CoarseTracker
+    instances and swaps them, System.cpp:127-133): a new keyframe only rebuilds the reference cloud."""
+
+    def __init__(self, backend, trk, levels):
+        self.backend, self.trk, self.levels = backend, trk, levels
 
     def track(self, img, T0, aff0, coarsest):
-        if self.frame is None:
-            self.frame = self.capi.Frame(self.ctx, img, self.levels)
+        b = self.backend
+        if b._frame is None:
+            b._frame = b.capi.Frame(b.ctx, img, self.levels)
         else:
-            self.frame.update(img)
-        return self.trk.trackNewestCoarse(self.frame, T0, aff0, coarsest)
+            b._frame.update(img)
+        return self.trk.trackNewestCoarse(b._frame, T0, aff0, coarsest)
 
     def close(self):
-        self.trk.close()
-        if self.frame is not None:
-            self.frame.close()
+        pass
 
 
 class _CudaBA:
@@ -332,6 +360,8 @@ class CudaBackend:
 
     def __init__(self, capi, ctx):
         self.capi, self.ctx = capi, ctx
+        self._trk = None          # one CoarseTracker, re-referenced at every keyframe
+        self._frame = None        # one device frame for the incoming images
 
     def new_frame(self, img, levels):
         return self.capi.Frame(self.ctx, img, levels)
@@ -342,17 +372,27 @@ class CudaBackend:
     def open_ba(self, win, handles):
         return _CudaBA(self.capi, self.ctx, win, handles)
 
+    def _tracker(self, cam, levels):
+        if self._trk is None:
+            self._trk = self.capi.CoarseTracker(self.ctx, cam.w, cam.h)
+            self._trk.makeK(cam, levels)
+        return self._trk
+
     def tracker_from_points(self, cam, levels, kf):
-        trk = self.capi.CoarseTracker(self.ctx, cam.w, cam.h)
-        trk.makeK(cam, levels)
+        trk = self._tracker(cam, levels)
         cpt = np.stack([kf.u, kf.v, kf.idepth], 1).astype(np.float32)
         hdi = np.full(len(kf.u), 1e-3, np.float32)            # weight sqrt(1e-3 / (HdiF + 1e-12)) ~ 1
         trk.makeCoarseDepthL0(kf.handle, cpt, hdi, ref_aff=kf.aff_now())
-        return _CudaTracker(self.capi, self.ctx, trk, levels)
+        return _CudaTracker(self, trk, levels)
 
     def tracker_from_ba(self, cam, levels, kf, ba, win, lin, ids):
-        trk = self.capi.CoarseTracker(self.ctx, cam.w, cam.h)
-        trk.makeK(cam, levels)
+        trk = self._tracker(cam, levels)
         # device-resident: centerProjectedTo of the last linearisation and HdiF of the last Schur pass never leave HBM
         trk.makeCoarseDepthL0_from_ba(kf.handle, ba.ef, ids, ref_aff=kf.aff_now())
-        return _CudaTracker(self.capi, self.ctx, trk, levels)
+        return _CudaTracker(self, trk, levels)
+
+    def close(self):
+        if self._trk is not None:
+            self._trk.close(); self._trk = None
+        if self._frame is not None:
+            self._frame.close(); self._frame = None
