@@ -1,0 +1,342 @@
+// ref_driver.cpp — C interface around the UNMODIFIED reference translation units of the BA hot path.  TEST INFRASTRUCTURE.
+//
+// oracle/Makefile compiles, from where they lie under /root/reference (nothing is copied into this repository):
+//     Src/OptimizationClasses.cpp      FrameFramePrecalc::set, PointFrameResidual::linearize / applyRes / fixLinearizationF
+//     Src/AccumulatedTopHessian.cpp    AccumulatedTopHessianSSE::addPoint<mode>, stitchDouble, stitchDoubleInternal
+//     Src/AccumulatedSCHessian.cpp     AccumulatedSCHessianSSE::addPoint, stitchDouble, stitchDoubleInternal
+//     Src/Settings.cpp                 the setting_* globals
+// together with their own headers (Include/GlobalTypes.h, MatrixAccumulators.h, OptimizationClasses.h, DirectProjection.h,
+// CalibData.h, Frame.h, MapPoint.h, EnergyFunctional.h, Accumulated*Hessian.h, IndexThreadReduce.h, ...) against the small
+// stand-ins of oracle/ref_shim/ for the libraries this image lacks (Eigen, Sophus-on-Eigen, Boost.Thread, the OpenCV /
+// DBoW3 type names), into oracle/_ref/libhslam_ref.so.  This file is OUR code: it builds the reference's object graph
+// (FrameShell / Frame / FrameOptimizationData / MapPoint / PointFrameResidual / EnergyFunctional / CalibData) from the same
+// flat window description the oracle and the CUDA library take, calls the reference's member functions in the order of
+// EnergyFunctional::accumulate{A,L,SC}F_MT's single-thread branch (Src/EnergyFunctional.cpp:155-220: that file itself
+// needs Eigen's LDLT / SVD and is not compiled) and of System::linearizeAll_Reductor / applyRes_Reductor (Src/
+// FullSystemOptimize.cpp:19-59), and hands the results back as flat arrays.  It also DEFINES the few out-of-line symbols
+// whose own translation units are not part of the path (Frame / ImmaturePoint / EnergyFunctional constructors, static
+// members): trivial bodies, they only have to satisfy the linker.
+//
+// tests/test_oracle_vs_reference.py feeds one window to this library and to the oracle's float restatement and compares
+// every output: that is what pins the oracle to the reference's own code.
+#include "AccumulatedSCHessian.h"
+#include "AccumulatedTopHessian.h"
+#include "CalibData.h"
+#include "EnergyFunctional.h"
+#include "Frame.h"
+#include "MapPoint.h"
+#include "OptimizationClasses.h"
+
+#include "hslam_oracle.h"   // orc_window + the hslam_*_soa data-format structs
+
+using namespace FSLAM;
+
+// ---- out-of-line symbols of translation units that are not on the path ---------------------------------------------
+namespace FSLAM {
+bool EFAdjointsValid = false, EFIndicesValid = false, EFDeltaValid = false;   // Src/EnergyFunctional.cpp:17-19
+size_t FrameShell::Globalid = 0;
+int FrameShell::GlobalKfId = 0;
+int Frame::mnGridCols = 0, Frame::mnGridRows = 0, Frame::EDGE_THRESHOLD = 0;
+float Frame::mnMinX = 0, Frame::mnMaxX = 0, Frame::mnMinY = 0, Frame::mnMaxY = 0, Frame::mfGridElementWidthInv = 0,
+      Frame::mfGridElementHeightInv = 0;
+bool Frame::GridStructInit = false;
+Frame::Frame(std::shared_ptr<ImageData>, int id, float, std::shared_ptr<FeatureDetector>, std::shared_ptr<CalibData> _Calib,
+             std::shared_ptr<IndexThreadReduce<Vec10>>, bool)
+    : idx(id), Calib(_Calib) {
+  frameEnergyTH = 8 * 8 * patternNum;   // Src/Frame.cpp:47
+  FlaggedForMarginalization = false; isReduced = false; NeedRefresh = false; nFeatures = 0; MovedByOpt = 0;
+  statistics_outlierResOnThis = statistics_goodResOnThis = 0;
+}
+Frame::~Frame() {}
+ImmaturePoint::ImmaturePoint(float u_, float v_, shared_ptr<FrameShell> host_, float type, shared_ptr<CalibData>)
+    : u(u_), v(v_), host(host_), my_type(type), idepth_min(0), idepth_max(NAN) {
+  energyTH = 0; quality = 0; idxInImmaturePoints = 0; lastTraceStatus = IPS_UNINITIALIZED; lastTracePixelInterval = 0;
+}
+EnergyFunctional::EnergyFunctional() {
+  adHost = adTarget = nullptr; adHostF = adTargetF = nullptr; adHTdeltaF = nullptr; red = nullptr;
+  accSSE_top_L = accSSE_top_A = nullptr; accSSE_bot = nullptr;
+  nFrames = nResiduals = nPoints = 0; resInA = resInL = resInM = 0; currentLambda = 0;
+}
+EnergyFunctional::~EnergyFunctional() {}
+}  // namespace FSLAM
+
+struct ref_ba {
+  std::shared_ptr<CalibData> calib;
+  std::shared_ptr<EnergyFunctional> ef;
+  std::vector<std::shared_ptr<FrameShell>> frames;
+  std::vector<std::shared_ptr<MapPoint>> points;              // caller order
+  std::vector<std::shared_ptr<PointFrameResidual>> residuals; // caller order
+  std::vector<Mat88> adHost, adTarget;
+  std::vector<Mat88f> adHostF, adTargetF;
+  std::vector<Mat18f> adHTdeltaF;
+  AccumulatedTopHessianSSE topA, topL;
+  AccumulatedSCHessianSSE bot;
+  int n = 0;
+};
+
+extern "C" {
+
+ref_ba* ref_ba_create(void) { return new ref_ba(); }
+void ref_ba_destroy(ref_ba* b) {
+  if (!b) return;
+  for (auto& r : b->residuals) r->Clear();
+  for (auto& p : b->points) p->Clear();
+  delete b;
+}
+
+int ref_ba_set_window(ref_ba* b, const orc_window* w) {
+  const int n = w->n_frames;
+  const bool fresh = b->n != n || b->frames.empty();
+  if (fresh) {
+    b->n = n;
+    Mat33 K = Mat33::Identity();
+    K(0, 0) = w->fx; K(1, 1) = w->fy; K(0, 2) = w->cx; K(1, 2) = w->cy;
+    int dirPyr = 1;
+    b->calib.reset(new CalibData(w->w, w->h, K, 0.f, nullptr, nullptr, dirPyr, 1, 1.2f));
+    b->ef.reset(new EnergyFunctional());
+    b->frames.clear();
+    std::shared_ptr<ImageData> img(new ImageData(1, 1));
+    img->timestamp = 0; img->ExposureL = 1.f; img->ExposureR = 1.f;
+    for (int f = 0; f < n; ++f) {
+      std::shared_ptr<FrameShell> fs(new FrameShell(img, nullptr, b->calib, nullptr, false));
+      fs->frame->idx = f;
+      fs->frame->efFrame.reset(new FrameOptimizationData(f, 1.f));
+      fs->frame->targetPrecalc.resize(n);
+      fs->frame->DirPyr.resize(1);
+      b->frames.push_back(fs);
+    }
+    b->ef->frames = b->frames;
+    b->ef->nFrames = n;
+    b->adHost.resize(n * n); b->adTarget.resize(n * n); b->adHostF.resize(n * n); b->adTargetF.resize(n * n); b->adHTdeltaF.resize(n * n);
+    b->ef->adHost = b->adHost.data(); b->ef->adTarget = b->adTarget.data();
+    b->ef->adHostF = b->adHostF.data(); b->ef->adTargetF = b->adTargetF.data(); b->ef->adHTdeltaF = b->adHTdeltaF.data();
+    b->ef->accSSE_top_A = &b->topA; b->ef->accSSE_top_L = &b->topL; b->ef->accSSE_bot = &b->bot;
+  }
+  for (int f = 0; f < n; ++f) {
+    Frame& F = *b->frames[f]->frame;
+    F.DirPyr[0] = reinterpret_cast<Vec3f*>(const_cast<float*>(w->dI[f]));
+    F.frameEnergyTH = w->frameEnergyTH[f];
+    for (int i = 0; i < 8; ++i) { F.efFrame->prior[i] = w->framePrior[8 * f + i]; F.efFrame->delta_prior[i] = w->frameDeltaPrior[8 * f + i]; }
+  }
+  for (int h = 0; h < n; ++h)
+    for (int t = 0; t < n; ++t) {
+      const int idx = h + t * n;
+      const float* p = w->precalc + (size_t)HSLAM_PRECALC_STRIDE * idx;
+      FrameFramePrecalc& P = b->frames[h]->frame->targetPrecalc[t];
+      P.host = b->frames[h]; P.target = b->frames[t];
+      for (int i = 0; i < 3; ++i)
+        for (int j = 0; j < 3; ++j) { P.PRE_KRKiTll(i, j) = p[3 * i + j]; P.PRE_RTll_0(i, j) = p[12 + 3 * i + j]; }
+      for (int i = 0; i < 3; ++i) { P.PRE_KtTll[i] = p[9 + i]; P.PRE_tTll_0[i] = p[21 + i]; }
+      P.PRE_aff_mode[0] = p[24]; P.PRE_aff_mode[1] = p[25]; P.PRE_b0_mode = p[26];
+      for (int c = 0; c < 8; ++c)
+        for (int r = 0; r < 8; ++r) {   // col-major tables
+          b->adHost[idx](r, c) = w->adHost[64 * (size_t)idx + r + 8 * c];
+          b->adTarget[idx](r, c) = w->adTarget[64 * (size_t)idx + r + 8 * c];
+        }
+      b->adHostF[idx] = b->adHost[idx].cast<float>();     // Src/EnergyFunctional.cpp:73-74
+      b->adTargetF[idx] = b->adTarget[idx].cast<float>();
+      for (int i = 0; i < 8; ++i) b->adHTdeltaF[idx][i] = w->adHTdeltaF[8 * (size_t)idx + i];
+    }
+  for (int i = 0; i < 4; ++i) { b->ef->cDeltaF[i] = w->cDeltaF[i]; b->ef->cPrior[i] = w->cPrior[i]; }
+  b->ef->cPriorF = b->ef->cPrior.cast<float>();
+  return 0;
+}
+
+int ref_ba_set_topology(ref_ba* b, const hslam_point_soa* p, const hslam_residual_soa* r) {
+  for (auto& q : b->residuals) q->Clear();
+  for (auto& q : b->points) q->Clear();
+  b->points.clear(); b->residuals.clear();
+  for (auto& f : b->frames) f->frame->pointHessians.clear();
+  const int P = p->n_points, R = r->n_residuals;
+  for (int i = 0; i < P; ++i) {
+    std::shared_ptr<FrameShell>& host = b->frames[p->host_idx[i]];
+    std::shared_ptr<ImmaturePoint> raw(new ImmaturePoint(p->u[i], p->v[i], host, 0.f, b->calib));
+    memcpy(raw->color, p->color + 8 * (size_t)i, sizeof(float) * 8);
+    memcpy(raw->weights, p->weights + 8 * (size_t)i, sizeof(float) * 8);
+    raw->idepth_min = raw->idepth_max = p->idepth[i];
+    std::shared_ptr<MapPoint> mp(new MapPoint(raw, b->calib));
+    mp->setIdepth(p->idepth[i]);
+    mp->efPoint->setIdepthZero(p->idepth_zero[i]);
+    mp->efPoint->priorF = p->priorF[i];
+    mp->efPoint->deltaF = p->deltaF[i];
+    mp->setPointStatus(ACTIVE);
+    mp->idx = i;
+    b->points.push_back(mp);
+    host->frame->pointHessians.push_back(mp);
+  }
+  b->residuals.resize(R);
+  for (int i = 0; i < P; ++i)
+    for (int k = p->res_begin[i]; k < p->res_begin[i + 1]; ++k) {
+      const int id = p->res_index[k];
+      std::shared_ptr<MapPoint>& mp = b->points[i];
+      std::shared_ptr<PointFrameResidual> res(new PointFrameResidual(mp, mp->host, b->frames[r->target_idx[id]]));
+      res->hostIDX = p->host_idx[i]; res->targetIDX = r->target_idx[id];
+      res->state_state = (ResState)r->state_state[id];
+      res->state_energy = r->state_energy ? r->state_energy[id] : 0.0;
+      res->isLinearized = r->is_linearized[id] != 0;
+      res->isActiveAndIsGoodNEW = r->is_active[id] != 0;
+      res->res_toZeroF.setZero();
+      mp->residuals.push_back(res);     // the point's own order
+      b->residuals[id] = res;
+    }
+  b->ef->allPoints = b->points;
+  return 0;
+}
+
+int ref_ba_update_points(ref_ba* b, const float* idepth, const float* deltaF, const float* idepth_zero) {
+  for (size_t i = 0; i < b->points.size(); ++i) {
+    if (idepth) b->points[i]->setIdepth(idepth[i]);
+    if (idepth_zero) b->points[i]->efPoint->setIdepthZero(idepth_zero[i]);
+    if (deltaF) b->points[i]->efPoint->deltaF = deltaF[i];
+  }
+  return 0;
+}
+
+// System::linearizeAll_Reductor over activeResiduals = the non-linearised residuals (FullSystemOptimize.cpp:19-52,371-391)
+int ref_ba_linearize(ref_ba* b, int fix, double* energy_sum, int8_t* newState, float* newEnergy, float* newEnergyWO, float* cpt,
+                     float* pto) {
+  double e = 0;
+  for (auto& r : b->residuals) {
+    if (r->isLinearized) continue;
+    e += r->linearize(b->calib);
+    if (fix) r->applyRes(true);
+  }
+  if (energy_sum) *energy_sum = e;
+  for (size_t i = 0; i < b->residuals.size(); ++i) {
+    PointFrameResidual& r = *b->residuals[i];
+    if (newState) newState[i] = (int8_t)r.state_NewState;
+    if (newEnergy) newEnergy[i] = (float)r.state_NewEnergy;
+    if (newEnergyWO) newEnergyWO[i] = (float)r.state_NewEnergyWithOutlier;
+    if (cpt) for (int k = 0; k < 3; ++k) cpt[3 * i + k] = r.centerProjectedTo[k];
+    if (pto) for (int k = 0; k < 8; ++k) { pto[16 * i + 2 * k] = r.projectedTo[k][0]; pto[16 * i + 2 * k + 1] = r.projectedTo[k][1]; }
+  }
+  return 0;
+}
+
+int ref_ba_apply_res(ref_ba* b) {   // System::applyRes_Reductor (FullSystemOptimize.cpp:55-59)
+  for (auto& r : b->residuals) if (!r->isLinearized) r->applyRes(true);
+  return 0;
+}
+
+int ref_ba_fix_linearization(ref_ba* b, const int32_t* ids, int count) {
+  for (int i = 0; i < count; ++i) {
+    b->residuals[ids[i]]->fixLinearizationF(b->ef);
+  }
+  return 0;
+}
+
+// EnergyFunctional::accumulate{A,L,SC}F_MT, single-thread branch (EnergyFunctional.cpp:166-175,189-196,212-219)
+int ref_ba_accumulate(ref_ba* b, int which, double* H, double* bvec, int* nres) {
+  MatXX Hm; VecX bm;
+  EnergyFunctional* ef = b->ef.get();
+  const int n = b->n;
+  if (which == 0) {
+    b->topA.setZero(n);
+    for (auto& f : b->frames) for (auto& p : f->frame->pointHessians) b->topA.addPoint<0>(p, ef);
+    b->topA.stitchDoubleMT(nullptr, Hm, bm, ef, false, false);
+    if (nres) *nres = b->topA.nres[0];
+  } else if (which == 1) {
+    b->topL.setZero(n);
+    for (auto& f : b->frames) for (auto& p : f->frame->pointHessians) b->topL.addPoint<1>(p, ef);
+    b->topL.stitchDoubleMT(nullptr, Hm, bm, ef, true, false);
+    if (nres) *nres = b->topL.nres[0];
+  } else {
+    b->bot.setZero(n);
+    for (auto& f : b->frames) for (auto& p : f->frame->pointHessians) b->bot.addPoint(p, true);
+    b->bot.stitchDoubleMT(nullptr, Hm, bm, ef, false);
+  }
+  const int N = 8 * n + 4;
+  for (int j = 0; j < N; ++j) for (int i = 0; i < N; ++i) H[i + (size_t)N * j] = Hm(i, j);
+  for (int i = 0; i < N; ++i) bvec[i] = bm[i];
+  return 0;
+}
+
+int ref_ba_point_results(ref_ba* b, double* HdiF, double* bdSumF, double* idepth_hessian, double* Hdd_accAF, double* bd_accAF,
+                         double* Hcd_accAF, double* Hdd_accLF, double* bd_accLF, double* Hcd_accLF) {
+  for (size_t i = 0; i < b->points.size(); ++i) {
+    const MapPoint& p = *b->points[i];
+    const MapPointOptimizationData& e = *p.efPoint;
+    if (HdiF) HdiF[i] = e.HdiF;
+    if (bdSumF) bdSumF[i] = e.bdSumF;
+    if (idepth_hessian) idepth_hessian[i] = p.idepth_hessian;
+    if (Hdd_accAF) Hdd_accAF[i] = e.Hdd_accAF;
+    if (bd_accAF) bd_accAF[i] = e.bd_accAF;
+    if (Hdd_accLF) Hdd_accLF[i] = e.Hdd_accLF;
+    if (bd_accLF) bd_accLF[i] = e.bd_accLF;
+    for (int k = 0; k < 4; ++k) {
+      if (Hcd_accAF) Hcd_accAF[4 * i + k] = e.Hcd_accAF[k];
+      if (Hcd_accLF) Hcd_accLF[4 * i + k] = e.Hcd_accLF[k];
+    }
+  }
+  return 0;
+}
+
+// RawResidualJacobian in member order (Include/OptimizationClasses.h:48-77): resF[8], Jpdxi[2][6], Jpdc[2][4], Jpdd[2],
+// JIdx[2][8], JabF[2][8], JIdx2[4], JabJIdx[4], Jab2[4] (2x2 blocks column-major)
+int ref_ba_residual_results(ref_ba* b, int8_t* state_state, uint8_t* is_active, double* JpJdF, double* J74, double* rtz) {
+  for (size_t i = 0; i < b->residuals.size(); ++i) {
+    const PointFrameResidual& r = *b->residuals[i];
+    if (state_state) state_state[i] = (int8_t)r.state_state;
+    if (is_active) is_active[i] = r.isActiveAndIsGoodNEW ? 1 : 0;
+    if (JpJdF) for (int k = 0; k < 8; ++k) JpJdF[8 * i + k] = r.JpJdF[k];
+    if (rtz) for (int k = 0; k < 8; ++k) rtz[8 * i + k] = r.res_toZeroF[k];
+    if (J74) {
+      double* o = J74 + 74 * i;
+      const RawResidualJacobian& J = *r.J;
+      int q = 0;
+      for (int k = 0; k < 8; ++k) o[q++] = J.resF[k];
+      for (int a = 0; a < 2; ++a) for (int k = 0; k < 6; ++k) o[q++] = J.Jpdxi[a][k];
+      for (int a = 0; a < 2; ++a) for (int k = 0; k < 4; ++k) o[q++] = J.Jpdc[a][k];
+      for (int k = 0; k < 2; ++k) o[q++] = J.Jpdd[k];
+      for (int a = 0; a < 2; ++a) for (int k = 0; k < 8; ++k) o[q++] = J.JIdx[a][k];
+      for (int a = 0; a < 2; ++a) for (int k = 0; k < 8; ++k) o[q++] = J.JabF[a][k];
+      for (int c = 0; c < 2; ++c) for (int rr = 0; rr < 2; ++rr) o[q++] = J.JIdx2(rr, c);
+      for (int c = 0; c < 2; ++c) for (int rr = 0; rr < 2; ++rr) o[q++] = J.JabJIdx(rr, c);
+      for (int c = 0; c < 2; ++c) for (int rr = 0; rr < 2; ++rr) o[q++] = J.Jab2(rr, c);
+    }
+  }
+  return 0;
+}
+
+// FrameFramePrecalc::set (Src/OptimizationClasses.cpp:13-39) for one ordered pair from the frames' poses and states:
+// w2c_evalPT (12: R row-major, t), state / state_zero (10) per frame, exposures.  Out: the 28 floats of the precalc record.
+int ref_precalc_set(int n, const double* w2c_evalPT, const double* state, const double* state_zero, const float* ab_exposure, float fx,
+                    float fy, float cx, float cy, int w, int h, float* precalc_out) {
+  Mat33 K = Mat33::Identity();
+  K(0, 0) = fx; K(1, 1) = fy; K(0, 2) = cx; K(1, 2) = cy;
+  int dirPyr = 1;
+  std::shared_ptr<CalibData> calib(new CalibData(w, h, K, 0.f, nullptr, nullptr, dirPyr, 1, 1.2f));
+  std::shared_ptr<ImageData> img(new ImageData(1, 1));
+  img->timestamp = 0; img->ExposureL = 1.f; img->ExposureR = 1.f;
+  std::vector<std::shared_ptr<FrameShell>> fr;
+  for (int f = 0; f < n; ++f) {
+    std::shared_ptr<FrameShell> fs(new FrameShell(img, nullptr, calib, nullptr, false));
+    fs->frame->idx = f;
+    fs->ab_exposure = ab_exposure[f];
+    fs->frame->efFrame.reset(new FrameOptimizationData(f, ab_exposure[f]));
+    FrameOptimizationData& e = *fs->frame->efFrame;
+    Eigen::Matrix<double, 3, 3> R; Eigen::Matrix<double, 3, 1> t;
+    for (int i = 0; i < 3; ++i) { for (int j = 0; j < 3; ++j) R(i, j) = w2c_evalPT[12 * f + 3 * i + j]; t[i] = w2c_evalPT[12 * f + 9 + i]; }
+    e.worldToCam_evalPT = SE3(R, t);
+    Vec10 s, s0;
+    for (int i = 0; i < 10; ++i) { s[i] = state[10 * f + i]; s0[i] = state_zero[10 * f + i]; }
+    e.state_zero = s0;   // (setStateZero also builds the nullspaces, which the path does not use)
+    e.setState(s);
+    fs->frame->targetPrecalc.resize(n);
+    fr.push_back(fs);
+  }
+  for (int hI = 0; hI < n; ++hI)
+    for (int tI = 0; tI < n; ++tI) {
+      FrameFramePrecalc& P = fr[hI]->frame->targetPrecalc[tI];
+      P.set(fr[hI], fr[tI], calib);
+      float* o = precalc_out + (size_t)HSLAM_PRECALC_STRIDE * (hI + tI * n);
+      for (int i = 0; i < 3; ++i)
+        for (int j = 0; j < 3; ++j) { o[3 * i + j] = P.PRE_KRKiTll(i, j); o[12 + 3 * i + j] = P.PRE_RTll_0(i, j); }
+      for (int i = 0; i < 3; ++i) { o[9 + i] = P.PRE_KtTll[i]; o[21 + i] = P.PRE_tTll_0[i]; }
+      o[24] = P.PRE_aff_mode[0]; o[25] = P.PRE_aff_mode[1]; o[26] = P.PRE_b0_mode; o[27] = 0.f;
+      P.host.reset(); P.target.reset();
+    }
+  return 0;
+}
+
+}  // extern "C"

@@ -1,0 +1,129 @@
+"""ctypes front end of oracle/_ref/libhslam_ref.so: the UNMODIFIED reference translation units of the BA hot path
+(Src/OptimizationClasses.cpp, Src/AccumulatedTopHessian.cpp, Src/AccumulatedSCHessian.cpp, Src/Settings.cpp + their headers)
+compiled against the stand-ins of oracle/ref_shim/ with oracle/ref_driver.cpp around them (see oracle/Makefile, target
+_ref).  TEST INFRASTRUCTURE: it pins the oracle (tests/test_oracle_vs_reference.py); nothing of the product loads it."""
+import ctypes as C
+import os
+
+import numpy as np
+
+from . import oraclelib as O
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+LIB = os.path.join(HERE, "_ref", "libhslam_ref.so")
+
+
+def available():
+    return os.path.exists(LIB)
+
+
+_lib = None
+
+
+def lib():
+    global _lib
+    if _lib is None:
+        L = C.CDLL(LIB)
+        L.ref_ba_create.restype = C.c_void_p
+        L.ref_ba_destroy.argtypes = [C.c_void_p]
+        _lib = L
+    return _lib
+
+
+_ptr = O._ptr
+
+
+class RefBA:
+    """Same call surface as oraclelib.BAOracle, answered by the reference's own code."""
+
+    def __init__(self, win, dI_level0_list):
+        self.L = lib()
+        self.h = C.c_void_p(self.L.ref_ba_create())
+        self.win, self.n = win, win.n
+        self._keep = []
+        self.set_window(win, dI_level0_list)
+        ps, k1 = O.fill_point_soa(win)
+        rs, k2 = O.fill_residual_soa(win)
+        self._keep += [k1, k2]
+        assert self.L.ref_ba_set_topology(self.h, C.byref(ps), C.byref(rs)) == 0
+        self.P, self.R = win.P, win.R
+
+    def __del__(self):
+        try:
+            self.L.ref_ba_destroy(self.h)
+        except Exception:
+            pass
+
+    def set_window(self, win, dI_list=None):
+        if dI_list is not None:
+            self._dI = [np.ascontiguousarray(d, np.float32) for d in dI_list]
+        cam = win.cam
+        ow = O.OrcWindow()
+        ow.n_frames, ow.w, ow.h = win.n, cam.w, cam.h
+        ow.fx, ow.fy, ow.cx, ow.cy = cam.fx, cam.fy, cam.cx, cam.cy
+        ow.fxi, ow.fyi = np.float32(1.0) / np.float32(cam.fx), np.float32(1.0) / np.float32(cam.fy)
+        self._dIp = (C.c_void_p * win.n)(*[_ptr(d) for d in self._dI])
+        ow.dI = C.cast(self._dIp, C.c_void_p)
+        ka = dict(frameEnergyTH=np.ascontiguousarray(win.frameEnergyTH, np.float32), precalc=np.ascontiguousarray(win.precalc, np.float32),
+                  adHost=np.ascontiguousarray(win.adHost, np.float64), adTarget=np.ascontiguousarray(win.adTarget, np.float64),
+                  adHTdeltaF=np.ascontiguousarray(win.adHTdeltaF, np.float32), framePrior=np.ascontiguousarray(win.framePrior, np.float64),
+                  frameDeltaPrior=np.ascontiguousarray(win.frameDeltaPrior, np.float64))
+        for k, a in ka.items():
+            setattr(ow, k, _ptr(a))
+        for i in range(4):
+            ow.cDeltaF[i] = float(win.cDeltaF[i]); ow.cPrior[i] = float(win.cPrior[i])
+        self._keep.append(ka)
+        assert self.L.ref_ba_set_window(self.h, C.byref(ow)) == 0
+
+    def update_points(self, idepth=None, deltaF=None, idepth_zero=None):
+        a = [None if x is None else np.ascontiguousarray(x, np.float32) for x in (idepth, deltaF, idepth_zero)]
+        assert self.L.ref_ba_update_points(self.h, _ptr(a[0]), _ptr(a[1]), _ptr(a[2])) == 0
+
+    def linearize(self, fix=False):
+        R = self.R
+        e = C.c_double(0)
+        ns = np.zeros(R, np.int8); ne = np.zeros(R, np.float32); nwo = np.zeros(R, np.float32)
+        cpt = np.zeros(R * 3, np.float32); pto = np.zeros(R * 16, np.float32)
+        assert self.L.ref_ba_linearize(self.h, C.c_int(int(fix)), C.byref(e), _ptr(ns), _ptr(ne), _ptr(nwo), _ptr(cpt), _ptr(pto)) == 0
+        return dict(energy=e.value, newState=ns, newEnergy=ne, newEnergyWithOutlier=nwo, centerProjectedTo=cpt.reshape(R, 3),
+                    projectedTo=pto.reshape(R, 8, 2))
+
+    def apply_res(self):
+        assert self.L.ref_ba_apply_res(self.h) == 0
+
+    def fix_linearization(self, ids):
+        ids = np.ascontiguousarray(ids, np.int32)
+        assert self.L.ref_ba_fix_linearization(self.h, _ptr(ids), C.c_int(len(ids))) == 0
+
+    def accumulate(self, which):
+        N = 8 * self.n + 4
+        H = np.zeros(N * N); b = np.zeros(N); nres = C.c_int(0)
+        assert self.L.ref_ba_accumulate(self.h, C.c_int(which), _ptr(H), _ptr(b), C.byref(nres)) == 0
+        return H.reshape(N, N).T.copy(), b, nres.value
+
+    def point_results(self):
+        P = self.P
+        names = ["HdiF", "bdSumF", "idepth_hessian", "Hdd_accAF", "bd_accAF", "Hcd_accAF", "Hdd_accLF", "bd_accLF", "Hcd_accLF"]
+        arrs = [np.zeros(P * (4 if "Hcd" in k else 1)) for k in names]
+        assert self.L.ref_ba_point_results(self.h, *[_ptr(a) for a in arrs]) == 0
+        d = dict(zip(names, arrs))
+        d["Hcd_accAF"] = d["Hcd_accAF"].reshape(P, 4); d["Hcd_accLF"] = d["Hcd_accLF"].reshape(P, 4)
+        return d
+
+    def residual_results(self):
+        R = self.R
+        st = np.zeros(R, np.int8); act = np.zeros(R, np.uint8); jp = np.zeros(R * 8); j74 = np.zeros(R * 74); rtz = np.zeros(R * 8)
+        assert self.L.ref_ba_residual_results(self.h, _ptr(st), _ptr(act), _ptr(jp), _ptr(j74), _ptr(rtz)) == 0
+        return dict(state_state=st, is_active=act, JpJdF=jp.reshape(R, 8), J=j74.reshape(R, 74), res_toZeroF=rtz.reshape(R, 8))
+
+
+def precalc_set(cam, T_eval, state, state_zero, exposure):
+    """FrameFramePrecalc::set (Src/OptimizationClasses.cpp:13-39) of every ordered pair -> n*n*28 floats."""
+    n = len(T_eval)
+    out = np.zeros(n * n * 28, np.float32)
+    rc = lib().ref_precalc_set(C.c_int(n), _ptr(np.ascontiguousarray(T_eval, np.float64)), _ptr(np.ascontiguousarray(state, np.float64)),
+                               _ptr(np.ascontiguousarray(state_zero, np.float64)), _ptr(np.ascontiguousarray(exposure, np.float32)),
+                               C.c_float(cam.fx), C.c_float(cam.fy), C.c_float(cam.cx), C.c_float(cam.cy), C.c_int(cam.w), C.c_int(cam.h),
+                               _ptr(out))
+    assert rc == 0
+    return out

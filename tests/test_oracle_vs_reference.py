@@ -1,0 +1,114 @@
+"""PINS THE ORACLE TO THE REFERENCE'S OWN CODE.  oracle/_ref/libhslam_ref.so is built from the UNMODIFIED reference sources
+(/root/reference/Src/OptimizationClasses.cpp, AccumulatedTopHessian.cpp, AccumulatedSCHessian.cpp, Settings.cpp and their
+headers, incl. Include/MatrixAccumulators.h and DirectProjection.h) against the library stand-ins of oracle/ref_shim/
+(recipe: oracle/Makefile, target _ref; the .so travels with the repository, the reference tree does not).  The same
+window goes through that library and through the oracle's float restatement:
+  * PointFrameResidual::linearize / applyRes: states, energies, all 74 Jacobian floats, JpJdF, centerProjectedTo,
+    projectedTo — BIT-IDENTICAL; fixLinearizationF's res_toZeroF to fp32 round-off (Eigen dot-product order);
+  * AccumulatedTopHessianSSE::addPoint<0/1> and AccumulatedSCHessianSSE::addPoint side effects on the points
+    (Hdd/bd/Hcd_acc{A,L}F, HdiF, bdSumF, idepth_hessian), and stitchDouble of the three systems: the A system (no Eigen
+    reduction upstream of it) to 1e-12, L and SC to fp32 round-off; resInA / resInL exact;
+  * FrameFramePrecalc::set — the precalc tables the window generators produce.
+Skipped only when the library has not been built (a checkout without /root/reference and without the shipped .so)."""
+import importlib
+
+import numpy as np
+import pytest
+
+from conftest import rel_fro
+
+
+@pytest.fixture(scope="module")
+def RL():
+    from oracle import reflib
+    if not reflib.available():
+        pytest.skip("oracle/_ref/libhslam_ref.so not built (needs /root/reference: make -C oracle _ref)")
+    return reflib
+
+
+@pytest.fixture(scope="module")
+def pair(O, RL, synth):
+    win, is_lin = synth.make_window(points_per_frame=150, n_frames=6, seed=123, frac_linearized=0.3)
+    dIs = [O.pyramid(im, 1)[0][0] for im in win.images]
+    return win, is_lin, O.BAOracle(win, dIs, prec="f"), RL.RefBA(win, dIs), O.BAOracle(win, dIs, prec="d")
+
+
+def _same_lin(a, b):
+    assert np.array_equal(a["newState"], b["newState"])
+    assert np.array_equal(a["newEnergy"], b["newEnergy"]) and np.array_equal(a["newEnergyWithOutlier"], b["newEnergyWithOutlier"])
+    assert a["energy"] == b["energy"]
+    ok = b["newState"] != 1
+    assert np.array_equal(a["centerProjectedTo"][ok], b["centerProjectedTo"][ok])
+    assert np.array_equal(a["projectedTo"][ok], b["projectedTo"][ok])
+
+
+def _same_res(a, b):
+    ok = (b["state_state"] != 1) & (b["is_active"] != 0)   # an OOB residual keeps a partially written Jacobian in the reference
+    assert np.array_equal(a["state_state"], b["state_state"]) and np.array_equal(a["is_active"], b["is_active"])
+    for k in ("JpJdF", "J"):
+        assert np.array_equal(np.asarray(a[k])[ok], np.asarray(b[k])[ok]), k
+    # fixLinearizationF forms Jp*delta with two 6-term and two 4-term Eigen dot products (OptimizationClasses.cpp:263-268):
+    # the order Eigen reduces them in is an implementation detail of its version / SIMD flags (the stand-in splits
+    # binary, the oracle sums left to right), so res_toZeroF agrees to fp32 round-off, not bit for bit
+    ra, rb = np.asarray(a["res_toZeroF"])[ok], np.asarray(b["res_toZeroF"])[ok]
+    assert np.abs(ra - rb).max() <= 2e-6 * max(np.abs(rb).max(), 1.0)
+
+
+def test_linearize_apply_fix_bit_identical_to_reference_code(pair):
+    win, is_lin, f, r, _ = pair
+    lf, lr = f.linearize(False), r.linearize(False)
+    assert (lr["newState"] == 0).sum() > 0.8 * len(lr["newState"]) and (lr["newState"] == 1).any() and (lr["newState"] == 2).any()
+    _same_lin(lf, lr)
+    f.apply_res(); r.apply_res()
+    _same_res(f.residual_results(), r.residual_results())
+    ids = np.nonzero(is_lin)[0].astype(np.int32)
+    f.fix_linearization(ids); r.fix_linearization(ids)
+    _same_res(f.residual_results(), r.residual_results())
+    # second pass at a moved state: the linearised residuals stay frozen, the others are re-linearised
+    idp = (win.idepth * np.float32(1.002)).astype(np.float32)
+    for x in (f, r):
+        x.update_points(idepth=idp, deltaF=(idp - win.idepth_zero).astype(np.float32))
+    _same_lin(f.linearize(False), r.linearize(False))
+    f.apply_res(); r.apply_res()
+    _same_res(f.residual_results(), r.residual_results())
+
+
+def test_accumulate_and_stitch_match_reference_code(pair):
+    """Runs after the test above: the windows hold active A residuals, linearised L residuals and non-zero deltas."""
+    win, is_lin, f, r, d = pair
+    d.linearize(False); d.apply_res(); d.fix_linearization(np.nonzero(is_lin)[0].astype(np.int32))
+    idp = (win.idepth * np.float32(1.002)).astype(np.float32)
+    d.update_points(idepth=idp, deltaF=(idp - win.idepth_zero).astype(np.float32)); d.linearize(False); d.apply_res()
+    for which in (0, 1, 2):
+        Hf, bf, nf = f.accumulate(which)
+        Hr, br, nr = r.accumulate(which)
+        Hd, bd_, _ = d.accumulate(which)
+        assert nf == nr and (which == 2 or nr > 0)
+        # A: the fp32 accumulators hold the same numbers and the fp64 stitch is the same arithmetic.  L / SC sit downstream
+        # of res_toZeroF (see _same_res): the linearised residuals' r carries fp32 round-off into b_L, bd_accLF, bdSumF
+        tol_H, tol_b = (1e-12, 1e-12) if which == 0 else (1e-9, 1e-6)
+        assert rel_fro(Hf, Hr) < tol_H and rel_fro(bf, br) < tol_b, (which, rel_fro(Hf, Hr), rel_fro(bf, br))
+        assert np.abs(Hr).max() > 0
+        assert rel_fro(Hr, Hd) < 1e-4          # and the reference's own float error vs the fp64 restatement is what the GPU is held to
+    pf, pr = f.point_results(), r.point_results()
+    for k in pf:
+        a, b = np.asarray(pf[k], np.float32), np.asarray(pr[k], np.float32)
+        if k in ("bd_accLF", "bdSumF"):
+            assert np.allclose(a, b, rtol=1e-4, atol=1e-3 * np.abs(b).max()), k
+        else:
+            assert np.array_equal(a, b), k
+    assert np.abs(pr["HdiF"]).max() > 0 and np.abs(pr["Hdd_accLF"]).max() > 0
+
+
+def test_frame_frame_precalc_matches_reference_code(O, RL, synth):
+    """FrameFramePrecalc::set compiled from the reference vs the table generators (numpy and the oracle's C restatement)."""
+    kf = synth.render_keyframes(160, 120, 4, seed=9)
+    win, _ = synth.make_window(points_per_frame=10, seed=10, keyframes=kf)
+    ref = RL.precalc_set(win.cam, win.T_w2c_eval, win.state, win.state_zero, win.ab_exposure).reshape(-1, 28)
+    orc = O.prepare_window(win.cam, win.T_w2c_eval, win.state, win.state_zero, win.ab_exposure)[0].reshape(-1, 28)
+    npy = np.asarray(win.precalc, np.float32).reshape(-1, 28)
+    n = win.n
+    offdiag = np.array([h + t * n for h in range(n) for t in range(n) if h != t])
+    # fp64 pose algebra (Sophus stand-in vs the restatements) rounded to fp32: equal to a few ulp
+    assert np.allclose(ref[offdiag, :27], orc[offdiag, :27], rtol=3e-6, atol=3e-6)
+    assert np.allclose(ref[offdiag, :27], npy[offdiag, :27], rtol=3e-5, atol=3e-5)   # numpy forms K R K^-1 in another order
