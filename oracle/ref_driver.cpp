@@ -31,34 +31,7 @@
 
 using namespace FSLAM;
 
-// ---- out-of-line symbols of translation units that are not on the path ---------------------------------------------
-namespace FSLAM {
-bool EFAdjointsValid = false, EFIndicesValid = false, EFDeltaValid = false;   // Src/EnergyFunctional.cpp:17-19
-size_t FrameShell::Globalid = 0;
-int FrameShell::GlobalKfId = 0;
-int Frame::mnGridCols = 0, Frame::mnGridRows = 0, Frame::EDGE_THRESHOLD = 0;
-float Frame::mnMinX = 0, Frame::mnMaxX = 0, Frame::mnMinY = 0, Frame::mnMaxY = 0, Frame::mfGridElementWidthInv = 0,
-      Frame::mfGridElementHeightInv = 0;
-bool Frame::GridStructInit = false;
-Frame::Frame(std::shared_ptr<ImageData>, int id, float, std::shared_ptr<FeatureDetector>, std::shared_ptr<CalibData> _Calib,
-             std::shared_ptr<IndexThreadReduce<Vec10>>, bool)
-    : idx(id), Calib(_Calib) {
-  frameEnergyTH = 8 * 8 * patternNum;   // Src/Frame.cpp:47
-  FlaggedForMarginalization = false; isReduced = false; NeedRefresh = false; nFeatures = 0; MovedByOpt = 0;
-  statistics_outlierResOnThis = statistics_goodResOnThis = 0;
-}
-Frame::~Frame() {}
-ImmaturePoint::ImmaturePoint(float u_, float v_, shared_ptr<FrameShell> host_, float type, shared_ptr<CalibData>)
-    : u(u_), v(v_), host(host_), my_type(type), idepth_min(0), idepth_max(NAN) {
-  energyTH = 0; quality = 0; idxInImmaturePoints = 0; lastTraceStatus = IPS_UNINITIALIZED; lastTracePixelInterval = 0;
-}
-EnergyFunctional::EnergyFunctional() {
-  adHost = adTarget = nullptr; adHostF = adTargetF = nullptr; adHTdeltaF = nullptr; red = nullptr;
-  accSSE_top_L = accSSE_top_A = nullptr; accSSE_bot = nullptr;
-  nFrames = nResiduals = nPoints = 0; resInA = resInL = resInM = 0; currentLambda = 0;
-}
-EnergyFunctional::~EnergyFunctional() {}
-}  // namespace FSLAM
+#include "ref_stubs.inc"
 
 struct ref_ba {
   std::shared_ptr<CalibData> calib;

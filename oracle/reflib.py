@@ -127,3 +127,102 @@ def precalc_set(cam, T_eval, state, state_zero, exposure):
                                _ptr(out))
     assert rc == 0
     return out
+
+
+# ------------------------------------------------------------------ Stage T + tracing (oracle/_ref/libhslam_ref_trk.so)
+LIB_TRK = os.path.join(HERE, "_ref", "libhslam_ref_trk.so")
+_lib_trk = None
+
+
+def available_trk():
+    return os.path.exists(LIB_TRK)
+
+
+def lib_trk():
+    global _lib_trk
+    if _lib_trk is None:
+        L = C.CDLL(LIB_TRK)
+        L.ref_trk_create.restype = C.c_void_p
+        L.ref_trk_destroy.argtypes = [C.c_void_p]
+        _lib_trk = L
+    return _lib_trk
+
+
+class RefTracker:
+    """CoarseTracker of the reference (Src/CoarseTracker.cpp, unmodified): makeK, calcRes, calcGSSSE, trackNewestCoarse."""
+
+    def __init__(self, cam, levels, pc, dI_new_flat, ref_exposure=1.0, new_exposure=1.0, ref_aff=(0.0, 0.0)):
+        self.L = lib_trk()
+        self.levels = levels
+        self.h = C.c_void_p(self.L.ref_trk_create(C.c_int(cam.w), C.c_int(cam.h), C.c_int(levels), C.c_float(cam.fx), C.c_float(cam.fy),
+                                                  C.c_float(cam.cx), C.c_float(cam.cy)))
+        self.n = []
+        for l in range(levels):
+            a = [np.ascontiguousarray(x, np.float32) for x in pc[l]]
+            assert self.L.ref_trk_set_ref(self.h, C.c_int(l), _ptr(a[0]), _ptr(a[1]), _ptr(a[2]), _ptr(a[3]), C.c_int(len(a[0]))) == 0
+            self.n.append(len(a[0]))
+        self._dI = np.ascontiguousarray(dI_new_flat, np.float32)
+        assert self.L.ref_trk_set_frames(self.h, C.c_float(ref_exposure), C.c_float(new_exposure), C.c_double(ref_aff[0]),
+                                         C.c_double(ref_aff[1]), _ptr(self._dI)) == 0
+
+    def __del__(self):
+        try:
+            self.L.ref_trk_destroy(self.h)
+        except Exception:
+            pass
+
+    def level_K(self, l):
+        k = np.zeros(4, np.float32); wh = np.zeros(2, np.int32); K9 = np.zeros(9, np.float32); Ki9 = np.zeros(9, np.float32)
+        assert self.L.ref_trk_get_K(self.h, C.c_int(l), _ptr(k), _ptr(wh), _ptr(K9), _ptr(Ki9)) == 0
+        return dict(w=int(wh[0]), h=int(wh[1]), fx=k[0], fy=k[1], cx=k[2], cy=k[3], Ki=Ki9)
+
+    def calc_res(self, lvl, T, aff, cutoff):
+        n = self.n[lvl]
+        warped = [np.zeros(n + 8, np.float32) for _ in range(8)]
+        wp = (C.c_void_p * 8)(*[_ptr(a) for a in warped])
+        out6 = np.zeros(6); nw = C.c_int(0)
+        assert self.L.ref_trk_calc_res(self.h, C.c_int(lvl), _ptr(np.ascontiguousarray(T, np.float64)), C.c_double(aff[0]), C.c_double(aff[1]),
+                                       C.c_float(cutoff), _ptr(out6), wp, C.byref(nw)) == 0
+        return out6, warped, nw.value
+
+    def calc_gs(self, lvl, T, aff):
+        H = np.zeros(64); b = np.zeros(8)
+        assert self.L.ref_trk_calc_gs(self.h, C.c_int(lvl), _ptr(np.ascontiguousarray(T, np.float64)), C.c_double(aff[0]), C.c_double(aff[1]),
+                                      _ptr(H), _ptr(b)) == 0
+        return H.reshape(8, 8).T.copy(), b
+
+    def make_coarse_depth(self, cpt3, hdif, dI_ref_flat):
+        """CoarseTracker::setCoarseTrackingRef / makeCoarseDepthL0 of the reference; returns the per-level clouds."""
+        c = np.ascontiguousarray(cpt3, np.float32).reshape(-1, 3); hd = np.ascontiguousarray(hdif, np.float32)
+        self._dIref = np.ascontiguousarray(dI_ref_flat, np.float32)
+        assert self.L.ref_trk_make_coarse_depth(self.h, C.c_int(len(hd)), _ptr(c), _ptr(hd), _ptr(self._dIref)) == 0
+        out = []
+        for l in range(self.levels):
+            n = C.c_int(0)
+            self.L.ref_trk_get_ref(self.h, C.c_int(l), None, None, None, None, C.byref(n))
+            a = [np.zeros(n.value, np.float32) for _ in range(4)]
+            self.L.ref_trk_get_ref(self.h, C.c_int(l), _ptr(a[0]), _ptr(a[1]), _ptr(a[2]), _ptr(a[3]), C.byref(n))
+            out.append(tuple(a))
+        return out
+
+    def track(self, T0, aff0, coarsest, min_res=None):
+        T = np.array(T0, np.float64).copy(); aff = np.array(aff0, np.float64).copy()
+        mra = np.full(5, np.nan) if min_res is None else np.asarray(min_res, np.float64).copy()
+        lastRes = np.zeros(5); flow = np.zeros(3); ok = C.c_int(0)
+        assert self.L.ref_trk_track(self.h, _ptr(T), _ptr(aff), C.c_int(coarsest), _ptr(mra), _ptr(lastRes), _ptr(flow), C.byref(ok)) == 0
+        return dict(T=T, aff=aff, lastResiduals=lastRes, flow=flow, ok=bool(ok.value))
+
+
+def trace_immature(dI0, cam, ims):
+    """ImmaturePoint::traceOn of the reference for every point of `ims` (synth.ImmatureSet), in place like O.trace_immature."""
+    h, w = dI0.shape[0], dI0.shape[1]
+    a = lambda x, dt: np.ascontiguousarray(x, dt)
+    K, T, A = a(ims.KRKi, np.float32), a(ims.Kt, np.float32), a(ims.aff, np.float32)
+    rc = lib_trk().ref_trace_immature(_ptr(a(dI0, np.float32)), C.c_int(w), C.c_int(h), C.c_float(cam.fx), C.c_float(cam.fy), C.c_float(cam.cx),
+                                      C.c_float(cam.cy), C.c_int(len(K)), _ptr(K), _ptr(T), _ptr(A), C.c_int(len(ims.u)),
+                                      _ptr(a(ims.host_idx, np.int32)), _ptr(a(ims.u, np.float32)), _ptr(a(ims.v, np.float32)),
+                                      _ptr(a(ims.gradH, np.float32)), _ptr(a(ims.color, np.float32)), _ptr(a(ims.weights, np.float32)),
+                                      _ptr(a(ims.energyTH, np.float32)), _ptr(ims.idepth_min), _ptr(ims.idepth_max), _ptr(ims.quality),
+                                      _ptr(ims.status), _ptr(ims.lastTraceUV), _ptr(ims.lastTracePixelInterval))
+    assert rc == 0
+    return ims

@@ -112,3 +112,80 @@ def test_frame_frame_precalc_matches_reference_code(O, RL, synth):
     # fp64 pose algebra (Sophus stand-in vs the restatements) rounded to fp32: equal to a few ulp
     assert np.allclose(ref[offdiag, :27], orc[offdiag, :27], rtol=3e-6, atol=3e-6)
     assert np.allclose(ref[offdiag, :27], npy[offdiag, :27], rtol=3e-5, atol=3e-5)   # numpy forms K R K^-1 in another order
+
+
+# ---------------------------------------------------------------------------------------- Stage T, tracing, reference clouds
+@pytest.fixture(scope="module")
+def RT():
+    from oracle import reflib
+    if not reflib.available_trk():
+        pytest.skip("oracle/_ref/libhslam_ref_trk.so not built (needs /root/reference: make -C oracle _ref)")
+    return reflib
+
+
+T_ID = np.concatenate([np.eye(3).reshape(9), np.zeros(3)])
+
+
+def test_tracker_bit_identical_to_reference_code(O, RT, synth):
+    """Src/CoarseTracker.cpp compiled unmodified: makeK, calcRes (Vec6 + the eight warped buffers), calcGSSSE with the SSE
+    Accumulator9 (H, b) — BIT-IDENTICAL to the oracle's float restatement at several poses and cut-offs; trackNewestCoarse
+    lands on the same pose to fp64 round-off with the same residuals."""
+    tp = synth.make_tracking_pair(w=320, h=240, levels=4, n_seed_points=1500, seed=7)
+    lv, _, dI = O.pyramid(tp.img_new, tp.levels)
+    orc = O.TrackerOracle(tp.cam, tp.levels, tp.pc)
+    ref = RT.RefTracker(tp.cam, tp.levels, tp.pc, dI)
+    for l in range(tp.levels):
+        ko, kr = orc.level_K(l), ref.level_K(l)
+        assert all(np.float32(ko[k]) == np.float32(kr[k]) for k in ("w", "h", "fx", "fy", "cx", "cy")) and np.array_equal(ko["Ki"], kr["Ki"])
+    R, t = synth.se3_exp(np.array([0.01, -0.004, 0.006, 0.003, -0.002, 0.004]))
+    for T, aff, cutoff in ((T_ID, (0.0, 0.0), 20.0), (synth.T12(R, t), (0.02, 3.0), 20.0), (synth.T12(R, t), (0.0, 0.0), 5.0)):
+        for l in range(tp.levels):
+            o6, wo, nwo, _ = orc.calc_res(l, lv[l], T, aff, cutoff)
+            r6, wr, nwr = ref.calc_res(l, T, aff, cutoff)
+            assert np.array_equal(o6, r6) and nwr == (nwo + 3) // 4 * 4 and nwo > 50
+            assert all(np.array_equal(a[:nwo], b[:nwo]) for a, b in zip(wo, wr))
+            Ho, bo = orc.calc_gs(l, wo, nwo, aff)
+            Hr, br = ref.calc_gs(l, T, aff)
+            assert np.array_equal(Ho, Hr) and np.array_equal(bo, br)
+    ro = orc.track(dI, T_ID, (0.0, 0.0), tp.levels - 1, prec="f")
+    rr = ref.track(T_ID, (0.0, 0.0), tp.levels - 1)
+    assert ro["ok"] and rr["ok"]
+    assert np.abs(ro["T"] - rr["T"]).max() < 1e-12 and np.abs(ro["aff"] - rr["aff"]).max() < 1e-10   # 8x8 LDLT / SE3 exp round-off
+    assert np.allclose(ro["lastResiduals"], rr["lastResiduals"], rtol=1e-12, equal_nan=True)
+    assert np.allclose(ro["flow"], rr["flow"], rtol=1e-9)
+
+
+def test_make_coarse_depth_bit_identical_to_reference_code(O, RT, synth):
+    """CoarseTracker::makeCoarseDepthL0 compiled unmodified (splat incl. pixel collisions, pyramid, dilation, compaction)."""
+    tp = synth.make_tracking_pair(w=320, h=240, levels=4, n_seed_points=1500, seed=7)
+    w, h, levels = tp.cam.w, tp.cam.h, tp.levels
+    rng = np.random.default_rng(11)
+    n = 3000
+    cx = rng.uniform(3, w - 4, n).astype(np.float32); cy = rng.uniform(3, h - 4, n).astype(np.float32)
+    cx[100:160] = cx[40:100]; cy[100:160] = cy[40:100]
+    idp = rng.uniform(0.1, 1.5, n).astype(np.float32); hdi = rng.uniform(1e-4, 1e-1, n).astype(np.float32)
+    su = (cx + np.float32(0.5)).astype(np.int32); sv = (cy + np.float32(0.5)).astype(np.int32)
+    sw = np.sqrt((1e-3 / (hdi.astype(np.float64) + 1e-12)).astype(np.float32)).astype(np.float32)
+    _, _, dI_ref = O.pyramid(tp.img_ref, levels)
+    orc = O.make_coarse_depth(levels, w, h, su, sv, idp, sw, dI_ref)
+    ref = RT.RefTracker(tp.cam, levels, tp.pc, dI_ref).make_coarse_depth(np.stack([cx, cy, idp], 1), hdi, dI_ref)
+    for l in range(levels):
+        assert len(ref[l][0]) == len(orc[l][0]) > 0
+        for a, b in zip(orc[l], ref[l]):
+            assert np.array_equal(a, b), l
+
+
+def test_trace_on_bit_identical_to_reference_code(O, RT, synth):
+    """ImmaturePoint::traceOn (Src/ImmaturePoint.cpp, unmodified) over 1200 points, two consecutive frames."""
+    import copy
+    kf = synth.render_keyframes(320, 240, 5, seed=78)
+    ims = synth.make_immature_points(kf, hosts=[0, 1, 2], points_per_host=400, seed=5)
+    a, b = copy.deepcopy(ims), copy.deepcopy(ims)
+    for new in (3, 4):
+        dI0 = O.pyramid(kf.images[new], 1)[0][0]
+        for x in (a, b):
+            synth.trace_tables(kf, [0, 1, 2], new, x)
+        O.trace_immature(dI0, a); RT.trace_immature(dI0, kf.cam, b)
+        for k in ("status", "idepth_min", "idepth_max", "quality", "lastTraceUV", "lastTracePixelInterval"):
+            assert np.array_equal(getattr(a, k), getattr(b, k), equal_nan=True), (new, k)
+    assert (b.status == 0).sum() > 800 and (b.status != 0).any()
