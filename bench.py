@@ -301,10 +301,9 @@ def main():
         def step_e2e():
             # phase 1: ONE C-ABI call for the batch — host tables + per-point state up, linearizeAll + setNewFrameEnergyTH
             # + applyRes + accumulateAF/LF/SCF, results down, returns when they are valid
-            outs = batch.step_host(io)
+            batch.step_host(io)
             # the caller keeps the threshold in its Frame and hands it back in the next hslam_window (as the reference does)
-            for o, (ws, ka, inp), w in zip(outs, io["keep"], wins):
-                ka[1]["frameEnergyTH"][w.n - 1] = o["frameEnergyTH"][0]
+            batch.feed_back_thresholds(io)
             # (the host solves the 60x60 systems here in the real pipeline) phase 2: back-substitution, x up, steps down
             batch.resubstitute_host(io, xs)
 

@@ -683,13 +683,26 @@ class EnergyFunctionalBatch:
                 dt = np.dtype(dt)
                 buf = (C.c_char * (count * dt.itemsize)).from_address(addr)
                 return np.frombuffer(buf, dtype=dt, count=count)
+            nmax = max(w.n for w in wins)
+            th_all = np.zeros((n, nmax), np.float32)      # Frame::frameEnergyTH of every window, one row each
             for i, (ef, w) in enumerate(zip(self.efs, wins)):
                 N = 8 * w.n + 4
                 # the per-point INPUT slots are bound as well: the caller's idepth / deltaF arrays ARE the pinned block
                 ws, ka, _old = keep[i]
                 inp = dict(idepth=view(arr[i].idepth, ef.P, np.float32), deltaF=view(arr[i].deltaF, ef.P, np.float32))
                 inp["idepth"][:] = w.idepth; inp["deltaF"][:] = w.deltaF
-                keep[i] = (ws, ka, inp)
+                # ... and the window tables (hslam_ba_batch_window_bind): setPrecalcValues / setAdjointsF write them in place
+                _chk(self.L.hslam_ba_batch_window_bind(self.h, C.c_int(i), C.byref(ws)))
+                nn = w.n * w.n
+                tabs = dict(precalc=view(ws.precalc, nn * 28, np.float32), adHTdeltaF=view(ws.adHTdeltaF, nn * 8, np.float32),
+                            adHost=view(ws.adHost, nn * 64, np.float64), adTarget=view(ws.adTarget, nn * 64, np.float64),
+                            framePrior=view(ws.framePrior, w.n * 8, np.float64), frameDeltaPrior=view(ws.frameDeltaPrior, w.n * 8, np.float64))
+                for k, v in tabs.items():
+                    v[:] = np.asarray(ka[1][k]).reshape(-1)
+                th_all[i, :w.n] = ka[1]["frameEnergyTH"]
+                tabs["frameEnergyTH"] = th_all[i, :w.n]
+                ws.frameEnergyTH = th_all[i].ctypes.data
+                keep[i] = (ws, [ka[0], tabs], inp)
                 outs.append(dict(energy=view(arr[i].energy, 1, np.float64), newState=view(arr[i].newState, ef.R, np.int8),
                                  newEnergy=view(arr[i].newEnergy, ef.R, np.float32),
                                  newEnergyWithOutlier=view(arr[i].newEnergyWithOutlier, ef.R, np.float32),
@@ -709,7 +722,26 @@ class EnergyFunctionalBatch:
                 arr[i].frameEnergyTH_out = _ptr(o["frameEnergyTH"])
                 arr[i].newest_frame = (w.n - 1) if newest_frame is None else int(newest_frame)
                 outs.append(o)
-        return dict(arr=arr, keep=keep, out=outs)
+        res = dict(arr=arr, keep=keep, out=outs)
+        if pinned == "bound":
+            res["th_all"] = th_all
+            # the threshold slots of the result block are equally spaced when the windows have the same size: one strided view
+            addr = [arr[i].frameEnergyTH_out for i in range(n)]
+            step = addr[1] - addr[0] if n > 1 else 4
+            if n > 1 and all(addr[i + 1] - addr[i] == step for i in range(n - 1)) and step > 0 and step % 4 == 0:
+                buf = (C.c_char * (step * (n - 1) + 4)).from_address(addr[0])
+                res["th_out"] = np.ndarray((n,), np.float32, buffer=buf, strides=(step,))
+                res["th_col"] = np.array([arr[i].newest_frame for i in range(n)])
+        return res
+
+    def feed_back_thresholds(self, io):
+        """The caller keeps the new frameEnergyTH in its Frame and hands it back in the next hslam_window (what the reference does
+        with newFrame->frame->frameEnergyTH); for bound io blocks this is one strided copy."""
+        if "th_out" in io:
+            io["th_all"][np.arange(len(self.efs)), io["th_col"]] = io["th_out"]
+        else:
+            for i, o in enumerate(io["out"]):
+                io["keep"][i][1][1]["frameEnergyTH"][io["arr"][i].newest_frame] = o["frameEnergyTH"][0]
 
     def step_host(self, io):
         """One GN iteration of every window with host buffers (one H2D block, one D2H block, one wait)."""
@@ -718,11 +750,13 @@ class EnergyFunctionalBatch:
 
     def resubstitute_host(self, io, xs):
         n = len(self.efs)
-        xa = [np.ascontiguousarray(x, np.float64) for x in xs]
-        xp = (C.c_void_p * n)(*[a.ctypes.data for a in xa])
+        if io.get("xs_id") != id(xs) or any(not (isinstance(x, np.ndarray) and x.dtype == np.float64 and x.flags.c_contiguous) for x in xs):
+            io["xa"] = [np.ascontiguousarray(x, np.float64) for x in xs]
+            io["xp"] = (C.c_void_p * n)(*[a.ctypes.data for a in io["xa"]])
+            io["xs_id"] = id(xs)      # the same list of fp64 arrays next time: the pointer table is reused (values are read by the call)
         if "step_ptrs" not in io:
             io["step_ptrs"] = (C.c_void_p * n)(*[o["step"].ctypes.data for o in io["out"]])
-        _chk(self.L.hslam_ba_batch_resubstitute_host(self.h, xp, io["step_ptrs"]))
+        _chk(self.L.hslam_ba_batch_resubstitute_host(self.h, io["xp"], io["step_ptrs"]))
         return [o["step"] for o in io["out"]]
 
     def close(self):

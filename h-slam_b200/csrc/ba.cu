@@ -1650,6 +1650,19 @@ int hslam_ba_batch_io_bind(hslam_ba_batch* B, hslam_ba_step_io* io, float** step
   return 0;
 }
 
+int hslam_ba_batch_window_bind(hslam_ba_batch* B, int i, hslam_window* w) {
+  HS_ARG(B && w && i >= 0 && i < (int)B->items.size(), "hslam_ba_batch_window_bind: bad argument");
+  HS_CUDA(cudaSetDevice(B->ctx->device));
+  HS_CUDA(cudaStreamSynchronize(B->ctx->stream));
+  TRY(batch_layout_down(B));
+  TRY(batch_layout_up(B));
+  const BAIO& L = B->io[i];
+  w->precalc = (const float*)(B->h_up + L.up_precalc); w->adHTdeltaF = (const float*)(B->h_up + L.up_adHTd);
+  w->adHost = (const double*)(B->h_up + L.up_adH); w->adTarget = (const double*)(B->h_up + L.up_adT);
+  w->framePrior = (const double*)(B->h_up + L.up_fprior); w->frameDeltaPrior = (const double*)(B->h_up + L.up_fdprior);
+  return 0;
+}
+
 int hslam_ba_batch_step_host(hslam_ba_batch* B, const hslam_ba_step_io* io) {
   HS_ARG(B && io, "hslam_ba_batch_step_host: null argument");
   hslam_ctx* ctx = B->ctx;
@@ -1731,12 +1744,14 @@ int hslam_ba_batch_step_host(hslam_ba_batch* B, const hslam_ba_step_io* io) {
       const size_t nn = (size_t)ba->n * ba->n, P = ba->P;
       if (o.window) {
         const hslam_window* w = o.window;
-        memcpy(B->h_up + L.up_precalc, w->precalc, nn * HSLAM_PRECALC_STRIDE * 4);
-        memcpy(B->h_up + L.up_adHTd, w->adHTdeltaF, nn * 8 * 4);
-        memcpy(B->h_up + L.up_adH, w->adHost, nn * 64 * 8);
-        memcpy(B->h_up + L.up_adT, w->adTarget, nn * 64 * 8);
-        memcpy(B->h_up + L.up_fprior, w->framePrior, (size_t)ba->n * 8 * 8);
-        memcpy(B->h_up + L.up_fdprior, w->frameDeltaPrior, (size_t)ba->n * 8 * 8);
+        // a table that already lives in its slot of the pinned upload block (hslam_ba_batch_window_bind) needs no copy
+        auto tab = [&](const void* src, long long off, size_t bytes) { if (src != (const void*)(B->h_up + off)) memcpy(B->h_up + off, src, bytes); };
+        tab(w->precalc, L.up_precalc, nn * HSLAM_PRECALC_STRIDE * 4);
+        tab(w->adHTdeltaF, L.up_adHTd, nn * 8 * 4);
+        tab(w->adHost, L.up_adH, nn * 64 * 8);
+        tab(w->adTarget, L.up_adT, nn * 64 * 8);
+        tab(w->framePrior, L.up_fprior, (size_t)ba->n * 8 * 8);
+        tab(w->frameDeltaPrior, L.up_fdprior, (size_t)ba->n * 8 * 8);
         any_in = true;
       }
       // a per-point input that already lives in its slot of the pinned block (hslam_ba_batch_io_bind) needs no copy

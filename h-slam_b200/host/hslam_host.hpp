@@ -177,6 +177,22 @@ class CoarseTracker {
     aff_g2l_out.a = aff[0]; aff_g2l_out.b = aff[1];
     return ok != 0;
   }
+  // The motion hypotheses of System::trackNewCoarse (System.cpp:348-481) in ONE launch: every lastF_2_fh_tries[i] is
+  // tracked by its own thread-block cluster; the caller then walks the results in try order with the reference's
+  // acceptance rule.  ok / residuals / flow per hypothesis, each bit-identical to a single trackNewestCoarse call.
+  void trackNewestCoarse_hypotheses(const Frame& newFrame, std::vector<SE3>& lastToNew_io, std::vector<AffLight>& aff_io, int coarsestLvl,
+                                    const double minResForAbort[5], std::vector<int>& ok, std::vector<double>& residuals5,
+                                    std::vector<double>& flow3) {
+    const int n = (int)lastToNew_io.size();
+    std::vector<const hslam_frame*> fr(n, newFrame.get());
+    std::vector<float> ex(n, newFrame.ab_exposure);
+    std::vector<double> T(12 * (size_t)n), a(2 * (size_t)n);
+    for (int i = 0; i < n; ++i) { std::memcpy(&T[12 * i], lastToNew_io[i].data(), 12 * sizeof(double)); a[2 * i] = aff_io[i].a; a[2 * i + 1] = aff_io[i].b; }
+    ok.assign(n, 0); residuals5.assign(5 * (size_t)n, 0.0); flow3.assign(3 * (size_t)n, 0.0);
+    check(hslam_tracker_track_batch(t_, n, fr.data(), ex.data(), T.data(), a.data(), coarsestLvl, minResForAbort, residuals5.data(),
+                                    flow3.data(), ok.data(), nullptr));
+    for (int i = 0; i < n; ++i) { std::memcpy(lastToNew_io[i].data(), &T[12 * i], 12 * sizeof(double)); aff_io[i].a = a[2 * i]; aff_io[i].b = a[2 * i + 1]; }
+  }
   // Vec6 calcRes(int lvl, const SE3& refToNew, AffLight aff_g2l, float cutoffTH)   (private in the reference)
   std::array<double, 6> calcRes(int lvl, const Frame& newFrame, const SE3& refToNew, AffLight aff_g2l, float cutoffTH) {
     std::array<double, 6> r;
@@ -331,6 +347,17 @@ class EnergyFunctional {
     return e;
   }
   void applyRes_Reductor() { check(hslam_ba_apply_res(ba_)); }
+  // void System::setNewFrameEnergyTH() (FullSystemOptimize.cpp:60-101; System::linearizeAll calls it after every pass, :124):
+  // exact nth_element on the device over the residuals into the newest keyframe; the frame's threshold is updated like
+  // newFrame->frame->frameEnergyTH, the per-residual energies never reach the host
+  float setNewFrameEnergyTH() {
+    float th = 0.f;
+    check(hslam_ba_new_frame_energy_th(ba_, nFrames - 1, &th));
+    const_cast<Frame*>(frames[nFrames - 1].frame)->frameEnergyTH = th;   // the reference writes newFrame->frame->frameEnergyTH
+    return th;
+  }
+  // GN-loop Jacobian mode (hslam_ba_set_jacobian_mode): per-pixel rows + projectedTo only when a residual is fixed
+  void setJacobianMode(int mode) { check(hslam_ba_set_jacobian_mode(ba_, mode)); }
 
   // void accumulateAF_MT(MatXX& H, VecX& b, bool MT) etc. (EnergyFunctional.cpp:155-220); MT is ignored:
   // the CUDA grid replaces IndexThreadReduce.

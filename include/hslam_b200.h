@@ -413,6 +413,12 @@ int hslam_ba_batch_step_host(hslam_ba_batch* batch, const hslam_ba_step_io* io /
  * no per-array work; the caller reads them in place (e.g. Eigen::Map).  The pointers stay valid until a
  * member's topology changes or the batch is destroyed. */
 int hslam_ba_batch_io_bind(hslam_ba_batch* batch, hslam_ba_step_io* io, float** step_out /*nullable*/);
+/* Zero-copy window tables: point the table members of `w` (precalc, adHTdeltaF, adHost, adTarget, framePrior,
+ * frameDeltaPrior) at window i's slots of the batch's page-locked upload block.  The caller's setPrecalcValues /
+ * setAdjointsF / setDeltaF then write the tables THERE (e.g. through Eigen::Map), and hslam_ba_batch_step_host uploads
+ * them without a staging copy.  Scalars, frames and frameEnergyTH of `w` stay the caller's.  Valid until a member's
+ * topology changes or the batch is destroyed. */
+int hslam_ba_batch_window_bind(hslam_ba_batch* batch, int i, hslam_window* w);
 /* EnergyFunctional::resubstituteF_MT for every window of the batch: x[i] = (8n+4) host doubles,
  * step_out[i] = P host floats (nullable). */
 int hslam_ba_batch_resubstitute_host(hslam_ba_batch* batch, const double* const* x, float* const* step_out);

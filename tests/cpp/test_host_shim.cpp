@@ -68,6 +68,7 @@ int main(int argc, char** argv) {
     ef.makeIDX();
     std::vector<int8_t> newState;
     double energy = ef.linearizeAll(false, &newState);
+    const float newFrameTH = ef.setNewFrameEnergyTH();   // System::linearizeAll calls it after the pass (FullSystemOptimize.cpp:124)
     ef.applyRes_Reductor();
     MatXX HA, HL, HS; VecX bA, bL, bS;
     ef.accumulateAF_MT(HA, bA, true);
@@ -113,6 +114,7 @@ int main(int argc, char** argv) {
     wr(fo, ef.adHost.data(), ef.adHost.size());
     wr(fo, ef.adTarget.data(), ef.adTarget.size());
     wr(fo, ef.adHTdeltaF.data(), ef.adHTdeltaF.size());
+    wr(fo, &newFrameTH, 1);
   } catch (const std::exception& e) {
     fprintf(stderr, "FAILED: %s\n", e.what());
     return 1;

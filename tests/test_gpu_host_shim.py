@@ -97,6 +97,7 @@ def test_host_shim_end_to_end(tmp_path, O, synth):
         adH = np.fromfile(f, np.float64, n * n * 64)
         adT = np.fromfile(f, np.float64, n * n * 64)
         adHTd = np.fromfile(f, np.float32, n * n * 8)
+        newFrameTH = np.fromfile(f, np.float32, 1)[0]
     # host tables: same operation order as the oracle's restatement of the reference
     pc_o, adH_o, adT_o, adHTd_o = O.prepare_window(win.cam, win.T_w2c_eval, win.state, win.state_zero, win.ab_exposure)
     # (the mirror's SE3::exp is Rodrigues, the oracle's goes through the unit quaternion as Sophus does:
@@ -111,7 +112,9 @@ def test_host_shim_end_to_end(tmp_path, O, synth):
     dIs = [O.pyramid(im, 1)[0][0] for im in win.images]
     of = O.BAOracle(w2, dIs, prec="f")
     od = O.BAOracle(w2, dIs, prec="d")
-    lf = of.linearize(False); of.apply_res()
+    lf = of.linearize(False)
+    assert newFrameTH == of.new_frame_energy_th(n - 1)      # System::setNewFrameEnergyTH through the mirror, bit-exact
+    of.apply_res()
     od.linearize(False); od.apply_res()
     assert np.array_equal(newState, lf["newState"])
     assert energy == pytest.approx(lf["energy"], rel=1e-12)
