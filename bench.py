@@ -140,7 +140,7 @@ def reference_arm(args, rank):
 
 def workload_config(windows):
     return {"workload": f"cfg2 (SURVEY 8d): BA window 7KF x 2000pts/KF x 8px (P=14000, R=84000), 30% of residuals isLinearized, "
-                        f"1 GN iteration hot path, {windows} independent windows per GPU per step over {N_SCENES} rendered scenes",
+                        f"1 GN iteration hot path (linearizeAll incl. setNewFrameEnergyTH + applyRes + accumulateAF/LF/SCF + stitch), {windows} independent windows per GPU per step over {N_SCENES} rendered scenes",
             "windows_per_gpu": windows, "frac_linearized": FRAC_LINEARIZED, "scenes": N_SCENES}
 
 
@@ -206,6 +206,7 @@ def main():
     res_per_step = sum(w.R for w in wins)
 
     batch = capi.EnergyFunctionalBatch(ctx, efs)
+    batch.set_newest_frame(N_FRAMES - 1)   # linearizeAll includes System::setNewFrameEnergyTH (device-side select, side branch of the graph)
 
     def step_device():
         batch.iteration()          # one CUDA graph of the launch chain for all windows of this GPU

@@ -660,6 +660,10 @@ class EnergyFunctionalBatch:
     def iteration(self):
         _chk(self.L.hslam_ba_batch_iteration(self.h))
 
+    def set_newest_frame(self, newest_frame):
+        """Device-resident GN loop: iteration() also runs System::setNewFrameEnergyTH for this frame of every window (-1: off)."""
+        _chk(self.L.hslam_ba_batch_set_newest_frame(self.h, C.c_int(int(newest_frame))))
+
     def make_io(self, wins, frames_per_window, pinned=True, newest_frame=None):
         """Persistent host-side I/O block for step_host(): per window the hslam_window struct, the per-point
         inputs and the output arrays.  pinned="bound": the outputs are views of the batch's own page-locked

@@ -312,14 +312,55 @@ static int build_chunks(hslam_ba* ba) {
       ba->sched_bb0[m] = (int)bb.size();
       ba->n_topblocks[m] = T;
       const int c0 = (int)ch.size();
-      for (int b = 0; b < T; ++b) {
-        bb.push_back(b * per);
-        const int e = std::min(NT, (b + 1) * per);
-        for (int t = b * per; t < e; ++t) {
-          if (t == b * per || ht[t].pair != ht[t - 1].pair) ch.push_back(TopChunk{ht[t].pair, ht[t].start, 0, m});
-          ch.back().count += ht[t].count;
-          tiles.push_back(TopTile{ht[t].start, ht[t].count, (int)ch.size() - 1, ht[t].pair});
+#ifndef TOP_ITEM_TILES
+#define TOP_ITEM_TILES 12
+#endif
+      // ITEMS: a pair's tiles are cut into pieces of <= TOP_ITEM_TILES tiles (= one chunk each: one fp32 partial, folded
+      // in chunk order).  Chunk ids follow the pair order (the fold walks pcb[pair] .. pcb[pair + 1]).  The items are then
+      // dealt to the blocks in the order (host, piece, target), each to the block with the least tiles so far: the
+      // blocks of a window — resident together, progressing in step — work on the SAME stretch of a host's points
+      // towards its different targets at the same time, so the 32-byte records that they store into the point-major
+      // record array (stride pstr per point, one record per target) meet in L2 and leave as whole lines.  With equal
+      // runs of tiles per block the six records of a point were written a whole kernel apart: 45 us of 390 went into
+      // partial-line write-backs (measured: records stored in residual order instead).
+      struct Item { int t0, nt, chunk, host, piece, target; };
+      std::vector<Item> items;
+      {
+        const int lim = std::max(1, std::min(TOP_ITEM_TILES, per));
+        int t = 0;
+        while (t < NT) {
+          int e = t;
+          while (e < NT && ht[e].pair == ht[t].pair) ++e;
+          const int nt = e - t, pieces = (nt + lim - 1) / lim, sz = (nt + pieces - 1) / pieces;
+          for (int q = 0; q < pieces; ++q) {
+            const int a = t + q * sz, b = std::min(e, a + sz);
+            if (a >= b) break;
+            int cnt = 0;
+            for (int x = a; x < b; ++x) cnt += ht[x].count;
+            ch.push_back(TopChunk{ht[t].pair, ht[a].start, cnt, m});
+            items.push_back(Item{a, b - a, (int)ch.size() - 1, ht[t].pair % n, q, ht[t].pair / n});
+          }
+          t = e;
         }
+      }
+      std::stable_sort(items.begin(), items.end(), [](const Item& x, const Item& y) {
+        if (x.host != y.host) return x.host < y.host;
+        if (x.piece != y.piece) return x.piece < y.piece;
+        return x.target < y.target;
+      });
+      std::vector<std::vector<int>> mine(T);
+      std::vector<int> load(T, 0);
+      for (size_t it = 0; it < items.size(); ++it) {
+        int best = 0;
+        for (int b = 1; b < T; ++b) if (load[b] < load[best]) best = b;
+        mine[best].push_back((int)it); load[best] += items[it].nt;
+      }
+      int off = 0;
+      for (int b = 0; b < T; ++b) {
+        bb.push_back(off);
+        for (int it : mine[b])
+          for (int x = items[it].t0; x < items[it].t0 + items[it].nt; ++x, ++off)
+            tiles.push_back(TopTile{ht[x].start, ht[x].count, items[it].chunk, ht[x].pair});
       }
       bb.push_back(NT);
       int c = c0;
@@ -339,6 +380,8 @@ static int build_chunks(hslam_ba* ba) {
     // pairs without any chunk in a schedule are never folded: their accumulators must read as zero
     HS_CUDA(cudaMemsetAsync(ba->d_accTop.p, 0, 3 * (size_t)nn * TOP_DENSE * sizeof(double), ctx->stream));
     // lineariser: tiles of <= LIN_THREADS non-linearised residuals of one pair
+    // (Order: pair-major, i.e. the sorted order.  A host-major order — the j-th tiles of all targets of a host next to each
+    // other, so that the host's point records are re-read from L2 — was measured: 636 vs 635 us, all-active 1.446 vs 1.408 ms.)
     std::vector<LinTile> lt;
     for (int k = 0; k < nn; ++k)
       for (int s0 = seg[2 * k]; s0 < seg[2 * k + 1]; s0 += LIN_THREADS)
@@ -809,7 +852,7 @@ static int top_attr(hslam_ctx* ctx) {
   return 0;
 }
 // modes: bit 0 = A, bit 1 = L
-static int launch_top(hslam_ba* ba, int modes) {
+static int launch_top(hslam_ba* ba, int modes, bool fold = true) {
   hslam_ctx* ctx = ba->ctx;
   TRY(sync_desc(ba));
   TRY(top_attr(ctx));
@@ -820,6 +863,8 @@ static int launch_top(hslam_ba* ba, int modes) {
     HS_LAUNCH(ctx, HSLAM_K_BA_TOP, (ba_top_kernel<1><<<ba->n_topblocks[1], 2 * TOP_THREADS, kTopSmem, ctx->stream>>>(ba->d_desc.p, nullptr, 1)));
   if (ba->n_topblocks[2] > 0 && (modes & 4))   // addPoint<2> over the points flagged in desc.marg
     HS_LAUNCH(ctx, HSLAM_K_BA_TOP, (ba_top_kernel<2><<<ba->n_topblocks[2], 2 * TOP_THREADS, kTopSmem, ctx->stream>>>(ba->d_desc.p, nullptr, 1)));
+  if (fold)   // chunk partials -> dense fp64 accumulators (the fused paths let the Schur fold launch do it)
+    HS_LAUNCH(ctx, HSLAM_K_BA_FOLD_SC, (ba_fold_sc_kernel<<<fold_top_blocks(ba->n, modes), 256, 0, ctx->stream>>>(ba->d_desc.p, nullptr, 1, modes, 0)));
   HS_CUDA(cudaGetLastError());
   return 0;
 }
@@ -855,14 +900,14 @@ static void schur_launch(int maxt, int blocks, size_t smem, cudaStream_t st, con
   schur_dispatch(maxt, [&](auto k) -> int { k<<<blocks, SC_THREADS, smem, st>>>(d, pf, n); return 0; });
 }
 
-static int launch_schur(hslam_ba* ba) {
+static int launch_schur(hslam_ba* ba, int top_modes = 0) {
   hslam_ctx* ctx = ba->ctx;
   TRY(sync_desc(ba));
   size_t smem = schur_smem(ba->LD, ba->maxres);
   TRY(schur_attr(ctx, smem));
   if (ba->n_ptchunks > 0)
     HS_LAUNCH(ctx, HSLAM_K_BA_SCHUR, schur_launch(schur_maxt(ba->LD), ba->n_ptchunks, smem, ctx->stream, ba->d_desc.p, nullptr, 1));
-  HS_LAUNCH(ctx, HSLAM_K_BA_FOLD_SC, (ba_fold_sc_kernel<<<ba->n * ((ba->LD * ba->LD + 255) / 256), 256, 0, ctx->stream>>>(ba->d_desc.p, nullptr, 1)));
+  HS_LAUNCH(ctx, HSLAM_K_BA_FOLD_SC, (ba_fold_sc_kernel<<<ba->n * ((ba->LD * ba->LD + 255) / 256) + (top_modes ? fold_top_blocks(ba->n, top_modes) : 0), 256, 0, ctx->stream>>>(ba->d_desc.p, nullptr, 1, top_modes, 1)));
   HS_CUDA(cudaGetLastError());
   return 0;
 }
@@ -898,8 +943,8 @@ static int queue_Hb(hslam_ba* ba, int sys, double* H, double* b) {
 
 static int enqueue_accumulate_all(hslam_ba* ba, int with_energy = 0) {
   const int modes = 1 | (ba->n_linearized != 0 ? 2 : 0);
-  TRY(launch_top(ba, modes));
-  TRY(launch_schur(ba));
+  TRY(launch_top(ba, modes, false));
+  TRY(launch_schur(ba, 3));   // the fold launch also folds the top accumulators of A and L (L reads as zero without chunks)
   TRY(launch_stitch(ba, 0, 3, with_energy));
   return 0;
 }
@@ -1229,8 +1274,8 @@ int hslam_ba_marginalize_points(hslam_ba* ba, const int32_t* point_ids, int coun
   ba->hdesc.marg = ba->d_marg.p; ba->hdesc.shift_prior = 0;
   ba->hdesc.S.add_priors = 0; ba->hdesc.S.has_L = 1; ba->hdesc.S.L_set = 2;
   ba->desc_version++;
-  TRY(launch_top(ba, 4));
-  TRY(launch_schur(ba));
+  TRY(launch_top(ba, 4, false));
+  TRY(launch_schur(ba, 4));
   TRY(launch_stitch(ba, 1, 3));
   TRY(queue_Hb(ba, 1, M, Mb));
   TRY(queue_Hb(ba, 2, Msc, Mbsc));
@@ -1345,6 +1390,8 @@ struct hslam_ba_batch {
   cudaStream_t up_stream = nullptr;   // step_host: uploads + import of group g+1 run here while group g is linearised
   cudaEvent_t ev_up[8] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
   cudaEvent_t ev_begin = nullptr;
+  int th_newest = -1;                 // >= 0: hslam_ba_batch_iteration also runs setNewFrameEnergyTH for this frame of every window
+  cudaEvent_t ev_th[2] = {nullptr, nullptr};
   size_t dn_state_end = 0, dn_res_end = 0, dn_sys_end = 0, dn_end = 0;   // D2H block regions: [0,res) per-residual arrays, [res,sys) systems, [sys,end) steps
 };
 static const int NPF = 7;
@@ -1378,7 +1425,7 @@ static int batch_refresh(hslam_ba_batch* B) {
     pf[1][i + 1] = pf[1][i] + top;
     pf[2][i + 1] = pf[2][i] + ba->n_ptchunks;
     pf[3][i + 1] = pf[3][i] + 3 * (ba->n + 1) * (ba->n + 1);
-    pf[4][i + 1] = pf[4][i] + ba->n * ((ba->LD * ba->LD + 255) / 256);
+    pf[4][i + 1] = pf[4][i] + ba->n * ((ba->LD * ba->LD + 255) / 256) + fold_top_blocks(ba->n, 3);   // Schur fold + top folds (A, L)
     pf[5][i + 1] = pf[5][i] + (ba->P + 127) / 128;
     B->smem = std::max(B->smem, schur_smem(ba->LD, ba->maxres));
     B->maxt = std::max(B->maxt, schur_maxt(ba->LD));
@@ -1430,6 +1477,7 @@ int hslam_ba_batch_create(hslam_ctx* ctx, hslam_ba* const* items, int count, hsl
   HS_CUDA(cudaMallocHost((void**)&B->h_prefix, NPF * (size_t)(count + 1) * sizeof(int)));
   HS_CUDA(cudaEventCreateWithFlags(&B->copied, cudaEventDisableTiming));
   for (int g = 0; g < 8; ++g) HS_CUDA(cudaEventCreateWithFlags(&B->ev_grp[g], cudaEventDisableTiming));
+  for (int g = 0; g < 2; ++g) HS_CUDA(cudaEventCreateWithFlags(&B->ev_th[g], cudaEventDisableTiming));
   for (int g = 0; g < 8; ++g) HS_CUDA(cudaEventCreateWithFlags(&B->ev_up[g], cudaEventDisableTiming));
   HS_CUDA(cudaEventCreateWithFlags(&B->ev_begin, cudaEventDisableTiming));
   HS_CUDA(cudaStreamCreateWithFlags(&B->up_stream, cudaStreamNonBlocking));
@@ -1447,6 +1495,7 @@ int hslam_ba_batch_destroy(hslam_ba_batch* B) {
   if (B->h_dn) cudaFreeHost(B->h_dn);
   cudaEventDestroy(B->copied);
   for (int g = 0; g < 8; ++g) if (B->ev_grp[g]) cudaEventDestroy(B->ev_grp[g]);
+  for (int g = 0; g < 2; ++g) if (B->ev_th[g]) cudaEventDestroy(B->ev_th[g]);
   for (int g = 0; g < 8; ++g) if (B->ev_up[g]) cudaEventDestroy(B->ev_up[g]);
   if (B->ev_begin) cudaEventDestroy(B->ev_begin);
   if (B->up_stream) { cudaStreamSynchronize(B->up_stream); cudaStreamDestroy(B->up_stream); }
@@ -1469,7 +1518,24 @@ static int batch_enqueue_linearize(hslam_ba_batch* B, int g0 = 0, int g1 = -1) {
   HS_CUDA(cudaGetLastError());
   return 0;
 }
-static int batch_enqueue_accumulate(hslam_ba_batch* B) {
+// System::setNewFrameEnergyTH inside the device-resident iteration (FullSystemOptimize.cpp:124: part of linearizeAll):
+// one block per window on the side stream, forked in front of the stitch and joined behind it — the accumulate kernels
+// do not read the threshold, the next linearisation does.  (Forked right behind the lineariser it ran beside the top
+// kernel, whose two 128-register blocks per SM then no longer fit on 64 of the SMs: +23 us per step; the stitch's small
+// blocks do not care.)
+static int batch_fork_th(hslam_ba_batch* B) {
+  hslam_ctx* ctx = B->ctx;
+  HS_CUDA(cudaEventRecord(B->ev_th[0], ctx->stream));
+  HS_CUDA(cudaStreamWaitEvent(ctx->side, B->ev_th[0], 0));
+  ctx->launches++;   // side stream: counted, not event-timed
+  ba_energy_th_kernel<<<(unsigned)B->items.size(), TH_THREADS, 0, ctx->side>>>(B->d_descs.p, B->th_newest, nullptr, nullptr, nullptr);
+  HS_CUDA(cudaGetLastError());
+  HS_CUDA(cudaEventRecord(B->ev_th[1], ctx->side));
+  return 0;
+}
+static int batch_join_th(hslam_ba_batch* B) { HS_CUDA(cudaStreamWaitEvent(B->ctx->stream, B->ev_th[1], 0)); return 0; }
+
+static int batch_enqueue_accumulate(hslam_ba_batch* B, bool with_th = false) {
   hslam_ctx* ctx = B->ctx;
   const int n = (int)B->items.size();
   const int* pf = B->d_prefix.p;
@@ -1482,9 +1548,11 @@ static int batch_enqueue_accumulate(hslam_ba_batch* B) {
     HS_LAUNCH(ctx, HSLAM_K_BA_TOP, (ba_top_kernel<1><<<B->blocks[6], 2 * TOP_THREADS, kTopSmem, ctx->stream>>>(B->d_descs.p, pf + 6 * (n + 1), B->uniform[6] ? -B->uniform[6] : n)));
   if (B->blocks[2] > 0)
     HS_LAUNCH(ctx, HSLAM_K_BA_SCHUR, schur_launch(B->maxt, B->blocks[2], B->smem, ctx->stream, B->d_descs.p, pf + 2 * (n + 1), B->uniform[2] ? -B->uniform[2] : n));
-  HS_LAUNCH(ctx, HSLAM_K_BA_FOLD_SC, (ba_fold_sc_kernel<<<B->blocks[4], 256, 0, ctx->stream>>>(B->d_descs.p, pf + 4 * (n + 1), B->uniform[4] ? -B->uniform[4] : n)));
+  HS_LAUNCH(ctx, HSLAM_K_BA_FOLD_SC, (ba_fold_sc_kernel<<<B->blocks[4], 256, 0, ctx->stream>>>(B->d_descs.p, pf + 4 * (n + 1), B->uniform[4] ? -B->uniform[4] : n, 3, 1)));
+  if (with_th) TRY(batch_fork_th(B));
   HS_LAUNCH(ctx, HSLAM_K_BA_STITCH, (ba_stitch_kernel<<<B->blocks[3], ST_THREADS, 0, ctx->stream>>>(B->d_descs.p, pf + 3 * (n + 1), B->uniform[3] ? -B->uniform[3] : n, 0, 3, 1)));
   HS_CUDA(cudaGetLastError());
+  if (with_th) TRY(batch_join_th(B));
   return 0;
 }
 
@@ -1496,9 +1564,10 @@ static int batch_graph_launch(hslam_ba_batch* B, bool with_linearize) {
   uint64_t& ver = with_linearize ? B->graph_iter_version : B->graph_acc_version;
   int& nk = with_linearize ? B->graph_iter_kernels : B->graph_acc_kernels;
   static const bool disabled = getenv("HSLAM_NO_GRAPH") != nullptr;
+  const bool with_th = with_linearize && B->th_newest >= 0;
   if (ctx->profile || disabled) {
     if (with_linearize) TRY(batch_enqueue_linearize(B));
-    return batch_enqueue_accumulate(B);
+    return batch_enqueue_accumulate(B, with_th);
   }
   if (!exec || ver != B->refresh_version) {
     TRY(schur_attr(ctx, B->smem));
@@ -1508,7 +1577,7 @@ static int batch_graph_launch(hslam_ba_batch* B, bool with_linearize) {
     HS_CUDA(cudaStreamBeginCapture(ctx->stream, cudaStreamCaptureModeThreadLocal));
     int rc = 0;
     if (with_linearize) rc = batch_enqueue_linearize(B);
-    if (!rc) rc = batch_enqueue_accumulate(B);
+    if (!rc) rc = batch_enqueue_accumulate(B, with_th);
     cudaGraph_t g = nullptr;
     cudaError_t e = cudaStreamEndCapture(ctx->stream, &g);
     if (rc) { if (g) cudaGraphDestroy(g); return rc; }
@@ -1521,6 +1590,14 @@ static int batch_graph_launch(hslam_ba_batch* B, bool with_linearize) {
   }
   HS_CUDA(cudaGraphLaunch(exec, ctx->stream));
   ctx->launches += nk;
+  return 0;
+}
+
+int hslam_ba_batch_set_newest_frame(hslam_ba_batch* B, int newest_frame) {
+  HS_ARG(B, "hslam_ba_batch_set_newest_frame: null");
+  for (hslam_ba* ba : B->items) HS_ARG(newest_frame < ba->n, "hslam_ba_batch_set_newest_frame: frame index out of range for a window");
+  if (newest_frame < 0) newest_frame = -1;
+  if (newest_frame != B->th_newest) { B->th_newest = newest_frame; B->refresh_version++; }   // the graph is re-captured
   return 0;
 }
 

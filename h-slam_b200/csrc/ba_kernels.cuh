@@ -254,12 +254,23 @@ __global__ void __launch_bounds__(LIN_THREADS, LIN_MINB) ba_linearize_kernel(con
     valid = (int)threadIdx.x < tl.count;
     k = tl.start + threadIdx.x;
     pair = tl.pair;
+#ifdef LIN_EXP_NOTILE   /* timing experiment only (wrong results): the residual index does not wait for the tile descriptor */
+    k = min(lb * LIN_THREADS + (int)threadIdx.x, r.R - 1); valid = true;
+#endif
   }
   double energy_ret = 0.0;
   // every per-residual input is loaded up front (independent loads, one round trip)
   const int8_t st0 = valid ? r.state_state[k] : (int8_t)HSLAM_RES_OOB;
   const float old_energy = valid ? r.state_energy[k] : 0.f;
+#ifdef LIN_EXP_NOPOINT  /* timing experiment only (wrong results): the point record does not wait for the point index */
+  const int p = k / 6;
+#elif defined(LIN_EXP_NOPOINT2)   /* no dependency, but 32 distinct consecutive points per warp (the real traffic) */
+  const int p = k % D.p.P;
+#elif defined(LIN_EXP_DEPPOINT)   /* dependency kept, 6 residuals share a point (less traffic) */
+  const int p = valid ? (r.point[k] >> 30) + k / 6 : 0;
+#else
   const int p = valid ? r.point[k] : 0;
+#endif
   const int sp = (APPLY && valid && !refresh) ? r.slotpos[k] : 0;
   if (valid) {
     float* J = r.J + k;
@@ -839,9 +850,11 @@ __device__ __forceinline__ void top_unpack_index(int t, int& r, int& c) {
   else if (t < 85) { r = (t - 55) / 3; c = 10 + (t - 55) % 3; }
   else { const int u = t - 85; r = u < 3 ? 10 : (u < 5 ? 11 : 12); c = u < 3 ? 10 + u : (u < 5 ? 8 + u : 12); }
 }
-// chunk partial -> global, then the per-(mode,pair) fold by the last block of that pair (chunks in index order)
-__device__ __forceinline__ void top_flush(const BADesc& D, int chunk, int part, float (&acc)[56], int nres,
-                                          float (*red)[33], bool* last) {
+// chunk partial -> global.  The per-(mode, pair) fold of the partials into fp64 (chunks in index order) is a separate,
+// wide launch (fold_top_slot, run by extra blocks of ba_fold_sc_kernel): folding here by "the last block of a pair" put a
+// __threadfence (= wait for the tile's record stores), an atomic round trip and two more barriers into EVERY flush — 6.4 us
+// per flush measured, during which half of the SM's warps and the block's TMA ring stood still.
+__device__ __forceinline__ void top_flush(const BADesc& D, int chunk, int part, float (&acc)[56], int nres, float (*red)[33]) {
   // two shuffle levels take a warp's 32 lanes to 8, the remaining 8 lanes x 4 warps = 32 values per
   // accumulator are summed in a fixed order by one thread per accumulator (a full shuffle tree per
   // accumulator costs 10 instructions x 91 per warp; this is 4 x 91 + a 32-term sum by 92 threads)
@@ -875,36 +888,35 @@ __device__ __forceinline__ void top_flush(const BADesc& D, int chunk, int part, 
       for (int w = 0; w < 32; ++w) v += red[t][w];
       out[t] = v;
     }
-    __threadfence();
   }
-  __syncthreads();
-  const TopChunk ch = D.topchunks[chunk];
-  const int nn = D.W.n * D.W.n;
-  const int slot = ch.mode * nn + ch.pair;
+  __syncthreads();   // `red` is reused by the next chunk
+}
+
+// Fold of the chunk partials of one (mode, pair) slot into the dense fp64 13x13 accumulator that the stitch reads, chunks
+// in index order; thread t < 92 owns accumulator t (91 = the residual count).  A slot without chunks reads as zero.
+__device__ __forceinline__ void fold_top_slot(const BADesc& D, int slot, int t) {
+  if (t >= 92) return;
   const int cb = D.pair_chunk_begin[slot], ce = D.pair_chunk_begin[slot + 1];
-  if (threadIdx.x == 0) *last = (atomicAdd(D.pair_ticket + slot, 1u) == (unsigned)(ce - cb) - 1);
-  __syncthreads();
-  if (*last) {
-    __threadfence();
-    if (threadIdx.x < 92) {
-      int t = threadIdx.x;
-      // the folded accumulator is stored as a DENSE symmetric 13x13 (what the stitch reads with plain indexing)
-      double* dst = D.accTop + (size_t)slot * TOP_DENSE;
-      if (t == 91) {
-        int n = 0;
-        for (int c = cb; c < ce; ++c) n += __float_as_int(__ldcg(D.toppartial + (size_t)c * TOP_PART + 91));
-        dst[169] = (double)n;
-      } else {
-        double sum = 0.0;
-        for (int c = cb; c < ce; ++c) sum += (double)__ldcg(D.toppartial + (size_t)c * TOP_PART + t);
-        int rr, cc;
-        top_unpack_index(t, rr, cc);
-        dst[rr * 13 + cc] = sum; dst[cc * 13 + rr] = sum;
-      }
+  double* dst = D.accTop + (size_t)slot * TOP_DENSE;
+  if (t == 91) {
+    int n = 0;
+    for (int c = cb; c < ce; ++c) n += __float_as_int(__ldcg(D.toppartial + (size_t)c * TOP_PART + 91));
+    dst[169] = (double)n;
+  } else {
+    double sum = 0.0;
+    int c = cb;
+    for (; c + 4 <= ce; c += 4) {   // four independent loads in flight, summed in chunk order
+      float v[4];
+#pragma unroll
+      for (int q = 0; q < 4; ++q) v[q] = __ldcg(D.toppartial + (size_t)(c + q) * TOP_PART + t);
+#pragma unroll
+      for (int q = 0; q < 4; ++q) sum += (double)v[q];
     }
-    if (threadIdx.x == 0) D.pair_ticket[slot] = 0;
+    for (; c < ce; ++c) sum += (double)__ldcg(D.toppartial + (size_t)c * TOP_PART + t);
+    int rr, cc;
+    top_unpack_index(t, rr, cc);
+    dst[rr * 13 + cc] = sum; dst[cc * 13 + rr] = sum;
   }
-  __syncthreads();   // `last` and `red` are reused by the next chunk
 }
 
 // 10x10 upper triangle of [x y] [[a b],[b c]] [x y]^T into acc[0..54] (PART 0 threads).  Packed fp32 (FMUL2 / FFMA2 /
@@ -957,7 +969,6 @@ __global__ void __launch_bounds__(2 * TOP_THREADS, 2) ba_top_kernel(const BADesc
   // 128-byte alignment in the shared window (the launch reserves 128 spare bytes)
   Stage* ring = reinterpret_cast<Stage*>(top_smem + ((128u - (smem_u32(top_smem) & 127u)) & 127u));
   __shared__ float red[92][33];   // [accumulator][4 warps x 8 lanes], padded: conflict-free both ways
-  __shared__ bool last;
   int lb;
   const int win = find_window(prefix, nwin, blockIdx.x, lb);
   const BADesc& D = descs[win];
@@ -1035,7 +1046,7 @@ __global__ void __launch_bounds__(2 * TOP_THREADS, 2) ba_top_kernel(const BADesc
     const int chunk = tl.chunk;
     if (chunk != cur) {
       if (cur >= 0) {
-        top_flush(D, cur, part, acc, nres, red, &last);
+        top_flush(D, cur, part, acc, nres, red);
 #pragma unroll
         for (int i = 0; i < 55; ++i) acc[i] = 0.f;
         nres = 0;
@@ -1108,7 +1119,13 @@ __global__ void __launch_bounds__(2 * TOP_THREADS, 2) ba_top_kernel(const BADesc
         // the point's own order by the Schur kernel, which keeps Hdd/bd/Hcd bit-identical to the oracle.
         const float Ji0 = xadd(xmul(a, d0), xmul(b, d1)), Ji1 = xadd(xmul(b, d0), xmul(c, d1));
         // the residual's 32-byte record in its point's slot: one 256-bit store
+#if defined(TOP_EXP_LINREC)      /* timing experiment only: records in residual order (coalesced) */
+        stg256(r.prec + 8 * (size_t)(tl.start + l),
+#elif defined(TOP_EXP_NOREC)     /* timing experiment only: no record store */
+        if (rr == 123456.f) stg256(r.prec + S.sp[col],
+#else
         stg256(r.prec + S.sp[col],
+#endif
                make_float4(xadd(xmul(JIr0, d0), xmul(JIr1, d1)), xadd(xmul(Ji0, d0), xmul(Ji1, d1)),
                            xadd(xmul(x[0], Ji0), xmul(y[0], Ji1)), xadd(xmul(x[1], Ji0), xmul(y[1], Ji1))),
                make_float4(xadd(xmul(x[2], Ji0), xmul(y[2], Ji1)), xadd(xmul(x[3], Ji0), xmul(y[3], Ji1)), MODE == 1 ? 2.f : 1.f,
@@ -1121,7 +1138,7 @@ __global__ void __launch_bounds__(2 * TOP_THREADS, 2) ba_top_kernel(const BADesc
     __syncwarp();
     if (lane == 0) mbar_arrive(&empty_bar[j % STAGES]);   // this warp is done with the stage
   }
-  if (cur >= 0) top_flush(D, cur, part, acc, nres, red, &last);
+  if (cur >= 0) top_flush(D, cur, part, acc, nres, red);
 }
 
 // Per-point sums of Hdd/bd/Hcd over the point's residuals in the point's own order (the tail of
@@ -1375,12 +1392,30 @@ ba_schur_kernel(const BADesc* __restrict__ descs, const int* __restrict__ prefix
 // folding inside the Schur kernel by "the last block of a host" put ~0.5 MB of dependent reads per host
 // on ONE block at the very end of the kernel (measured: 165 us of a 190 us launch for 8 windows).
 // grid: per window n * ceil(LD*LD / 256) blocks.
+// Blocks behind the Schur part fold the top accumulators (fold_top_slot): two (mode, pair) slots per block, the modes
+// of bit mask `top_modes` (1 = A, 2 = L, 4 = marginalisation) in bit order.  with_sc = 0: top folds only.
+__host__ __device__ inline int fold_top_blocks(int n, int top_modes) {
+  const int nm = (top_modes & 1) + ((top_modes >> 1) & 1) + ((top_modes >> 2) & 1);
+  return (nm * n * n + 1) / 2;
+}
 __global__ void __launch_bounds__(256) ba_fold_sc_kernel(const BADesc* __restrict__ descs,
-                                                         const int* __restrict__ prefix, int nwin) {
+                                                         const int* __restrict__ prefix, int nwin, int top_modes, int with_sc) {
   int lb;
   const int win = find_window(prefix, nwin, blockIdx.x, lb);
   const BADesc& D = descs[win];
   const int LD = D.LD, per = (LD * LD + 255) / 256;
+  const int nsc = with_sc ? D.W.n * per : 0;
+  if (lb >= nsc) {
+    const int nn = D.W.n * D.W.n;
+    int idx = (lb - nsc) * 2 + (threadIdx.x >> 7);
+#pragma unroll
+    for (int m = 0; m < 3; ++m) {
+      if (!((top_modes >> m) & 1)) continue;
+      if (idx < nn) { fold_top_slot(D, m * nn + idx, threadIdx.x & 127); return; }
+      idx -= nn;
+    }
+    return;
+  }
   const int host = lb / per;
   const int i = (lb % per) * 256 + threadIdx.x;
   if (i >= LD * LD) return;

@@ -419,6 +419,11 @@ int hslam_ba_batch_io_bind(hslam_ba_batch* batch, hslam_ba_step_io* io, float** 
  * them without a staging copy.  Scalars, frames and frameEnergyTH of `w` stay the caller's.  Valid until a member's
  * topology changes or the batch is destroyed. */
 int hslam_ba_batch_window_bind(hslam_ba_batch* batch, int i, hslam_window* w);
+/* Device-resident GN loop: with newest_frame >= 0 every hslam_ba_batch_iteration also runs System::setNewFrameEnergyTH
+ * (FullSystemOptimize.cpp:60-101; part of linearizeAll, :124) for frame `newest_frame` of every window: the new threshold
+ * is written into the window's device-side frameEnergyTH table, where the next linearisation reads it (it is replaced by
+ * the caller's table at the next hslam_ba_set_window / step_host with a window).  -1 switches it off (default). */
+int hslam_ba_batch_set_newest_frame(hslam_ba_batch* batch, int newest_frame);
 /* EnergyFunctional::resubstituteF_MT for every window of the batch: x[i] = (8n+4) host doubles,
  * step_out[i] = P host floats (nullable). */
 int hslam_ba_batch_resubstitute_host(hslam_ba_batch* batch, const double* const* x, float* const* step_out);

@@ -6,12 +6,20 @@
  * bench.py's cpu_baseline / --impl reference legs may load this library; the
  * product (h-slam_b200/) never does.
  *
- * PARITY UNPINNED: the reference ships no tests, golden vectors or fixtures for
- * this path and cannot be compiled in this environment
- * (Eigen/Boost/OpenCV absent), so the oracle is pinned only by (a) analytic
- * known answers (finite-difference Jacobians, Schur identity vs a dense
- * elimination, zero-motion tracking, Sophus group identities) and (b) agreement
- * between its two independent precisions, see tests/test_oracle_*.py.
+ * PARITY PINNED AGAINST THE COMPILED REFERENCE (round 2): the reference ships no
+ * tests, golden vectors or fixtures for this path and its
+ * build needs Eigen/Boost/OpenCV, which this image lacks.  oracle/Makefile
+ * therefore compiles the reference's own hot-path translation units UNMODIFIED,
+ * from where they lie under /root/reference (OptimizationClasses.cpp,
+ * AccumulatedTopHessian.cpp, AccumulatedSCHessian.cpp, CoarseTracker.cpp,
+ * ImmaturePoint.cpp, Settings.cpp), against the minimal library stand-ins of
+ * oracle/ref_shim/ (fixed-size Eigen subset with Eigen 3.3's evaluation order,
+ * Sophus SE3, boost->std, type stubs) into oracle/_ref/libhslam_ref*.so;
+ * tests/test_oracle_vs_reference.py drives both on the same inputs: linearize /
+ * applyRes, the tracker's LM path, makeCoarseDepthL0 and traceOn agree BIT FOR
+ * BIT with the float restatement, the stitched systems to 1e-9..1e-12.  The
+ * analytic known answers of tests/test_oracle_*.py (finite differences, dense
+ * Schur elimination, zero motion, group identities) remain as a second anchor.
  *
  * Two restatements of every function:
  *   *_f : float-faithful — fp32 arithmetic in the operation order written in

@@ -468,6 +468,40 @@ def test_batch_step_host_slim_outputs_with_device_threshold(ctx, capi, O, synth)
         f.close()
 
 
+def test_batch_iteration_with_device_threshold(ctx, capi, O, synth):
+    """Device-resident GN loop: hslam_ba_batch_set_newest_frame makes every hslam_ba_batch_iteration run
+    setNewFrameEnergyTH on the device; the NEXT linearisation classifies with the new threshold, like the oracle's
+    linearizeAll -> setNewFrameEnergyTH -> applyRes -> linearizeAll sequence."""
+    kf = synth.render_keyframes(320, 240, 5, seed=84)
+    wins = [synth.make_window(points_per_frame=120 + 40 * i, seed=650 + i, keyframes=kf, frac_linearized=0.1 * i)[0] for i in range(5)]
+    frames = [capi.Frame(ctx, im, 1) for im in kf.images]
+    dIs = [O.pyramid(im, 1)[0][0] for im in kf.images]
+    efs = []
+    for w in wins:
+        b = capi.EnergyFunctional(ctx); b.set_window(w, frames); b.set_topology(w); efs.append(b)
+    batch = capi.EnergyFunctionalBatch(ctx, efs)
+    batch.set_newest_frame(wins[0].n - 1)
+    orcs = [O.BAOracle(w, dIs, prec="f") for w in wins]
+    changed = 0
+    for it in range(3):
+        batch.iteration()
+        for w, ef, orc in zip(wins, efs, orcs):
+            lo = orc.linearize(False)
+            th = orc.new_frame_energy_th(w.n - 1)
+            orc.apply_res()
+            rg = ef.residual_results(want_J=False)
+            assert np.array_equal(rg["state_state"], orc.residual_results()["state_state"]), it
+            e, _, _ = ef.download_stats()
+            assert e == pytest.approx(lo["energy"], rel=1e-12)
+            changed += int(th != np.float32(w.frameEnergyTH[w.n - 1]))   # (the oracle keeps the new threshold itself)
+    assert changed > 0
+    batch.close()
+    for e in efs:
+        e.close()
+    for f in frames:
+        f.close()
+
+
 def test_calc_l_energy_after_step_host_with_new_window(ctx, capi, O, synth):
     """calcLEnergy's frame-prior term must follow the window tables passed through hslam_ba_batch_step_host."""
     import copy

@@ -78,7 +78,7 @@ def test_two_million_residual_window_properties(ctx, capi, synth):
     assert np.isfinite(full).all() and np.linalg.norm(full) > 0
     assert np.array_equal(full, _systems(capi, ctx, win, frames))                      # deterministic
     other = _systems(capi, ctx, win, frames, parallelism=97)                           # different chunking: fp32 regrouping only
-    assert 0 < rel_fro(other, full) < 1e-6
+    assert rel_fro(other, full) < 1e-6   # (0 when the chunking does not depend on the block count)
     for world in (2, 8):                                                               # shard linearity
         acc = np.zeros_like(full)
         for r in range(world):

@@ -2,7 +2,7 @@
 # usage: tools/sweep_env.sh VAR v1 v2 ... : bench once per value of an environment tuning variable
 cd "$(dirname "$0")/.."
 var=$1; shift
-for v in "$@"; do env $var=$v $EXTRA_ENV python bench.py --steps 10 --warmup 3 --no-cpu-baseline --no-extras 2>/dev/null | python -c "
+for v in "$@"; do env $var=$v $EXTRA_ENV python bench.py --steps 10 --warmup 3 --no-cpu-baseline --no-extras --no-sharded 2>/dev/null | python -c "
 import sys, json
 for l in sys.stdin:
     if l.startswith('{'):
