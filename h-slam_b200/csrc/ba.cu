@@ -405,8 +405,10 @@ static int build_chunks(hslam_ba* ba) {
     if (sc_blocks > 4 * n) sc_blocks -= n;
     // batched windows: measured (64 x config-2 windows) the Schur launch keeps gaining down to ~6 chunk waves for
     // the whole batch (finer chunks balance the 3-blocks-per-SM kernel; below that the fold cost grows)
-    // An explicit target (set_parallelism) asks for 9/2 x as many Schur chunks as top blocks.
-    if (ba->target_blocks > 0) sc_blocks = std::min(9 * ba->target_blocks / 2, std::max(n, total_sub / 2));
+    // An explicit target (set_parallelism, i.e. a member of a batch) asks for 3 x as many Schur chunks as top blocks:
+    // ~6 waves of the 2-blocks-per-SM 8x8-tile kernel for the whole batch (measured at 64 config-2 windows: 14 chunks
+    // per window 218 us, 28: 211, 35: 212, 42: 215, 56: 223 — and the fold grows with the chunk count: 30 .. 45 us).
+    if (ba->target_blocks > 0) sc_blocks = std::min(3 * ba->target_blocks, std::max(n, total_sub / 2));
     if (const char* e = getenv("HSLAM_SC_BLOCKS")) sc_blocks = atoi(e);   // tuning override (per window)
     if (sc_blocks < 1) sc_blocks = 1;
     const int q = std::max(1, (total_sub + sc_blocks - 1) / sc_blocks);   // sub-tiles per chunk
@@ -869,25 +871,34 @@ static int launch_top(hslam_ba* ba, int modes, bool fold = true) {
   return 0;
 }
 
-// tiles per thread of the Schur kernel: (NT-2)(NT-1)/2 4x4 tiles over 128 thread pairs
+// Schur kernel variant of a window: 1 = 8x8 tiles, 8 point slices (n <= 7); 2 = 8x8 tiles, 4 slices (n <= 10);
+// 5 = the 4x4-tile kernel with up to five tiles per thread (n <= 16).  HSLAM_SCHUR_4X4=1 (A/B measurements) selects the
+// 4x4-tile kernel for every n: 11 / 12 / 15 = one / two / five tiles per thread.
 static int schur_maxt(int LD) {
+  static const bool old4 = getenv("HSLAM_SCHUR_4X4") != nullptr;
+  const int n = LD / 8 - 1;
+  if (!old4 && n <= 10) return n <= 7 ? 1 : 2;
   int NTR = LD / 4 - 2, t = NTR * (NTR + 1) / 2;
-  return t <= 128 ? 1 : (t <= 256 ? 2 : 5);
+  return old4 ? (t <= 128 ? 11 : (t <= 256 ? 12 : 15)) : 5;
 }
-// rows + staged records; the final exchange of the two point halves needs MAXT * 128 * 16 floats
+// 4x4 kernel: rows + staged records; the final exchange of the two point halves needs MAXT * 128 * 16 floats
 static size_t schur_smem(int LD, int maxres) {
-  size_t fl = std::max(sc_smem_floats(LD, maxres), (size_t)schur_maxt(LD) * 128 * 16 + 4);
+  const int k = schur_maxt(LD);
+  if (k <= 2) return sc8_smem_floats(LD, maxres) * sizeof(float);
+  size_t fl = std::max(sc_smem_floats(LD, maxres), (size_t)(k % 10) * 128 * 16 + 4);
   return fl * sizeof(float);
 }
 template <class F> static int schur_dispatch(int maxt, F f) {
-  if (maxt == 1) return f(ba_schur_kernel<1>);
-  if (maxt == 2) return f(ba_schur_kernel<2>);
+  if (maxt == 1) return f(ba_schur8_kernel<8>);
+  if (maxt == 2) return f(ba_schur8_kernel<4>);
+  if (maxt == 11) return f(ba_schur_kernel<1>);
+  if (maxt == 12) return f(ba_schur_kernel<2>);
   return f(ba_schur_kernel<5>);
 }
 static int schur_attr(hslam_ctx* ctx, size_t smem) {
   size_t& configured = ctx->schur_smem_configured;
   if (smem > configured) {
-    for (int maxt : {1, 2, 5})
+    for (int maxt : {1, 2, 5, 11, 12})
       TRY(schur_dispatch(maxt, [&](auto k) -> int {
         HS_CUDA(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         return 0;

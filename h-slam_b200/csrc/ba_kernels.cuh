@@ -1388,6 +1388,229 @@ ba_schur_kernel(const BADesc* __restrict__ descs, const int* __restrict__ prefix
   }
 }
 
+// ------------------------------------------------------------------------------------------------
+// Schur fold, 8x8 register tiles (n <= 10).  Same data path and the same phase 1 as ba_schur_kernel; the Gram phase is
+// re-blocked so that it no longer lives on shared-memory bandwidth (the 4x4 version: L1 wavefronts 86 %, two LDS.128 per
+// 8 FFMA2):
+//   * a thread owns ONE 8x8 tile of the upper block triangle (8-blocks = the frames + the tail block [Hcd | bdSum | pad],
+//     without the host's own block) and 1/SLICES of the sub-tile's points: 4 LDS.128 per 32 FFMA2;
+//   * the lanes of a warp are different tiles of the SAME point, and a row of A is stored with the low halves of all
+//     8-blocks first and the high halves behind them (sc8_col), so one operand load of a warp touches one contiguous
+//     <= 128-byte piece of one row: a single wavefront with broadcast;
+//   * the SLICES partial tiles of a thread group are summed through shared memory in a fixed binary tree at the end of
+//     the chunk (the staging buffers are free then).
+//   * the staged records are double-buffered: the bulk copies of sub-tile i+1 are issued BEFORE phase 1 of sub-tile i
+//     (single-buffered, a block's time per sub-tile was phase 1 + the copy latency: 91 us of the launch).
+// SLICES = 8: <= 32 tiles (n <= 7); SLICES = 4: <= 64 tiles (n <= 10).  Shared memory (floats): 2 mbarriers (4) |
+// A[SC_PTS][LD+4] | {jp, pt} x 2 stages, at least 4 + 8192 for the final reduction.
+__host__ __device__ inline int sc8_col(int c, int LD) { return ((c & 4) ? (LD >> 1) : 0) + ((c >> 3) << 2) + (c & 3); }
+__host__ __device__ inline size_t sc8_smem_floats(int LD, int maxres) {
+  const size_t a = (size_t)SC_PTS * (LD + 4) + 4 * (size_t)SC_PTS * sc_pstr(maxres);   // A + two stages of {jp, pt}
+  return 4 + (a > 8192 ? a : 8192);
+}
+template <int SLICES>
+__global__ void __launch_bounds__(SC_THREADS, 2)
+ba_schur8_kernel(const BADesc* __restrict__ descs, const int* __restrict__ prefix, int nwin) {
+  static_assert(SC_PTS * 4 == SC_THREADS, "phase 1 gives four lanes to every point of a sub-tile");
+  constexpr int TL = SC_THREADS / SLICES;   // tile lanes per slice
+  extern __shared__ __align__(16) float smem[];
+  int lb;
+  const int win = find_window(prefix, nwin, blockIdx.x, lb);
+  const BADesc& D = descs[win];
+  const BARes& r = D.r;
+  const BAPts& pts = D.p;
+  const int LD = D.LD, LDP = LD + 4, HALF = LD >> 1;
+  const int maxres = D.maxres, PSTR = r.pstr;
+  uint64_t* full = reinterpret_cast<uint64_t*>(smem);
+  float* A = smem + 4;                           // [SC_PTS][LDP]  sqrt(HdiF_p) * a_p, columns permuted by sc8_col
+  float* stage0 = A + SC_PTS * LDP;              // two stages of { jp[SC_PTS][PSTR] JpJdF records | pt[SC_PTS][PSTR] point-term records }
+  const int STG = 2 * SC_PTS * PSTR;
+  const PtChunk ch = D.ptchunks[lb];
+  const int n = D.W.n;
+  const int NB = LD >> 3, NBR = NB - 1, ntiles = NBR * (NBR + 1) / 2;
+  const int slice = threadIdx.x / TL, tile = threadIdx.x % TL;
+  int bi = -1, bj = -1;
+  if (tile < ntiles) {
+    tri_decode(tile, NBR, bi, bj);
+    if (bi >= ch.host) bi++;   // skip the host's own block row / column
+    if (bj >= ch.host) bj++;
+  }
+  __align__(8) float acc[8][8];
+#pragma unroll
+  for (int i = 0; i < 8; ++i)
+#pragma unroll
+    for (int j = 0; j < 8; ++j) acc[i][j] = 0.f;
+  if (threadIdx.x == 0) {
+    mbar_init(&full[0], 1); mbar_init(&full[1], 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+  }
+  __syncthreads();
+  auto fetch = [&](int base, int stg) {   // thread 0: the records of sub-tile [base, base + SC_PTS) of the chunk
+    const int cnt = min(SC_PTS, ch.count - base);
+    if (cnt <= 0) return;
+    const unsigned bytes = (unsigned)cnt * PSTR * 4;
+    float* jpd = stage0 + stg * STG;
+    mbar_expect_tx(&full[stg], 2 * bytes);
+    bulk_g2s(jpd, r.JpJdF + (size_t)(ch.start + base) * PSTR, bytes, &full[stg]);
+    bulk_g2s(jpd + SC_PTS * PSTR, r.prec + (size_t)(ch.start + base) * PSTR, bytes, &full[stg]);
+  };
+  if (threadIdx.x == 0) fetch(0, 0);
+  const int lp = threadIdx.x >> 2, q = threadIdx.x & 3;   // phase 1: point of the sub-tile, lane within the point
+  float pr_n = 0.f, de_n = 0.f;
+  if (q < 2 && lp < ch.count) { pr_n = pts.priorF[ch.start + lp]; if (q == 0) de_n = pts.deltaF[ch.start + lp]; }
+  for (int base = 0, it = 0; base < ch.count; base += SC_PTS, ++it) {
+    const int cnt = min(SC_PTS, ch.count - base);
+    const int stg = it & 1;
+    // the other stage was consumed by phase 1 of the previous sub-tile (two block barriers ago): refill it now, the
+    // copy runs under this sub-tile's phase 1 and Gram phase
+    if (threadIdx.x == 0) fetch(base + SC_PTS, stg ^ 1);
+    const float* jp = stage0 + stg * STG;
+    const float* pt = jp + SC_PTS * PSTR;
+    const float prc = pr_n, dec = de_n;
+    {
+      const int nb = base + SC_PTS + lp;
+      pr_n = de_n = 0.f;
+      if (q < 2 && nb < ch.count) { pr_n = pts.priorF[ch.start + nb]; if (q == 0) de_n = pts.deltaF[ch.start + nb]; }
+    }
+    mbar_wait(&full[stg], (unsigned)(it >> 1) & 1u);
+    // ---- phase 1 (as in ba_schur_kernel; only the column positions in the row differ)
+    {
+      float* row = A + lp * LDP;
+      for (int i = q; i < LDP / 4; i += 4) reinterpret_cast<float4*>(row)[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+      const int p = ch.start + base + lp;
+#ifdef SC8_EXP_NOP1
+      const bool live = lp < cnt && (!D.marg || D.marg[p] != 0) && cnt == 12345;
+#else
+      const bool live = lp < cnt && (!D.marg || D.marg[p] != 0);
+#endif
+      float hdi = 0.f, mine0 = 0.f, mine1 = 0.f;
+      if (live) {
+        const float* pl = pt + lp * PSTR;
+        float s0[2] = {0.f, 0.f}, s1[2] = {0.f, 0.f};
+        int ngood = 0;
+        // the first six slots fully unrolled (all 18 loads in flight at once); a slot index beyond the point's list reads
+        // the always-zero pad record (flag 0: adds +0, exact)
+        const int q1 = q < 2 ? q + 4 : q;
+#pragma unroll
+        for (int slot = 0; slot < 6; ++slot) {
+          const int sl = 8 * min(slot, maxres);
+          const float f = pl[sl + 6], v0 = pl[sl + q], v1 = pl[sl + q1];
+          ngood += (f != 0.f) ? 1 : 0;
+          s0[0] = xadd(s0[0], f == 1.f ? v0 : 0.f); s0[1] = xadd(s0[1], f == 2.f ? v0 : 0.f);
+          s1[0] = xadd(s1[0], f == 1.f ? v1 : 0.f); s1[1] = xadd(s1[1], f == 2.f ? v1 : 0.f);
+        }
+        for (int slot = 6; slot < maxres; ++slot) {
+          const float f = pl[8 * slot + 6], v0 = pl[8 * slot + q], v1 = pl[8 * slot + q1];
+          ngood += (f != 0.f) ? 1 : 0;
+          s0[0] = xadd(s0[0], f == 1.f ? v0 : 0.f); s0[1] = xadd(s0[1], f == 2.f ? v0 : 0.f);
+          s1[0] = xadd(s1[0], f == 1.f ? v1 : 0.f); s1[1] = xadd(s1[1], f == 2.f ? v1 : 0.f);
+        }
+        if (q == 0) {
+          pts.bd[0][p] = s0[0]; pts.bd[1][p] = s0[1];
+          if (ngood > 0) {
+            mine0 = xadd(s0[0], s0[1]);
+            if (D.shift_prior) mine0 = xadd(mine0, xmul(prc, dec));
+          }
+          pts.bdSumF[p] = mine0;
+        } else if (q == 1) {
+          pts.Hdd[0][p] = s0[0]; pts.Hdd[1][p] = s0[1];
+          float idh = 0.f;
+          if (ngood > 0) {
+            float H = xadd(xadd(s0[0], s0[1]), prc);
+            if (H < 1e-10f) H = 1e-10f;
+            idh = H;
+            hdi = xdiv(1.0f, H);
+          }
+          pts.HdiF[p] = hdi; pts.idepth_hessian[p] = idh;
+        } else {
+          reinterpret_cast<float*>(pts.Hcd[0])[4 * (size_t)p + (q - 2)] = s0[0];
+          reinterpret_cast<float*>(pts.Hcd[1])[4 * (size_t)p + (q - 2)] = s0[1];
+          mine0 = xadd(s0[0], s0[1]);
+        }
+        if (q < 2) {
+          reinterpret_cast<float*>(pts.Hcd[0])[4 * (size_t)p + (q + 2)] = s1[0];
+          reinterpret_cast<float*>(pts.Hcd[1])[4 * (size_t)p + (q + 2)] = s1[1];
+          mine1 = xadd(s1[0], s1[1]);
+        }
+      }
+      const float sw = sqrtf(__shfl_sync(0xffffffffu, hdi, (threadIdx.x & 28) + 1));
+      __syncwarp();   // the row is zeroed
+      if (live) {
+        // a_p tail (logical columns 8n .. 8n+4): Hcd[0..3] = low half of block n, bdSum = first entry of its high half
+        float* lo = row + 4 * n;
+        float* hi = row + HALF + 4 * n;
+        if (q == 0) { hi[0] = sw * mine0; lo[2] = sw * mine1; }
+        else if (q == 1) { lo[3] = sw * mine1; }
+        else { lo[q - 2] = sw * mine0; }
+        const float* pl = pt + lp * PSTR;
+        const float* jl = jp + lp * PSTR;
+        for (int slot = q; slot < maxres; slot += 4) {
+          if (pl[8 * slot + 6] == 0.f) continue;
+          const int t = (int)pl[8 * slot + 7];
+          const float4 j0 = *reinterpret_cast<const float4*>(jl + 8 * slot), j1 = *reinterpret_cast<const float4*>(jl + 8 * slot + 4);
+          *reinterpret_cast<float4*>(row + 4 * t) = make_float4(sw * j0.x, sw * j0.y, sw * j0.z, sw * j0.w);
+          *reinterpret_cast<float4*>(row + HALF + 4 * t) = make_float4(sw * j1.x, sw * j1.y, sw * j1.z, sw * j1.w);
+        }
+      }
+    }
+    __syncthreads();   // rows complete
+    // ---- phase 2: this thread's 8x8 tile over its slice of the points, in point order
+#ifdef SC8_EXP_NOGRAM
+    if (bi >= 0 && cnt == 12345) {
+#else
+    if (bi >= 0) {
+#endif
+      const float* ap = A + 4 * bi;
+      const float* bp = A + 4 * bj;
+#pragma unroll 2
+      for (int l2 = slice; l2 < cnt; l2 += SLICES) {
+        const float4 a0 = *reinterpret_cast<const float4*>(ap + l2 * LDP), a1 = *reinterpret_cast<const float4*>(ap + l2 * LDP + HALF);
+        const float4 b0 = *reinterpret_cast<const float4*>(bp + l2 * LDP), b1 = *reinterpret_cast<const float4*>(bp + l2 * LDP + HALF);
+        const float a8[8] = {a0.x, a0.y, a0.z, a0.w, a1.x, a1.y, a1.z, a1.w};
+        const float2 bb[4] = {make_float2(b0.x, b0.y), make_float2(b0.z, b0.w), make_float2(b1.x, b1.y), make_float2(b1.z, b1.w)};
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          const float2 aa = make_float2(a8[i], a8[i]);
+          float2* row2 = reinterpret_cast<float2*>(acc[i]);
+#pragma unroll
+          for (int j = 0; j < 4; ++j) row2[j] = __ffma2_rn(aa, bb[j], row2[j]);   // packed fp32 FMA, each lane rounded like fmaf
+        }
+      }
+    }
+    __syncthreads();   // A is free again
+  }
+  // ---- sum of the SLICES partial tiles: binary tree through shared memory (everything staged is consumed by now)
+  float* scr = smem + 4;
+#pragma unroll
+  for (int half = SLICES / 2; half >= 1; half >>= 1) {
+    if (slice >= half && slice < 2 * half) {
+      float* dst = scr + (size_t)(slice - half) * 64 * TL + tile;
+#pragma unroll
+      for (int i = 0; i < 8; ++i)
+#pragma unroll
+        for (int j = 0; j < 8; ++j) dst[(i * 8 + j) * TL] = acc[i][j];
+    }
+    __syncthreads();
+    if (slice < half) {
+      const float* src = scr + (size_t)slice * 64 * TL + tile;
+#pragma unroll
+      for (int i = 0; i < 8; ++i)
+#pragma unroll
+        for (int j = 0; j < 8; ++j) acc[i][j] += src[(i * 8 + j) * TL];
+    }
+    __syncthreads();
+  }
+  if (slice == 0 && bi >= 0) {
+    float* out = D.scpartial + (size_t)lb * LD * LD + (size_t)(8 * bi) * LD + 8 * bj;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      *reinterpret_cast<float4*>(out + (size_t)i * LD) = make_float4(acc[i][0], acc[i][1], acc[i][2], acc[i][3]);
+      *reinterpret_cast<float4*>(out + (size_t)i * LD + 4) = make_float4(acc[i][4], acc[i][5], acc[i][6], acc[i][7]);
+    }
+  }
+}
+
 // Fold of the Schur chunk partials into fp64 G[host], chunks in index order.  A separate, wide launch:
 // folding inside the Schur kernel by "the last block of a host" put ~0.5 MB of dependent reads per host
 // on ONE block at the very end of the kernel (measured: 165 us of a 190 us launch for 8 windows).
