@@ -918,7 +918,7 @@ static int launch_schur(hslam_ba* ba, int top_modes = 0) {
   TRY(schur_attr(ctx, smem));
   if (ba->n_ptchunks > 0)
     HS_LAUNCH(ctx, HSLAM_K_BA_SCHUR, schur_launch(schur_maxt(ba->LD), ba->n_ptchunks, smem, ctx->stream, ba->d_desc.p, nullptr, 1));
-  HS_LAUNCH(ctx, HSLAM_K_BA_FOLD_SC, (ba_fold_sc_kernel<<<ba->n * ((ba->LD * ba->LD + 255) / 256) + (top_modes ? fold_top_blocks(ba->n, top_modes) : 0), 256, 0, ctx->stream>>>(ba->d_desc.p, nullptr, 1, top_modes, 1)));
+  HS_LAUNCH(ctx, HSLAM_K_BA_FOLD_SC, (ba_fold_sc_kernel<<<ba->n * fold_sc_blocks(ba->LD) + (top_modes ? fold_top_blocks(ba->n, top_modes) : 0), 256, 0, ctx->stream>>>(ba->d_desc.p, nullptr, 1, top_modes, 1)));
   HS_CUDA(cudaGetLastError());
   return 0;
 }
@@ -1436,7 +1436,7 @@ static int batch_refresh(hslam_ba_batch* B) {
     pf[1][i + 1] = pf[1][i] + top;
     pf[2][i + 1] = pf[2][i] + ba->n_ptchunks;
     pf[3][i + 1] = pf[3][i] + 3 * (ba->n + 1) * (ba->n + 1);
-    pf[4][i + 1] = pf[4][i] + ba->n * ((ba->LD * ba->LD + 255) / 256) + fold_top_blocks(ba->n, 3);   // Schur fold + top folds (A, L)
+    pf[4][i + 1] = pf[4][i] + ba->n * fold_sc_blocks(ba->LD) + fold_top_blocks(ba->n, 3);   // Schur fold + top folds (A, L)
     pf[5][i + 1] = pf[5][i] + (ba->P + 127) / 128;
     B->smem = std::max(B->smem, schur_smem(ba->LD, ba->maxres));
     B->maxt = std::max(B->maxt, schur_maxt(ba->LD));
@@ -1552,11 +1552,29 @@ static int batch_enqueue_accumulate(hslam_ba_batch* B, bool with_th = false) {
   const int* pf = B->d_prefix.p;
   TRY(schur_attr(ctx, B->smem));
   TRY(top_attr(ctx));
+  // modes A and L touch disjoint residuals, accumulators and records: outside the per-kernel event profiling they run
+  // side by side (L on the side stream), so the two ~2-wave launches share ONE wave tail
+  static const bool serial_top = getenv("HSLAM_TOP_SERIAL") != nullptr;
+  const bool has_L = B->any_L && B->blocks[6] > 0;
+  const bool par = has_L && B->blocks[1] > 0 && !ctx->profile && !serial_top;
+  if (par) {
+    HS_CUDA(cudaEventRecord(B->ev_th[0], ctx->stream));
+    HS_CUDA(cudaStreamWaitEvent(ctx->side, B->ev_th[0], 0));
+  }
   if (B->blocks[1] > 0) {
     HS_LAUNCH(ctx, HSLAM_K_BA_TOP, (ba_top_kernel<0><<<B->blocks[1], 2 * TOP_THREADS, kTopSmem, ctx->stream>>>(B->d_descs.p, pf + (n + 1), B->uniform[1] ? -B->uniform[1] : n)));
   }
-  if (B->any_L && B->blocks[6] > 0)
-    HS_LAUNCH(ctx, HSLAM_K_BA_TOP, (ba_top_kernel<1><<<B->blocks[6], 2 * TOP_THREADS, kTopSmem, ctx->stream>>>(B->d_descs.p, pf + 6 * (n + 1), B->uniform[6] ? -B->uniform[6] : n)));
+  if (has_L) {
+    cudaStream_t ls = par ? ctx->side : ctx->stream;
+    if (par) {
+      ctx->launches++;
+      ba_top_kernel<1><<<B->blocks[6], 2 * TOP_THREADS, kTopSmem, ls>>>(B->d_descs.p, pf + 6 * (n + 1), B->uniform[6] ? -B->uniform[6] : n);
+      HS_CUDA(cudaEventRecord(B->ev_th[1], ctx->side));
+      HS_CUDA(cudaStreamWaitEvent(ctx->stream, B->ev_th[1], 0));
+    } else {
+      HS_LAUNCH(ctx, HSLAM_K_BA_TOP, (ba_top_kernel<1><<<B->blocks[6], 2 * TOP_THREADS, kTopSmem, ls>>>(B->d_descs.p, pf + 6 * (n + 1), B->uniform[6] ? -B->uniform[6] : n)));
+    }
+  }
   if (B->blocks[2] > 0)
     HS_LAUNCH(ctx, HSLAM_K_BA_SCHUR, schur_launch(B->maxt, B->blocks[2], B->smem, ctx->stream, B->d_descs.p, pf + 2 * (n + 1), B->uniform[2] ? -B->uniform[2] : n));
   HS_LAUNCH(ctx, HSLAM_K_BA_FOLD_SC, (ba_fold_sc_kernel<<<B->blocks[4], 256, 0, ctx->stream>>>(B->d_descs.p, pf + 4 * (n + 1), B->uniform[4] ? -B->uniform[4] : n, 3, 1)));

@@ -1614,9 +1614,10 @@ ba_schur8_kernel(const BADesc* __restrict__ descs, const int* __restrict__ prefi
 // Fold of the Schur chunk partials into fp64 G[host], chunks in index order.  A separate, wide launch:
 // folding inside the Schur kernel by "the last block of a host" put ~0.5 MB of dependent reads per host
 // on ONE block at the very end of the kernel (measured: 165 us of a 190 us launch for 8 windows).
-// grid: per window n * ceil(LD*LD / 256) blocks.
+// grid: per window n * fold_sc_blocks(LD) blocks (+ the top folds).
 // Blocks behind the Schur part fold the top accumulators (fold_top_slot): two (mode, pair) slots per block, the modes
 // of bit mask `top_modes` (1 = A, 2 = L, 4 = marginalisation) in bit order.  with_sc = 0: top folds only.
+__host__ __device__ inline int fold_sc_blocks(int LD) { return (LD * LD / 4 + 255) / 256; }   // per host: one thread per four elements
 __host__ __device__ inline int fold_top_blocks(int n, int top_modes) {
   const int nm = (top_modes & 1) + ((top_modes >> 1) & 1) + ((top_modes >> 2) & 1);
   return (nm * n * n + 1) / 2;
@@ -1626,7 +1627,7 @@ __global__ void __launch_bounds__(256) ba_fold_sc_kernel(const BADesc* __restric
   int lb;
   const int win = find_window(prefix, nwin, blockIdx.x, lb);
   const BADesc& D = descs[win];
-  const int LD = D.LD, per = (LD * LD + 255) / 256;
+  const int LD = D.LD, per = fold_sc_blocks(LD);
   const int nsc = with_sc ? D.W.n * per : 0;
   if (lb >= nsc) {
     const int nn = D.W.n * D.W.n;
@@ -1639,28 +1640,38 @@ __global__ void __launch_bounds__(256) ba_fold_sc_kernel(const BADesc* __restric
     }
     return;
   }
+  // four neighbouring elements of a row per thread (LD is a multiple of 8: a float4 never leaves its row or its 4x4 tile)
   const int host = lb / per;
-  const int i = (lb % per) * 256 + threadIdx.x;
+  const int i = 4 * ((lb % per) * 256 + threadIdx.x);
   if (i >= LD * LD) return;
   const int row = i / LD, col = i % LD;
   if ((col >> 2) < (row >> 2)) return;   // lower tiles are not produced
   const int cb = D.host_chunk_begin[host], ce = D.host_chunk_begin[host + 1];
   const float* src = D.scpartial + (size_t)cb * LD * LD + i;
   const size_t stride = (size_t)LD * LD;
-  double sum = 0.0;
+  double s0 = 0.0, s1 = 0.0, s2 = 0.0, s3 = 0.0;
   int c = cb;
-  for (; c + 8 <= ce; c += 8) {   // 8 independent loads in flight, summed in chunk order
-    float v[8];
+  for (; c + 4 <= ce; c += 4) {   // four independent 16-byte loads in flight, summed in chunk order
+    float4 v[4];
 #pragma unroll
-    for (int j = 0; j < 8; ++j) v[j] = __ldcg(src + (size_t)j * stride);
+    for (int j = 0; j < 4; ++j) v[j] = __ldcg(reinterpret_cast<const float4*>(src + (size_t)j * stride));
 #pragma unroll
-    for (int j = 0; j < 8; ++j) sum += (double)v[j];
-    src += 8 * stride;
+    for (int j = 0; j < 4; ++j) { s0 += (double)v[j].x; s1 += (double)v[j].y; s2 += (double)v[j].z; s3 += (double)v[j].w; }
+    src += 4 * stride;
   }
-  for (; c < ce; ++c) { sum += (double)__ldcg(src); src += stride; }
-  // G_h is symmetric; the Schur kernel produces its upper 4x4 tiles only: store the mirror too, the stitch reads a dense matrix
-  D.G[(size_t)host * LD * LD + i] = sum;
-  if ((col >> 2) > (row >> 2)) D.G[(size_t)host * LD * LD + (size_t)col * LD + row] = sum;
+  for (; c < ce; ++c) {
+    const float4 v = __ldcg(reinterpret_cast<const float4*>(src));
+    s0 += (double)v.x; s1 += (double)v.y; s2 += (double)v.z; s3 += (double)v.w;
+    src += stride;
+  }
+  // G_h is symmetric; the Schur kernel produces its upper tiles only: store the mirror too, the stitch reads a dense matrix
+  double* G = D.G + (size_t)host * LD * LD;
+  reinterpret_cast<double2*>(G + i)[0] = make_double2(s0, s1);
+  reinterpret_cast<double2*>(G + i)[1] = make_double2(s2, s3);
+  if ((col >> 2) > (row >> 2)) {
+    G[(size_t)col * LD + row] = s0; G[(size_t)(col + 1) * LD + row] = s1;
+    G[(size_t)(col + 2) * LD + row] = s2; G[(size_t)(col + 3) * LD + row] = s3;
+  }
 }
 
 // ------------------------------------------------------------------------------------------------
