@@ -1546,7 +1546,7 @@ static int batch_fork_th(hslam_ba_batch* B) {
 }
 static int batch_join_th(hslam_ba_batch* B) { HS_CUDA(cudaStreamWaitEvent(B->ctx->stream, B->ev_th[1], 0)); return 0; }
 
-static int batch_enqueue_accumulate(hslam_ba_batch* B, bool with_th = false) {
+static int batch_enqueue_top(hslam_ba_batch* B) {
   hslam_ctx* ctx = B->ctx;
   const int n = (int)B->items.size();
   const int* pf = B->d_prefix.p;
@@ -1575,6 +1575,14 @@ static int batch_enqueue_accumulate(hslam_ba_batch* B, bool with_th = false) {
       HS_LAUNCH(ctx, HSLAM_K_BA_TOP, (ba_top_kernel<1><<<B->blocks[6], 2 * TOP_THREADS, kTopSmem, ls>>>(B->d_descs.p, pf + 6 * (n + 1), B->uniform[6] ? -B->uniform[6] : n)));
     }
   }
+  HS_CUDA(cudaGetLastError());
+  return 0;
+}
+static int batch_enqueue_accumulate(hslam_ba_batch* B, bool with_th = false) {
+  hslam_ctx* ctx = B->ctx;
+  const int n = (int)B->items.size();
+  const int* pf = B->d_prefix.p;
+  TRY(batch_enqueue_top(B));
   if (B->blocks[2] > 0)
     HS_LAUNCH(ctx, HSLAM_K_BA_SCHUR, schur_launch(B->maxt, B->blocks[2], B->smem, ctx->stream, B->d_descs.p, pf + 2 * (n + 1), B->uniform[2] ? -B->uniform[2] : n));
   HS_LAUNCH(ctx, HSLAM_K_BA_FOLD_SC, (ba_fold_sc_kernel<<<B->blocks[4], 256, 0, ctx->stream>>>(B->d_descs.p, pf + 4 * (n + 1), B->uniform[4] ? -B->uniform[4] : n, 3, 1)));
@@ -1924,9 +1932,57 @@ int hslam_ba_batch_step_host(hslam_ba_batch* B, const hslam_ba_step_io* io) {
     bulk_res |= bulk_st || bulk_en;
   }
   if (any_res || any_th) HS_CUDA(cudaEventRecord(ctx->ev_join, ctx->side));
+  // ---- accumulate.  SPLIT form (a batch of same-shape windows whose system outputs are the bound slots of the batch's
+  // result block): the A and L systems, the energy and the counts are final once the top accumulators are folded — they
+  // are stitched, exported and copied to the host on a second stream WHILE the Schur fold runs; only the Schur-complement
+  // system (a third of the bytes) is copied behind the last kernel.
+  bool split = any_sys && n >= 8 && !ctx->profile && B->uniform[2] && B->uniform[3] && B->uniform[4] && getenv("HSLAM_NO_SPLIT") == nullptr;
+  for (int i = 0; i < n && split; ++i) {
+    const hslam_ba* ba = B->items[i];
+    split = !io[i].newEnergy && !io[i].newEnergyWithOutlier && ba->n == B->items[0]->n && ba->LD == B->items[0]->LD && io[i].Hb == (double*)(B->h_dn + B->io[i].dn_Hb) &&
+            (!io[i].energy || io[i].energy == (double*)(B->h_dn + B->io[i].dn_energy)) &&
+            (!io[i].nres2 || (void*)io[i].nres2 == (void*)(B->h_dn + B->io[i].dn_nres)) &&
+            (!io[i].frameEnergyTH_out || (void*)io[i].frameEnergyTH_out == (void*)(B->h_dn + B->io[i].dn_th)) &&
+            (i == 0 || B->io[i].dn_energy - B->io[i - 1].dn_energy == B->io[1].dn_energy - B->io[0].dn_energy);
+  }
+  if (split) {
+    const int nf = B->items[0]->n, LD = B->items[0]->LD;
+    const size_t N = B->items[0]->N, per = (N * N + N) * 8, pitch = (size_t)(B->io[1].dn_energy - B->io[0].dn_energy);
+    const int* pf = B->d_prefix.p;
+    TRY(batch_enqueue_top(B));
+    const int ftb = fold_top_blocks(nf, 3), fsb = nf * fold_sc_blocks(LD);
+    HS_LAUNCH(ctx, HSLAM_K_BA_FOLD_SC, (ba_fold_sc_kernel<<<n * ftb, 256, 0, ctx->stream>>>(B->d_descs.p, nullptr, -ftb, 3, 0)));
+    // (the high-priority side stream: its blocks go ahead of the Schur kernel's, and the threshold kernels, whose floats
+    // ride in this copy, precede in stream order.  Measured alternatives: the same on the normal-priority upload stream
+    // 1.57 ms per step_host instead of 1.48 — the stitch then trickles in behind the Schur blocks; with the per-residual
+    // energy arrays requested (43 MB on the side stream) the split form loses 0.3 ms, so it is not used then.)
+    cudaStream_t bs = ctx->side;
+    HS_CUDA(cudaEventRecord(B->ev_th[0], ctx->stream));
+    HS_CUDA(cudaStreamWaitEvent(bs, B->ev_th[0], 0));
+    ctx->launches += 2;   // counted, not event-timed
+    ba_stitch_kernel<<<B->blocks[3], ST_THREADS, 0, bs>>>(B->d_descs.p, pf + 3 * (n + 1), -B->uniform[3], 0, 2, 1);
+    ba_batch_export_kernel<<<dim3(2, (unsigned)n), 256, 0, bs>>>(B->d_descs.p, d_io, B->d_dn.p, 4);
+    HS_CUDA(cudaGetLastError());
+    {   // per window [energy | counts | threshold | H_A b_A H_L b_L]: one strided copy
+      const size_t lo = (size_t)B->io[0].dn_energy, width = (size_t)(B->io[0].dn_Hb - B->io[0].dn_energy) + 2 * per;
+      HS_CUDA(cudaMemcpy2DAsync(B->h_dn + lo, pitch, B->d_dn.p + lo, pitch, width, n, cudaMemcpyDeviceToHost, bs));
+    }
+    HS_CUDA(cudaEventRecord(B->ev_th[1], bs));
+    HS_LAUNCH(ctx, HSLAM_K_BA_SCHUR, schur_launch(B->maxt, B->blocks[2], B->smem, ctx->stream, B->d_descs.p, pf + 2 * (n + 1), -B->uniform[2]));
+    HS_LAUNCH(ctx, HSLAM_K_BA_FOLD_SC, (ba_fold_sc_kernel<<<n * fsb, 256, 0, ctx->stream>>>(B->d_descs.p, nullptr, -fsb, 0, 1)));
+    HS_LAUNCH(ctx, HSLAM_K_BA_STITCH, (ba_stitch_kernel<<<B->blocks[3], ST_THREADS, 0, ctx->stream>>>(B->d_descs.p, pf + 3 * (n + 1), -B->uniform[3], 2, 3, 0)));
+    HS_LAUNCH(ctx, HSLAM_K_BA_EXPORT, (ba_batch_export_kernel<<<dim3(2, (unsigned)n), 256, 0, ctx->stream>>>(B->d_descs.p, d_io, B->d_dn.p, 8)));
+    HS_CUDA(cudaGetLastError());
+    {
+      const size_t lo = (size_t)B->io[0].dn_Hb + 2 * per;
+      HS_CUDA(cudaMemcpy2DAsync(B->h_dn + lo, pitch, B->d_dn.p + lo, pitch, per, n, cudaMemcpyDeviceToHost, ctx->stream));
+    }
+    HS_CUDA(cudaStreamWaitEvent(ctx->stream, B->ev_th[1], 0));
+  } else {
   TRY(batch_graph_launch(B, false));
   if (any_th) HS_CUDA(cudaStreamWaitEvent(ctx->stream, ctx->ev_join, 0));   // the thresholds ride in the systems region
-  if (any_sys) {
+  }
+  if (any_sys && !split) {
     HS_LAUNCH(ctx, HSLAM_K_BA_EXPORT, (ba_batch_export_kernel<<<dim3(2, (unsigned)n), 256, 0, ctx->stream>>>(B->d_descs.p, d_io, B->d_dn.p, 2)));
     HS_CUDA(cudaGetLastError());
     for (int i = 0; i < n; ++i) {

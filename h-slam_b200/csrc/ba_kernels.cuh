@@ -2082,12 +2082,16 @@ __global__ void __launch_bounds__(256) ba_batch_export_kernel(const BADesc* __re
       if (oW) oW[q] = D.r.newEnergyWO[k];
       if (oS) oS[q] = D.r.newState[k];
     }
-  if (!(what & 2)) return;
+  // what & 2: the three systems + energy + counts; & 4: the A and L systems + energy + counts (final before the Schur
+  // fold has run); & 8: the Schur-complement system alone
+  if (!(what & (2 | 4 | 8))) return;
   if (o.dn_Hb >= 0) {
-    const int N = 8 * D.W.n + 4, cnt = 3 * (N * N + N);
+    const int N = 8 * D.W.n + 4, per = N * N + N;
+    const int lo = (what & (2 | 4)) ? 0 : 2 * per, hi = (what & (2 | 8)) ? 3 * per : 2 * per;
     double* dst = reinterpret_cast<double*>(dn + o.dn_Hb);
-    for (int i = tid; i < cnt; i += stride) dst[i] = D.S.Hb[i];
+    for (int i = lo + tid; i < hi; i += stride) dst[i] = D.S.Hb[i];
   }
+  if (!(what & (2 | 4))) return;
   if (tid < 2 && o.dn_nres >= 0) reinterpret_cast<int*>(dn + o.dn_nres)[tid] = D.S.nres[tid];
   if (tid == 0 && o.dn_energy >= 0) *reinterpret_cast<double*>(dn + o.dn_energy) = *D.energy;
 }

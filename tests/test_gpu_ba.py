@@ -468,6 +468,44 @@ def test_batch_step_host_slim_outputs_with_device_threshold(ctx, capi, O, synth)
         f.close()
 
 
+def test_batch_step_host_split_accumulate_is_bit_identical(ctx, capi, synth):
+    """hslam_ba_batch_step_host on >= 8 same-shape windows with bound outputs takes the SPLIT accumulate path (A / L systems,
+    energy and counts stitched and copied under the Schur fold, the Schur-complement system behind it): every output is
+    bit-identical to the plain path (HSLAM_NO_SPLIT)."""
+    import os
+    kf = synth.render_keyframes(320, 240, 5, seed=85)
+    wins = [synth.make_window(points_per_frame=150, seed=800 + i, keyframes=kf, frac_linearized=0.2)[0] for i in range(8)]
+    assert len({w.R for w in wins}) == 1
+    frames = [capi.Frame(ctx, im, 1) for im in kf.images]
+    res = {}
+    for mode in ("split", "plain"):
+        if mode == "plain":
+            os.environ["HSLAM_NO_SPLIT"] = "1"
+        try:
+            efs = []
+            for w in wins:
+                b = capi.EnergyFunctional(ctx); b.set_window(w, frames); b.set_topology(w); efs.append(b)
+            batch = capi.EnergyFunctionalBatch(ctx, efs)
+            io = batch.make_io(wins, [frames] * len(wins), pinned="bound")
+            for o in io["arr"]:
+                o.newEnergy = None; o.newEnergyWithOutlier = None      # the slim result set: what the split form is for
+            outs = None
+            for it in range(2):
+                outs = batch.step_host(io)
+            res[mode] = [{k: np.array(o[k]).copy() for k in ("Hb", "energy", "nres2", "newState", "frameEnergyTH")} for o in outs]
+            batch.close()
+            for e in efs:
+                e.close()
+        finally:
+            os.environ.pop("HSLAM_NO_SPLIT", None)
+    for a, b in zip(res["split"], res["plain"]):
+        for k in a:
+            assert np.array_equal(a[k], b[k]), k
+        assert np.isfinite(a["Hb"]).all() and np.abs(a["Hb"]).max() > 0
+    for f in frames:
+        f.close()
+
+
 def test_batch_iteration_with_device_threshold(ctx, capi, O, synth):
     """Device-resident GN loop: hslam_ba_batch_set_newest_frame makes every hslam_ba_batch_iteration run
     setNewFrameEnergyTH on the device; the NEXT linearisation classifies with the new threshold, like the oracle's
