@@ -291,10 +291,12 @@ def main():
     N = 8 * N_FRAMES + 4
     xs = [np.ascontiguousarray(np.random.default_rng(i).normal(0, 1e-4, N)) for i in range(len(wins))]
     n2 = N_FRAMES * N_FRAMES
-    h2d = sum(n2 * 28 * 4 + n2 * 8 * 4 + 2 * n2 * 64 * 8 + 2 * N_FRAMES * 64 + 2 * w.P * 4 + N * 8 + 2 * 144 for w in wins)
+    h2d = sum(n2 * 28 * 4 + n2 * 8 * 4 + 2 * n2 * 64 * 8 + 2 * N_FRAMES * 64 + w.P * 4 + N * 8 + 2 * 144 for w in wins)   # tables, idepth, x, scalars
 
     def e2e_leg(with_energies):
         io = batch.make_io(wins, frames_all, pinned="bound")  # outputs live in the batch's page-locked result block (zero-copy views)
+        for o in io["arr"]:
+            o.deltaF = None; o.derive_deltaF = 1      # deltaF = idepth - idepth_zero is formed on the device (setDeltaF's point part)
         if not with_energies:
             for o in io["arr"]:
                 o.newEnergy = None; o.newEnergyWithOutlier = None

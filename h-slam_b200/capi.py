@@ -53,7 +53,7 @@ class ResidualSoA(C.Structure):
 
 class StepIO(C.Structure):
     _fields_ = [(k, C.c_void_p) for k in ("window", "idepth", "deltaF", "idepth_zero", "energy", "newState", "newEnergy",
-                                          "newEnergyWithOutlier", "Hb", "nres2", "frameEnergyTH_out")] + [("newest_frame", C.c_int32)]
+                                          "newEnergyWithOutlier", "Hb", "nres2", "frameEnergyTH_out")] + [("newest_frame", C.c_int32), ("derive_deltaF", C.c_int32)]
 
 
 def _ptr(a):

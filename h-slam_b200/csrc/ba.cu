@@ -1396,7 +1396,7 @@ struct hslam_ba_batch {
   cudaGraphExec_t graph_iter = nullptr, graph_acc = nullptr;
   uint64_t refresh_version = 1, graph_iter_version = 0, graph_acc_version = 0;
   int graph_iter_kernels = 0, graph_acc_kernels = 0;
-  size_t up_tab_begin = 0, up_idz_begin = 0, up_end = 0;   // H2D block regions: [0,tab) offset table + x slots, [tab,idz) window chunks, [idz,end) idepth_zero slots
+  size_t up_tab_begin = 0, up_dF_begin = 0, up_idz_begin = 0, up_end = 0;   // H2D block regions: [0,tab) offset table + x slots, [tab,idz) window chunks, [idz,end) idepth_zero slots
   std::vector<size_t> up_win_begin;   // start of window i's chunk [tables | idepth | deltaF]; [n] = up_idz_begin
   cudaStream_t up_stream = nullptr;   // step_host: uploads + import of group g+1 run here while group g is linearised
   cudaEvent_t ev_up[8] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
@@ -1732,9 +1732,12 @@ static int batch_layout_up(hslam_ba_batch* B) {
     L.up_adH = take(nn * 64 * 8); L.up_adT = take(nn * 64 * 8);
     L.up_fprior = take((size_t)ba->n * 8 * 8); L.up_fdprior = take((size_t)ba->n * 8 * 8);
     L.up_idepth = take((size_t)ba->P * 4);
-    L.up_deltaF = take((size_t)ba->P * 4);
   }
-  B->up_win_begin[n] = B->up_idz_begin = up;
+  // deltaF and idepth_zero have regions of their own: a caller that lets the device form deltaF (derive_deltaF) or leaves
+  // idepth_zero unchanged does not pay for their bytes
+  B->up_win_begin[n] = B->up_dF_begin = up;
+  for (int i = 0; i < n; ++i) B->io[i].up_deltaF = take((size_t)B->items[i]->P * 4);
+  B->up_idz_begin = up;
   for (int i = 0; i < n; ++i) B->io[i].up_idz = take((size_t)B->items[i]->P * 4);
   B->up_end = up;
   TRY(pinned_ensure(&B->h_up, &B->h_up_cap, up));
@@ -1796,6 +1799,7 @@ int hslam_ba_batch_step_host(hslam_ba_batch* B, const hslam_ba_step_io* io) {
     else E.up_precalc = E.up_adHTd = E.up_adH = E.up_adT = E.up_fprior = E.up_fdprior = -1;
     if (!o.idepth) E.up_idepth = -1;
     if (!o.deltaF) E.up_deltaF = -1;
+    E.pad = (o.derive_deltaF && o.idepth && !o.deltaF) ? 1 : 0;   // the import kernel forms deltaF = idepth - idepth_zero
     if (!o.idepth_zero) E.up_idz = -1;
     E.up_x = -1;
     // outputs the caller did not ask for are neither exported nor copied
@@ -1849,7 +1853,7 @@ int hslam_ba_batch_step_host(hslam_ba_batch* B, const hslam_ba_step_io* io) {
   for (int g = 0; g < G; ++g) {
     const int g0 = (int)((long long)n * g / G), g1 = (int)((long long)n * (g + 1) / G);
     // ---- inputs of the group: pack what is not already in its pinned slot, one H2D of the group's span, import
-    bool any_in = false, any_idz = false;
+    bool any_in = false, any_idz = false, any_dF = false;
     int gP = 1, gR = 1;
     for (int i = g0; i < g1; ++i) {
       hslam_ba* ba = B->items[i];
@@ -1875,7 +1879,7 @@ int hslam_ba_batch_step_host(hslam_ba_batch* B, const hslam_ba_step_io* io) {
         flag = true;
       };
       put(o.idepth, L.up_idepth, any_in);
-      put(o.deltaF, L.up_deltaF, any_in);
+      put(o.deltaF, L.up_deltaF, any_dF);
       put(o.idepth_zero, L.up_idz, any_idz);
       gP = std::max(gP, ba->P); gR = std::max(gR, ba->R);
     }
@@ -1883,11 +1887,15 @@ int hslam_ba_batch_step_host(hslam_ba_batch* B, const hslam_ba_step_io* io) {
       const size_t lo = B->up_win_begin[g0], hi = B->up_win_begin[g1];
       HS_CUDA(cudaMemcpyAsync(B->d_up.p + lo, B->h_up + lo, hi - lo, cudaMemcpyHostToDevice, B->up_stream));
     }
+    if (any_dF) {
+      const size_t lo = (size_t)B->io[g0].up_deltaF, hi = g1 < n ? (size_t)B->io[g1].up_deltaF : B->up_idz_begin;
+      HS_CUDA(cudaMemcpyAsync(B->d_up.p + lo, B->h_up + lo, hi - lo, cudaMemcpyHostToDevice, B->up_stream));
+    }
     if (any_idz) {
       const size_t lo = (size_t)B->io[g0].up_idz, hi = g1 < n ? (size_t)B->io[g1].up_idz : B->up_end;
       HS_CUDA(cudaMemcpyAsync(B->d_up.p + lo, B->h_up + lo, hi - lo, cudaMemcpyHostToDevice, B->up_stream));
     }
-    if (any_in || any_idz) {
+    if (any_in || any_idz || any_dF) {
       dim3 grid((unsigned)std::max(1, std::min(64, (gP + 255) / 256)), (unsigned)(g1 - g0));
       ctx->launches++;   // upload stream: counted, not event-timed
       ba_batch_import_kernel<<<grid, 256, 0, B->up_stream>>>(B->d_descs.p + g0, d_io + g0, B->d_up.p);

@@ -176,7 +176,7 @@ struct BAIO {
   long long up_precalc, up_adHTd, up_adH, up_adT, up_fprior, up_fdprior, up_idepth, up_deltaF, up_idz, up_x;
   long long dn_energy, dn_nres, dn_Hb, dn_newEnergy, dn_newEnergyWO, dn_newState, dn_step;
   long long dn_th;           // new frameEnergyTH of frame `newest` (System::setNewFrameEnergyTH), 1 float
-  int newest, pad;
+  int newest, pad;           // pad: 1 = deltaF is formed on the device (hslam_ba_step_io::derive_deltaF)
 };
 
 __device__ __forceinline__ int find_window(const int* __restrict__ prefix, int nwin, int b, int& local) {
@@ -2054,12 +2054,14 @@ __global__ void __launch_bounds__(256) ba_batch_import_kernel(const BADesc* __re
   const float* s_id = o.up_idepth >= 0 ? reinterpret_cast<const float*>(up + o.up_idepth) : nullptr;
   const float* s_iz = o.up_idz >= 0 ? reinterpret_cast<const float*>(up + o.up_idz) : nullptr;
   const float* s_dF = o.up_deltaF >= 0 ? reinterpret_cast<const float*>(up + o.up_deltaF) : nullptr;
+  const bool derive = o.pad != 0 && s_id && !s_dF;   // EnergyFunctional::setDeltaF's point part (EnergyFunctional.cpp:148) on the device
   if (s_id || s_iz || s_dF)
     for (int p = tid; p < P; p += stride) {
       const int q = D.p_s2o[p];
       if (s_id) uvid[4 * (size_t)p + 2] = s_id[q];
       if (s_iz) uvid[4 * (size_t)p + 3] = s_iz[q];
       if (s_dF) deltaF[p] = s_dF[q];
+      else if (derive) deltaF[p] = xsub(s_id[q], s_iz ? s_iz[q] : uvid[4 * (size_t)p + 3]);   // one exactly-rounded subtraction, as on the host
     }
 }
 // Export: per-residual results back to caller order, the stitched systems, counts and energy, all into

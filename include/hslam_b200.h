@@ -404,6 +404,10 @@ typedef struct hslam_ba_step_io {
    * returned here (1 float) — the caller then needs neither newEnergy nor newEnergyWithOutlier on the host. */
   float* frameEnergyTH_out;
   int32_t newest_frame;
+  /* non-zero, with idepth given and deltaF null: the device forms deltaF = idepth - idepth_zero itself (the point part
+   * of EnergyFunctional::setDeltaF, EnergyFunctional.cpp:148; one exactly-rounded float subtraction, bit-identical to the
+   * host's), so the deltaF array does not cross PCIe. */
+  int32_t derive_deltaF;
 } hslam_ba_step_io;
 int hslam_ba_batch_step_host(hslam_ba_batch* batch, const hslam_ba_step_io* io /* one per window */);
 /* Zero-copy buffers: point every OUTPUT member of io[0..count) (and step_out[i], if not null) at the window's

@@ -471,14 +471,14 @@ def test_batch_step_host_slim_outputs_with_device_threshold(ctx, capi, O, synth)
 def test_batch_step_host_split_accumulate_is_bit_identical(ctx, capi, synth):
     """hslam_ba_batch_step_host on >= 8 same-shape windows with bound outputs takes the SPLIT accumulate path (A / L systems,
     energy and counts stitched and copied under the Schur fold, the Schur-complement system behind it): every output is
-    bit-identical to the plain path (HSLAM_NO_SPLIT)."""
+    bit-identical to the plain path (HSLAM_NO_SPLIT); so is a run that lets the device form deltaF (derive_deltaF)."""
     import os
     kf = synth.render_keyframes(320, 240, 5, seed=85)
     wins = [synth.make_window(points_per_frame=150, seed=800 + i, keyframes=kf, frac_linearized=0.2)[0] for i in range(8)]
     assert len({w.R for w in wins}) == 1
     frames = [capi.Frame(ctx, im, 1) for im in kf.images]
     res = {}
-    for mode in ("split", "plain"):
+    for mode in ("split", "plain", "derive"):
         if mode == "plain":
             os.environ["HSLAM_NO_SPLIT"] = "1"
         try:
@@ -489,8 +489,13 @@ def test_batch_step_host_split_accumulate_is_bit_identical(ctx, capi, synth):
             io = batch.make_io(wins, [frames] * len(wins), pinned="bound")
             for o in io["arr"]:
                 o.newEnergy = None; o.newEnergyWithOutlier = None      # the slim result set: what the split form is for
+                if mode == "derive":                                   # deltaF = idepth - idepth_zero formed on the device
+                    o.deltaF = None; o.derive_deltaF = 1
             outs = None
             for it in range(2):
+                for w, (ws, ka, inp) in zip(wins, io["keep"]):
+                    inp["idepth"][:] = (w.idepth * np.float32(1.0 + 0.003 * (it + 1))).astype(np.float32)
+                    inp["deltaF"][:] = inp["idepth"] - w.idepth_zero
                 outs = batch.step_host(io)
             res[mode] = [{k: np.array(o[k]).copy() for k in ("Hb", "energy", "nres2", "newState", "frameEnergyTH")} for o in outs]
             batch.close()
@@ -498,9 +503,10 @@ def test_batch_step_host_split_accumulate_is_bit_identical(ctx, capi, synth):
                 e.close()
         finally:
             os.environ.pop("HSLAM_NO_SPLIT", None)
-    for a, b in zip(res["split"], res["plain"]):
+    for a, b, c in zip(res["split"], res["plain"], res["derive"]):
         for k in a:
             assert np.array_equal(a[k], b[k]), k
+            assert np.array_equal(a[k], c[k]), ("derive_deltaF", k)
         assert np.isfinite(a["Hb"]).all() and np.abs(a["Hb"]).max() > 0
     for f in frames:
         f.close()
