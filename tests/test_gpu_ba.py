@@ -100,6 +100,32 @@ def test_accumulate_against_double_oracle(ba_setup):
         assert np.array_equal(H1, H2) and np.array_equal(b1, b2)
 
 
+@pytest.mark.parametrize("n_frames", [2, 3, 9, 11])
+def test_schur_kernel_variants_by_window_size(ctx, capi, O, synth, n_frames):
+    """The Schur fold picks its kernel by the number of keyframes: 8x8 register tiles with eight point slices (n <= 7), with
+    four slices (n <= 10), 4x4 tiles beyond.  Every variant: per-point results bit-exact vs the float restatement, the three
+    systems <= 1e-5 vs the fp64 oracle (and no worse than 1.5 x the float restatement)."""
+    kf = synth.render_keyframes(320, 240, n_frames, seed=90 + n_frames)
+    win, is_lin = synth.make_window(points_per_frame=90, seed=300 + n_frames, keyframes=kf, frac_linearized=0.25)
+    frames = [capi.Frame(ctx, im, 1) for im in win.images]
+    dIs = [O.pyramid(im, 1)[0][0] for im in win.images]
+    ef = capi.EnergyFunctional(ctx); ef.set_window(win, frames); ef.set_topology(win)
+    of, od = O.BAOracle(win, dIs, prec="f"), O.BAOracle(win, dIs, prec="d")
+    run_sequence(ef, win, is_lin, "gpu"); run_sequence(of, win, is_lin, "orc"); run_sequence(od, win, is_lin, "orc")
+    sys3 = ef.accumulate_all()
+    for k, (Hg, bg) in enumerate(sys3):
+        Hd, bd, _ = od.accumulate(k)
+        Hf, bf, _ = of.accumulate(k)
+        assert rel_fro(Hg, Hd) <= max(1e-5, 1.5 * rel_fro(Hf, Hd)), (n_frames, k)
+        assert rel_fro(bg, bd) <= max(1e-5, 1.5 * rel_fro(bf, bd)), (n_frames, k)
+    pg, pf = ef.point_results(), of.point_results()
+    for key in ("HdiF", "bdSumF"):
+        assert np.array_equal(pg[key], pf[key].astype(np.float32)), (n_frames, key)
+    ef.close()
+    for f in frames:
+        f.close()
+
+
 def test_point_side_effects_bit_exact(ba_setup):
     ef, of = ba_setup["ef"], ba_setup["of"]
     ef.accumulateAF_MT(); ef.accumulateLF_MT(); ef.accumulateSCF_MT()
