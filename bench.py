@@ -43,7 +43,7 @@ ALGO_BYTES_PER_RES = {
     # 8 px x 4 texels x 12 B, point record/6, indices/state; written: the 34 geometric + summed floats of RawResidualJacobian
     # (GN-loop mode: the 40 per-pixel floats and projectedTo, 160 + 64 B, are not materialised; 769 B with them)
     "ba_linearize": 384 + 13.3 + 12 + 136,
-    "ba_top": 148 + 2 + 24,                       # 37 Jacobian floats + flags read; 6 per-residual point terms written
+    "ba_top": 156 + 32,                           # mode A: 39 Jacobian floats read, one 32-byte point-term record written
     "ba_schur": 32 + 2,                           # JpJdF read per residual
 }
 
