@@ -376,7 +376,7 @@ def main():
     if rank == 0:
         if not args.no_extras:
             line["extra"] = extras(ctx, capi, synth, torch, stream, None, wins[0])
-        if not args.no_cpu_baseline:
+        if not args.no_cpu_baseline and world == 1:      # the CPU baseline is a rank-0, N=1 figure (contract)
             line["cpu_baseline"] = cpu_baseline(synth, wins[0], lins[0])
         print(json.dumps(line), flush=True)
     if world > 1:
