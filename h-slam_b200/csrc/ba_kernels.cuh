@@ -30,11 +30,13 @@ constexpr int J_RESF = 0, J_XI0 = 8, J_XI1 = 14, J_C0 = 20, J_C1 = 24, J_DD = 28
 // Lineariser launch shape, measured on B200 with the pair-image gather (64 cfg2 windows = 5.4 M residuals per launch):
 //   64 threads x 8 blocks/SM (128 regs, no spills) 1015 us | 64 x 10 (96 regs) 1028 | 32 x 20 1026 | 128 x 5 1041 | 128 x 4 1047
 //   64 x 9 / 96 x 7 (spills) 1180.   With the float4 image (four 16-byte loads per tap): 128 x 6 (80 regs) 1094, 64 x 12 1081.
+// Round 2 (tile schedule, GN-loop mode, 3.76 M residuals per launch): 32 x 16 628 us | 64 x 8 635 | 128 x 4 642 — with one
+// warp per tile a warp retires as soon as its own residuals are done and the last tile of a pair wastes less.
 #ifndef LIN_MINB
-#define LIN_MINB 8
+#define LIN_MINB 16
 #endif
 #ifndef LIN_THREADS_
-#define LIN_THREADS_ 64
+#define LIN_THREADS_ 32
 #endif
 constexpr int LIN_THREADS = LIN_THREADS_;
 // Streaming (evict-first) stores for the big per-residual output streams: they are written once per
