@@ -60,7 +60,13 @@ constexpr int SC_THREADS = 256;
 #define SC_PTS_ 64
 #endif
 constexpr int SC_PTS = SC_PTS_;        // points staged in shared memory per sub-tile (32 / 64 / 128)
-constexpr int ST_WARPS = 8;            // warps per stitch block (80 regs x 256 threads: 3 blocks per SM)
+// warps per stitch block.  Measured on the 64-window batch (12 288 output blocks, most of them with two sandwiches):
+// 16 warps 134 us | 8: 72 | 4: 56 | 3: 53 | 2: 50.  Four: a window that runs alone (192 blocks, up to 38 sandwiches each) still
+// gets its sandwiches done in ten rounds.  One value for every entry point: the warp count fixes the fp64 summation order.
+#ifndef ST_WARPS_
+#define ST_WARPS_ 4
+#endif
+constexpr int ST_WARPS = ST_WARPS_;
 constexpr int ST_THREADS = ST_WARPS * 32;
 
 __constant__ int c_pat[8][2] = {{0, -2}, {-1, -1}, {1, -1}, {-2, 0}, {0, 0}, {2, 0}, {-1, 1}, {0, 2}};
@@ -501,9 +507,20 @@ __global__ void __launch_bounds__(LIN_THREADS, LIN_MINB) ba_linearize_kernel(con
 // multiple of 32, <= 512).  `red` is shared scratch of 16 doubles.
 __device__ __forceinline__ void energy_sum_block(const BADesc& D, double* red) {
   const int nparts = D.lin_warps;
-  double acc = 0.0;
-#pragma unroll 4
-  for (int b = threadIdx.x; b < nparts; b += blockDim.x) acc += __ldcg(D.epart + b);
+  // eight independent loads per round, four accumulators: the sum is one block's work and latency-bound — for the
+  // 2 M-residual window (62 500 partials) the dependent-add loop it replaces was ~100 us of the 0.55 ms iteration
+  double a0 = 0.0, a1 = 0.0, a2 = 0.0, a3 = 0.0;
+  const int st = blockDim.x;
+  int b = threadIdx.x;
+  for (; b + 7 * st < nparts; b += 8 * st) {
+    double v[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) v[j] = __ldcg(D.epart + b + j * st);
+    a0 += v[0]; a1 += v[1]; a2 += v[2]; a3 += v[3];
+    a0 += v[4]; a1 += v[5]; a2 += v[6]; a3 += v[7];
+  }
+  for (; b < nparts; b += st) a0 += __ldcg(D.epart + b);
+  double acc = (a0 + a1) + (a2 + a3);
   acc = warp_sum(acc);
   if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = acc;
   __syncthreads();
