@@ -927,7 +927,7 @@ static int launch_stitch(hslam_ba* ba, int sys_begin, int sys_end, int with_ener
   hslam_ctx* ctx = ba->ctx;
   TRY(sync_desc(ba));
   int blocks = 3 * (ba->n + 1) * (ba->n + 1);
-  HS_LAUNCH(ctx, HSLAM_K_BA_STITCH, (ba_stitch_kernel<<<blocks, ST_THREADS, 0, ctx->stream>>>(ba->d_desc.p, nullptr, 1, sys_begin, sys_end, with_energy)));
+  HS_LAUNCH(ctx, HSLAM_K_BA_STITCH, (ba_stitch_kernel<8><<<blocks, 256, 0, ctx->stream>>>(ba->d_desc.p, nullptr, 1, sys_begin, sys_end, with_energy)));
   HS_CUDA(cudaGetLastError());
   return 0;
 }
@@ -1587,7 +1587,7 @@ static int batch_enqueue_accumulate(hslam_ba_batch* B, bool with_th = false) {
     HS_LAUNCH(ctx, HSLAM_K_BA_SCHUR, schur_launch(B->maxt, B->blocks[2], B->smem, ctx->stream, B->d_descs.p, pf + 2 * (n + 1), B->uniform[2] ? -B->uniform[2] : n));
   HS_LAUNCH(ctx, HSLAM_K_BA_FOLD_SC, (ba_fold_sc_kernel<<<B->blocks[4], 256, 0, ctx->stream>>>(B->d_descs.p, pf + 4 * (n + 1), B->uniform[4] ? -B->uniform[4] : n, 3, 1)));
   if (with_th) TRY(batch_fork_th(B));
-  HS_LAUNCH(ctx, HSLAM_K_BA_STITCH, (ba_stitch_kernel<<<B->blocks[3], ST_THREADS, 0, ctx->stream>>>(B->d_descs.p, pf + 3 * (n + 1), B->uniform[3] ? -B->uniform[3] : n, 0, 3, 1)));
+  HS_LAUNCH(ctx, HSLAM_K_BA_STITCH, (ba_stitch_kernel<4><<<B->blocks[3], 128, 0, ctx->stream>>>(B->d_descs.p, pf + 3 * (n + 1), B->uniform[3] ? -B->uniform[3] : n, 0, 3, 1)));
   HS_CUDA(cudaGetLastError());
   if (with_th) TRY(batch_join_th(B));
   return 0;
@@ -1968,7 +1968,7 @@ int hslam_ba_batch_step_host(hslam_ba_batch* B, const hslam_ba_step_io* io) {
     HS_CUDA(cudaEventRecord(B->ev_th[0], ctx->stream));
     HS_CUDA(cudaStreamWaitEvent(bs, B->ev_th[0], 0));
     ctx->launches += 2;   // counted, not event-timed
-    ba_stitch_kernel<<<B->blocks[3], ST_THREADS, 0, bs>>>(B->d_descs.p, pf + 3 * (n + 1), -B->uniform[3], 0, 2, 1);
+    ba_stitch_kernel<4><<<B->blocks[3], 128, 0, bs>>>(B->d_descs.p, pf + 3 * (n + 1), -B->uniform[3], 0, 2, 1);
     ba_batch_export_kernel<<<dim3(2, (unsigned)n), 256, 0, bs>>>(B->d_descs.p, d_io, B->d_dn.p, 4);
     HS_CUDA(cudaGetLastError());
     {   // per window [energy | counts | threshold | H_A b_A H_L b_L]: one strided copy
@@ -1978,7 +1978,7 @@ int hslam_ba_batch_step_host(hslam_ba_batch* B, const hslam_ba_step_io* io) {
     HS_CUDA(cudaEventRecord(B->ev_th[1], bs));
     HS_LAUNCH(ctx, HSLAM_K_BA_SCHUR, schur_launch(B->maxt, B->blocks[2], B->smem, ctx->stream, B->d_descs.p, pf + 2 * (n + 1), -B->uniform[2]));
     HS_LAUNCH(ctx, HSLAM_K_BA_FOLD_SC, (ba_fold_sc_kernel<<<n * fsb, 256, 0, ctx->stream>>>(B->d_descs.p, nullptr, -fsb, 0, 1)));
-    HS_LAUNCH(ctx, HSLAM_K_BA_STITCH, (ba_stitch_kernel<<<B->blocks[3], ST_THREADS, 0, ctx->stream>>>(B->d_descs.p, pf + 3 * (n + 1), -B->uniform[3], 2, 3, 0)));
+    HS_LAUNCH(ctx, HSLAM_K_BA_STITCH, (ba_stitch_kernel<4><<<B->blocks[3], 128, 0, ctx->stream>>>(B->d_descs.p, pf + 3 * (n + 1), -B->uniform[3], 2, 3, 0)));
     HS_LAUNCH(ctx, HSLAM_K_BA_EXPORT, (ba_batch_export_kernel<<<dim3(2, (unsigned)n), 256, 0, ctx->stream>>>(B->d_descs.p, d_io, B->d_dn.p, 8)));
     HS_CUDA(cudaGetLastError());
     {

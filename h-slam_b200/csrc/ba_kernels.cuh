@@ -60,14 +60,12 @@ constexpr int SC_THREADS = 256;
 #define SC_PTS_ 64
 #endif
 constexpr int SC_PTS = SC_PTS_;        // points staged in shared memory per sub-tile (32 / 64 / 128)
-// warps per stitch block.  Measured on the 64-window batch (12 288 output blocks, most of them with two sandwiches):
-// 16 warps 134 us | 8: 72 | 4: 56 | 3: 53 | 2: 50.  Four: a window that runs alone (192 blocks, up to 38 sandwiches each) still
-// gets its sandwiches done in ten rounds.  One value for every entry point: the warp count fixes the fp64 summation order.
-#ifndef ST_WARPS_
-#define ST_WARPS_ 4
-#endif
-constexpr int ST_WARPS = ST_WARPS_;
-constexpr int ST_THREADS = ST_WARPS * 32;
+// Stitch blocks: the sandwiches of an output block are dealt round-robin to ST_SLOTS = 8 accumulator SLOTS; a block of
+// eight warps gives every warp one slot, a block of four warps two — the slots are summed in slot order, so the result
+// does not depend on the warp count.  Measured on the 64-window batch (12 288 output blocks, most of them with two
+// sandwiches): 16 warps 134 us | 8: 72 | 4: 56 | 2: 50; a window that runs alone (192 blocks, up to 38 sandwiches each)
+// is latency-bound and wants the eight warps.  So: four warps for a batch, eight for a single window, same bits.
+constexpr int ST_SLOTS = 8;
 
 __constant__ int c_pat[8][2] = {{0, -2}, {-1, -1}, {1, -1}, {-2, 0}, {0, 0}, {2, 0}, {-1, 1}, {0, 2}};
 
@@ -503,15 +501,16 @@ __global__ void __launch_bounds__(LIN_THREADS, LIN_MINB) ba_linearize_kernel(con
   if ((threadIdx.x & 31) == 0) D.epart[lb * (LIN_THREADS / 32) + (threadIdx.x >> 5)] = e;
 }
 
-// Fixed-order sum of the per-warp energy partials of ONE window by one block (any block size that is a
-// multiple of 32, <= 512).  `red` is shared scratch of 16 doubles.
+// Fixed-order sum of the per-warp energy partials of ONE window by one block (any block size >= 128 that is a
+// multiple of 32).  `red` is shared scratch of 16 doubles.
 __device__ __forceinline__ void energy_sum_block(const BADesc& D, double* red) {
   const int nparts = D.lin_warps;
   // eight independent loads per round, four accumulators: the sum is one block's work and latency-bound — for the
   // 2 M-residual window (62 500 partials) the dependent-add loop it replaces was ~100 us of the 0.55 ms iteration
+  // (the first 128 threads do it, whatever the block size: the order must not depend on who calls)
   double a0 = 0.0, a1 = 0.0, a2 = 0.0, a3 = 0.0;
-  const int st = blockDim.x;
-  int b = threadIdx.x;
+  const int st = 128;
+  int b = threadIdx.x < 128 ? (int)threadIdx.x : nparts;
   for (; b + 7 * st < nparts; b += 8 * st) {
     double v[8];
 #pragma unroll
@@ -522,11 +521,11 @@ __device__ __forceinline__ void energy_sum_block(const BADesc& D, double* red) {
   for (; b < nparts; b += st) a0 += __ldcg(D.epart + b);
   double acc = (a0 + a1) + (a2 + a3);
   acc = warp_sum(acc);
-  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = acc;
+  if ((threadIdx.x & 31) == 0 && threadIdx.x < 128) red[threadIdx.x >> 5] = acc;
   __syncthreads();
   if (threadIdx.x == 0) {
     double t = 0.0;
-    for (int w = 0; w < (int)(blockDim.x >> 5); ++w) t += red[w];
+    for (int w = 0; w < 4; ++w) t += red[w];
     *D.energy = t;
     if (D.S.Hb) { const int N = 8 * D.S.n + 4; D.S.Hb[3 * ((size_t)N * N + N)] = t; }   // rides with the systems through hslam_ba_allreduce
   }
@@ -1724,9 +1723,11 @@ __device__ __forceinline__ void sandwich_dmma(const double* __restrict__ A1, con
 // system; index n is the calibration block.  The Ad * M * Ad^T sandwiches that land in a block are dealt round-robin to the
 // block's warps (four fp64 tensor-core steps each, accumulated in the warp's DMMA accumulators), then the warps' partial
 // blocks are summed in warp order.  The 8x8x8 fp64 products are the one true contraction on the path (and exact fp64 FMAs).
-__global__ void __launch_bounds__(ST_THREADS) ba_stitch_kernel(const BADesc* __restrict__ descs,
+template <int WARPS>
+__global__ void __launch_bounds__(WARPS * 32) ba_stitch_kernel(const BADesc* __restrict__ descs,
                                                                const int* __restrict__ prefix, int nwin,
                                                                int sys_begin, int sys_end, int with_energy) {
+  static_assert(WARPS == 4 || WARPS == 8, "a warp owns one or two of the eight accumulator slots");
   int lb;
   const int win = find_window(prefix, nwin, blockIdx.x, lb);
   const StitchArgs& S = descs[win].S;
@@ -1736,28 +1737,32 @@ __global__ void __launch_bounds__(ST_THREADS) ba_stitch_kernel(const BADesc* __r
   const int a = ab % nb1, b = ab / nb1;
   if (sys < sys_begin || sys >= sys_end) return;   // systems (0=A, 1=L, 2=SC) this launch produces
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  __shared__ double part[ST_WARPS][64];
+  __shared__ double part[ST_SLOTS][64];
   double* H = S.Hb + (size_t)sys * ((size_t)N * N + N);
   double* bv = H + (size_t)N * N;
   const int nn = n * n;
   auto AdH = [&](int h, int t) { return S.adHost + 64 * (size_t)(h + t * n); };
   auto AdT = [&](int h, int t) { return S.adTarget + 64 * (size_t)(h + t * n); };
-  double o0 = 0.0, o1 = 0.0;
+  double o0 = 0.0, o1 = 0.0;   // slot `warp`
+  double p0 = 0.0, p1 = 0.0;   // slot `warp + 4` (four-warp blocks)
   int ci = 0;   // contribution counter, identical in every warp
-#define CONTRIB(A1, A2, MB, LDM)                                                            \
-  do {                                                                                      \
-    if ((ci % ST_WARPS) == warp) sandwich_dmma((A1), (A2), (MB), (LDM), lane, o0, o1);      \
-    ci++;                                                                                   \
+#define CONTRIB(A1, A2, MB, LDM)                                                                          \
+  do {                                                                                                    \
+    const int sl_ = ci & (ST_SLOTS - 1);                                                                  \
+    if (sl_ == warp) sandwich_dmma((A1), (A2), (MB), (LDM), lane, o0, o1);                                \
+    else if (WARPS == 4 && sl_ == warp + 4) sandwich_dmma((A1), (A2), (MB), (LDM), lane, p0, p1);         \
+    ci++;                                                                                                 \
   } while (0)
-  // the warps' accumulator pairs (row g, columns 2t, 2t+1) -> part[warp][row + 8 col], summed in warp order by 64 threads
+  // the slots' accumulator pairs (row g, columns 2t, 2t+1) -> part[slot][row + 8 col], summed in slot order by 64 threads
   auto reduce_block = [&](auto&& store) {
     const int g = lane >> 2, t = lane & 3;
     part[warp][g + 8 * (2 * t)] = o0; part[warp][g + 8 * (2 * t + 1)] = o1;
+    if (WARPS == 4) { part[warp + 4][g + 8 * (2 * t)] = p0; part[warp + 4][g + 8 * (2 * t + 1)] = p1; }
     __syncthreads();
     if (threadIdx.x < 64) {
       double o = 0.0;
 #pragma unroll
-      for (int w = 0; w < ST_WARPS; ++w) o += part[w][threadIdx.x];
+      for (int w = 0; w < ST_SLOTS; ++w) o += part[w][threadIdx.x];
       store(threadIdx.x & 7, threadIdx.x >> 3, o);
     }
   };
