@@ -224,6 +224,32 @@ int ref_ba_accumulate(ref_ba* b, int which, double* H, double* bvec, int* nres) 
   return 0;
 }
 
+// EnergyFunctional::marginalizePointsF (EnergyFunctional.cpp:545-609), the part on the path: priorF scaling (:564),
+// addPoint<2> + SC addPoint(p, false) over the points to marginalise (:574-579), stitchDouble(usePrior=false) of both
+// (:582-583).  The caller forms H = M - Msc, b = Mb - Mbsc (:587-588).
+int ref_ba_marginalize_points(ref_ba* b, const int32_t* ids, int count, float prior_scale, double* M, double* Mb, double* Msc,
+                              double* Mbsc, int* nres) {
+  EnergyFunctional* ef = b->ef.get();
+  const int n = b->n;
+  b->bot.setZero(n);
+  b->topA.setZero(n);
+  for (int i = 0; i < count; ++i) {
+    if (ids[i] < 0 || ids[i] >= (int)b->points.size()) return -1;
+    std::shared_ptr<MapPoint>& p = b->points[ids[i]];
+    p->efPoint->priorF *= prior_scale;
+    b->topA.addPoint<2>(p, ef);
+    b->bot.addPoint(p, false);
+  }
+  MatXX Mm, Mscm; VecX Mbm, Mbscm;
+  b->topA.stitchDouble(Mm, Mbm, ef, false, false);
+  b->bot.stitchDouble(Mscm, Mbscm, ef);
+  if (nres) *nres = b->topA.nres[0];
+  const int N = 8 * n + 4;
+  for (int j = 0; j < N; ++j) for (int i = 0; i < N; ++i) { M[i + (size_t)N * j] = Mm(i, j); Msc[i + (size_t)N * j] = Mscm(i, j); }
+  for (int i = 0; i < N; ++i) { Mb[i] = Mbm[i]; Mbsc[i] = Mbscm[i]; }
+  return 0;
+}
+
 int ref_ba_point_results(ref_ba* b, double* HdiF, double* bdSumF, double* idepth_hessian, double* Hdd_accAF, double* bd_accAF,
                          double* Hcd_accAF, double* Hdd_accLF, double* bd_accLF, double* Hcd_accLF) {
   for (size_t i = 0; i < b->points.size(); ++i) {

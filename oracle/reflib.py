@@ -101,6 +101,15 @@ class RefBA:
         assert self.L.ref_ba_accumulate(self.h, C.c_int(which), _ptr(H), _ptr(b), C.byref(nres)) == 0
         return H.reshape(N, N).T.copy(), b, nres.value
 
+    def marginalize_points(self, point_ids, prior_scale):
+        """EnergyFunctional::marginalizePointsF's accumulate + stitch part: addPoint<2>, SC addPoint(p, false), stitchDouble."""
+        N = 8 * self.n + 4
+        M = np.zeros(N * N); Mb = np.zeros(N); Ms = np.zeros(N * N); Mbs = np.zeros(N); nres = C.c_int(0)
+        ids = np.ascontiguousarray(point_ids, np.int32)
+        assert self.L.ref_ba_marginalize_points(self.h, _ptr(ids), C.c_int(len(ids)), C.c_float(prior_scale), _ptr(M), _ptr(Mb),
+                                                _ptr(Ms), _ptr(Mbs), C.byref(nres)) == 0
+        return M.reshape(N, N).T.copy(), Mb, Ms.reshape(N, N).T.copy(), Mbs, nres.value
+
     def point_results(self):
         P = self.P
         names = ["HdiF", "bdSumF", "idepth_hessian", "Hdd_accAF", "bd_accAF", "Hcd_accAF", "Hdd_accLF", "bd_accLF", "Hcd_accLF"]

@@ -100,6 +100,26 @@ def test_accumulate_and_stitch_match_reference_code(pair):
     assert np.abs(pr["HdiF"]).max() > 0 and np.abs(pr["Hdd_accLF"]).max() > 0
 
 
+def test_marginalisation_accumulate_matches_reference_code(pair):
+    """Runs after the tests above.  EnergyFunctional::marginalizePointsF's part on the path — priorF scaling, addPoint<2> over
+    the points to marginalise, SC addPoint(p, shiftPriorToZero=false), stitchDouble(usePrior=false) of both — compiled from the
+    reference vs the oracle: M, Mb (mode 2 mixes active and linearised residuals, so they sit downstream of res_toZeroF like
+    the L system) and Msc, Mbsc to fp32 round-off; resInM exact."""
+    win, is_lin, f, r, d = pair
+    rng = np.random.default_rng(5)
+    ids = np.sort(rng.choice(win.P, size=win.P // 5, replace=False)).astype(np.int32)
+    # flagPointsForRemoval fixes the linearisation of every residual of a point before it is marginalised (Mapping.cpp:286-293;
+    # addPoint<2> asserts it, AccumulatedTopHessian.cpp:46)
+    rids = np.concatenate([win.res_index[win.res_begin[p]:win.res_begin[p + 1]] for p in ids]).astype(np.int32)
+    f.fix_linearization(rids); r.fix_linearization(rids)
+    of = f.marginalize_points(ids, 0.5)
+    rf = r.marginalize_points(ids, 0.5)
+    assert of[4] == rf[4] and rf[4] > 0
+    for a, b, tol in ((of[0], rf[0], 1e-9), (of[1], rf[1], 1e-6), (of[2], rf[2], 1e-9), (of[3], rf[3], 1e-6)):
+        assert np.abs(b).max() > 0
+        assert rel_fro(a, b) < tol, rel_fro(a, b)
+
+
 def test_frame_frame_precalc_matches_reference_code(O, RL, synth):
     """FrameFramePrecalc::set compiled from the reference vs the table generators (numpy and the oracle's C restatement)."""
     kf = synth.render_keyframes(160, 120, 4, seed=9)
