@@ -207,4 +207,92 @@ int ref_trace_immature(const float* dI0, int w, int h, float fx, float fy, float
   return 0;
 }
 
+// System::optimizeImmaturePoint (Src/FullSystemOptPoint.cpp:24-175) is a System member (not compilable here); its loop is
+// followed line by line below with the REFERENCE's ImmaturePoint::linearizeResidual (Src/ImmaturePoint.cpp:389-451, with
+// projectPoint / derive_idepth of Include/DirectProjection.h) doing every residual evaluation.  Same argument list as
+// orc_activate_immature.
+int ref_activate_immature(int n_frames, const float* const* dI0, int w, int h, float fx, float fy, float cx, float cy, const float* RtAff,
+                          float huber, float minIdepthH_act, int GNIts, int minObs, int n, const int32_t* host_idx, const float* u,
+                          const float* v, const float* color, const float* weights, const float* energyTH, const float* idepth_min,
+                          const float* idepth_max, int8_t* ok_out, float* idepth_out, int8_t* res_state_out) {
+  Mat33 K = Mat33::Identity();
+  K(0, 0) = fx; K(1, 1) = fy; K(0, 2) = cx; K(1, 2) = cy;
+  int dirPyr = 1;
+  std::shared_ptr<CalibData> calib(new CalibData(w, h, K, 0.f, nullptr, nullptr, dirPyr, 1, 1.2f));
+  setting_huberTH = huber;
+  std::vector<std::shared_ptr<FrameShell>> frames;
+  for (int f = 0; f < n_frames; ++f) {
+    frames.push_back(make_shell(calib, 1.f, 1));
+    frames[f]->frame->DirPyr[0] = reinterpret_cast<Vec3f*>(const_cast<float*>(dI0[f]));
+    frames[f]->frame->idx = f;
+  }
+  for (int hh = 0; hh < n_frames; ++hh) {   // the three members of FrameFramePrecalc that linearizeResidual reads
+    frames[hh]->frame->targetPrecalc.resize(n_frames);
+    for (int t = 0; t < n_frames; ++t) {
+      const float* T = RtAff + 14 * (size_t)(hh + t * n_frames);
+      FrameFramePrecalc& pc = frames[hh]->frame->targetPrecalc[t];
+      for (int i = 0; i < 3; ++i) { for (int j = 0; j < 3; ++j) pc.PRE_RTll(i, j) = T[3 * i + j]; pc.PRE_tTll[i] = T[9 + i]; }
+      pc.PRE_aff_mode[0] = T[12]; pc.PRE_aff_mode[1] = T[13];
+    }
+  }
+  for (int p = 0; p < n; ++p) {
+    const int host = host_idx[p];
+    if (host < 0 || host >= n_frames) return -1;
+    ok_out[p] = 0; idepth_out[p] = 0;
+    for (int f = 0; f < n_frames; ++f) res_state_out[(size_t)p * n_frames + f] = 1;
+    std::shared_ptr<ImmaturePoint> point(new ImmaturePoint(8.f, 8.f, frames[host], 0.f, calib));
+    point->u = u[p]; point->v = v[p];
+    for (int k = 0; k < 8; ++k) { point->color[k] = color[8 * (size_t)p + k]; point->weights[k] = weights[8 * (size_t)p + k]; }
+    point->energyTH = energyTH[p];
+    point->idepth_min = idepth_min[p]; point->idepth_max = idepth_max[p];
+    std::vector<std::shared_ptr<ImmaturePointTemporaryResidual>> residuals;
+    std::vector<int> tgt;
+    for (int f = 0; f < n_frames; ++f)      // :28-38
+      if (f != host) {
+        std::shared_ptr<ImmaturePointTemporaryResidual> r(new ImmaturePointTemporaryResidual());
+        r->state_NewEnergy = r->state_energy = 0;
+        r->state_NewState = ResState::OUT;
+        r->state_state = ResState::IN;
+        r->target = frames[f];
+        residuals.push_back(r); tgt.push_back(f);
+      }
+    const int nres = (int)residuals.size();
+    float lastEnergy = 0, lastHdd = 0, lastbd = 0;
+    float currentIdepth = (point->idepth_max + point->idepth_min) * 0.5f;
+    for (int i = 0; i < nres; ++i) {        // :51-56
+      lastEnergy += point->linearizeResidual(1000, residuals[i], lastHdd, lastbd, currentIdepth, calib);
+      residuals[i]->state_state = residuals[i]->state_NewState;
+      residuals[i]->state_energy = residuals[i]->state_NewEnergy;
+    }
+    if (!std::isfinite(lastEnergy) || lastHdd < minIdepthH_act) continue;   // :58-64
+    float lambda = 0.1;
+    bool dead = false;
+    for (int iteration = 0; iteration < GNIts; iteration++) {               // :70-117
+      float H = lastHdd;
+      H *= 1 + lambda;
+      float step = (1.0 / H) * lastbd;
+      float newIdepth = currentIdepth - step;
+      float newHdd = 0; float newbd = 0; float newEnergy = 0;
+      for (int i = 0; i < nres; i++) newEnergy += point->linearizeResidual(1, residuals[i], newHdd, newbd, newIdepth, calib);
+      if (!std::isfinite(lastEnergy) || newHdd < minIdepthH_act) { dead = true; break; }
+      if (newEnergy < lastEnergy) {
+        currentIdepth = newIdepth; lastHdd = newHdd; lastbd = newbd; lastEnergy = newEnergy;
+        for (int i = 0; i < nres; i++) { residuals[i]->state_state = residuals[i]->state_NewState; residuals[i]->state_energy = residuals[i]->state_NewEnergy; }
+        lambda *= 0.5;
+      } else {
+        lambda *= 5;
+      }
+      if (fabsf(step) < 0.0001 * currentIdepth) break;
+    }
+    if (dead || !std::isfinite(currentIdepth)) continue;                    // :119-124
+    int numGoodRes = 0;
+    for (int i = 0; i < nres; i++) if (residuals[i]->state_state == ResState::IN) numGoodRes++;
+    if (numGoodRes < minObs) continue;                                      // :127-135
+    if (!std::isfinite(point->energyTH)) continue;
+    ok_out[p] = 1; idepth_out[p] = currentIdepth;
+    for (int i = 0; i < nres; ++i) res_state_out[(size_t)p * n_frames + tgt[i]] = (int8_t)residuals[i]->state_state;
+  }
+  return 0;
+}
+
 }  // extern "C"

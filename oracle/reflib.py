@@ -235,3 +235,22 @@ def trace_immature(dI0, cam, ims):
                                       _ptr(ims.status), _ptr(ims.lastTraceUV), _ptr(ims.lastTracePixelInterval))
     assert rc == 0
     return ims
+
+
+def activate_immature(dI0_list, cam, RtAff, ims, minObs=1, minIdepthH_act=100.0, GNIts=3, huber=9.0):
+    """System::optimizeImmaturePoint's loop around the reference's own ImmaturePoint::linearizeResidual for every point of
+    `ims`: (ok, idepth, res_state[n, n_frames]) like O.activate_immature."""
+    nf, n = len(dI0_list), len(ims.u)
+    imgs = [np.ascontiguousarray(d, np.float32) for d in dI0_list]
+    ptrs = (C.c_void_p * nf)(*[i.ctypes.data for i in imgs])
+    a = lambda x, dt: np.ascontiguousarray(x, dt)
+    ok = np.zeros(n, np.int8); idp = np.zeros(n, np.float32); st = np.zeros((n, nf), np.int8)
+    h, w = imgs[0].shape[:2]
+    rc = lib_trk().ref_activate_immature(C.c_int(nf), ptrs, C.c_int(w), C.c_int(h), C.c_float(cam.fx), C.c_float(cam.fy), C.c_float(cam.cx),
+                                         C.c_float(cam.cy), _ptr(a(RtAff, np.float32)), C.c_float(huber), C.c_float(minIdepthH_act),
+                                         C.c_int(GNIts), C.c_int(minObs), C.c_int(n), _ptr(a(ims.host_idx, np.int32)),
+                                         _ptr(a(ims.u, np.float32)), _ptr(a(ims.v, np.float32)), _ptr(a(ims.color, np.float32)),
+                                         _ptr(a(ims.weights, np.float32)), _ptr(a(ims.energyTH, np.float32)),
+                                         _ptr(a(ims.idepth_min, np.float32)), _ptr(a(ims.idepth_max, np.float32)), _ptr(ok), _ptr(idp), _ptr(st))
+    assert rc == 0
+    return ok, idp, st

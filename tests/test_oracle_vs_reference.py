@@ -209,3 +209,29 @@ def test_trace_on_bit_identical_to_reference_code(O, RT, synth):
         for k in ("status", "idepth_min", "idepth_max", "quality", "lastTraceUV", "lastTracePixelInterval"):
             assert np.array_equal(getattr(a, k), getattr(b, k), equal_nan=True), (new, k)
     assert (b.status == 0).sum() > 800 and (b.status != 0).any()
+
+
+def test_point_activation_bit_identical_to_reference_code(O, RT, synth):
+    """ImmaturePoint::linearizeResidual (+ projectPoint / derive_idepth of DirectProjection.h), compiled unmodified and driven by
+    System::optimizeImmaturePoint's loop, vs the oracle's restatement: activation flag, optimised inverse depth and the final
+    state of every residual, bit for bit — for candidates with tight intervals and for hopeless ones."""
+    import copy
+    kf = synth.render_keyframes(320, 240, 5, seed=79)
+    ims = synth.make_immature_points(kf, hosts=[0, 1, 2], points_per_host=500, seed=6)
+    dIs = [O.pyramid(im, 1)[0][0] for im in kf.images]
+    for new in (3, 4):
+        synth.trace_tables(kf, [0, 1, 2], new, ims)
+        O.trace_immature(dIs[new], ims)
+    cand = np.nonzero(np.isfinite(ims.idepth_max))[0]          # good and not-so-good traces alike
+    assert len(cand) > 800
+    sub = copy.deepcopy(ims)
+    for k in ("host_idx", "u", "v", "gradH", "color", "weights", "energyTH", "idepth_min", "idepth_max"):
+        setattr(sub, k, np.ascontiguousarray(getattr(ims, k)[cand]))
+    T = synth.activation_tables(kf)
+    for min_obs in (1, 3):
+        o = O.activate_immature(dIs, kf.cam, T, sub, minObs=min_obs)
+        r = RT.activate_immature(dIs, kf.cam, T, sub, minObs=min_obs)
+        assert np.array_equal(o[0], r[0]) and np.array_equal(o[1], r[1]) and np.array_equal(o[2], r[2])
+        assert 0.3 < r[0].mean() < 1.0 or min_obs == 3
+    assert r[0].sum() > 100
+
