@@ -254,3 +254,26 @@ def activate_immature(dI0_list, cam, RtAff, ims, minObs=1, minIdepthH_act=100.0,
                                          _ptr(a(ims.idepth_min, np.float32)), _ptr(a(ims.idepth_max, np.float32)), _ptr(ok), _ptr(idp), _ptr(st))
     assert rc == 0
     return ok, idp, st
+
+
+def available_frame():
+    return os.path.exists(os.path.join(HERE, "_ref", "libhslam_ref_frame.so"))
+
+
+def create_dir_pyrs(img, levels):
+    """Frame::CreateDirPyrs of the reference (run by its Frame constructor) on a float image:
+    (list of (h,w,3) {I,dx,dy}, list of (h,w) absSquaredGrad).  The first and the last row of dx / dy / absSquaredGrad are
+    never written by the reference (uninitialised memory): compare rows 1 .. h-2 only."""
+    L = C.CDLL(os.path.join(HERE, "_ref", "libhslam_ref_frame.so"))
+    img = np.ascontiguousarray(img, np.float32)
+    h, w = img.shape
+    n = sum((w >> l) * (h >> l) for l in range(levels))
+    dI = np.zeros(3 * n, np.float32); ab = np.zeros(n, np.float32)
+    assert L.ref_frame_create_dir_pyrs(_ptr(img), C.c_int(w), C.c_int(h), C.c_int(levels), _ptr(dI), _ptr(ab)) == 0
+    lv, la, o = [], [], 0
+    for l in range(levels):
+        wl, hl = w >> l, h >> l
+        lv.append(dI[3 * o:3 * (o + wl * hl)].reshape(hl, wl, 3)); la.append(ab[o:o + wl * hl].reshape(hl, wl))
+        o += wl * hl
+    return lv, la
+

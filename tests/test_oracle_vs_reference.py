@@ -235,3 +235,24 @@ def test_point_activation_bit_identical_to_reference_code(O, RT, synth):
         assert 0.3 < r[0].mean() < 1.0 or min_obs == 3
     assert r[0].sum() > 100
 
+
+def test_frame_pyramid_bit_identical_to_reference_code(O, synth):
+    """Frame::CreateDirPyrs (Src/Frame.cpp:104-181, compiled unmodified and run by the reference's own Frame constructor) vs
+    the oracle's pyramid, which the GPU pyramid kernel equals bit for bit: intensity of every level everywhere; dx, dy and
+    absSquaredGrad on rows 1 .. h-2 (the reference never writes the first and the last row)."""
+    from oracle import reflib
+    if not reflib.available_frame():
+        pytest.skip("oracle/_ref/libhslam_ref_frame.so not built (needs /root/reference: make -C oracle _ref)")
+    kf = synth.render_keyframes(320, 240, 1, seed=77)
+    rng = np.random.default_rng(3)
+    for img, (w, h) in ((kf.images[0], (320, 240)), ((rng.random((96, 160)) * 255).astype(np.float32), (160, 96))):
+        levels = 5 if w == 320 else 4
+        lo, ao, _ = O.pyramid(img, levels)
+        lr, ar = reflib.create_dir_pyrs(img, levels)
+        for l in range(levels):
+            hl = h >> l
+            assert np.array_equal(lo[l][..., 0], lr[l][..., 0]), l
+            assert np.array_equal(lo[l][1:hl - 1], lr[l][1:hl - 1]), l
+            assert np.array_equal(ao[l][1:hl - 1], ar[l][1:hl - 1]), l
+            assert np.abs(lr[l][1:hl - 1, :, 1]).max() > 0
+
