@@ -27,10 +27,13 @@
 #include "MapPoint.h"
 #include "OptimizationClasses.h"
 
+#include "IndexThreadReduce.h"
+
 #include "hslam_oracle.h"   // orc_window + the hslam_*_soa data-format structs
 
 using namespace FSLAM;
 
+#define REF_HAVE_ENERGYFUNCTIONAL_CPP   /* Src/EnergyFunctional.cpp is part of this library */
 #include "ref_stubs.inc"
 
 struct ref_ba {
@@ -39,11 +42,8 @@ struct ref_ba {
   std::vector<std::shared_ptr<FrameShell>> frames;
   std::vector<std::shared_ptr<MapPoint>> points;              // caller order
   std::vector<std::shared_ptr<PointFrameResidual>> residuals; // caller order
-  std::vector<Mat88> adHost, adTarget;
-  std::vector<Mat88f> adHostF, adTargetF;
-  std::vector<Mat18f> adHTdeltaF;
-  AccumulatedTopHessianSSE topA, topL;
-  AccumulatedSCHessianSSE bot;
+  // adjoint tables and the three accumulators are the EnergyFunctional's own (its constructor news the accumulators, its
+  // destructor delete[]s the tables: Src/EnergyFunctional.cpp:84-121)
   int n = 0;
 };
 
@@ -80,10 +80,9 @@ int ref_ba_set_window(ref_ba* b, const orc_window* w) {
     }
     b->ef->frames = b->frames;
     b->ef->nFrames = n;
-    b->adHost.resize(n * n); b->adTarget.resize(n * n); b->adHostF.resize(n * n); b->adTargetF.resize(n * n); b->adHTdeltaF.resize(n * n);
-    b->ef->adHost = b->adHost.data(); b->ef->adTarget = b->adTarget.data();
-    b->ef->adHostF = b->adHostF.data(); b->ef->adTargetF = b->adTargetF.data(); b->ef->adHTdeltaF = b->adHTdeltaF.data();
-    b->ef->accSSE_top_A = &b->topA; b->ef->accSSE_top_L = &b->topL; b->ef->accSSE_bot = &b->bot;
+    b->ef->adHost = new Mat88[n * n]; b->ef->adTarget = new Mat88[n * n];       // as setAdjointsF allocates them (:26-27, 75-78)
+    b->ef->adHostF = new Mat88f[n * n]; b->ef->adTargetF = new Mat88f[n * n];
+    b->ef->adHTdeltaF = new Mat18f[n * n];
   }
   for (int f = 0; f < n; ++f) {
     Frame& F = *b->frames[f]->frame;
@@ -103,12 +102,12 @@ int ref_ba_set_window(ref_ba* b, const orc_window* w) {
       P.PRE_aff_mode[0] = p[24]; P.PRE_aff_mode[1] = p[25]; P.PRE_b0_mode = p[26];
       for (int c = 0; c < 8; ++c)
         for (int r = 0; r < 8; ++r) {   // col-major tables
-          b->adHost[idx](r, c) = w->adHost[64 * (size_t)idx + r + 8 * c];
-          b->adTarget[idx](r, c) = w->adTarget[64 * (size_t)idx + r + 8 * c];
+          b->ef->adHost[idx](r, c) = w->adHost[64 * (size_t)idx + r + 8 * c];
+          b->ef->adTarget[idx](r, c) = w->adTarget[64 * (size_t)idx + r + 8 * c];
         }
-      b->adHostF[idx] = b->adHost[idx].cast<float>();     // Src/EnergyFunctional.cpp:73-74
-      b->adTargetF[idx] = b->adTarget[idx].cast<float>();
-      for (int i = 0; i < 8; ++i) b->adHTdeltaF[idx][i] = w->adHTdeltaF[8 * (size_t)idx + i];
+      b->ef->adHostF[idx] = b->ef->adHost[idx].cast<float>();     // Src/EnergyFunctional.cpp:73-74
+      b->ef->adTargetF[idx] = b->ef->adTarget[idx].cast<float>();
+      for (int i = 0; i < 8; ++i) b->ef->adHTdeltaF[idx][i] = w->adHTdeltaF[8 * (size_t)idx + i];
     }
   for (int i = 0; i < 4; ++i) { b->ef->cDeltaF[i] = w->cDeltaF[i]; b->ef->cPrior[i] = w->cPrior[i]; }
   b->ef->cPriorF = b->ef->cPrior.cast<float>();
@@ -204,19 +203,19 @@ int ref_ba_accumulate(ref_ba* b, int which, double* H, double* bvec, int* nres) 
   EnergyFunctional* ef = b->ef.get();
   const int n = b->n;
   if (which == 0) {
-    b->topA.setZero(n);
-    for (auto& f : b->frames) for (auto& p : f->frame->pointHessians) b->topA.addPoint<0>(p, ef);
-    b->topA.stitchDoubleMT(nullptr, Hm, bm, ef, false, false);
-    if (nres) *nres = b->topA.nres[0];
+    b->ef->accSSE_top_A->setZero(n);
+    for (auto& f : b->frames) for (auto& p : f->frame->pointHessians) b->ef->accSSE_top_A->addPoint<0>(p, ef);
+    b->ef->accSSE_top_A->stitchDoubleMT(nullptr, Hm, bm, ef, false, false);
+    if (nres) *nres = b->ef->accSSE_top_A->nres[0];
   } else if (which == 1) {
-    b->topL.setZero(n);
-    for (auto& f : b->frames) for (auto& p : f->frame->pointHessians) b->topL.addPoint<1>(p, ef);
-    b->topL.stitchDoubleMT(nullptr, Hm, bm, ef, true, false);
-    if (nres) *nres = b->topL.nres[0];
+    b->ef->accSSE_top_L->setZero(n);
+    for (auto& f : b->frames) for (auto& p : f->frame->pointHessians) b->ef->accSSE_top_L->addPoint<1>(p, ef);
+    b->ef->accSSE_top_L->stitchDoubleMT(nullptr, Hm, bm, ef, true, false);
+    if (nres) *nres = b->ef->accSSE_top_L->nres[0];
   } else {
-    b->bot.setZero(n);
-    for (auto& f : b->frames) for (auto& p : f->frame->pointHessians) b->bot.addPoint(p, true);
-    b->bot.stitchDoubleMT(nullptr, Hm, bm, ef, false);
+    b->ef->accSSE_bot->setZero(n);
+    for (auto& f : b->frames) for (auto& p : f->frame->pointHessians) b->ef->accSSE_bot->addPoint(p, true);
+    b->ef->accSSE_bot->stitchDoubleMT(nullptr, Hm, bm, ef, false);
   }
   const int N = 8 * n + 4;
   for (int j = 0; j < N; ++j) for (int i = 0; i < N; ++i) H[i + (size_t)N * j] = Hm(i, j);
@@ -231,19 +230,19 @@ int ref_ba_marginalize_points(ref_ba* b, const int32_t* ids, int count, float pr
                               double* Mbsc, int* nres) {
   EnergyFunctional* ef = b->ef.get();
   const int n = b->n;
-  b->bot.setZero(n);
-  b->topA.setZero(n);
+  b->ef->accSSE_bot->setZero(n);
+  b->ef->accSSE_top_A->setZero(n);
   for (int i = 0; i < count; ++i) {
     if (ids[i] < 0 || ids[i] >= (int)b->points.size()) return -1;
     std::shared_ptr<MapPoint>& p = b->points[ids[i]];
     p->efPoint->priorF *= prior_scale;
-    b->topA.addPoint<2>(p, ef);
-    b->bot.addPoint(p, false);
+    b->ef->accSSE_top_A->addPoint<2>(p, ef);
+    b->ef->accSSE_bot->addPoint(p, false);
   }
   MatXX Mm, Mscm; VecX Mbm, Mbscm;
-  b->topA.stitchDouble(Mm, Mbm, ef, false, false);
-  b->bot.stitchDouble(Mscm, Mbscm, ef);
-  if (nres) *nres = b->topA.nres[0];
+  b->ef->accSSE_top_A->stitchDouble(Mm, Mbm, ef, false, false);
+  b->ef->accSSE_bot->stitchDouble(Mscm, Mbscm, ef);
+  if (nres) *nres = b->ef->accSSE_top_A->nres[0];
   const int N = 8 * n + 4;
   for (int j = 0; j < N; ++j) for (int i = 0; i < N; ++i) { M[i + (size_t)N * j] = Mm(i, j); Msc[i + (size_t)N * j] = Mscm(i, j); }
   for (int i = 0; i < N; ++i) { Mb[i] = Mbm[i]; Mbsc[i] = Mbscm[i]; }
@@ -266,6 +265,69 @@ int ref_ba_point_results(ref_ba* b, double* HdiF, double* bdSumF, double* idepth
       if (Hcd_accAF) Hcd_accAF[4 * i + k] = e.Hcd_accAF[k];
       if (Hcd_accLF) Hcd_accLF[4 * i + k] = e.Hcd_accLF[k];
     }
+  }
+  return 0;
+}
+
+// EnergyFunctional::resubstituteF_MT / resubstituteFPt (Src/EnergyFunctional.cpp:222-274), single-thread branch: the
+// reference's own member function on the driver's window.  x: (8n+4) solution; step_out: P floats (efPoint->step).
+int ref_ba_resubstitute(ref_ba* b, const double* x, float* step_out) {
+  const int N = 8 * b->n + 4;
+  VecX xv(N);
+  for (int i = 0; i < N; ++i) xv[i] = x[i];
+  b->ef->resubstituteF_MT(xv, b->calib, false);
+  for (size_t i = 0; i < b->points.size(); ++i) step_out[i] = b->points[i]->efPoint->step;
+  return 0;
+}
+
+// EnergyFunctional::calcLEnergyF_MT / calcLEnergyPt (Src/EnergyFunctional.cpp:289-364) with the reference's own
+// IndexThreadReduce (one worker thread, chunks of 50 points).
+int ref_ba_calc_l_energy(ref_ba* b, double* E_out) {
+  static IndexThreadReduce<Vec10> red;
+  b->ef->red = &red;
+  EFDeltaValid = EFAdjointsValid = EFIndicesValid = true;   // the tables were set by ref_ba_set_window / ref_ba_set_topology
+  *E_out = b->ef->calcLEnergyF_MT();
+  b->ef->red = nullptr;
+  return 0;
+}
+
+// EnergyFunctional::setAdjointsF + setDeltaF (Src/EnergyFunctional.cpp:22-82, 128-152) from the frames' poses and states:
+// w2c_evalPT (12: R row-major, t), state / state_zero (10) per frame, exposures.  Out: adHost / adTarget (n*n*64, column-
+// major 8x8, index host + target*n) and adHTdeltaF (n*n*8).
+int ref_ef_adjoints_deltas(int n, const double* w2c_evalPT, const double* state, const double* state_zero, const float* ab_exposure,
+                           double* adHost_out, double* adTarget_out, float* adHTdeltaF_out) {
+  Mat33 K = Mat33::Identity();
+  K(0, 0) = 300; K(1, 1) = 300; K(0, 2) = 160; K(1, 2) = 120;
+  int dirPyr = 1;
+  std::shared_ptr<CalibData> calib(new CalibData(320, 240, K, 0.f, nullptr, nullptr, dirPyr, 1, 1.2f));
+  std::shared_ptr<ImageData> img(new ImageData(1, 1));
+  img->timestamp = 0; img->ExposureL = 1.f; img->ExposureR = 1.f;
+  EnergyFunctional ef;
+  for (int f = 0; f < n; ++f) {
+    std::shared_ptr<FrameShell> fs(new FrameShell(img, nullptr, calib, nullptr, false));
+    fs->frame->idx = f;
+    fs->ab_exposure = ab_exposure[f];
+    fs->frame->efFrame.reset(new FrameOptimizationData(f, ab_exposure[f]));
+    FrameOptimizationData& e = *fs->frame->efFrame;
+    Eigen::Matrix<double, 3, 3> R; Eigen::Matrix<double, 3, 1> t;
+    for (int i = 0; i < 3; ++i) { for (int j = 0; j < 3; ++j) R(i, j) = w2c_evalPT[12 * f + 3 * i + j]; t[i] = w2c_evalPT[12 * f + 9 + i]; }
+    e.worldToCam_evalPT = SE3(R, t);
+    Vec10 s, s0;
+    for (int i = 0; i < 10; ++i) { s[i] = state[10 * f + i]; s0[i] = state_zero[10 * f + i]; }
+    e.state_zero = s0;   // (setStateZero also builds the nullspaces, which the path does not use)
+    e.setState(s);
+    ef.frames.push_back(fs);
+  }
+  ef.nFrames = n;
+  ef.setAdjointsF(calib);
+  ef.setDeltaF(calib);
+  for (int idx = 0; idx < n * n; ++idx) {
+    for (int c = 0; c < 8; ++c)
+      for (int r = 0; r < 8; ++r) {
+        adHost_out[64 * (size_t)idx + r + 8 * c] = ef.adHost[idx](r, c);
+        adTarget_out[64 * (size_t)idx + r + 8 * c] = ef.adTarget[idx](r, c);
+      }
+    for (int i = 0; i < 8; ++i) adHTdeltaF_out[8 * (size_t)idx + i] = ef.adHTdeltaF[idx][i];
   }
   return 0;
 }

@@ -110,6 +110,19 @@ class RefBA:
                                                 _ptr(Ms), _ptr(Mbs), C.byref(nres)) == 0
         return M.reshape(N, N).T.copy(), Mb, Ms.reshape(N, N).T.copy(), Mbs, nres.value
 
+    def resubstitute(self, x):
+        """EnergyFunctional::resubstituteF_MT (single-thread branch) of the reference: per-point steps."""
+        x = np.ascontiguousarray(x, np.float64)
+        step = np.zeros(self.P, np.float32)
+        assert self.L.ref_ba_resubstitute(self.h, _ptr(x), _ptr(step)) == 0
+        return step
+
+    def calc_l_energy(self):
+        """EnergyFunctional::calcLEnergyF_MT of the reference (its own IndexThreadReduce, one worker)."""
+        e = C.c_double(0)
+        assert self.L.ref_ba_calc_l_energy(self.h, C.byref(e)) == 0
+        return e.value
+
     def point_results(self):
         P = self.P
         names = ["HdiF", "bdSumF", "idepth_hessian", "Hdd_accAF", "bd_accAF", "Hcd_accAF", "Hdd_accLF", "bd_accLF", "Hcd_accLF"]
@@ -141,6 +154,17 @@ def precalc_set(cam, T_eval, state, state_zero, exposure):
 # ------------------------------------------------------------------ Stage T + tracing (oracle/_ref/libhslam_ref_trk.so)
 LIB_TRK = os.path.join(HERE, "_ref", "libhslam_ref_trk.so")
 _lib_trk = None
+
+
+def adjoints_deltas(T_eval, state, state_zero, exposure):
+    """EnergyFunctional::setAdjointsF + setDeltaF of the reference: (adHost, adTarget, adHTdeltaF) flat like O.prepare_window."""
+    n = len(T_eval)
+    adH = np.zeros(n * n * 64); adT = np.zeros(n * n * 64); adHTd = np.zeros(n * n * 8, np.float32)
+    a = lambda x, dt: np.ascontiguousarray(x, dt)
+    rc = lib().ref_ef_adjoints_deltas(C.c_int(n), _ptr(a(T_eval, np.float64)), _ptr(a(state, np.float64)), _ptr(a(state_zero, np.float64)),
+                                      _ptr(a(exposure, np.float32)), _ptr(adH), _ptr(adT), _ptr(adHTd))
+    assert rc == 0
+    return adH, adT, adHTd
 
 
 def available_trk():

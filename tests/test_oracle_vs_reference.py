@@ -1,5 +1,5 @@
 """PINS THE ORACLE TO THE REFERENCE'S OWN CODE.  oracle/_ref/libhslam_ref.so is built from the UNMODIFIED reference sources
-(/root/reference/Src/OptimizationClasses.cpp, AccumulatedTopHessian.cpp, AccumulatedSCHessian.cpp, Settings.cpp and their
+(/root/reference/Src/OptimizationClasses.cpp, AccumulatedTopHessian.cpp, AccumulatedSCHessian.cpp, EnergyFunctional.cpp, Settings.cpp and their
 headers, incl. Include/MatrixAccumulators.h and DirectProjection.h) against the library stand-ins of oracle/ref_shim/
 (recipe: oracle/Makefile, target _ref; the .so travels with the repository, the reference tree does not).  The same
 window goes through that library and through the oracle's float restatement:
@@ -255,4 +255,43 @@ def test_frame_pyramid_bit_identical_to_reference_code(O, synth):
             assert np.array_equal(lo[l][1:hl - 1], lr[l][1:hl - 1]), l
             assert np.array_equal(ao[l][1:hl - 1], ar[l][1:hl - 1]), l
             assert np.abs(lr[l][1:hl - 1, :, 1]).max() > 0
+
+
+def test_adjoints_and_deltas_match_reference_code(O, RL, synth):
+    """EnergyFunctional::setAdjointsF + setDeltaF (Src/EnergyFunctional.cpp:22-82, 128-152, compiled unmodified) vs the table
+    generator the oracle / the host mirror use: adTarget bit-identical, adHost to one fp64 ulp (the order inside SE3::Adj), the
+    float adHTdeltaF to float round-off."""
+    kf = synth.render_keyframes(160, 120, 5, seed=9)
+    win, _ = synth.make_window(points_per_frame=10, seed=10, keyframes=kf)
+    _, adH, adT, adHTd = O.prepare_window(win.cam, win.T_w2c_eval, win.state, win.state_zero, win.ab_exposure)
+    rH, rT, rD = RL.adjoints_deltas(win.T_w2c_eval, win.state, win.state_zero, win.ab_exposure)
+    assert np.array_equal(adT, rT)
+    assert np.abs(adH - rH).max() <= 4e-16 * max(1.0, np.abs(rH).max()) and np.abs(rH).max() > 0.5
+    assert np.abs(adHTd - rD).max() <= 1e-6 * np.abs(rD).max() and np.abs(rD).max() > 1e-3
+
+
+def test_resubstitute_and_lenergy_match_reference_code(O, RL, synth):
+    """EnergyFunctional::resubstituteF_MT / resubstituteFPt and calcLEnergyF_MT / calcLEnergyPt — the reference's own member
+    functions (with its own IndexThreadReduce, one worker) after linearize / applyRes / fixLinearizationF / accumulate A, L, SC —
+    vs the oracle: point steps to float round-off (the 8-term dot products xAd * JpJdF associate as the build's Eigen does),
+    the linearised energy to 1e-8."""
+    kf = synth.render_keyframes(320, 240, 5, seed=12)
+    win, is_lin = synth.make_window(points_per_frame=150, seed=40, keyframes=kf, frac_linearized=0.3)
+    dIs = [O.pyramid(im, 1)[0][0] for im in win.images]
+    f, r = O.BAOracle(win, dIs, prec="f"), RL.RefBA(win, dIs)
+    ids = np.nonzero(is_lin)[0].astype(np.int32)
+    idp = (win.idepth * np.float32(1.002)).astype(np.float32)
+    for x in (f, r):
+        x.linearize(False); x.apply_res(); x.fix_linearization(ids)
+        x.update_points(idepth=idp, deltaF=(idp - win.idepth_zero).astype(np.float32))
+        x.linearize(False); x.apply_res()
+        for k in (0, 1, 2):
+            x.accumulate(k)
+    xs = np.random.default_rng(1).normal(0, 1e-3, 8 * win.n + 4)
+    sf, sr = f.resubstitute(xs), r.resubstitute(xs)
+    assert np.abs(sr).max() > 1e-3 and (sr == 0).sum() < 0.2 * len(sr)
+    assert np.abs(sf - sr).max() <= 1e-6 * np.abs(sr).max()
+    assert (sf == sr).mean() > 0.25                      # (half of the points even bit for bit)
+    ef, er = f.calc_l_energy(), r.calc_l_energy()
+    assert er > 0 and abs(ef - er) <= 1e-8 * abs(er)
 
