@@ -197,25 +197,20 @@ int ref_ba_fix_linearization(ref_ba* b, const int32_t* ids, int count) {
   return 0;
 }
 
-// EnergyFunctional::accumulate{A,L,SC}F_MT, single-thread branch (EnergyFunctional.cpp:166-175,189-196,212-219)
+// EnergyFunctional::accumulate{A,L,SC}F_MT (Src/EnergyFunctional.cpp:155-220): the reference's own member functions,
+// single-thread branch (MT = false)
 int ref_ba_accumulate(ref_ba* b, int which, double* H, double* bvec, int* nres) {
   MatXX Hm; VecX bm;
   EnergyFunctional* ef = b->ef.get();
   const int n = b->n;
   if (which == 0) {
-    b->ef->accSSE_top_A->setZero(n);
-    for (auto& f : b->frames) for (auto& p : f->frame->pointHessians) b->ef->accSSE_top_A->addPoint<0>(p, ef);
-    b->ef->accSSE_top_A->stitchDoubleMT(nullptr, Hm, bm, ef, false, false);
-    if (nres) *nres = b->ef->accSSE_top_A->nres[0];
+    ef->accumulateAF_MT(Hm, bm, false);
+    if (nres) *nres = ef->resInA;
   } else if (which == 1) {
-    b->ef->accSSE_top_L->setZero(n);
-    for (auto& f : b->frames) for (auto& p : f->frame->pointHessians) b->ef->accSSE_top_L->addPoint<1>(p, ef);
-    b->ef->accSSE_top_L->stitchDoubleMT(nullptr, Hm, bm, ef, true, false);
-    if (nres) *nres = b->ef->accSSE_top_L->nres[0];
+    ef->accumulateLF_MT(Hm, bm, false);
+    if (nres) *nres = ef->resInL;
   } else {
-    b->ef->accSSE_bot->setZero(n);
-    for (auto& f : b->frames) for (auto& p : f->frame->pointHessians) b->ef->accSSE_bot->addPoint(p, true);
-    b->ef->accSSE_bot->stitchDoubleMT(nullptr, Hm, bm, ef, false);
+    ef->accumulateSCF_MT(Hm, bm, false);
   }
   const int N = 8 * n + 4;
   for (int j = 0; j < N; ++j) for (int i = 0; i < N; ++i) H[i + (size_t)N * j] = Hm(i, j);
