@@ -12,11 +12,11 @@
  * therefore compiles the reference's own hot-path translation units UNMODIFIED,
  * from where they lie under /root/reference (OptimizationClasses.cpp,
  * AccumulatedTopHessian.cpp, AccumulatedSCHessian.cpp, EnergyFunctional.cpp,
- * CoarseTracker.cpp, ImmaturePoint.cpp, Frame.cpp, Settings.cpp), against the minimal library stand-ins of
+ * FullSystemOptimize.cpp, CoarseTracker.cpp, ImmaturePoint.cpp, Frame.cpp, Settings.cpp), against the minimal library stand-ins of
  * oracle/ref_shim/ (fixed-size Eigen subset with Eigen 3.3's evaluation order,
  * Sophus SE3, boost->std, type stubs) into oracle/_ref/libhslam_ref*.so;
  * tests/test_oracle_vs_reference.py drives both on the same inputs: linearize /
- * applyRes, the frame pyramid, the tracker's LM path, makeCoarseDepthL0, traceOn and the point
+ * applyRes, System::linearizeAll with setNewFrameEnergyTH, the frame pyramid, the tracker's LM path, makeCoarseDepthL0, traceOn and the point
  * activation (linearizeResidual) agree BIT FOR BIT with the float restatement,
  * the stitched systems (incl. the marginalisation pass) to 1e-9..1e-12.  The
  * analytic known answers of tests/test_oracle_*.py (finite differences, dense

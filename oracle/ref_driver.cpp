@@ -4,21 +4,37 @@
 //     Src/OptimizationClasses.cpp      FrameFramePrecalc::set, PointFrameResidual::linearize / applyRes / fixLinearizationF
 //     Src/AccumulatedTopHessian.cpp    AccumulatedTopHessianSSE::addPoint<mode>, stitchDouble, stitchDoubleInternal
 //     Src/AccumulatedSCHessian.cpp     AccumulatedSCHessianSSE::addPoint, stitchDouble, stitchDoubleInternal
+//     Src/EnergyFunctional.cpp         EnergyFunctional: constructor, setAdjointsF, setDeltaF, accumulate{A,L,SC}F_MT,
+//                                      resubstituteF_MT / resubstituteFPt, calcLEnergyF_MT / calcLEnergyPt
+//     Src/FullSystemOptimize.cpp       System::linearizeAll / linearizeAll_Reductor / setNewFrameEnergyTH
 //     Src/Settings.cpp                 the setting_* globals
 // together with their own headers (Include/GlobalTypes.h, MatrixAccumulators.h, OptimizationClasses.h, DirectProjection.h,
-// CalibData.h, Frame.h, MapPoint.h, EnergyFunctional.h, Accumulated*Hessian.h, IndexThreadReduce.h, ...) against the small
-// stand-ins of oracle/ref_shim/ for the libraries this image lacks (Eigen, Sophus-on-Eigen, Boost.Thread, the OpenCV /
-// DBoW3 type names), into oracle/_ref/libhslam_ref.so.  This file is OUR code: it builds the reference's object graph
-// (FrameShell / Frame / FrameOptimizationData / MapPoint / PointFrameResidual / EnergyFunctional / CalibData) from the same
-// flat window description the oracle and the CUDA library take, calls the reference's member functions in the order of
-// EnergyFunctional::accumulate{A,L,SC}F_MT's single-thread branch (Src/EnergyFunctional.cpp:155-220: that file itself
-// needs Eigen's LDLT / SVD and is not compiled) and of System::linearizeAll_Reductor / applyRes_Reductor (Src/
-// FullSystemOptimize.cpp:19-59), and hands the results back as flat arrays.  It also DEFINES the few out-of-line symbols
-// whose own translation units are not part of the path (Frame / ImmaturePoint / EnergyFunctional constructors, static
-// members): trivial bodies, they only have to satisfy the linker.
+// CalibData.h, Frame.h, MapPoint.h, EnergyFunctional.h, Accumulated*Hessian.h, IndexThreadReduce.h, System.h, ...) against
+// the small stand-ins of oracle/ref_shim/ for the libraries this image lacks (Eigen, Sophus-on-Eigen, Boost.Thread, the
+// OpenCV / DBoW3 type names), into oracle/_ref/libhslam_ref.so.  This file is OUR code: it builds the reference's object
+// graph (FrameShell / Frame / FrameOptimizationData / MapPoint / PointFrameResidual / EnergyFunctional / CalibData) from the
+// same flat window description the oracle and the CUDA library take, calls the reference's member functions and hands the
+// results back as flat arrays.  It also DEFINES the few out-of-line symbols whose own translation units are not part of
+// the path (Frame / ImmaturePoint constructors, static members, System::setPrecalcValues): trivial bodies, they only have
+// to satisfy the linker.
 //
 // tests/test_oracle_vs_reference.py feeds one window to this library and to the oracle's float restatement and compares
 // every output: that is what pins the oracle to the reference's own code.
+#include <algorithm>
+#include <cmath>
+#include <cstdlib>
+#include <cstring>
+#include <deque>
+#include <iostream>
+#include <map>
+#include <memory>
+#include <string>
+#include <vector>
+// System keeps its CalibData in a private member; the driver sets up a bare System object by hand (its constructor starts the
+// whole SLAM system), so the reference headers are read with `private` opened up — the standard headers above are not
+#define private public
+#include "System.h"
+#undef private
 #include "AccumulatedSCHessian.h"
 #include "AccumulatedTopHessian.h"
 #include "CalibData.h"
@@ -46,6 +62,10 @@ struct ref_ba {
   // destructor delete[]s the tables: Src/EnergyFunctional.cpp:84-121)
   int n = 0;
 };
+
+namespace FSLAM {
+void System::setPrecalcValues() { std::abort(); }   // Src/System.cpp (not compiled); only System::optimize calls it
+}  // namespace FSLAM
 
 extern "C" {
 
@@ -325,6 +345,31 @@ int ref_ef_adjoints_deltas(int n, const double* w2c_evalPT, const double* state,
     for (int i = 0; i < 8; ++i) adHTdeltaF_out[8 * (size_t)idx + i] = ef.adHTdeltaF[idx][i];
   }
   return 0;
+}
+
+// System::linearizeAll(false) (Src/FullSystemOptimize.cpp:103-165): linearizeAll_Reductor over activeResiduals (:19-52) and
+// setNewFrameEnergyTH (:60-101), the reference's own member functions, single-thread branch.  The System object is a
+// zero-filled block with the five members the functions touch set by hand (never constructed, never destroyed: the
+// constructor would start the whole SLAM system).  activeResiduals in the order System::optimize builds it (:371-391):
+// frames -> points -> the point's residuals, the non-linearised ones.  Out: the summed energy and the new
+// frameEnergyTH of the newest frame (frameHessians.back()).
+int ref_ba_system_linearize_all(ref_ba* b, double* energy_out, float* frameEnergyTH_out) {
+  System* sys = static_cast<System*>(std::calloc(1, sizeof(System)));
+  new (&sys->frameHessians) std::vector<std::shared_ptr<FrameShell>>(b->frames);
+  new (&sys->activeResiduals) std::vector<std::shared_ptr<PointFrameResidual>>();
+  new (&sys->allResVec) std::vector<float>();
+  new (&sys->Calib) std::shared_ptr<CalibData>(b->calib);
+  new (&sys->ef) std::shared_ptr<EnergyFunctional>(b->ef);
+  for (auto& fh : b->frames)
+    for (auto& ph : fh->frame->pointHessians)
+      for (auto& r : ph->residuals)
+        if (!r->isLinearized) sys->activeResiduals.push_back(r);
+  multiThreading = false;
+  const Vec3 res = sys->linearizeAll(false);
+  *energy_out = res[0];
+  *frameEnergyTH_out = b->frames.back()->frame->frameEnergyTH;
+  sys->frameHessians.clear(); sys->activeResiduals.clear(); sys->Calib.reset(); sys->ef.reset();
+  return 0;   // (the block itself is leaked on purpose: ~System must not run)
 }
 
 // RawResidualJacobian in member order (Include/OptimizationClasses.h:48-77): resF[8], Jpdxi[2][6], Jpdc[2][4], Jpdd[2],

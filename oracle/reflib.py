@@ -110,6 +110,13 @@ class RefBA:
                                                 _ptr(Ms), _ptr(Mbs), C.byref(nres)) == 0
         return M.reshape(N, N).T.copy(), Mb, Ms.reshape(N, N).T.copy(), Mbs, nres.value
 
+    def system_linearize_all(self):
+        """System::linearizeAll(false) of the reference (linearizeAll_Reductor + setNewFrameEnergyTH): (energy, new
+        frameEnergyTH of the newest frame).  Per-residual results: residual_results() / linearize() fields as usual."""
+        e = C.c_double(0); th = C.c_float(0)
+        assert self.L.ref_ba_system_linearize_all(self.h, C.byref(e), C.byref(th)) == 0
+        return e.value, np.float32(th.value)
+
     def resubstitute(self, x):
         """EnergyFunctional::resubstituteF_MT (single-thread branch) of the reference: per-point steps."""
         x = np.ascontiguousarray(x, np.float64)

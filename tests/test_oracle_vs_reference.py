@@ -295,3 +295,32 @@ def test_resubstitute_and_lenergy_match_reference_code(O, RL, synth):
     ef, er = f.calc_l_energy(), r.calc_l_energy()
     assert er > 0 and abs(ef - er) <= 1e-8 * abs(er)
 
+
+def test_system_linearize_all_and_new_frame_energy_th_bit_identical(O, RL, synth):
+    """System::linearizeAll(false) — linearizeAll_Reductor over activeResiduals and System::setNewFrameEnergyTH
+    (Src/FullSystemOptimize.cpp:19-165, compiled unmodified; the bare System object is set up by the driver) — over three
+    GN-style iterations with the threshold fed back through Frame::frameEnergyTH, some residuals fixed after the first: the
+    summed energy and the new threshold (std::nth_element at 70 %, the float arithmetic of :86-91) equal the oracle's BIT FOR
+    BIT, and so do the residual states that the thresholds decide."""
+    kf = synth.render_keyframes(320, 240, 5, seed=12)
+    win, is_lin = synth.make_window(points_per_frame=150, seed=40, keyframes=kf, frac_linearized=0.3)
+    dIs = [O.pyramid(im, 1)[0][0] for im in win.images]
+    f, r = O.BAOracle(win, dIs, prec="f"), RL.RefBA(win, dIs)
+    ids = np.nonzero(is_lin)[0].astype(np.int32)
+    ths = []
+    for it in range(3):
+        lf = f.linearize(False)
+        thf = f.new_frame_energy_th(win.n - 1)
+        er, thr = r.system_linearize_all()
+        assert lf["energy"] == er and er > 0
+        assert np.float32(thf) == thr
+        ths.append(float(thr))
+        f.apply_res(); r.apply_res()
+        if it == 0:
+            f.fix_linearization(ids); r.fix_linearization(ids)
+        idp = (win.idepth * np.float32(1.0 + 0.002 * (it + 1))).astype(np.float32)
+        for x in (f, r):
+            x.update_points(idepth=idp, deltaF=(idp - win.idepth_zero).astype(np.float32))
+    assert len(set(ths)) == 3 and all(t != win.frameEnergyTH[win.n - 1] for t in ths)
+    assert np.array_equal(f.residual_results()["state_state"], r.residual_results()["state_state"])
+
