@@ -12,7 +12,7 @@
  * therefore compiles the reference's own hot-path translation units UNMODIFIED,
  * from where they lie under /root/reference (OptimizationClasses.cpp,
  * AccumulatedTopHessian.cpp, AccumulatedSCHessian.cpp, EnergyFunctional.cpp,
- * FullSystemOptimize.cpp, CoarseTracker.cpp, ImmaturePoint.cpp, Frame.cpp, Settings.cpp), against the minimal library stand-ins of
+ * FullSystemOptimize.cpp, FullSystemOptPoint.cpp, CoarseTracker.cpp, ImmaturePoint.cpp, Frame.cpp, Settings.cpp), against the minimal library stand-ins of
  * oracle/ref_shim/ (fixed-size Eigen subset with Eigen 3.3's evaluation order,
  * Sophus SE3, boost->std, type stubs) into oracle/_ref/libhslam_ref*.so;
  * tests/test_oracle_vs_reference.py drives both on the same inputs: linearize /

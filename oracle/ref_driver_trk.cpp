@@ -1,11 +1,22 @@
 // ref_driver_trk.cpp — C interface around the UNMODIFIED reference translation units of Stage T and of the immature-point
-// tracing: Src/CoarseTracker.cpp (makeK, calcRes, calcGSSSE + Accumulator9, trackNewestCoarse) and Src/ImmaturePoint.cpp
-// (the constructor, traceOn), compiled from /root/reference against the stand-ins of oracle/ref_shim/ into
+// tracing / activation: Src/CoarseTracker.cpp (makeK, calcRes, calcGSSSE + Accumulator9, trackNewestCoarse), Src/ImmaturePoint.cpp
+// (the constructor, traceOn, linearizeResidual) and Src/FullSystemOptPoint.cpp (System::optimizeImmaturePoint), compiled from /root/reference against the stand-ins of oracle/ref_shim/ into
 // oracle/_ref/libhslam_ref_trk.so (oracle/Makefile).  TEST INFRASTRUCTURE, our code: it builds the objects those member
 // functions work on from the same flat inputs the oracle takes and returns flat outputs; tests/test_oracle_vs_reference.py
 // compares them with the oracle's float restatement.
-#define private public      // our driver fills the tracker's reference clouds and calls calcRes / calcGSSSE directly
-#include "CoarseTracker.h"
+#include <algorithm>
+#include <cmath>
+#include <cstdlib>
+#include <cstring>
+#include <deque>
+#include <iostream>
+#include <map>
+#include <memory>
+#include <string>
+#include <vector>
+#define private public      // our driver fills the tracker's reference clouds, calls calcRes / calcGSSSE directly and sets up
+#include "CoarseTracker.h"  // a bare System object (its CalibData member is private) for System::optimizeImmaturePoint
+#include "System.h"
 #undef private
 #include "CalibData.h"
 #include "EnergyFunctional.h"
@@ -207,10 +218,10 @@ int ref_trace_immature(const float* dI0, int w, int h, float fx, float fy, float
   return 0;
 }
 
-// System::optimizeImmaturePoint (Src/FullSystemOptPoint.cpp:24-175) is a System member (not compilable here); its loop is
-// followed line by line below with the REFERENCE's ImmaturePoint::linearizeResidual (Src/ImmaturePoint.cpp:389-451, with
-// projectPoint / derive_idepth of Include/DirectProjection.h) doing every residual evaluation.  Same argument list as
-// orc_activate_immature.
+// System::optimizeImmaturePoint (Src/FullSystemOptPoint.cpp:24-175, compiled unmodified) with ImmaturePoint::linearizeResidual
+// (Src/ImmaturePoint.cpp:389-451; projectPoint / derive_idepth of Include/DirectProjection.h) for every candidate.  The
+// System object is a zero-filled block with frameHessians and Calib set by hand (never constructed, never destroyed: the
+// constructor would start the whole SLAM system).  Same argument list as orc_activate_immature.
 int ref_activate_immature(int n_frames, const float* const* dI0, int w, int h, float fx, float fy, float cx, float cy, const float* RtAff,
                           float huber, float minIdepthH_act, int GNIts, int minObs, int n, const int32_t* host_idx, const float* u,
                           const float* v, const float* color, const float* weights, const float* energyTH, const float* idepth_min,
@@ -220,6 +231,8 @@ int ref_activate_immature(int n_frames, const float* const* dI0, int w, int h, f
   int dirPyr = 1;
   std::shared_ptr<CalibData> calib(new CalibData(w, h, K, 0.f, nullptr, nullptr, dirPyr, 1, 1.2f));
   setting_huberTH = huber;
+  setting_minIdepthH_act = minIdepthH_act;
+  setting_GNItsOnPointActivation = GNIts;
   std::vector<std::shared_ptr<FrameShell>> frames;
   for (int f = 0; f < n_frames; ++f) {
     frames.push_back(make_shell(calib, 1.f, 1));
@@ -235,6 +248,11 @@ int ref_activate_immature(int n_frames, const float* const* dI0, int w, int h, f
       pc.PRE_aff_mode[0] = T[12]; pc.PRE_aff_mode[1] = T[13];
     }
   }
+  System* sys = static_cast<System*>(std::calloc(1, sizeof(System)));
+  new (&sys->frameHessians) std::vector<std::shared_ptr<FrameShell>>(frames);
+  new (&sys->Calib) std::shared_ptr<CalibData>(calib);
+  std::vector<std::shared_ptr<ImmaturePointTemporaryResidual>> residuals;   // as System::activatePointsMT_Reductor provides them
+  for (int f = 0; f < n_frames; ++f) residuals.push_back(std::shared_ptr<ImmaturePointTemporaryResidual>(new ImmaturePointTemporaryResidual()));
   for (int p = 0; p < n; ++p) {
     const int host = host_idx[p];
     if (host < 0 || host >= n_frames) return -1;
@@ -245,54 +263,19 @@ int ref_activate_immature(int n_frames, const float* const* dI0, int w, int h, f
     for (int k = 0; k < 8; ++k) { point->color[k] = color[8 * (size_t)p + k]; point->weights[k] = weights[8 * (size_t)p + k]; }
     point->energyTH = energyTH[p];
     point->idepth_min = idepth_min[p]; point->idepth_max = idepth_max[p];
-    std::vector<std::shared_ptr<ImmaturePointTemporaryResidual>> residuals;
-    std::vector<int> tgt;
-    for (int f = 0; f < n_frames; ++f)      // :28-38
-      if (f != host) {
-        std::shared_ptr<ImmaturePointTemporaryResidual> r(new ImmaturePointTemporaryResidual());
-        r->state_NewEnergy = r->state_energy = 0;
-        r->state_NewState = ResState::OUT;
-        r->state_state = ResState::IN;
-        r->target = frames[f];
-        residuals.push_back(r); tgt.push_back(f);
-      }
-    const int nres = (int)residuals.size();
-    float lastEnergy = 0, lastHdd = 0, lastbd = 0;
-    float currentIdepth = (point->idepth_max + point->idepth_min) * 0.5f;
-    for (int i = 0; i < nres; ++i) {        // :51-56
-      lastEnergy += point->linearizeResidual(1000, residuals[i], lastHdd, lastbd, currentIdepth, calib);
-      residuals[i]->state_state = residuals[i]->state_NewState;
-      residuals[i]->state_energy = residuals[i]->state_NewEnergy;
-    }
-    if (!std::isfinite(lastEnergy) || lastHdd < minIdepthH_act) continue;   // :58-64
-    float lambda = 0.1;
-    bool dead = false;
-    for (int iteration = 0; iteration < GNIts; iteration++) {               // :70-117
-      float H = lastHdd;
-      H *= 1 + lambda;
-      float step = (1.0 / H) * lastbd;
-      float newIdepth = currentIdepth - step;
-      float newHdd = 0; float newbd = 0; float newEnergy = 0;
-      for (int i = 0; i < nres; i++) newEnergy += point->linearizeResidual(1, residuals[i], newHdd, newbd, newIdepth, calib);
-      if (!std::isfinite(lastEnergy) || newHdd < minIdepthH_act) { dead = true; break; }
-      if (newEnergy < lastEnergy) {
-        currentIdepth = newIdepth; lastHdd = newHdd; lastbd = newbd; lastEnergy = newEnergy;
-        for (int i = 0; i < nres; i++) { residuals[i]->state_state = residuals[i]->state_NewState; residuals[i]->state_energy = residuals[i]->state_NewEnergy; }
-        lambda *= 0.5;
-      } else {
-        lambda *= 5;
-      }
-      if (fabsf(step) < 0.0001 * currentIdepth) break;
-    }
-    if (dead || !std::isfinite(currentIdepth)) continue;                    // :119-124
-    int numGoodRes = 0;
-    for (int i = 0; i < nres; i++) if (residuals[i]->state_state == ResState::IN) numGoodRes++;
-    if (numGoodRes < minObs) continue;                                      // :127-135
-    if (!std::isfinite(point->energyTH)) continue;
-    ok_out[p] = 1; idepth_out[p] = currentIdepth;
-    for (int i = 0; i < nres; ++i) res_state_out[(size_t)p * n_frames + tgt[i]] = (int8_t)residuals[i]->state_state;
+    std::shared_ptr<MapPoint> mp = sys->optimizeImmaturePoint(point, minObs, residuals);
+    if (!mp) continue;
+    ok_out[p] = 1; idepth_out[p] = mp->idepth;
+    // the final states of the temporary residuals, in frame order without the host (:28-38)
+    int k = 0;
+    for (int f = 0; f < n_frames; ++f)
+      if (f != host) res_state_out[(size_t)p * n_frames + f] = (int8_t)residuals[k++]->state_state;
+    for (auto& r : mp->residuals) r->Clear();
+    mp->Clear();
   }
-  return 0;
+  for (auto& r : residuals) r->target.reset();
+  sys->frameHessians.clear(); sys->Calib.reset();
+  return 0;   // (the block itself is leaked on purpose: ~System must not run)
 }
 
 }  // extern "C"

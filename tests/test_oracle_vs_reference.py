@@ -212,8 +212,8 @@ def test_trace_on_bit_identical_to_reference_code(O, RT, synth):
 
 
 def test_point_activation_bit_identical_to_reference_code(O, RT, synth):
-    """ImmaturePoint::linearizeResidual (+ projectPoint / derive_idepth of DirectProjection.h), compiled unmodified and driven by
-    System::optimizeImmaturePoint's loop, vs the oracle's restatement: activation flag, optimised inverse depth and the final
+    """System::optimizeImmaturePoint (Src/FullSystemOptPoint.cpp) with ImmaturePoint::linearizeResidual (+ projectPoint /
+    derive_idepth of DirectProjection.h), both compiled unmodified, vs the oracle's restatement: activation flag, optimised inverse depth and the final
     state of every residual, bit for bit — for candidates with tight intervals and for hopeless ones."""
     import copy
     kf = synth.render_keyframes(320, 240, 5, seed=79)
